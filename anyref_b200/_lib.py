@@ -1,0 +1,82 @@
+"""ctypes binding of libanyref_sam.so (C ABI declared in include/anyref_sam.h).
+
+There is deliberately no fallback: if the library is missing or a call fails, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libanyref_sam.so"
+
+_lib = None
+
+c_void_p, c_int, c_float, c_char_p = C.c_void_p, C.c_int, C.c_float, C.c_char_p
+
+# name -> argtypes (restype is int unless listed in _RESTYPES)
+_PROTOS = {
+    "sam_last_error": [],
+    "sam_abi_version": [],
+    "sam_gemm": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p,
+                 c_int, c_void_p, c_int, c_int, c_void_p],
+    "sam_umma_probe": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                       c_void_p],
+}
+_RESTYPES = {"sam_last_error": c_char_p}
+
+
+def exported_symbols() -> list[str]:
+    return sorted(_PROTOS)
+
+
+def load() -> C.CDLL:
+    """Load the shared library (building it is the job of anyref_b200.build / __graft_entry__.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise RuntimeError(
+            f"{LIB_PATH} not found: run `python -m anyref_b200.build` (there is no CPU or PyTorch fallback)")
+    lib = C.CDLL(os.fspath(LIB_PATH))
+    for name, argtypes in _PROTOS.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPES.get(name, c_int)
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().sam_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (code {rc}): {msg}")
+
+
+def ptr(t) -> int | None:
+    """Device pointer of a torch tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def stream_ptr(device=None) -> int:
+    import torch
+
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+FMT_F16, FMT_BF16, FMT_F32 = 0, 1, 2
+
+
+def fmt_of(dtype) -> int:
+    import torch
+
+    if dtype == torch.float16:
+        return FMT_F16
+    if dtype == torch.bfloat16:
+        return FMT_BF16
+    if dtype == torch.float32:
+        return FMT_F32
+    raise TypeError(f"unsupported dtype {dtype}")

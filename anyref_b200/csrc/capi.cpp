@@ -1,0 +1,44 @@
+// extern "C" boundary of libanyref_sam.so (declared in include/anyref_sam.h).
+#include "../../include/anyref_sam.h"
+
+#include "host_common.h"
+#include "kernels.h"
+
+static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
+
+extern "C" {
+
+const char* sam_last_error(void) { return samhost::last_error(); }
+int sam_abi_version(void) { return 1; }
+
+int sam_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, int K, int fmt, void* out, int ldo,
+             int out_fmt, const float* bias, int act, const float* res, int ldr, int res_mod, void* stream) {
+  GemmEpilogue ep;
+  ep.out = out;
+  ep.ldo = ldo;
+  ep.out_fmt = out_fmt;
+  ep.bias = bias;
+  ep.act = act;
+  ep.res = res;
+  ep.ldr = ldr;
+  ep.res_mod = res_mod;
+  return samk_gemm(A, lda, W, ldw, M, N, K, fmt, ep, S(stream));
+}
+
+int sam_umma_probe(const void* A, const void* B, float* D, int N, int K, int fmt, int a_mode, int b_mode, int a_lbo,
+                   int a_sbo, int b_lbo, int b_sbo, void* stream) {
+  UmmaProbe p;
+  p.N = N;
+  p.K = K;
+  p.fmt = fmt;
+  p.a_mode = a_mode;
+  p.b_mode = b_mode;
+  p.a_lbo = a_lbo;
+  p.a_sbo = a_sbo;
+  p.b_lbo = b_lbo;
+  p.b_sbo = b_sbo;
+  p.a_kstep = p.b_kstep = 0;
+  return samk_umma_probe(A, B, D, p, S(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,83 @@
+#include "host_common.h"
+
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+namespace samhost {
+
+static thread_local char g_err[1024] = "";
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+const char* last_error() { return g_err; }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// The driver entry point is resolved through the runtime so the library has no link-time libcuda dependency.
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+  if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+int encode_tmap_nd(CUtensorMap* out, int elem_bytes, int is_bf16, const void* base, int rank, const uint64_t* dims,
+                   const uint64_t* strides_bytes, const uint32_t* box, int swizzle) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_error(3, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+  CUtensorMapDataType dt;
+  if (elem_bytes == 2)
+    dt = is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  else if (elem_bytes == 4)
+    dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  else
+    return set_error(1, "encode_tmap: unsupported element size %d", elem_bytes);
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bx[5];
+  cuuint32_t es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i > 0) gstr[i - 1] = strides_bytes[i];
+  }
+  CUresult r = fn(out, dt, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim, gstr, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, static_cast<CUtensorMapSwizzle>(swizzle),
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(3, "cuTensorMapEncodeTiled failed: CUresult=%d (rank=%d dims0=%llu box0=%u swz=%d)", (int)r,
+                     rank, (unsigned long long)dims[0], box[0], swizzle);
+  return 0;
+}
+
+int encode_tmap_2d(CUtensorMap* out, int elem_bytes, int is_bf16, const void* base, uint64_t inner, uint64_t outer,
+                   uint64_t outer_stride_bytes, uint32_t box_inner, uint32_t box_outer, int swizzle) {
+  uint64_t dims[2] = {inner, outer};
+  uint64_t strides[2] = {static_cast<uint64_t>(elem_bytes), outer_stride_bytes};
+  uint32_t box[2] = {box_inner, box_outer};
+  return encode_tmap_nd(out, elem_bytes, is_bf16, base, 2, dims, strides, box, swizzle);
+}
+
+int sm_count() {
+  static int n = 0;
+  if (n) return n;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  return n;
+}
+
+}  // namespace samhost

@@ -1,0 +1,37 @@
+// Host-side helpers shared by the C-ABI entry points: error reporting and TMA tensor-map encoding.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace samhost {
+
+// Records a message retrievable through sam_last_error(); returns `code` (non-zero).
+int set_error(int code, const char* fmt, ...);
+const char* last_error();
+
+#define SAM_CHECK_CUDA(expr)                                                                              \
+  do {                                                                                                    \
+    cudaError_t _e = (expr);                                                                              \
+    if (_e != cudaSuccess)                                                                                \
+      return samhost::set_error(2, "%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,                   \
+                                cudaGetErrorString(_e));                                                  \
+  } while (0)
+
+#define SAM_REQUIRE(cond, ...)                                     \
+  do {                                                             \
+    if (!(cond)) return samhost::set_error(1, __VA_ARGS__);        \
+  } while (0)
+
+// Row-major 2-D tensor [outer, inner] of 2- or 4-byte elements; box = [box_outer, box_inner].
+// swizzle: 0 none, 1 32B, 2 64B, 3 128B (CUtensorMapSwizzle values). Returns 0 on success.
+int encode_tmap_2d(CUtensorMap* out, int elem_bytes, int is_bf16, const void* base, uint64_t inner, uint64_t outer,
+                   uint64_t outer_stride_bytes, uint32_t box_inner, uint32_t box_outer, int swizzle);
+
+// Generic up-to-5-D encode (dims/strides innermost first; strides[0] is implied by the element size).
+int encode_tmap_nd(CUtensorMap* out, int elem_bytes, int is_bf16, const void* base, int rank, const uint64_t* dims,
+                   const uint64_t* strides_bytes, const uint32_t* box, int swizzle);
+
+int sm_count();
+
+}  // namespace samhost
