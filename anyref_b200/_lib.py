@@ -23,6 +23,13 @@ _PROTOS = {
                  c_int, c_void_p, c_int, c_int, c_void_p],
     "sam_umma_probe": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                        c_void_p],
+    "sam_layernorm": [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_int, c_int,
+                      c_int, c_void_p],
+    "sam_patch_im2col": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "sam_im2col3x3": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
+    "sam_ln_nhwc_to_nchw": [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "sam_attn_window": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "sam_attn_global": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
 }
 _RESTYPES = {"sam_last_error": c_char_p}
 

@@ -41,4 +41,27 @@ int sam_umma_probe(const void* A, const void* B, float* D, int N, int K, int fmt
   return samk_umma_probe(A, B, D, p, S(stream));
 }
 
+int sam_layernorm(const float* x, int ldx, const float* res, int ldr, const float* gamma, const float* beta, float eps,
+                  void* out, int ldo, int out_fmt, int M, int C, int normalize, void* stream) {
+  return samk_layernorm_rows(x, ldx, res, ldr, gamma, beta, eps, out, ldo, out_fmt, M, C, normalize, S(stream));
+}
+int sam_patch_im2col(const void* img, int in_fmt, void* out, int out_fmt, int B, int Sz, int p, void* stream) {
+  return samk_patch_im2col(img, in_fmt, out, out_fmt, B, Sz, p, S(stream));
+}
+int sam_im2col3x3(const void* in, void* out, int B, int g, int C, void* stream) {
+  return samk_im2col3x3(in, out, B, g, C, S(stream));
+}
+int sam_ln_nhwc_to_nchw(const float* x, const float* gamma, const float* beta, float eps, void* out, int out_fmt,
+                        int B, int tokens_per_img, int C, void* stream) {
+  return samk_ln_nhwc_to_nchw(x, gamma, beta, eps, out, out_fmt, B, tokens_per_img, C, S(stream));
+}
+int sam_attn_window(const void* qkv, const void* bias_op, const void* rel_tab, void* out, int B, int E, int heads,
+                    int fmt, void* stream) {
+  return samk_attn_window(qkv, bias_op, rel_tab, out, B, E, heads, fmt, S(stream));
+}
+int sam_attn_global(const void* qkv, const void* rh_rev, const void* rw_rev, void* out, int B, int E, int heads,
+                    int fmt, void* stream) {
+  return samk_attn_global(qkv, rh_rev, rw_rev, out, B, E, heads, fmt, S(stream));
+}
+
 }  // extern "C"

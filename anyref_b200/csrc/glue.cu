@@ -1,0 +1,234 @@
+// Memory-bound glue kernels of the SAM ViT-H encoder (vectorised, one pass over HBM each):
+//   samk_layernorm_rows  : nn.LayerNorm over the channel dim of token-major fp32 rows (optionally of x + res, the
+//                          decoder's post-residual norms, transformer.py:157-181) -> operand format or fp32
+//                          (image_encoder.py:179 norm1, :191 norm2; also LayerNorm2d on NHWC rows, common.py:38-43)
+//   samk_patch_im2col    : NCHW image -> [B*g*g, 3*p*p] patch matrix (A operand of the patch-embed GEMM,
+//                          image_encoder.py:418-426)
+//   samk_im2col3x3       : NHWC [B,g,g,C] -> [B*g*g, 9C] with zero padding (neck 3x3 conv, image_encoder.py:100-106)
+//   samk_ln_nhwc_to_nchw : LayerNorm2d (common.py:31-43) on NHWC fp32 rows fused with the NHWC->NCHW transposition
+//                          that produces the encoder output [B,C,g,g] (image_encoder.py:107, :124)
+#include "host_common.h"
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+constexpr int kLnMaxVec = 10;  // float4 per lane: supports C <= 1280
+
+// One warp per row. normalize == 0 degenerates to a dtype cast (used in front of the neck GEMM).
+__global__ void __launch_bounds__(256)
+layernorm_rows_kernel(const float* x, int ldx, const float* res, int ldr, const float* __restrict__ gamma,
+                      const float* __restrict__ beta, float eps, void* out, int ldo, int out_fmt, int M, int C,
+                      int normalize) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const int nvec = C >> 2;
+  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * ldx);
+  const float4* rr = res ? reinterpret_cast<const float4*>(res + static_cast<size_t>(row) * ldr) : nullptr;
+  float4 v[kLnMaxVec];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    const int idx = lane + i * 32;
+    if (idx < nvec) {
+      v[i] = xr[idx];
+      if (rr) {
+        const float4 r = rr[idx];
+        v[i].x += r.x; v[i].y += r.y; v[i].z += r.z; v[i].w += r.w;
+      }
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  float mean = 0.f, rstd = 1.f;
+  if (normalize) {
+    mean = warp_sum(s) / static_cast<float>(C);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLnMaxVec; ++i) {
+      const int idx = lane + i * 32;
+      if (idx < nvec) {
+        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+        q += (a * a + b * b) + (c * c + d * d);
+      }
+    }
+    rstd = rsqrtf(warp_sum(q) / static_cast<float>(C) + eps);
+  }
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    const int idx = lane + i * 32;
+    if (idx < nvec) {
+      float4 y = v[i];
+      if (normalize) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + idx);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + idx);
+        y.x = (y.x - mean) * rstd * g.x + b.x;
+        y.y = (y.y - mean) * rstd * g.y + b.y;
+        y.z = (y.z - mean) * rstd * g.z + b.z;
+        y.w = (y.w - mean) * rstd * g.w + b.w;
+      }
+      if (out_fmt == 2) {
+        reinterpret_cast<float4*>(static_cast<float*>(out) + static_cast<size_t>(row) * ldo)[idx] = y;
+      } else {
+        uint2 u;
+        u.x = ptx::pack2(y.x, y.y, out_fmt);
+        u.y = ptx::pack2(y.z, y.w, out_fmt);
+        reinterpret_cast<uint2*>(static_cast<uint16_t*>(out) + static_cast<size_t>(row) * ldo)[idx] = u;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void load8(const void* img, int fmt, size_t idx, float (&f)[8]) {
+  if (fmt == 2) {
+    const float4 a = reinterpret_cast<const float4*>(static_cast<const float*>(img) + idx)[0];
+    const float4 b = reinterpret_cast<const float4*>(static_cast<const float*>(img) + idx)[1];
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  } else {
+    const uint4 u = *reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(img) + idx);
+    const float2 a = ptx::unpack2(u.x, fmt), b = ptx::unpack2(u.y, fmt), c = ptx::unpack2(u.z, fmt),
+                 d = ptx::unpack2(u.w, fmt);
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+  }
+}
+
+// Each thread moves 8 consecutive pixels of one patch row: out[(b,py,px), c*p*p + ky*p + kx0..kx0+7].
+__global__ void __launch_bounds__(256)
+patch_im2col_kernel(const void* __restrict__ img, int in_fmt, uint16_t* __restrict__ out, int out_fmt, int B, int S,
+                    int p) {
+  const int g = S / p;
+  const int halves = p / 8;
+  const size_t total = static_cast<size_t>(B) * 3 * S * g * halves;  // (b, c, y, px, half)
+  const size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  size_t r = t;
+  const int half = r % halves; r /= halves;
+  const int px = r % g; r /= g;
+  const int y = r % S; r /= S;
+  const int c = r % 3;
+  const int b = r / 3;
+  const int py = y / p, ky = y % p;
+  float f[8];
+  load8(img, in_fmt, ((static_cast<size_t>(b) * 3 + c) * S + y) * S + px * p + half * 8, f);
+  uint4 u;
+  u.x = ptx::pack2(f[0], f[1], out_fmt);
+  u.y = ptx::pack2(f[2], f[3], out_fmt);
+  u.z = ptx::pack2(f[4], f[5], out_fmt);
+  u.w = ptx::pack2(f[6], f[7], out_fmt);
+  const size_t orow = (static_cast<size_t>(b) * g + py) * g + px;
+  *reinterpret_cast<uint4*>(out + orow * (3 * p * p) + c * p * p + ky * p + half * 8) = u;
+}
+
+// out[(b,y,x), (ky*3+kx)*C + c] = in[b, y+ky-1, x+kx-1, c] (zero outside); 16 bytes per thread.
+__global__ void __launch_bounds__(256)
+im2col3x3_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, int B, int g, int C) {
+  const int cv = C / 8;
+  const size_t total = static_cast<size_t>(B) * g * g * 9 * cv;
+  const size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  size_t r = t;
+  const int c8 = r % cv; r /= cv;
+  const int tap = r % 9; r /= 9;
+  const int x = r % g; r /= g;
+  const int y = r % g;
+  const int b = r / g;
+  const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (yy >= 0 && yy < g && xx >= 0 && xx < g)
+    v = *reinterpret_cast<const uint4*>(in + ((static_cast<size_t>(b) * g + yy) * g + xx) * C + c8 * 8);
+  *reinterpret_cast<uint4*>(out + ((static_cast<size_t>(b) * g + y) * g + x) * (9 * C) + tap * C + c8 * 8) = v;
+}
+
+// Block = 32 consecutive tokens x C channels (C <= 256): per-token LayerNorm over channels, then a transposed,
+// coalesced store into NCHW.
+__global__ void __launch_bounds__(256)
+ln_nhwc_to_nchw_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                       float eps, void* __restrict__ out, int out_fmt, int tokens_per_img, int C) {
+  __shared__ float tile[256][33];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t tok0 = static_cast<size_t>(blockIdx.x) * 32;
+  for (int p = warp; p < 32; p += 8) {
+    const float* xr = x + (tok0 + p) * C;
+    float v[8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = lane + i * 32;
+      v[i] = (c < C) ? xr[c] : 0.f;
+      s += v[i];
+    }
+    const float mean = warp_sum(s) / static_cast<float>(C);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = lane + i * 32;
+      if (c < C) q += (v[i] - mean) * (v[i] - mean);
+    }
+    const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(C) + eps);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = lane + i * 32;
+      if (c < C) tile[c][p] = (v[i] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
+    }
+  }
+  __syncthreads();
+  const size_t img = tok0 / tokens_per_img;
+  const size_t pix0 = tok0 % tokens_per_img;
+  for (int c = warp; c < C; c += 8) {
+    const float y = tile[c][lane];
+    const size_t o = (img * C + c) * tokens_per_img + pix0 + lane;
+    if (out_fmt == 2)
+      static_cast<float*>(out)[o] = y;
+    else
+      static_cast<uint16_t*>(out)[o] = ptx::pack1(y, out_fmt);
+  }
+}
+
+}  // namespace
+
+int samk_layernorm_rows(const float* x, int ldx, const float* res, int ldr, const float* gamma, const float* beta,
+                        float eps, void* out, int ldo, int out_fmt, int M, int C, int normalize, cudaStream_t stream) {
+  SAM_REQUIRE(C % 4 == 0 && C <= kLnMaxVec * 128, "layernorm: C=%d must be a multiple of 4 and <= %d", C, kLnMaxVec * 128);
+  SAM_REQUIRE(ldx % 4 == 0 && ldo % 4 == 0 && (!res || ldr % 4 == 0), "layernorm: leading dimensions must be multiples of 4");
+  SAM_REQUIRE(M > 0, "layernorm: empty input");
+  SAM_REQUIRE(!normalize || (gamma && beta), "layernorm: affine parameters missing");
+  layernorm_rows_kernel<<<(M + 7) / 8, 256, 0, stream>>>(x, ldx, res, ldr, gamma, beta, eps, out, ldo, out_fmt, M, C,
+                                                         normalize);
+  SAM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int samk_patch_im2col(const void* img, int in_fmt, void* out, int out_fmt, int B, int S, int p, cudaStream_t stream) {
+  SAM_REQUIRE(p % 8 == 0 && S % p == 0, "patch_im2col: patch %d / image %d unsupported", p, S);
+  SAM_REQUIRE(out_fmt == 0 || out_fmt == 1, "patch_im2col: output must be fp16/bf16");
+  const size_t total = static_cast<size_t>(B) * 3 * S * (S / p) * (p / 8);
+  patch_im2col_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+      img, in_fmt, static_cast<uint16_t*>(out), out_fmt, B, S, p);
+  SAM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int samk_im2col3x3(const void* in, void* out, int B, int g, int C, cudaStream_t stream) {
+  SAM_REQUIRE(C % 8 == 0, "im2col3x3: C must be a multiple of 8");
+  const size_t total = static_cast<size_t>(B) * g * g * 9 * (C / 8);
+  im2col3x3_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+      static_cast<const uint16_t*>(in), static_cast<uint16_t*>(out), B, g, C);
+  SAM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int samk_ln_nhwc_to_nchw(const float* x, const float* gamma, const float* beta, float eps, void* out, int out_fmt,
+                         int B, int tokens_per_img, int C, cudaStream_t stream) {
+  SAM_REQUIRE(C <= 256 && tokens_per_img % 32 == 0, "ln_nhwc_to_nchw: C<=256 and tokens%%32==0 required");
+  const size_t blocks = static_cast<size_t>(B) * tokens_per_img / 32;
+  ln_nhwc_to_nchw_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(x, gamma, beta, eps, out, out_fmt,
+                                                                           tokens_per_img, C);
+  SAM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -34,3 +34,22 @@ struct UmmaProbe {
   int b_lbo, b_sbo, b_kstep;
 };
 int samk_umma_probe(const void* A, const void* B, float* D, const UmmaProbe& p, cudaStream_t stream);
+
+// 14x14 windowed attention with fused decomposed rel-pos bias (attn_window.cu).
+//   qkv [B*4096, 3E] op-format; bias_op [3E] op-format (qkv bias, used for padded window tokens);
+//   rel_tab [64, 80] op-format: rows 0..26 rel_pos_h, 27..53 rel_pos_w, rest zero; out [B*4096, E] op-format.
+int samk_attn_window(const void* qkv, const void* bias_op, const void* rel_tab, void* out, int B, int E, int heads,
+                     int fmt, cudaStream_t stream);
+// Global 64x64 attention with fused rel-pos bias (attn_global.cu).
+//   rh_rev / rw_rev [128, 80] op-format: row j = rel_pos_{h,w}[126 - j] for j < 127, row 127 zero.
+int samk_attn_global(const void* qkv, const void* rh_rev, const void* rw_rev, void* out, int B, int E, int heads,
+                     int fmt, cudaStream_t stream);
+
+// Memory-bound glue (glue.cu).  All fp32 activations are token-major rows.
+//   layernorm_rows : out[row] = LN(x[row] (+ res[row])) * gamma + beta  (normalize == 0: plain dtype cast)
+int samk_layernorm_rows(const float* x, int ldx, const float* res, int ldr, const float* gamma, const float* beta,
+                        float eps, void* out, int ldo, int out_fmt, int M, int C, int normalize, cudaStream_t stream);
+int samk_patch_im2col(const void* img, int in_fmt, void* out, int out_fmt, int B, int S, int p, cudaStream_t stream);
+int samk_im2col3x3(const void* in, void* out, int B, int g, int C, cudaStream_t stream);
+int samk_ln_nhwc_to_nchw(const float* x, const float* gamma, const float* beta, float eps, void* out, int out_fmt,
+                         int B, int tokens_per_img, int C, cudaStream_t stream);

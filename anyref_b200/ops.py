@@ -52,3 +52,90 @@ def umma_probe(a: torch.Tensor, b: torch.Tensor, N: int, K: int, a_mode: int, b_
                             stream_ptr(a.device))
     check(rc, "sam_umma_probe")
     return d
+
+
+def layernorm(x: torch.Tensor, gamma, beta, eps: float, out_dtype, *, residual=None, normalize: bool = True,
+              out: torch.Tensor | None = None) -> torch.Tensor:
+    """Row LayerNorm of fp32 [M, C] (optionally of x + residual) -> out_dtype; see sam_layernorm."""
+    _req_cuda(x, gamma, beta, residual, out)
+    assert x.dim() == 2 and x.dtype == torch.float32 and x.stride(1) == 1
+    M, Cc = x.shape
+    if out is None:
+        out = torch.empty((M, Cc), device=x.device, dtype=out_dtype)
+    rc = _lib.load().sam_layernorm(ptr(x), x.stride(0), ptr(residual), residual.stride(0) if residual is not None else 0,
+                                   ptr(gamma), ptr(beta), float(eps), ptr(out), out.stride(0), fmt_of(out.dtype), M, Cc,
+                                   1 if normalize else 0, stream_ptr(x.device))
+    check(rc, "sam_layernorm")
+    return out
+
+
+def patch_im2col(img: torch.Tensor, patch: int, out_dtype) -> torch.Tensor:
+    _req_cuda(img)
+    B, ch, S, S2 = img.shape
+    assert ch == 3 and S == S2 and img.is_contiguous()
+    g = S // patch
+    out = torch.empty((B * g * g, 3 * patch * patch), device=img.device, dtype=out_dtype)
+    rc = _lib.load().sam_patch_im2col(ptr(img), fmt_of(img.dtype), ptr(out), fmt_of(out_dtype), B, S, patch,
+                                      stream_ptr(img.device))
+    check(rc, "sam_patch_im2col")
+    return out
+
+
+def im2col3x3(x: torch.Tensor, B: int, g: int) -> torch.Tensor:
+    _req_cuda(x)
+    Cc = x.shape[-1]
+    assert x.is_contiguous() and x.numel() == B * g * g * Cc and x.element_size() == 2
+    out = torch.empty((B * g * g, 9 * Cc), device=x.device, dtype=x.dtype)
+    rc = _lib.load().sam_im2col3x3(ptr(x), ptr(out), B, g, Cc, stream_ptr(x.device))
+    check(rc, "sam_im2col3x3")
+    return out
+
+
+def ln_nhwc_to_nchw(x: torch.Tensor, gamma, beta, eps: float, B: int, g: int, out_dtype) -> torch.Tensor:
+    _req_cuda(x, gamma, beta)
+    Cc = x.shape[-1]
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    out = torch.empty((B, Cc, g, g), device=x.device, dtype=out_dtype)
+    rc = _lib.load().sam_ln_nhwc_to_nchw(ptr(x), ptr(gamma), ptr(beta), float(eps), ptr(out), fmt_of(out_dtype), B, g * g,
+                                         Cc, stream_ptr(x.device))
+    check(rc, "sam_ln_nhwc_to_nchw")
+    return out
+
+
+def window_rel_table(rel_pos_h: torch.Tensor, rel_pos_w: torch.Tensor, dtype) -> torch.Tensor:
+    """[64, hd] operand table of sam_attn_window: rows 0..26 rel_pos_h, 27..53 rel_pos_w, rest zero."""
+    n, hd = rel_pos_h.shape
+    t = torch.zeros((64, hd), device=rel_pos_h.device, dtype=dtype)
+    t[:n] = rel_pos_h.to(dtype)
+    t[n:2 * n] = rel_pos_w.to(dtype)
+    return t
+
+
+def global_rel_table(rel_pos: torch.Tensor, dtype) -> torch.Tensor:
+    """[128, hd] operand table of sam_attn_global: row j = rel_pos[126 - j] (j < 127), row 127 zero."""
+    n, hd = rel_pos.shape
+    t = torch.zeros((n + 1, hd), device=rel_pos.device, dtype=dtype)
+    t[:n] = rel_pos.flip(0).to(dtype)
+    return t
+
+
+def attn_window(qkv: torch.Tensor, bias_op: torch.Tensor, rel_tab: torch.Tensor, B: int, heads: int) -> torch.Tensor:
+    _req_cuda(qkv, bias_op, rel_tab)
+    E = qkv.shape[1] // 3
+    assert qkv.is_contiguous() and qkv.shape[0] == B * 4096 and bias_op.dtype == qkv.dtype == rel_tab.dtype
+    out = torch.empty((B * 4096, E), device=qkv.device, dtype=qkv.dtype)
+    rc = _lib.load().sam_attn_window(ptr(qkv), ptr(bias_op), ptr(rel_tab), ptr(out), B, E, heads, fmt_of(qkv.dtype),
+                                     stream_ptr(qkv.device))
+    check(rc, "sam_attn_window")
+    return out
+
+
+def attn_global(qkv: torch.Tensor, rh_rev: torch.Tensor, rw_rev: torch.Tensor, B: int, heads: int) -> torch.Tensor:
+    _req_cuda(qkv, rh_rev, rw_rev)
+    E = qkv.shape[1] // 3
+    assert qkv.is_contiguous() and qkv.shape[0] == B * 4096
+    out = torch.empty((B * 4096, E), device=qkv.device, dtype=qkv.dtype)
+    rc = _lib.load().sam_attn_global(ptr(qkv), ptr(rh_rev), ptr(rw_rev), ptr(out), B, E, heads, fmt_of(qkv.dtype),
+                                     stream_ptr(qkv.device))
+    check(rc, "sam_attn_global")
+    return out

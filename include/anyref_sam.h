@@ -48,6 +48,55 @@ int sam_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, int K
 int sam_umma_probe(const void* A, const void* B, float* D, int N, int K, int fmt, int a_mode, int b_mode, int a_lbo,
                    int a_sbo, int b_lbo, int b_sbo, void* stream);
 
+/*
+ * Row LayerNorm: out[row] = (v - mean(v)) / sqrt(var(v) + eps) * gamma + beta with v = x[row] (+ res[row]).
+ * Replaces nn.LayerNorm(eps=1e-6) of Block.norm1 / norm2 (image_encoder.py:179, :191; eps from build_sam.py:73),
+ * LayerNorm2d on channels-last rows (common.py:38-43) and the decoder's post-residual norms (transformer.py:157-181,
+ * eps 1e-5).  x, res fp32 [M, ld*]; out fmt 0/1/2.  normalize == 0 -> plain cast of x (+res) to out_fmt.
+ */
+int sam_layernorm(const float* x, int ldx, const float* res, int ldr, const float* gamma, const float* beta, float eps,
+                  void* out, int ldo, int out_fmt, int M, int C, int normalize, void* stream);
+
+/*
+ * PatchEmbed im2col (image_encoder.py:418-426): img [B,3,S,S] (fmt in_fmt) -> out [B*(S/p)^2, 3*p*p] (fmt out_fmt),
+ * column order (c, ky, kx) == the flattened Conv2d weight, so patch-embed becomes sam_gemm with W = proj.weight.
+ */
+int sam_patch_im2col(const void* img, int in_fmt, void* out, int out_fmt, int B, int S, int p, void* stream);
+
+/*
+ * 3x3 / pad 1 im2col on channels-last activations for the neck's second conv (image_encoder.py:100-106):
+ * in [B,g,g,C] (16-bit) -> out [B*g*g, 9*C], column order (ky, kx, c).
+ */
+int sam_im2col3x3(const void* in, void* out, int B, int g, int C, void* stream);
+
+/*
+ * LayerNorm2d (common.py:31-43, eps 1e-6) on channels-last fp32 rows fused with the NHWC -> NCHW transposition that
+ * yields the encoder output [B,C,g,g] (image_encoder.py:107, :124).  x [B*tokens, C] fp32; out fmt 0/1/2.
+ */
+int sam_ln_nhwc_to_nchw(const float* x, const float* gamma, const float* beta, float eps, void* out, int out_fmt,
+                        int B, int tokens_per_img, int C, void* stream);
+
+/*
+ * Windowed (14x14) encoder attention with window partition / un-partition and the decomposed rel-pos bias fused in.
+ * Replaces image_encoder.py:235-257 (Attention.forward without qkv/proj), :263-318 (window_partition/unpartition)
+ * and :354-392 (add_decomposed_rel_pos) for the 28 windowed blocks.
+ *   qkv     [B*64*64, 3E] fmt 0/1, token-major, NOT partitioned, columns ordered (q|k|v, head, d)
+ *   bias_op [3E]          qkv bias in operand format -- q/k/v of the zero-padded window tokens (image_encoder.py:281)
+ *   rel_tab [64, 80]      operand format: rows 0..26 rel_pos_h, rows 27..53 rel_pos_w, rest zero
+ *   out     [B*64*64, E]  operand format, heads merged (the A operand of the proj GEMM)
+ * head_dim must be 80 (ViT-H), grid 64x64.
+ */
+int sam_attn_window(const void* qkv, const void* bias_op, const void* rel_tab, void* out, int B, int E, int heads,
+                    int fmt, void* stream);
+
+/*
+ * Global (64x64 tokens) encoder attention, flash-style, decomposed rel-pos bias fused into the online softmax.
+ * Replaces image_encoder.py:235-257 + :354-392 for blocks 7/15/23/31.
+ *   rh_rev / rw_rev [128, 80] operand format: row j = rel_pos_{h,w}[126 - j] for j < 127, row 127 zero.
+ */
+int sam_attn_global(const void* qkv, const void* rh_rev, const void* rw_rev, void* out, int B, int E, int heads,
+                    int fmt, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
