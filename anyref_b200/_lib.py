@@ -13,7 +13,23 @@ LIB_PATH = _PKG / "libanyref_sam.so"
 
 _lib = None
 
-c_void_p, c_int, c_float, c_char_p = C.c_void_p, C.c_int, C.c_float, C.c_char_p
+c_void_p, c_int, c_float, c_char_p, c_size_t = C.c_void_p, C.c_int, C.c_float, C.c_char_p, C.c_size_t
+
+
+class SamEncoderShape(C.Structure):
+    """Mirror of `struct SamEncoderShape` (include/anyref_sam.h)."""
+    _fields_ = [("embed_dim", c_int), ("depth", c_int), ("heads", c_int), ("mlp_dim", c_int), ("img", c_int),
+                ("patch", c_int), ("window", c_int), ("out_chans", c_int), ("fmt", c_int),
+                ("global_mask", C.c_ulonglong), ("tap_block", c_int), ("tap_out", c_void_p)]
+
+
+class SamDecoderShape(C.Structure):
+    """Mirror of `struct SamDecoderShape` (include/anyref_sam.h)."""
+    _fields_ = [("C", c_int), ("heads", c_int), ("depth", c_int), ("mlp_dim", c_int), ("num_mask_tokens", c_int),
+                ("iou_hidden", c_int), ("grid", c_int)]
+
+
+_ENC_P, _DEC_P = C.POINTER(SamEncoderShape), C.POINTER(SamDecoderShape)
 
 # name -> argtypes (restype is int unless listed in _RESTYPES)
 _PROTOS = {
@@ -30,8 +46,22 @@ _PROTOS = {
     "sam_ln_nhwc_to_nchw": [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "sam_attn_window": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "sam_attn_global": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "sam_encoder_w16_elems": [_ENC_P],
+    "sam_encoder_w32_elems": [_ENC_P],
+    "sam_encoder_workspace_bytes": [_ENC_P, c_int],
+    "sam_encoder_forward": [_ENC_P, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_size_t,
+                            c_void_p],
+    "sam_decoder_weight_elems": [_DEC_P],
+    "sam_decoder_workspace_bytes": [_DEC_P, c_int, c_int],
+    "sam_decoder_forward": [_DEC_P, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
+                            c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p],
+    "sam_postprocess_masks": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                              c_float, c_void_p],
+    "sam_dense_pe": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
 }
-_RESTYPES = {"sam_last_error": c_char_p}
+_RESTYPES = {"sam_last_error": c_char_p, "sam_encoder_w16_elems": c_size_t, "sam_encoder_w32_elems": c_size_t,
+             "sam_encoder_workspace_bytes": c_size_t, "sam_decoder_weight_elems": c_size_t,
+             "sam_decoder_workspace_bytes": c_size_t}
 
 
 def exported_symbols() -> list[str]:

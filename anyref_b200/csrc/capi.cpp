@@ -64,4 +64,34 @@ int sam_attn_global(const void* qkv, const void* rh_rev, const void* rw_rev, voi
   return samk_attn_global(qkv, rh_rev, rw_rev, out, B, E, heads, fmt, S(stream));
 }
 
+size_t sam_encoder_w16_elems(const SamEncoderShape* s) { return samk_encoder_w16_elems(*s); }
+size_t sam_encoder_w32_elems(const SamEncoderShape* s) { return samk_encoder_w32_elems(*s); }
+size_t sam_encoder_workspace_bytes(const SamEncoderShape* s, int B) { return samk_encoder_workspace_bytes(*s, B); }
+int sam_encoder_forward(const SamEncoderShape* s, const void* w16, const float* w32, const void* images, int in_fmt,
+                        int B, void* out, int out_fmt, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!s || !w16 || !w32 || !images || !out || !workspace) return samhost::set_error(1, "sam_encoder_forward: NULL argument");
+  return samk_encoder_forward(*s, w16, w32, images, in_fmt, B, out, out_fmt, workspace, workspace_bytes, S(stream));
+}
+size_t sam_decoder_weight_elems(const SamDecoderShape* s) { return samk_decoder_weight_elems(*s); }
+size_t sam_decoder_workspace_bytes(const SamDecoderShape* s, int n, int k) { return samk_decoder_workspace_bytes(*s, n, k); }
+int sam_decoder_forward(const SamDecoderShape* s, const float* weights, const void* image_embeddings, int emb_fmt,
+                        const int* img_index, const void* image_pe, int pe_fmt, const void* sparse, int sparse_fmt,
+                        int n, int k, const void* dense_vec, const void* dense_full, int dense_fmt, void* masks,
+                        void* iou, int out_fmt, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!s || !weights || !image_embeddings || !image_pe || !masks || !iou || !workspace)
+    return samhost::set_error(1, "sam_decoder_forward: NULL argument");
+  if (k > 0 && !sparse) return samhost::set_error(1, "sam_decoder_forward: sparse embeddings missing");
+  return samk_decoder_forward(*s, weights, image_embeddings, emb_fmt, img_index, image_pe, pe_fmt, sparse, sparse_fmt,
+                              n, k, dense_vec, dense_full, dense_fmt, masks, iou, out_fmt, workspace, workspace_bytes,
+                              S(stream));
+}
+int sam_postprocess_masks(const void* low, int low_fmt, int num_masks, int L, int Sz, int h_in, int w_in, int H, int W,
+                          float* logits, unsigned char* binary, float threshold, void* stream) {
+  return samk_postprocess(low, low_fmt, num_masks, L, Sz, h_in, w_in, H, W, logits, binary, threshold, S(stream));
+}
+
+int sam_dense_pe(const float* gauss, void* out, int out_fmt, int C, int g, void* stream) {
+  return samk_dense_pe(gauss, out, out_fmt, C, g, S(stream));
+}
+
 }  // extern "C"

@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "../../include/anyref_sam.h"  // SamEncoderShape / SamDecoderShape
+
 // Operand / storage formats used across the library.
 //   0 = fp16, 1 = bf16 (tensor-core operand formats; identical to the tcgen05 idesc encoding), 2 = fp32
 enum SamFmt : int { SAM_F16 = 0, SAM_BF16 = 1, SAM_F32 = 2 };
@@ -53,3 +55,19 @@ int samk_patch_im2col(const void* img, int in_fmt, void* out, int out_fmt, int B
 int samk_im2col3x3(const void* in, void* out, int B, int g, int C, cudaStream_t stream);
 int samk_ln_nhwc_to_nchw(const float* x, const float* gamma, const float* beta, float eps, void* out, int out_fmt,
                          int B, int tokens_per_img, int C, cudaStream_t stream);
+
+// Whole-module drivers (encoder.cpp, decoder.cu, postprocess.cu); see include/anyref_sam.h for the semantics.
+size_t samk_encoder_w16_elems(const SamEncoderShape& s);
+size_t samk_encoder_w32_elems(const SamEncoderShape& s);
+size_t samk_encoder_workspace_bytes(const SamEncoderShape& s, int B);
+int samk_encoder_forward(const SamEncoderShape& s, const void* w16, const float* w32, const void* images, int in_fmt,
+                         int B, void* out, int out_fmt, void* workspace, size_t workspace_bytes, cudaStream_t st);
+size_t samk_decoder_weight_elems(const SamDecoderShape& s);
+size_t samk_decoder_workspace_bytes(const SamDecoderShape& s, int n, int k);
+int samk_decoder_forward(const SamDecoderShape& s, const float* blob, const void* image_embeddings, int emb_fmt,
+                         const int* img_index, const void* image_pe, int pe_fmt, const void* sparse, int sparse_fmt,
+                         int n, int k, const void* dense_vec, const void* dense_full, int dense_fmt, void* masks,
+                         void* iou, int out_fmt, void* workspace, size_t workspace_bytes, cudaStream_t st);
+int samk_postprocess(const void* low, int low_fmt, int num_masks, int L, int S, int h_in, int w_in, int H, int W,
+                     float* logits, uint8_t* binary, float threshold, cudaStream_t stream);
+int samk_dense_pe(const float* gauss, void* out, int out_fmt, int C, int g, cudaStream_t stream);

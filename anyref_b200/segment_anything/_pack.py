@@ -1,0 +1,171 @@
+"""Packs module parameters into the weight blobs the C ABI consumes (layouts: csrc/encoder.cpp, csrc/decoder.cu).
+
+Runs once per parameter change (see _runtime.params_signature); pure data movement (casts, permutes, copies).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from .. import _lib
+
+
+def _align8(n: int) -> int:
+    return (n + 7) & ~7
+
+
+class _Blob:
+    def __init__(self, n: int, dtype, device):
+        self.t = torch.zeros(n, dtype=dtype, device=device)
+        self.off = 0
+
+    def put(self, src: torch.Tensor, n_expected: int | None = None):
+        flat = src.detach().reshape(-1)
+        n = flat.numel()
+        if n_expected is not None and n != n_expected:
+            raise RuntimeError(f"pack: segment has {n} elements, layout expects {n_expected}")
+        self.t[self.off:self.off + n].copy_(flat)
+        self.off += _align8(n)
+
+    def put_exact(self, src: torch.Tensor):  # unpadded (decoder blob)
+        flat = src.detach().reshape(-1)
+        self.t[self.off:self.off + flat.numel()].copy_(flat)
+        self.off += flat.numel()
+
+
+def encoder_shape(enc, op_dtype) -> _lib.SamEncoderShape:
+    gmask = 0
+    for i, blk in enumerate(enc.blocks):
+        if blk.window_size == 0:
+            gmask |= 1 << i
+    return _lib.SamEncoderShape(embed_dim=enc.embed_dim, depth=len(enc.blocks), heads=enc.num_heads,
+                                mlp_dim=enc.blocks[0].mlp.lin1.out_features, img=enc.img_size, patch=enc.patch_size,
+                                window=enc.window_size, out_chans=enc.out_chans, fmt=_lib.fmt_of(op_dtype),
+                                global_mask=gmask, tap_block=-1, tap_out=None)
+
+
+def pack_encoder(enc, op_dtype):
+    """-> (shape, w16 blob, w32 blob)."""
+    lib = _lib.load()
+    shape = encoder_shape(enc, op_dtype)
+    dev = enc.pos_embed.device
+    n16 = lib.sam_encoder_w16_elems(C.byref(shape))
+    n32 = lib.sam_encoder_w32_elems(C.byref(shape))
+    b16 = _Blob(n16, op_dtype, dev)
+    b32 = _Blob(n32, torch.float32, dev)
+    E, hd = enc.embed_dim, enc.embed_dim // enc.num_heads
+    g = enc.img_size // enc.patch_size
+    b16.put(enc.patch_embed.proj.weight.reshape(E, -1).to(op_dtype))
+    b32.put(enc.pos_embed.float(), g * g * E)
+    b32.put(enc.patch_embed.proj.bias.float())
+    for blk in enc.blocks:
+        a = blk.attn
+        b16.put(a.qkv.weight.to(op_dtype))
+        b16.put(a.proj.weight.to(op_dtype))
+        b16.put(blk.mlp.lin1.weight.to(op_dtype))
+        b16.put(blk.mlp.lin2.weight.to(op_dtype))
+        b16.put(a.qkv.bias.to(op_dtype))
+        s = g if blk.window_size == 0 else blk.window_size
+        if a.rel_pos_h.shape != (2 * s - 1, hd) or a.rel_pos_w.shape != (2 * s - 1, hd):
+            raise RuntimeError("rel_pos tables must have 2*size-1 rows (the interpolating branch of get_rel_pos, "
+                               "image_encoder.py:336-343, is never taken by SAM checkpoints and is not implemented)")
+        rel = torch.zeros(2 * 128 * hd, dtype=op_dtype, device=dev)
+        if blk.window_size == 0:
+            if s != 64:
+                raise RuntimeError("global attention kernel expects a 64x64 token grid")
+            rel[:127 * hd] = a.rel_pos_h.detach().flip(0).to(op_dtype).reshape(-1)
+            rel[128 * hd:128 * hd + 127 * hd] = a.rel_pos_w.detach().flip(0).to(op_dtype).reshape(-1)
+        else:
+            if s != 14:
+                raise RuntimeError("windowed attention kernel expects 14x14 windows")
+            rel[:27 * hd] = a.rel_pos_h.detach().to(op_dtype).reshape(-1)
+            rel[27 * hd:54 * hd] = a.rel_pos_w.detach().to(op_dtype).reshape(-1)
+        b16.put(rel)
+        b32.put(blk.norm1.weight.float()); b32.put(blk.norm1.bias.float())
+        b32.put(a.qkv.bias.float())
+        b32.put(a.proj.bias.float())
+        b32.put(blk.norm2.weight.float()); b32.put(blk.norm2.bias.float())
+        b32.put(blk.mlp.lin1.bias.float())
+        b32.put(blk.mlp.lin2.bias.float())
+    Cc = enc.out_chans
+    b16.put(enc.neck[0].weight.reshape(Cc, E).to(op_dtype))
+    b16.put(enc.neck[2].weight.permute(0, 2, 3, 1).reshape(Cc, 9 * Cc).to(op_dtype))
+    b32.put(enc.neck[1].weight.float()); b32.put(enc.neck[1].bias.float())
+    b32.put(enc.neck[3].weight.float()); b32.put(enc.neck[3].bias.float())
+    if b16.off != n16 or b32.off != n32:
+        raise RuntimeError(f"encoder blob layout mismatch: {b16.off}/{n16} {b32.off}/{n32}")
+    return shape, b16.t, b32.t
+
+
+def decoder_shape(dec, grid: int) -> _lib.SamDecoderShape:
+    tr = dec.transformer
+    return _lib.SamDecoderShape(C=dec.transformer_dim, heads=tr.num_heads, depth=tr.depth, mlp_dim=tr.mlp_dim,
+                                num_mask_tokens=dec.num_mask_tokens,
+                                iou_hidden=dec.iou_prediction_head.layers[0].out_features, grid=grid)
+
+
+def _unwrap(m):
+    """peft's ModulesToSaveWrapper keeps the live copy under modules_to_save[active_adapter] (the reference
+    tolerates the wrapper with try/except, mask_decoder.py:126-136, :162-169)."""
+    mts = getattr(m, "modules_to_save", None)
+    if mts is not None:
+        name = getattr(m, "active_adapter", None)
+        if isinstance(name, (list, tuple)):
+            name = name[0]
+        if name in mts:
+            return mts[name]
+    return m
+
+
+def pack_decoder(dec, grid: int):
+    """-> (shape, fp32 blob) in the order of csrc/decoder.cu carve_weights."""
+    lib = _lib.load()
+    shape = decoder_shape(dec, grid)
+    n = lib.sam_decoder_weight_elems(C.byref(shape))
+    dev = dec.iou_token.weight.device
+    b = _Blob(n, torch.float32, dev)
+    f = lambda t: t.detach().float()
+
+    def attn(a):
+        for lin in (a.q_proj, a.k_proj, a.v_proj, a.out_proj):
+            b.put_exact(f(lin.weight)); b.put_exact(f(lin.bias))
+
+    def norm(ln):
+        b.put_exact(f(ln.weight)); b.put_exact(f(ln.bias))
+
+    b.put_exact(f(dec.iou_token.weight))
+    b.put_exact(f(_unwrap(dec.mask_tokens).weight))
+    tr = dec.transformer
+    for layer in tr.layers:
+        attn(layer.self_attn); norm(layer.norm1)
+        attn(layer.cross_attn_token_to_image); norm(layer.norm2)
+        b.put_exact(f(layer.mlp.lin1.weight)); b.put_exact(f(layer.mlp.lin1.bias))
+        b.put_exact(f(layer.mlp.lin2.weight)); b.put_exact(f(layer.mlp.lin2.bias))
+        norm(layer.norm3); norm(layer.norm4)
+        attn(layer.cross_attn_image_to_token)
+    attn(tr.final_attn_token_to_image); norm(tr.norm_final_attn)
+    up = _unwrap(dec.output_upscaling)
+    # ConvTranspose2d(k=2,s=2) weight [in, out, dy, dx] -> per-pixel linear weight [(dy,dx,out), in]
+    w0 = f(up[0].weight)
+    b.put_exact(w0.permute(2, 3, 1, 0).reshape(-1, w0.shape[0]).contiguous())
+    b.put_exact(f(up[0].bias).repeat(4))
+    norm(up[1])
+    w1 = f(up[3].weight)
+    b.put_exact(w1.permute(2, 3, 1, 0).contiguous())     # [(ey,ex), out, in]
+    b.put_exact(f(up[3].bias))
+    hyper = _unwrap(dec.output_hypernetworks_mlps)
+    for i in range(dec.num_mask_tokens):
+        m = hyper[i]
+        if len(m.layers) != 3:
+            raise RuntimeError("hypernetwork MLPs must have 3 layers")
+        for lin in m.layers:
+            b.put_exact(f(lin.weight)); b.put_exact(f(lin.bias))
+    head = dec.iou_prediction_head
+    if len(head.layers) != 3:
+        raise RuntimeError("iou_head_depth must be 3")
+    for lin in head.layers:
+        b.put_exact(f(lin.weight)); b.put_exact(f(lin.bias))
+    if b.off != n:
+        raise RuntimeError(f"decoder blob layout mismatch: packed {b.off}, library expects {n}")
+    return shape, b.t

@@ -1,0 +1,72 @@
+"""Sam wrapper (reference: modeling/sam.py:18-184): holds the three modules, `mask_threshold`, the pixel
+normalisation buffers, and `postprocess_masks` -- here one fused CUDA kernel (`sam_postprocess_masks`) instead of two
+F.interpolate calls with a [n,C,1024,1024] intermediate (sam.py:159-172).
+
+The reference's `Sam.forward` (:56-135) is dead code on AnyRef's path (it calls the prompt encoder without the
+required `text_embeds`) and is not provided.
+"""
+from __future__ import annotations
+
+from typing import Any, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from .. import _runtime
+from ... import _lib
+from .image_encoder import ImageEncoderViT
+from .mask_decoder import MaskDecoder
+from .prompt_encoder import PromptEncoder
+
+
+class Sam(nn.Module):
+    mask_threshold: float = 0.0
+    image_format: str = "RGB"
+
+    def __init__(self, image_encoder: ImageEncoderViT, prompt_encoder: PromptEncoder, mask_decoder: MaskDecoder,
+                 pixel_mean: List[float] = [123.675, 116.28, 103.53],
+                 pixel_std: List[float] = [58.395, 57.12, 57.375]) -> None:
+        super().__init__()
+        self.image_encoder = image_encoder
+        self.prompt_encoder = prompt_encoder
+        self.mask_decoder = mask_decoder
+        self.register_buffer("pixel_mean", torch.Tensor(pixel_mean).view(-1, 1, 1), False)
+        self.register_buffer("pixel_std", torch.Tensor(pixel_std).view(-1, 1, 1), False)
+
+    @property
+    def device(self) -> Any:
+        return self.pixel_mean.device
+
+    def forward(self, *args, **kwargs):  # pragma: no cover
+        raise NotImplementedError("Sam.forward is unused (and broken) in AnyRef; call image_encoder / prompt_encoder / "
+                                  "mask_decoder / postprocess_masks as model/anyref.py:793-819 does")
+
+    @torch.no_grad()
+    def postprocess_masks(self, masks: torch.Tensor, input_size: Tuple[int, ...], original_size: Tuple[int, ...],
+                          return_binary: bool = False):
+        """[n,C,L,L] low-res logits -> fp32 logits [n,C,H,W] (sam.py:137-172).  With return_binary=True also returns
+        the uint8 mask `logits > mask_threshold` produced in the same pass."""
+        _runtime.require_cuda(masks, "Sam.postprocess_masks")
+        if masks.dim() != 4 or masks.shape[2] != masks.shape[3]:
+            raise ValueError(f"expected masks [n,C,L,L], got {tuple(masks.shape)}")
+        m = masks.contiguous()
+        n, ch, L, _ = m.shape
+        h_in, w_in = int(input_size[0]), int(input_size[1])
+        H, W = int(original_size[0]), int(original_size[1])
+        S = self.image_encoder.img_size
+        out = torch.empty((n, ch, H, W), device=m.device, dtype=torch.float32)
+        binary = torch.empty((n, ch, H, W), device=m.device, dtype=torch.uint8) if return_binary else None
+        if n * ch > 0:
+            rc = _lib.load().sam_postprocess_masks(m.data_ptr(), _lib.fmt_of(m.dtype), n * ch, L, S, h_in, w_in, H, W,
+                                                   out.data_ptr(), binary.data_ptr() if return_binary else None,
+                                                   float(self.mask_threshold), _lib.stream_ptr(m.device))
+            _lib.check(rc, "sam_postprocess_masks")
+        return (out, binary) if return_binary else out
+
+    def preprocess(self, x: torch.Tensor) -> torch.Tensor:
+        """Normalise pixel values and pad to a square (sam.py:174-184) -- CPU-side data preparation in AnyRef
+        (utils/refer_seg.py:560-570); kept as plain tensor ops, outside the measured path."""
+        x = (x - self.pixel_mean) / self.pixel_std
+        h, w = x.shape[-2:]
+        S = self.image_encoder.img_size
+        return torch.nn.functional.pad(x, (0, S - w, 0, S - h))

@@ -16,11 +16,40 @@
 #ifndef ANYREF_SAM_H_
 #define ANYREF_SAM_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
 extern "C" {
 #endif
+
+
+/* Shape of the ViT image encoder (arguments of _build_sam, build_sam.py:56-88). */
+typedef struct SamEncoderShape {
+  int embed_dim;          /* 1280 for ViT-H */
+  int depth;              /* 32 */
+  int heads;              /* 16 (head_dim must be 80) */
+  int mlp_dim;            /* embed_dim * mlp_ratio = 5120 */
+  int img;                /* 1024 */
+  int patch;              /* 16 */
+  int window;             /* 14 */
+  int out_chans;          /* 256 */
+  int fmt;                /* tensor-core operand format: 0 fp16, 1 bf16 */
+  unsigned long long global_mask; /* bit i set <=> block i uses global attention (global_attn_indexes) */
+  int tap_block;          /* test hook: copy the fp32 residual stream after this block to tap_out (-1 = off) */
+  float* tap_out;         /* device [B*64*64, embed_dim] fp32 or NULL */
+} SamEncoderShape;
+
+/* Shape of the mask decoder (mask_decoder.py:17-73, transformer.py:16-60). */
+typedef struct SamDecoderShape {
+  int C;                  /* transformer_dim = 256 */
+  int heads;              /* 8 */
+  int depth;              /* 2 */
+  int mlp_dim;            /* 2048 */
+  int num_mask_tokens;    /* num_multimask_outputs + 1 = 4 */
+  int iou_hidden;         /* 256 */
+  int grid;               /* image embedding size = 64 */
+} SamDecoderShape;
 
 /* Text of the last error raised on the calling thread ("" if none). */
 const char* sam_last_error(void);
@@ -96,6 +125,55 @@ int sam_attn_window(const void* qkv, const void* bias_op, const void* rel_tab, v
  */
 int sam_attn_global(const void* qkv, const void* rh_rev, const void* rw_rev, void* out, int B, int E, int heads,
                     int fmt, void* stream);
+
+/*
+ * ImageEncoderViT.forward (image_encoder.py:110-125): images [B,3,1024,1024] (in_fmt 0/1/2) -> out [B,256,64,64]
+ * (out_fmt 0/1/2).  One call enqueues the whole encoder (patch-embed GEMM, 32 x {LN, QKV GEMM, fused attention,
+ * proj GEMM + residual, LN, MLP GEMMs with GELU / residual epilogues}, neck).
+ *   w16 / w32 : weight blobs in the layout documented in csrc/encoder.cpp (operand-format matrices / fp32 vectors);
+ *               sizes from sam_encoder_w16_elems / sam_encoder_w32_elems; packed by segment_anything/_pack.py
+ *   workspace : device scratch of at least sam_encoder_workspace_bytes(shape, B) bytes, 1024-byte aligned
+ */
+size_t sam_encoder_w16_elems(const SamEncoderShape* shape);
+size_t sam_encoder_w32_elems(const SamEncoderShape* shape);
+size_t sam_encoder_workspace_bytes(const SamEncoderShape* shape, int B);
+int sam_encoder_forward(const SamEncoderShape* shape, const void* w16, const float* w32, const void* images,
+                        int in_fmt, int B, void* out, int out_fmt, void* workspace, size_t workspace_bytes,
+                        void* stream);
+
+/*
+ * MaskDecoder.forward / predict_masks (mask_decoder.py:75-179) incl. TwoWayTransformer (transformer.py:62-106) for n
+ * prompts in one call.  Prompt p uses image embedding img_index[p] (img_index == NULL: all prompts use image 0, the
+ * reference's per-image call, model/anyref.py:807).
+ *   weights          fp32 blob, state_dict order of mask_decoder.* with the two ConvTranspose2d weights rearranged
+ *                    (see csrc/decoder.cu carve_weights); size from sam_decoder_weight_elems
+ *   image_embeddings [Bimg, C, g, g] emb_fmt;  image_pe [1, C, g, g] pe_fmt
+ *   sparse           [n, k, C] sparse_fmt (the [SEG] embeddings; tokens = [iou, mask x4, sparse...])
+ *   dense_vec        [C] (no_mask_embed broadcast, prompt_encoder.py:181-184) or NULL;
+ *   dense_full       [n, C, g, g] or NULL (mask prompts); both in dense_fmt
+ *   masks            [n, num_mask_tokens, 4g, 4g] out_fmt -- ALL mask tokens (caller slices [0:1] or [1:], :106-111)
+ *   iou              [n, num_mask_tokens] out_fmt
+ */
+size_t sam_decoder_weight_elems(const SamDecoderShape* shape);
+size_t sam_decoder_workspace_bytes(const SamDecoderShape* shape, int n, int k);
+int sam_decoder_forward(const SamDecoderShape* shape, const float* weights, const void* image_embeddings, int emb_fmt,
+                        const int* img_index, const void* image_pe, int pe_fmt, const void* sparse, int sparse_fmt,
+                        int n, int k, const void* dense_vec, const void* dense_full, int dense_fmt, void* masks,
+                        void* iou, int out_fmt, void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Sam.postprocess_masks (sam.py:159-172) fused: bilinear L x L -> S x S, crop [:h_in, :w_in], bilinear -> H x W, both
+ * align_corners=False, no antialias.  low [num_masks, L, L] (low_fmt); logits fp32 [num_masks, H, W] and/or binary
+ * uint8 [num_masks, H, W] = logits > threshold (Sam.mask_threshold, sam.py:19).  Either output may be NULL.
+ */
+int sam_postprocess_masks(const void* low, int low_fmt, int num_masks, int L, int S, int h_in, int w_in, int H, int W,
+                          float* logits, unsigned char* binary, float threshold, void* stream);
+
+/*
+ * PromptEncoder.get_dense_pe (prompt_encoder.py:67-76; PositionEmbeddingRandom :203-219): gauss fp32 [2, C/2]
+ * (positional_encoding_gaussian_matrix) -> out [1, C, g, g] in out_fmt.
+ */
+int sam_dense_pe(const float* gauss, void* out, int out_fmt, int C, int g, void* stream);
 
 #ifdef __cplusplus
 }
