@@ -57,11 +57,18 @@ _PROTOS = {
                             c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p],
     "sam_postprocess_masks": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                               c_float, c_void_p],
+    "sam_launch_count": [],
+    "sam_profile_enable": [c_int],
+    "sam_profile_reset": [],
+    "sam_profile_collect": [],
+    "sam_profile_get": [c_int, C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.POINTER(C.c_double),
+                        C.POINTER(C.c_double)],
     "sam_dense_pe": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
 }
 _RESTYPES = {"sam_last_error": c_char_p, "sam_encoder_w16_elems": c_size_t, "sam_encoder_w32_elems": c_size_t,
              "sam_encoder_workspace_bytes": c_size_t, "sam_decoder_weight_elems": c_size_t,
-             "sam_decoder_workspace_bytes": c_size_t}
+             "sam_decoder_workspace_bytes": c_size_t, "sam_launch_count": C.c_longlong, "sam_profile_enable": None,
+             "sam_profile_reset": None, "sam_profile_get": None}
 
 
 def exported_symbols() -> list[str]:
@@ -117,3 +124,30 @@ def fmt_of(dtype) -> int:
     if dtype == torch.float32:
         return FMT_F32
     raise TypeError(f"unsupported dtype {dtype}")
+
+
+KERNEL_CLASSES = ("gemm", "attn_window", "attn_global", "layernorm", "layout", "decoder", "postprocess")
+
+
+def launch_count() -> int:
+    return int(load().sam_launch_count())
+
+
+def profile_enable(on: bool) -> None:
+    load().sam_profile_enable(1 if on else 0)
+
+
+def profile_reset() -> None:
+    load().sam_profile_reset()
+
+
+def profile_read() -> dict:
+    """Synchronises the recorded event pairs and returns {class: {ms, launches, flops, bytes}} since the last reset."""
+    lib = load()
+    check(lib.sam_profile_collect(), "sam_profile_collect")
+    out = {}
+    for i, name in enumerate(KERNEL_CLASSES):
+        ms, n, fl, by = C.c_double(), C.c_longlong(), C.c_double(), C.c_double()
+        lib.sam_profile_get(i, C.byref(ms), C.byref(n), C.byref(fl), C.byref(by))
+        out[name] = {"ms": ms.value, "launches": n.value, "flops": fl.value, "bytes": by.value}
+    return out

@@ -353,6 +353,9 @@ int samk_attn_global(const void* qkv, const void* rh_rev, const void* rw_rev, vo
   }
   const float scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
   const int grid = B * heads * (G * G / BQ);
+  const double bh = static_cast<double>(B) * heads;
+  samhost::LaunchScope scope(samhost::KC_ATTN_GLOBAL, stream, bh * (4.0 * 4096 * 4096 * 80 + 4.0 * 4096 * 64 * 80),
+                             static_cast<double>(B) * 4096 * E * 2 * 4);
   glob_attn_kernel<<<grid, kThreads, kSmemBytes, stream>>>(maps, static_cast<const uint16_t*>(rh_rev),
                                                             static_cast<const uint16_t*>(rw_rev),
                                                             static_cast<uint16_t*>(out), E, heads, fmt, scale_log2e);

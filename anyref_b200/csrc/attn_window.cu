@@ -372,6 +372,10 @@ int samk_attn_window(const void* qkv, const void* bias_op, const void* rel_tab, 
   }
   const float scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
   const int grid = B * 25 * heads * 2;
+  // algorithmic work per (window, head): QK^T + PV over 196 x 196 x 80 and the two rel-pos products (196 x 14 x 80 x 2)
+  const double wh = static_cast<double>(B) * 25 * heads;
+  samhost::LaunchScope scope(samhost::KC_ATTN_WINDOW, stream, wh * (4.0 * 196 * 196 * 80 + 4.0 * 196 * 14 * 80),
+                             static_cast<double>(B) * 4096 * E * 2 * 4);
   win_attn_kernel<<<grid, kThreads, kSmemBytes, stream>>>(maps, static_cast<const uint16_t*>(bias_op),
                                                            static_cast<const uint16_t*>(rel_tab),
                                                            static_cast<uint16_t*>(out), E, heads, fmt, scale_log2e);

@@ -94,4 +94,12 @@ int sam_dense_pe(const float* gauss, void* out, int out_fmt, int C, int g, void*
   return samk_dense_pe(gauss, out, out_fmt, C, g, S(stream));
 }
 
+long long sam_launch_count(void) { return samhost::launch_count(); }
+void sam_profile_enable(int on) { samhost::profile_enable(on); }
+void sam_profile_reset(void) { samhost::profile_reset(); }
+int sam_profile_collect(void) { return samhost::profile_collect(); }
+void sam_profile_get(int cls, double* ms, long long* launches, double* flops, double* bytes) {
+  samhost::profile_get(cls, ms, launches, flops, bytes);
+}
+
 }  // extern "C"

@@ -541,6 +541,7 @@ int launch_linear(const float* X, int ldx, const float* X2, int ldx2, int x2_mod
   SAM_REQUIRE(ldx % 4 == 0 && ldy % 4 == 0 && (!X2 || ldx2 % 4 == 0) && (!R || ldr % 4 == 0), "dec_linear: ld %% 4");
   LinArgs a{X, ldx, X2, ldx2, x2_mod > 0 ? x2_mod : M, W, b, R, ldr, Y, ldy, M, N, K, act};
   dim3 grid((M + LBM - 1) / LBM, N / LBN);
+  samhost::LaunchScope scope(samhost::KC_DECODER, st, 2.0 * M * N * K);
   dec_linear_kernel<<<grid, 256, 0, st>>>(a);
   SAM_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -690,6 +691,7 @@ int samk_decoder_forward(const SamDecoderShape& s, const float* blob, const void
   // ---- prologue (mask_decoder.py:126-149, transformer.py:82-84)
   {
     dim3 grid(HW / 32, C / 32, n), blk(32, 8);
+    samhost::LaunchScope scope(samhost::KC_DECODER, st, 0.0, 0.0, 3);
     nchw_to_tokens_kernel<<<grid, blk, 0, st>>>(image_embeddings, emb_fmt, img_index, dense_vec, dense_full, dense_fmt,
                                                 keys, C, HW);
     dim3 grid1(HW / 32, C / 32, 1);
@@ -723,6 +725,7 @@ int samk_decoder_forward(const SamDecoderShape& s, const float* blob, const void
     LIN(keys, C, pe_t, C, HW, a.kw, a.kb, nullptr, 0, kbuf, Ci, MK, Ci, C, 0);
     LIN(keys, C, nullptr, 0, 0, a.vw, a.vb, nullptr, 0, vbuf, Ci, MK, Ci, C, 0);
     dim3 grid(s.heads, n, (T + TQ - 1) / TQ);
+    samhost::LaunchScope scope(samhost::KC_DECODER, st, 4.0 * n * T * HW * Ci);
     dec_attn_t2i_kernel<<<grid, 256, t2i_smem, st>>>(tq, kbuf, vbuf, ta, T, HW, Ci, sc_cross);
     SAM_CHECK_CUDA(cudaGetLastError());
     LIN(ta, Ci, nullptr, 0, 0, a.ow, a.ob, qry, C, tb, C, MT, C, Ci, 0);
@@ -739,6 +742,7 @@ int samk_decoder_forward(const SamDecoderShape& s, const float* blob, const void
     LIN(src, C, pe, C, MT, L.self_attn.qw, L.self_attn.qb, nullptr, 0, tq, C, MT, C, C, 0);
     LIN(src, C, pe, C, MT, L.self_attn.kw, L.self_attn.kb, nullptr, 0, tk, C, MT, C, C, 0);
     LIN(src, C, nullptr, 0, 0, L.self_attn.vw, L.self_attn.vb, nullptr, 0, tv, C, MT, C, C, 0);
+    samhost::LaunchScope scope_sa(samhost::KC_DECODER, st, 4.0 * n * T * T * C);
     dec_self_attn_kernel<<<n, 256, (3 * T * C + s.heads * T * T) * sizeof(float), st>>>(tq, tk, tv, ta, T, C, s.heads,
                                                                                         sc_self);
     SAM_CHECK_CUDA(cudaGetLastError());
@@ -756,6 +760,7 @@ int samk_decoder_forward(const SamDecoderShape& s, const float* blob, const void
     LIN(qry, C, nullptr, 0, 0, L.i2t.vw, L.i2t.vb, nullptr, 0, tv, Ci, MT, Ci, C, 0);
     {
       dim3 grid(HW / 32, n);
+      samhost::LaunchScope scope(samhost::KC_DECODER, st, 4.0 * n * T * HW * Ci);
       dec_attn_i2t_kernel<<<grid, 256, 0, st>>>(qbuf, tk, tv, qbuf, T, HW, Ci, s.heads, sc_cross);
       SAM_CHECK_CUDA(cudaGetLastError());
     }
@@ -773,11 +778,13 @@ int samk_decoder_forward(const SamDecoderShape& s, const float* blob, const void
     h.nm = nm; h.C = C; h.hidden_iou = s.iou_hidden; h.out_hyper = C / 8; h.T = T;
     h.hs = qry; h.hyper = hyper; h.iou = iou; h.iou_fmt = out_fmt;
     dim3 grid(nm + 1, n);
+    samhost::LaunchScope scope(samhost::KC_DECODER, st, 2.0 * n * (nm * (2.0 * C * C + C * C / 8) + 2.0 * C * C));
     dec_hyper_kernel<<<grid, 256, 0, st>>>(h);
     SAM_CHECK_CUDA(cudaGetLastError());
   }
   // upscaling + mask product
   LIN(keys, C, nullptr, 0, 0, w.up0w, w.up0b, nullptr, 0, tmp, C, MK, C, C, 0);
+  samhost::LaunchScope scope_up(samhost::KC_DECODER, st, 2.0 * MK * 4 * (4.0 * (C / 8) * (C / 4) + 4.0 * nm * (C / 8)));
   dec_upscale_tail_kernel<<<static_cast<unsigned>((size_t)MK * 4 / 256), 256, 0, st>>>(
       tmp, w.upln_w, w.upln_b, w.up1w, w.up1b, hyper, masks, out_fmt, g, nm);
   SAM_CHECK_CUDA(cudaGetLastError());

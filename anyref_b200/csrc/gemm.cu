@@ -11,6 +11,7 @@
 //
 // Operands are bf16 or fp16 (runtime `fmt`, same tensor-core rate); accumulation and epilogue math are fp32.
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "host_common.h"
 #include "kernels.h"
@@ -223,6 +224,10 @@ int launch_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, in
   if (max_ctas > 0 && max_ctas < cap) cap = max_ctas;
   if (grid > cap) grid = cap;
   const uint32_t idesc = ptx::make_idesc((uint32_t)fmt, BM, BN, 0, 0);
+  const double out_b = (ep.out_fmt == 2) ? 4.0 : 2.0;
+  samhost::LaunchScope scope(samhost::KC_GEMM, stream, 2.0 * M * N * K,
+                             2.0 * (static_cast<double>(M) * K + static_cast<double>(N) * K) +
+                                 out_b * M * N + (ep.res ? 4.0 * M * N : 0.0));
   gemm_tn_kernel<BN><<<grid, kGemmThreads, Cfg::kSmem, stream>>>(tmA, tmB, ep, M, N, K, idesc);
   SAM_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -241,6 +246,12 @@ int samk_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, int 
               "gemm: operands must be 16-byte aligned");
   SAM_REQUIRE(ep.ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(ep.out) & 15) == 0, "gemm: output must be 16B aligned");
   if (ep.res) SAM_REQUIRE(ep.res_mod > 0 && ep.ldr % 4 == 0, "gemm: residual needs res_mod>0, ldr%%4==0");
+  // big problems go to the 2-CTA kernel (gemm2.cu); it declines (-1) epilogues it does not implement
+  static const bool force_v1 = getenv("SAM_GEMM_V1") != nullptr;
+  if (!force_v1) {
+    const int rc2 = samk_gemm2(A, lda, W, ldw, M, N, K, fmt, ep, stream);
+    if (rc2 >= 0) return rc2;
+  }
   if (N % 256 == 0 || N > 256) return launch_gemm<256>(A, lda, W, ldw, M, N, K, fmt, ep, 0, stream);
   return launch_gemm<128>(A, lda, W, ldw, M, N, K, fmt, ep, 0, stream);
 }

@@ -1,0 +1,404 @@
+// 2-CTA (cta_group::2) tcgen05 GEMM for the big encoder linears:   C[M,N] = epilogue( A[M,K] * W[N,K]^T )
+//
+// A CTA pair (one cluster = the two SMs of a TPC) owns a 256 x 256 output tile.  CTA r loads A rows [r*128, +128) and
+// W rows [r*128, +128) of the tile; the leader CTA issues tcgen05.mma.cta_group::2 (M = 256, N = 256, K = 16), which
+// reads both halves of W from the two shared memories -- each W byte is fetched from L2 and written to smem once per
+// pair -- and leaves each CTA's 128 x 256 fp32 accumulator in its own TMEM.
+//
+// Warp roles (320 threads):  warp 0 TMA producer | warp 1 MMA issuer (leader CTA) + TMEM alloc | warps 2..9 epilogue.
+// Epilogue: tcgen05.ld -> +bias -> GELU -> round -> 128B-swizzled smem staging -> TMA bulk tensor store (coalesced,
+// OOB-clipped, no LSU store traffic); the in-place fp32 residual add  x += A.W^T + b  (image_encoder.py:190-191) is a
+// TMA reduce-add (cp.reduce.async.bulk.tensor ... .add), so the residual stream is never loaded by the SM.
+// Two TMEM accumulator stages (2 x 256 columns) let the epilogue of tile i overlap the main loop of tile i+1.
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "host_common.h"
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace {
+
+constexpr int BM2 = 128;          // rows per CTA (256 per pair)
+constexpr int BN2 = 256;          // tile width
+constexpr int BK2 = 64;
+constexpr int kStages2 = 5;
+constexpr int kStageA2 = BM2 * BK2 * 2;         // 16 KB
+constexpr int kStageB2 = (BN2 / 2) * BK2 * 2;   // 16 KB (this CTA's half of W)
+constexpr int kStage2 = kStageA2 + kStageB2;
+constexpr int kEpiWarps = 8;
+constexpr int kStagingPerWarp = 2 * 4096;       // double-buffered 32 x 128 B boxes
+constexpr int kThreads2 = 64 + kEpiWarps * 32;
+constexpr int kSmem2 = kStages2 * kStage2 + kEpiWarps * kStagingPerWarp + 1024 /*align*/ + 256 /*barriers*/;
+constexpr uint32_t kTmemCols2 = 512;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 ra;\n"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n"
+      "}\n" ::"r"(ptx::smem_u32(bar)),
+      "r"(cta)
+      : "memory");
+}
+// TMA load into THIS CTA's smem; completion bytes go to the LEADER CTA's mbarrier (peer bit cleared).
+__device__ __forceinline__ void tma_load_2d_cg2(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(ptx::smem_u32(dst)), "l"(m), "r"(ptx::smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void mma_f16_ss_cg2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the same-offset mbarrier of both CTAs once all previously issued MMAs have completed
+__device__ __forceinline__ void mma_commit_cg2(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          ptx::smem_u32(bar)),
+      "h"(static_cast<uint16_t>(3))
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_cg2(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ptx::smem_u32(dst_smem)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_cg2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(m),
+               "r"(ptx::smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(m),
+               "r"(ptx::smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+
+// exact-erf GELU (common.py:18) with erf from Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7, far below the 16-bit
+// rounding of the stored activation); two MUFU ops + 8 FMAs instead of erff's branchy polynomial
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = p * t * exp2f(-1.4426950408889634f * z * z);   // 1 - erf(z)
+  const float erf_abs = 1.0f - e;
+  const float erf_x = copysignf(erf_abs, x);
+  return 0.5f * x * (1.0f + erf_x);
+}
+
+struct Gemm2Params {
+  const float* bias;
+  int act;         // 0 none, 1 GELU
+  int out_mode;    // 0: 16-bit store, 1: fp32 store, 2: fp32 reduce-add (in-place residual)
+  int out_fmt;     // SamFmt of the output
+  int M, N, K;
+  uint32_t idesc;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
+gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+             const __grid_constant__ CUtensorMap tmC, const Gemm2Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* staging = smem + kStages2 * kStage2;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + kEpiWarps * kStagingPerWarp);
+  uint64_t* empty_bar = full_bar + kStages2;
+  uint64_t* acc_full = empty_bar + kStages2;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = (rank == 0);
+  const int m_tiles = (p.M + 2 * BM2 - 1) / (2 * BM2);
+  const int n_tiles = (p.N + BN2 - 1) / BN2;
+  const int num_tiles = m_tiles * n_tiles;
+  const int num_kb = (p.K + BK2 - 1) / BK2;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+    ptx::prefetch_tmap(&tmC);
+    for (int s = 0; s < kStages2; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);    // leader's arrive.expect_tx (bytes of BOTH CTAs' loads)
+      ptx::mbar_init(&empty_bar[s], 1);   // multicast tcgen05.commit
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&acc_full[s], 1);                  // multicast tcgen05.commit
+      ptx::mbar_init(&acc_empty[s], 2 * kEpiWarps);     // epilogue warps of BOTH CTAs (used in the leader only)
+    }
+    ptx::fence_mbar_init();
+  }
+  cluster_sync();   // barriers of both CTAs initialised before anyone touches a remote one
+  if (warp == 1) tmem_alloc_cg2(tmem_slot, kTmemCols2);
+  ptx::tc_fence_before();
+  cluster_sync();   // both TMEM allocations done before the leader's first MMA writes the peer's TMEM
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (one lane per CTA)
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+        const int row_a = m_blk * (2 * BM2) + static_cast<int>(rank) * BM2;
+        const int row_b = n_blk * BN2 + static_cast<int>(rank) * (BN2 / 2);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem + s * kStage2;
+          uint8_t* sb = sa + kStageA2;
+          // the peer's bytes may land before this expect_tx (tx-count is signed); they cannot land in an earlier
+          // phase because the peer waited for the commit that followed the MMAs of that phase
+          if (leader) ptx::mbar_expect_tx(&full_bar[s], 2 * kStage2);
+          tma_load_2d_cg2(sa, &tmA, &full_bar[s], kb * BK2, row_a);
+          tma_load_2d_cg2(sb, &tmB, &full_bar[s], kb * BK2, row_b);
+          if (++s == kStages2) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (leader && lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      int as = 0;
+      uint32_t aph = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        ptx::mbar_wait(&acc_empty[as], aph ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN2);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(&full_bar[s], ph);
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(smem + s * kStage2);
+          const uint32_t sb = sa + kStageA2;
+          const uint64_t da = ptx::make_smem_desc(sa, 16, 1024, ptx::kSwz128);
+          const uint64_t db = ptx::make_smem_desc(sb, 16, 1024, ptx::kSwz128);
+#pragma unroll
+          for (int k = 0; k < BK2 / 16; ++k) mma_f16_ss_cg2(d_tmem, da + 2 * k, db + 2 * k, p.idesc, (kb | k) != 0);
+          mma_commit_cg2(&empty_bar[s]);
+          if (++s == kStages2) { s = 0; ph ^= 1; }
+        }
+        mma_commit_cg2(&acc_full[as]);
+        if (++as == 2) { as = 0; aph ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (8 warps per CTA)
+    const int ew = warp - 2;
+    const int quad = warp & 3;        // TMEM lane quadrant this warp may access
+    const int half = ew >> 2;         // column half [half*128, +128) of the tile
+    uint8_t* stg = staging + ew * kStagingPerWarp;
+    int buf = 0;
+    int as = 0;
+    uint32_t aph = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      ptx::mbar_wait(&acc_full[as], aph);
+      ptx::tc_fence_after();
+      const int row0 = m_blk * (2 * BM2) + static_cast<int>(rank) * BM2 + quad * 32;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * BN2 + half * 128);
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        const int col0 = n_blk * BN2 + half * 128 + c * 32;
+        uint32_t v[32];
+        ptx::tmem_ld_32x32b_x32(t_row + c * 32, v);
+        ptx::tmem_ld_wait();
+        if (c == 3) {
+          // accumulator stage fully read by this warp -> hand it back to the MMA issuer early
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(&acc_empty[as], 0);
+        }
+        // tile overhang (all conditions are warp-uniform); TMA clips partially out-of-range boxes itself
+        const bool valid = row0 < p.M && col0 < p.N;
+        const bool pair_valid = row0 < p.M && (col0 - (c & 1) * 32) < p.N;   // 16-bit mode: chunks c-1 | c share a box
+        if (p.out_mode == 0 ? !pair_valid : !valid) continue;
+        float f[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+        if (p.bias && valid) {
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (col0 + 4 * i < p.N) {
+              const float4 b = __ldg(b4 + i);
+              f[4 * i + 0] += b.x; f[4 * i + 1] += b.y; f[4 * i + 2] += b.z; f[4 * i + 3] += b.w;
+            }
+          }
+        }
+        if (p.act == 1) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = gelu_fast(f[i]);
+        }
+        if (p.out_mode == 0) {
+          // 16-bit output: two 32-column chunks share one 32 x 64 (128 B rows) staging box
+          if ((c & 1) == 0) {
+            if (lane == 0) bulk_wait_read<1>();
+            __syncwarp();
+          }
+          uint8_t* sb = stg + buf * 4096 + lane * 128;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 u;
+            u.x = ptx::pack2(f[8 * i + 0], f[8 * i + 1], p.out_fmt);
+            u.y = ptx::pack2(f[8 * i + 2], f[8 * i + 3], p.out_fmt);
+            u.z = ptx::pack2(f[8 * i + 4], f[8 * i + 5], p.out_fmt);
+            u.w = ptx::pack2(f[8 * i + 6], f[8 * i + 7], p.out_fmt);
+            const int chunk = (c & 1) * 4 + i;
+            *reinterpret_cast<uint4*>(sb + ((chunk ^ (lane & 7)) << 4)) = u;
+          }
+          if ((c & 1) == 1) {
+            ptx::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmC, stg + buf * 4096, col0 - 32, row0);
+              bulk_commit();
+            }
+            buf ^= 1;
+          }
+        } else {
+          if (lane == 0) bulk_wait_read<1>();
+          __syncwarp();
+          uint8_t* sb = stg + buf * 4096 + lane * 128;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            *reinterpret_cast<float4*>(sb + ((i ^ (lane & 7)) << 4)) =
+                make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (p.out_mode == 2)
+              tma_reduce_add_2d(&tmC, stg + buf * 4096, col0, row0);
+            else
+              tma_store_2d(&tmC, stg + buf * 4096, col0, row0);
+            bulk_commit();
+          }
+          buf ^= 1;
+        }
+      }
+      if (++as == 2) { as = 0; aph ^= 1; }
+    }
+    if (lane == 0) bulk_wait_read<0>();   // staging smem must outlive the bulk reads
+  }
+
+  ptx::tc_fence_before();
+  cluster_sync();   // nobody exits (or frees TMEM) while the peer may still touch this CTA's smem / TMEM / barriers
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    tmem_dealloc_cg2(tmem_base, kTmemCols2);
+  }
+}
+
+}  // namespace
+
+// Returns -1 if this kernel does not cover the request (caller falls back to the 1-CTA kernel), else 0 / error code.
+int samk_gemm2(const void* A, int lda, const void* W, int ldw, int M, int N, int K, int fmt, const GemmEpilogue& ep,
+               cudaStream_t stream) {
+  int out_mode;
+  if (ep.out_fmt != SAM_F32) {
+    if (ep.res) return -1;
+    out_mode = 0;
+  } else if (!ep.res) {
+    out_mode = 1;
+  } else if (ep.res == static_cast<const float*>(ep.out) && ep.res_mod == M && ep.ldr == ep.ldo) {
+    out_mode = 2;
+  } else {
+    return -1;
+  }
+  if (N % 8 != 0 || M < 1) return -1;
+  CUtensorMap tmA, tmB, tmC;
+  const int is_bf16 = (fmt == 1);
+  int rc = samhost::encode_tmap_2d(&tmA, 2, is_bf16, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, BK2, BM2, 3);
+  if (rc) return rc;
+  rc = samhost::encode_tmap_2d(&tmB, 2, is_bf16, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw * 2, BK2, BN2 / 2, 3);
+  if (rc) return rc;
+  if (out_mode == 0)
+    rc = samhost::encode_tmap_2d(&tmC, 2, ep.out_fmt == SAM_BF16, ep.out, (uint64_t)N, (uint64_t)M, (uint64_t)ep.ldo * 2, 64, 32, 3);
+  else
+    rc = samhost::encode_tmap_2d(&tmC, 4, 0, ep.out, (uint64_t)N, (uint64_t)M, (uint64_t)ep.ldo * 4, 32, 32, 3);
+  if (rc) return rc;
+  static bool attr_done = false;
+  if (!attr_done) {
+    SAM_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2));
+    attr_done = true;
+  }
+  Gemm2Params p;
+  p.bias = ep.bias;
+  p.act = ep.act;
+  p.out_mode = out_mode;
+  p.out_fmt = ep.out_fmt;
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.idesc = ptx::make_idesc((uint32_t)fmt, 2 * BM2, BN2, 0, 0);
+  const int m_tiles = (M + 2 * BM2 - 1) / (2 * BM2), n_tiles = (N + BN2 - 1) / BN2;
+  int clusters = m_tiles * n_tiles;
+  // persistent kernel: never launch more CTA pairs than can be co-resident (GPCs with an odd number of free SMs make
+  // this smaller than sm_count / 2), otherwise the late pairs serialise behind the early ones
+  static int max_clusters = 0;
+  if (max_clusters == 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(samhost::sm_count());
+    cfg.blockDim = dim3(kThreads2);
+    cfg.dynamicSmemBytes = kSmem2;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, gemm2_kernel, &cfg) != cudaSuccess || n <= 0) {
+      (void)cudaGetLastError();
+      n = samhost::sm_count() / 2;
+    }
+    max_clusters = n;
+    if (getenv("SAM_GEMM_DEBUG")) fprintf(stderr, "[anyref_sam] gemm2: max co-resident CTA pairs = %d\n", n);
+  }
+  if (clusters > max_clusters) clusters = max_clusters;
+  const double out_b = (ep.out_fmt == 2) ? 4.0 : 2.0;
+  samhost::LaunchScope scope(samhost::KC_GEMM, stream, 2.0 * M * N * K,
+                             2.0 * (static_cast<double>(M) * K + static_cast<double>(N) * K) + out_b * M * N +
+                                 (ep.res ? 4.0 * M * N : 0.0));
+  gemm2_kernel<<<2 * clusters, kThreads2, kSmem2, stream>>>(tmA, tmB, tmC, p);
+  SAM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

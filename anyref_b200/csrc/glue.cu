@@ -198,6 +198,8 @@ int samk_layernorm_rows(const float* x, int ldx, const float* res, int ldr, cons
   SAM_REQUIRE(ldx % 4 == 0 && ldo % 4 == 0 && (!res || ldr % 4 == 0), "layernorm: leading dimensions must be multiples of 4");
   SAM_REQUIRE(M > 0, "layernorm: empty input");
   SAM_REQUIRE(!normalize || (gamma && beta), "layernorm: affine parameters missing");
+  samhost::LaunchScope scope(samhost::KC_LAYERNORM, stream, 0.0,
+                             static_cast<double>(M) * C * ((res ? 8.0 : 4.0) + (out_fmt == 2 ? 4.0 : 2.0)));
   layernorm_rows_kernel<<<(M + 7) / 8, 256, 0, stream>>>(x, ldx, res, ldr, gamma, beta, eps, out, ldo, out_fmt, M, C,
                                                          normalize);
   SAM_CHECK_CUDA(cudaGetLastError());
@@ -208,6 +210,8 @@ int samk_patch_im2col(const void* img, int in_fmt, void* out, int out_fmt, int B
   SAM_REQUIRE(p % 8 == 0 && S % p == 0, "patch_im2col: patch %d / image %d unsupported", p, S);
   SAM_REQUIRE(out_fmt == 0 || out_fmt == 1, "patch_im2col: output must be fp16/bf16");
   const size_t total = static_cast<size_t>(B) * 3 * S * (S / p) * (p / 8);
+  samhost::LaunchScope scope(samhost::KC_LAYOUT, stream, 0.0,
+                             static_cast<double>(B) * 3 * S * S * ((in_fmt == 2 ? 4.0 : 2.0) + 2.0));
   patch_im2col_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
       img, in_fmt, static_cast<uint16_t*>(out), out_fmt, B, S, p);
   SAM_CHECK_CUDA(cudaGetLastError());
@@ -217,6 +221,7 @@ int samk_patch_im2col(const void* img, int in_fmt, void* out, int out_fmt, int B
 int samk_im2col3x3(const void* in, void* out, int B, int g, int C, cudaStream_t stream) {
   SAM_REQUIRE(C % 8 == 0, "im2col3x3: C must be a multiple of 8");
   const size_t total = static_cast<size_t>(B) * g * g * 9 * (C / 8);
+  samhost::LaunchScope scope(samhost::KC_LAYOUT, stream, 0.0, static_cast<double>(B) * g * g * C * 2.0 * 10);
   im2col3x3_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
       static_cast<const uint16_t*>(in), static_cast<uint16_t*>(out), B, g, C);
   SAM_CHECK_CUDA(cudaGetLastError());
@@ -227,6 +232,8 @@ int samk_ln_nhwc_to_nchw(const float* x, const float* gamma, const float* beta, 
                          int B, int tokens_per_img, int C, cudaStream_t stream) {
   SAM_REQUIRE(C <= 256 && tokens_per_img % 32 == 0, "ln_nhwc_to_nchw: C<=256 and tokens%%32==0 required");
   const size_t blocks = static_cast<size_t>(B) * tokens_per_img / 32;
+  samhost::LaunchScope scope(samhost::KC_LAYERNORM, stream, 0.0,
+                             static_cast<double>(B) * tokens_per_img * C * (4.0 + (out_fmt == 2 ? 4.0 : 2.0)));
   ln_nhwc_to_nchw_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(x, gamma, beta, eps, out, out_fmt,
                                                                            tokens_per_img, C);
   SAM_CHECK_CUDA(cudaGetLastError());

@@ -4,6 +4,10 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
+#include <mutex>
+#include <vector>
+
 namespace samhost {
 
 static thread_local char g_err[1024] = "";
@@ -78,6 +82,82 @@ int sm_count() {
   if (cudaGetDevice(&dev) != cudaSuccess) return 148;
   if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
   return n;
+}
+
+// ------------------------------------------------------------------------------------------------- launch accounting
+namespace {
+std::atomic<long long> g_launches{0};
+std::atomic<int> g_profile_on{0};
+struct Rec {
+  cudaEvent_t a, b;
+  int cls;
+  double flops, bytes;
+  int launches;
+};
+std::mutex g_mu;
+std::vector<Rec> g_recs;      // event pool; entries [0, g_used) are live
+size_t g_used = 0;
+struct Tot {
+  double ms = 0, flops = 0, bytes = 0;
+  long long launches = 0;
+} g_tot[KC_COUNT];
+}  // namespace
+
+LaunchScope::LaunchScope(int cls, cudaStream_t stream, double flops, double bytes, int launches)
+    : slot_(-1), stream_(stream) {
+  g_launches.fetch_add(launches, std::memory_order_relaxed);
+  if (!g_profile_on.load(std::memory_order_relaxed)) return;
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_used == g_recs.size()) {
+    Rec r{};
+    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+    g_recs.push_back(r);
+  }
+  Rec& r = g_recs[g_used];
+  r.cls = cls;
+  r.flops = flops;
+  r.bytes = bytes;
+  r.launches = launches;
+  slot_ = static_cast<int>(g_used++);
+  cudaEventRecord(r.a, stream);
+}
+LaunchScope::~LaunchScope() {
+  if (slot_ < 0) return;
+  std::lock_guard<std::mutex> lk(g_mu);
+  cudaEventRecord(g_recs[slot_].b, stream_);
+}
+long long launch_count() { return g_launches.load(); }
+void profile_enable(int on) { g_profile_on.store(on ? 1 : 0); }
+int profile_collect() {
+  std::lock_guard<std::mutex> lk(g_mu);
+  for (size_t i = 0; i < g_used; ++i) {
+    Rec& r = g_recs[i];
+    cudaError_t e = cudaEventSynchronize(r.b);
+    if (e != cudaSuccess) return set_error(2, "profile_collect: %s", cudaGetErrorString(e));
+    float ms = 0.f;
+    e = cudaEventElapsedTime(&ms, r.a, r.b);
+    if (e != cudaSuccess) return set_error(2, "profile_collect: %s", cudaGetErrorString(e));
+    Tot& t = g_tot[r.cls];
+    t.ms += ms;
+    t.flops += r.flops;
+    t.bytes += r.bytes;
+    t.launches += r.launches;
+  }
+  g_used = 0;
+  return 0;
+}
+void profile_reset() {
+  std::lock_guard<std::mutex> lk(g_mu);
+  g_used = 0;
+  for (auto& t : g_tot) t = Tot();
+}
+void profile_get(int cls, double* ms, long long* launches, double* flops, double* bytes) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (cls < 0 || cls >= KC_COUNT) return;
+  *ms = g_tot[cls].ms;
+  *launches = g_tot[cls].launches;
+  *flops = g_tot[cls].flops;
+  *bytes = g_tot[cls].bytes;
 }
 
 }  // namespace samhost

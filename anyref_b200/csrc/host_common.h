@@ -34,4 +34,27 @@ int encode_tmap_nd(CUtensorMap* out, int elem_bytes, int is_bf16, const void* ba
 
 int sm_count();
 
+// ---------------------------------------------------------------------------------------------------------------
+// Launch accounting + optional per-kernel-class timing (bench.py: `gpu_launches` and the roofline leg).
+// Every kernel launch site opens a LaunchScope.  It always bumps the launch counter; when profiling is enabled it
+// also brackets the launch with a CUDA event pair on the launch stream.  profile_collect() synchronises the recorded
+// events and folds them into per-class totals (time, launches, algorithmic FLOPs and bytes as stated by the site).
+// ---------------------------------------------------------------------------------------------------------------
+enum KernelClass {
+  KC_GEMM = 0, KC_ATTN_WINDOW, KC_ATTN_GLOBAL, KC_LAYERNORM, KC_LAYOUT, KC_DECODER, KC_POSTPROCESS, KC_COUNT
+};
+struct LaunchScope {
+  LaunchScope(int cls, cudaStream_t stream, double flops = 0.0, double bytes = 0.0, int launches = 1);
+  ~LaunchScope();
+  int slot_;
+  cudaStream_t stream_;
+};
+long long launch_count();
+void profile_enable(int on);
+// Folds all recorded event pairs into the totals; returns 0 or a CUDA error code.
+int profile_collect();
+void profile_reset();
+// totals since the last reset for class `cls`
+void profile_get(int cls, double* ms, long long* launches, double* flops, double* bytes);
+
 }  // namespace samhost

@@ -25,6 +25,10 @@ struct GemmEpilogue {
 int samk_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, int K, int fmt, const GemmEpilogue& ep,
               cudaStream_t stream);
 
+// 2-CTA variant (gemm2.cu): returns -1 when it does not implement the requested epilogue (caller falls back).
+int samk_gemm2(const void* A, int lda, const void* W, int ldw, int M, int N, int K, int fmt, const GemmEpilogue& ep,
+               cudaStream_t stream);
+
 // UMMA layout probe (test-only kernel, see probe.cu).
 struct UmmaProbe {
   int N;          // MMA N (multiple of 16, <= 256); M is fixed at 128

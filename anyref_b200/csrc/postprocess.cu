@@ -4,9 +4,10 @@
 // output pixel evaluates its 4 stage-2 taps on the fly, each from 4 low-resolution taps (the 256 KB low-res mask
 // stays in L1/L2).  HBM traffic = read L*L*4 + write H*W*4 bytes per mask (the algorithmic minimum).
 //
-// Tap arithmetic follows ATen's area_pixel_compute_source_index exactly (scale = in/out in fp32,
-// src = max(0, scale*(dst+0.5)-0.5) with separately rounded multiply and subtract, i1 = i0 + (i0 < in-1)), so tap
-// INDICES are bit-exact with the reference; values agree to fp32 rounding.
+// Tap arithmetic follows ATen's area_pixel_compute_source_index (scale = in/out in fp32,
+// src = max(0, scale*(dst+0.5)-0.5) evaluated as ONE fused multiply-add, which is what both ATen's vectorised CPU
+// kernel and its CUDA kernel compile to; i1 = i0 + (i0 < in-1)), so tap INDICES are exact with the reference and
+// values agree to fp32 rounding.
 #include "host_common.h"
 #include "kernels.h"
 #include "ptx.cuh"
@@ -19,7 +20,7 @@ struct Tap {
 };
 
 __device__ __forceinline__ Tap make_tap(int dst, float scale, int in_size) {
-  const float src = fmaxf(__fsub_rn(__fmul_rn(scale, static_cast<float>(dst) + 0.5f), 0.5f), 0.0f);
+  const float src = fmaxf(fmaf(scale, static_cast<float>(dst) + 0.5f, -0.5f), 0.0f);
   Tap t;
   t.i0 = static_cast<int>(src);
   t.i1 = t.i0 + (t.i0 < in_size - 1 ? 1 : 0);
@@ -112,6 +113,10 @@ int samk_postprocess(const void* low, int low_fmt, int num_masks, int L, int S, 
   SAM_REQUIRE(num_masks <= 65535, "postprocess: at most 65535 masks per call");
   dim3 blk(64, 4);
   dim3 grid(((W + 3) / 4 + blk.x - 1) / blk.x, (H + blk.y - 1) / blk.y, num_masks);
+  samhost::LaunchScope scope(samhost::KC_POSTPROCESS, stream, 0.0,
+                             static_cast<double>(num_masks) *
+                                 (static_cast<double>(L) * L * (low_fmt == 2 ? 4.0 : 2.0) +
+                                  static_cast<double>(H) * W * ((logits ? 4.0 : 0.0) + (binary ? 1.0 : 0.0))));
   postprocess_kernel<<<grid, blk, 0, stream>>>(low, low_fmt, L, S, h_in, w_in, H, W, logits, binary, threshold);
   SAM_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -141,6 +146,7 @@ __global__ void dense_pe_kernel(const float* __restrict__ gauss, void* __restric
 
 int samk_dense_pe(const float* gauss, void* out, int out_fmt, int C, int g, cudaStream_t stream) {
   SAM_REQUIRE(C % 2 == 0 && g > 0, "dense_pe: bad shape");
+  samhost::LaunchScope scope(samhost::KC_LAYOUT, stream);
   dense_pe_kernel<<<(C * g * g + 255) / 256, 256, 0, stream>>>(gauss, out, out_fmt, C, g);
   SAM_CHECK_CUDA(cudaGetLastError());
   return 0;

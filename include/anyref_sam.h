@@ -175,6 +175,19 @@ int sam_postprocess_masks(const void* low, int low_fmt, int num_masks, int L, in
  */
 int sam_dense_pe(const float* gauss, void* out, int out_fmt, int C, int g, void* stream);
 
+/*
+ * Launch accounting and per-kernel-class timing (used by bench.py for `gpu_launches` and the roofline leg).
+ * sam_launch_count: kernels launched by this library since load.  With profiling enabled every launch is bracketed by
+ * a CUDA event pair on its stream; sam_profile_collect synchronises those events and adds them to per-class totals.
+ * Classes: 0 GEMM, 1 windowed attention, 2 global attention, 3 LayerNorm, 4 layout (im2col / dense PE), 5 mask
+ * decoder, 6 postprocess.  flops / bytes are the ALGORITHMIC work stated by each launch site.
+ */
+long long sam_launch_count(void);
+void sam_profile_enable(int on);
+void sam_profile_reset(void);
+int sam_profile_collect(void);
+void sam_profile_get(int cls, double* ms, long long* launches, double* flops, double* bytes);
+
 #ifdef __cplusplus
 }
 #endif

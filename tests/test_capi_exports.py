@@ -1,0 +1,85 @@
+"""The C-ABI library must build, load and export every symbol include/anyref_sam.h declares (no compute: no GPU here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    text = open(os.path.join(ROOT, "include", "anyref_sam.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(sam_[a-z0-9_]+)\s*\(", text)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from anyref_b200 import build
+
+    path = build.build()
+    return ctypes.CDLL(os.fspath(path))
+
+
+def test_header_declares_the_path_entry_points():
+    names = declared_functions()
+    for need in ("sam_encoder_forward", "sam_decoder_forward", "sam_postprocess_masks", "sam_dense_pe", "sam_gemm",
+                 "sam_attn_window", "sam_attn_global", "sam_layernorm", "sam_last_error"):
+        assert need in names
+
+
+def test_every_declared_symbol_is_exported(lib):
+    for name in declared_functions():
+        assert hasattr(lib, name), f"{name} declared in include/anyref_sam.h but not exported"
+
+
+def test_python_binding_covers_the_header(lib):
+    from anyref_b200 import _lib
+
+    assert set(_lib.exported_symbols()) == set(declared_functions())
+    _lib.load()
+
+
+def test_sizes_and_errors_without_gpu(lib):
+    from anyref_b200 import _lib
+
+    L = _lib.load()
+    assert L.sam_abi_version() == 1
+    enc = _lib.SamEncoderShape(embed_dim=1280, depth=32, heads=16, mlp_dim=5120, img=1024, patch=16, window=14,
+                               out_chans=256, fmt=1, global_mask=0, tap_block=-1, tap_out=None)
+    n16 = L.sam_encoder_w16_elems(ctypes.byref(enc))
+    # all encoder matrices + per-block operand bias and rel-pos slot
+    mats = 1280 * 768 + 32 * (3 * 1280 * 1280 + 1280 * 1280 + 2 * 5120 * 1280) + 256 * 1280 + 256 * 2304
+    assert n16 == mats + 32 * (3 * 1280 + 2 * 128 * 80)
+    assert L.sam_encoder_workspace_bytes(ctypes.byref(enc), 16) > 16 * 4096 * 1280 * 4
+    dec = _lib.SamDecoderShape(C=256, heads=8, depth=2, mlp_dim=2048, num_mask_tokens=4, iou_hidden=256, grid=64)
+    # reference decoder parameter count + the 3 extra copies of the first ConvTranspose bias (one per output sub-pixel)
+    assert L.sam_decoder_weight_elems(ctypes.byref(dec)) == 4058340 + 3 * 64
+    # argument validation happens before any CUDA call
+    rc = L.sam_gemm(None, 0, None, 0, 0, 0, 0, 7, None, 0, 0, None, 0, None, 0, 0, None)
+    assert rc != 0 and b"fmt" in L.sam_last_error()
+    rc = L.sam_postprocess_masks(None, 2, 0, 256, 1024, 1024, 1024, 1024, 1024, None, None, 0.0, None)
+    assert rc != 0 and b"postprocess" in L.sam_last_error()
+
+
+def test_product_path_has_no_cpu_fallback():
+    import torch
+
+    from anyref_b200.segment_anything import build_sam_from_config
+    from anyref_b200.synthetic import CONFIGS
+
+    sam = build_sam_from_config(CONFIGS["vit_tiny80"])
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        sam.image_encoder(torch.zeros(1, 3, 1024, 1024))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        sam.postprocess_masks(torch.zeros(1, 1, 256, 256), (1024, 1024), (1024, 1024))
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "anyref_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".h", ".cuh")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f

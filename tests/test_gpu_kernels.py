@@ -1,0 +1,200 @@
+"""Parity of the individual CUDA kernels (through the C ABI) against fp32 restatements of the reference ops.
+Integer work (window maps, im2col, taps) is bit-exact; floating point within the stated tolerances."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import sam_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from anyref_b200 import ops as _ops
+
+    return _ops
+
+
+def rel_fro(got, ref):
+    return ((got.float() - ref.float()).norm() / ref.float().norm()).item()
+
+
+# ------------------------------------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("dt,tol", [(torch.float16, 2e-3), (torch.bfloat16, 1e-2)])
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (300, 256, 192), (4900, 3840, 1280), (4096, 1280, 5120),
+                                   (4096, 256, 2304), (513, 480, 160), (1000, 160, 640)])
+def test_gemm_epilogues(ops, dt, tol, M, N, K):
+    torch.manual_seed(M + N + K)
+    a = (torch.randn(M, K, device=DEV) * 0.5).to(dt)
+    w = (torch.randn(N, K, device=DEV) * 0.05).to(dt)
+    bias = torch.randn(N, device=DEV)
+    ref = a.float() @ w.float().t()
+    # fp32 output: only accumulation-order differences
+    assert rel_fro(ops.gemm(a, w, out_dtype=torch.float32), ref) < 1e-5
+    # bias + exact-erf GELU, rounded to the operand format (common.py:21-26)
+    got = ops.gemm(a, w, bias=bias, act="gelu", out_dtype=dt)
+    want = F.gelu(ref + bias)
+    assert (got.float() - want).abs().max().item() <= tol * max(1.0, want.abs().max().item())
+    # in-place fp32 residual (image_encoder.py:190-191)
+    res = torch.randn(M, N, device=DEV)
+    x = res.clone()
+    ops.gemm(a, w, bias=bias, residual=x, out=x)
+    assert rel_fro(x, ref + bias + res) < 1e-5
+    # broadcast residual rows (pos_embed add, image_encoder.py:112-113)
+    pos = torch.randn(128, N, device=DEV)
+    got = ops.gemm(a, w, bias=bias, residual=pos, res_mod=128, out_dtype=torch.float32)
+    assert rel_fro(got, ref + bias + pos[torch.arange(M, device=DEV) % 128]) < 1e-5
+
+
+def test_gemm_rejects_bad_arguments(ops):
+    a = torch.zeros(64, 60, device=DEV, dtype=torch.bfloat16)
+    w = torch.zeros(64, 60, device=DEV, dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError, match="multiples of 8"):
+        ops.gemm(a, w)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.gemm(a.cpu(), w.cpu())
+
+
+@pytest.mark.parametrize("a_mode,b_mode,N,K", [(0, 0, 208, 128), (1, 1, 208, 16), (0, 2, 128, 64), (0, 3, 64, 128),
+                                               (0, 4, 80, 128), (0, 6, 96, 128)])
+def test_umma_descriptor_conventions(ops, a_mode, b_mode, N, K):
+    """Pins the shared-memory descriptor / swizzle conventions the attention kernels rely on."""
+    torch.manual_seed(0)
+    a = torch.randn(128, K, device=DEV).to(torch.bfloat16)
+    if b_mode <= 2:
+        b = torch.randn(N, K, device=DEV).to(torch.bfloat16)
+        ref = a.float() @ b.float().t()
+    else:
+        b = torch.randn(K, N, device=DEV).to(torch.bfloat16)
+        ref = a.float() @ b.float()
+    assert (ops.umma_probe(a, b, N, K, a_mode, b_mode) - ref).abs().max().item() < 1e-3
+
+
+# ------------------------------------------------------------------------------------------------------------ glue
+def test_layernorm_rows(ops):
+    torch.manual_seed(1)
+    x = torch.randn(4096 + 3, 1280, device=DEV) * 2 + 0.3
+    g = torch.rand(1280, device=DEV) + 0.5
+    b = torch.randn(1280, device=DEV) * 0.1
+    ref = F.layer_norm(x, (1280,), g, b, 1e-6)
+    assert (ops.layernorm(x, g, b, 1e-6, torch.float32) - ref).abs().max().item() < 5e-6
+    assert (ops.layernorm(x, g, b, 1e-6, torch.bfloat16).float() - ref).abs().max().item() < 2e-2 * ref.abs().max().item()
+    r = torch.randn_like(x)
+    assert (ops.layernorm(x, g, b, 1e-5, torch.float32, residual=r) - F.layer_norm(x + r, (1280,), g, b, 1e-5)).abs().max() < 5e-6
+    assert torch.equal(ops.layernorm(x, None, None, 0.0, torch.bfloat16, normalize=False), x.to(torch.bfloat16))
+
+
+def test_patch_im2col_is_exact(ops):
+    img = torch.randn(2, 3, 1024, 1024, device=DEV)
+    for dt_in in (torch.float32, torch.bfloat16):
+        got = ops.patch_im2col(img.to(dt_in), 16, torch.bfloat16)
+        want = F.unfold(img.to(dt_in).float(), 16, stride=16).transpose(1, 2).reshape(-1, 768).to(torch.bfloat16)
+        assert torch.equal(got, want)
+
+
+def test_im2col3x3_is_exact(ops):
+    y = torch.randn(2, 64, 64, 256, device=DEV).to(torch.float16)
+    got = ops.im2col3x3(y, 2, 64)
+    yp = F.pad(y, (0, 0, 1, 1, 1, 1))
+    want = torch.stack([yp[:, ky:ky + 64, kx:kx + 64] for ky in range(3) for kx in range(3)], dim=3).reshape(-1, 9 * 256)
+    assert torch.equal(got, want)
+
+
+def test_layernorm2d_to_nchw(ops):
+    z = torch.randn(2 * 4096, 256, device=DEV) * 3
+    g = torch.rand(256, device=DEV) + 0.5
+    b = torch.randn(256, device=DEV) * 0.1
+    got = ops.ln_nhwc_to_nchw(z, g, b, 1e-6, 2, 64, torch.float32)
+    x_nchw = z.view(2, 64, 64, 256).permute(0, 3, 1, 2)
+    want = O.layer_norm_2d(x_nchw, g, b, 1e-6)
+    assert (got - want).abs().max().item() < 5e-6
+
+
+# ------------------------------------------------------------------------------------------------------- attention
+def _window_reference(qkv, bias, rel_h, rel_w, B, heads):
+    """image_encoder.py:263-288 + :235-257 + :354-392 on projected qkv; padded tokens carry the qkv bias because the
+    reference pads the LayerNorm output with zeros BEFORE the qkv Linear (image_encoder.py:179-183)."""
+    E = qkv.shape[1] // 3
+    xp = bias.float().view(1, 1, 1, -1).expand(B, 70, 70, 3 * E).clone()
+    xp[:, :64, :64] = qkv.float().view(B, 64, 64, 3 * E)
+    win = xp.view(B, 5, 14, 5, 14, 3 * E).permute(0, 1, 3, 2, 4, 5).reshape(-1, 14, 14, 3 * E)
+    b = win.shape[0]
+    q, k, v = win.reshape(b, 196, 3, heads, 80).permute(2, 0, 3, 1, 4).reshape(3, b * heads, 196, 80).unbind(0)
+    attn = (q * 80 ** -0.5) @ k.transpose(-2, -1)
+    rh, rw = O._rel_table(14, 14, rel_h.float()), O._rel_table(14, 14, rel_w.float())
+    rq = q.reshape(b * heads, 14, 14, 80)
+    a = torch.einsum("bhwc,hkc->bhwk", rq, rh)
+    c = torch.einsum("bhwc,wkc->bhwk", rq, rw)
+    attn = (attn.view(b * heads, 14, 14, 14, 14) + a[..., None] + c[:, :, :, None, :]).view(b * heads, 196, 196)
+    o = (attn.softmax(-1) @ v).view(b, heads, 14, 14, 80).permute(0, 2, 3, 1, 4).reshape(b, 14, 14, E)
+    return O._unpartition(o, 14, (70, 70), (64, 64)).reshape(B * 4096, E)
+
+
+def _global_reference(qkv, rel_h, rel_w, heads):
+    E = qkv.shape[1] // 3
+    x = qkv.float().view(1, 4096, 3, heads, 80).permute(2, 0, 3, 1, 4).reshape(3, heads, 4096, 80)
+    q, k, v = x.unbind(0)
+    attn = (q * 80 ** -0.5) @ k.transpose(-2, -1)
+    rh, rw = O._rel_table(64, 64, rel_h.float()), O._rel_table(64, 64, rel_w.float())
+    rq = q.reshape(heads, 64, 64, 80)
+    a = torch.einsum("bhwc,hkc->bhwk", rq, rh)
+    c = torch.einsum("bhwc,wkc->bhwk", rq, rw)
+    attn = (attn.view(heads, 64, 64, 64, 64) + a[..., None] + c[:, :, :, None, :]).view(heads, 4096, 4096)
+    return (attn.softmax(-1) @ v).permute(1, 0, 2).reshape(4096, E)
+
+
+@pytest.mark.parametrize("dt,tol", [(torch.float16, 1e-3), (torch.bfloat16, 5e-3)])
+@pytest.mark.parametrize("B,heads", [(1, 2), (2, 16)])
+def test_windowed_attention(ops, dt, tol, B, heads):
+    torch.manual_seed(3)
+    E = heads * 80
+    qkv = torch.randn(B * 4096, 3 * E, device=DEV).to(dt)
+    bias = (torch.randn(3 * E, device=DEV) * 0.5).to(dt)
+    rel_h = (torch.randn(27, 80, device=DEV) * 0.2).to(dt)
+    rel_w = (torch.randn(27, 80, device=DEV) * 0.2).to(dt)
+    got = ops.attn_window(qkv, bias, ops.window_rel_table(rel_h, rel_w, dt), B, heads)
+    assert rel_fro(got, _window_reference(qkv, bias, rel_h, rel_w, B, heads)) < tol
+
+
+def test_windowed_attention_token_map_is_exact(ops):
+    """q = k = 0 and zero rel-pos make the softmax uniform, so every output is the mean of v over its window:
+    checks the partition / padding / un-partition index maps (image_encoder.py:263-318) independently of the maths."""
+    heads, E, B = 2, 160, 2
+    qkv = torch.zeros(B * 4096, 3 * E, device=DEV)
+    ids = torch.arange(B * 4096, device=DEV, dtype=torch.float32)
+    qkv[:, 2 * E:] = (ids % 251)[:, None] / 8.0          # exactly representable in fp16
+    qkv = qkv.to(torch.float16)
+    bias = torch.zeros(3 * E, device=DEV, dtype=torch.float16)
+    bias[2 * E:] = 7.0
+    tab = torch.zeros(64, 80, device=DEV, dtype=torch.float16)
+    got = ops.attn_window(qkv, bias, tab, B, heads)
+    want = _window_reference(qkv, bias, tab[:27], tab[27:54], B, heads)
+    assert (got.float() - want).abs().max().item() < 2e-2    # fp16 rounding of p = 1/196 only
+
+
+@pytest.mark.parametrize("dt,tol", [(torch.float16, 1.5e-3), (torch.bfloat16, 5e-3)])
+def test_global_attention(ops, dt, tol):
+    torch.manual_seed(4)
+    heads, E, B = 2, 160, 2
+    qkv = torch.randn(B * 4096, 3 * E, device=DEV).to(dt)
+    gh = (torch.randn(127, 80, device=DEV) * 0.2).to(dt)
+    gw = (torch.randn(127, 80, device=DEV) * 0.2).to(dt)
+    got = ops.attn_global(qkv, ops.global_rel_table(gh, dt), ops.global_rel_table(gw, dt), B, heads)
+    want = torch.cat([_global_reference(qkv[i * 4096:(i + 1) * 4096], gh, gw, heads) for i in range(B)])
+    assert rel_fro(got, want) < tol
+
+
+def test_rel_pos_index_tables_match_get_rel_pos(ops):
+    """INT-exact: row j of the reversed table is rel_pos[126 - j]; get_rel_pos index (image_encoder.py:345-351)."""
+    t = torch.arange(127 * 80, device=DEV, dtype=torch.float32).view(127, 80)
+    rev = ops.global_rel_table(t, torch.float32)
+    idx = O.rel_pos_index(64)
+    q, k = 10, 50
+    assert torch.equal(rev[63 - q + k], t[idx[q, k]])
+    assert int(idx.min()) == 0 and int(idx.max()) == 126
+    assert int(O.rel_pos_index(14).max()) == 26

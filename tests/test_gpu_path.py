@@ -1,0 +1,215 @@
+"""Parity of the whole path through the reference-shaped module API against the CPU oracle (small encoder, full tensors)
+and against the committed reference goldens (ViT-H).  Tolerances (measured precision envelope):
+  fp16 operands : embeddings rel-Frobenius <= 2e-3, low-res logits rel <= 2e-3, mask IoU >= 0.999
+  bf16 operands : embeddings rel-Frobenius <= 1e-2 / max-abs <= 5e-2, low-res logits rel <= 1e-2, mask IoU >= 0.995
+  decoder / postprocess (fp32 kernels): max-abs <= 2e-5 / 1e-6
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from anyref_b200.synthetic import CONFIGS, synthetic_images, synthetic_seg_embeddings, synthetic_state_dict
+from oracle import sam_oracle as O
+from oracle.make_goldens import SIZES, sub
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def rel_fro(got, ref):
+    got, ref = got.float().cpu(), ref.float().cpu()
+    return ((got - ref).norm() / ref.norm()).item()
+
+
+def mask_iou(a, b):
+    a, b = a.cpu() > 0, b.cpu() > 0
+    return (a & b).sum().item() / max((a | b).sum().item(), 1)
+
+
+@pytest.fixture(scope="module")
+def tiny():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from anyref_b200.segment_anything import build_sam_from_config
+
+    cfg = CONFIGS["vit_tiny80"]
+    sd = synthetic_state_dict(cfg)
+    x = synthetic_images(2, seed=0)
+    seg = synthetic_seg_embeddings(2, 3, seed=0)
+    taps = {}
+    with torch.no_grad():
+        emb = O.image_encoder(sd, x, cfg, taps)
+        pe = O.dense_pe(sd, cfg)
+    sam = build_sam_from_config(cfg)
+    sam.load_state_dict(sd, strict=True)
+    return {"cfg": cfg, "sd": sd, "x": x, "seg": seg, "emb": emb, "pe": pe, "taps": taps, "sam": sam.cuda()}
+
+
+@pytest.mark.parametrize("dt,tol", [(torch.float16, 2e-3), (torch.bfloat16, 1e-2)])
+def test_encoder_vs_oracle(tiny, dt, tol):
+    sam = tiny["sam"]
+    sam.image_encoder.set_operand_dtype(dt)
+    xc = tiny["x"].cuda()
+    for blk in (0, 1):  # block 0 windowed, block 1 global
+        tap = torch.empty(2 * 4096, tiny["cfg"].embed_dim, device="cuda")
+        sam.image_encoder(xc, _tap=(blk, tap))
+        assert rel_fro(tap.view(2, 64, 64, -1), tiny["taps"][f"block{blk}"]) < tol
+    emb = sam.image_encoder(xc)
+    assert emb.dtype == torch.float32 and emb.shape == (2, 256, 64, 64)
+    assert rel_fro(emb, tiny["emb"]) < tol
+    # output dtype follows the input dtype (image_encoder.py:110-125)
+    assert sam.image_encoder(xc.to(dt)).dtype == dt
+
+
+def test_dense_pe_vs_oracle(tiny):
+    pe = tiny["sam"].prompt_encoder.get_dense_pe()
+    assert pe.shape == (1, 256, 64, 64)
+    assert (pe.cpu() - tiny["pe"]).abs().max().item() < 2e-5
+
+
+@pytest.mark.parametrize("multimask", [False, True])
+def test_decoder_vs_oracle(tiny, multimask):
+    sam, cfg, sd = tiny["sam"], tiny["cfg"], tiny["sd"]
+    pe = sam.prompt_encoder.get_dense_pe()
+    for b in range(2):
+        s_ref, d_ref = O.prompt_encoder(sd, cfg, text_embeds=tiny["seg"][b])
+        low_ref, iou_ref = O.mask_decoder(sd, cfg, tiny["emb"][b:b + 1], tiny["pe"], s_ref, d_ref, multimask)
+        sparse, dense = sam.prompt_encoder(points=None, boxes=None, masks=None, text_embeds=tiny["seg"][b].cuda())
+        low, iou = sam.mask_decoder(image_embeddings=tiny["emb"][b:b + 1].cuda(), image_pe=pe,
+                                    sparse_prompt_embeddings=sparse, dense_prompt_embeddings=dense,
+                                    multimask_output=multimask)
+        assert low.shape == low_ref.shape and iou.shape == iou_ref.shape
+        assert (low.cpu() - low_ref).abs().max().item() < 2e-5
+        assert (iou.cpu() - iou_ref).abs().max().item() < 2e-5
+
+
+def test_decoder_with_several_prompt_tokens_and_dense_input(tiny):
+    """k = 3 sparse embeddings per prompt (T = 8 tokens) and a full dense prompt embedding [n,C,g,g]."""
+    sam, cfg, sd = tiny["sam"], tiny["cfg"], tiny["sd"]
+    g = torch.Generator().manual_seed(5)
+    sparse = torch.randn(2, 3, 256, generator=g)
+    dense = torch.randn(2, 256, 64, 64, generator=g) * 0.1
+    low_ref, iou_ref = O.mask_decoder(sd, cfg, tiny["emb"][:1], tiny["pe"], sparse, dense, True)
+    low, iou = sam.mask_decoder(image_embeddings=tiny["emb"][:1].cuda(), image_pe=tiny["pe"].cuda(),
+                                sparse_prompt_embeddings=sparse.cuda(), dense_prompt_embeddings=dense.cuda(),
+                                multimask_output=True)
+    assert (low.cpu() - low_ref).abs().max().item() < 2e-5
+    assert (iou.cpu() - iou_ref).abs().max().item() < 2e-5
+
+
+@pytest.mark.parametrize("inp,orig", SIZES + [((1024, 1024), (333, 517)), ((512, 1024), (1, 7))])
+def test_postprocess_vs_oracle(tiny, inp, orig):
+    sam = tiny["sam"]
+    g = torch.Generator().manual_seed(7)
+    low = torch.randn(3, 2, 256, 256, generator=g)
+    want = O.postprocess_masks(low, inp, orig, 1024)
+    want_taps = O.postprocess_masks_taps(low, inp, orig, 1024)
+    got, binary = sam.postprocess_masks(low.cuda(), inp, orig, return_binary=True)
+    assert got.dtype == torch.float32 and got.shape == want.shape
+    assert (got.cpu() - want).abs().max().item() < 2e-6
+    # explicit tap tables (indices are exact; the source coordinate is rounded once more without FMA -> 1 ulp of src)
+    assert (got.cpu() - want_taps).abs().max().item() < 3e-5
+    assert torch.equal(binary, (got > sam.mask_threshold).to(torch.uint8))
+    flips = ((got.cpu() > 0) != (want > 0)).sum().item()
+    assert flips <= max(1, int(1e-5 * want.numel()))
+
+
+def test_postprocess_constant_mask_is_constant(tiny):
+    low = torch.full((1, 1, 256, 256), 0.37, device="cuda")
+    out = tiny["sam"].postprocess_masks(low, (1024, 683), (640, 427))
+    assert (out - 0.37).abs().max().item() < 1e-6
+
+
+def test_batched_equals_per_image_loop(tiny):
+    """GroundingPath (one batched decoder call) == the reference's per-image loop (model/anyref.py:797-819)."""
+    from anyref_b200.grounding import GroundingPath
+
+    sam = tiny["sam"]
+    sam.image_encoder.set_operand_dtype(torch.float16)
+    path = GroundingPath(sam)
+    x = tiny["x"].cuda()
+    segs = [tiny["seg"][0].cuda(), tiny["seg"][1][:1].cuda()]        # ragged: 3 prompts and 1 prompt
+    ins, outs = [(1024, 683), (768, 1024)], [(640, 427), (480, 640)]
+    a = path(x, segs, ins, outs, multimask_output=True)
+    b = path.per_image_loop(x, segs, ins, outs, multimask_output=True)
+    assert [t.shape for t in a] == [(3, 3, 640, 427), (1, 3, 480, 640)]
+    assert all(torch.equal(u, v) for u, v in zip(a, b))
+    # an image without any [SEG] prompt yields an empty result (ragged / empty edge case)
+    c = path(x, [segs[0], segs[1][:0]], ins, outs)
+    assert c[1].shape == (0, 1, 480, 640) and torch.equal(c[0], path(x[:1], segs[:1], ins[:1], outs[:1])[0])
+
+
+def test_whole_path_vs_oracle(tiny):
+    from anyref_b200.grounding import GroundingPath
+
+    sam, cfg, sd = tiny["sam"], tiny["cfg"], tiny["sd"]
+    segs = [tiny["seg"][0], tiny["seg"][1]]
+    sizes = [(1024, 1024), (1024, 1024)]
+    want = O.grounding_path(sd, cfg, tiny["x"], segs, sizes, sizes, multimask_output=False)
+    sam.image_encoder.set_operand_dtype(torch.float16)
+    got = GroundingPath(sam)(tiny["x"].cuda(), [s.cuda() for s in segs], sizes, sizes)
+    for g, w in zip(got, want):
+        assert rel_fro(g, w) < 3e-3
+        assert mask_iou(g, w) >= 0.995
+
+
+def test_parameter_updates_are_picked_up(tiny):
+    """Derived kernel-side weight copies are rebuilt when parameters change."""
+    sam = tiny["sam"]
+    sam.image_encoder.set_operand_dtype(torch.float16)
+    x = tiny["x"][:1].cuda()
+    a = sam.image_encoder(x)
+    with torch.no_grad():
+        sam.image_encoder.neck[3].bias.add_(1.0)
+    b = sam.image_encoder(x)
+    with torch.no_grad():
+        sam.image_encoder.neck[3].bias.sub_(1.0)
+    assert (b - a - 1.0).abs().max().item() < 1e-5
+    assert torch.equal(sam.image_encoder(x), a)     # deterministic + restored
+
+
+@pytest.mark.parametrize("dt,emb_tol,low_tol,iou_min", [(torch.float16, 2e-3, 2e-3, 0.999),
+                                                        (torch.bfloat16, 1e-2, 1e-2, 0.995)])
+def test_vit_h_against_reference_goldens(dt, emb_tol, low_tol, iou_min):
+    """Full-size ViT-H vs tests/golden/vit_h_seed1234_in0.pt (outputs of the UNMODIFIED reference modules)."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from anyref_b200.segment_anything import build_sam_vit_h
+
+    g = torch.load(os.path.join(GOLD, "vit_h_seed1234_in0.pt"), weights_only=False)
+    cfg = CONFIGS["vit_h"]
+    sd = synthetic_state_dict(cfg, seed=g["meta"]["seed_ckpt"])
+    sam = build_sam_vit_h(None)
+    sam.load_state_dict(sd, strict=True)
+    del sd
+    sam = sam.cuda()
+    sam.image_encoder.set_operand_dtype(dt)
+    x = synthetic_images(1, seed=g["meta"]["seed_in"]).cuda()
+    seg = synthetic_seg_embeddings(1, g["meta"]["n_seg"], seed=g["meta"]["seed_in"])[0].cuda()
+    emb = sam.image_encoder(x)
+    assert rel_fro(sub(emb, (1, 4, 4, 4)), g["emb_sub"]) < emb_tol
+    if dt == torch.bfloat16:
+        assert (sub(emb, (1, 4, 4, 4)).cpu() - g["emb_sub"]).abs().max().item() < 5e-2
+    pe = sam.prompt_encoder.get_dense_pe()
+    assert (sub(pe, (1, 8, 8, 8)).cpu() - g["dense_pe_sub"]).abs().max().item() < 2e-5
+    sparse, dense = sam.prompt_encoder(points=None, boxes=None, masks=None, text_embeds=seg)
+    for mm in (False, True):
+        tag = "multi" if mm else "single"
+        low, iou = sam.mask_decoder(image_embeddings=emb, image_pe=pe, sparse_prompt_embeddings=sparse,
+                                    dense_prompt_embeddings=dense, multimask_output=mm)
+        assert rel_fro(sub(low, (1, 1, 4, 4)), g[f"low_{tag}_sub"]) < low_tol
+        assert (iou.cpu() - g[f"iou_{tag}"]).abs().max().item() < 1e-3
+        if mm:
+            continue
+        for inp, orig in SIZES:
+            key = f"post_{tag}_{inp[0]}x{inp[1]}_{orig[0]}x{orig[1]}"
+            post = sam.postprocess_masks(low, inp, orig)
+            want = np.unpackbits(g[key + "_bits"].numpy())[:post.numel()].reshape(post.shape).astype(bool)
+            got = (post > 0).cpu().numpy()
+            for i in range(post.shape[0]):
+                iou_i = (want[i] & got[i]).sum() / max((want[i] | got[i]).sum(), 1)
+                assert iou_i >= iou_min, (key, i, iou_i)
+    del sam
+    torch.cuda.empty_cache()
