@@ -43,7 +43,7 @@ int samk_umma_probe(const void* A, const void* B, float* D, const UmmaProbe& p, 
 
 // 14x14 windowed attention with fused decomposed rel-pos bias (attn_window.cu).
 //   qkv [B*4096, 3E] op-format; bias_op [3E] op-format (qkv bias, used for padded window tokens);
-//   rel_tab [64, 80] op-format: rows 0..26 rel_pos_h, 27..53 rel_pos_w, rest zero; out [B*4096, E] op-format.
+//   rel_tab [64, 80] op-format: rows 0..26 rel_pos_h, rows 32..58 rel_pos_w, rest zero; out [B*4096, E] op-format.
 int samk_attn_window(const void* qkv, const void* bias_op, const void* rel_tab, void* out, int B, int E, int heads,
                      int fmt, cudaStream_t stream);
 // Global 64x64 attention with fused rel-pos bias (attn_global.cu).

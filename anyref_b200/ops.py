@@ -103,11 +103,11 @@ def ln_nhwc_to_nchw(x: torch.Tensor, gamma, beta, eps: float, B: int, g: int, ou
 
 
 def window_rel_table(rel_pos_h: torch.Tensor, rel_pos_w: torch.Tensor, dtype) -> torch.Tensor:
-    """[64, hd] operand table of sam_attn_window: rows 0..26 rel_pos_h, 27..53 rel_pos_w, rest zero."""
+    """[64, hd] operand table of sam_attn_window: rows 0..26 rel_pos_h, rows 32..58 rel_pos_w, rest zero."""
     n, hd = rel_pos_h.shape
     t = torch.zeros((64, hd), device=rel_pos_h.device, dtype=dtype)
     t[:n] = rel_pos_h.to(dtype)
-    t[n:2 * n] = rel_pos_w.to(dtype)
+    t[32:32 + n] = rel_pos_w.to(dtype)
     return t
 
 

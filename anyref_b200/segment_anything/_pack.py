@@ -80,7 +80,7 @@ def pack_encoder(enc, op_dtype):
             if s != 14:
                 raise RuntimeError("windowed attention kernel expects 14x14 windows")
             rel[:27 * hd] = a.rel_pos_h.detach().to(op_dtype).reshape(-1)
-            rel[27 * hd:54 * hd] = a.rel_pos_w.detach().to(op_dtype).reshape(-1)
+            rel[32 * hd:59 * hd] = a.rel_pos_w.detach().to(op_dtype).reshape(-1)
         b16.put(rel)
         b32.put(blk.norm1.weight.float()); b32.put(blk.norm1.bias.float())
         b32.put(a.qkv.bias.float())

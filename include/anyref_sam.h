@@ -111,7 +111,7 @@ int sam_ln_nhwc_to_nchw(const float* x, const float* gamma, const float* beta, f
  * and :354-392 (add_decomposed_rel_pos) for the 28 windowed blocks.
  *   qkv     [B*64*64, 3E] fmt 0/1, token-major, NOT partitioned, columns ordered (q|k|v, head, d)
  *   bias_op [3E]          qkv bias in operand format -- q/k/v of the zero-padded window tokens (image_encoder.py:281)
- *   rel_tab [64, 80]      operand format: rows 0..26 rel_pos_h, rows 27..53 rel_pos_w, rest zero
+ *   rel_tab [64, 80]      operand format: rows 0..26 rel_pos_h, rows 32..58 rel_pos_w, rest zero
  *   out     [B*64*64, E]  operand format, heads merged (the A operand of the proj GEMM)
  * head_dim must be 80 (ViT-H), grid 64x64.
  */

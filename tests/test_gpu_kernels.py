@@ -173,7 +173,7 @@ def test_windowed_attention_token_map_is_exact(ops):
     bias[2 * E:] = 7.0
     tab = torch.zeros(64, 80, device=DEV, dtype=torch.float16)
     got = ops.attn_window(qkv, bias, tab, B, heads)
-    want = _window_reference(qkv, bias, tab[:27], tab[27:54], B, heads)
+    want = _window_reference(qkv, bias, tab[:27], tab[32:59], B, heads)
     assert (got.float() - want).abs().max().item() < 2e-2    # fp16 rounding of p = 1/196 only
 
 
