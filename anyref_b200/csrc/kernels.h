@@ -53,6 +53,9 @@ int samk_attn_window3(const void* qkv, const void* bias_op, const void* rel_tab,
 int samk_attn_global(const void* qkv, const void* rh_rev, const void* rw_rev, void* out, int B, int E, int heads,
                      int fmt, cudaStream_t stream);
 
+int samk_attn_global2(const void* qkv, const void* rh_rev, const void* rw_rev, void* out, int B, int E, int heads,
+                      int fmt, cudaStream_t stream);
+
 // Memory-bound glue (glue.cu).  All fp32 activations are token-major rows.
 //   layernorm_rows : out[row] = LN(x[row] (+ res[row])) * gamma + beta  (normalize == 0: plain dtype cast)
 int samk_layernorm_rows(const float* x, int ldx, const float* res, int ldr, const float* gamma, const float* beta,
