@@ -54,7 +54,7 @@ struct GlobAttnMapsG {
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
-  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 __device__ __forceinline__ uint32_t row_off64(int r, int c) { return r * 128 + ((c ^ (r & 7)) << 4); }
@@ -72,9 +72,9 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 
 // One 32-key chunk of a block: logits (log2 domain, relative to the reference max folded into rh), running block
 // max, exp2, row-sum, P -> shared memory (operand format).  C = chunk index 0..3 (keys C*32 .. C*32+31).
-template <int C>
+template <int C, int FMT>
 __device__ __forceinline__ void softmax_chunk(uint32_t trow, const uint32_t (&relw)[32], float rh, float scale_log2e,
-                                              uint8_t* pbase, int row, int fmt, float& bmax, float& bsum) {
+                                              uint32_t pbase, int row, float& bmax, float& bsum) {
   uint32_t v[32];
   ptx::tmem_ld_32x32b_x32(trow + C * 32, v);
   ptx::tmem_ld_wait();
@@ -94,11 +94,11 @@ __device__ __forceinline__ void softmax_chunk(uint32_t trow, const uint32_t (&re
   for (int g = 0; g < 4; ++g) {
     const int j0 = C * 32 + g * 8;
     uint4 u;
-    u.x = ptx::pack2(p[g * 8 + 0], p[g * 8 + 1], fmt);
-    u.y = ptx::pack2(p[g * 8 + 2], p[g * 8 + 3], fmt);
-    u.z = ptx::pack2(p[g * 8 + 4], p[g * 8 + 5], fmt);
-    u.w = ptx::pack2(p[g * 8 + 6], p[g * 8 + 7], fmt);
-    *reinterpret_cast<uint4*>(pbase + (j0 >> 6) * 16384 + row_off64(row, (j0 & 63) >> 3)) = u;
+    u.x = ptx::pack2t<FMT>(p[g * 8 + 0], p[g * 8 + 1]);
+    u.y = ptx::pack2t<FMT>(p[g * 8 + 2], p[g * 8 + 3]);
+    u.z = ptx::pack2t<FMT>(p[g * 8 + 4], p[g * 8 + 5]);
+    u.w = ptx::pack2t<FMT>(p[g * 8 + 6], p[g * 8 + 7]);
+    ptx::st_shared_v4(pbase + (j0 >> 6) * 16384 + row_off64(row, (j0 & 63) >> 3), u);
   }
 }
 
@@ -118,10 +118,12 @@ __device__ __forceinline__ void max_chunk(uint32_t trow, const uint32_t (&relw)[
   }
 }
 
+template <int FMT>
 __global__ void __launch_bounds__(kThreadsG, 1)
 glob_attn2_kernel(const __grid_constant__ GlobAttnMapsG maps, const uint16_t* __restrict__ rh_rev,
                   const uint16_t* __restrict__ rw_rev, uint16_t* __restrict__ out, const int E, const int heads,
-                  const int fmt, const float scale_log2e) {
+                  const float scale_log2e) {
+  constexpr int fmt = FMT;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
@@ -304,7 +306,7 @@ glob_attn2_kernel(const __grid_constant__ GlobAttnMapsG maps, const uint16_t* __
     const int row = ((warp & 3) << 5) + lane;            // TMEM lane == query row inside the tile
     const uint32_t slot = tmem + g * 256;
     const uint32_t trow = slot + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-    uint8_t* pbase = smem + OFF_P + g * 32768;
+    const uint32_t pbase = sbase + OFF_P + g * 32768;
     uint32_t* relh_s = reinterpret_cast<uint32_t*>(smem + OFF_RELH) + g * 128 + row;   // [pair * 256]
     const int qh = qh0 + g * 2 + (row >> 6);
     const int qw = row & 63;
@@ -367,10 +369,10 @@ glob_attn2_kernel(const __grid_constant__ GlobAttnMapsG maps, const uint16_t* __
       }
       float bmax = -INFINITY, bsum = 0.f;
       float rh0 = rhp.x - m_ref, rh1 = rhp.y - m_ref;
-      softmax_chunk<0>(trow, relw, rh0, scale_log2e, pbase, row, fmt, bmax, bsum);
-      softmax_chunk<1>(trow, relw, rh0, scale_log2e, pbase, row, fmt, bmax, bsum);
-      softmax_chunk<2>(trow, relw, rh1, scale_log2e, pbase, row, fmt, bmax, bsum);
-      softmax_chunk<3>(trow, relw, rh1, scale_log2e, pbase, row, fmt, bmax, bsum);
+      softmax_chunk<0, FMT>(trow, relw, rh0, scale_log2e, pbase, row, bmax, bsum);
+      softmax_chunk<1, FMT>(trow, relw, rh0, scale_log2e, pbase, row, bmax, bsum);
+      softmax_chunk<2, FMT>(trow, relw, rh1, scale_log2e, pbase, row, bmax, bsum);
+      softmax_chunk<3, FMT>(trow, relw, rh1, scale_log2e, pbase, row, bmax, bsum);
       if (__any_sync(0xffffffffu, bmax > kRescaleThreshold)) {
         // rare: this block exceeds the reference by more than 2^8 for some row of the warp.  Move the reference,
         // rescale the accumulated O row and row sum, and redo the block against the new reference.
@@ -392,10 +394,10 @@ glob_attn2_kernel(const __grid_constant__ GlobAttnMapsG maps, const uint16_t* __
         bsum = 0.f;
         rh0 = rhp.x - m_ref;
         rh1 = rhp.y - m_ref;
-        softmax_chunk<0>(trow, relw, rh0, scale_log2e, pbase, row, fmt, bmax, bsum);
-        softmax_chunk<1>(trow, relw, rh0, scale_log2e, pbase, row, fmt, bmax, bsum);
-        softmax_chunk<2>(trow, relw, rh1, scale_log2e, pbase, row, fmt, bmax, bsum);
-        softmax_chunk<3>(trow, relw, rh1, scale_log2e, pbase, row, fmt, bmax, bsum);
+        softmax_chunk<0, FMT>(trow, relw, rh0, scale_log2e, pbase, row, bmax, bsum);
+        softmax_chunk<1, FMT>(trow, relw, rh0, scale_log2e, pbase, row, bmax, bsum);
+        softmax_chunk<2, FMT>(trow, relw, rh1, scale_log2e, pbase, row, bmax, bsum);
+        softmax_chunk<3, FMT>(trow, relw, rh1, scale_log2e, pbase, row, bmax, bsum);
       }
       l += bsum;
       ptx::fence_proxy_async_smem();
@@ -413,14 +415,14 @@ glob_attn2_kernel(const __grid_constant__ GlobAttnMapsG maps, const uint16_t* __
       ptx::tmem_ld_32x32b_x16(trow + TM_O + c * 16, v);
       ptx::tmem_ld_wait();
       uint4 u0, u1;
-      u0.x = ptx::pack2(__uint_as_float(v[0]) * inv, __uint_as_float(v[1]) * inv, fmt);
-      u0.y = ptx::pack2(__uint_as_float(v[2]) * inv, __uint_as_float(v[3]) * inv, fmt);
-      u0.z = ptx::pack2(__uint_as_float(v[4]) * inv, __uint_as_float(v[5]) * inv, fmt);
-      u0.w = ptx::pack2(__uint_as_float(v[6]) * inv, __uint_as_float(v[7]) * inv, fmt);
-      u1.x = ptx::pack2(__uint_as_float(v[8]) * inv, __uint_as_float(v[9]) * inv, fmt);
-      u1.y = ptx::pack2(__uint_as_float(v[10]) * inv, __uint_as_float(v[11]) * inv, fmt);
-      u1.z = ptx::pack2(__uint_as_float(v[12]) * inv, __uint_as_float(v[13]) * inv, fmt);
-      u1.w = ptx::pack2(__uint_as_float(v[14]) * inv, __uint_as_float(v[15]) * inv, fmt);
+      u0.x = ptx::pack2t<FMT>(__uint_as_float(v[0]) * inv, __uint_as_float(v[1]) * inv);
+      u0.y = ptx::pack2t<FMT>(__uint_as_float(v[2]) * inv, __uint_as_float(v[3]) * inv);
+      u0.z = ptx::pack2t<FMT>(__uint_as_float(v[4]) * inv, __uint_as_float(v[5]) * inv);
+      u0.w = ptx::pack2t<FMT>(__uint_as_float(v[6]) * inv, __uint_as_float(v[7]) * inv);
+      u1.x = ptx::pack2t<FMT>(__uint_as_float(v[8]) * inv, __uint_as_float(v[9]) * inv);
+      u1.y = ptx::pack2t<FMT>(__uint_as_float(v[10]) * inv, __uint_as_float(v[11]) * inv);
+      u1.z = ptx::pack2t<FMT>(__uint_as_float(v[12]) * inv, __uint_as_float(v[13]) * inv);
+      u1.w = ptx::pack2t<FMT>(__uint_as_float(v[14]) * inv, __uint_as_float(v[15]) * inv);
       reinterpret_cast<uint4*>(dst + c * 16)[0] = u0;
       reinterpret_cast<uint4*>(dst + c * 16)[1] = u1;
     }
@@ -450,7 +452,8 @@ int samk_attn_global2(const void* qkv, const void* rh_rev, const void* rw_rev, v
   if (rc) return rc;
   static bool attr_done = false;
   if (!attr_done) {
-    SAM_CHECK_CUDA(cudaFuncSetAttribute(glob_attn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesG));
+    SAM_CHECK_CUDA(cudaFuncSetAttribute(glob_attn2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesG));
+    SAM_CHECK_CUDA(cudaFuncSetAttribute(glob_attn2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesG));
     attr_done = true;
   }
   const float scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
@@ -458,9 +461,14 @@ int samk_attn_global2(const void* qkv, const void* rh_rev, const void* rw_rev, v
   const double bh = static_cast<double>(B) * heads;
   samhost::LaunchScope scope(samhost::KC_ATTN_GLOBAL, stream, bh * (4.0 * 4096 * 4096 * 80 + 4.0 * 4096 * 64 * 80),
                              static_cast<double>(B) * 4096 * E * 2 * 4);
-  glob_attn2_kernel<<<grid, kThreadsG, kSmemBytesG, stream>>>(maps, static_cast<const uint16_t*>(rh_rev),
-                                                               static_cast<const uint16_t*>(rw_rev),
-                                                               static_cast<uint16_t*>(out), E, heads, fmt, scale_log2e);
+  if (fmt == 0)
+    glob_attn2_kernel<0><<<grid, kThreadsG, kSmemBytesG, stream>>>(maps, static_cast<const uint16_t*>(rh_rev),
+                                                                    static_cast<const uint16_t*>(rw_rev),
+                                                                    static_cast<uint16_t*>(out), E, heads, scale_log2e);
+  else
+    glob_attn2_kernel<1><<<grid, kThreadsG, kSmemBytesG, stream>>>(maps, static_cast<const uint16_t*>(rh_rev),
+                                                                    static_cast<const uint16_t*>(rw_rev),
+                                                                    static_cast<uint16_t*>(out), E, heads, scale_log2e);
   SAM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -49,7 +49,7 @@ struct WinAttnMaps3 {
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
-  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 __device__ __forceinline__ uint32_t row_off64(int r, int c) { return r * 128 + ((c ^ (r & 7)) << 4); }
@@ -98,9 +98,9 @@ __device__ __forceinline__ void max_chunk(uint32_t trow, const float (&relh)[WS]
   }
 }
 
-template <int C>
+template <int C, int FMT>
 __device__ __forceinline__ void exp_chunk(uint32_t trow, const float (&relh)[WS], const float (&relw)[WS],
-                                          float scale_log2e, uint8_t* pbase, int row, int fmt, float& sum) {
+                                          float scale_log2e, uint32_t pbase, int row, float& sum) {
   uint32_t v[32];
   load_s_chunk<C>(trow, v);
   float p[32];
@@ -119,14 +119,14 @@ __device__ __forceinline__ void exp_chunk(uint32_t trow, const float (&relh)[WS]
     const int j0 = C * 32 + g * 8;
     if (j0 < NKEY) {
       uint4 u;
-      u.x = ptx::pack2(p[g * 8 + 0], p[g * 8 + 1], fmt);
-      u.y = ptx::pack2(p[g * 8 + 2], p[g * 8 + 3], fmt);
-      u.z = ptx::pack2(p[g * 8 + 4], p[g * 8 + 5], fmt);
-      u.w = ptx::pack2(p[g * 8 + 6], p[g * 8 + 7], fmt);
+      u.x = ptx::pack2t<FMT>(p[g * 8 + 0], p[g * 8 + 1]);
+      u.y = ptx::pack2t<FMT>(p[g * 8 + 2], p[g * 8 + 3]);
+      u.z = ptx::pack2t<FMT>(p[g * 8 + 4], p[g * 8 + 5]);
+      u.w = ptx::pack2t<FMT>(p[g * 8 + 6], p[g * 8 + 7]);
       if (j0 < 192)
-        *reinterpret_cast<uint4*>(pbase + (j0 >> 6) * 16384 + row_off64(row, (j0 & 63) >> 3)) = u;
+        ptx::st_shared_v4(pbase + (j0 >> 6) * 16384 + row_off64(row, (j0 & 63) >> 3), u);
       else
-        *reinterpret_cast<uint4*>(pbase + 49152 + row_off16(row, (j0 - 192) >> 3)) = u;
+        ptx::st_shared_v4(pbase + 49152 + row_off16(row, (j0 - 192) >> 3), u);
     }
   }
 }
@@ -145,10 +145,12 @@ __device__ __forceinline__ Item decode_item(int it, int heads) {
   return r;
 }
 
+template <int FMT>
 __global__ void __launch_bounds__(kThreads3, 1)
 win_attn3_kernel(const __grid_constant__ WinAttnMaps3 maps, const uint16_t* __restrict__ bias_op,
-                 uint16_t* __restrict__ out, const int E, const int heads, const int num_items, const int fmt,
+                 uint16_t* __restrict__ out, const int E, const int heads, const int num_items,
                  const float scale_log2e) {
+  constexpr int fmt = FMT;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
@@ -332,8 +334,8 @@ win_attn3_kernel(const __grid_constant__ WinAttnMaps3 maps, const uint16_t* __re
     const int g = (warp - 2) >> 2;
     const int row = ((warp & 3) << 5) + lane;          // TMEM lane == query row of the tile (warp & 3 = lane quadrant)
     const uint32_t trow = tmem + g * 256 + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-    uint8_t* pbase = smem + OFF_P + g * kPBytes;
-    float* sc = reinterpret_cast<float*>(pbase) + row * kScratchStride;
+    const uint32_t pbase = sbase + OFF_P + g * kPBytes;
+    float* sc = reinterpret_cast<float*>(smem + OFF_P + g * kPBytes) + row * kScratchStride;
     const int nq = g ? 70 : 126;
     const int qiy = (g ? 9 : 0) + row / WS;
     const int qix = row % WS;
@@ -375,13 +377,13 @@ win_attn3_kernel(const __grid_constant__ WinAttnMaps3 maps, const uint16_t* __re
 #pragma unroll
       for (int kh = 0; kh < WS; ++kh) relh[kh] -= mx;
       float sum = 0.f;
-      exp_chunk<0>(trow, relh, relw, scale_log2e, pbase, row, fmt, sum);
-      exp_chunk<1>(trow, relh, relw, scale_log2e, pbase, row, fmt, sum);
-      exp_chunk<2>(trow, relh, relw, scale_log2e, pbase, row, fmt, sum);
-      exp_chunk<3>(trow, relh, relw, scale_log2e, pbase, row, fmt, sum);
-      exp_chunk<4>(trow, relh, relw, scale_log2e, pbase, row, fmt, sum);
-      exp_chunk<5>(trow, relh, relw, scale_log2e, pbase, row, fmt, sum);
-      exp_chunk<6>(trow, relh, relw, scale_log2e, pbase, row, fmt, sum);
+      exp_chunk<0, FMT>(trow, relh, relw, scale_log2e, pbase, row, sum);
+      exp_chunk<1, FMT>(trow, relh, relw, scale_log2e, pbase, row, sum);
+      exp_chunk<2, FMT>(trow, relh, relw, scale_log2e, pbase, row, sum);
+      exp_chunk<3, FMT>(trow, relh, relw, scale_log2e, pbase, row, sum);
+      exp_chunk<4, FMT>(trow, relh, relw, scale_log2e, pbase, row, sum);
+      exp_chunk<5, FMT>(trow, relh, relw, scale_log2e, pbase, row, sum);
+      exp_chunk<6, FMT>(trow, relh, relw, scale_log2e, pbase, row, sum);
       ptx::fence_proxy_async_smem();
       ptx::tc_fence_before();
       ptx::mbar_arrive(&p_ready[g]);
@@ -400,14 +402,14 @@ win_attn3_kernel(const __grid_constant__ WinAttnMaps3 maps, const uint16_t* __re
           ptx::tmem_ld_wait();
           if (ok) {
             uint4 u0, u1;
-            u0.x = ptx::pack2(__uint_as_float(v[0]) * inv, __uint_as_float(v[1]) * inv, fmt);
-            u0.y = ptx::pack2(__uint_as_float(v[2]) * inv, __uint_as_float(v[3]) * inv, fmt);
-            u0.z = ptx::pack2(__uint_as_float(v[4]) * inv, __uint_as_float(v[5]) * inv, fmt);
-            u0.w = ptx::pack2(__uint_as_float(v[6]) * inv, __uint_as_float(v[7]) * inv, fmt);
-            u1.x = ptx::pack2(__uint_as_float(v[8]) * inv, __uint_as_float(v[9]) * inv, fmt);
-            u1.y = ptx::pack2(__uint_as_float(v[10]) * inv, __uint_as_float(v[11]) * inv, fmt);
-            u1.z = ptx::pack2(__uint_as_float(v[12]) * inv, __uint_as_float(v[13]) * inv, fmt);
-            u1.w = ptx::pack2(__uint_as_float(v[14]) * inv, __uint_as_float(v[15]) * inv, fmt);
+            u0.x = ptx::pack2t<FMT>(__uint_as_float(v[0]) * inv, __uint_as_float(v[1]) * inv);
+            u0.y = ptx::pack2t<FMT>(__uint_as_float(v[2]) * inv, __uint_as_float(v[3]) * inv);
+            u0.z = ptx::pack2t<FMT>(__uint_as_float(v[4]) * inv, __uint_as_float(v[5]) * inv);
+            u0.w = ptx::pack2t<FMT>(__uint_as_float(v[6]) * inv, __uint_as_float(v[7]) * inv);
+            u1.x = ptx::pack2t<FMT>(__uint_as_float(v[8]) * inv, __uint_as_float(v[9]) * inv);
+            u1.y = ptx::pack2t<FMT>(__uint_as_float(v[10]) * inv, __uint_as_float(v[11]) * inv);
+            u1.z = ptx::pack2t<FMT>(__uint_as_float(v[12]) * inv, __uint_as_float(v[13]) * inv);
+            u1.w = ptx::pack2t<FMT>(__uint_as_float(v[14]) * inv, __uint_as_float(v[15]) * inv);
             reinterpret_cast<uint4*>(dst + c * 16)[0] = u0;
             reinterpret_cast<uint4*>(dst + c * 16)[1] = u1;
           }
@@ -452,7 +454,8 @@ int samk_attn_window3(const void* qkv, const void* bias_op, const void* rel_tab,
   if (rc) return rc;
   static bool attr_done = false;
   if (!attr_done) {
-    SAM_CHECK_CUDA(cudaFuncSetAttribute(win_attn3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes3));
+    SAM_CHECK_CUDA(cudaFuncSetAttribute(win_attn3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes3));
+    SAM_CHECK_CUDA(cudaFuncSetAttribute(win_attn3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes3));
     attr_done = true;
   }
   const float scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
@@ -462,9 +465,14 @@ int samk_attn_window3(const void* qkv, const void* bias_op, const void* rel_tab,
   const double wh = static_cast<double>(num_items);
   samhost::LaunchScope scope(samhost::KC_ATTN_WINDOW, stream, wh * (4.0 * 196 * 196 * 80 + 4.0 * 196 * 14 * 80),
                              static_cast<double>(B) * 4096 * E * 2 * 4);
-  win_attn3_kernel<<<grid, kThreads3, kSmemBytes3, stream>>>(maps, static_cast<const uint16_t*>(bias_op),
-                                                              static_cast<uint16_t*>(out), E, heads, num_items, fmt,
-                                                              scale_log2e);
+  if (fmt == 0)
+    win_attn3_kernel<0><<<grid, kThreads3, kSmemBytes3, stream>>>(maps, static_cast<const uint16_t*>(bias_op),
+                                                                   static_cast<uint16_t*>(out), E, heads, num_items,
+                                                                   scale_log2e);
+  else
+    win_attn3_kernel<1><<<grid, kThreads3, kSmemBytes3, stream>>>(maps, static_cast<const uint16_t*>(bias_op),
+                                                                   static_cast<uint16_t*>(out), E, heads, num_items,
+                                                                   scale_log2e);
   SAM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -126,6 +126,9 @@ struct Gemm2Params {
   uint32_t idesc;
 };
 
+// OUT_FMT: SamFmt of the output (0 fp16, 1 bf16, 2 fp32);  ACT: 0 none, 1 GELU  (compile-time so the epilogue carries
+// exactly one conversion / activation path)
+template <int OUT_FMT, int ACT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmC, const Gemm2Params p) {
@@ -249,7 +252,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         // tile overhang (all conditions are warp-uniform); TMA clips partially out-of-range boxes itself
         const bool valid = row0 < p.M && col0 < p.N;
         const bool pair_valid = row0 < p.M && (col0 - (c & 1) * 32) < p.N;   // 16-bit mode: chunks c-1 | c share a box
-        if (p.out_mode == 0 ? !pair_valid : !valid) continue;
+        if (OUT_FMT != 2 ? !pair_valid : !valid) continue;
         float f[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
@@ -263,26 +266,26 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             }
           }
         }
-        if (p.act == 1) {
+        if (ACT == 1) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] = gelu_fast(f[i]);
         }
-        if (p.out_mode == 0) {
+        if (OUT_FMT != 2) {
           // 16-bit output: two 32-column chunks share one 32 x 64 (128 B rows) staging box
           if ((c & 1) == 0) {
             if (lane == 0) bulk_wait_read<1>();
             __syncwarp();
           }
-          uint8_t* sb = stg + buf * 4096 + lane * 128;
+          const uint32_t sb = ptx::smem_u32(stg) + buf * 4096 + lane * 128;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             uint4 u;
-            u.x = ptx::pack2(f[8 * i + 0], f[8 * i + 1], p.out_fmt);
-            u.y = ptx::pack2(f[8 * i + 2], f[8 * i + 3], p.out_fmt);
-            u.z = ptx::pack2(f[8 * i + 4], f[8 * i + 5], p.out_fmt);
-            u.w = ptx::pack2(f[8 * i + 6], f[8 * i + 7], p.out_fmt);
+            u.x = ptx::pack2t<OUT_FMT>(f[8 * i + 0], f[8 * i + 1]);
+            u.y = ptx::pack2t<OUT_FMT>(f[8 * i + 2], f[8 * i + 3]);
+            u.z = ptx::pack2t<OUT_FMT>(f[8 * i + 4], f[8 * i + 5]);
+            u.w = ptx::pack2t<OUT_FMT>(f[8 * i + 6], f[8 * i + 7]);
             const int chunk = (c & 1) * 4 + i;
-            *reinterpret_cast<uint4*>(sb + ((chunk ^ (lane & 7)) << 4)) = u;
+            ptx::st_shared_v4(sb + ((chunk ^ (lane & 7)) << 4), u);
           }
           if ((c & 1) == 1) {
             ptx::fence_proxy_async_smem();
@@ -296,11 +299,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         } else {
           if (lane == 0) bulk_wait_read<1>();
           __syncwarp();
-          uint8_t* sb = stg + buf * 4096 + lane * 128;
+          const uint32_t sb = ptx::smem_u32(stg) + buf * 4096 + lane * 128;
 #pragma unroll
           for (int i = 0; i < 8; ++i)
-            *reinterpret_cast<float4*>(sb + ((i ^ (lane & 7)) << 4)) =
-                make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+            ptx::st_shared_v4f(sb + ((i ^ (lane & 7)) << 4), make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]));
           ptx::fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
@@ -354,11 +356,19 @@ int samk_gemm2(const void* A, int lda, const void* W, int ldw, int M, int N, int
   else
     rc = samhost::encode_tmap_2d(&tmC, 4, 0, ep.out, (uint64_t)N, (uint64_t)M, (uint64_t)ep.ldo * 4, 32, 32, 3);
   if (rc) return rc;
+  typedef void (*KernelFn)(CUtensorMap, CUtensorMap, CUtensorMap, Gemm2Params);
+  static const KernelFn kernels[3][2] = {{gemm2_kernel<0, 0>, gemm2_kernel<0, 1>},
+                                         {gemm2_kernel<1, 0>, gemm2_kernel<1, 1>},
+                                         {gemm2_kernel<2, 0>, gemm2_kernel<2, 1>}};
   static bool attr_done = false;
   if (!attr_done) {
-    SAM_CHECK_CUDA(cudaFuncSetAttribute(gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2));
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 2; ++b)
+        SAM_CHECK_CUDA(cudaFuncSetAttribute(kernels[a][b], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2));
     attr_done = true;
   }
+  if (ep.act != 0 && ep.act != 1) return -1;
+  const KernelFn kernel = kernels[ep.out_fmt][ep.act];
   Gemm2Params p;
   p.bias = ep.bias;
   p.act = ep.act;
@@ -386,7 +396,7 @@ int samk_gemm2(const void* A, int lda, const void* W, int ldw, int M, int N, int
     cfg.attrs = at;
     cfg.numAttrs = 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, gemm2_kernel, &cfg) != cudaSuccess || n <= 0) {
+    if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess || n <= 0) {
       (void)cudaGetLastError();
       n = samhost::sm_count() / 2;
     }
@@ -398,7 +408,7 @@ int samk_gemm2(const void* A, int lda, const void* W, int ldw, int M, int N, int
   samhost::LaunchScope scope(samhost::KC_GEMM, stream, 2.0 * M * N * K,
                              2.0 * (static_cast<double>(M) * K + static_cast<double>(N) * K) + out_b * M * N +
                                  (ep.res ? 4.0 * M * N : 0.0));
-  gemm2_kernel<<<2 * clusters, kThreads2, kSmem2, stream>>>(tmA, tmB, tmC, p);
+  kernel<<<2 * clusters, kThreads2, kSmem2, stream>>>(tmA, tmB, tmC, p);
   SAM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

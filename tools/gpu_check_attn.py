@@ -127,17 +127,20 @@ def attn_bench():
     gw = ops.global_rel_table(torch.randn(127, 80, device=dev) * 0.1, dt)
     for fn, name, flops in ((lambda: ops.attn_window(qkv, bias, tab, B, heads), "attn_window", B * 5.27e9),
                             (lambda: ops.attn_global(qkv, gh, gw, B, heads), "attn_global", B * 87.2e9)):
-        for _ in range(3):
+        for _ in range(20):
             fn()
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(10):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / 10
-        print(f"{name} B=16: {ms:.3f} ms  {flops / ms / 1e9:.1f} TFLOP/s")
+        times = []
+        for rep in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(40):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1) / 40)
+        ms = sorted(times)[len(times) // 2]
+        print(f"{name} B=16: median {ms:.3f} ms (min {min(times):.3f} max {max(times):.3f})  {flops / ms / 1e9:.1f} TFLOP/s")
 
 
 if __name__ == "__main__":
