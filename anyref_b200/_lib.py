@@ -53,7 +53,9 @@ _PROTOS = {
                             c_void_p],
     "sam_decoder_weight_elems": [_DEC_P],
     "sam_decoder_workspace_bytes": [_DEC_P, c_int, c_int],
-    "sam_decoder_forward": [_DEC_P, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
+    "sam_decoder_derived_bytes": [_DEC_P],
+    "sam_decoder_prepare": [_DEC_P, c_void_p, c_void_p, c_void_p],
+    "sam_decoder_forward": [_DEC_P, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
                             c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p],
     "sam_postprocess_masks": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                               c_float, c_void_p],
@@ -67,7 +69,7 @@ _PROTOS = {
 }
 _RESTYPES = {"sam_last_error": c_char_p, "sam_encoder_w16_elems": c_size_t, "sam_encoder_w32_elems": c_size_t,
              "sam_encoder_workspace_bytes": c_size_t, "sam_decoder_weight_elems": c_size_t,
-             "sam_decoder_workspace_bytes": c_size_t, "sam_launch_count": C.c_longlong, "sam_profile_enable": None,
+             "sam_decoder_workspace_bytes": c_size_t, "sam_decoder_derived_bytes": c_size_t, "sam_launch_count": C.c_longlong, "sam_profile_enable": None,
              "sam_profile_reset": None, "sam_profile_get": None}
 
 

@@ -74,14 +74,19 @@ int sam_encoder_forward(const SamEncoderShape* s, const void* w16, const float* 
 }
 size_t sam_decoder_weight_elems(const SamDecoderShape* s) { return samk_decoder_weight_elems(*s); }
 size_t sam_decoder_workspace_bytes(const SamDecoderShape* s, int n, int k) { return samk_decoder_workspace_bytes(*s, n, k); }
-int sam_decoder_forward(const SamDecoderShape* s, const float* weights, const void* image_embeddings, int emb_fmt,
+size_t sam_decoder_derived_bytes(const SamDecoderShape* s) { return samk_decoder_derived_bytes(*s); }
+int sam_decoder_prepare(const SamDecoderShape* s, const float* weights, void* derived, void* stream) {
+  if (!s || !weights || !derived) return samhost::set_error(1, "sam_decoder_prepare: NULL argument");
+  return samk_decoder_prepare(*s, weights, derived, S(stream));
+}
+int sam_decoder_forward(const SamDecoderShape* s, const float* weights, const void* derived, const void* image_embeddings, int emb_fmt,
                         const int* img_index, const void* image_pe, int pe_fmt, const void* sparse, int sparse_fmt,
                         int n, int k, const void* dense_vec, const void* dense_full, int dense_fmt, void* masks,
                         void* iou, int out_fmt, void* workspace, size_t workspace_bytes, void* stream) {
-  if (!s || !weights || !image_embeddings || !image_pe || !masks || !iou || !workspace)
+  if (!s || !weights || !derived || !image_embeddings || !image_pe || !masks || !iou || !workspace)
     return samhost::set_error(1, "sam_decoder_forward: NULL argument");
   if (k > 0 && !sparse) return samhost::set_error(1, "sam_decoder_forward: sparse embeddings missing");
-  return samk_decoder_forward(*s, weights, image_embeddings, emb_fmt, img_index, image_pe, pe_fmt, sparse, sparse_fmt,
+  return samk_decoder_forward(*s, weights, derived, image_embeddings, emb_fmt, img_index, image_pe, pe_fmt, sparse, sparse_fmt,
                               n, k, dense_vec, dense_full, dense_fmt, masks, iou, out_fmt, workspace, workspace_bytes,
                               S(stream));
 }

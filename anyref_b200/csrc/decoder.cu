@@ -196,6 +196,60 @@ dec_linear_kernel(const LinArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Tensor-core path for the image-token-side linears (M = n*4096 rows): fp32 accuracy from bf16 tcgen05 MMAs by
+// operand splitting.  x = hi + lo with hi = bf16(x), lo = bf16(x - hi)  (16 mantissa bits together);
+//   x.w ~= hi_x.hi_w + hi_x.lo_w + lo_x.hi_w          (the dropped lo.lo term is ~2^-18 relative)
+// which is ONE GEMM over a 3x longer K:  A' = [hi_x | hi_x | lo_x],  W' = [hi_w | lo_w | hi_w], fp32 accumulation in
+// TMEM (gemm2.cu).  The activation split (with the positional-encoding add fused in) is one elementwise pass; the
+// weight split is done once per weight change (samk_decoder_prepare).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+dec_split3_rows_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ X2, int ldx2, int x2_mod,
+                       uint16_t* __restrict__ out, int M, int K) {
+  const int kq = K >> 2;
+  const size_t total = static_cast<size_t>(M) * kq;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int row = static_cast<int>(i / kq), k = static_cast<int>(i % kq) * 4;
+    float4 v = *reinterpret_cast<const float4*>(X + static_cast<size_t>(row) * ldx + k);
+    if (X2) {
+      const float4 u = *reinterpret_cast<const float4*>(X2 + static_cast<size_t>(row % x2_mod) * ldx2 + k);
+      v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+    }
+    const float f[4] = {v.x, v.y, v.z, v.w};
+    uint16_t hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __nv_bfloat16 h = __float2bfloat16_rn(f[j]);
+      const __nv_bfloat16 l = __float2bfloat16_rn(f[j] - __bfloat162float(h));
+      hi[j] = *reinterpret_cast<const uint16_t*>(&h);
+      lo[j] = *reinterpret_cast<const uint16_t*>(&l);
+    }
+    const uint2 H = make_uint2(hi[0] | (uint32_t(hi[1]) << 16), hi[2] | (uint32_t(hi[3]) << 16));
+    const uint2 L = make_uint2(lo[0] | (uint32_t(lo[1]) << 16), lo[2] | (uint32_t(lo[3]) << 16));
+    uint16_t* o = out + static_cast<size_t>(row) * (3 * K) + k;
+    *reinterpret_cast<uint2*>(o) = H;
+    *reinterpret_cast<uint2*>(o + K) = H;
+    *reinterpret_cast<uint2*>(o + 2 * K) = L;
+  }
+}
+
+// W fp32 [N, K] -> [N, 3K] bf16 = [hi | lo | hi]
+__global__ void dec_wsplit3_kernel(const float* __restrict__ W, uint16_t* __restrict__ out, int N, int K) {
+  const int total = N * K;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int n = i / K, k = i % K;
+    const float x = W[i];
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+    uint16_t* o = out + static_cast<size_t>(n) * (3 * K) + k;
+    o[0] = *reinterpret_cast<const uint16_t*>(&h);
+    o[K] = *reinterpret_cast<const uint16_t*>(&l);
+    o[2 * K] = *reinterpret_cast<const uint16_t*>(&h);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Attention kernels (transformer.py:220-242).  Inputs are the already-projected q / k / v.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int TMAX = 16;    // max tokens per prompt (1 IoU + 4 mask + up to 11 prompt embeddings)
@@ -619,6 +673,33 @@ int carve_weights(const SamDecoderShape& s, const float* blob, DecoderWeights* w
   return 0;
 }
 
+// bf16x3-split copies of the weights that multiply image-token-sized operands (layout of the `derived` buffer)
+struct DerivedW {
+  const uint16_t *t2i_k[9], *t2i_v[9];   // per layer; index depth = final_attn_token_to_image
+  const uint16_t *i2t_q[8], *i2t_o[8];
+  const uint16_t* up0;
+  size_t total;   // elements
+};
+void carve_derived(const SamDecoderShape& s, const uint16_t* base, DerivedW* d) {
+  const size_t C = s.C, Ci = C / 2;
+  size_t off = 0;
+  auto take = [&](size_t n) {
+    const uint16_t* p = base ? base + off : nullptr;
+    off += (n + 7) & ~size_t(7);
+    return p;
+  };
+  for (int l = 0; l <= s.depth; ++l) {
+    d->t2i_k[l] = take(Ci * 3 * C);
+    d->t2i_v[l] = take(Ci * 3 * C);
+  }
+  for (int l = 0; l < s.depth; ++l) {
+    d->i2t_q[l] = take(Ci * 3 * C);
+    d->i2t_o[l] = take(C * 3 * Ci);
+  }
+  d->up0 = take(C * 3 * C);
+  d->total = off;
+}
+
 int check_shape(const SamDecoderShape& s) {
   SAM_REQUIRE(s.C == 256 && s.heads == 8, "mask decoder: transformer_dim must be 256 with 8 heads (got %d, %d)", s.C, s.heads);
   SAM_REQUIRE(s.depth >= 1 && s.depth <= 8, "mask decoder: depth %d unsupported", s.depth);
@@ -636,6 +717,38 @@ size_t samk_decoder_weight_elems(const SamDecoderShape& s) {
   return w.total;
 }
 
+size_t samk_decoder_derived_bytes(const SamDecoderShape& s) {
+  DerivedW d;
+  carve_derived(s, nullptr, &d);
+  return d.total * sizeof(uint16_t);
+}
+
+int samk_decoder_prepare(const SamDecoderShape& s, const float* blob, void* derived, cudaStream_t st) {
+  if (int rc = check_shape(s)) return rc;
+  SAM_REQUIRE((reinterpret_cast<uintptr_t>(derived) & 15) == 0, "mask decoder: derived-weight buffer must be 16-byte aligned");
+  DecoderWeights w;
+  carve_weights(s, blob, &w);
+  DerivedW d;
+  carve_derived(s, static_cast<const uint16_t*>(derived), &d);
+  const int C = s.C, Ci = C / 2;
+  auto split = [&](const float* W, const uint16_t* out, int N, int K) {
+    samhost::LaunchScope scope(samhost::KC_DECODER, st);
+    dec_wsplit3_kernel<<<(N * K + 255) / 256, 256, 0, st>>>(W, const_cast<uint16_t*>(out), N, K);
+  };
+  for (int l = 0; l <= s.depth; ++l) {
+    const AttnW& a = (l < s.depth) ? w.layer[l].t2i : w.final_attn;
+    split(a.kw, d.t2i_k[l], Ci, C);
+    split(a.vw, d.t2i_v[l], Ci, C);
+  }
+  for (int l = 0; l < s.depth; ++l) {
+    split(w.layer[l].i2t.qw, d.i2t_q[l], Ci, C);
+    split(w.layer[l].i2t.ow, d.i2t_o[l], C, Ci);
+  }
+  split(w.up0w, d.up0, C, C);
+  SAM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 size_t samk_decoder_workspace_bytes(const SamDecoderShape& s, int n, int k) {
   const size_t HW = static_cast<size_t>(s.grid) * s.grid, C = s.C, T = 1 + s.num_mask_tokens + k;
   size_t f = 0;
@@ -645,10 +758,11 @@ size_t samk_decoder_workspace_bytes(const SamDecoderShape& s, int n, int k) {
   f += n * T * C * 8;                  // tokens0, queries, tq, tk, tv, ta, tb + slack
   f += n * T * s.mlp_dim;              // mlp hidden
   f += n * s.num_mask_tokens * (C / 8);  // hyper_in
+  f += (3 * n * HW * C) / 2 + 16;         // a3: bf16 [n*HW, 3C] operand of the split-bf16 GEMMs
   return f * sizeof(float) + 256;
 }
 
-int samk_decoder_forward(const SamDecoderShape& s, const float* blob, const void* image_embeddings, int emb_fmt,
+int samk_decoder_forward(const SamDecoderShape& s, const float* blob, const void* derived, const void* image_embeddings, int emb_fmt,
                          const int* img_index, const void* image_pe, int pe_fmt, const void* sparse, int sparse_fmt,
                          int n, int k, const void* dense_vec, const void* dense_full, int dense_fmt, void* masks,
                          void* iou, int out_fmt, void* workspace, size_t workspace_bytes, cudaStream_t st) {
@@ -661,6 +775,10 @@ int samk_decoder_forward(const SamDecoderShape& s, const float* blob, const void
               "mask decoder: workspace / weight blob must be 16-byte aligned");
   DecoderWeights w;
   carve_weights(s, blob, &w);
+  DerivedW dw;
+  carve_derived(s, static_cast<const uint16_t*>(derived), &dw);
+  SAM_REQUIRE(derived != nullptr && (reinterpret_cast<uintptr_t>(derived) & 15) == 0,
+              "mask decoder: derived weights missing (call sam_decoder_prepare) or misaligned");
 
   float* f = static_cast<float*>(workspace);
   auto take = [&](size_t nelem) {
@@ -684,6 +802,7 @@ int samk_decoder_forward(const SamDecoderShape& s, const float* blob, const void
   float* tb = take(tc);
   float* hid = take((size_t)n * T * s.mlp_dim);
   float* hyper = take((size_t)n * nm * (C / 8));
+  uint16_t* a3 = reinterpret_cast<uint16_t*>(take(((size_t)3 * n * HW * C) / 2 + 8));
   const int MT = n * T, MK = n * HW;
   const float sc_self = 1.0f / sqrtf(static_cast<float>(C / s.heads));
   const float sc_cross = 1.0f / sqrtf(static_cast<float>(Ci / s.heads));
@@ -714,16 +833,34 @@ int samk_decoder_forward(const SamDecoderShape& s, const float* blob, const void
   do {                                             \
     if (int rc_ = launch_linear(__VA_ARGS__, st)) return rc_; \
   } while (0)
+  // image-token-side linear on the tensor cores: Y = (X [+ X2]) . W^T + b, or Y += ... when `inplace`
+  auto lin_tc = [&](const float* X, int ldx, const float* X2, int ldx2, int x2_mod, const uint16_t* W3, const float* b,
+                    bool inplace, float* Y, int ldy, int M, int N, int K) -> int {
+    {
+      samhost::LaunchScope scope(samhost::KC_DECODER, st);
+      const size_t total = static_cast<size_t>(M) * (K / 4);
+      dec_split3_rows_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(X, ldx, X2, ldx2,
+                                                                                         x2_mod > 0 ? x2_mod : M, a3, M, K);
+      SAM_CHECK_CUDA(cudaGetLastError());
+    }
+    GemmEpilogue ep{Y, ldy, SAM_F32, b, 0, inplace ? Y : nullptr, ldy, M};
+    return samk_gemm(a3, 3 * K, W3, 3 * K, M, N, 3 * K, SAM_BF16, ep, st);
+  };
+#define LINTC(...)                              \
+  do {                                          \
+    if (int rc_ = lin_tc(__VA_ARGS__)) return rc_; \
+  } while (0)
 #define LNORM(x, res, gw, gb, out, M)                                                                       \
   do {                                                                                                      \
     if (int rc_ = samk_layernorm_rows(x, C, res, C, gw, gb, 1e-5f, out, C, SAM_F32, M, C, 1, st)) return rc_; \
   } while (0)
 
   // token -> image attention: queries(+pe) attend to keys(+pe); result (after out_proj) added to `qry`, then LN.
-  auto token_to_image = [&](const AttnW& a, const float* gw, const float* gb) -> int {
+  auto token_to_image = [&](const AttnW& a, const uint16_t* k3, const uint16_t* v3, const float* gw,
+                            const float* gb) -> int {
     LIN(qry, C, tok0, C, MT, a.qw, a.qb, nullptr, 0, tq, Ci, MT, Ci, C, 0);
-    LIN(keys, C, pe_t, C, HW, a.kw, a.kb, nullptr, 0, kbuf, Ci, MK, Ci, C, 0);
-    LIN(keys, C, nullptr, 0, 0, a.vw, a.vb, nullptr, 0, vbuf, Ci, MK, Ci, C, 0);
+    LINTC(keys, C, pe_t, C, HW, k3, a.kb, false, kbuf, Ci, MK, Ci, C);
+    LINTC(keys, C, nullptr, 0, 0, v3, a.vb, false, vbuf, Ci, MK, Ci, C);
     dim3 grid(s.heads, n, (T + TQ - 1) / TQ);
     samhost::LaunchScope scope(samhost::KC_DECODER, st, 4.0 * n * T * HW * Ci);
     dec_attn_t2i_kernel<<<grid, 256, t2i_smem, st>>>(tq, kbuf, vbuf, ta, T, HW, Ci, sc_cross);
@@ -749,13 +886,13 @@ int samk_decoder_forward(const SamDecoderShape& s, const float* blob, const void
     LIN(ta, C, nullptr, 0, 0, L.self_attn.ow, L.self_attn.ob, (l == 0) ? nullptr : qry, C, tb, C, MT, C, C, 0);
     LNORM(tb, nullptr, L.n1w, L.n1b, qry, MT);
     // (2) token -> image cross attention
-    if (int rc = token_to_image(L.t2i, L.n2w, L.n2b)) return rc;
+    if (int rc = token_to_image(L.t2i, dw.t2i_k[l], dw.t2i_v[l], L.n2w, L.n2b)) return rc;
     // (3) MLP (ReLU)
     LIN(qry, C, nullptr, 0, 0, L.l1w, L.l1b, nullptr, 0, hid, s.mlp_dim, MT, s.mlp_dim, C, 1);
     LIN(hid, s.mlp_dim, nullptr, 0, 0, L.l2w, L.l2b, qry, C, tb, C, MT, C, s.mlp_dim, 0);
     LNORM(tb, nullptr, L.n3w, L.n3b, qry, MT);
     // (4) image -> token cross attention
-    LIN(keys, C, pe_t, C, HW, L.i2t.qw, L.i2t.qb, nullptr, 0, qbuf, Ci, MK, Ci, C, 0);
+    LINTC(keys, C, pe_t, C, HW, dw.i2t_q[l], L.i2t.qb, false, qbuf, Ci, MK, Ci, C);
     LIN(qry, C, tok0, C, MT, L.i2t.kw, L.i2t.kb, nullptr, 0, tk, Ci, MT, Ci, C, 0);
     LIN(qry, C, nullptr, 0, 0, L.i2t.vw, L.i2t.vb, nullptr, 0, tv, Ci, MT, Ci, C, 0);
     {
@@ -764,11 +901,11 @@ int samk_decoder_forward(const SamDecoderShape& s, const float* blob, const void
       dec_attn_i2t_kernel<<<grid, 256, 0, st>>>(qbuf, tk, tv, qbuf, T, HW, Ci, s.heads, sc_cross);
       SAM_CHECK_CUDA(cudaGetLastError());
     }
-    LIN(qbuf, Ci, nullptr, 0, 0, L.i2t.ow, L.i2t.ob, keys, C, tmp, C, MK, C, Ci, 0);
-    LNORM(tmp, nullptr, L.n4w, L.n4b, keys, MK);
+    LINTC(qbuf, Ci, nullptr, 0, 0, dw.i2t_o[l], L.i2t.ob, true, keys, C, MK, C, Ci);   // keys += out_proj(attn)
+    LNORM(keys, nullptr, L.n4w, L.n4b, keys, MK);
   }
   // final token -> image attention + norm (transformer.py:99-104)
-  if (int rc = token_to_image(w.final_attn, w.nfw, w.nfb)) return rc;
+  if (int rc = token_to_image(w.final_attn, dw.t2i_k[s.depth], dw.t2i_v[s.depth], w.nfw, w.nfb)) return rc;
 
   // hypernetwork MLPs + IoU head
   {
@@ -783,12 +920,13 @@ int samk_decoder_forward(const SamDecoderShape& s, const float* blob, const void
     SAM_CHECK_CUDA(cudaGetLastError());
   }
   // upscaling + mask product
-  LIN(keys, C, nullptr, 0, 0, w.up0w, w.up0b, nullptr, 0, tmp, C, MK, C, C, 0);
+  LINTC(keys, C, nullptr, 0, 0, dw.up0, w.up0b, false, tmp, C, MK, C, C);
   samhost::LaunchScope scope_up(samhost::KC_DECODER, st, 2.0 * MK * 4 * (4.0 * (C / 8) * (C / 4) + 4.0 * nm * (C / 8)));
   dec_upscale_tail_kernel<<<static_cast<unsigned>((size_t)MK * 4 / 256), 256, 0, st>>>(
       tmp, w.upln_w, w.upln_b, w.up1w, w.up1b, hyper, masks, out_fmt, g, nm);
   SAM_CHECK_CUDA(cudaGetLastError());
 #undef LIN
+#undef LINTC
 #undef LNORM
   return 0;
 }

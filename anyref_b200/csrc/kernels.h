@@ -73,7 +73,9 @@ int samk_encoder_forward(const SamEncoderShape& s, const void* w16, const float*
                          int B, void* out, int out_fmt, void* workspace, size_t workspace_bytes, cudaStream_t st);
 size_t samk_decoder_weight_elems(const SamDecoderShape& s);
 size_t samk_decoder_workspace_bytes(const SamDecoderShape& s, int n, int k);
-int samk_decoder_forward(const SamDecoderShape& s, const float* blob, const void* image_embeddings, int emb_fmt,
+size_t samk_decoder_derived_bytes(const SamDecoderShape& s);
+int samk_decoder_prepare(const SamDecoderShape& s, const float* blob, void* derived, cudaStream_t st);
+int samk_decoder_forward(const SamDecoderShape& s, const float* blob, const void* derived, const void* image_embeddings, int emb_fmt,
                          const int* img_index, const void* image_pe, int pe_fmt, const void* sparse, int sparse_fmt,
                          int n, int k, const void* dense_vec, const void* dense_full, int dense_fmt, void* masks,
                          void* iou, int out_fmt, void* workspace, size_t workspace_bytes, cudaStream_t st);

@@ -65,7 +65,11 @@ class MaskDecoder(nn.Module):
         sig = (_runtime.params_signature(self), grid)
         if self._packed is None or self._packed[0] != sig:
             shape, blob = _pack.pack_decoder(self, grid)
-            self._packed = (sig, shape, blob)
+            lib = _lib.load()
+            derived = torch.empty(lib.sam_decoder_derived_bytes(C.byref(shape)), dtype=torch.uint8, device=blob.device)
+            rc = lib.sam_decoder_prepare(C.byref(shape), blob.data_ptr(), derived.data_ptr(), _lib.stream_ptr(blob.device))
+            _lib.check(rc, "sam_decoder_prepare")
+            self._packed = (sig, shape, blob, derived)
         return self._packed[1:]
 
     def forward(self, image_embeddings: torch.Tensor, image_pe: torch.Tensor,
@@ -116,14 +120,14 @@ class MaskDecoder(nn.Module):
             image_index = image_index.contiguous()
         elif emb.shape[0] != 1:
             raise ValueError("image_index is required when several image embeddings are given")
-        shape, blob = self._weights(g)
+        shape, blob, derived = self._weights(g)
         out_dtype = emb.dtype
         masks = torch.empty((n, self.num_mask_tokens, 4 * g, 4 * g), device=emb.device, dtype=out_dtype)
         iou = torch.empty((n, self.num_mask_tokens), device=emb.device, dtype=out_dtype)
         nbytes = lib.sam_decoder_workspace_bytes(C.byref(shape), n, k)
         keep, wsp = _runtime.workspace(emb.device, nbytes, "decoder")
         rc = lib.sam_decoder_forward(
-            C.byref(shape), blob.data_ptr(), emb.data_ptr(), _lib.fmt_of(emb.dtype),
+            C.byref(shape), blob.data_ptr(), derived.data_ptr(), emb.data_ptr(), _lib.fmt_of(emb.dtype),
             image_index.data_ptr() if image_index is not None else None, pe.data_ptr(), _lib.fmt_of(pe.dtype),
             sparse.data_ptr() if k > 0 else None, _lib.fmt_of(sparse.dtype), n, k,
             dense_vec.data_ptr() if dense_vec is not None else None,

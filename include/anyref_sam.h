@@ -156,7 +156,12 @@ int sam_encoder_forward(const SamEncoderShape* shape, const void* w16, const flo
  */
 size_t sam_decoder_weight_elems(const SamDecoderShape* shape);
 size_t sam_decoder_workspace_bytes(const SamDecoderShape* shape, int n, int k);
-int sam_decoder_forward(const SamDecoderShape* shape, const float* weights, const void* image_embeddings, int emb_fmt,
+/* `derived`: device buffer of sam_decoder_derived_bytes() bytes holding split-bf16 copies of the weights that multiply
+ * image-token-sized operands; filled by sam_decoder_prepare whenever `weights` change. */
+size_t sam_decoder_derived_bytes(const SamDecoderShape* shape);
+int sam_decoder_prepare(const SamDecoderShape* shape, const float* weights, void* derived, void* stream);
+int sam_decoder_forward(const SamDecoderShape* shape, const float* weights, const void* derived,
+                        const void* image_embeddings, int emb_fmt,
                         const int* img_index, const void* image_pe, int pe_fmt, const void* sparse, int sparse_fmt,
                         int n, int k, const void* dense_vec, const void* dense_full, int dense_fmt, void* masks,
                         void* iou, int out_fmt, void* workspace, size_t workspace_bytes, void* stream);

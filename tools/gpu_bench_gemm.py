@@ -29,7 +29,8 @@ def main():
     iters = int(sys.argv[1]) if len(sys.argv) > 1 else 200
     x32 = torch.randn(M, 1280, device=dev)
     for name, N, K, kind in (("qkv", 3840, 1280, "bias16"), ("proj", 1280, 1280, "res32"), ("lin1", 5120, 1280, "gelu16"),
-                             ("lin2", 1280, 5120, "res32"), ("plain_qkv", 3840, 1280, "plain16"),
+                             ("lin2", 1280, 5120, "res32"), ("lin1_noact", 5120, 1280, "bias16"), ("lin1", 5120, 1280, "gelu16"),
+                             ("plain_qkv", 3840, 1280, "plain16"),
                              ("plain_proj", 1280, 1280, "plain16"), ("proj_f32out", 1280, 1280, "f32")):
         a = (torch.randn(M, K, device=dev) * 0.5).to(dt)
         w = (torch.randn(N, K, device=dev) * 0.05).to(dt)
