@@ -7,6 +7,8 @@
 //   samk_im2col3x3       : NHWC [B,g,g,C] -> [B*g*g, 9C] with zero padding (neck 3x3 conv, image_encoder.py:100-106)
 //   samk_ln_nhwc_to_nchw : LayerNorm2d (common.py:31-43) on NHWC fp32 rows fused with the NHWC->NCHW transposition
 //                          that produces the encoder output [B,C,g,g] (image_encoder.py:107, :124)
+#include <stdlib.h>
+
 #include "host_common.h"
 #include "kernels.h"
 #include "ptx.cuh"
@@ -80,6 +82,111 @@ layernorm_rows_kernel(const float* x, int ldx, const float* res, int ldr, const 
         u.x = ptx::pack2(y.x, y.y, out_fmt);
         u.y = ptx::pack2(y.z, y.w, out_fmt);
         reinterpret_cast<uint2*>(static_cast<uint16_t*>(out) + static_cast<size_t>(row) * ldo)[idx] = u;
+      }
+    }
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Streaming LayerNorm for the encoder's big activations (M = B*4096 rows of 1280 fp32 -> 16-bit operand rows).
+// The register-resident kernel above keeps only ~120 KB of loads in flight per SM (one row per warp, bounded by
+// the register file), which is half of what HBM3e needs.  Here one persistent CTA per SM keeps a 32-row ring in
+// shared memory filled by 1-D bulk async copies (TMA engine, mbarrier completion): 8 consumer warps normalise rows
+// straight out of shared memory while the producer thread keeps ~160 KB of reads in flight.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kLnStages = 5;      // ring slots (100 KB: two CTAs per SM)
+constexpr int kLnGroup = 4;       // consecutive rows per slot (one bulk copy)
+
+constexpr int kLnConsumerWarps = 16;
+
+__global__ void __launch_bounds__(32 * (kLnConsumerWarps + 1), 2)
+layernorm_stream_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                        float eps, void* __restrict__ out, int ldo, int out_fmt, int M, int C) {
+  extern __shared__ __align__(128) uint8_t ln_smem[];
+  const int row_bytes = C * 4;
+  const int slot_bytes = kLnGroup * row_bytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(ln_smem + kLnStages * slot_bytes);
+  uint64_t* empty = full + kLnStages;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kLnStages; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&empty[s], kLnGroup);
+    }
+    ptx::fence_mbar_init();
+  }
+  __syncthreads();
+  // row groups of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...  (x rows are contiguous: ldx == C)
+  const int num_groups = M / kLnGroup;
+  const int my_groups = (num_groups - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  if (warp == kLnConsumerWarps) {
+    if (lane == 0) {
+      for (int i = 0; i < my_groups; ++i) {
+        const int s = i % kLnStages;
+        const uint32_t ph = (i / kLnStages) & 1;
+        if (i >= kLnStages) ptx::mbar_wait(&empty[s], ph ^ 1);
+        const size_t grp = static_cast<size_t>(blockIdx.x) + static_cast<size_t>(i) * gridDim.x;
+        ptx::mbar_expect_tx(&full[s], slot_bytes);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         ptx::smem_u32(ln_smem + s * slot_bytes)),
+                     "l"(x + grp * kLnGroup * C), "r"(slot_bytes), "r"(ptx::smem_u32(&full[s]))
+                     : "memory");
+      }
+    }
+    return;
+  }
+  // consumer warp w: row (w & 3) of every (kLnConsumerWarps / 4)-th group, starting with group (w >> 2)
+  const int nvec = C >> 2;
+  const int sub = warp & (kLnGroup - 1);
+  for (int i = warp >> 2; i < my_groups; i += kLnConsumerWarps / kLnGroup) {
+    const int s = i % kLnStages;
+    const uint32_t ph = (i / kLnStages) & 1;
+    ptx::mbar_wait(&full[s], ph);
+    const float4* xr = reinterpret_cast<const float4*>(ln_smem + s * slot_bytes + sub * row_bytes);
+    float4 v[kLnMaxVec];
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < kLnMaxVec; ++j) {
+      const int idx = lane + j * 32;
+      if (idx < nvec) {
+        v[j] = xr[idx];
+        sum += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(&empty[s]);   // row copied to registers: hand the slot back
+    const float mean = warp_sum(sum) / static_cast<float>(C);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < kLnMaxVec; ++j) {
+      const int idx = lane + j * 32;
+      if (idx < nvec) {
+        const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+        q += (a * a + b * b) + (c * c + d * d);
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(C) + eps);
+    const size_t row = (static_cast<size_t>(blockIdx.x) + static_cast<size_t>(i) * gridDim.x) * kLnGroup + sub;
+#pragma unroll
+    for (int j = 0; j < kLnMaxVec; ++j) {
+      const int idx = lane + j * 32;
+      if (idx < nvec) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + idx);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + idx);
+        float4 y;
+        y.x = (v[j].x - mean) * rstd * g.x + b.x;
+        y.y = (v[j].y - mean) * rstd * g.y + b.y;
+        y.z = (v[j].z - mean) * rstd * g.z + b.z;
+        y.w = (v[j].w - mean) * rstd * g.w + b.w;
+        if (out_fmt == 2) {
+          reinterpret_cast<float4*>(static_cast<float*>(out) + row * ldo)[idx] = y;
+        } else {
+          uint2 u;
+          u.x = ptx::pack2(y.x, y.y, out_fmt);
+          u.y = ptx::pack2(y.z, y.w, out_fmt);
+          reinterpret_cast<uint2*>(static_cast<uint16_t*>(out) + row * ldo)[idx] = u;
+        }
       }
     }
   }
@@ -200,6 +307,21 @@ int samk_layernorm_rows(const float* x, int ldx, const float* res, int ldr, cons
   SAM_REQUIRE(!normalize || (gamma && beta), "layernorm: affine parameters missing");
   samhost::LaunchScope scope(samhost::KC_LAYERNORM, stream, 0.0,
                              static_cast<double>(M) * C * ((res ? 8.0 : 4.0) + (out_fmt == 2 ? 4.0 : 2.0)));
+  // big plain LayerNorms (the encoder's norm1 / norm2) stream through the shared-memory ring
+  static const bool no_stream = getenv("SAM_LN_NO_STREAM") != nullptr;
+  if (!no_stream && normalize && !res && M >= 8192 && M % kLnGroup == 0 && (C * 4) % 16 == 0 && ldx == C &&
+      (reinterpret_cast<uintptr_t>(x) & 15) == 0 && x != out) {
+    const int smem = kLnStages * kLnGroup * C * 4 + 2 * kLnStages * 8;
+    static int smem_set = 0;
+    if (smem > smem_set) {
+      SAM_CHECK_CUDA(cudaFuncSetAttribute(layernorm_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      smem_set = smem;
+    }
+    int grid = 2 * samhost::sm_count();
+    layernorm_stream_kernel<<<grid, 32 * (kLnConsumerWarps + 1), smem, stream>>>(x, gamma, beta, eps, out, ldo, out_fmt, M, C);
+    SAM_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   layernorm_rows_kernel<<<(M + 7) / 8, 256, 0, stream>>>(x, ldx, res, ldr, gamma, beta, eps, out, ldo, out_fmt, M, C,
                                                          normalize);
   SAM_CHECK_CUDA(cudaGetLastError());
