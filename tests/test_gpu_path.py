@@ -161,11 +161,12 @@ def test_parameter_updates_are_picked_up(tiny):
     sam.image_encoder.set_operand_dtype(torch.float16)
     x = tiny["x"][:1].cuda()
     a = sam.image_encoder(x)
+    saved = sam.image_encoder.neck[3].bias.detach().clone()
     with torch.no_grad():
         sam.image_encoder.neck[3].bias.add_(1.0)
     b = sam.image_encoder(x)
     with torch.no_grad():
-        sam.image_encoder.neck[3].bias.sub_(1.0)
+        sam.image_encoder.neck[3].bias.copy_(saved)     # (bias + 1) - 1 != bias in fp32: restore the exact bits
     assert (b - a - 1.0).abs().max().item() < 1e-5
     assert torch.equal(sam.image_encoder(x), a)     # deterministic + restored
 
