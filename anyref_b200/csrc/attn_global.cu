@@ -341,10 +341,12 @@ int samk_attn_global(const void* qkv, const void* rh_rev, const void* rw_rev, vo
   SAM_REQUIRE(fmt == 0 || fmt == 1, "attn_global: fmt must be fp16/bf16");
   SAM_REQUIRE(E == heads * HD, "attn_global: head_dim must be 80 (E=%d heads=%d)", E, heads);
   SAM_REQUIRE(B > 0, "attn_global: empty batch");
-  // default: the warp-specialised two-tile kernel (attn_global2.cu); SAM_ATTN_GLOBAL_V1=1 selects this file's simpler
-  // one-tile-per-CTA kernel
+  // default: the decoupled-pipeline kernel (attn_global3.cu); SAM_ATTN_GLOBAL_V2=1 selects the two-tile ping-pong kernel
+  // (attn_global2.cu), SAM_ATTN_GLOBAL_V1=1 this file's simpler one-tile-per-CTA kernel
   static const bool use_v1 = getenv("SAM_ATTN_GLOBAL_V1") != nullptr;
-  if (!use_v1) return samk_attn_global2(qkv, rh_rev, rw_rev, out, B, E, heads, fmt, stream);
+  static const bool use_v2 = getenv("SAM_ATTN_GLOBAL_V2") != nullptr;
+  if (use_v2) return samk_attn_global2(qkv, rh_rev, rw_rev, out, B, E, heads, fmt, stream);
+  if (!use_v1) return samk_attn_global3(qkv, rh_rev, rw_rev, out, B, E, heads, fmt, stream);
   GlobAttnMaps maps;
   const int is_bf16 = (fmt == 1);
   const uint64_t rows = static_cast<uint64_t>(B) * G * G;

@@ -1,0 +1,506 @@
+// Global (64x64 = 4096 token) attention of the 4 non-windowed SAM ViT-H blocks, decoupled-pipeline version ("v3").
+// Same contract as attn_global.cu (replaces image_encoder.py:235-257 + :354-392 for blocks 7/15/23/31).
+//
+// v2 (attn_global2.cu) ping-pongs two 128-query tiles on one S buffer each, so a tile's softmax warpgroup idles while
+// the tensor core produces its next S (P.V of block j, then Q.K^T of block j+1, plus two mbarrier hand-offs): ncu
+// showed the softmax warps parked on that wait for a third of the kernel.  v3 removes the dependency:
+//   * key blocks are ONE image row (64 keys), S is double-buffered in TMEM (2 x 64 columns per tile) and P is
+//     double-buffered in shared memory, so Q.K^T of block j+1 is issued BEFORE the softmax of block j finishes and the
+//     softmax warps find their next S already waiting;
+//   * logits / probabilities are computed two at a time with the packed fp32 pipe (fma.rn.f32x2 / add.rn.f32x2);
+//   * no running maximum: probabilities are taken against a reference maximum (true maximum of the first key row);
+//     only if a block's probability SUM overflows 2^10 (rare) is the reference moved, O rescaled in TMEM and the block
+//     redone.  The result is exactly softmax -- the reference cancels in O / l.
+//   warp 0      : TMA -- Q tiles once, then K / V rows through 4-stage rings
+//   warp 1      : one thread issues all tcgen05 MMAs:  S_g = Q_g.K^T (128x64x80),  O_g += P_g.V (128x80x64)
+//   warps 2..5  : softmax of tile 0, one thread per query row (TMEM lane);  warps 6..9: tile 1
+// Relative position (image_encoder.py:354-392): with Rrev[j] = rel_pos[126 - j], q.Rrev[63 - q_pos + k_pos] is the
+// bias term.  Two prologue MMAs per tile compute T_w = Q.Rw_rev^T (all 127 offsets) and T_h = Q.Rh_rev[start..+80)^T;
+// each thread keeps its 64 rel_w terms in registers (fp32) and parks its 64 rel_h terms in shared memory (fp16 pairs).
+// TMEM (512 columns): tile g: S buffers at g*256 + [0,64) and [64,128), O at g*256 + [128,208).
+#include "host_common.h"
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace {
+
+constexpr int HD = 80;
+constexpr int G = 64;            // token grid
+constexpr int BKV = 64;          // keys per block = one image row
+constexpr int kThreadsG = 352;
+constexpr int kNBlk = G * G / BKV;   // 64
+constexpr int kStagesKV = 4;
+
+// shared-memory map (bytes from the 1024-aligned base)
+constexpr int OFF_Q64 = 0;          // 2 tiles x (128 x 128B) SWIZZLE_128B
+constexpr int OFF_K64 = 32768;      // 4 stages x 8192
+constexpr int OFF_V64 = 65536;      // 4 stages x 8192
+constexpr int OFF_P = 98304;        // 2 tiles x 2 buffers x 16384 (128 rows x 128B, SWIZZLE_128B)
+constexpr int OFF_Q16 = 163840;     // 2 x (128 x 32B) SWIZZLE_32B
+constexpr int OFF_K16 = 172032;     // 4 stages x 2048
+constexpr int OFF_V16 = 180224;     // 4 stages x 2048
+constexpr int OFF_RELH = 188416;    // [32 pairs][256 rows] half2 : rel_h terms (x log2e) of every query row
+constexpr int OFF_BAR = 221184;
+constexpr int kSmemBytesG = OFF_BAR + 512 + 1024;
+// prologue overlays (all consumed before the first K / V block lands)
+constexpr int OFF_RW64 = OFF_V64;   // Rw_rev rows 0..127 (K-major B operand), 16 KB
+constexpr int OFF_RW16 = OFF_V16;
+constexpr int OFF_RH = OFF_K64;     // Rh_rev sub-table, 80 rows, un-swizzled core-matrix layout (5 x 80 x 32B)
+constexpr int OFF_STAGE0 = OFF_K64; // tile 0: 128 x 127 fp32 staging of T_w (65024 B <= K64 + V64)
+constexpr int OFF_STAGE1 = OFF_P;   // tile 1: same, over the P buffers
+constexpr int kStageStride = 127;
+
+constexpr uint32_t TM_O = 128;      // column offset of O inside a tile's 256-column slot
+constexpr float kSumLimit = 1024.0f;   // a block's probability sum above this moves the reference maximum
+
+struct GlobAttnMaps3 {
+  CUtensorMap q64, q16;    // 2-D over qkv [B*4096, 3E]: box {64,128} SWIZZLE_128B and {16,128} SWIZZLE_32B
+  CUtensorMap kv64, kv16;  // box {64,64} and {16,64}
+};
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// packed fp32 pairs (Blackwell FFMA2 / FADD2)
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+__device__ __forceinline__ uint32_t row_off64(int r, int c) { return r * 128 + ((c ^ (r & 7)) << 4); }
+__device__ __forceinline__ uint32_t row_off16(int r, int c) { return r * 32 + ((c ^ ((r >> 2) & 1)) << 4); }
+
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// 32 keys (kw = C*32 .. C*32+31) of a key row: logits in the log2 domain relative to the reference maximum (folded
+// into rh), exp2, row-sum (two partial sums), P -> shared memory in operand format.
+template <int C, int FMT>
+__device__ __forceinline__ void softmax_half(const uint32_t (&v)[32], const float (&relw)[64], f32x2 rh2, f32x2 sc2,
+                                             uint32_t prow, int sw, f32x2& bsum2) {
+  uint32_t pk[16];
+#pragma unroll
+  for (int i = 0; i < 32; i += 2) {
+    f32x2 x = fma2(pk2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), sc2, rh2);
+    x = add2(x, pk2(relw[C * 32 + i], relw[C * 32 + i + 1]));
+    float x0, x1;
+    upk2(x, x0, x1);
+    const float p0 = ex2(x0), p1 = ex2(x1);
+    bsum2 = add2(bsum2, pk2(p0, p1));
+    pk[i >> 1] = ptx::pack2t<FMT>(p0, p1);
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int chunk = C * 4 + q;   // 16-byte chunk (8 keys) of the 128-byte P row
+    ptx::st_shared_v4(prow + ((chunk ^ sw) << 4), make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]));
+  }
+}
+
+template <int C>
+__device__ __forceinline__ void max_half(const uint32_t (&v)[32], const float (&relw)[64], float rh, float scale_log2e,
+                                         float& bmax) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 2) {
+    bmax = fmaxf(bmax, fmaxf(fmaf(__uint_as_float(v[i]), scale_log2e, rh) + relw[C * 32 + i],
+                             fmaf(__uint_as_float(v[i + 1]), scale_log2e, rh) + relw[C * 32 + i + 1]));
+  }
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(kThreadsG, 1)
+glob_attn3_kernel(const __grid_constant__ GlobAttnMaps3 maps, const uint16_t* __restrict__ rh_rev,
+                  const uint16_t* __restrict__ rw_rev, uint16_t* __restrict__ out, const int E, const int heads,
+                  const float scale_log2e) {
+  constexpr int fmt = FMT;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* q_full = bars + 0;
+  uint64_t* pro_done = bars + 2;   // all 256 softmax threads finished the prologue (count 256)
+  uint64_t* k_full = bars + 3;     // [4]
+  uint64_t* k_free = bars + 7;     // [4]
+  uint64_t* v_full = bars + 11;    // [4]
+  uint64_t* v_free = bars + 15;    // [4]
+  uint64_t* s_full = bars + 19;    // [tile*2 + buf]  S in TMEM                    (MMA -> softmax)
+  uint64_t* s_free = bars + 23;    // [tile*2 + buf]  S read out, count 128        (softmax -> MMA)
+  uint64_t* p_ready = bars + 27;   // [tile*2 + buf]  P in smem, count 128         (softmax -> MMA)
+  uint64_t* pv_done = bars + 31;   // [tile*2 + buf]  P.V finished: P buffer free  (MMA -> softmax)
+  uint64_t* t_full = bars + 35;    // [2] prologue MMAs of tile g done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 37);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int w = blockIdx.x;
+  const int qt = w % (G * G / 256);          // 256-query group: image rows 4*qt .. 4*qt+3
+  w /= (G * G / 256);
+  const int head = w % heads;
+  const int b = w / heads;
+  const int qh0 = qt * 4;
+  const int th_start = ((60 - qh0) >> 3) << 3;   // first Rh_rev row held in T_h (multiple of 8, >= 0)
+  const uint32_t sbase = ptx::smem_u32(smem);
+  const int row0 = b * (G * G) + qt * 256;
+  const int cq = head * HD, ck = E + head * HD, cv = 2 * E + head * HD;
+
+  if (tid == 0) {
+    ptx::prefetch_tmap(&maps.q64);
+    ptx::prefetch_tmap(&maps.q16);
+    ptx::prefetch_tmap(&maps.kv64);
+    ptx::prefetch_tmap(&maps.kv16);
+    ptx::mbar_init(q_full, 1);
+    ptx::mbar_init(&t_full[0], 1);
+    ptx::mbar_init(&t_full[1], 1);
+    ptx::mbar_init(pro_done, 256);
+    for (int i = 0; i < kStagesKV; ++i) {
+      ptx::mbar_init(&k_full[i], 1);
+      ptx::mbar_init(&k_free[i], 2);
+      ptx::mbar_init(&v_full[i], 1);
+      ptx::mbar_init(&v_free[i], 2);
+      ptx::mbar_init(&s_full[i], 1);
+      ptx::mbar_init(&s_free[i], 128);
+      ptx::mbar_init(&p_ready[i], 128);
+      ptx::mbar_init(&pv_done[i], 1);
+    }
+    ptx::fence_mbar_init();
+    // Q tiles: issued right away (their buffers alias nothing)
+    ptx::mbar_expect_tx(q_full, 2 * 128 * HD * 2);
+    ptx::tma_load_2d(smem + OFF_Q64, &maps.q64, q_full, cq, row0);
+    ptx::tma_load_2d(smem + OFF_Q16, &maps.q16, q_full, cq + 64, row0);
+    ptx::tma_load_2d(smem + OFF_Q64 + 16384, &maps.q64, q_full, cq, row0 + 128);
+    ptx::tma_load_2d(smem + OFF_Q16 + 4096, &maps.q16, q_full, cq + 64, row0 + 128);
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  // rel-pos operand tables -> smem (generic proxy)
+  for (int i = tid; i < 128 * 10; i += kThreadsG) {
+    const int r = i / 10, c = i % 10;
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(rw_rev + r * HD) + c);
+    if (c < 8)
+      *reinterpret_cast<uint4*>(smem + OFF_RW64 + row_off64(r, c)) = v;
+    else
+      *reinterpret_cast<uint4*>(smem + OFF_RW16 + row_off16(r, c - 8)) = v;
+  }
+  for (int i = tid; i < 80 * 10; i += kThreadsG) {
+    const int r = i / 10, c = i % 10;  // local row r <-> Rh_rev row th_start + r (rows >= 128 do not exist: zero)
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (th_start + r < 128) v = __ldg(reinterpret_cast<const uint4*>(rh_rev + (th_start + r) * HD) + c);
+    // K-major, no swizzle: per 16-wide K step a block of 80 rows x 32B; 8-row groups of 256B = [k-lo 128B][k-hi 128B]
+    *reinterpret_cast<uint4*>(smem + OFF_RH + (c >> 1) * (80 * 32) + (r >> 3) * 256 + (c & 1) * 128 + (r & 7) * 16) = v;
+  }
+  ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (tmem != 0) {   // a CTA that owns all 512 columns gets base 0; the MMA issuers rely on it (uniform addresses)
+    if (tid == 0) printf("glob_attn3: unexpected TMEM base %u\n", tmem);
+    __trap();
+  }
+
+  if (warp == 0) {
+    // ============================================================ TMA producer
+    if (lane == 0) {
+      ptx::mbar_wait(pro_done, 0);   // staging areas (alias K / V / P) are free again
+      for (int j = 0; j < kNBlk; ++j) {
+        const int s = j & (kStagesKV - 1);
+        const uint32_t ph = (j >> 2) & 1;
+        const int r = b * (G * G) + j * BKV;
+        if (j >= kStagesKV) ptx::mbar_wait(&k_free[s], ph ^ 1);
+        ptx::mbar_expect_tx(&k_full[s], BKV * HD * 2);
+        ptx::tma_load_2d(smem + OFF_K64 + s * 8192, &maps.kv64, &k_full[s], ck, r);
+        ptx::tma_load_2d(smem + OFF_K16 + s * 2048, &maps.kv16, &k_full[s], ck + 64, r);
+        if (j >= kStagesKV) ptx::mbar_wait(&v_free[s], ph ^ 1);
+        ptx::mbar_expect_tx(&v_full[s], BKV * HD * 2);
+        ptx::tma_load_2d(smem + OFF_V64 + s * 8192, &maps.kv64, &v_full[s], cv, r);
+        ptx::tma_load_2d(smem + OFF_V16 + s * 2048, &maps.kv16, &v_full[s], cv + 64, r);
+      }
+    }
+  } else if (warp == 1 || warp == 10) {
+    // ============================================================ MMA issuers: warp 1 -> tile 0, warp 10 -> tile 1
+    // (ncu: with one issuing thread for both tiles that thread was busy ~90 % of the kernel -- ~12 SASS instructions
+    // per UTCHMMA -- and the softmax warps starved; two issuers halve the per-thread MMA count.)
+    if (ptx::elect_one()) {
+      const int g = (warp == 1) ? 0 : 1;
+      const uint32_t slot = g * 256;   // TMEM base is 0: this CTA owns all 512 columns (checked after the allocation)
+      const uint32_t id_T = ptx::make_idesc((uint32_t)fmt, 128, 128, 0, 0);
+      const uint32_t id_S = ptx::make_idesc((uint32_t)fmt, 128, 64, 0, 0);
+      const uint32_t id_TH = ptx::make_idesc((uint32_t)fmt, 128, 80, 0, 0);
+      const uint32_t id_O64 = ptx::make_idesc((uint32_t)fmt, 128, 64, 0, 1);
+      const uint32_t id_O16 = ptx::make_idesc((uint32_t)fmt, 128, 16, 0, 1);
+      const uint64_t dq64 = ptx::make_smem_desc(sbase + OFF_Q64 + g * 16384, 16, 1024, ptx::kSwz128);
+      const uint64_t dq16 = ptx::make_smem_desc(sbase + OFF_Q16 + g * 4096, 16, 256, ptx::kSwz32);
+      const uint64_t drw64 = ptx::make_smem_desc(sbase + OFF_RW64, 16, 1024, ptx::kSwz128);
+      const uint64_t drw16 = ptx::make_smem_desc(sbase + OFF_RW16, 16, 256, ptx::kSwz32);
+      const uint64_t drh = ptx::make_smem_desc(sbase + OFF_RH, 128, 256, ptx::kSwzNone);
+      // stage-0 descriptors; stage s adds a constant to the (16-byte granular) start-address field
+      const uint64_t dk64_0 = ptx::make_smem_desc(sbase + OFF_K64, 16, 1024, ptx::kSwz128);
+      const uint64_t dk16_0 = ptx::make_smem_desc(sbase + OFF_K16, 16, 256, ptx::kSwz32);
+      const uint64_t dv64_0 = ptx::make_smem_desc(sbase + OFF_V64, BKV * 128, 1024, ptx::kSwz128);
+      const uint64_t dv16_0 = ptx::make_smem_desc(sbase + OFF_V16, BKV * 32, 256, ptx::kSwz32);
+      const uint64_t dp_0 = ptx::make_smem_desc(sbase + OFF_P + g * 32768, 16, 1024, ptx::kSwz128);
+      ptx::mbar_wait(q_full, 0);
+      ptx::tc_fence_after();
+      // prologue: T_w = Q . Rw_rev^T -> S columns [0,128) ;  T_h = Q . Rh_rev[th_start..+80)^T -> O columns
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        const uint64_t da = (k < 4) ? dq64 + 2 * k : dq16;
+        const uint64_t dw = (k < 4) ? drw64 + 2 * k : drw16;
+        ptx::mma_f16_ss(slot, da, dw, id_T, k != 0);
+        ptx::mma_f16_ss(slot + TM_O, da, drh + ((k * 80 * 32) >> 4), id_TH, k != 0);
+      }
+      ptx::mma_commit(&t_full[g]);
+      ptx::mbar_wait(pro_done, 0);
+
+      // S_g(j) = Q_g . K(j)^T into buffer j & 1
+      auto issue_s = [&](int j) {
+        const int s = j & (kStagesKV - 1);
+        const uint64_t dk64 = dk64_0 + static_cast<uint64_t>(s * (8192 >> 4));
+        const uint64_t dk16 = dk16_0 + static_cast<uint64_t>(s * (2048 >> 4));
+        const uint32_t d = slot + (j & 1) * 64;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ptx::mma_f16_ss(d, dq64 + 2 * k, dk64 + 2 * k, id_S, k != 0);
+        ptx::mma_f16_ss(d, dq16, dk16, id_S, 1);
+        ptx::mma_commit(&s_full[g * 2 + (j & 1)]);
+        ptx::mma_commit(&k_free[s]);   // K(j) consumed by this tile (count 2: both issuers)
+      };
+      ptx::mbar_wait(&k_full[0], 0);
+      ptx::tc_fence_after();
+      issue_s(0);
+#pragma unroll 1
+      for (int j = 0; j < kNBlk; ++j) {
+        const int s = j & (kStagesKV - 1);
+        const int bf = j & 1;
+        if (j + 1 < kNBlk) {
+          // next S first: it only needs K(j+1) and the S buffer released by the softmax of block j-1
+          const int jn = j + 1;
+          ptx::mbar_wait(&k_full[jn & (kStagesKV - 1)], (jn >> 2) & 1);
+          if (jn >= 2) ptx::mbar_wait(&s_free[g * 2 + (jn & 1)], ((jn >> 1) & 1) ^ 1);
+          ptx::tc_fence_after();
+          issue_s(jn);
+        }
+        const uint64_t dv64 = dv64_0 + static_cast<uint64_t>(s * (8192 >> 4));
+        const uint64_t dv16 = dv16_0 + static_cast<uint64_t>(s * (2048 >> 4));
+        const uint64_t dp = dp_0 + static_cast<uint64_t>(bf * (16384 >> 4));
+        ptx::mbar_wait(&v_full[s], (j >> 2) & 1);
+        ptx::mbar_wait(&p_ready[g * 2 + bf], (j >> 1) & 1);   // P_g(j) in smem
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < BKV / 16; ++ks) {
+          ptx::mma_f16_ss(slot + TM_O, dp + 2 * ks, dv64 + ((ks * 2048) >> 4), id_O64, (j | ks) != 0);
+          ptx::mma_f16_ss(slot + TM_O + 64, dp + 2 * ks, dv16 + ((ks * 512) >> 4), id_O16, (j | ks) != 0);
+        }
+        ptx::mma_commit(&pv_done[g * 2 + bf]);
+        ptx::mma_commit(&v_free[s]);   // V(j) consumed by this tile (count 2)
+      }
+    }
+  } else {
+    // ============================================================ softmax warpgroups (g = query tile)
+    const int g = (warp - 2) >> 2;
+    const int row = ((warp & 3) << 5) + lane;            // TMEM lane == query row inside the tile
+    const uint32_t slot = tmem + g * 256;
+    const uint32_t trow = slot + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    const int sw = row & 7;
+    const uint32_t* relh_s = reinterpret_cast<const uint32_t*>(smem + OFF_RELH) + g * 128 + row;   // [pair * 256]
+    const int qh = qh0 + g * 2 + (row >> 6);
+    const int qw = row & 63;
+    const float kLog2e = 1.4426950408889634f;
+    float relw[64];   // rel_w[kw] * log2e
+    ptx::mbar_wait(&t_full[g], 0);
+    ptx::tc_fence_after();
+    {
+      float* st = reinterpret_cast<float*>(smem + (g ? OFF_STAGE1 : OFF_STAGE0)) + row * kStageStride;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32b_x32(trow + c * 32, v);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c * 32 + i < 127) st[c * 32 + i] = __uint_as_float(v[i]);
+      }
+      const float* src = st + (63 - qw);
+#pragma unroll
+      for (int i = 0; i < 64; ++i) relw[i] = src[i] * kLog2e;
+      // rel_h: 64 consecutive T_h columns starting at a warp-uniform offset
+      const uint32_t th_col = TM_O + static_cast<uint32_t>(63 - qh - th_start);
+      uint32_t* relh_w = reinterpret_cast<uint32_t*>(smem + OFF_RELH) + g * 128 + row;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32b_x32(trow + th_col + c * 32, v);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          __half2 h = __floats2half2_rn(__uint_as_float(v[2 * i]) * kLog2e, __uint_as_float(v[2 * i + 1]) * kLog2e);
+          relh_w[(c * 16 + i) * 256] = *reinterpret_cast<uint32_t*>(&h);
+        }
+      }
+    }
+    ptx::tc_fence_before();
+    ptx::mbar_arrive(pro_done);
+
+    const f32x2 sc2 = pk2(scale_log2e, scale_log2e);
+    float m_ref = 0.f;   // reference maximum (log2 domain) all stored probabilities are relative to
+    float l = 0.f;       // running row sum relative to m_ref
+#pragma unroll 1
+    for (int j = 0; j < kNBlk; ++j) {
+      const int bf = j & 1;
+      const uint32_t ph = (j >> 1) & 1;
+      const uint32_t ts = trow + bf * 64;
+      const uint32_t prow = sbase + OFF_P + (g * 2 + bf) * 16384 + row * 128;
+      const float2 rhp = __half22float2(*reinterpret_cast<const __half2*>(&relh_s[(j >> 1) * 256]));
+      float rh = (bf ? rhp.y : rhp.x);
+      uint32_t va[32], vb[32];
+      ptx::mbar_wait(&s_full[g * 2 + bf], ph);
+      ptx::tc_fence_after();
+      ptx::tmem_ld_32x32b_x32(ts, va);
+      ptx::tmem_ld_32x32b_x32(ts + 32, vb);
+      ptx::tmem_ld_wait();
+      if (j == 0) {
+        float bm = -INFINITY;
+        max_half<0>(va, relw, rh, scale_log2e, bm);
+        max_half<1>(vb, relw, rh, scale_log2e, bm);
+        m_ref = bm;
+      }
+      if (j >= 2) {
+        ptx::mbar_wait(&pv_done[g * 2 + bf], ph ^ 1);   // P.V of block j-2 finished: this P buffer is reusable
+      }
+      rh -= m_ref;
+      f32x2 bsum2 = 0ull;
+      softmax_half<0, FMT>(va, relw, pk2(rh, rh), sc2, prow, sw, bsum2);
+      softmax_half<1, FMT>(vb, relw, pk2(rh, rh), sc2, prow, sw, bsum2);
+      float s0, s1;
+      upk2(bsum2, s0, s1);
+      float bsum = s0 + s1;
+      if (__any_sync(0xffffffffu, !(bsum <= kSumLimit))) {
+        // rare: some row of this warp has logits far above its reference.  Move the reference to the block maximum,
+        // rescale the accumulated O row and row sum, and redo the block.  (j == 0 never gets here: its reference is
+        // its own maximum, so bsum <= 64.)
+        float bm = -INFINITY;
+        max_half<0>(va, relw, rh, scale_log2e, bm);
+        max_half<1>(vb, relw, rh, scale_log2e, bm);
+        const float delta = fmaxf(bm, 0.f);
+        const float alpha = ex2(-delta);
+        m_ref += delta;
+        l *= alpha;
+        rh -= delta;
+        ptx::mbar_wait(&pv_done[g * 2 + (bf ^ 1)], ((j - 1) >> 1) & 1);   // every earlier P.V has landed in O
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+          uint32_t v[16];
+          ptx::tmem_ld_32x32b_x16(trow + TM_O + c * 16, v);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+          tmem_st_32x32b_x16(trow + TM_O + c * 16, v);
+        }
+        tmem_st_wait();
+        bsum2 = 0ull;
+        softmax_half<0, FMT>(va, relw, pk2(rh, rh), sc2, prow, sw, bsum2);
+        softmax_half<1, FMT>(vb, relw, pk2(rh, rh), sc2, prow, sw, bsum2);
+        upk2(bsum2, s0, s1);
+        bsum = s0 + s1;
+      }
+      l += bsum;
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&s_free[g * 2 + bf]);
+      ptx::fence_proxy_async_smem();
+      ptx::mbar_arrive(&p_ready[g * 2 + bf]);
+    }
+    // epilogue: O / l -> out
+    ptx::mbar_wait(&pv_done[g * 2 + ((kNBlk - 1) & 1)], ((kNBlk - 1) >> 1) & 1);
+    ptx::tc_fence_after();
+    const float inv = 1.0f / l;
+    uint16_t* dst = out + static_cast<size_t>(row0 + g * 128 + row) * E + head * HD;
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+      uint32_t v[16];
+      ptx::tmem_ld_32x32b_x16(trow + TM_O + c * 16, v);
+      ptx::tmem_ld_wait();
+      uint4 u0, u1;
+      u0.x = ptx::pack2t<FMT>(__uint_as_float(v[0]) * inv, __uint_as_float(v[1]) * inv);
+      u0.y = ptx::pack2t<FMT>(__uint_as_float(v[2]) * inv, __uint_as_float(v[3]) * inv);
+      u0.z = ptx::pack2t<FMT>(__uint_as_float(v[4]) * inv, __uint_as_float(v[5]) * inv);
+      u0.w = ptx::pack2t<FMT>(__uint_as_float(v[6]) * inv, __uint_as_float(v[7]) * inv);
+      u1.x = ptx::pack2t<FMT>(__uint_as_float(v[8]) * inv, __uint_as_float(v[9]) * inv);
+      u1.y = ptx::pack2t<FMT>(__uint_as_float(v[10]) * inv, __uint_as_float(v[11]) * inv);
+      u1.z = ptx::pack2t<FMT>(__uint_as_float(v[12]) * inv, __uint_as_float(v[13]) * inv);
+      u1.w = ptx::pack2t<FMT>(__uint_as_float(v[14]) * inv, __uint_as_float(v[15]) * inv);
+      reinterpret_cast<uint4*>(dst + c * 16)[0] = u0;
+      reinterpret_cast<uint4*>(dst + c * 16)[1] = u1;
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem, 512);
+  }
+}
+
+}  // namespace
+
+int samk_attn_global3(const void* qkv, const void* rh_rev, const void* rw_rev, void* out, int B, int E, int heads,
+                      int fmt, cudaStream_t stream) {
+  SAM_REQUIRE(fmt == 0 || fmt == 1, "attn_global: fmt must be fp16/bf16");
+  SAM_REQUIRE(E == heads * HD, "attn_global: head_dim must be 80 (E=%d heads=%d)", E, heads);
+  SAM_REQUIRE(B > 0, "attn_global: empty batch");
+  GlobAttnMaps3 maps;
+  const int is_bf16 = (fmt == 1);
+  const uint64_t rows = static_cast<uint64_t>(B) * G * G;
+  int rc = samhost::encode_tmap_2d(&maps.q64, 2, is_bf16, qkv, 3ull * E, rows, 3ull * E * 2, 64, 128, 3);
+  if (rc) return rc;
+  rc = samhost::encode_tmap_2d(&maps.q16, 2, is_bf16, qkv, 3ull * E, rows, 3ull * E * 2, 16, 128, 1);
+  if (rc) return rc;
+  rc = samhost::encode_tmap_2d(&maps.kv64, 2, is_bf16, qkv, 3ull * E, rows, 3ull * E * 2, 64, BKV, 3);
+  if (rc) return rc;
+  rc = samhost::encode_tmap_2d(&maps.kv16, 2, is_bf16, qkv, 3ull * E, rows, 3ull * E * 2, 16, BKV, 1);
+  if (rc) return rc;
+  static bool attr_done = false;
+  if (!attr_done) {
+    SAM_CHECK_CUDA(cudaFuncSetAttribute(glob_attn3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesG));
+    SAM_CHECK_CUDA(cudaFuncSetAttribute(glob_attn3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesG));
+    attr_done = true;
+  }
+  const float scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
+  const int grid = B * heads * (G * G / 256);
+  const double bh = static_cast<double>(B) * heads;
+  samhost::LaunchScope scope(samhost::KC_ATTN_GLOBAL, stream, bh * (4.0 * 4096 * 4096 * 80 + 4.0 * 4096 * 64 * 80),
+                             static_cast<double>(B) * 4096 * E * 2 * 4);
+  if (fmt == 0)
+    glob_attn3_kernel<0><<<grid, kThreadsG, kSmemBytesG, stream>>>(maps, static_cast<const uint16_t*>(rh_rev),
+                                                                    static_cast<const uint16_t*>(rw_rev),
+                                                                    static_cast<uint16_t*>(out), E, heads, scale_log2e);
+  else
+    glob_attn3_kernel<1><<<grid, kThreadsG, kSmemBytesG, stream>>>(maps, static_cast<const uint16_t*>(rh_rev),
+                                                                    static_cast<const uint16_t*>(rw_rev),
+                                                                    static_cast<uint16_t*>(out), E, heads, scale_log2e);
+  SAM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

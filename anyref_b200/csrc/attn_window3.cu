@@ -6,8 +6,8 @@
 //
 //   warp 0 (TMA)   : streams Q0/Q1/K and V of item i+1 while item i is in its softmax; patches the zero-padded window
 //                    tokens with the qkv bias (image_encoder.py:281) off the critical path
-//   warp 1 (MMA)   : one thread issues, per tile g:  S = Q_g.K^T (N=208), Tw = Q_g.Rw^T, Th = Q_g.Rh^T  -> TMEM slot g,
-//                    later O = P_g.V (N = 64 + 16) into the same slot
+//   warps 1, 10    : MMA issuers (one elected thread each) for tile 0 / tile 1:  S = Q_g.K^T (N=208), Tw = Q_g.Rw^T,
+//                    Th = Q_g.Rh^T -> TMEM slot g, later O = P_g.V (N = 64 + 16) into the same slot
 //   warps 2..5     : softmax of tile 0 (one thread per query row / TMEM lane)
 //   warps 6..9     : softmax of tile 1
 //
@@ -23,7 +23,7 @@ constexpr int HD = 80;
 constexpr int WS = 14;
 constexpr int NTOK = WS * WS;  // 196
 constexpr int NKEY = 208;
-constexpr int kThreads3 = 320;
+constexpr int kThreads3 = 352;
 
 // shared-memory map (bytes from the 1024-aligned base)
 constexpr int OFF_Q64 = 0;            // 2 x (128 x 128B) SWIZZLE_128B   (tile g at + g*16384)
@@ -176,10 +176,10 @@ win_attn3_kernel(const __grid_constant__ WinAttnMaps3 maps, const uint16_t* __re
     ptx::prefetch_tmap(&maps.qb64);
     ptx::mbar_init(qk_full, 1);
     ptx::mbar_init(qk_ready, 1);
-    ptx::mbar_init(qk_free, 1);
+    ptx::mbar_init(qk_free, 2);
     ptx::mbar_init(v_full, 1);
     ptx::mbar_init(v_ready, 1);
-    ptx::mbar_init(v_free, 1);
+    ptx::mbar_init(v_free, 2);
     for (int g = 0; g < 2; ++g) {
       ptx::mbar_init(&s_full[g], 1);
       ptx::mbar_init(&p_ready[g], 128);
@@ -206,6 +206,10 @@ win_attn3_kernel(const __grid_constant__ WinAttnMaps3 maps, const uint16_t* __re
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  if (tmem != 0) {   // a CTA that owns all 512 columns gets base 0; the MMA issuers rely on it (uniform addresses)
+    if (tid == 0) printf("win_attn3: unexpected TMEM base %u\n", tmem);
+    __trap();
+  }
 
   if (warp == 0) {
     // ============================================================ TMA + padded-token patch warp
@@ -268,9 +272,13 @@ win_attn3_kernel(const __grid_constant__ WinAttnMaps3 maps, const uint16_t* __re
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(v_ready);
     }
-  } else if (warp == 1) {
-    // ============================================================ MMA issuer
-    if (lane == 0) {
+  } else if (warp == 1 || warp == 10) {
+    // ============================================================ MMA issuers: warp 1 -> tile 0, warp 10 -> tile 1
+    // elect.sync + a constant TMEM base keep descriptors / addresses on the uniform datapath (2 SASS instructions per
+    // UTCHMMA instead of a 12-instruction ELECT / R2UR waterfall); one issuer per tile halves the per-thread MMA count.
+    if (ptx::elect_one()) {
+      const int g = (warp == 1) ? 0 : 1;
+      const uint32_t slot = g * 256;   // TMEM base is 0: this CTA owns all 512 columns (checked after the allocation)
       const uint32_t id_T = ptx::make_idesc((uint32_t)fmt, 128, 32, 0, 0);
       const uint32_t id_S = ptx::make_idesc((uint32_t)fmt, 128, NKEY, 0, 0);
       const uint32_t id_O64 = ptx::make_idesc((uint32_t)fmt, 128, 64, 0, 1);
@@ -281,52 +289,40 @@ win_attn3_kernel(const __grid_constant__ WinAttnMaps3 maps, const uint16_t* __re
       const uint64_t dr16 = ptx::make_smem_desc(sbase + OFF_R16, 16, 256, ptx::kSwz32);
       const uint64_t dv64 = ptx::make_smem_desc(sbase + OFF_V64, NKEY * 128, 1024, ptx::kSwz128);
       const uint64_t dv16 = ptx::make_smem_desc(sbase + OFF_V16, NKEY * 32, 256, ptx::kSwz32);
-      uint64_t dq64[2], dq16[2], dp64[2], dp16[2];
-#pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        dq64[g] = ptx::make_smem_desc(sbase + OFF_Q64 + g * 16384, 16, 1024, ptx::kSwz128);
-        dq16[g] = ptx::make_smem_desc(sbase + OFF_Q16 + g * 4096, 16, 256, ptx::kSwz32);
-        dp64[g] = ptx::make_smem_desc(sbase + OFF_P + g * kPBytes, 16, 1024, ptx::kSwz128);
-        dp16[g] = ptx::make_smem_desc(sbase + OFF_P + g * kPBytes + 49152, 16, 256, ptx::kSwz32);
-      }
+      const uint64_t dq64 = ptx::make_smem_desc(sbase + OFF_Q64 + g * 16384, 16, 1024, ptx::kSwz128);
+      const uint64_t dq16 = ptx::make_smem_desc(sbase + OFF_Q16 + g * 4096, 16, 256, ptx::kSwz32);
+      const uint64_t dp64 = ptx::make_smem_desc(sbase + OFF_P + g * kPBytes, 16, 1024, ptx::kSwz128);
+      const uint64_t dp16 = ptx::make_smem_desc(sbase + OFF_P + g * kPBytes + 49152, 16, 256, ptx::kSwz32);
       int n = 0;
       for (int it = blockIdx.x; it < num_items; it += gridDim.x, ++n) {
         const uint32_t ph = n & 1;
         ptx::mbar_wait(qk_ready, ph);
+        if (n > 0) ptx::mbar_wait(&o_done[g], ph ^ 1);   // slot g drained by the previous item's epilogue
+        ptx::tc_fence_after();
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          if (n > 0) ptx::mbar_wait(&o_done[g], ph ^ 1);   // slot g drained by the previous item's epilogue
-          ptx::tc_fence_after();
-          const uint32_t slot = tmem + g * 256;
+        for (int k = 0; k < 4; ++k) ptx::mma_f16_ss(slot, dq64 + 2 * k, dk64 + 2 * k, id_S, k != 0);
+        ptx::mma_f16_ss(slot, dq16, dk16, id_S, 1);
+        // table rows 32..63 = rel_pos_w (+4096 B / +1024 B), rows 0..31 = rel_pos_h.  Tw is issued after S on
+        // purpose: it overwrites the dead pad-key columns 196..207 of S.
 #pragma unroll
-          for (int k = 0; k < 4; ++k) ptx::mma_f16_ss(slot, dq64[g] + 2 * k, dk64 + 2 * k, id_S, k != 0);
-          ptx::mma_f16_ss(slot, dq16[g], dk16, id_S, 1);
-          // table rows 32..63 = rel_pos_w (+4096 B / +1024 B), rows 0..31 = rel_pos_h.  Tw is issued after S on
-          // purpose: it overwrites the dead pad-key columns 196..207 of S.
+        for (int k = 0; k < 4; ++k) ptx::mma_f16_ss(slot + 196, dq64 + 2 * k, dr64 + (4096 >> 4) + 2 * k, id_T, k != 0);
+        ptx::mma_f16_ss(slot + 196, dq16, dr16 + (1024 >> 4), id_T, 1);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) ptx::mma_f16_ss(slot + 196, dq64[g] + 2 * k, dr64 + (4096 >> 4) + 2 * k, id_T, k != 0);
-          ptx::mma_f16_ss(slot + 196, dq16[g], dr16 + (1024 >> 4), id_T, 1);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) ptx::mma_f16_ss(slot + 224, dq64[g] + 2 * k, dr64 + 2 * k, id_T, k != 0);
-          ptx::mma_f16_ss(slot + 224, dq16[g], dr16, id_T, 1);
-          ptx::mma_commit(&s_full[g]);
-        }
-        ptx::mma_commit(qk_free);
+        for (int k = 0; k < 4; ++k) ptx::mma_f16_ss(slot + 224, dq64 + 2 * k, dr64 + 2 * k, id_T, k != 0);
+        ptx::mma_f16_ss(slot + 224, dq16, dr16, id_T, 1);
+        ptx::mma_commit(&s_full[g]);
+        ptx::mma_commit(qk_free);       // count 2: both issuers
         ptx::mbar_wait(v_ready, ph);
+        ptx::mbar_wait(&p_ready[g], ph);
+        ptx::tc_fence_after();
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          ptx::mbar_wait(&p_ready[g], ph);
-          ptx::tc_fence_after();
-          const uint32_t slot = tmem + g * 256;
-#pragma unroll
-          for (int ks = 0; ks < NKEY / 16; ++ks) {
-            const uint64_t da = (ks < 12) ? dp64[g] + (((ks >> 2) * 16384 + (ks & 3) * 32) >> 4) : dp16[g];
-            ptx::mma_f16_ss(slot, da, dv64 + ((ks * 2048) >> 4), id_O64, ks != 0);
-            ptx::mma_f16_ss(slot + 64, da, dv16 + ((ks * 512) >> 4), id_O16, ks != 0);
-          }
-          ptx::mma_commit(&o_full[g]);
+        for (int ks = 0; ks < NKEY / 16; ++ks) {
+          const uint64_t da = (ks < 12) ? dp64 + (((ks >> 2) * 16384 + (ks & 3) * 32) >> 4) : dp16;
+          ptx::mma_f16_ss(slot, da, dv64 + ((ks * 2048) >> 4), id_O64, ks != 0);
+          ptx::mma_f16_ss(slot + 64, da, dv16 + ((ks * 512) >> 4), id_O16, ks != 0);
         }
-        ptx::mma_commit(v_free);
+        ptx::mma_commit(&o_full[g]);
+        ptx::mma_commit(v_free);        // count 2
       }
     }
   } else {

@@ -55,6 +55,8 @@ int samk_attn_global(const void* qkv, const void* rh_rev, const void* rw_rev, vo
 
 int samk_attn_global2(const void* qkv, const void* rh_rev, const void* rw_rev, void* out, int B, int E, int heads,
                       int fmt, cudaStream_t stream);
+int samk_attn_global3(const void* qkv, const void* rh_rev, const void* rw_rev, void* out, int B, int E, int heads,
+                      int fmt, cudaStream_t stream);
 
 // Memory-bound glue (glue.cu).  All fp32 activations are token-major rows.
 //   layernorm_rows : out[row] = LN(x[row] (+ res[row])) * gamma + beta  (normalize == 0: plain dtype cast)

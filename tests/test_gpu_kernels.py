@@ -189,6 +189,24 @@ def test_global_attention(ops, dt, tol):
     assert rel_fro(got, want) < tol
 
 
+@pytest.mark.parametrize("dt,tol", [(torch.float16, 2e-3), (torch.bfloat16, 8e-3)])
+def test_global_attention_peaked_logits(ops, dt, tol):
+    """Logits with a std of ~13 log2 units: later key rows exceed the reference maximum taken from the first key row by
+    far more than the 2^10 headroom, so the lazy-reference path (rescale O in TMEM, redo the block) must run -- the
+    result is still the exact softmax of image_encoder.py:250-256."""
+    torch.manual_seed(5)
+    heads, E, B = 2, 160, 1
+    qkv = torch.randn(B * 4096, 3 * E, device=DEV)
+    qkv[:, :2 * E] *= 3.0
+    qkv = qkv.to(dt)
+    gh = (torch.randn(127, 80, device=DEV) * 0.2).to(dt)
+    gw = (torch.randn(127, 80, device=DEV) * 0.2).to(dt)
+    got = ops.attn_global(qkv, ops.global_rel_table(gh, dt), ops.global_rel_table(gw, dt), B, heads)
+    want = _global_reference(qkv, gh, gw, heads)
+    assert bool(torch.isfinite(got.float()).all())
+    assert rel_fro(got, want) < tol
+
+
 def test_rel_pos_index_tables_match_get_rel_pos(ops):
     """INT-exact: row j of the reversed table is rel_pos[126 - j]; get_rel_pos index (image_encoder.py:345-351)."""
     t = torch.arange(127 * 80, device=DEV, dtype=torch.float32).view(127, 80)
