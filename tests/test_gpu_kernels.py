@@ -161,6 +161,24 @@ def test_windowed_attention(ops, dt, tol, B, heads):
     assert rel_fro(got, _window_reference(qkv, bias, rel_h, rel_w, B, heads)) < tol
 
 
+@pytest.mark.parametrize("dt,tol", [(torch.float16, 2e-3), (torch.bfloat16, 8e-3)])
+def test_windowed_attention_peaked_logits(ops, dt, tol):
+    """Logits with a std of ~13 log2 units: keys beyond the first 32 beat the single-pass reference maximum by more than
+    the 2^10 headroom for many rows, so the two-pass redo must run; the result is still the exact softmax."""
+    torch.manual_seed(6)
+    B, heads = 1, 2
+    E = heads * 80
+    qkv = torch.randn(B * 4096, 3 * E, device=DEV)
+    qkv[:, :2 * E] *= 3.0
+    qkv = qkv.to(dt)
+    bias = (torch.randn(3 * E, device=DEV) * 0.5).to(dt)
+    rel_h = (torch.randn(27, 80, device=DEV) * 0.2).to(dt)
+    rel_w = (torch.randn(27, 80, device=DEV) * 0.2).to(dt)
+    got = ops.attn_window(qkv, bias, ops.window_rel_table(rel_h, rel_w, dt), B, heads)
+    assert bool(torch.isfinite(got.float()).all())
+    assert rel_fro(got, _window_reference(qkv, bias, rel_h, rel_w, B, heads)) < tol
+
+
 def test_windowed_attention_token_map_is_exact(ops):
     """q = k = 0 and zero rel-pos make the softmax uniform, so every output is the mean of v over its window:
     checks the partition / padding / un-partition index maps (image_encoder.py:263-318) independently of the maths."""
