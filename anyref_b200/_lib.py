@@ -66,10 +66,16 @@ _PROTOS = {
     "sam_profile_get": [c_int, C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.POINTER(C.c_double),
                         C.POINTER(C.c_double)],
     "sam_dense_pe": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
+    "sam_prompt_sparse": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                          c_int, c_int, c_void_p],
+    "sam_prompt_mask_blob_elems": [c_int, c_int],
+    "sam_prompt_mask_embed": [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "sam_preprocess": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, C.POINTER(C.c_float),
+                       C.POINTER(C.c_float), c_void_p],
 }
 _RESTYPES = {"sam_last_error": c_char_p, "sam_encoder_w16_elems": c_size_t, "sam_encoder_w32_elems": c_size_t,
              "sam_encoder_workspace_bytes": c_size_t, "sam_decoder_weight_elems": c_size_t,
-             "sam_decoder_workspace_bytes": c_size_t, "sam_decoder_derived_bytes": c_size_t, "sam_launch_count": C.c_longlong, "sam_profile_enable": None,
+             "sam_decoder_workspace_bytes": c_size_t, "sam_decoder_derived_bytes": c_size_t, "sam_prompt_mask_blob_elems": c_size_t, "sam_launch_count": C.c_longlong, "sam_profile_enable": None,
              "sam_profile_reset": None, "sam_profile_get": None}
 
 

@@ -99,6 +99,25 @@ int sam_dense_pe(const float* gauss, void* out, int out_fmt, int C, int g, void*
   return samk_dense_pe(gauss, out, out_fmt, C, g, S(stream));
 }
 
+int sam_prompt_sparse(const float* coords, const float* labels, const float* gauss, const float* table, float* out, int n,
+                      int n_in, int pad, int mode, int C, int img_h, int img_w, int ld_tokens, int tok0, void* stream) {
+  if (!gauss || !table || !out || (n_in > 0 && !coords))
+    return samhost::set_error(1, "sam_prompt_sparse: NULL argument");
+  return samk_prompt_sparse(coords, labels, gauss, table, out, n, n_in, pad, mode, C, img_h, img_w, ld_tokens, tok0,
+                            S(stream));
+}
+size_t sam_prompt_mask_blob_elems(int mask_in_chans, int C) { return samk_prompt_mask_blob_elems(mask_in_chans, C); }
+int sam_prompt_mask_embed(const void* masks, int in_fmt, const float* blob, int mask_in_chans, void* out, int out_fmt,
+                          int n, int g, int C, void* stream) {
+  if (!masks || !blob || !out) return samhost::set_error(1, "sam_prompt_mask_embed: NULL argument");
+  return samk_prompt_mask_embed(masks, in_fmt, blob, mask_in_chans, out, out_fmt, n, g, C, S(stream));
+}
+int sam_preprocess(const void* img, int in_fmt, void* out, int out_fmt, int B, int h, int w, int Sz, const float* mean,
+                   const float* std, void* stream) {
+  if (!img || !out || !mean || !std) return samhost::set_error(1, "sam_preprocess: NULL argument");
+  return samk_preprocess(img, in_fmt, out, out_fmt, B, h, w, Sz, mean, std, S(stream));
+}
+
 long long sam_launch_count(void) { return samhost::launch_count(); }
 void sam_profile_enable(int on) { samhost::profile_enable(on); }
 void sam_profile_reset(void) { samhost::profile_reset(); }

@@ -84,3 +84,13 @@ int samk_decoder_forward(const SamDecoderShape& s, const float* blob, const void
 int samk_postprocess(const void* low, int low_fmt, int num_masks, int L, int S, int h_in, int w_in, int H, int W,
                      float* logits, uint8_t* binary, float threshold, cudaStream_t stream);
 int samk_dense_pe(const float* gauss, void* out, int out_fmt, int C, int g, cudaStream_t stream);
+
+// PromptEncoder point / box / mask prompts and Sam.preprocess (prompt.cu).
+int samk_prompt_sparse(const float* coords, const float* labels, const float* gauss, const float* table, float* out,
+                       int n, int n_in, int pad, int mode, int C, int img_h, int img_w, int ld_tokens, int tok0,
+                       cudaStream_t stream);
+size_t samk_prompt_mask_blob_elems(int mask_in_chans, int C);
+int samk_prompt_mask_embed(const void* masks, int in_fmt, const float* blob, int mask_in_chans, void* out, int out_fmt,
+                           int n, int g, int C, cudaStream_t stream);
+int samk_preprocess(const void* img, int in_fmt, void* out, int out_fmt, int B, int h, int w, int S, const float* mean,
+                    const float* std, cudaStream_t stream);

@@ -1,0 +1,252 @@
+// PromptEncoder's non-text prompt types (prompt_encoder.py:78-114) and Sam.preprocess (sam.py:174-184) as fused,
+// memory-bound kernels.  They sit either side of the hot path: SamPredictor.predict_torch and
+// convert_avs_masks.py (box prompt, multimask_output=True) run on them.
+#include <math.h>
+
+#include "host_common.h"
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------------------
+// sparse prompts.  mode 0: points with labels (prompt_encoder.py:78-98), n_out = n_in + pad;  mode 1: box corners
+// (:100-109), coords = [n, 2, 2], corner j gets point_embeddings[2 + j].
+//   pe(c) = sin | cos( 2 pi * ( (2 (c.x + 0.5) / W - 1) G[0, :] + (2 (c.y + 0.5) / H - 1) G[1, :] ) )   (:203-214, :231-238)
+//   label -1 -> not_a_point_embed alone (the encoding is zeroed, :93-94); 0 / 1 -> + point_embeddings[0 / 1];
+//   any other label -> the bare encoding.  The pad point (pad = 1, index n_in) is (0, 0) with label -1.
+// table: [5, C] = point_embeddings[0..3].weight, not_a_point_embed.weight.   out: [n, ld_tokens, C], written at token
+// offset tok0.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void prompt_sparse_kernel(const float* __restrict__ coords, const float* __restrict__ labels,
+                                     const float* __restrict__ gauss, const float* __restrict__ table,
+                                     float* __restrict__ out, int n, int n_in, int n_out, int mode, int C, float img_h,
+                                     float img_w, int ld_tokens, int tok0) {
+  const int half = C / 2;
+  const int total = n * n_out * C;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = i % C;
+    const int j = (i / C) % n_out;
+    const int b = i / (C * n_out);
+    float* dst = out + (static_cast<size_t>(b) * ld_tokens + tok0 + j) * C + c;
+    int code;   // -1 not-a-point, 0..3 embedding index, 9 none
+    if (mode == 1) {
+      code = 2 + j;
+    } else if (j >= n_in) {
+      code = -1;
+    } else {
+      const float l = labels[b * n_in + j];
+      code = (l == -1.0f) ? -1 : (l == 0.0f) ? 0 : (l == 1.0f) ? 1 : 9;
+    }
+    if (code == -1) {
+      *dst = table[4 * C + c];
+      continue;
+    }
+    const float* p = coords + (static_cast<size_t>(b) * n_in + j) * 2;
+    const float px = __fadd_rn(p[0], 0.5f) / img_w;
+    const float py = __fadd_rn(p[1], 0.5f) / img_h;
+    const float cx = __fsub_rn(__fmul_rn(2.0f, px), 1.0f);
+    const float cy = __fsub_rn(__fmul_rn(2.0f, py), 1.0f);
+    const int cc = c % half;
+    const float d = __fadd_rn(__fmul_rn(cx, gauss[cc]), __fmul_rn(cy, gauss[half + cc]));
+    const float a = __fmul_rn(6.283185307179586f, d);
+    float v = (c < half) ? sinf(a) : cosf(a);
+    if (code >= 0 && code < 4) v = __fadd_rn(v, table[code * C + c]);
+    *dst = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// mask prompts: mask_downscaling (prompt_encoder.py:56-64, :111-114), one thread per output pixel of the g x g grid:
+//   Conv2d(1, c1, k2, s2) -> LayerNorm2d(c1) -> GELU -> Conv2d(c1, c2, k2, s2) -> LayerNorm2d(c2) -> GELU -> Conv2d(c2, C, 1)
+// with c1 = 4, c2 = 16 (mask_in_chans = 16, build_sam.py:85).  blob (fp32, state_dict order):
+//   w0 [c1,1,2,2] b0 [c1] | ln1 w,b [c1] | w3 [c2,c1,2,2] b3 [c2] | ln4 w,b [c2] | w6 [C,c2] b6 [C]
+// masks [n, 1, 4g, 4g] (in_fmt) -> out [n, C, g, g] (out_fmt).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int MC1 = 4, MC2 = 16;
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+__device__ __forceinline__ float load_any(const void* p, size_t i, int fmt) {
+  if (fmt == 2) return static_cast<const float*>(p)[i];
+  return ptx::unpack1(static_cast<const uint16_t*>(p)[i], fmt);
+}
+
+__global__ void prompt_mask_kernel(const void* __restrict__ masks, int in_fmt, const float* __restrict__ blob,
+                                   void* __restrict__ out, int out_fmt, int n, int g, int C) {
+  const float* w0 = blob;
+  const float* b0 = w0 + MC1 * 4;
+  const float* l1w = b0 + MC1;
+  const float* l1b = l1w + MC1;
+  const float* w3 = l1b + MC1;
+  const float* b3 = w3 + MC2 * MC1 * 4;
+  const float* l4w = b3 + MC2;
+  const float* l4b = l4w + MC2;
+  const float* w6 = l4b + MC2;
+  const float* b6 = w6 + C * MC2;
+  const int S = 4 * g;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * g * g) return;
+  const int x = idx % g, y = (idx / g) % g, b = idx / (g * g);
+  float acc2[MC2];
+#pragma unroll
+  for (int o = 0; o < MC2; ++o) acc2[o] = b3[o];
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy) {
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      // stage-1 pixel (2y + dy, 2x + dx): conv over the 2x2 input patch, LN over c1 channels, GELU
+      const int iy = (2 * y + dy) * 2, ix = (2 * x + dx) * 2;
+      float m[4];
+#pragma unroll
+      for (int ky = 0; ky < 2; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 2; ++kx)
+          m[ky * 2 + kx] = load_any(masks, (static_cast<size_t>(b) * S + iy + ky) * S + ix + kx, in_fmt);
+      float h[MC1];
+      float mean = 0.f;
+#pragma unroll
+      for (int o = 0; o < MC1; ++o) {
+        float a = b0[o];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) a = fmaf(m[t], w0[o * 4 + t], a);
+        h[o] = a;
+        mean += a;
+      }
+      mean *= (1.0f / MC1);
+      float var = 0.f;
+#pragma unroll
+      for (int o = 0; o < MC1; ++o) var += (h[o] - mean) * (h[o] - mean);
+      const float rstd = 1.0f / sqrtf(var * (1.0f / MC1) + 1e-6f);
+#pragma unroll
+      for (int o = 0; o < MC1; ++o) h[o] = gelu_erf((h[o] - mean) * rstd * l1w[o] + l1b[o]);
+      // stage-2 accumulation: w3[o, i, dy, dx]
+#pragma unroll
+      for (int o = 0; o < MC2; ++o)
+#pragma unroll
+        for (int i = 0; i < MC1; ++i) acc2[o] = fmaf(h[i], w3[(o * MC1 + i) * 4 + dy * 2 + dx], acc2[o]);
+    }
+  }
+  float mean = 0.f;
+#pragma unroll
+  for (int o = 0; o < MC2; ++o) mean += acc2[o];
+  mean *= (1.0f / MC2);
+  float var = 0.f;
+#pragma unroll
+  for (int o = 0; o < MC2; ++o) var += (acc2[o] - mean) * (acc2[o] - mean);
+  const float rstd = 1.0f / sqrtf(var * (1.0f / MC2) + 1e-6f);
+#pragma unroll
+  for (int o = 0; o < MC2; ++o) acc2[o] = gelu_erf((acc2[o] - mean) * rstd * l4w[o] + l4b[o]);
+  const size_t plane = static_cast<size_t>(g) * g;
+  const size_t o0 = static_cast<size_t>(b) * C * plane + static_cast<size_t>(y) * g + x;
+  for (int c = 0; c < C; ++c) {
+    float a = b6[c];
+#pragma unroll
+    for (int i = 0; i < MC2; ++i) a = fmaf(acc2[i], __ldg(w6 + c * MC2 + i), a);
+    if (out_fmt == 2)
+      static_cast<float*>(out)[o0 + c * plane] = a;
+    else
+      static_cast<uint16_t*>(out)[o0 + c * plane] = ptx::pack1(a, out_fmt);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Sam.preprocess (sam.py:174-184) fused with the dtype cast:  out[b, c, y, x] = (img[b, c, y, x] - mean[c]) / std[c] for
+// y < h, x < w, else 0 (F.pad after the normalisation).  img: [B, 3, h, w] uint8 (in_fmt 3) or fp32 / 16-bit, values in
+// 0..255; out: [B, 3, S, S] in out_fmt.  One thread per 8 output pixels of a row (16-byte stores for 16-bit outputs).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void preprocess_kernel(const void* __restrict__ img, int in_fmt, void* __restrict__ out, int out_fmt, int B,
+                                  int h, int w, int S, float m0, float m1, float m2, float s0, float s1, float s2) {
+  const int per_row = S / 8;
+  const size_t total = static_cast<size_t>(B) * 3 * S * per_row;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int xg = static_cast<int>(i % per_row);
+    const int y = static_cast<int>((i / per_row) % S);
+    const int c = static_cast<int>((i / (static_cast<size_t>(per_row) * S)) % 3);
+    const int b = static_cast<int>(i / (static_cast<size_t>(per_row) * S * 3));
+    const float mean = c == 0 ? m0 : (c == 1 ? m1 : m2);
+    const float sd = c == 0 ? s0 : (c == 1 ? s1 : s2);
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int x = xg * 8 + k;
+      float t = 0.f;
+      if (y < h && x < w) {
+        const size_t src = ((static_cast<size_t>(b) * 3 + c) * h + y) * w + x;
+        const float p = (in_fmt == 3) ? static_cast<float>(static_cast<const uint8_t*>(img)[src]) : load_any(img, src, in_fmt);
+        t = __fsub_rn(p, mean) / sd;
+      }
+      v[k] = t;
+    }
+    const size_t dst = ((static_cast<size_t>(b) * 3 + c) * S + y) * S + static_cast<size_t>(xg) * 8;
+    if (out_fmt == 2) {
+      float4* o = reinterpret_cast<float4*>(static_cast<float*>(out) + dst);
+      o[0] = make_float4(v[0], v[1], v[2], v[3]);
+      o[1] = make_float4(v[4], v[5], v[6], v[7]);
+    } else {
+      uint4 u;
+      u.x = ptx::pack2(v[0], v[1], out_fmt);
+      u.y = ptx::pack2(v[2], v[3], out_fmt);
+      u.z = ptx::pack2(v[4], v[5], out_fmt);
+      u.w = ptx::pack2(v[6], v[7], out_fmt);
+      *reinterpret_cast<uint4*>(static_cast<uint16_t*>(out) + dst) = u;
+    }
+  }
+}
+
+}  // namespace
+
+int samk_prompt_sparse(const float* coords, const float* labels, const float* gauss, const float* table, float* out,
+                       int n, int n_in, int pad, int mode, int C, int img_h, int img_w, int ld_tokens, int tok0,
+                       cudaStream_t stream) {
+  SAM_REQUIRE(n > 0 && n_in >= 0 && C % 2 == 0, "prompt_sparse: bad shape (n=%d n_in=%d C=%d)", n, n_in, C);
+  SAM_REQUIRE(mode == 0 || (mode == 1 && n_in == 2 && pad == 0), "prompt_sparse: box mode takes [n, 2, 2] corners");
+  SAM_REQUIRE(mode == 1 || labels != nullptr || n_in == 0, "prompt_sparse: point mode needs labels");
+  const int n_out = n_in + (pad ? 1 : 0);
+  SAM_REQUIRE(tok0 >= 0 && tok0 + n_out <= ld_tokens, "prompt_sparse: token window [%d, %d) outside %d", tok0,
+              tok0 + n_out, ld_tokens);
+  if (n_out == 0) return 0;
+  samhost::LaunchScope scope(samhost::KC_LAYOUT, stream);
+  const int total = n * n_out * C;
+  prompt_sparse_kernel<<<(total + 255) / 256, 256, 0, stream>>>(coords, labels, gauss, table, out, n, n_in, n_out, mode,
+                                                                C, static_cast<float>(img_h), static_cast<float>(img_w),
+                                                                ld_tokens, tok0);
+  SAM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+size_t samk_prompt_mask_blob_elems(int mask_in_chans, int C) {
+  const size_t c1 = mask_in_chans / 4, c2 = mask_in_chans;
+  return c1 * 4 + c1 + 2 * c1 + c2 * c1 * 4 + c2 + 2 * c2 + static_cast<size_t>(C) * c2 + C;
+}
+
+int samk_prompt_mask_embed(const void* masks, int in_fmt, const float* blob, int mask_in_chans, void* out, int out_fmt,
+                           int n, int g, int C, cudaStream_t stream) {
+  SAM_REQUIRE(mask_in_chans == MC2, "prompt_mask_embed: mask_in_chans must be %d (build_sam.py:85), got %d", MC2,
+              mask_in_chans);
+  SAM_REQUIRE(n > 0 && g > 0 && C > 0, "prompt_mask_embed: bad shape");
+  SAM_REQUIRE(in_fmt >= 0 && in_fmt <= 2 && out_fmt >= 0 && out_fmt <= 2, "prompt_mask_embed: bad format");
+  samhost::LaunchScope scope(samhost::KC_LAYOUT, stream);
+  const int total = n * g * g;
+  prompt_mask_kernel<<<(total + 127) / 128, 128, 0, stream>>>(masks, in_fmt, blob, out, out_fmt, n, g, C);
+  SAM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int samk_preprocess(const void* img, int in_fmt, void* out, int out_fmt, int B, int h, int w, int S, const float* mean,
+                    const float* std, cudaStream_t stream) {
+  SAM_REQUIRE(B > 0 && h > 0 && w > 0 && h <= S && w <= S && S % 8 == 0, "preprocess: bad shape (%d x %d -> %d)", h, w, S);
+  SAM_REQUIRE(in_fmt >= 0 && in_fmt <= 3 && out_fmt >= 0 && out_fmt <= 2, "preprocess: bad format");
+  samhost::LaunchScope scope(samhost::KC_LAYOUT, stream, 0.0,
+                             static_cast<double>(B) * 3 * (static_cast<double>(h) * w * (in_fmt == 3 ? 1 : in_fmt == 2 ? 4 : 2) +
+                                                           static_cast<double>(S) * S * (out_fmt == 2 ? 4 : 2)));
+  const size_t total = static_cast<size_t>(B) * 3 * S * (S / 8);
+  int blocks = static_cast<int>((total + 255) / 256);
+  const int cap = samhost::sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  preprocess_kernel<<<blocks, 256, 0, stream>>>(img, in_fmt, out, out_fmt, B, h, w, S, mean[0], mean[1], mean[2], std[0],
+                                                std[1], std[2]);
+  SAM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

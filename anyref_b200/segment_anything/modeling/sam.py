@@ -63,10 +63,31 @@ class Sam(nn.Module):
             _lib.check(rc, "sam_postprocess_masks")
         return (out, binary) if return_binary else out
 
-    def preprocess(self, x: torch.Tensor) -> torch.Tensor:
-        """Normalise pixel values and pad to a square (sam.py:174-184) -- CPU-side data preparation in AnyRef
-        (utils/refer_seg.py:560-570); kept as plain tensor ops, outside the measured path."""
-        x = (x - self.pixel_mean) / self.pixel_std
-        h, w = x.shape[-2:]
+    @torch.no_grad()
+    def preprocess(self, x: torch.Tensor, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+        """Normalise pixel values and pad to a square (sam.py:174-184; AnyRef's sam_preprocess,
+        utils/refer_seg.py:560-593) as ONE kernel that also does the cast to the encoder's input dtype:
+        [3,h,w] or [B,3,h,w], uint8 / fp16 / bf16 / fp32 in 0..255 -> [..., 3, S, S] in `out_dtype` (default: fp32 for
+        float inputs as in the reference, which keeps the input dtype)."""
+        _runtime.require_cuda(x, "Sam.preprocess")
+        squeeze = x.dim() == 3
+        xb = (x.unsqueeze(0) if squeeze else x).contiguous()
+        if xb.dim() != 4 or xb.shape[1] != 3:
+            raise ValueError(f"expected [3,h,w] or [B,3,h,w], got {tuple(x.shape)}")
+        B, _, h, w = xb.shape
         S = self.image_encoder.img_size
-        return torch.nn.functional.pad(x, (0, S - w, 0, S - h))
+        if xb.dtype == torch.uint8:
+            in_fmt = 3
+        else:
+            in_fmt = _lib.fmt_of(xb.dtype)
+        if out_dtype is None:
+            out_dtype = torch.float32 if xb.dtype == torch.uint8 else xb.dtype
+        out = torch.empty((B, 3, S, S), device=xb.device, dtype=out_dtype)
+        import ctypes
+
+        mean = (ctypes.c_float * 3)(*[float(v) for v in self.pixel_mean.flatten().tolist()])
+        std = (ctypes.c_float * 3)(*[float(v) for v in self.pixel_std.flatten().tolist()])
+        rc = _lib.load().sam_preprocess(xb.data_ptr(), in_fmt, out.data_ptr(), _lib.fmt_of(out_dtype), B, h, w, S, mean,
+                                        std, _lib.stream_ptr(xb.device))
+        _lib.check(rc, "sam_preprocess")
+        return out[0] if squeeze else out

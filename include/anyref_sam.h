@@ -181,6 +181,35 @@ int sam_postprocess_masks(const void* low, int low_fmt, int num_masks, int L, in
 int sam_dense_pe(const float* gauss, void* out, int out_fmt, int C, int g, void* stream);
 
 /*
+ * PromptEncoder point / box prompts (prompt_encoder.py:78-109; PositionEmbeddingRandom.forward_with_coords :231-238).
+ *   mode 0: coords fp32 [n, n_in, 2] (x, y in input-image pixels), labels fp32 [n, n_in] (-1 not-a-point, 0 negative,
+ *           1 positive, anything else: bare encoding); pad = 1 appends the (0, 0) / -1 padding point (:86-90).
+ *   mode 1: coords fp32 [n, 2, 2] = box corners (x1, y1), (x2, y2); corner j gets point_embeddings[2 + j].
+ * gauss fp32 [2, C/2]; table fp32 [5, C] = point_embeddings[0..3].weight, not_a_point_embed.weight.
+ * Writes n_in + pad tokens per prompt into out fp32 [n, ld_tokens, C] starting at token tok0 (so points, boxes and
+ * text embeddings can be laid side by side as the reference's torch.cat does, :165-177).
+ */
+int sam_prompt_sparse(const float* coords, const float* labels, const float* gauss, const float* table, float* out, int n,
+                      int n_in, int pad, int mode, int C, int img_h, int img_w, int ld_tokens, int tok0, void* stream);
+
+/*
+ * PromptEncoder mask prompts: mask_downscaling (prompt_encoder.py:56-64, :111-114) fused per output pixel.
+ * blob fp32 in state_dict order: mask_downscaling.0.{weight,bias}, .1.{weight,bias}, .3.{weight,bias}, .4.{weight,bias},
+ * .6.{weight,bias} (sam_prompt_mask_blob_elems floats).  masks [n, 1, 4g, 4g] (in_fmt) -> out [n, C, g, g] (out_fmt).
+ */
+size_t sam_prompt_mask_blob_elems(int mask_in_chans, int C);
+int sam_prompt_mask_embed(const void* masks, int in_fmt, const float* blob, int mask_in_chans, void* out, int out_fmt,
+                          int n, int g, int C, void* stream);
+
+/*
+ * Sam.preprocess (sam.py:174-184; AnyRef's sam_preprocess, utils/refer_seg.py:560-593): (img - mean) / std, zero-pad
+ * to S x S, cast.  img [B, 3, h, w]: in_fmt 0 fp16, 1 bf16, 2 fp32, 3 uint8;  out [B, 3, S, S] in out_fmt (0 / 1 / 2).
+ * mean / std: HOST pointers to 3 floats (Sam.pixel_mean / pixel_std, sam.py:46-49).
+ */
+int sam_preprocess(const void* img, int in_fmt, void* out, int out_fmt, int B, int h, int w, int S, const float* mean,
+                   const float* std, void* stream);
+
+/*
  * Launch accounting and per-kernel-class timing (used by bench.py for `gpu_launches` and the roofline leg).
  * sam_launch_count: kernels launched by this library since load.  With profiling enabled every launch is bracketed by
  * a CUDA event pair on its stream; sam_profile_collect synchronises those events and adds them to per-class totals.

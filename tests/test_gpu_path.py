@@ -214,3 +214,149 @@ def test_vit_h_against_reference_goldens(dt, emb_tol, low_tol, iou_min):
                 assert iou_i >= iou_min, (key, i, iou_i)
     del sam
     torch.cuda.empty_cache()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# point / box / mask prompts and Sam.preprocess (the callers either side of the path)
+# ---------------------------------------------------------------------------------------------------------------------
+def _prompt_inputs():
+    g = torch.Generator().manual_seed(11)
+    coords = torch.rand(3, 5, 2, generator=g) * 1024
+    labels = torch.tensor([[1, 0, -1, 1, 0], [0, 0, 1, 1, -1], [1, 1, 1, 0, 2]], dtype=torch.float32)
+    boxes = torch.rand(3, 4, generator=g) * 1024
+    masks = torch.randn(3, 1, 256, 256, generator=g)
+    text = torch.randn(3, 2, 256, generator=g)
+    return coords, labels, boxes, masks, text
+
+
+@pytest.mark.parametrize("case", ["points", "boxes", "points+boxes", "points+boxes+text", "masks", "points+masks"])
+def test_prompt_types_vs_oracle(tiny, case):
+    """PromptEncoder.forward for every prompt combination (prompt_encoder.py:140-186) against the oracle restatement
+    (itself bit-identical to the imported reference, tests/test_oracle_vs_reference.py)."""
+    sam, cfg, sd = tiny["sam"], tiny["cfg"], tiny["sd"]
+    coords, labels, boxes, masks, text = _prompt_inputs()
+    kw = dict(points=None, boxes=None, masks=None, text_embeds=None)
+    if "points" in case:
+        kw["points"] = (coords, labels)
+    if "boxes" in case:
+        kw["boxes"] = boxes
+    if "text" in case:
+        kw["text_embeds"] = text
+    if "masks" in case:
+        kw["masks"] = masks
+    with torch.no_grad():
+        sparse_o, dense_o = O.prompt_encoder(sd, cfg, **kw)
+    cuda_kw = {k: (tuple(t.cuda() for t in v) if isinstance(v, tuple) else (v.cuda() if v is not None else None))
+               for k, v in kw.items()}
+    sparse, dense = sam.prompt_encoder(**cuda_kw)
+    assert sparse.shape == sparse_o.shape and sparse.dtype == torch.float32
+    assert dense.shape == dense_o.shape
+    if sparse.numel():
+        # sin / cos of arguments up to ~2 pi * 4 sigma: a few fp32 ulps of the argument
+        assert (sparse.cpu() - sparse_o).abs().max().item() < 5e-5
+    assert (dense.cpu().float() - dense_o).abs().max().item() < 2e-5
+
+
+def test_not_a_point_and_padding_are_exact(tiny):
+    """label -1 (and the padding point appended when no box is given, prompt_encoder.py:86-94) must be EXACTLY
+    not_a_point_embed: the positional encoding is zeroed, not added."""
+    sam = tiny["sam"]
+    coords = torch.rand(2, 2, 2, device="cuda") * 1024
+    labels = torch.tensor([[-1.0, 1.0], [0.0, -1.0]], device="cuda")
+    sparse, _ = sam.prompt_encoder(points=(coords, labels), boxes=None, masks=None, text_embeds=None)
+    nap = sam.prompt_encoder.not_a_point_embed.weight[0]
+    assert sparse.shape == (2, 3, 256)
+    assert torch.equal(sparse[0, 0], nap) and torch.equal(sparse[1, 1], nap)
+    assert torch.equal(sparse[0, 2], nap) and torch.equal(sparse[1, 2], nap)   # padding point
+
+
+def test_box_prompt_through_decoder_vs_oracle(tiny):
+    """convert_avs_masks.py:53-58: box prompt, multimask_output=True, best mask by predicted IoU."""
+    sam, cfg, sd = tiny["sam"], tiny["cfg"], tiny["sd"]
+    boxes = torch.tensor([[100.0, 200.0, 700.0, 900.0]])
+    with torch.no_grad():
+        so, do = O.prompt_encoder(sd, cfg, boxes=boxes)
+        mo, io = O.mask_decoder(sd, cfg, tiny["emb"][:1], tiny["pe"], so, do, True)
+    emb = tiny["emb"][:1].cuda()
+    sp, de = sam.prompt_encoder(points=None, boxes=boxes.cuda(), masks=None, text_embeds=None)
+    m, iou = sam.mask_decoder(image_embeddings=emb, image_pe=sam.prompt_encoder.get_dense_pe(),
+                              sparse_prompt_embeddings=sp, dense_prompt_embeddings=de, multimask_output=True)
+    assert m.shape == (1, 3, 256, 256) and iou.shape == (1, 3)
+    assert (m.cpu() - mo).abs().max().item() < 1e-4
+    assert (iou.cpu() - io).abs().max().item() < 1e-4
+    assert int(iou.argmax()) == int(io.argmax())
+
+
+def test_mask_prompt_through_decoder_vs_oracle(tiny):
+    """SamPredictor.predict_torch with mask_input (predictor.py:233-252): the dense embedding is a full tensor."""
+    sam, cfg, sd = tiny["sam"], tiny["cfg"], tiny["sd"]
+    g = torch.Generator().manual_seed(3)
+    masks = torch.randn(2, 1, 256, 256, generator=g) * 4
+    coords = torch.rand(2, 1, 2, generator=g) * 1024
+    labels = torch.ones(2, 1)
+    with torch.no_grad():
+        so, do = O.prompt_encoder(sd, cfg, points=(coords, labels), masks=masks)
+        mo, io = O.mask_decoder(sd, cfg, tiny["emb"][:1], tiny["pe"], so, do, False)
+    sp, de = sam.prompt_encoder(points=(coords.cuda(), labels.cuda()), boxes=None, masks=masks.cuda(), text_embeds=None)
+    m, iou = sam.mask_decoder(image_embeddings=tiny["emb"][:1].cuda(), image_pe=sam.prompt_encoder.get_dense_pe(),
+                              sparse_prompt_embeddings=sp, dense_prompt_embeddings=de, multimask_output=False)
+    assert (m.cpu() - mo).abs().max().item() < 2e-4
+    assert (iou.cpu() - io).abs().max().item() < 1e-4
+
+
+@pytest.mark.parametrize("dtype", [torch.uint8, torch.float32])
+@pytest.mark.parametrize("hw", [(1024, 683), (768, 1024), (1024, 1024), (5, 9)])
+def test_preprocess_is_bit_exact(tiny, dtype, hw):
+    """Sam.preprocess (sam.py:174-184): fp32 normalise + zero pad must be BIT-identical to (x - mean) / std + F.pad."""
+    sam = tiny["sam"]
+    h, w = hw
+    g = torch.Generator().manual_seed(h * 7 + w)
+    img = torch.randint(0, 256, (2, 3, h, w), generator=g, dtype=torch.uint8)
+    x = img if dtype == torch.uint8 else img.float() + 0.25
+    mean = torch.tensor([123.675, 116.28, 103.53]).view(-1, 1, 1)
+    std = torch.tensor([58.395, 57.12, 57.375]).view(-1, 1, 1)
+    ref = torch.nn.functional.pad((x.float() - mean) / std, (0, 1024 - w, 0, 1024 - h))
+    got = sam.preprocess(x.cuda(), out_dtype=torch.float32)
+    assert got.shape == (2, 3, 1024, 1024)
+    assert torch.equal(got.cpu(), ref)
+    got16 = sam.preprocess(x.cuda(), out_dtype=torch.bfloat16)
+    assert torch.equal(got16.cpu(), ref.to(torch.bfloat16))
+    assert torch.equal(sam.preprocess(x[0].cuda(), out_dtype=torch.float32).cpu(), ref[0])
+
+
+def test_sam_predictor_box_prompt_vs_oracle(tiny):
+    """SamPredictor.set_torch_image + predict (predictor.py:64-176) as convert_avs_masks.py:29-58 drives it: uint8
+    image in the resized frame, box in ORIGINAL pixels, multimask_output=True, best mask by predicted IoU."""
+    from anyref_b200.segment_anything import SamPredictor
+
+    sam, cfg, sd = tiny["sam"], tiny["cfg"], tiny["sd"]
+    sam.image_encoder.set_operand_dtype(torch.float16)
+    g = torch.Generator().manual_seed(21)
+    orig = (480, 640)
+    img = torch.randint(0, 256, (1, 3, 768, 1024), generator=g, dtype=torch.uint8)   # already ResizeLongestSide'd
+    box = np.array([50.0, 60.0, 400.0, 300.0])
+    # oracle: the same steps with the CPU restatement
+    mean = torch.tensor([123.675, 116.28, 103.53]).view(-1, 1, 1)
+    std = torch.tensor([58.395, 57.12, 57.375]).view(-1, 1, 1)
+    x = torch.nn.functional.pad((img.float() - mean) / std, (0, 0, 0, 256))
+    with torch.no_grad():
+        emb = O.image_encoder(sd, x, cfg)
+        b = torch.tensor(box).reshape(1, 2, 2).float()
+        b[..., 0] *= 1024 / 640
+        b[..., 1] *= 768 / 480
+        so, do = O.prompt_encoder(sd, cfg, boxes=b.reshape(1, 4))
+        mo, io = O.mask_decoder(sd, cfg, emb, O.dense_pe(sd, cfg), so, do, True)
+        full = O.postprocess_masks(mo, (768, 1024), orig)
+    pred = SamPredictor(sam)
+    pred.set_torch_image(img.cuda(), orig)
+    assert pred.input_size == (768, 1024) and pred.original_size == orig
+    masks, scores, low = pred.predict(box=box, multimask_output=True)
+    assert masks.shape == (3, 480, 640) and masks.dtype == np.bool_ and scores.shape == (3,) and low.shape == (3, 256, 256)
+    assert np.abs(scores - io[0].numpy()).max() < 5e-3
+    best = int(scores.argmax())
+    assert best == int(io[0].argmax())
+    assert mask_iou(torch.from_numpy(masks[best]).float() - 0.5, full[0, best]) > 0.99
+    logits, _, _ = pred.predict(box=box, multimask_output=True, return_logits=True)
+    assert rel_fro(torch.from_numpy(logits), full[0]) < 5e-3
+    with pytest.raises(RuntimeError):
+        SamPredictor(sam).predict(box=box)

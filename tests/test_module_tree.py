@@ -54,8 +54,13 @@ def test_prompt_encoder_text_embeds_plumbing():
     assert torch.equal(sparse, text.float())
     assert dense.shape == (3, 256, 64, 64) and dense.stride() == (0, 1, 0, 0)
     assert torch.equal(dense[1, :, 5, 7], sam.prompt_encoder.no_mask_embed.weight[0])
-    with pytest.raises(NotImplementedError):
+    # point / box / mask prompts are CUDA kernels: on CPU tensors they fail loudly instead of falling back
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
         sam.prompt_encoder(points=(torch.zeros(1, 1, 2), torch.zeros(1, 1)), boxes=None, masks=None, text_embeds=None)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        sam.prompt_encoder(points=None, boxes=None, masks=torch.zeros(1, 1, 256, 256), text_embeds=None)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        sam.preprocess(torch.zeros(3, 8, 8))
 
 
 @pytest.mark.parametrize("name", ["vit_tiny80", "vit_h"])

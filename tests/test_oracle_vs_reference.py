@@ -103,3 +103,25 @@ def test_rel_pos_matches_reference(ref_sa):
     for s in (14, 64):
         t = torch.randn(2 * s - 1, 8)
         assert torch.equal(get_rel_pos(s, s, t), t[O.rel_pos_index(s)])
+
+
+def test_resize_longest_side_matches_reference(ref_sa):
+    """The predictor's host-side geometry (utils/transforms.py:17-113): shapes, coordinate and box maps, and the PIL
+    bilinear image resize are identical to the reference's ResizeLongestSide."""
+    import numpy as np
+    from segment_anything.utils.transforms import ResizeLongestSide as RefResize
+
+    from anyref_b200.segment_anything.utils import ResizeLongestSide
+
+    ref, mine = RefResize(1024), ResizeLongestSide(1024)
+    rng = np.random.default_rng(0)
+    for (h, w) in ((480, 640), (683, 1024), (1333, 800), (1024, 1024), (37, 1999)):
+        assert mine.get_preprocess_shape(h, w, 1024) == ref.get_preprocess_shape(h, w, 1024)
+        pts = rng.uniform(0, max(h, w), size=(7, 2))
+        assert np.array_equal(mine.apply_coords(pts, (h, w)), ref.apply_coords(pts, (h, w)))
+        box = rng.uniform(0, max(h, w), size=(3, 4))
+        assert np.array_equal(mine.apply_boxes(box, (h, w)), ref.apply_boxes(box, (h, w)))
+        assert torch.equal(mine.apply_boxes_torch(torch.from_numpy(box), (h, w)),
+                           ref.apply_boxes_torch(torch.from_numpy(box), (h, w)))
+    img = rng.integers(0, 256, size=(120, 200, 3), dtype=np.uint8)
+    assert np.array_equal(mine.apply_image(img), ref.apply_image(img))
