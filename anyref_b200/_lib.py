@@ -66,6 +66,9 @@ _PROTOS = {
     "sam_profile_get": [c_int, C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.POINTER(C.c_double),
                         C.POINTER(C.c_double)],
     "sam_dense_pe": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
+    "sam_postprocess_masks_iou": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                  c_float, c_void_p, c_void_p, c_void_p],
+    "sam_iou_finalize": [c_void_p, c_int, c_void_p, c_void_p],
     "sam_prompt_sparse": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                           c_int, c_int, c_void_p],
     "sam_prompt_mask_blob_elems": [c_int, c_int],

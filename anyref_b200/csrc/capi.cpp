@@ -95,6 +95,16 @@ int sam_postprocess_masks(const void* low, int low_fmt, int num_masks, int L, in
   return samk_postprocess(low, low_fmt, num_masks, L, Sz, h_in, w_in, H, W, logits, binary, threshold, S(stream));
 }
 
+int sam_postprocess_masks_iou(const void* low, int low_fmt, int num_masks, int L, int Sz, int h_in, int w_in, int H, int W,
+                              float* logits, unsigned char* binary, float threshold, const unsigned char* target,
+                              int* counts, void* stream) {
+  return samk_postprocess_iou(low, low_fmt, num_masks, L, Sz, h_in, w_in, H, W, logits, binary, threshold, target, counts,
+                              S(stream));
+}
+int sam_iou_finalize(const int* counts, int n, double* stats, void* stream) {
+  return samk_iou_finalize(counts, n, stats, S(stream));
+}
+
 int sam_dense_pe(const float* gauss, void* out, int out_fmt, int C, int g, void* stream) {
   return samk_dense_pe(gauss, out, out_fmt, C, g, S(stream));
 }

@@ -52,13 +52,21 @@ __device__ __forceinline__ float stage1(const void* low, int fmt, size_t base, i
 
 // grid (ceil(W/128), ceil(H/8), n*C), block (128, 1): each thread produces 8 rows? -> keep it simple: 1 pixel/thread
 // with 4-wide vector stores when W % 4 == 0.
+// With `target` / `counts` the intersectionAndUnionGPU statistics of the thresholded mask (utils/utils.py:79-91, K = 2,
+// ignore_index = 255) are accumulated in the same pass: counts[m] = {inter_0, inter_1, pred_0, pred_1, target_0,
+// target_1} (int32, atomically added), so the evaluation loop (eval_referseg.py:186-211) needs neither the full
+// resolution logits nor the mask in HBM.
 __global__ void __launch_bounds__(256)
 postprocess_kernel(const void* __restrict__ low, int low_fmt, int L, int S, int h_in, int w_in, int H, int W,
-                   float* __restrict__ logits, uint8_t* __restrict__ binary, float threshold) {
+                   float* __restrict__ logits, uint8_t* __restrict__ binary, float threshold,
+                   const uint8_t* __restrict__ target, int* __restrict__ counts) {
   const int m = blockIdx.z;
   const int Y = blockIdx.y * blockDim.y + threadIdx.y;
   const int X4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  if (Y >= H || X4 >= W) return;
+  const bool active = (Y < H && X4 < W);
+  if (!active && counts == nullptr) return;
+  int cnt[6] = {0, 0, 0, 0, 0, 0};
+  if (active) {
   const float scale1 = static_cast<float>(L) / static_cast<float>(S);
   const float sy = static_cast<float>(h_in) / static_cast<float>(H);
   const float sx = static_cast<float>(w_in) / static_cast<float>(W);
@@ -99,16 +107,84 @@ postprocess_kernel(const void* __restrict__ low, int low_fmt, int L, int S, int 
         if (X4 + i < W) binary[o + i] = v[i] > threshold;
     }
   }
+  if (counts) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (X4 + i < W) {
+        const int t = target[o + i];
+        if (t != 255) {
+          const int p = v[i] > threshold ? 1 : 0;
+          cnt[2 + p] += 1;
+          if (t < 2) {
+            cnt[4 + t] += 1;
+            if (t == p) cnt[p] += 1;
+          }
+        }
+      }
+    }
+  }
+  }  // active
+  if (counts) {
+    __shared__ int s_cnt[6];
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    if (tid < 6) s_cnt[tid] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const int w = __reduce_add_sync(0xffffffffu, cnt[k]);
+      if ((tid & 31) == 0 && w) atomicAdd(&s_cnt[k], w);
+    }
+    __syncthreads();
+    if (tid < 6 && s_cnt[tid]) atomicAdd(&counts[m * 6 + tid], s_cnt[tid]);
+  }
+}
+
+// Folds per-mask counts into the running evaluation statistics (eval_referseg.py:197-211):
+//   stats[0:2] += intersection, stats[2:4] += union, stats[4:6] += intersection / (union + 1e-5) (+1 where union == 0:
+//   "no-object target"), stats[6] += 1 per mask.  fp64 accumulation in mask order: deterministic.
+__global__ void iou_finalize_kernel(const int* __restrict__ counts, int n, double* __restrict__ stats) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+  for (int m = 0; m < n; ++m) {
+    for (int k = 0; k < 2; ++k) {
+      const float inter = static_cast<float>(counts[m * 6 + k]);
+      const float uni = static_cast<float>(counts[m * 6 + 2 + k] + counts[m * 6 + 4 + k] - counts[m * 6 + k]);
+      float a = inter / (uni + 1e-5f);   // fp32 like the torch tensors of the reference
+      if (uni == 0.0f) a += 1.0f;
+      acc[k] += inter;
+      acc[2 + k] += uni;
+      acc[4 + k] += a;
+    }
+    acc[6] += 1.0;
+  }
+  for (int k = 0; k < 7; ++k) stats[k] += acc[k];
 }
 
 }  // namespace
 
 int samk_postprocess(const void* low, int low_fmt, int num_masks, int L, int S, int h_in, int w_in, int H, int W,
                      float* logits, uint8_t* binary, float threshold, cudaStream_t stream) {
+  return samk_postprocess_iou(low, low_fmt, num_masks, L, S, h_in, w_in, H, W, logits, binary, threshold, nullptr, nullptr,
+                              stream);
+}
+
+int samk_iou_finalize(const int* counts, int n, double* stats, cudaStream_t stream) {
+  SAM_REQUIRE(counts && stats && n >= 0, "iou_finalize: bad arguments");
+  if (n == 0) return 0;
+  samhost::LaunchScope scope(samhost::KC_POSTPROCESS, stream);
+  iou_finalize_kernel<<<1, 32, 0, stream>>>(counts, n, stats);
+  SAM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int samk_postprocess_iou(const void* low, int low_fmt, int num_masks, int L, int S, int h_in, int w_in, int H, int W,
+                         float* logits, uint8_t* binary, float threshold, const uint8_t* target, int* counts,
+                         cudaStream_t stream) {
   SAM_REQUIRE(num_masks > 0 && L > 0 && S > 0 && H > 0 && W > 0, "postprocess: empty problem");
   SAM_REQUIRE(h_in > 0 && w_in > 0 && h_in <= S && w_in <= S, "postprocess: input_size (%d,%d) outside the %d canvas",
               h_in, w_in, S);
-  SAM_REQUIRE(logits || binary, "postprocess: no output requested");
+  SAM_REQUIRE(logits || binary || counts, "postprocess: no output requested");
+  SAM_REQUIRE((target == nullptr) == (counts == nullptr), "postprocess: target and counts go together");
   SAM_REQUIRE(low_fmt >= 0 && low_fmt <= 2, "postprocess: bad input format");
   SAM_REQUIRE(num_masks <= 65535, "postprocess: at most 65535 masks per call");
   dim3 blk(64, 4);
@@ -116,8 +192,9 @@ int samk_postprocess(const void* low, int low_fmt, int num_masks, int L, int S, 
   samhost::LaunchScope scope(samhost::KC_POSTPROCESS, stream, 0.0,
                              static_cast<double>(num_masks) *
                                  (static_cast<double>(L) * L * (low_fmt == 2 ? 4.0 : 2.0) +
-                                  static_cast<double>(H) * W * ((logits ? 4.0 : 0.0) + (binary ? 1.0 : 0.0))));
-  postprocess_kernel<<<grid, blk, 0, stream>>>(low, low_fmt, L, S, h_in, w_in, H, W, logits, binary, threshold);
+                                  static_cast<double>(H) * W * ((logits ? 4.0 : 0.0) + (binary ? 1.0 : 0.0) + (target ? 1.0 : 0.0))));
+  postprocess_kernel<<<grid, blk, 0, stream>>>(low, low_fmt, L, S, h_in, w_in, H, W, logits, binary, threshold, target,
+                                               counts);
   SAM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

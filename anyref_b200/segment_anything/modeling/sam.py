@@ -64,6 +64,38 @@ class Sam(nn.Module):
         return (out, binary) if return_binary else out
 
     @torch.no_grad()
+    def postprocess_and_score(self, masks: torch.Tensor, input_size: Tuple[int, ...], original_size: Tuple[int, ...],
+                              gt_masks: torch.Tensor, stats: Optional[torch.Tensor] = None,
+                              return_binary: bool = False):
+        """postprocess_masks + thresholding + the evaluation statistics of eval_referseg.py:186-211 in ONE pass:
+        `gt_masks` uint8 [n,C,H,W] (0 / 1, 255 = ignore).  Adds this call's masks to `stats` (fp64 [7] =
+        intersection bg/fg, union bg/fg, accumulated IoU bg/fg, count; created when None) and returns it -- that
+        vector is what `anyref_b200.dp.all_reduce_stats` sums across ranks.  Nothing of full resolution is written
+        unless return_binary=True (then the uint8 masks are returned as well)."""
+        _runtime.require_cuda(masks, "Sam.postprocess_and_score")
+        m = masks.contiguous()
+        n, ch, L, _ = m.shape
+        H, W = int(original_size[0]), int(original_size[1])
+        if tuple(gt_masks.shape) != (n, ch, H, W) or gt_masks.dtype != torch.uint8:
+            raise ValueError(f"gt_masks must be uint8 [{n},{ch},{H},{W}], got {gt_masks.dtype} {tuple(gt_masks.shape)}")
+        gt = gt_masks.to(m.device).contiguous()
+        if stats is None:
+            stats = torch.zeros(7, dtype=torch.float64, device=m.device)
+        binary = torch.empty((n, ch, H, W), device=m.device, dtype=torch.uint8) if return_binary else None
+        if n * ch > 0:
+            counts = torch.zeros((n * ch, 6), dtype=torch.int32, device=m.device)
+            L_ = _lib.load()
+            st = _lib.stream_ptr(m.device)
+            rc = L_.sam_postprocess_masks_iou(m.data_ptr(), _lib.fmt_of(m.dtype), n * ch, L, self.image_encoder.img_size,
+                                              int(input_size[0]), int(input_size[1]), H, W, None,
+                                              binary.data_ptr() if return_binary else None, float(self.mask_threshold),
+                                              gt.data_ptr(), counts.data_ptr(), st)
+            _lib.check(rc, "sam_postprocess_masks_iou")
+            rc = L_.sam_iou_finalize(counts.data_ptr(), n * ch, stats.data_ptr(), st)
+            _lib.check(rc, "sam_iou_finalize")
+        return (stats, binary) if return_binary else stats
+
+    @torch.no_grad()
     def preprocess(self, x: torch.Tensor, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
         """Normalise pixel values and pad to a square (sam.py:174-184; AnyRef's sam_preprocess,
         utils/refer_seg.py:560-593) as ONE kernel that also does the cast to the encoder's input dtype:

@@ -175,6 +175,19 @@ int sam_postprocess_masks(const void* low, int low_fmt, int num_masks, int L, in
                           float* logits, unsigned char* binary, float threshold, void* stream);
 
 /*
+ * postprocess_masks fused with the evaluation statistics (eval_referseg.py:186-211 over intersectionAndUnionGPU,
+ * utils/utils.py:79-91, K = 2, ignore_index = 255): target uint8 [num_masks, H, W] (0 / 1 / 255); counts int32
+ * [num_masks, 6] = {inter_0, inter_1, pred_0, pred_1, target_0, target_1} is ADDED to (zero it first).  logits and
+ * binary may both be NULL: then nothing of full resolution is written at all.
+ * sam_iou_finalize folds counts into stats fp64 [7] = {inter_bg, inter_fg, union_bg, union_fg, acc_iou_bg, acc_iou_fg,
+ * count} (+=), the per-rank vector that one ncclAllReduce(SUM) combines.
+ */
+int sam_postprocess_masks_iou(const void* low, int low_fmt, int num_masks, int L, int S, int h_in, int w_in, int H, int W,
+                              float* logits, unsigned char* binary, float threshold, const unsigned char* target,
+                              int* counts, void* stream);
+int sam_iou_finalize(const int* counts, int n, double* stats, void* stream);
+
+/*
  * PromptEncoder.get_dense_pe (prompt_encoder.py:67-76; PositionEmbeddingRandom :203-219): gauss fp32 [2, C/2]
  * (positional_encoding_gaussian_matrix) -> out [1, C, g, g] in out_fmt.
  */

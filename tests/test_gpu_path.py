@@ -360,3 +360,47 @@ def test_sam_predictor_box_prompt_vs_oracle(tiny):
     assert rel_fro(torch.from_numpy(logits), full[0]) < 5e-3
     with pytest.raises(RuntimeError):
         SamPredictor(sam).predict(box=box)
+
+
+@pytest.mark.parametrize("inp,orig", [((1024, 1024), (1024, 1024)), ((1024, 683), (640, 427)), ((768, 1024), (481, 643))])
+def test_fused_iou_statistics_are_exact(tiny, inp, orig):
+    """postprocess + threshold + intersectionAndUnionGPU (utils/utils.py:79-91, eval_referseg.py:197-211) in one pass:
+    integer counts must equal the reference formula applied to the separately produced binary mask, ignore pixels
+    (255) and an all-background ("no-object", union == 0 -> acc_iou += 1) target included."""
+    from anyref_b200 import dp
+
+    sam = tiny["sam"]
+    g = torch.Generator().manual_seed(orig[0])
+    low = (torch.randn(5, 1, 256, 256, generator=g) * 0.3).cuda()
+    low[4] = -1.0                                                     # predicts nothing
+    gt = (torch.rand(5, 1, *orig, generator=g) > 0.5).to(torch.uint8)
+    gt[1, :, :7, :] = 255                                             # ignore band
+    gt[4] = 0                                                         # no-object target
+    _, binary = sam.postprocess_masks(low, inp, orig, return_binary=True)
+    stats, binary2 = sam.postprocess_and_score(low, inp, orig, gt.cuda(), return_binary=True)
+    assert torch.equal(binary, binary2)
+    want = torch.zeros(7, dtype=torch.float64)
+    for i in range(5):
+        p = binary[i, 0].cpu().long().clone()
+        t = gt[i, 0].long()
+        p[t == 255] = 255
+        inter = p[p == t]
+        ai = torch.histc(inter.float(), bins=2, min=0, max=1)
+        ap = torch.histc(p.float(), bins=2, min=0, max=1)
+        at = torch.histc(t.float(), bins=2, min=0, max=1)
+        au = ap + at - ai
+        acc = ai / (au + 1e-5)
+        acc[au == 0] += 1.0
+        want[0:2] += ai.double()
+        want[2:4] += au.double()
+        want[4:6] += acc.double()
+        want[6] += 1
+    assert torch.equal(stats.cpu()[:4], want[:4]) and stats.cpu()[6] == 5
+    assert (stats.cpu()[4:6] - want[4:6]).abs().max().item() < 1e-6
+    # accumulates across calls, and matches the host-side helper used by the gloo tests
+    stats = sam.postprocess_and_score(low, inp, orig, gt.cuda(), stats=stats)
+    assert torch.equal(stats.cpu()[:4], 2 * want[:4]) and stats.cpu()[6] == 10
+    clean = [0, 2, 3, 4]   # dp.iou_stats has no ignore handling
+    ref = dp.iou_stats([binary[i, 0].cpu() for i in clean], [gt[i, 0] for i in clean])
+    s2 = sam.postprocess_and_score(low[clean], inp, orig, gt[clean].cuda())
+    assert torch.allclose(s2.cpu().float(), ref, rtol=1e-6, atol=1e-6)
