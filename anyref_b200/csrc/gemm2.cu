@@ -118,6 +118,34 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return fmaf(-0.70710678118654752f * z, erfc_z, fmaxf(x, 0.0f));
 }
 
+// Two elements at a time on the packed fp32 pipe (FFMA2 / FMUL2): 10 issue slots per element instead of 16 -- the
+// epilogue's ALU energy is what separates the GELU GEMM from the plain one under the power cap.
+__device__ __forceinline__ void gelu_fast2(float& x0, float& x1) {
+  using ptx::f32x2;
+  const float a0 = fabsf(x0), a1 = fabsf(x1);
+  const f32x2 ax = ptx::pk2(a0, a1);
+  const f32x2 d = ptx::fma2(ax, ptx::pk2(0.3275911f * 0.70710678118654752f, 0.3275911f * 0.70710678118654752f),
+                            ptx::pk2(1.0f, 1.0f));
+  float d0, d1, t0, t1;
+  ptx::upk2(d, d0, d1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
+  const f32x2 t = ptx::pk2(t0, t1);
+  f32x2 p = ptx::fma2(ptx::pk2(1.061405429f, 1.061405429f), t, ptx::pk2(-1.453152027f, -1.453152027f));
+  p = ptx::fma2(p, t, ptx::pk2(1.421413741f, 1.421413741f));
+  p = ptx::fma2(p, t, ptx::pk2(-0.284496736f, -0.284496736f));
+  p = ptx::fma2(p, t, ptx::pk2(0.254829592f, 0.254829592f));
+  // exp(-z^2) with z = |x| / sqrt2:  ex2(x^2 * (-0.5 * log2 e))
+  const f32x2 w = ptx::mul2(ptx::mul2(ax, ax), ptx::pk2(-0.72134752044448170f, -0.72134752044448170f));
+  float w0, w1, e0, e1;
+  ptx::upk2(w, w0, w1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(w0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(w1));
+  const f32x2 erfc_z = ptx::mul2(ptx::mul2(p, t), ptx::pk2(e0, e1));
+  const f32x2 r = ptx::fma2(ptx::mul2(ax, ptx::pk2(-0.5f, -0.5f)), erfc_z, ptx::pk2(fmaxf(x0, 0.0f), fmaxf(x1, 0.0f)));
+  ptx::upk2(r, x0, x1);
+}
+
 struct Gemm2Params {
   const float* bias;
   int act;         // 0 none, 1 GELU
@@ -263,13 +291,14 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           for (int i = 0; i < 8; ++i) {
             if (col0 + 4 * i < p.N) {
               const float4 b = __ldg(b4 + i);
-              f[4 * i + 0] += b.x; f[4 * i + 1] += b.y; f[4 * i + 2] += b.z; f[4 * i + 3] += b.w;
+              ptx::upk2(ptx::add2(ptx::pk2(f[4 * i + 0], f[4 * i + 1]), ptx::pk2(b.x, b.y)), f[4 * i + 0], f[4 * i + 1]);
+              ptx::upk2(ptx::add2(ptx::pk2(f[4 * i + 2], f[4 * i + 3]), ptx::pk2(b.z, b.w)), f[4 * i + 2], f[4 * i + 3]);
             }
           }
         }
         if (ACT == 1) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = gelu_fast(f[i]);
+          for (int i = 0; i < 32; i += 2) gelu_fast2(f[i], f[i + 1]);
         }
         if (OUT_FMT != 2) {
           // 16-bit output: two 32-column chunks share one 32 x 64 (128 B rows) staging box

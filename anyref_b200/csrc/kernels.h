@@ -48,6 +48,8 @@ int samk_attn_window(const void* qkv, const void* bias_op, const void* rel_tab, 
                      int fmt, cudaStream_t stream);
 int samk_attn_window3(const void* qkv, const void* bias_op, const void* rel_tab, void* out, int B, int E, int heads,
                       int fmt, cudaStream_t stream);
+int samk_attn_window4(const void* qkv, const void* bias_op, const void* rel_tab, void* out, int B, int E, int heads,
+                      int fmt, cudaStream_t stream);
 // Global 64x64 attention with fused rel-pos bias (attn_global.cu).
 //   rh_rev / rw_rev [128, 80] op-format: row j = rel_pos_{h,w}[126 - j] for j < 127, row 127 zero.
 int samk_attn_global(const void* qkv, const void* rh_rev, const void* rw_rev, void* out, int B, int E, int heads,

@@ -73,9 +73,11 @@ umma_probe_kernel(const uint16_t* __restrict__ A, const uint16_t* __restrict__ B
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int N = p.N, K = p.K;
 
-  for (int i = tid; i < 128 * K; i += 128) {
-    const int r = i / K, k = i % K;
-    *reinterpret_cast<uint16_t*>(sA + off_kmajor(p.a_mode, 128, r, k)) = A[i];
+  if (p.a_mode != 7) {
+    for (int i = tid; i < 128 * K; i += 128) {
+      const int r = i / K, k = i % K;
+      *reinterpret_cast<uint16_t*>(sA + off_kmajor(p.a_mode, 128, r, k)) = A[i];
+    }
   }
   if (p.b_mode <= 2) {
     for (int i = tid; i < N * K; i += 128) {
@@ -93,8 +95,29 @@ umma_probe_kernel(const uint16_t* __restrict__ A, const uint16_t* __restrict__ B
     ptx::fence_mbar_init();
   }
   if (warp == 0) {
-    ptx::tmem_alloc(&tmem_slot, 256);
+    ptx::tmem_alloc(&tmem_slot, 512);
     ptx::tmem_relinquish();
+  }
+  if (p.a_mode == 7) {
+    // a_mode 7: A lives in TENSOR MEMORY (tcgen05.mma "ts" form): lane = row, 32-bit column j = elements (2j, 2j+1)
+    // of the row, element 2j in the low half.  Written with tcgen05.st by the thread that owns the lane, as a softmax
+    // warp would write its probabilities.  A sits at columns [256, 256 + K/2).
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tm = tmem_slot;
+    const int row = warp * 32 + lane;
+    for (int c = 0; c < K / 16; ++c) {
+      uint32_t v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        v[j] = static_cast<uint32_t>(A[row * K + c * 16 + 2 * j]) | (static_cast<uint32_t>(A[row * K + c * 16 + 2 * j + 1]) << 16);
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(
+                       tm + (static_cast<uint32_t>(warp * 32) << 16) + 256 + c * 8),
+                   "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                   : "memory");
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
   }
   ptx::fence_proxy_async_smem();
   ptx::tc_fence_before();
@@ -110,7 +133,11 @@ umma_probe_kernel(const uint16_t* __restrict__ A, const uint16_t* __restrict__ B
     if (p.b_sbo >= 0) mb.sbo = p.b_sbo;
     const uint32_t idesc = ptx::make_idesc((uint32_t)p.fmt, 128, (uint32_t)N, 0, p.b_mode >= 3 ? 1u : 0u);
     const uint32_t a0 = ptx::smem_u32(sA), b0 = ptx::smem_u32(sB);
-    for (int ks = 0; ks < K / 16; ++ks) {
+    for (int ks = 0; ks < K / 16 && p.a_mode == 7; ++ks) {
+      const uint32_t bb = b0 + (ks / mb.ksteps_per_chunk) * mb.chunk_stride + (ks % mb.ksteps_per_chunk) * mb.kstep_small;
+      ptx::mma_f16_ts(tmem, tmem + 256 + ks * 8, ptx::make_smem_desc(bb, mb.lbo, mb.sbo, mb.swz), idesc, ks != 0);
+    }
+    for (int ks = 0; ks < K / 16 && p.a_mode != 7; ++ks) {
       const uint32_t aa = a0 + (ks / ma.ksteps_per_chunk) * ma.chunk_stride + (ks % ma.ksteps_per_chunk) * ma.kstep_small;
       const uint32_t bb = b0 + (ks / mb.ksteps_per_chunk) * mb.chunk_stride + (ks % mb.ksteps_per_chunk) * mb.kstep_small;
       ptx::mma_f16_ss(tmem, ptx::make_smem_desc(aa, ma.lbo, ma.sbo, ma.swz),
@@ -132,7 +159,7 @@ umma_probe_kernel(const uint16_t* __restrict__ A, const uint16_t* __restrict__ B
   __syncthreads();
   if (warp == 0) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem, 256);
+    ptx::tmem_dealloc(tmem, 512);
   }
 }
 
@@ -141,7 +168,7 @@ umma_probe_kernel(const uint16_t* __restrict__ A, const uint16_t* __restrict__ B
 int samk_umma_probe(const void* A, const void* B, float* D, const UmmaProbe& p, cudaStream_t stream) {
   SAM_REQUIRE(p.N % 16 == 0 && p.N >= 16 && p.N <= 256, "probe: bad N %d", p.N);
   SAM_REQUIRE(p.K % 16 == 0 && p.K >= 16 && p.K <= 256, "probe: bad K %d", p.K);
-  SAM_REQUIRE(p.a_mode >= 0 && p.a_mode <= 2 && p.b_mode >= 0 && p.b_mode <= 6, "probe: bad mode");
+  SAM_REQUIRE(((p.a_mode >= 0 && p.a_mode <= 2) || p.a_mode == 7) && p.b_mode >= 0 && p.b_mode <= 6, "probe: bad mode");
   const int smem = 65536 + 131072 + 1024;
   static bool attr_done = false;
   if (!attr_done) {
