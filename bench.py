@@ -166,6 +166,17 @@ def workload_name(args):
             f"{args.batch} images x {args.n_seg} [SEG] per GPU, 1024x1024 synthetic -> 1024x1024 masks")
 
 
+def gemm_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per GEMM launch (mean over the qkv / proj / lin1 / lin2 launches of an
+    encoder block) from the committed ncu capture profiles/r01_kernel_traffic.json; None if the file is absent."""
+    p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_kernel_traffic.json")
+    try:
+        with open(p) as f:
+            return json.load(f)["gemm_block_mean"]["traffic_bytes_per_launch"]
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -305,10 +316,10 @@ def main():
                     "d2h_bytes_per_step": host_out.numel() * 4},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "gemm_tn_kernel (tcgen05 GEMM, all encoder linears)",
+            "roofline": {"bound": "tensor", "kernel": "gemm2_kernel (2-CTA tcgen05 GEMM, all encoder linears)",
                          "achieved": gemm_tflops, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                          "frac": gemm_tflops / peaks["bf16_sustained"], "peak_source": peaks["source"] + " sustained",
-                         "traffic": None,
+                         "traffic": gemm_traffic(),
                          "launches_per_step": classes["gemm"]["launches_per_step"],
                          "share_of_step": classes["gemm"]["share"]},
             "path_tflops": {"achieved": path_tflops, "flop_per_image": ENC_FLOP_PER_IMAGE_USEFUL + n_seg * DEC_FLOP_PER_PROMPT,
