@@ -161,6 +161,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (ep.act == 1) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) f[i] = gelu_erf(f[i]);
+          } else if (ep.act == 2) {   // ReLU (text_hidden_fcs, model/anyref.py:118-123)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.0f);
           }
           if (res_row) {
             const float4* r4 = reinterpret_cast<const float4*>(res_row + col0);

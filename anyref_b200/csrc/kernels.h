@@ -16,7 +16,7 @@ struct GemmEpilogue {
   int ldo;           // elements
   int out_fmt;       // SamFmt
   const float* bias; // [N] or null
-  int act;           // 0 none, 1 exact-erf GELU
+  int act;           // 0 none, 1 exact-erf GELU, 2 ReLU
   const float* res;  // fp32 residual source or null; row used = (row % res_mod); may alias `out` (fp32, in place)
   int ldr;
   int res_mod;

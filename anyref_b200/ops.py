@@ -37,7 +37,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, act: str = "none", resi
         assert bias.dtype == torch.float32 and bias.numel() == N and bias.is_contiguous()
     lib = _lib.load()
     rc = lib.sam_gemm(ptr(a), a.stride(0), ptr(w), w.stride(0), M, N, K, fmt_of(a.dtype), ptr(out), out.stride(0),
-                      fmt_of(out.dtype), ptr(bias), {"none": 0, "gelu": 1}[act], ptr(residual), ldr, rmod,
+                      fmt_of(out.dtype), ptr(bias), {"none": 0, "gelu": 1, "relu": 2}[act], ptr(residual), ldr, rmod,
                       stream_ptr(a.device))
     check(rc, "sam_gemm")
     return out

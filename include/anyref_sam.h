@@ -63,7 +63,7 @@ int sam_abi_version(void);
  *   A, W       : operand format `fmt` (0 fp16 / 1 bf16), row-major with leading dimensions lda / ldw (elements)
  *   out        : out_fmt 0/1/2, leading dimension ldo
  *   bias       : fp32 [N] or NULL
- *   act        : 0 none, 1 exact-erf GELU (common.py:18)
+ *   act        : 0 none, 1 exact-erf GELU (common.py:18), 2 ReLU (text_hidden_fcs, model/anyref.py:118-123)
  *   res        : fp32 residual [res_mod, ldr] or NULL; out[row] += res[row % res_mod]; may alias out (in place)
  */
 int sam_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, int K, int fmt, void* out, int ldo,

@@ -404,3 +404,45 @@ def test_fused_iou_statistics_are_exact(tiny, inp, orig):
     ref = dp.iou_stats([binary[i, 0].cpu() for i in clean], [gt[i, 0] for i in clean])
     s2 = sam.postprocess_and_score(low[clean], inp, orig, gt[clean].cuda())
     assert torch.allclose(s2.cpu().float(), ref, rtol=1e-6, atol=1e-6)
+
+
+def test_seg_head_from_hidden_states_vs_oracle(tiny):
+    """SURVEY 8a row T1 + 8f-1: last-layer hidden states -> text_hidden_fcs (model/anyref.py:116-127, :770) -> prompt
+    encoder / decoder / postprocess for every image, against the fp32 restatement of the same steps."""
+    from anyref_b200.seg_head import SegHead, build_text_hidden_fcs
+
+    sam, cfg, sd = tiny["sam"], tiny["cfg"], tiny["sd"]
+    sam.image_encoder.set_operand_dtype(torch.float16)
+    torch.manual_seed(5)
+    H = 512                                         # LLM width of the stand-in (4096 in AnyRef-7B)
+    fcs = build_text_hidden_fcs(H, 256)
+    assert list(fcs.state_dict()) == ["0.0.weight", "0.0.bias", "0.2.weight", "0.2.bias"]   # model/anyref.py:124 layout
+    ref_fcs = torch.nn.Sequential(torch.nn.Linear(H, H), torch.nn.ReLU(), torch.nn.Linear(H, 256), torch.nn.Dropout(0.0))
+    ref_fcs.load_state_dict(fcs[0].state_dict())
+    hidden = torch.randn(2, 40 + 255, H)
+    out_ids = torch.zeros(2, 41, dtype=torch.long)
+    SEG = 7
+    out_ids[0, 12] = SEG
+    out_ids[0, 30] = SEG
+    out_ids[1, 5] = SEG
+    idx = torch.where(out_ids[:, 1:] == SEG)
+    sizes, origs = [(1024, 1024), (1024, 683)], [(1024, 1024), (640, 427)]
+    with torch.no_grad():
+        pred = ref_fcs(hidden[idx[0], idx[1] + 255, :])
+        emb = tiny["emb"]
+        want = []
+        for b in range(2):
+            sp, de = O.prompt_encoder(sd, cfg, text_embeds=pred[idx[0] == b].unsqueeze(1))
+            low, _ = O.mask_decoder(sd, cfg, emb[b:b + 1], tiny["pe"], sp, de, False)
+            want.append(O.postprocess_masks(low, sizes[b], origs[b]).squeeze(1))
+    head = SegHead(sam, fcs.cuda())
+    got = head(hidden.cuda().to(torch.bfloat16), tuple(t.cuda() for t in idx), tiny["x"].cuda(), sizes, origs)
+    assert [tuple(g.shape) for g in got] == [(2, 1024, 1024), (1, 640, 427)]
+    for g, w in zip(got, want):
+        assert mask_iou(g, w) > 0.99
+        assert rel_fro(g, w) < 3e-2      # bf16 hidden states and projection operands
+    # no [SEG] token: one zero mask per image (model/anyref.py:762-764)
+    none = head(hidden.cuda(), (torch.empty(0, dtype=torch.long, device="cuda"),) * 2, tiny["x"].cuda(), sizes, origs)
+    assert len(none) == 2 and none[0].shape == (1, 1024, 1024) and float(none[0].abs().max()) == 0.0
+    with pytest.raises(NotImplementedError):
+        fcs[0](torch.randn(1, H, device="cuda"))    # grad enabled + trainable parameters: training is out of scope
