@@ -220,7 +220,8 @@ glob_attn2_kernel(const __grid_constant__ GlobAttnMapsG maps, const uint16_t* __
     }
   } else if (warp == 1) {
     // ============================================================ MMA issuer
-    if (lane == 0) {
+    if (ptx::elect_one()) {
+      const uint32_t tmem = 0;   // experiment: uniform-datapath issue (TMEM base is 0 for a 512-column allocation)
       const uint32_t id_S = ptx::make_idesc((uint32_t)fmt, 128, 128, 0, 0);
       const uint32_t id_TH = ptx::make_idesc((uint32_t)fmt, 128, 80, 0, 0);
       const uint32_t id_O64 = ptx::make_idesc((uint32_t)fmt, 128, 64, 0, 1);
