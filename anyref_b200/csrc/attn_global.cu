@@ -339,14 +339,14 @@ glob_attn_kernel(const __grid_constant__ GlobAttnMaps maps, const uint16_t* __re
 int samk_attn_global(const void* qkv, const void* rh_rev, const void* rw_rev, void* out, int B, int E, int heads,
                      int fmt, cudaStream_t stream) {
   SAM_REQUIRE(fmt == 0 || fmt == 1, "attn_global: fmt must be fp16/bf16");
-  SAM_REQUIRE(E == heads * HD, "attn_global: head_dim must be 80 (E=%d heads=%d)", E, heads);
   SAM_REQUIRE(B > 0, "attn_global: empty batch");
   // default: the decoupled-pipeline kernel (attn_global3.cu); SAM_ATTN_GLOBAL_V2=1 selects the two-tile ping-pong kernel
   // (attn_global2.cu), SAM_ATTN_GLOBAL_V1=1 this file's simpler one-tile-per-CTA kernel
   static const bool use_v1 = getenv("SAM_ATTN_GLOBAL_V1") != nullptr;
   static const bool use_v2 = getenv("SAM_ATTN_GLOBAL_V2") != nullptr;
+  if (!use_v1 && !use_v2) return samk_attn_global3(qkv, rh_rev, rw_rev, out, B, E, heads, fmt, stream);
+  SAM_REQUIRE(E == heads * HD, "attn_global: the v1 / v2 kernels need head_dim 80 (E=%d heads=%d)", E, heads);
   if (use_v2) return samk_attn_global2(qkv, rh_rev, rw_rev, out, B, E, heads, fmt, stream);
-  if (!use_v1) return samk_attn_global3(qkv, rh_rev, rw_rev, out, B, E, heads, fmt, stream);
   GlobAttnMaps maps;
   const int is_bf16 = (fmt == 1);
   const uint64_t rows = static_cast<uint64_t>(B) * G * G;

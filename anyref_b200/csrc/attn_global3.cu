@@ -24,7 +24,8 @@
 
 namespace {
 
-constexpr int HD = 80;
+// head_dim HD is a template parameter: 80 (ViT-H: 64-wide SWIZZLE_128B tile + 16-wide SWIZZLE_32B tail per operand) or
+// 64 (ViT-L / ViT-B: the 64-wide tile alone)
 constexpr int G = 64;            // token grid
 constexpr int BKV = 64;          // keys per block = one image row
 constexpr int kThreadsG = 352;
@@ -142,12 +143,15 @@ __device__ __forceinline__ void max_half(const uint32_t (&v)[32], const float (&
   }
 }
 
-template <int FMT>
+template <int FMT, int HD>
 __global__ void __launch_bounds__(kThreadsG, 1)
 glob_attn3_kernel(const __grid_constant__ GlobAttnMaps3 maps, const uint16_t* __restrict__ rh_rev,
                   const uint16_t* __restrict__ rw_rev, uint16_t* __restrict__ out, const int E, const int heads,
                   const float scale_log2e) {
   constexpr int fmt = FMT;
+  constexpr bool kTail = (HD > 64);
+  constexpr int kU4 = HD / 8;     // 16-byte units per operand row
+  constexpr int kKS = HD / 16;    // 16-wide K steps of a Q.K^T product / 16-column chunks of O
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
@@ -199,25 +203,27 @@ glob_attn3_kernel(const __grid_constant__ GlobAttnMaps3 maps, const uint16_t* __
     // Q tiles: issued right away (their buffers alias nothing)
     ptx::mbar_expect_tx(q_full, 2 * 128 * HD * 2);
     ptx::tma_load_2d(smem + OFF_Q64, &maps.q64, q_full, cq, row0);
-    ptx::tma_load_2d(smem + OFF_Q16, &maps.q16, q_full, cq + 64, row0);
     ptx::tma_load_2d(smem + OFF_Q64 + 16384, &maps.q64, q_full, cq, row0 + 128);
-    ptx::tma_load_2d(smem + OFF_Q16 + 4096, &maps.q16, q_full, cq + 64, row0 + 128);
+    if (kTail) {
+      ptx::tma_load_2d(smem + OFF_Q16, &maps.q16, q_full, cq + 64, row0);
+      ptx::tma_load_2d(smem + OFF_Q16 + 4096, &maps.q16, q_full, cq + 64, row0 + 128);
+    }
   }
   if (warp == 1) {
     ptx::tmem_alloc(tmem_slot, 512);
     ptx::tmem_relinquish();
   }
   // rel-pos operand tables -> smem (generic proxy)
-  for (int i = tid; i < 128 * 10; i += kThreadsG) {
-    const int r = i / 10, c = i % 10;
+  for (int i = tid; i < 128 * kU4; i += kThreadsG) {
+    const int r = i / kU4, c = i % kU4;
     const uint4 v = __ldg(reinterpret_cast<const uint4*>(rw_rev + r * HD) + c);
     if (c < 8)
       *reinterpret_cast<uint4*>(smem + OFF_RW64 + row_off64(r, c)) = v;
     else
       *reinterpret_cast<uint4*>(smem + OFF_RW16 + row_off16(r, c - 8)) = v;
   }
-  for (int i = tid; i < 80 * 10; i += kThreadsG) {
-    const int r = i / 10, c = i % 10;  // local row r <-> Rh_rev row th_start + r (rows >= 128 do not exist: zero)
+  for (int i = tid; i < 80 * kU4; i += kThreadsG) {
+    const int r = i / kU4, c = i % kU4;  // local row r <-> Rh_rev row th_start + r (rows >= 128 do not exist: zero)
     uint4 v = make_uint4(0, 0, 0, 0);
     if (th_start + r < 128) v = __ldg(reinterpret_cast<const uint4*>(rh_rev + (th_start + r) * HD) + c);
     // K-major, no swizzle: per 16-wide K step a block of 80 rows x 32B; 8-row groups of 256B = [k-lo 128B][k-hi 128B]
@@ -244,11 +250,11 @@ glob_attn3_kernel(const __grid_constant__ GlobAttnMaps3 maps, const uint16_t* __
         if (j >= kStagesKV) ptx::mbar_wait(&k_free[s], ph ^ 1);
         ptx::mbar_expect_tx(&k_full[s], BKV * HD * 2);
         ptx::tma_load_2d(smem + OFF_K64 + s * 8192, &maps.kv64, &k_full[s], ck, r);
-        ptx::tma_load_2d(smem + OFF_K16 + s * 2048, &maps.kv16, &k_full[s], ck + 64, r);
+        if (kTail) ptx::tma_load_2d(smem + OFF_K16 + s * 2048, &maps.kv16, &k_full[s], ck + 64, r);
         if (j >= kStagesKV) ptx::mbar_wait(&v_free[s], ph ^ 1);
         ptx::mbar_expect_tx(&v_full[s], BKV * HD * 2);
         ptx::tma_load_2d(smem + OFF_V64 + s * 8192, &maps.kv64, &v_full[s], cv, r);
-        ptx::tma_load_2d(smem + OFF_V16 + s * 2048, &maps.kv16, &v_full[s], cv + 64, r);
+        if (kTail) ptx::tma_load_2d(smem + OFF_V16 + s * 2048, &maps.kv16, &v_full[s], cv + 64, r);
       }
     }
   } else if (warp == 1 || warp == 10) {
@@ -278,7 +284,7 @@ glob_attn3_kernel(const __grid_constant__ GlobAttnMaps3 maps, const uint16_t* __
       ptx::tc_fence_after();
       // prologue: T_w = Q . Rw_rev^T -> S columns [0,128) ;  T_h = Q . Rh_rev[th_start..+80)^T -> O columns
 #pragma unroll
-      for (int k = 0; k < 5; ++k) {
+      for (int k = 0; k < kKS; ++k) {
         const uint64_t da = (k < 4) ? dq64 + 2 * k : dq16;
         const uint64_t dw = (k < 4) ? drw64 + 2 * k : drw16;
         ptx::mma_f16_ss(slot, da, dw, id_T, k != 0);
@@ -295,7 +301,7 @@ glob_attn3_kernel(const __grid_constant__ GlobAttnMaps3 maps, const uint16_t* __
         const uint32_t d = slot + (j & 1) * 64;
 #pragma unroll
         for (int k = 0; k < 4; ++k) ptx::mma_f16_ss(d, dq64 + 2 * k, dk64 + 2 * k, id_S, k != 0);
-        ptx::mma_f16_ss(d, dq16, dk16, id_S, 1);
+        if (kTail) ptx::mma_f16_ss(d, dq16, dk16, id_S, 1);
         ptx::mma_commit(&s_full[g * 2 + (j & 1)]);
         ptx::mma_commit(&k_free[s]);   // K(j) consumed by this tile (count 2: both issuers)
       };
@@ -323,7 +329,7 @@ glob_attn3_kernel(const __grid_constant__ GlobAttnMaps3 maps, const uint16_t* __
 #pragma unroll
         for (int ks = 0; ks < BKV / 16; ++ks) {
           ptx::mma_f16_ss(slot + TM_O, dp + 2 * ks, dv64 + ((ks * 2048) >> 4), id_O64, (j | ks) != 0);
-          ptx::mma_f16_ss(slot + TM_O + 64, dp + 2 * ks, dv16 + ((ks * 512) >> 4), id_O16, (j | ks) != 0);
+          if (kTail) ptx::mma_f16_ss(slot + TM_O + 64, dp + 2 * ks, dv16 + ((ks * 512) >> 4), id_O16, (j | ks) != 0);
         }
         ptx::mma_commit(&pv_done[g * 2 + bf]);
         ptx::mma_commit(&v_free[s]);   // V(j) consumed by this tile (count 2)
@@ -423,7 +429,7 @@ glob_attn3_kernel(const __grid_constant__ GlobAttnMaps3 maps, const uint16_t* __
         ptx::mbar_wait(&pv_done[g * 2 + (bf ^ 1)], ((j - 1) >> 1) & 1);   // every earlier P.V has landed in O
         ptx::tc_fence_after();
 #pragma unroll
-        for (int c = 0; c < 5; ++c) {
+        for (int c = 0; c < kKS; ++c) {
           uint32_t v[16];
           ptx::tmem_ld_32x32b_x16(trow + TM_O + c * 16, v);
           ptx::tmem_ld_wait();
@@ -450,7 +456,7 @@ glob_attn3_kernel(const __grid_constant__ GlobAttnMaps3 maps, const uint16_t* __
     const float inv = 1.0f / l;
     uint16_t* dst = out + static_cast<size_t>(row0 + g * 128 + row) * E + head * HD;
 #pragma unroll
-    for (int c = 0; c < 5; ++c) {
+    for (int c = 0; c < kKS; ++c) {
       uint32_t v[16];
       ptx::tmem_ld_32x32b_x16(trow + TM_O + c * 16, v);
       ptx::tmem_ld_wait();
@@ -481,7 +487,9 @@ glob_attn3_kernel(const __grid_constant__ GlobAttnMaps3 maps, const uint16_t* __
 int samk_attn_global3(const void* qkv, const void* rh_rev, const void* rw_rev, void* out, int B, int E, int heads,
                       int fmt, cudaStream_t stream) {
   SAM_REQUIRE(fmt == 0 || fmt == 1, "attn_global: fmt must be fp16/bf16");
-  SAM_REQUIRE(E == heads * HD, "attn_global: head_dim must be 80 (E=%d heads=%d)", E, heads);
+  SAM_REQUIRE(heads > 0 && E % heads == 0 && (E / heads == 80 || E / heads == 64),
+              "attn_global: head_dim must be 80 (ViT-H) or 64 (ViT-L / ViT-B), got E=%d heads=%d", E, heads);
+  const int HD = E / heads;
   SAM_REQUIRE(B > 0, "attn_global: empty batch");
   GlobAttnMaps3 maps;
   const int is_bf16 = (fmt == 1);
@@ -496,23 +504,23 @@ int samk_attn_global3(const void* qkv, const void* rh_rev, const void* rw_rev, v
   if (rc) return rc;
   static bool attr_done = false;
   if (!attr_done) {
-    SAM_CHECK_CUDA(cudaFuncSetAttribute(glob_attn3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesG));
-    SAM_CHECK_CUDA(cudaFuncSetAttribute(glob_attn3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesG));
+    SAM_CHECK_CUDA(cudaFuncSetAttribute(glob_attn3_kernel<0, 80>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesG));
+    SAM_CHECK_CUDA(cudaFuncSetAttribute(glob_attn3_kernel<1, 80>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesG));
+    SAM_CHECK_CUDA(cudaFuncSetAttribute(glob_attn3_kernel<0, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesG));
+    SAM_CHECK_CUDA(cudaFuncSetAttribute(glob_attn3_kernel<1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesG));
     attr_done = true;
   }
   const float scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
   const int grid = B * heads * (G * G / 256);
   const double bh = static_cast<double>(B) * heads;
-  samhost::LaunchScope scope(samhost::KC_ATTN_GLOBAL, stream, bh * (4.0 * 4096 * 4096 * 80 + 4.0 * 4096 * 64 * 80),
+  samhost::LaunchScope scope(samhost::KC_ATTN_GLOBAL, stream, bh * (4.0 * 4096 * 4096 * HD + 4.0 * 4096 * 64 * HD),
                              static_cast<double>(B) * 4096 * E * 2 * 4);
-  if (fmt == 0)
-    glob_attn3_kernel<0><<<grid, kThreadsG, kSmemBytesG, stream>>>(maps, static_cast<const uint16_t*>(rh_rev),
-                                                                    static_cast<const uint16_t*>(rw_rev),
-                                                                    static_cast<uint16_t*>(out), E, heads, scale_log2e);
-  else
-    glob_attn3_kernel<1><<<grid, kThreadsG, kSmemBytesG, stream>>>(maps, static_cast<const uint16_t*>(rh_rev),
-                                                                    static_cast<const uint16_t*>(rw_rev),
-                                                                    static_cast<uint16_t*>(out), E, heads, scale_log2e);
+  typedef void (*KernelFn)(GlobAttnMaps3, const uint16_t*, const uint16_t*, uint16_t*, int, int, float);
+  const KernelFn kernel = (HD == 80) ? (fmt == 0 ? glob_attn3_kernel<0, 80> : glob_attn3_kernel<1, 80>)
+                                     : (fmt == 0 ? glob_attn3_kernel<0, 64> : glob_attn3_kernel<1, 64>);
+  kernel<<<grid, kThreadsG, kSmemBytesG, stream>>>(maps, static_cast<const uint16_t*>(rh_rev),
+                                                   static_cast<const uint16_t*>(rw_rev), static_cast<uint16_t*>(out), E,
+                                                   heads, scale_log2e);
   SAM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

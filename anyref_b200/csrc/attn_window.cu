@@ -396,14 +396,14 @@ win_attn_kernel(const __grid_constant__ WinAttnMaps maps, const uint16_t* __rest
 int samk_attn_window(const void* qkv, const void* bias_op, const void* rel_tab, void* out, int B, int E, int heads,
                      int fmt, cudaStream_t stream) {
   SAM_REQUIRE(fmt == 0 || fmt == 1, "attn_window: fmt must be fp16/bf16");
-  SAM_REQUIRE(E == heads * HD, "attn_window: head_dim must be 80 (E=%d heads=%d)", E, heads);
   SAM_REQUIRE(B > 0, "attn_window: empty batch");
   // default: the tensor-memory-P kernel (attn_window4.cu); SAM_ATTN_WINDOW_V3=1 selects the shared-memory-P persistent
   // kernel (attn_window3.cu), SAM_ATTN_WINDOW_V2=1 this file's one-CTA-per-tile kernel (the simplest implementation)
   static const bool use_v2 = getenv("SAM_ATTN_WINDOW_V2") != nullptr;
   static const bool use_v3 = getenv("SAM_ATTN_WINDOW_V3") != nullptr;
+  if (!use_v2 && !use_v3) return samk_attn_window4(qkv, bias_op, rel_tab, out, B, E, heads, fmt, stream);
+  SAM_REQUIRE(E == heads * HD, "attn_window: the v2 / v3 kernels need head_dim 80 (E=%d heads=%d)", E, heads);
   if (use_v3) return samk_attn_window3(qkv, bias_op, rel_tab, out, B, E, heads, fmt, stream);
-  if (!use_v2) return samk_attn_window4(qkv, bias_op, rel_tab, out, B, E, heads, fmt, stream);
   WinAttnMaps maps;
   const int is_bf16 = (fmt == 1);
   const uint64_t ld = static_cast<uint64_t>(3) * E * 2;  // bytes per token row

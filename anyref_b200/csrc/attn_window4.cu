@@ -27,7 +27,8 @@
 
 namespace {
 
-constexpr int HD = 80;
+// head_dim HD is a template parameter: 80 (ViT-H: a 64-wide SWIZZLE_128B tile + a 16-wide SWIZZLE_32B tile per operand)
+// or 64 (ViT-L / ViT-B: the 64-wide tile alone)
 constexpr int WS = 14;
 constexpr int NTOK = WS * WS;  // 196
 constexpr int NKEY = 208;
@@ -197,12 +198,15 @@ __device__ __forceinline__ Item decode_item(int it, int heads) {
   return r;
 }
 
-template <int FMT>
+template <int FMT, int HD>
 __global__ void __launch_bounds__(kThreads4, 1)
 win_attn4_kernel(const __grid_constant__ WinAttnMaps4 maps, const uint16_t* __restrict__ bias_op,
                  uint16_t* __restrict__ out, const int E, const int heads, const int num_items,
                  const float scale_log2e) {
   constexpr int fmt = FMT;
+  constexpr bool kTail = (HD > 64);   // operands have a 16-wide tail beyond the 64-wide tile
+  constexpr int kU4 = HD / 8;         // 16-byte units per operand row
+  constexpr int kVCh = HD / 16;       // 16-wide V chunks
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
@@ -278,23 +282,25 @@ win_attn4_kernel(const __grid_constant__ WinAttnMaps4 maps, const uint16_t* __re
         ptx::mbar_expect_tx(&qk_full[s], bytes);
         if (n == 0) {
           ptx::tma_load_2d(smem + OFF_R64, &maps.r64, &qk_full[s], 0, 0);
-          ptx::tma_load_2d(smem + OFF_R16, &maps.r16, &qk_full[s], 64, 0);
+          if (kTail) ptx::tma_load_2d(smem + OFF_R16, &maps.r16, &qk_full[s], 64, 0);
         }
         ptx::tma_load_4d(st + OFF_Q64, &maps.qa64, &qk_full[s], cq, x0, y0, w.b);
-        ptx::tma_load_4d(st + OFF_Q16, &maps.qa16, &qk_full[s], cq + 64, x0, y0, w.b);
         ptx::tma_load_4d(st + OFF_Q64 + 16384, &maps.qb64, &qk_full[s], cq, x0, y0 + 9, w.b);
-        ptx::tma_load_4d(st + OFF_Q16 + 4096, &maps.qb16, &qk_full[s], cq + 64, x0, y0 + 9, w.b);
         ptx::tma_load_4d(st + OFF_K64, &maps.kv64, &qk_full[s], ck, x0, y0, w.b);
-        ptx::tma_load_4d(st + OFF_K16, &maps.kv16, &qk_full[s], ck + 64, x0, y0, w.b);
+        if (kTail) {
+          ptx::tma_load_4d(st + OFF_Q16, &maps.qa16, &qk_full[s], cq + 64, x0, y0, w.b);
+          ptx::tma_load_4d(st + OFF_Q16 + 4096, &maps.qb16, &qk_full[s], cq + 64, x0, y0 + 9, w.b);
+          ptx::tma_load_4d(st + OFF_K16, &maps.kv16, &qk_full[s], ck + 64, x0, y0, w.b);
+        }
       }
       __syncwarp();
       if (padded) {
         // token r of the window (iy = r / 14, ix = r % 14) lies outside the 64x64 grid -> q / k := qkv bias
         // (image_encoder.py:281 pads x with zeros BEFORE the qkv projection).  The two bias rows are fetched into
         // registers while the TMA is in flight, so the patch itself is shared-memory stores only.
-        uint4 bq[10], bk[10];
+        uint4 bq[kU4], bk[kU4];
 #pragma unroll
-        for (int c = 0; c < 10; ++c) {
+        for (int c = 0; c < kU4; ++c) {
           bq[c] = __ldg(reinterpret_cast<const uint4*>(bias_op + w.head * HD) + c);
           bk[c] = __ldg(reinterpret_cast<const uint4*>(bias_op + E + w.head * HD) + c);
         }
@@ -306,7 +312,7 @@ win_attn4_kernel(const __grid_constant__ WinAttnMaps4 maps, const uint16_t* __re
             uint8_t* q16 = st + OFF_Q16 + (r < 126 ? 0 : 4096);
             const int rq = r < 126 ? r : r - 126;
 #pragma unroll
-            for (int c = 0; c < 10; ++c) {
+            for (int c = 0; c < kU4; ++c) {
               if (c < 8) {
                 *reinterpret_cast<uint4*>(st + OFF_K64 + row_off64(r, c)) = bk[c];
                 *reinterpret_cast<uint4*>(q64 + row_off64(rq, c)) = bq[c];
@@ -339,19 +345,19 @@ win_attn4_kernel(const __grid_constant__ WinAttnMaps4 maps, const uint16_t* __re
         if (n >= 2) ptx::mbar_wait(&v_free[s], sph ^ 1);
         ptx::mbar_expect_tx(&v_full[s], static_cast<uint32_t>(NTOK * HD * 2));
 #pragma unroll
-        for (int c = 0; c < 5; ++c) ptx::tma_load_4d(sv + c * kVChunk, &maps.kv16, &v_full[s], cv + 16 * c, x0, y0, w.b);
+        for (int c = 0; c < kVCh; ++c) ptx::tma_load_4d(sv + c * kVChunk, &maps.kv16, &v_full[s], cv + 16 * c, x0, y0, w.b);
       }
       __syncwarp();
       if (padded) {
-        uint4 bv[10];
+        uint4 bv[kU4];
 #pragma unroll
-        for (int c = 0; c < 10; ++c) bv[c] = __ldg(reinterpret_cast<const uint4*>(bias_op + cv) + c);
+        for (int c = 0; c < kU4; ++c) bv[c] = __ldg(reinterpret_cast<const uint4*>(bias_op + cv) + c);
         ptx::mbar_wait(&v_full[s], sph);
         for (int r = lane; r < NTOK; r += 32) {
           const int iy = r / WS, ix = r % WS;
           if (y0 + iy >= 64 || x0 + ix >= 64) {
 #pragma unroll
-            for (int c = 0; c < 10; ++c)
+            for (int c = 0; c < kU4; ++c)
               *reinterpret_cast<uint4*>(sv + (c >> 1) * kVChunk + row_off16(r, c & 1)) = bv[c];
           }
         }
@@ -388,15 +394,15 @@ win_attn4_kernel(const __grid_constant__ WinAttnMaps4 maps, const uint16_t* __re
         ptx::tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 4; ++k) ptx::mma_f16_ss(slot, dq64 + 2 * k, dk64 + 2 * k, id_S, k != 0);
-        ptx::mma_f16_ss(slot, dq16, dk16, id_S, 1);
+        if (kTail) ptx::mma_f16_ss(slot, dq16, dk16, id_S, 1);
         // table rows 32..63 = rel_pos_w (+4096 B / +1024 B), rows 0..31 = rel_pos_h.  Tw is issued after S on
         // purpose: it overwrites the dead pad-key columns 196..207 of S.
 #pragma unroll
         for (int k = 0; k < 4; ++k) ptx::mma_f16_ss(slot + 196, dq64 + 2 * k, dr64 + (4096 >> 4) + 2 * k, id_T, k != 0);
-        ptx::mma_f16_ss(slot + 196, dq16, dr16 + (1024 >> 4), id_T, 1);
+        if (kTail) ptx::mma_f16_ss(slot + 196, dq16, dr16 + (1024 >> 4), id_T, 1);
 #pragma unroll
         for (int k = 0; k < 4; ++k) ptx::mma_f16_ss(slot + 224, dq64 + 2 * k, dr64 + 2 * k, id_T, k != 0);
-        ptx::mma_f16_ss(slot + 224, dq16, dr16, id_T, 1);
+        if (kTail) ptx::mma_f16_ss(slot + 224, dq16, dr16, id_T, 1);
         ptx::mma_commit(&s_full[g]);
         ptx::mma_commit(&qk_free[s]);
         ptx::mbar_wait(&v_ready[s], sph);
@@ -498,10 +504,10 @@ win_attn4_kernel(const __grid_constant__ WinAttnMaps4 maps, const uint16_t* __re
         uint32_t o0[32], o1[32], o2[32];
         ptx::tmem_ld_32x32b_x32(trow + TM_O, o0);
         ptx::tmem_ld_32x32b_x32(trow + TM_O + 32, o1);
-        ptx::tmem_ld_32x32b_x16_lo(trow + TM_O + 64, o2);
+        if (kTail) ptx::tmem_ld_32x32b_x16_lo(trow + TM_O + 64, o2);
         ptx::tmem_ld_wait_dep(o0);
         ptx::tmem_ld_wait_dep(o1);
-        ptx::tmem_ld_wait_dep(o2);
+        if (kTail) ptx::tmem_ld_wait_dep(o2);
         ptx::tc_fence_before();
         ptx::mbar_arrive(&o_done[g]);
         const float inv = 1.0f / sum;
@@ -510,7 +516,7 @@ win_attn4_kernel(const __grid_constant__ WinAttnMaps4 maps, const uint16_t* __re
         if (ok) {
           uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<size_t>(w.b) * 4096 + (y * 64 + x)) * E + w.head * HD);
 #pragma unroll
-          for (int c = 0; c < 10; ++c) {
+          for (int c = 0; c < kU4; ++c) {
             const uint32_t* v = (c < 4) ? &o0[c * 8] : (c < 8) ? &o1[(c - 4) * 8] : &o2[(c - 8) * 8];
             uint4 u;
             u.x = ptx::pack2t<FMT>(__uint_as_float(v[0]) * inv, __uint_as_float(v[1]) * inv);
@@ -537,7 +543,9 @@ win_attn4_kernel(const __grid_constant__ WinAttnMaps4 maps, const uint16_t* __re
 int samk_attn_window4(const void* qkv, const void* bias_op, const void* rel_tab, void* out, int B, int E, int heads,
                       int fmt, cudaStream_t stream) {
   SAM_REQUIRE(fmt == 0 || fmt == 1, "attn_window: fmt must be fp16/bf16");
-  SAM_REQUIRE(E == heads * HD, "attn_window: head_dim must be 80 (E=%d heads=%d)", E, heads);
+  SAM_REQUIRE(heads > 0 && E % heads == 0 && (E / heads == 80 || E / heads == 64),
+              "attn_window: head_dim must be 80 (ViT-H) or 64 (ViT-L / ViT-B), got E=%d heads=%d", E, heads);
+  const int HD = E / heads;
   SAM_REQUIRE(B > 0, "attn_window: empty batch");
   WinAttnMaps4 maps;
   const int is_bf16 = (fmt == 1);
@@ -558,8 +566,10 @@ int samk_attn_window4(const void* qkv, const void* bias_op, const void* rel_tab,
   if (rc) return rc;
   static bool attr_done = false;
   if (!attr_done) {
-    SAM_CHECK_CUDA(cudaFuncSetAttribute(win_attn4_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes4));
-    SAM_CHECK_CUDA(cudaFuncSetAttribute(win_attn4_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes4));
+    SAM_CHECK_CUDA(cudaFuncSetAttribute(win_attn4_kernel<0, 80>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes4));
+    SAM_CHECK_CUDA(cudaFuncSetAttribute(win_attn4_kernel<1, 80>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes4));
+    SAM_CHECK_CUDA(cudaFuncSetAttribute(win_attn4_kernel<0, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes4));
+    SAM_CHECK_CUDA(cudaFuncSetAttribute(win_attn4_kernel<1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes4));
     attr_done = true;
   }
   const float scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
@@ -567,16 +577,13 @@ int samk_attn_window4(const void* qkv, const void* bias_op, const void* rel_tab,
   int grid = samhost::sm_count();
   if (grid > num_items) grid = num_items;
   const double wh = static_cast<double>(num_items);
-  samhost::LaunchScope scope(samhost::KC_ATTN_WINDOW, stream, wh * (4.0 * 196 * 196 * 80 + 4.0 * 196 * 14 * 80),
+  samhost::LaunchScope scope(samhost::KC_ATTN_WINDOW, stream, wh * (4.0 * 196 * 196 * HD + 4.0 * 196 * 14 * HD),
                              static_cast<double>(B) * 4096 * E * 2 * 4);
-  if (fmt == 0)
-    win_attn4_kernel<0><<<grid, kThreads4, kSmemBytes4, stream>>>(maps, static_cast<const uint16_t*>(bias_op),
-                                                                   static_cast<uint16_t*>(out), E, heads, num_items,
-                                                                   scale_log2e);
-  else
-    win_attn4_kernel<1><<<grid, kThreads4, kSmemBytes4, stream>>>(maps, static_cast<const uint16_t*>(bias_op),
-                                                                   static_cast<uint16_t*>(out), E, heads, num_items,
-                                                                   scale_log2e);
+  typedef void (*KernelFn)(WinAttnMaps4, const uint16_t*, uint16_t*, int, int, int, float);
+  const KernelFn kernel = (HD == 80) ? (fmt == 0 ? win_attn4_kernel<0, 80> : win_attn4_kernel<1, 80>)
+                                     : (fmt == 0 ? win_attn4_kernel<0, 64> : win_attn4_kernel<1, 64>);
+  kernel<<<grid, kThreads4, kSmemBytes4, stream>>>(maps, static_cast<const uint16_t*>(bias_op), static_cast<uint16_t*>(out),
+                                                   E, heads, num_items, scale_log2e);
   SAM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -69,7 +69,8 @@ int samk_encoder_forward(const SamEncoderShape& s, const void* w16v, const float
   SAM_REQUIRE(B > 0, "image encoder: empty batch");
   SAM_REQUIRE(fmt == 0 || fmt == 1, "image encoder: operand format must be fp16 (0) or bf16 (1)");
   SAM_REQUIRE(s.img == 1024 && s.patch == 16 && s.window == 14, "image encoder: only 1024/16 images with 14x14 windows");
-  SAM_REQUIRE(E % s.heads == 0 && E / s.heads == 80, "image encoder: head_dim must be 80 (ViT-H family), got %d/%d", E, s.heads);
+  SAM_REQUIRE(E % s.heads == 0 && (E / s.heads == 80 || E / s.heads == 64),
+              "image encoder: head_dim must be 80 (ViT-H) or 64 (ViT-L / ViT-B), got %d/%d", E, s.heads);
   SAM_REQUIRE(s.depth <= 64, "image encoder: depth %d > 64", s.depth);
   SAM_REQUIRE(workspace_bytes >= samk_encoder_workspace_bytes(s, B), "image encoder: workspace too small");
   SAM_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "image encoder: workspace must be 1024-byte aligned");

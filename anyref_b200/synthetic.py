@@ -55,6 +55,8 @@ CONFIGS = {
     "vit_b": SamConfig(embed_dim=768, depth=12, num_heads=12, global_attn_indexes=(2, 5, 8, 11)),
     # test-size model with ViT-H's head_dim (80), one windowed + one global block
     "vit_tiny80": SamConfig(embed_dim=160, depth=2, num_heads=2, global_attn_indexes=(1,)),
+    # same with ViT-L / ViT-B's head_dim (64)
+    "vit_tiny64": SamConfig(embed_dim=128, depth=2, num_heads=2, global_attn_indexes=(1,)),
 }
 
 

@@ -117,6 +117,7 @@ def test_layernorm2d_to_nchw(ops):
 
 # ------------------------------------------------------------------------------------------------------- attention
 def _window_reference(qkv, bias, rel_h, rel_w, B, heads):
+    hd = qkv.shape[1] // 3 // heads
     """image_encoder.py:263-288 + :235-257 + :354-392 on projected qkv; padded tokens carry the qkv bias because the
     reference pads the LayerNorm output with zeros BEFORE the qkv Linear (image_encoder.py:179-183)."""
     E = qkv.shape[1] // 3
@@ -124,24 +125,25 @@ def _window_reference(qkv, bias, rel_h, rel_w, B, heads):
     xp[:, :64, :64] = qkv.float().view(B, 64, 64, 3 * E)
     win = xp.view(B, 5, 14, 5, 14, 3 * E).permute(0, 1, 3, 2, 4, 5).reshape(-1, 14, 14, 3 * E)
     b = win.shape[0]
-    q, k, v = win.reshape(b, 196, 3, heads, 80).permute(2, 0, 3, 1, 4).reshape(3, b * heads, 196, 80).unbind(0)
-    attn = (q * 80 ** -0.5) @ k.transpose(-2, -1)
+    q, k, v = win.reshape(b, 196, 3, heads, hd).permute(2, 0, 3, 1, 4).reshape(3, b * heads, 196, hd).unbind(0)
+    attn = (q * hd ** -0.5) @ k.transpose(-2, -1)
     rh, rw = O._rel_table(14, 14, rel_h.float()), O._rel_table(14, 14, rel_w.float())
-    rq = q.reshape(b * heads, 14, 14, 80)
+    rq = q.reshape(b * heads, 14, 14, hd)
     a = torch.einsum("bhwc,hkc->bhwk", rq, rh)
     c = torch.einsum("bhwc,wkc->bhwk", rq, rw)
     attn = (attn.view(b * heads, 14, 14, 14, 14) + a[..., None] + c[:, :, :, None, :]).view(b * heads, 196, 196)
-    o = (attn.softmax(-1) @ v).view(b, heads, 14, 14, 80).permute(0, 2, 3, 1, 4).reshape(b, 14, 14, E)
+    o = (attn.softmax(-1) @ v).view(b, heads, 14, 14, hd).permute(0, 2, 3, 1, 4).reshape(b, 14, 14, E)
     return O._unpartition(o, 14, (70, 70), (64, 64)).reshape(B * 4096, E)
 
 
 def _global_reference(qkv, rel_h, rel_w, heads):
+    hd = qkv.shape[1] // 3 // heads
     E = qkv.shape[1] // 3
-    x = qkv.float().view(1, 4096, 3, heads, 80).permute(2, 0, 3, 1, 4).reshape(3, heads, 4096, 80)
+    x = qkv.float().view(1, 4096, 3, heads, hd).permute(2, 0, 3, 1, 4).reshape(3, heads, 4096, hd)
     q, k, v = x.unbind(0)
-    attn = (q * 80 ** -0.5) @ k.transpose(-2, -1)
+    attn = (q * hd ** -0.5) @ k.transpose(-2, -1)
     rh, rw = O._rel_table(64, 64, rel_h.float()), O._rel_table(64, 64, rel_w.float())
-    rq = q.reshape(heads, 64, 64, 80)
+    rq = q.reshape(heads, 64, 64, hd)
     a = torch.einsum("bhwc,hkc->bhwk", rq, rh)
     c = torch.einsum("bhwc,wkc->bhwk", rq, rw)
     attn = (attn.view(heads, 64, 64, 64, 64) + a[..., None] + c[:, :, :, None, :]).view(heads, 4096, 4096)
@@ -223,6 +225,29 @@ def test_global_attention_peaked_logits(ops, dt, tol):
     want = _global_reference(qkv, gh, gw, heads)
     assert bool(torch.isfinite(got.float()).all())
     assert rel_fro(got, want) < tol
+
+
+@pytest.mark.parametrize("dt,tol", [(torch.float16, 1.5e-3), (torch.bfloat16, 6e-3)])
+@pytest.mark.parametrize("peaked", [False, True])
+def test_attention_head_dim_64(ops, dt, tol, peaked):
+    """ViT-L / ViT-B (build_sam.py:28-45) have head_dim 64: the same kernels without the 16-wide operand tail."""
+    torch.manual_seed(9)
+    heads, hd, B = 3, 64, 1
+    E = heads * hd
+    qkv = torch.randn(B * 4096, 3 * E, device=DEV)
+    if peaked:
+        qkv[:, :2 * E] *= 3.0
+    qkv = qkv.to(dt)
+    bias = (torch.randn(3 * E, device=DEV) * 0.5).to(dt)
+    rel_h = (torch.randn(27, hd, device=DEV) * 0.2).to(dt)
+    rel_w = (torch.randn(27, hd, device=DEV) * 0.2).to(dt)
+    got = ops.attn_window(qkv, bias, ops.window_rel_table(rel_h, rel_w, dt), B, heads)
+    assert rel_fro(got, _window_reference(qkv, bias, rel_h, rel_w, B, heads)) < (tol * 1.5 if peaked else tol)
+    gh = (torch.randn(127, hd, device=DEV) * 0.2).to(dt)
+    gw = (torch.randn(127, hd, device=DEV) * 0.2).to(dt)
+    got = ops.attn_global(qkv, ops.global_rel_table(gh, dt), ops.global_rel_table(gw, dt), B, heads)
+    assert bool(torch.isfinite(got.float()).all())
+    assert rel_fro(got, _global_reference(qkv, gh, gw, heads)) < (tol * 1.5 if peaked else tol)
 
 
 def test_rel_pos_index_tables_match_get_rel_pos(ops):

@@ -446,3 +446,42 @@ def test_seg_head_from_hidden_states_vs_oracle(tiny):
     assert len(none) == 2 and none[0].shape == (1, 1024, 1024) and float(none[0].abs().max()) == 0.0
     with pytest.raises(NotImplementedError):
         fcs[0](torch.randn(1, H, device="cuda"))    # grad enabled + trainable parameters: training is out of scope
+
+
+@pytest.mark.parametrize("dt,tol", [(torch.float16, 2e-3), (torch.bfloat16, 1e-2)])
+def test_head_dim_64_encoder_vs_oracle(dt, tol):
+    """the ViT-L / ViT-B family (head_dim 64, build_sam.py:28-45) through the same encoder driver, on a
+    test-size model with one windowed and one global block."""
+    from anyref_b200.segment_anything import build_sam_from_config
+
+    cfg = CONFIGS["vit_tiny64"]
+    sd = synthetic_state_dict(cfg)
+    x = synthetic_images(1, seed=3)
+    taps = {}
+    with torch.no_grad():
+        want = O.image_encoder(sd, x, cfg, taps)
+    sam = build_sam_from_config(cfg)
+    sam.load_state_dict(sd, strict=True)
+    sam = sam.cuda()
+    sam.image_encoder.set_operand_dtype(dt)
+    for blk in (0, 1):
+        tap = torch.empty(4096, cfg.embed_dim, device="cuda")
+        sam.image_encoder(x.cuda(), _tap=(blk, tap))
+        assert rel_fro(tap.view(1, 64, 64, -1), taps[f"block{blk}"]) < tol
+    assert rel_fro(sam.image_encoder(x.cuda()), want) < tol
+
+
+def test_vit_l_and_vit_b_builders_run():
+    """build_sam_vit_l / build_sam_vit_b (model/anyref.py:98-105 picks them by checkpoint name): full-size encoders with
+    synthetic weights produce finite [B,256,64,64] embeddings (shape / launch-configuration coverage; numerics are
+    pinned by the head_dim-64 tests above)."""
+    from anyref_b200.segment_anything import build_sam_vit_b, build_sam_vit_l
+
+    x = synthetic_images(1, seed=4).cuda()
+    for build, name in ((build_sam_vit_b, "vit_b"), (build_sam_vit_l, "vit_l")):
+        sam = build(None)
+        sam.load_state_dict(synthetic_state_dict(name), strict=True)
+        sam = sam.cuda()
+        emb = sam.image_encoder(x)
+        assert emb.shape == (1, 256, 64, 64) and bool(torch.isfinite(emb).all())
+        assert 0.5 < float(emb.std()) < 2.0      # LayerNorm2d output

@@ -125,3 +125,14 @@ def test_resize_longest_side_matches_reference(ref_sa):
                            ref.apply_boxes_torch(torch.from_numpy(box), (h, w)))
     img = rng.integers(0, 256, size=(120, 200, 3), dtype=np.uint8)
     assert np.array_equal(mine.apply_image(img), ref.apply_image(img))
+
+
+@torch.no_grad()
+def test_encoder_bit_identical_head_dim_64(ref_sa):
+    """The ViT-L / ViT-B family (head_dim 64): the restatement stays bit-identical to the reference encoder."""
+    cfg = CONFIGS["vit_tiny64"]
+    sd = synthetic_state_dict(cfg, seed=1234)
+    ref = build_reference_sam(ref_sa, cfg)
+    ref.load_state_dict(sd, strict=True)
+    x = synthetic_images(1, seed=3)
+    assert torch.equal(O.image_encoder(sd, x, cfg), ref.image_encoder(x))
