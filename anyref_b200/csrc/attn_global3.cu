@@ -88,59 +88,57 @@ __device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// 32 keys (kw = C*32 .. C*32+31) of a key row: logits in the log2 domain relative to the reference maximum (folded
-// into rh), exp2, row-sum (two partial sums), P -> shared memory in operand format.
-template <int C, int FMT>
-__device__ __forceinline__ void softmax_half(const uint32_t (&v)[32], const float (&relw)[64], f32x2 rh2, f32x2 sc2,
-                                             uint32_t prow, int sw, f32x2& bsum2) {
-  uint32_t pk[16];
+// 16 keys (kw = Q*16 .. Q*16+15) of a key row: logits in the log2 domain relative to the reference maximum (folded
+// into rh), exp2, row-sum (two partial sums), P -> shared memory in operand format (two 16-byte units of the row).
+template <int Q, int FMT>
+__device__ __forceinline__ void softmax_q16(const uint32_t (&v)[16], const float (&relw)[64], f32x2 rh2, f32x2 sc2,
+                                            uint32_t prow /* row base ^ (swizzle << 4) */, f32x2& bsum2) {
+  uint32_t pk[8];
 #pragma unroll
-  for (int i = 0; i < 32; i += 2) {
+  for (int i = 0; i < 16; i += 2) {
     f32x2 x = fma2(pk2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), sc2, rh2);
-    x = add2(x, pk2(relw[C * 32 + i], relw[C * 32 + i + 1]));
-    float x0, x1, p0, p1;
+    x = add2(x, pk2(relw[Q * 16 + i], relw[Q * 16 + i + 1]));
+    float x0, x1;
     upk2(x, x0, x1);
-    if (kPolyEvery > 0 && ((i >> 1) % kPolyEvery) == kPolyEvery - 1) {
-      // every kPolyEvery-th pair takes its exponentials on the FMA pipe instead of the MUFU (the kernel's bound):
-      // 2^x = 2^n * 2^f, n = round(x) via the 1.5 * 2^23 trick, 2^f by a degree-4 polynomial on [-0.5, 0.5]
-      // (max relative error 3.1e-6, far below the 16-bit rounding of P); the exponent is added as an integer.
-      x0 = fmaxf(x0, -125.0f);
-      x1 = fmaxf(x1, -125.0f);
-      const f32x2 xc = pk2(x0, x1);
-      const f32x2 t = add2(xc, pk2(12582912.0f, 12582912.0f));
-      const f32x2 nf = add2(t, pk2(-12582912.0f, -12582912.0f));
-      const f32x2 f = fma2(nf, pk2(-1.0f, -1.0f), xc);
-      f32x2 q = fma2(pk2(0.00960039533674717f, 0.00960039533674717f), f, pk2(0.05591689422726631f, 0.05591689422726631f));
-      q = fma2(q, f, pk2(0.24023719131946564f, 0.24023719131946564f));
-      q = fma2(q, f, pk2(0.6931219696998596f, 0.6931219696998596f));
-      q = fma2(q, f, pk2(1.0f, 1.0f));
-      float q0, q1, t0, t1;
-      upk2(q, q0, q1);
-      upk2(t, t0, t1);
-      p0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(t0) << 23));
-      p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(t1) << 23));
-    } else {
-      p0 = ex2(x0);
-      p1 = ex2(x1);
-    }
+    const float p0 = ex2(x0), p1 = ex2(x1);
     bsum2 = add2(bsum2, pk2(p0, p1));
     pk[i >> 1] = ptx::pack2t<FMT>(p0, p1);
   }
+  ptx::st_shared_v4(prow ^ ((Q * 2) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
+  ptx::st_shared_v4(prow ^ ((Q * 2 + 1) << 4), make_uint4(pk[4], pk[5], pk[6], pk[7]));
+}
+
+template <int Q>
+__device__ __forceinline__ void max_q16(const uint32_t (&v)[16], const float (&relw)[64], float rh, float scale_log2e,
+                                        float& m0, float& m1) {
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int chunk = C * 4 + q;   // 16-byte chunk (8 keys) of the 128-byte P row
-    ptx::st_shared_v4(prow + ((chunk ^ sw) << 4), make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]));
+  for (int i = 0; i < 16; i += 2) {
+    m0 = fmaxf(m0, fmaf(__uint_as_float(v[i]), scale_log2e, rh) + relw[Q * 16 + i]);
+    m1 = fmaxf(m1, fmaf(__uint_as_float(v[i + 1]), scale_log2e, rh) + relw[Q * 16 + i + 1]);
   }
 }
 
-template <int C>
-__device__ __forceinline__ void max_half(const uint32_t (&v)[32], const float (&relw)[64], float rh, float scale_log2e,
-                                         float& bmax) {
-#pragma unroll
-  for (int i = 0; i < 32; i += 2) {
-    bmax = fmaxf(bmax, fmaxf(fmaf(__uint_as_float(v[i]), scale_log2e, rh) + relw[C * 32 + i],
-                             fmaf(__uint_as_float(v[i + 1]), scale_log2e, rh) + relw[C * 32 + i + 1]));
-  }
+// One pass over the 64 S columns of a key row, 16 at a time with the next tcgen05.ld in flight behind the arithmetic of
+// the current quarter (only 32 S registers live).  MODE 0: probabilities (P -> smem, row sum);  MODE 1: maximum only.
+template <int MODE, int FMT>
+__device__ __forceinline__ void block_pass(uint32_t ts, const float (&relw)[64], float rh, float scale_log2e,
+                                           uint32_t prow, f32x2& bsum2, float& bmax) {
+  const f32x2 sc2 = pk2(scale_log2e, scale_log2e), rh2 = pk2(rh, rh);
+  float m0 = -INFINITY, m1 = -INFINITY;
+  uint32_t a[16], b[16];
+  ptx::tmem_ld_32x32b_x16(ts, a);
+  ptx::tmem_ld_wait_dep16(a);
+  ptx::tmem_ld_32x32b_x16(ts + 16, b);
+  if (MODE == 0) softmax_q16<0, FMT>(a, relw, rh2, sc2, prow, bsum2); else max_q16<0>(a, relw, rh, scale_log2e, m0, m1);
+  ptx::tmem_ld_wait_dep16(b);
+  ptx::tmem_ld_32x32b_x16(ts + 32, a);
+  if (MODE == 0) softmax_q16<1, FMT>(b, relw, rh2, sc2, prow, bsum2); else max_q16<1>(b, relw, rh, scale_log2e, m0, m1);
+  ptx::tmem_ld_wait_dep16(a);
+  ptx::tmem_ld_32x32b_x16(ts + 48, b);
+  if (MODE == 0) softmax_q16<2, FMT>(a, relw, rh2, sc2, prow, bsum2); else max_q16<2>(a, relw, rh, scale_log2e, m0, m1);
+  ptx::tmem_ld_wait_dep16(b);
+  if (MODE == 0) softmax_q16<3, FMT>(b, relw, rh2, sc2, prow, bsum2); else max_q16<3>(b, relw, rh, scale_log2e, m0, m1);
+  if (MODE == 1) bmax = fmaxf(m0, m1);
 }
 
 template <int FMT, int HD>
@@ -381,7 +379,6 @@ glob_attn3_kernel(const __grid_constant__ GlobAttnMaps3 maps, const uint16_t* __
     ptx::tc_fence_before();
     ptx::mbar_arrive(pro_done);
 
-    const f32x2 sc2 = pk2(scale_log2e, scale_log2e);
     float m_ref = 0.f;   // reference maximum (log2 domain) all stored probabilities are relative to
     float l = 0.f;       // running row sum relative to m_ref
 #pragma unroll 1
@@ -389,38 +386,30 @@ glob_attn3_kernel(const __grid_constant__ GlobAttnMaps3 maps, const uint16_t* __
       const int bf = j & 1;
       const uint32_t ph = (j >> 1) & 1;
       const uint32_t ts = trow + bf * 64;
-      const uint32_t prow = sbase + OFF_P + (g * 2 + bf) * 16384 + row * 128;
+      const uint32_t prow = (sbase + OFF_P + (g * 2 + bf) * 16384 + row * 128) ^ (sw << 4);   // 128-byte aligned row
       const float2 rhp = __half22float2(*reinterpret_cast<const __half2*>(&relh_s[(j >> 1) * 256]));
       float rh = (bf ? rhp.y : rhp.x);
-      uint32_t va[32], vb[32];
       ptx::mbar_wait(&s_full[g * 2 + bf], ph);
       ptx::tc_fence_after();
-      ptx::tmem_ld_32x32b_x32(ts, va);
-      ptx::tmem_ld_32x32b_x32(ts + 32, vb);
-      ptx::tmem_ld_wait();
+      f32x2 bsum2 = 0ull;
+      float bm = 0.f;
       if (j == 0) {
-        float bm = -INFINITY;
-        max_half<0>(va, relw, rh, scale_log2e, bm);
-        max_half<1>(vb, relw, rh, scale_log2e, bm);
+        block_pass<1, FMT>(ts, relw, rh, scale_log2e, prow, bsum2, bm);
         m_ref = bm;
       }
       if (j >= 2) {
         ptx::mbar_wait(&pv_done[g * 2 + bf], ph ^ 1);   // P.V of block j-2 finished: this P buffer is reusable
       }
       rh -= m_ref;
-      f32x2 bsum2 = 0ull;
-      softmax_half<0, FMT>(va, relw, pk2(rh, rh), sc2, prow, sw, bsum2);
-      softmax_half<1, FMT>(vb, relw, pk2(rh, rh), sc2, prow, sw, bsum2);
+      block_pass<0, FMT>(ts, relw, rh, scale_log2e, prow, bsum2, bm);
       float s0, s1;
       upk2(bsum2, s0, s1);
       float bsum = s0 + s1;
       if (__any_sync(0xffffffffu, !(bsum <= kSumLimit))) {
         // rare: some row of this warp has logits far above its reference.  Move the reference to the block maximum,
-        // rescale the accumulated O row and row sum, and redo the block.  (j == 0 never gets here: its reference is
-        // its own maximum, so bsum <= 64.)
-        float bm = -INFINITY;
-        max_half<0>(va, relw, rh, scale_log2e, bm);
-        max_half<1>(vb, relw, rh, scale_log2e, bm);
+        // rescale the accumulated O row and row sum, and redo the block (S is still in its TMEM buffer).  (j == 0 never
+        // gets here: its reference is its own maximum, so bsum <= 64.)
+        block_pass<1, FMT>(ts, relw, rh, scale_log2e, prow, bsum2, bm);
         const float delta = fmaxf(bm, 0.f);
         const float alpha = ex2(-delta);
         m_ref += delta;
@@ -439,8 +428,7 @@ glob_attn3_kernel(const __grid_constant__ GlobAttnMaps3 maps, const uint16_t* __
         }
         tmem_st_wait();
         bsum2 = 0ull;
-        softmax_half<0, FMT>(va, relw, pk2(rh, rh), sc2, prow, sw, bsum2);
-        softmax_half<1, FMT>(vb, relw, pk2(rh, rh), sc2, prow, sw, bsum2);
+        block_pass<0, FMT>(ts, relw, rh, scale_log2e, prow, bsum2, bm);
         upk2(bsum2, s0, s1);
         bsum = s0 + s1;
       }

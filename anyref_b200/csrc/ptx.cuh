@@ -264,6 +264,13 @@ __device__ __forceinline__ void tmem_ld_wait_dep(uint32_t (&v)[32]) {
                :
                : "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait_dep16(uint32_t (&v)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+               :
+               : "memory");
+}
 // 16 columns into the first half of a 32-register array
 __device__ __forceinline__ void tmem_ld_32x32b_x16_lo(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
