@@ -56,8 +56,9 @@ constexpr float kSumLimit = 1024.0f;
 #ifndef SAM_GLOB3_POLY_EVERY
 #define SAM_GLOB3_POLY_EVERY 0
 #endif
-constexpr int kPolyEvery = SAM_GLOB3_POLY_EVERY;   // 0: all exponentials on the MUFU (4 measured 4 % SLOWER: the softmax
-                                                   // warps are issue / latency bound, not MUFU bound)   // a block's probability sum above this moves the reference maximum
+constexpr int kPolyEvery = SAM_GLOB3_POLY_EVERY;   // 0: all exponentials on the MUFU.  Measured: every 4th pair on the
+                                                   // FMA pipe 2.04 ms, every 2nd 2.13 ms, none 2.03 ms -- the softmax warps are
+                                                   // issue / latency bound, not MUFU bound, so the offload does not pay   // a block's probability sum above this moves the reference maximum
 
 struct GlobAttnMaps3 {
   CUtensorMap q64, q16;    // 2-D over qkv [B*4096, 3E]: box {64,128} SWIZZLE_128B and {16,128} SWIZZLE_32B
@@ -98,9 +99,31 @@ __device__ __forceinline__ void softmax_q16(const uint32_t (&v)[16], const float
   for (int i = 0; i < 16; i += 2) {
     f32x2 x = fma2(pk2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), sc2, rh2);
     x = add2(x, pk2(relw[Q * 16 + i], relw[Q * 16 + i + 1]));
-    float x0, x1;
+    float x0, x1, p0, p1;
     upk2(x, x0, x1);
-    const float p0 = ex2(x0), p1 = ex2(x1);
+    if (kPolyEvery > 0 && ((Q * 8 + (i >> 1)) % kPolyEvery) == kPolyEvery - 1) {
+      // every kPolyEvery-th pair takes its exponentials on the FMA pipe instead of the MUFU:
+      // 2^x = 2^n * 2^f, n = round(x) via the 1.5 * 2^23 trick, 2^f by a degree-4 polynomial on [-0.5, 0.5]
+      // (max relative error 3.1e-6, far below the 16-bit rounding of P); the exponent is added as an integer.
+      x0 = fmaxf(x0, -125.0f);
+      x1 = fmaxf(x1, -125.0f);
+      const f32x2 xc = pk2(x0, x1);
+      const f32x2 t = add2(xc, pk2(12582912.0f, 12582912.0f));
+      const f32x2 nf = add2(t, pk2(-12582912.0f, -12582912.0f));
+      const f32x2 f = fma2(nf, pk2(-1.0f, -1.0f), xc);
+      f32x2 q = fma2(pk2(0.00960039533674717f, 0.00960039533674717f), f, pk2(0.05591689422726631f, 0.05591689422726631f));
+      q = fma2(q, f, pk2(0.24023719131946564f, 0.24023719131946564f));
+      q = fma2(q, f, pk2(0.6931219696998596f, 0.6931219696998596f));
+      q = fma2(q, f, pk2(1.0f, 1.0f));
+      float q0, q1, t0, t1;
+      upk2(q, q0, q1);
+      upk2(t, t0, t1);
+      p0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(t0) << 23));
+      p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(t1) << 23));
+    } else {
+      p0 = ex2(x0);
+      p1 = ex2(x1);
+    }
     bsum2 = add2(bsum2, pk2(p0, p1));
     pk[i >> 1] = ptx::pack2t<FMT>(p0, p1);
   }
