@@ -20,7 +20,7 @@ class SamEncoderShape(C.Structure):
     """Mirror of `struct SamEncoderShape` (include/anyref_sam.h)."""
     _fields_ = [("embed_dim", c_int), ("depth", c_int), ("heads", c_int), ("mlp_dim", c_int), ("img", c_int),
                 ("patch", c_int), ("window", c_int), ("out_chans", c_int), ("fmt", c_int),
-                ("global_mask", C.c_ulonglong), ("tap_block", c_int), ("tap_out", c_void_p)]
+                ("global_mask", C.c_ulonglong), ("tap_block", c_int), ("tap_out", c_void_p), ("ln_fold", c_int)]
 
 
 class SamDecoderShape(C.Structure):
@@ -37,6 +37,11 @@ _PROTOS = {
     "sam_abi_version": [],
     "sam_gemm": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p,
                  c_int, c_void_p, c_int, c_int, c_void_p],
+    "sam_gemm_residual_ln": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p,
+                             c_void_p, c_int, c_void_p, c_void_p],
+    "sam_cast_stats": [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p],
+    "sam_gemm_ln": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p,
+                    c_void_p, c_void_p, c_int, c_float, c_int, c_void_p],
     "sam_umma_probe": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                        c_void_p],
     "sam_layernorm": [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_int, c_int,

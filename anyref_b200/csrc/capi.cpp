@@ -9,7 +9,7 @@ static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
 extern "C" {
 
 const char* sam_last_error(void) { return samhost::last_error(); }
-int sam_abi_version(void) { return 1; }
+int sam_abi_version(void) { return 2; }
 
 int sam_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, int K, int fmt, void* out, int ldo,
              int out_fmt, const float* bias, int act, const float* res, int ldr, int res_mod, void* stream) {
@@ -23,6 +23,33 @@ int sam_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, int K
   ep.ldr = ldr;
   ep.res_mod = res_mod;
   return samk_gemm(A, lda, W, ldw, M, N, K, fmt, ep, S(stream));
+}
+
+int sam_gemm_residual_ln(const void* A, int lda, const void* W, int ldw, int M, int N, int K, int fmt, float* x, int ldx,
+                         const float* bias, void* xb, int ldxb, void* stats, void* stream) {
+  if (!A || !W || !x || !xb || !stats) return samhost::set_error(1, "sam_gemm_residual_ln: NULL argument");
+  GemmEpilogue ep{x, ldx, SAM_F32, bias, 0, x, ldx, M};
+  ep.xb = xb;
+  ep.ldxb = ldxb;
+  ep.stats_out = stats;
+  return samk_gemm(A, lda, W, ldw, M, N, K, fmt, ep, S(stream));
+}
+int sam_cast_stats(const float* x, int ldx, void* xb, int ldxb, int fmt, void* stats, int M, int C, void* stream) {
+  if (!x || !xb || !stats) return samhost::set_error(1, "sam_cast_stats: NULL argument");
+  return samk_cast_stats(x, ldx, xb, ldxb, fmt, stats, M, C, S(stream));
+}
+int sam_gemm_ln(const void* xb, int lda, const void* Wg, int ldw, int M, int N, int K, int fmt, void* out, int ldo,
+                int out_fmt, const float* bias_fold, const float* colsum, const void* stats, int parts, float eps,
+                int act, void* stream) {
+  if (!xb || !Wg || !out || !bias_fold || !colsum || !stats) return samhost::set_error(1, "sam_gemm_ln: NULL argument");
+  if (out_fmt != 0 && out_fmt != 1) return samhost::set_error(1, "sam_gemm_ln: output must be fp16/bf16");
+  GemmEpilogue ep{out, ldo, out_fmt, bias_fold, act, nullptr, 0, 0};
+  ep.ln_stats = stats;
+  ep.ln_parts = parts;
+  ep.ln_colsum = colsum;
+  ep.ln_c = K;
+  ep.ln_eps = eps;
+  return samk_gemm(xb, lda, Wg, ldw, M, N, K, fmt, ep, S(stream));
 }
 
 int sam_umma_probe(const void* A, const void* B, float* D, int N, int K, int fmt, int a_mode, int b_mode, int a_lbo,

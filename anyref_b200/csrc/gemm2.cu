@@ -10,6 +10,13 @@
 // OOB-clipped, no LSU store traffic); the in-place fp32 residual add  x += A.W^T + b  (image_encoder.py:190-191) is a
 // TMA reduce-add (cp.reduce.async.bulk.tensor ... .add), so the residual stream is never loaded by the SM.
 // Two TMEM accumulator stages (2 x 256 columns) let the epilogue of tile i overlap the main loop of tile i+1.
+//
+// LayerNorm folding (LNF).  The encoder's norm1 / norm2 (image_encoder.py:178, :191) never run as kernels of their own:
+//   * producer  (OUT_FMT = fp32, LNF): the residual GEMMs (proj, lin2) load the x tile with TMA, add, store the new
+//     fp32 x with TMA, store a 16-bit copy xb = round(x) for the next GEMM and write per-row partial sums
+//     (sum, sum of squares over each 128-column slice) -- x is read once and never again by a LayerNorm pass;
+//   * consumer  (OUT_FMT = 16-bit, LNF): qkv / lin1 multiply xb by W' = gamma o W and finish the normalisation in
+//     the epilogue:  LN(x).W^T + b = rstd * (xb.W'^T - mean * colsum(W')) + (beta.W^T + b).
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -30,6 +37,7 @@ constexpr int kEpiWarps = 8;
 constexpr int kStagingPerWarp = 2 * 4096;       // double-buffered 32 x 128 B boxes
 constexpr int kThreads2 = 64 + kEpiWarps * 32;
 constexpr int kSmem2 = kStages2 * kStage2 + kEpiWarps * kStagingPerWarp + 1024 /*align*/ + 256 /*barriers*/;
+static_assert((2 * kStages2 + 4 + 2 * kEpiWarps) * 8 + 4 <= 256, "barrier block overflows its 256 bytes");
 constexpr uint32_t kTmemCols2 = 512;
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -96,6 +104,11 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const vo
                "r"(ptx::smem_u32(src)), "r"(c0), "r"(c1)
                : "memory");
 }
+__device__ __forceinline__ float4 ld_shared_v4f(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() {
@@ -153,11 +166,22 @@ struct Gemm2Params {
   int out_fmt;     // SamFmt of the output
   int M, N, K;
   uint32_t idesc;
+  // LayerNorm folding, consumer side: per-row partial (sum, sumsq) [M, ln_parts], colsum(W') [N]
+  const float2* ln_stats;
+  int ln_parts;
+  const float* ln_colsum;
+  float ln_inv_c, ln_eps;
+  // LayerNorm folding, producer side: 16-bit copy of the new residual rows and their partial sums [M, N / 128]
+  void* xb;
+  int ldxb, xb_fmt;
+  float2* stats_out;
+  const float* xres;   // == the fp32 output (in-place residual), row stride ldx
+  int ldx;
 };
 
 // OUT_FMT: SamFmt of the output (0 fp16, 1 bf16, 2 fp32);  ACT: 0 none, 1 GELU  (compile-time so the epilogue carries
 // exactly one conversion / activation path)
-template <int OUT_FMT, int ACT>
+template <int OUT_FMT, int ACT, int LNF>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmC, const Gemm2Params p) {
@@ -168,7 +192,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint64_t* empty_bar = full_bar + kStages2;
   uint64_t* acc_full = empty_bar + kStages2;
   uint64_t* acc_empty = acc_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* ld_bar = acc_empty + 2;                       // LNF producer: x-tile loads, 2 per epilogue warp
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ld_bar + 2 * kEpiWarps);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -193,6 +218,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       ptx::mbar_init(&acc_full[s], 1);                  // multicast tcgen05.commit
       ptx::mbar_init(&acc_empty[s], 2 * kEpiWarps);     // epilogue warps of BOTH CTAs (used in the leader only)
     }
+    for (int s = 0; s < 2 * kEpiWarps; ++s) ptx::mbar_init(&ld_bar[s], 1);
     ptx::fence_mbar_init();
   }
   cluster_sync();   // barriers of both CTAs initialised before anyone touches a remote one
@@ -260,11 +286,134 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     int buf = 0;
     int as = 0;
     uint32_t aph = 0;
+    if constexpr (OUT_FMT == 2 && LNF == 1) {
+      // ---------------- LNF producer:  x <- x + A.W^T + b ;  xb <- round(x) ;  partial row sums of the new x.
+      // The x chunk of the NEXT step is loaded with plain vector loads one chunk ahead (it does not depend on the
+      // accumulator; x loads through the TMA queue would sit in front of the main loop's operand loads and stall
+      // them on their HBM misses); the new x leaves through the staging buffers as TMA stores.
+      const int my_tiles = (num_tiles - cluster_id + num_clusters - 1) / num_clusters;
+      const int total_q = 4 * my_tiles;
+      auto chunk_xy = [&](int q, int& col0, int& row0) {
+        const int tile = cluster_id + (q >> 2) * num_clusters;
+        const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+        row0 = m_blk * (2 * BM2) + static_cast<int>(rank) * BM2 + quad * 32;
+        col0 = n_blk * BN2 + half * 128 + (q & 3) * 32;
+      };
+      // coalesced: instruction i of lane l fetches 16 B piece (l & 7) of row 4 i + (l >> 3)  (4 full lines each)
+      auto load_x = [&](int q, float4 (&dst)[8]) {
+        int c0, r0;
+        chunk_xy(q, c0, r0);
+        if (r0 < p.M && c0 < p.N) {
+          const float* src = p.xres + static_cast<size_t>(r0 + (lane >> 3)) * p.ldx + c0 + (lane & 7) * 4;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) dst[i] = *reinterpret_cast<const float4*>(src + static_cast<size_t>(4 * i) * p.ldx);
+        }
+      };
+      float4 xn[8];
+      load_x(0, xn);
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+      for (int q = 0; q < total_q; ++q) {
+        const int c = q & 3;
+        int col0, row0;
+        chunk_xy(q, col0, row0);
+        const bool valid = row0 < p.M && col0 < p.N;     // warp-uniform (M % 32 == 0, N % 32 == 0)
+        const uint32_t sbuf = ptx::smem_u32(stg) + buf * 4096;
+        if (valid) {
+          // park the prefetched x chunk in the staging buffer (coalesced layout in, own row out later) so that
+          // the registers are free for the next prefetch, which then has a whole chunk period to arrive
+          if (lane == 0) bulk_wait_read<1>();
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = 4 * i + (lane >> 3);
+            ptx::st_shared_v4f(sbuf + r * 128 + (((lane & 7) ^ (r & 7)) << 4), xn[i]);
+          }
+        }
+        if (q + 1 < total_q) load_x(q + 1, xn);
+        if (c == 0) {
+          ptx::mbar_wait(&acc_full[as], aph);
+          ptx::tc_fence_after();
+          s1 = 0.f;
+          s2 = 0.f;
+        }
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * BN2 + half * 128);
+        uint32_t v[32];
+        ptx::tmem_ld_32x32b_x32(t_row + c * 32, v);
+        ptx::tmem_ld_wait();
+        if (c == 3) {
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(&acc_empty[as], 0);
+        }
+        if (valid) {
+          __syncwarp();
+          const uint32_t sb = sbuf + lane * 128;
+          float4 xr[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) xr[i] = ld_shared_v4f(sb + ((i ^ (lane & 7)) << 4));
+          const int row = row0 + lane;
+          uint16_t* xb_row = static_cast<uint16_t*>(p.xb) + static_cast<size_t>(row) * p.ldxb + col0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float4 x4 = xr[i];
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + i);
+            x4.x += __uint_as_float(v[4 * i + 0]) + b4.x;
+            x4.y += __uint_as_float(v[4 * i + 1]) + b4.y;
+            x4.z += __uint_as_float(v[4 * i + 2]) + b4.z;
+            x4.w += __uint_as_float(v[4 * i + 3]) + b4.w;
+            s1 += (x4.x + x4.y) + (x4.z + x4.w);
+            s2 = fmaf(x4.x, x4.x, s2); s2 = fmaf(x4.y, x4.y, s2); s2 = fmaf(x4.z, x4.z, s2); s2 = fmaf(x4.w, x4.w, s2);
+            ptx::st_shared_v4f(sb + ((i ^ (lane & 7)) << 4), x4);
+            xr[i] = x4;
+          }
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmC, stg + buf * 4096, col0, row0);
+            bulk_commit();
+          }
+          buf ^= 1;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 u;
+            u.x = ptx::pack2(xr[2 * i].x, xr[2 * i].y, p.xb_fmt);
+            u.y = ptx::pack2(xr[2 * i].z, xr[2 * i].w, p.xb_fmt);
+            u.z = ptx::pack2(xr[2 * i + 1].x, xr[2 * i + 1].y, p.xb_fmt);
+            u.w = ptx::pack2(xr[2 * i + 1].z, xr[2 * i + 1].w, p.xb_fmt);
+            reinterpret_cast<uint4*>(xb_row)[i] = u;
+          }
+          if (c == 3) {
+            const int tile = cluster_id + (q >> 2) * num_clusters;
+            const int part = (tile % n_tiles) * 2 + half;
+            p.stats_out[static_cast<size_t>(row) * (p.N >> 7) + part] = make_float2(s1, s2);
+          }
+        }
+        if (c == 3 && ++as == 2) { as = 0; aph ^= 1; }
+      }
+    } else
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      const int row0 = m_blk * (2 * BM2) + static_cast<int>(rank) * BM2 + quad * 32;
+      float ln_mu = 0.f, ln_r = 0.f;
+      if constexpr (LNF == 1) {
+        // LNF consumer: finish the row statistics of this thread's row while the main loop of the tile runs
+        const int row = row0 + lane;
+        if (row < p.M) {
+          const float2* st = p.ln_stats + static_cast<size_t>(row) * p.ln_parts;
+          float s1 = 0.f, s2 = 0.f;
+          for (int i = 0; i < p.ln_parts; ++i) {
+            const float2 t = __ldg(st + i);
+            s1 += t.x;
+            s2 += t.y;
+          }
+          ln_mu = s1 * p.ln_inv_c;
+          ln_r = rsqrtf(fmaxf(fmaf(-ln_mu, ln_mu, s2 * p.ln_inv_c), 0.f) + p.ln_eps);
+        }
+      }
       ptx::mbar_wait(&acc_full[as], aph);
       ptx::tc_fence_after();
-      const int row0 = m_blk * (2 * BM2) + static_cast<int>(rank) * BM2 + quad * 32;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * BN2 + half * 128);
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
@@ -285,7 +434,25 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         float f[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-        if (p.bias && valid) {
+        if (LNF == 1) {
+          // rstd * (acc - mean * colsum(W')) + (beta.W^T + b)
+          if (valid) {
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+            const float4* c4 = reinterpret_cast<const float4*>(p.ln_colsum + col0);
+            const ptx::f32x2 nmu = ptx::pk2(-ln_mu, -ln_mu), rr = ptx::pk2(ln_r, ln_r);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (col0 + 4 * i < p.N) {
+                const float4 b = __ldg(b4 + i);
+                const float4 cs = __ldg(c4 + i);
+                ptx::upk2(ptx::fma2(rr, ptx::fma2(nmu, ptx::pk2(cs.x, cs.y), ptx::pk2(f[4 * i + 0], f[4 * i + 1])), ptx::pk2(b.x, b.y)),
+                          f[4 * i + 0], f[4 * i + 1]);
+                ptx::upk2(ptx::fma2(rr, ptx::fma2(nmu, ptx::pk2(cs.z, cs.w), ptx::pk2(f[4 * i + 2], f[4 * i + 3])), ptx::pk2(b.z, b.w)),
+                          f[4 * i + 2], f[4 * i + 3]);
+              }
+            }
+          }
+        } else if (p.bias && valid) {
           const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -364,15 +531,27 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 int samk_gemm2(const void* A, int lda, const void* W, int ldw, int M, int N, int K, int fmt, const GemmEpilogue& ep,
                cudaStream_t stream) {
   int out_mode;
+  const bool ln_consumer = ep.ln_stats != nullptr, ln_producer = ep.xb != nullptr;
   if (ep.out_fmt != SAM_F32) {
-    if (ep.res) return -1;
+    if (ep.res || ln_producer) return -1;
     out_mode = 0;
+  } else if (ln_consumer) {
+    return -1;
   } else if (!ep.res) {
+    if (ln_producer) return -1;
     out_mode = 1;
   } else if (ep.res == static_cast<const float*>(ep.out) && ep.res_mod == M && ep.ldr == ep.ldo) {
-    out_mode = 2;
+    out_mode = ln_producer ? 3 : 2;
   } else {
     return -1;
+  }
+  if (ln_consumer) {
+    SAM_REQUIRE(ep.ln_colsum && ep.bias && ep.ln_parts > 0 && ep.ln_c > 0, "gemm (LN-fold consumer): colsum / bias / parts missing");
+  }
+  if (ln_producer) {
+    SAM_REQUIRE(ep.stats_out && N % 128 == 0 && M % 32 == 0 && ep.ldxb % 8 == 0 &&
+                    (reinterpret_cast<uintptr_t>(ep.xb) & 15) == 0 && ep.act == 0,
+                "gemm (LN-fold producer): needs stats_out, N %% 128 == 0, M %% 32 == 0, 16-byte aligned xb rows, no activation");
   }
   if (N % 8 != 0 || M < 1) return -1;
   CUtensorMap tmA, tmB, tmC;
@@ -387,18 +566,20 @@ int samk_gemm2(const void* A, int lda, const void* W, int ldw, int M, int N, int
     rc = samhost::encode_tmap_2d(&tmC, 4, 0, ep.out, (uint64_t)N, (uint64_t)M, (uint64_t)ep.ldo * 4, 32, 32, 3);
   if (rc) return rc;
   typedef void (*KernelFn)(CUtensorMap, CUtensorMap, CUtensorMap, Gemm2Params);
-  static const KernelFn kernels[3][2] = {{gemm2_kernel<0, 0>, gemm2_kernel<0, 1>},
-                                         {gemm2_kernel<1, 0>, gemm2_kernel<1, 1>},
-                                         {gemm2_kernel<2, 0>, gemm2_kernel<2, 1>}};
+  // [out_fmt][act][LNF]; the fp32 kernels have no activation, their LNF variant is the residual producer
+  static const KernelFn kernels[3][2][2] = {{{gemm2_kernel<0, 0, 0>, gemm2_kernel<0, 0, 1>}, {gemm2_kernel<0, 1, 0>, gemm2_kernel<0, 1, 1>}},
+                                            {{gemm2_kernel<1, 0, 0>, gemm2_kernel<1, 0, 1>}, {gemm2_kernel<1, 1, 0>, gemm2_kernel<1, 1, 1>}},
+                                            {{gemm2_kernel<2, 0, 0>, gemm2_kernel<2, 0, 1>}, {gemm2_kernel<2, 1, 0>, gemm2_kernel<2, 0, 1>}}};
   static bool attr_done = false;
   if (!attr_done) {
     for (int a = 0; a < 3; ++a)
       for (int b = 0; b < 2; ++b)
-        SAM_CHECK_CUDA(cudaFuncSetAttribute(kernels[a][b], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2));
+        for (int c = 0; c < 2; ++c)
+          SAM_CHECK_CUDA(cudaFuncSetAttribute(kernels[a][b][c], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2));
     attr_done = true;
   }
   if (ep.act != 0 && ep.act != 1) return -1;
-  const KernelFn kernel = kernels[ep.out_fmt][ep.act];
+  const KernelFn kernel = kernels[ep.out_fmt][ep.act][(ln_consumer || ln_producer) ? 1 : 0];
   Gemm2Params p;
   p.bias = ep.bias;
   p.act = ep.act;
@@ -408,6 +589,17 @@ int samk_gemm2(const void* A, int lda, const void* W, int ldw, int M, int N, int
   p.N = N;
   p.K = K;
   p.idesc = ptx::make_idesc((uint32_t)fmt, 2 * BM2, BN2, 0, 0);
+  p.ln_stats = static_cast<const float2*>(ep.ln_stats);
+  p.ln_parts = ep.ln_parts;
+  p.ln_colsum = ep.ln_colsum;
+  p.ln_inv_c = ep.ln_c > 0 ? 1.0f / static_cast<float>(ep.ln_c) : 0.f;
+  p.ln_eps = ep.ln_eps;
+  p.xb = ep.xb;
+  p.ldxb = ep.ldxb;
+  p.xb_fmt = fmt;
+  p.stats_out = static_cast<float2*>(ep.stats_out);
+  p.xres = static_cast<const float*>(ep.out);
+  p.ldx = ep.ldo;
   const int m_tiles = (M + 2 * BM2 - 1) / (2 * BM2), n_tiles = (N + BN2 - 1) / BN2;
   int clusters = m_tiles * n_tiles;
   // persistent kernel: never launch more CTA pairs than can be co-resident (GPCs with an odd number of free SMs make
@@ -437,7 +629,7 @@ int samk_gemm2(const void* A, int lda, const void* W, int ldw, int M, int N, int
   const double out_b = (ep.out_fmt == 2) ? 4.0 : 2.0;
   samhost::LaunchScope scope(samhost::KC_GEMM, stream, 2.0 * M * N * K,
                              2.0 * (static_cast<double>(M) * K + static_cast<double>(N) * K) + out_b * M * N +
-                                 (ep.res ? 4.0 * M * N : 0.0));
+                                 (ep.res ? 4.0 * M * N : 0.0) + (ln_producer ? 2.0 * M * N : 0.0));
   kernel<<<2 * clusters, kThreads2, kSmem2, stream>>>(tmA, tmB, tmC, p);
   SAM_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -297,7 +297,43 @@ ln_nhwc_to_nchw_kernel(const float* __restrict__ x, const float* __restrict__ ga
   }
 }
 
+// First producer of the LayerNorm-folding chain (gemm2.cu): xb = round(x) in the operand format plus the per-row
+// partial (sum, sum of squares) of every 128-column slice -- what the residual GEMM epilogues emit for all later
+// blocks.  One warp per row; lane l holds columns 128 j + 4 l .. + 3 of slice j.
+__global__ void __launch_bounds__(256)
+cast_stats_kernel(const float* __restrict__ x, int ldx, void* __restrict__ xb, int ldxb, int fmt,
+                  float2* __restrict__ stats, int M, int C) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int parts = C >> 7;
+  for (int row = blockIdx.x * 8 + warp; row < M; row += gridDim.x * 8) {
+    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * ldx);
+    uint2* orow = reinterpret_cast<uint2*>(static_cast<uint16_t*>(xb) + static_cast<size_t>(row) * ldxb);
+    for (int j = 0; j < parts; ++j) {
+      const float4 v = xr[j * 32 + lane];
+      uint2 u;
+      u.x = ptx::pack2(v.x, v.y, fmt);
+      u.y = ptx::pack2(v.z, v.w, fmt);
+      orow[j * 32 + lane] = u;
+      const float s1 = warp_sum((v.x + v.y) + (v.z + v.w));
+      const float s2 = warp_sum(fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w))));
+      if (lane == 0) stats[static_cast<size_t>(row) * parts + j] = make_float2(s1, s2);
+    }
+  }
+}
+
 }  // namespace
+
+int samk_cast_stats(const float* x, int ldx, void* xb, int ldxb, int fmt, void* stats, int M, int C, cudaStream_t stream) {
+  SAM_REQUIRE(C % 128 == 0 && ldx % 4 == 0 && ldxb % 4 == 0 && M > 0, "cast_stats: C=%d must be a multiple of 128", C);
+  SAM_REQUIRE(fmt == 0 || fmt == 1, "cast_stats: output must be fp16/bf16");
+  samhost::LaunchScope scope(samhost::KC_LAYERNORM, stream, 0.0, static_cast<double>(M) * C * 6.0);
+  int grid = (M + 7) / 8;
+  const int cap = samhost::sm_count() * 16;
+  if (grid > cap) grid = cap;
+  cast_stats_kernel<<<grid, 256, 0, stream>>>(x, ldx, xb, ldxb, fmt, static_cast<float2*>(stats), M, C);
+  SAM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
 
 int samk_layernorm_rows(const float* x, int ldx, const float* res, int ldr, const float* gamma, const float* beta,
                         float eps, void* out, int ldo, int out_fmt, int M, int C, int normalize, cudaStream_t stream) {

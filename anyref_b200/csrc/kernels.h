@@ -20,6 +20,20 @@ struct GemmEpilogue {
   const float* res;  // fp32 residual source or null; row used = (row % res_mod); may alias `out` (fp32, in place)
   int ldr;
   int res_mod;
+  // LayerNorm folding (gemm2.cu), all optional (zero = off):
+  //   consumer: A = 16-bit copy of the un-normalised rows, W = gamma o W; the epilogue computes
+  //             rstd * (acc - mean * ln_colsum[n]) + bias[n]  with mean / rstd from the partial sums ln_stats [M, ln_parts]
+  //             ((sum, sum of squares) per slice of the ln_c-wide row); bias must hold beta.W^T + b
+  const void* ln_stats = nullptr;
+  int ln_parts = 0;
+  const float* ln_colsum = nullptr;
+  int ln_c = 0;
+  float ln_eps = 0.f;
+  //   producer (in-place fp32 residual only): also writes xb [M, ldxb] = round(out) in the operand format and the
+  //             partial sums stats_out [M, N / 128] of the new rows
+  void* xb = nullptr;
+  int ldxb = 0;
+  void* stats_out = nullptr;
 };
 
 int samk_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, int K, int fmt, const GemmEpilogue& ep,
@@ -64,6 +78,8 @@ int samk_attn_global3(const void* qkv, const void* rh_rev, const void* rw_rev, v
 //   layernorm_rows : out[row] = LN(x[row] (+ res[row])) * gamma + beta  (normalize == 0: plain dtype cast)
 int samk_layernorm_rows(const float* x, int ldx, const float* res, int ldr, const float* gamma, const float* beta,
                         float eps, void* out, int ldo, int out_fmt, int M, int C, int normalize, cudaStream_t stream);
+//   cast_stats : xb = round(x) (operand format) + per-row partial (sum, sumsq) of every 128-column slice [M, C/128]
+int samk_cast_stats(const float* x, int ldx, void* xb, int ldxb, int fmt, void* stats, int M, int C, cudaStream_t stream);
 int samk_patch_im2col(const void* img, int in_fmt, void* out, int out_fmt, int B, int S, int p, cudaStream_t stream);
 int samk_im2col3x3(const void* in, void* out, int B, int g, int C, cudaStream_t stream);
 int samk_ln_nhwc_to_nchw(const float* x, const float* gamma, const float* beta, float eps, void* out, int out_fmt,

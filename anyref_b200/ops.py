@@ -43,6 +43,51 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, act: str = "none", resi
     return out
 
 
+def cast_stats(x: torch.Tensor, out_dtype):
+    """-> (xb = x.to(out_dtype), stats [M, C/128, 2] fp32 partial (sum, sumsq) per 128-column slice); see sam_cast_stats."""
+    _req_cuda(x)
+    assert x.dim() == 2 and x.dtype == torch.float32 and x.stride(1) == 1
+    M, Cc = x.shape
+    xb = torch.empty((M, Cc), device=x.device, dtype=out_dtype)
+    stats = torch.empty((M, Cc // 128, 2), device=x.device, dtype=torch.float32)
+    rc = _lib.load().sam_cast_stats(ptr(x), x.stride(0), ptr(xb), xb.stride(0), fmt_of(out_dtype), ptr(stats), M, Cc,
+                                    stream_ptr(x.device))
+    check(rc, "sam_cast_stats")
+    return xb, stats
+
+
+def gemm_residual_ln(a: torch.Tensor, w: torch.Tensor, x: torch.Tensor, bias=None, *, xb=None, stats=None):
+    """x += a @ w^T + bias in place (fp32); -> (xb = round(x) in a.dtype, stats [M, N/128, 2]); see sam_gemm_residual_ln."""
+    _req_cuda(a, w, x, bias)
+    M, K = a.shape
+    N = w.shape[0]
+    assert x.shape == (M, N) and x.dtype == torch.float32 and x.stride(1) == 1 and a.dtype == w.dtype
+    if xb is None:
+        xb = torch.empty((M, N), device=a.device, dtype=a.dtype)
+    if stats is None:
+        stats = torch.empty((M, N // 128, 2), device=a.device, dtype=torch.float32)
+    rc = _lib.load().sam_gemm_residual_ln(ptr(a), a.stride(0), ptr(w), w.stride(0), M, N, K, fmt_of(a.dtype), ptr(x),
+                                          x.stride(0), ptr(bias), ptr(xb), xb.stride(0), ptr(stats), stream_ptr(a.device))
+    check(rc, "sam_gemm_residual_ln")
+    return xb, stats
+
+
+def gemm_ln(xb: torch.Tensor, wg: torch.Tensor, bias_fold: torch.Tensor, colsum: torch.Tensor, stats: torch.Tensor,
+            eps: float, act: str = "none", out: torch.Tensor | None = None) -> torch.Tensor:
+    """act(LN(x) @ W^T + b) from the folded operands (see sam_gemm_ln / segment_anything/_pack.py::_fold_layernorm)."""
+    _req_cuda(xb, wg, bias_fold, colsum, stats)
+    M, K = xb.shape
+    N = wg.shape[0]
+    assert stats.dtype == torch.float32 and stats.is_contiguous() and stats.shape[0] == M and stats.shape[2] == 2
+    if out is None:
+        out = torch.empty((M, N), device=xb.device, dtype=xb.dtype)
+    rc = _lib.load().sam_gemm_ln(ptr(xb), xb.stride(0), ptr(wg), wg.stride(0), M, N, K, fmt_of(xb.dtype), ptr(out),
+                                 out.stride(0), fmt_of(out.dtype), ptr(bias_fold), ptr(colsum), ptr(stats),
+                                 stats.shape[1], float(eps), {"none": 0, "gelu": 1}[act], stream_ptr(xb.device))
+    check(rc, "sam_gemm_ln")
+    return out
+
+
 def umma_probe(a: torch.Tensor, b: torch.Tensor, N: int, K: int, a_mode: int, b_mode: int, a_lbo=-1, a_sbo=-1,
                b_lbo=-1, b_sbo=-1) -> torch.Tensor:
     _req_cuda(a, b)

@@ -34,7 +34,7 @@ class _Blob:
         self.off += flat.numel()
 
 
-def encoder_shape(enc, op_dtype) -> _lib.SamEncoderShape:
+def encoder_shape(enc, op_dtype, ln_fold: bool = False) -> _lib.SamEncoderShape:
     gmask = 0
     for i, blk in enumerate(enc.blocks):
         if blk.window_size == 0:
@@ -42,13 +42,24 @@ def encoder_shape(enc, op_dtype) -> _lib.SamEncoderShape:
     return _lib.SamEncoderShape(embed_dim=enc.embed_dim, depth=len(enc.blocks), heads=enc.num_heads,
                                 mlp_dim=enc.blocks[0].mlp.lin1.out_features, img=enc.img_size, patch=enc.patch_size,
                                 window=enc.window_size, out_chans=enc.out_chans, fmt=_lib.fmt_of(op_dtype),
-                                global_mask=gmask, tap_block=-1, tap_out=None)
+                                global_mask=gmask, tap_block=-1, tap_out=None, ln_fold=1 if ln_fold else 0)
 
 
-def pack_encoder(enc, op_dtype):
-    """-> (shape, w16 blob, w32 blob)."""
+def _fold_layernorm(norm, lin, op_dtype):
+    """LayerNorm folded into the Linear that follows it (csrc/gemm2.cu, "LayerNorm folding"):
+        LN(x) . W^T + b  =  rstd * (x . Wg^T - mean * colsum) + bias_fold
+    -> (Wg = gamma o W in the operand format, colsum = row sums of the ROUNDED Wg, bias_fold = beta . W^T + b)."""
+    w = lin.weight.detach().double()
+    wg = (w * norm.weight.detach().double()[None, :]).float().to(op_dtype)
+    colsum = wg.double().sum(dim=1).float()
+    bias_fold = (w @ norm.bias.detach().double() + lin.bias.detach().double()).float()
+    return wg, colsum, bias_fold
+
+
+def pack_encoder(enc, op_dtype, ln_fold: bool = False):
+    """-> (shape, w16 blob, w32 blob).  ln_fold selects the folded-LayerNorm blob layout (csrc/encoder.cpp)."""
     lib = _lib.load()
-    shape = encoder_shape(enc, op_dtype)
+    shape = encoder_shape(enc, op_dtype, ln_fold)
     dev = enc.pos_embed.device
     n16 = lib.sam_encoder_w16_elems(C.byref(shape))
     n32 = lib.sam_encoder_w32_elems(C.byref(shape))
@@ -61,9 +72,15 @@ def pack_encoder(enc, op_dtype):
     b32.put(enc.patch_embed.proj.bias.float())
     for blk in enc.blocks:
         a = blk.attn
-        b16.put(a.qkv.weight.to(op_dtype))
+        if ln_fold:
+            qkv_w, qkv_cs, qkv_fb = _fold_layernorm(blk.norm1, a.qkv, op_dtype)
+            lin1_w, lin1_cs, lin1_fb = _fold_layernorm(blk.norm2, blk.mlp.lin1, op_dtype)
+        else:
+            qkv_w, qkv_fb = a.qkv.weight.to(op_dtype), a.qkv.bias.float()
+            lin1_w, lin1_fb = blk.mlp.lin1.weight.to(op_dtype), blk.mlp.lin1.bias.float()
+        b16.put(qkv_w)
         b16.put(a.proj.weight.to(op_dtype))
-        b16.put(blk.mlp.lin1.weight.to(op_dtype))
+        b16.put(lin1_w)
         b16.put(blk.mlp.lin2.weight.to(op_dtype))
         b16.put(a.qkv.bias.to(op_dtype))
         s = g if blk.window_size == 0 else blk.window_size
@@ -83,11 +100,14 @@ def pack_encoder(enc, op_dtype):
             rel[32 * hd:59 * hd] = a.rel_pos_w.detach().to(op_dtype).reshape(-1)
         b16.put(rel)
         b32.put(blk.norm1.weight.float()); b32.put(blk.norm1.bias.float())
-        b32.put(a.qkv.bias.float())
+        b32.put(qkv_fb)
         b32.put(a.proj.bias.float())
         b32.put(blk.norm2.weight.float()); b32.put(blk.norm2.bias.float())
-        b32.put(blk.mlp.lin1.bias.float())
+        b32.put(lin1_fb)
         b32.put(blk.mlp.lin2.bias.float())
+        if ln_fold:
+            b32.put(qkv_cs)
+            b32.put(lin1_cs)
     Cc = enc.out_chans
     b16.put(enc.neck[0].weight.reshape(Cc, E).to(op_dtype))
     b16.put(enc.neck[2].weight.permute(0, 2, 3, 1).reshape(Cc, 9 * Cc).to(op_dtype))

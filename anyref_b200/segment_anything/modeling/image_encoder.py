@@ -112,6 +112,7 @@ class ImageEncoderViT(nn.Module):
         )
         self._packed = None          # (signature, op_dtype, shape, w16, w32)
         self._operand_dtype = None   # explicit override (set_operand_dtype)
+        self._ln_fold = None         # explicit override (set_ln_fold)
 
     # ------------------------------------------------------------------------------------------------ configuration
     def set_operand_dtype(self, dtype) -> None:
@@ -121,6 +122,20 @@ class ImageEncoderViT(nn.Module):
         if dtype not in (None, torch.float16, torch.bfloat16):
             raise ValueError("operand dtype must be torch.float16 or torch.bfloat16")
         self._operand_dtype = dtype
+
+    def set_ln_fold(self, on) -> None:
+        """norm1 / norm2 folded into the GEMMs around them (5 kernels per block instead of 7; csrc/gemm2.cu).
+        Default (None): on when embed_dim is a multiple of 256 (ViT-H / L / B) unless $ANYREF_SAM_LN_FOLD=0."""
+        if on not in (None, True, False):
+            raise ValueError("ln_fold must be None, True or False")
+        if on and self.embed_dim % 256 != 0:
+            raise ValueError("ln_fold needs embed_dim % 256 == 0")
+        self._ln_fold = on
+
+    def _resolve_ln_fold(self) -> bool:
+        if self._ln_fold is not None:
+            return bool(self._ln_fold)
+        return self.embed_dim % 256 == 0 and os.environ.get("ANYREF_SAM_LN_FOLD", "1") != "0"
 
     def _resolve_operand_dtype(self, x: torch.Tensor):
         if self._operand_dtype is not None:
@@ -134,9 +149,10 @@ class ImageEncoderViT(nn.Module):
         return torch.float16 if env in ("fp16", "float16", "half") else torch.bfloat16
 
     def _weights(self, op_dtype):
-        sig = (_runtime.params_signature(self), op_dtype)
+        fold = self._resolve_ln_fold()
+        sig = (_runtime.params_signature(self), op_dtype, fold)
         if self._packed is None or self._packed[0] != sig:
-            shape, w16, w32 = _pack.pack_encoder(self, op_dtype)
+            shape, w16, w32 = _pack.pack_encoder(self, op_dtype, fold)
             self._packed = (sig, shape, w16, w32)
         return self._packed[1:]
 

@@ -57,6 +57,8 @@ CONFIGS = {
     "vit_tiny80": SamConfig(embed_dim=160, depth=2, num_heads=2, global_attn_indexes=(1,)),
     # same with ViT-L / ViT-B's head_dim (64)
     "vit_tiny64": SamConfig(embed_dim=128, depth=2, num_heads=2, global_attn_indexes=(1,)),
+    # smallest width the folded-LayerNorm GEMMs accept (embed_dim % 256 == 0), head_dim 64
+    "vit_tiny256": SamConfig(embed_dim=256, depth=2, num_heads=4, global_attn_indexes=(1,)),
 }
 
 

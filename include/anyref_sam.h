@@ -38,6 +38,8 @@ typedef struct SamEncoderShape {
   unsigned long long global_mask; /* bit i set <=> block i uses global attention (global_attn_indexes) */
   int tap_block;          /* test hook: copy the fp32 residual stream after this block to tap_out (-1 = off) */
   float* tap_out;         /* device [B*64*64, embed_dim] fp32 or NULL */
+  int ln_fold;            /* 1: norm1 / norm2 folded into the neighbouring GEMMs (needs embed_dim % 256 == 0 and the
+                             folded weight-blob layout, csrc/encoder.cpp); 0: LayerNorm kernels */
 } SamEncoderShape;
 
 /* Shape of the mask decoder (mask_decoder.py:17-73, transformer.py:16-60). */
@@ -85,6 +87,26 @@ int sam_umma_probe(const void* A, const void* B, float* D, int N, int K, int fmt
  */
 int sam_layernorm(const float* x, int ldx, const float* res, int ldr, const float* gamma, const float* beta, float eps,
                   void* out, int ldo, int out_fmt, int M, int C, int normalize, void* stream);
+
+/*
+ * LayerNorm folded into the GEMMs on either side of it (Block.forward, image_encoder.py:177-193: norm1 -> attn.qkv,
+ * norm2 -> mlp.lin1, eps 1e-6), so that x is never re-read by a normalisation pass:
+ *
+ *   sam_gemm_residual_ln  x[M,N] += A[M,K].W[N,K]^T + bias  in place (fp32; image_encoder.py:190, :192), and in the
+ *                         same epilogue  xb[M,ldxb] = round(x) in format `fmt`  and  stats[M, N/128] (float2) = the
+ *                         (sum, sum of squares) of every 128-column slice of the new row.  N % 128 == 0, M % 32 == 0.
+ *   sam_cast_stats        the same xb / stats from an existing fp32 x [M, C] (first block).  C % 128 == 0.
+ *   sam_gemm_ln           out[M,N] = act( rstd_r * (xb[M,K].Wg[N,K]^T - mean_r * colsum[n]) + bias_fold[n] )  with
+ *                         Wg = gamma o W rounded to `fmt`, colsum[n] = sum_k Wg[n,k], bias_fold = beta.W^T + b,
+ *                         mean_r / rstd_r from stats[M, parts] over the K-wide row  ==  act(LN(x).W^T + b).
+ *                         out_fmt 0/1; act 0 none, 1 exact-erf GELU.
+ */
+int sam_gemm_residual_ln(const void* A, int lda, const void* W, int ldw, int M, int N, int K, int fmt, float* x, int ldx,
+                         const float* bias, void* xb, int ldxb, void* stats, void* stream);
+int sam_cast_stats(const float* x, int ldx, void* xb, int ldxb, int fmt, void* stats, int M, int C, void* stream);
+int sam_gemm_ln(const void* xb, int lda, const void* Wg, int ldw, int M, int N, int K, int fmt, void* out, int ldo,
+                int out_fmt, const float* bias_fold, const float* colsum, const void* stats, int parts, float eps,
+                int act, void* stream);
 
 /*
  * PatchEmbed im2col (image_encoder.py:418-426): img [B,3,S,S] (fmt in_fmt) -> out [B*(S/p)^2, 3*p*p] (fmt out_fmt),

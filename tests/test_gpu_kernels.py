@@ -51,6 +51,70 @@ def test_gemm_epilogues(ops, dt, tol, M, N, K):
     assert rel_fro(got, ref + bias + pos[torch.arange(M, device=DEV) % 128]) < 1e-5
 
 
+# ------------------------------------------------------------------------------------------ LayerNorm folding
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+def test_cast_stats(ops, dt):
+    torch.manual_seed(3)
+    x = torch.randn(4096 + 24, 1280, device=DEV) * 2 + 0.3
+    xb, stats = ops.cast_stats(x, dt)
+    assert torch.equal(xb, x.to(dt))                                           # rounding is bit-exact
+    xs = x.double().view(x.shape[0], 10, 128)
+    assert (stats[..., 0].double() - xs.sum(-1)).abs().max().item() < 1e-3
+    assert ((stats[..., 1].double() - (xs * xs).sum(-1)).abs() / (xs * xs).sum(-1)).max().item() < 1e-5
+
+
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("M,N,K", [(4096, 1280, 1280), (8192, 1280, 5120), (2048 + 32, 256, 256), (65536, 1280, 1280)])
+def test_gemm_residual_ln_producer(ops, dt, M, N, K):
+    """x += a.W^T + b in place; xb == round(x) bit-exactly; partial sums of the NEW x (image_encoder.py:190-192)."""
+    torch.manual_seed(M + N + K)
+    a = (torch.randn(M, K, device=DEV) * 0.5).to(dt)
+    w = (torch.randn(N, K, device=DEV) * 0.05).to(dt)
+    bias = torch.randn(N, device=DEV)
+    x0 = torch.randn(M, N, device=DEV) * 2 + 0.1
+    x = x0.clone()
+    xb, stats = ops.gemm_residual_ln(a, w, x, bias)
+    ref = a.float() @ w.float().t() + bias + x0
+    assert rel_fro(x, ref) < 1e-5
+    assert torch.equal(xb, x.to(dt))
+    xs = x.double().view(M, N // 128, 128)
+    assert (stats[..., 0].double() - xs.sum(-1)).abs().max().item() < 2e-3
+    assert ((stats[..., 1].double() - (xs * xs).sum(-1)).abs() / (xs * xs).sum(-1)).max().item() < 1e-5
+    # same numbers as the plain in-place residual epilogue (TMA reduce-add) up to the last fp32 bit
+    y = x0.clone()
+    ops.gemm(a, w, bias=bias, residual=y, out=y)
+    assert rel_fro(x, y) < 1e-6
+
+
+@pytest.mark.parametrize("dt,tol", [(torch.float16, 2e-3), (torch.bfloat16, 1e-2)])
+@pytest.mark.parametrize("M,N,K,act", [(4096, 3840, 1280, "none"), (4096, 5120, 1280, "gelu"), (1024 + 32, 768, 256, "none")])
+def test_gemm_ln_consumer_matches_layernorm_then_linear(ops, dt, tol, M, N, K, act):
+    """act(LN(x).W^T + b) (image_encoder.py:178-179 -> :238, :191 -> common.py:26) from the folded operands."""
+    import types
+
+    from anyref_b200.segment_anything._pack import _fold_layernorm
+
+    torch.manual_seed(M + N)
+    x = torch.randn(M, K, device=DEV) * 2 + 0.2 * torch.randn(M, 1, device=DEV)
+    gamma = torch.rand(K, device=DEV) * 0.2 + 0.9
+    beta = torch.rand(K, device=DEV) * 0.2 - 0.1
+    W = (torch.rand(N, K, device=DEV) * 2 - 1) / K ** 0.5
+    b = (torch.rand(N, device=DEV) * 2 - 1) / K ** 0.5
+    norm = types.SimpleNamespace(weight=gamma, bias=beta)
+    lin = types.SimpleNamespace(weight=W, bias=b)
+    wg, colsum, bias_fold = _fold_layernorm(norm, lin, dt)
+    xb, stats = ops.cast_stats(x, dt)
+    got = ops.gemm_ln(xb, wg, bias_fold, colsum, stats, 1e-6, act=act)
+    want = F.layer_norm(x.double(), (K,), gamma.double(), beta.double(), 1e-6) @ W.double().t() + b.double()
+    if act == "gelu":
+        want = F.gelu(want)
+    assert rel_fro(got, want.float()) < tol
+    # and it is as accurate as the unfused pair LayerNorm kernel -> GEMM
+    a16 = ops.layernorm(x, gamma, beta, 1e-6, dt)
+    plain = ops.gemm(a16, W.to(dt), bias=b, act=act, out_dtype=dt)
+    assert rel_fro(got, want.float()) < 1.5 * rel_fro(plain, want.float()) + 1e-4
+
+
 def test_gemm_rejects_bad_arguments(ops):
     a = torch.zeros(64, 60, device=DEV, dtype=torch.bfloat16)
     w = torch.zeros(64, 60, device=DEV, dtype=torch.bfloat16)

@@ -171,9 +171,10 @@ def test_parameter_updates_are_picked_up(tiny):
     assert torch.equal(sam.image_encoder(x), a)     # deterministic + restored
 
 
+@pytest.mark.parametrize("ln_fold", [True, False])
 @pytest.mark.parametrize("dt,emb_tol,low_tol,iou_min", [(torch.float16, 2e-3, 2e-3, 0.999),
                                                         (torch.bfloat16, 1e-2, 1e-2, 0.995)])
-def test_vit_h_against_reference_goldens(dt, emb_tol, low_tol, iou_min):
+def test_vit_h_against_reference_goldens(dt, emb_tol, low_tol, iou_min, ln_fold):
     """Full-size ViT-H vs tests/golden/vit_h_seed1234_in0.pt (outputs of the UNMODIFIED reference modules)."""
     if not torch.cuda.is_available():
         pytest.skip("needs a CUDA device")
@@ -187,6 +188,7 @@ def test_vit_h_against_reference_goldens(dt, emb_tol, low_tol, iou_min):
     del sd
     sam = sam.cuda()
     sam.image_encoder.set_operand_dtype(dt)
+    sam.image_encoder.set_ln_fold(ln_fold)
     x = synthetic_images(1, seed=g["meta"]["seed_in"]).cuda()
     seg = synthetic_seg_embeddings(1, g["meta"]["n_seg"], seed=g["meta"]["seed_in"])[0].cuda()
     emb = sam.image_encoder(x)
@@ -469,6 +471,40 @@ def test_head_dim_64_encoder_vs_oracle(dt, tol):
         sam.image_encoder(x.cuda(), _tap=(blk, tap))
         assert rel_fro(tap.view(1, 64, 64, -1), taps[f"block{blk}"]) < tol
     assert rel_fro(sam.image_encoder(x.cuda()), want) < tol
+
+
+@pytest.mark.parametrize("dt,tol", [(torch.float16, 2e-3), (torch.bfloat16, 1e-2)])
+def test_folded_layernorm_encoder_vs_oracle(dt, tol):
+    """norm1 / norm2 folded into the GEMMs around them (csrc/gemm2.cu; default for ViT-H / L / B) against the oracle, and
+    against the same encoder with stand-alone LayerNorm kernels: both meet the same tolerance."""
+    from anyref_b200.segment_anything import build_sam_from_config
+
+    cfg = CONFIGS["vit_tiny256"]
+    sd = synthetic_state_dict(cfg)
+    x = synthetic_images(2, seed=5)
+    taps = {}
+    with torch.no_grad():
+        want = O.image_encoder(sd, x, cfg, taps)
+    sam = build_sam_from_config(cfg)
+    sam.load_state_dict(sd, strict=True)
+    sam = sam.cuda()
+    enc = sam.image_encoder
+    enc.set_operand_dtype(dt)
+    assert enc._resolve_ln_fold()                      # default: folded
+    errs = {}
+    for fold in (True, False):
+        enc.set_ln_fold(fold)
+        for blk in (0, 1):
+            tap = torch.empty(2 * 4096, cfg.embed_dim, device="cuda")
+            enc(x.cuda(), _tap=(blk, tap))
+            assert rel_fro(tap.view(2, 64, 64, -1), taps[f"block{blk}"]) < tol
+        got = enc(x.cuda())
+        errs[fold] = rel_fro(got, want)
+        assert errs[fold] < tol
+        assert torch.equal(enc(x.cuda()), got)         # deterministic
+    assert errs[True] < 1.5 * errs[False] + 1e-4
+    with pytest.raises(ValueError):
+        build_sam_from_config(CONFIGS["vit_tiny80"]).image_encoder.set_ln_fold(True)
 
 
 def test_vit_l_and_vit_b_builders_run():

@@ -13,8 +13,9 @@ dt = torch.bfloat16
 which = sys.argv[1]
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 torch.manual_seed(0)
-if which in ("lin1", "proj", "qkv", "lin2"):
-    N, K = {"lin1": (5120, 1280), "proj": (1280, 1280), "qkv": (3840, 1280), "lin2": (1280, 5120)}[which]
+if which in ("lin1", "proj", "qkv", "lin2", "proj_ln", "lin2_ln"):
+    N, K = {"lin1": (5120, 1280), "proj": (1280, 1280), "qkv": (3840, 1280), "lin2": (1280, 5120),
+            "proj_ln": (1280, 1280), "lin2_ln": (1280, 5120)}[which]
     a = (torch.randn(M, K, device=dev) * 0.5).to(dt)
     w = (torch.randn(N, K, device=dev) * 0.05).to(dt)
     bias = torch.randn(N, device=dev)
@@ -24,6 +25,11 @@ if which in ("lin1", "proj", "qkv", "lin2"):
     elif which == "qkv":
         out = torch.empty(M, N, device=dev, dtype=dt)
         fn = lambda: ops.gemm(a, w, bias=bias, out=out)
+    elif which.endswith("_ln"):
+        x = torch.randn(M, N, device=dev)
+        xb = torch.empty(M, N, device=dev, dtype=dt)
+        stats = torch.empty(M, N // 128, 2, device=dev)
+        fn = lambda: ops.gemm_residual_ln(a, w, x, bias, xb=xb, stats=stats)
     else:
         x = torch.randn(M, N, device=dev)
         fn = lambda: ops.gemm(a, w, bias=bias, residual=x, out=x)
