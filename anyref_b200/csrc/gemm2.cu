@@ -177,6 +177,7 @@ struct Gemm2Params {
   float2* stats_out;
   const float* xres;   // == the fp32 output (in-place residual), row stride ldx
   int ldx;
+  int x_tma;           // producer: fetch the x chunks with TMA (short main loops) instead of vector loads
 };
 
 // OUT_FMT: SamFmt of the output (0 fp16, 1 bf16, 2 fp32);  ACT: 0 none, 1 GELU  (compile-time so the epilogue carries
@@ -299,6 +300,96 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         row0 = m_blk * (2 * BM2) + static_cast<int>(rank) * BM2 + quad * 32;
         col0 = n_blk * BN2 + half * 128 + (q & 3) * 32;
       };
+      if (p.x_tma) {
+        // Short main loops (proj, K = E): the x chunks stream through the two staging buffers with TMA loads issued
+        // two chunks ahead (TMA load -> add in place -> TMA store).  With a long main loop (lin2) this variant
+        // loses: the x loads miss to HBM and hold up the operand loads queued behind them in the TMA unit.
+        uint64_t* ldb = ld_bar + 2 * ew;
+        if (lane == 0) {
+          for (int q = 0; q < 2 && q < total_q; ++q) {
+            int c0, r0;
+            chunk_xy(q, c0, r0);
+            ptx::mbar_expect_tx(&ldb[q], 4096);
+            ptx::tma_load_2d(stg + q * 4096, &tmC, &ldb[q], c0, r0);
+          }
+        }
+        uint32_t lph = 0;
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+        for (int q = 0; q < total_q; ++q) {
+          const int c = q & 3, b = q & 1;
+          int col0, row0;
+          chunk_xy(q, col0, row0);
+          if (c == 0) {
+            ptx::mbar_wait(&acc_full[as], aph);
+            ptx::tc_fence_after();
+            s1 = 0.f;
+            s2 = 0.f;
+          }
+          const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * BN2 + half * 128);
+          uint32_t v[32];
+          ptx::tmem_ld_32x32b_x32(t_row + c * 32, v);
+          ptx::tmem_ld_wait();
+          if (c == 3) {
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(&acc_empty[as], 0);
+          }
+          ptx::mbar_wait(&ldb[b], (lph >> b) & 1u);
+          lph ^= 1u << b;
+          const bool valid = row0 < p.M && col0 < p.N;     // warp-uniform (M % 32 == 0, N % 32 == 0)
+          const uint32_t sb = ptx::smem_u32(stg) + b * 4096 + lane * 128;
+          const int row = row0 + lane;
+          uint16_t* xb_row = static_cast<uint16_t*>(p.xb) + static_cast<size_t>(row) * p.ldxb + col0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint32_t sa = sb + ((i ^ (lane & 7)) << 4);
+            float4 x4 = ld_shared_v4f(sa);
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias && valid) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + i);
+            x4.x += __uint_as_float(v[4 * i + 0]) + b4.x;
+            x4.y += __uint_as_float(v[4 * i + 1]) + b4.y;
+            x4.z += __uint_as_float(v[4 * i + 2]) + b4.z;
+            x4.w += __uint_as_float(v[4 * i + 3]) + b4.w;
+            s1 += (x4.x + x4.y) + (x4.z + x4.w);
+            s2 = fmaf(x4.x, x4.x, s2); s2 = fmaf(x4.y, x4.y, s2); s2 = fmaf(x4.z, x4.z, s2); s2 = fmaf(x4.w, x4.w, s2);
+            ptx::st_shared_v4f(sa, x4);
+            v[4 * i + 0] = __float_as_uint(x4.x); v[4 * i + 1] = __float_as_uint(x4.y);
+            v[4 * i + 2] = __float_as_uint(x4.z); v[4 * i + 3] = __float_as_uint(x4.w);
+          }
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && valid) {
+            tma_store_2d(&tmC, stg + b * 4096, col0, row0);
+            bulk_commit();
+          }
+          if (valid) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint4 u;
+              u.x = ptx::pack2(__uint_as_float(v[8 * i + 0]), __uint_as_float(v[8 * i + 1]), p.xb_fmt);
+              u.y = ptx::pack2(__uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3]), p.xb_fmt);
+              u.z = ptx::pack2(__uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5]), p.xb_fmt);
+              u.w = ptx::pack2(__uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7]), p.xb_fmt);
+              reinterpret_cast<uint4*>(xb_row)[i] = u;
+            }
+            if (c == 3) {
+              const int tile = cluster_id + (q >> 2) * num_clusters;
+              const int part = (tile % n_tiles) * 2 + half;
+              p.stats_out[static_cast<size_t>(row) * (p.N >> 7) + part] = make_float2(s1, s2);
+            }
+          }
+          if (c == 3 && ++as == 2) { as = 0; aph ^= 1; }
+          if (lane == 0 && q + 2 < total_q) {
+            bulk_wait_read<0>();              // the store of this chunk has read buffer b
+            int c2, r2;
+            chunk_xy(q + 2, c2, r2);
+            ptx::mbar_expect_tx(&ldb[b], 4096);
+            ptx::tma_load_2d(stg + b * 4096, &tmC, &ldb[b], c2, r2);
+          }
+          __syncwarp();
+        }
+      } else {
       // coalesced: instruction i of lane l fetches 16 B piece (l & 7) of row 4 i + (l >> 3)  (4 full lines each)
       auto load_x = [&](int q, float4 (&dst)[8]) {
         int c0, r0;
@@ -309,11 +400,13 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           for (int i = 0; i < 8; ++i) dst[i] = *reinterpret_cast<const float4*>(src + static_cast<size_t>(4 * i) * p.ldx);
         }
       };
-      float4 xn[8];
-      load_x(0, xn);
+      // two chunks of x in flight per warp (register sets xa / xb, alternating): the prefetch distance covers the
+      // HBM latency under load even when the main loop is short (proj)
+      float4 xa[8], xb2[8];
+      load_x(0, xa);
+      load_x(1, xb2);
       float s1 = 0.f, s2 = 0.f;
-#pragma unroll 1
-      for (int q = 0; q < total_q; ++q) {
+      auto process = [&](const int q, float4 (&xn)[8]) {
         const int c = q & 3;
         int col0, row0;
         chunk_xy(q, col0, row0);
@@ -330,7 +423,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             ptx::st_shared_v4f(sbuf + r * 128 + (((lane & 7) ^ (r & 7)) << 4), xn[i]);
           }
         }
-        if (q + 1 < total_q) load_x(q + 1, xn);
+        if (q + 2 < total_q) load_x(q + 2, xn);
         if (c == 0) {
           ptx::mbar_wait(&acc_full[as], aph);
           ptx::tc_fence_after();
@@ -391,6 +484,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
         }
         if (c == 3 && ++as == 2) { as = 0; aph ^= 1; }
+      };
+#pragma unroll 1
+      for (int q = 0; q < total_q; q += 2) {      // total_q is a multiple of 4
+        process(q, xa);
+        process(q + 1, xb2);
+      }
       }
     } else
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
@@ -600,6 +699,10 @@ int samk_gemm2(const void* A, int lda, const void* W, int ldw, int M, int N, int
   p.stats_out = static_cast<float2*>(ep.stats_out);
   p.xres = static_cast<const float*>(ep.out);
   p.ldx = ep.ldo;
+  {
+    static const char* xl = getenv("SAM_GEMM_XLOAD");   // experiment switch: "tma" | "lsu"
+    p.x_tma = xl ? (xl[0] == 't') : (K <= 2048);
+  }
   const int m_tiles = (M + 2 * BM2 - 1) / (2 * BM2), n_tiles = (N + BN2 - 1) / BN2;
   int clusters = m_tiles * n_tiles;
   // persistent kernel: never launch more CTA pairs than can be co-resident (GPCs with an odd number of free SMs make

@@ -67,6 +67,10 @@ class GroundingPath:
             b = e
         return outs
 
+    def host_pipeline(self, depth: int = 2) -> "HostPipeline":
+        """A double-buffered host-to-host runner over this path (see HostPipeline)."""
+        return HostPipeline(self, depth)
+
     @torch.no_grad()
     def per_image_loop(self, sam_images, seg_embeds, input_sizes, original_sizes, multimask_output: bool = False):
         """The reference's call sequence verbatim (model/anyref.py:793-819), one decoder call per image."""
@@ -81,3 +85,87 @@ class GroundingPath:
                                       multimask_output=multimask_output)
             outs.append(sam.postprocess_masks(low, input_size=input_sizes[b], original_size=original_sizes[b]))
         return outs
+
+
+class HostPipeline:
+    """Streams batches that live in (pinned) HOST memory through a GroundingPath and returns the mask logits to host
+    memory, the way an evaluation loop consumes the path (eval_referseg.py:130-211 moves every batch to the GPU and
+    every prediction back):  the upload of batch i+1 (copy-in stream) and the download of batch i-1 (copy-out
+    stream) overlap the kernels of batch i (the caller's current stream).  Results are bit-identical to calling the
+    path on device tensors; nothing is skipped -- every batch pays its own H2D and D2H.
+
+        pipe = path.host_pipeline()
+        for images, segs, host_out in batches:             # pinned tensors
+            pipe.submit(images, segs, input_sizes, original_sizes, host_out)
+        pipe.drain()                                       # all host_out buffers are complete after this
+    """
+
+    def __init__(self, path: GroundingPath, depth: int = 2):
+        if depth < 1:
+            raise ValueError("depth must be >= 1")
+        self.path = path
+        self.depth = depth
+        self._slots: list = []
+        self._n = 0
+        self._up = None
+        self._down = None
+
+    def _slot(self, dev):
+        if self._up is None:
+            self._up, self._down = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+            self._slots = [{"img": None, "seg": None, "done": None, "down": None} for _ in range(self.depth)]
+        s = self._slots[self._n % self.depth]
+        self._n += 1
+        return s
+
+    @torch.no_grad()
+    def submit(self, host_images: torch.Tensor, host_seg: torch.Tensor, input_sizes, original_sizes,
+               host_out: torch.Tensor, multimask_output: bool = False, device=None) -> None:
+        """host_images [B,3,1024,1024], host_seg [B,n,1,256] (the same number of [SEG] prompts per image), host_out
+        [B*n, C, H, W] fp32 -- all pinned host tensors (pageable ones work but serialise the copies)."""
+        if host_images.is_cuda or host_seg.is_cuda or host_out.is_cuda:
+            raise ValueError("HostPipeline takes host tensors; call the GroundingPath directly for device tensors")
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        main = torch.cuda.current_stream(dev)
+        slot = self._slot(dev)
+        fresh = False
+        if slot["img"] is None or slot["img"].shape != host_images.shape or slot["img"].dtype != host_images.dtype:
+            slot["img"] = torch.empty(host_images.shape, dtype=host_images.dtype, device=dev)
+            fresh = True
+        if slot["seg"] is None or slot["seg"].shape != host_seg.shape or slot["seg"].dtype != host_seg.dtype:
+            slot["seg"] = torch.empty(host_seg.shape, dtype=host_seg.dtype, device=dev)
+            fresh = True
+        if slot["down"] is not None:
+            slot["down"].synchronize()          # bounds how far the host runs ahead of the device
+        if fresh or slot["done"] is None:
+            self._up.wait_stream(main)          # new buffers: ordered after whatever used that memory before
+        else:
+            self._up.wait_event(slot["done"])   # only the kernels that last read THIS slot, not the batch in flight
+        with torch.cuda.stream(self._up):
+            slot["img"].copy_(host_images, non_blocking=True)
+            slot["seg"].copy_(host_seg, non_blocking=True)
+        main.wait_stream(self._up)
+        B = host_images.shape[0]
+        outs = self.path(slot["img"], [slot["seg"][b] for b in range(B)], input_sizes, original_sizes,
+                         multimask_output=multimask_output)
+        slot["done"] = torch.cuda.Event()
+        slot["done"].record(main)
+        self._down.wait_event(slot["done"])
+        with torch.cuda.stream(self._down):
+            o = 0
+            for t in outs:
+                if t.shape[0]:
+                    host_out[o:o + t.shape[0]].copy_(t, non_blocking=True)
+                    t.record_stream(self._down)
+                    o += t.shape[0]
+            slot["down"] = torch.cuda.Event()
+            slot["down"].record(self._down)
+
+    def drain(self) -> None:
+        """Blocks until every submitted batch has landed in its host_out buffer; the caller's current stream also
+        waits for the copy-out stream, so an event recorded after drain() brackets the whole pipeline."""
+        if self._down is not None:
+            torch.cuda.current_stream().wait_stream(self._down)
+            for s in self._slots:
+                if s["down"] is not None:
+                    s["down"].synchronize()

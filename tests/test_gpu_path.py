@@ -141,6 +141,31 @@ def test_batched_equals_per_image_loop(tiny):
     assert c[1].shape == (0, 1, 480, 640) and torch.equal(c[0], path(x[:1], segs[:1], ins[:1], outs[:1])[0])
 
 
+def test_host_pipeline_equals_direct_calls(tiny):
+    """GroundingPath.host_pipeline(): pinned host batches in, host logits out, copies overlapped with the kernels of the
+    neighbouring batches -- bit-identical to calling the path on device tensors, for more batches than slots."""
+    from anyref_b200.grounding import GroundingPath
+
+    sam = tiny["sam"]
+    sam.image_encoder.set_operand_dtype(torch.float16)
+    path = GroundingPath(sam)
+    sizes = [(1024, 1024)] * 2
+    batches = []
+    for i in range(5):
+        x = synthetic_images(2, seed=20 + i).pin_memory()
+        seg = synthetic_seg_embeddings(2, 2, seed=20 + i).pin_memory()
+        batches.append((x, seg, torch.empty(4, 1, 1024, 1024).pin_memory()))
+    pipe = path.host_pipeline(depth=2)
+    for x, seg, out in batches:
+        pipe.submit(x, seg, sizes, sizes, out)
+    pipe.drain()
+    for x, seg, out in batches:
+        want = path(x.cuda(), [seg[0].cuda(), seg[1].cuda()], sizes, sizes)
+        assert torch.equal(out, torch.cat(want).cpu())
+    with pytest.raises(ValueError):
+        pipe.submit(batches[0][0].cuda(), batches[0][1], sizes, sizes, batches[0][2])
+
+
 def test_whole_path_vs_oracle(tiny):
     from anyref_b200.grounding import GroundingPath
 
