@@ -1,18 +1,11 @@
 mkdir -p gpurun_out
-timeout 200 python -m pytest tests/test_gpu_kernels.py -x -q -m gpu -k "residual_ln" 2>&1 | tail -3
-SAM_GEMM_XLOAD=tma timeout 200 python -m pytest tests/test_gpu_kernels.py -x -q -m gpu -k "residual_ln" 2>&1 | tail -3
-SAM_GEMM_XLOAD=lsu timeout 200 python -m pytest tests/test_gpu_kernels.py -x -q -m gpu -k "residual_ln" 2>&1 | tail -3
-for i in 1 2; do
-echo "--- tma"; SAM_GEMM_XLOAD=tma timeout 300 python tools/gpu_bench_gemm.py 100 proj,proj_ln,lin2,lin2_ln 2>&1 | tee -a gpurun_out/f7_gemm.log
-echo "--- lsu"; SAM_GEMM_XLOAD=lsu timeout 300 python tools/gpu_bench_gemm.py 100 proj,proj_ln,lin2,lin2_ln 2>&1 | tee -a gpurun_out/f7_gemm.log
-done
-for v in auto tma lsu auto; do
-if [ $v = auto ]; then unset SAM_GEMM_XLOAD; else export SAM_GEMM_XLOAD=$v; fi
-timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/f7_bench_$v.log 2> gpurun_out/f7_bench_$v.err; echo "bench $v rc=$?"
-python - $v <<'PY'
-import json,sys
-n=sys.argv[1]
-d=json.loads(open(f"gpurun_out/f7_bench_{n}.log").read().strip().splitlines()[-1])
-print(n, round(d["value"],2), round(d["ms_per_step"],2), round(d["e2e"]["value"],2), d["clocks"]["sm_mhz"], {k:round(v["ms_per_step"],2) for k,v in d["kernel_classes"].items()}, round(d["roofline"]["achieved"],1))
-PY
-done
+M="dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,lts__t_sectors_srcunit_tex_op_read.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"
+run() { # name, env...
+  name=$1; shift
+  env "$@" timeout 120 python tools/ncu_target.py lin2_ln 3 > gpurun_out/plain_x.log 2>&1 && \
+  env "$@" timeout 300 ncu --metrics $M --clock-control none -k regex:gemm2 -s 2 -c 1 --csv --log-file gpurun_out/x_$name.csv python tools/ncu_target.py lin2_ln 3 > gpurun_out/ncu_x.log 2>&1
+  echo "== $name rc=$?"; grep -E "dram__bytes|gpu__time|tensor" gpurun_out/x_$name.csv | awk -F'","' '{print $13, $15}'
+}
+run lsu SAM_GEMM_XLOAD=lsu
+run tma SAM_GEMM_XLOAD=tma
+run lsucs SAM_GEMM_XLOAD=lsu SAM_GEMM_XCS=1

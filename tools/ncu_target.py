@@ -13,9 +13,9 @@ dt = torch.bfloat16
 which = sys.argv[1]
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 torch.manual_seed(0)
-if which in ("lin1", "proj", "qkv", "lin2", "proj_ln", "lin2_ln"):
+if which in ("lin1", "proj", "qkv", "lin2", "proj_ln", "lin2_ln", "qkv_fold", "lin1_fold"):
     N, K = {"lin1": (5120, 1280), "proj": (1280, 1280), "qkv": (3840, 1280), "lin2": (1280, 5120),
-            "proj_ln": (1280, 1280), "lin2_ln": (1280, 5120)}[which]
+            "proj_ln": (1280, 1280), "lin2_ln": (1280, 5120), "qkv_fold": (3840, 1280), "lin1_fold": (5120, 1280)}[which]
     a = (torch.randn(M, K, device=dev) * 0.5).to(dt)
     w = (torch.randn(N, K, device=dev) * 0.05).to(dt)
     bias = torch.randn(N, device=dev)
@@ -25,6 +25,12 @@ if which in ("lin1", "proj", "qkv", "lin2", "proj_ln", "lin2_ln"):
     elif which == "qkv":
         out = torch.empty(M, N, device=dev, dtype=dt)
         fn = lambda: ops.gemm(a, w, bias=bias, out=out)
+    elif which.endswith("_fold"):
+        out = torch.empty(M, N, device=dev, dtype=dt)
+        stats = torch.zeros(M, 10, 2, device=dev)
+        stats[..., 1] = 128.0
+        colsum = torch.randn(N, device=dev)
+        fn = lambda: ops.gemm_ln(a, w, bias, colsum, stats, 1e-6, act="gelu" if which == "lin1_fold" else "none", out=out)
     elif which.endswith("_ln"):
         x = torch.randn(M, N, device=dev)
         xb = torch.empty(M, N, device=dev, dtype=dt)
