@@ -9,7 +9,8 @@ import os
 from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libanyref_sam.so"
+# $ANYREF_SAM_LIB selects another build of the same ABI (A/B timing of kernel variants on one box)
+LIB_PATH = Path(os.environ["ANYREF_SAM_LIB"]) if os.environ.get("ANYREF_SAM_LIB") else _PKG / "libanyref_sam.so"
 
 _lib = None
 
