@@ -166,6 +166,35 @@ def test_host_pipeline_equals_direct_calls(tiny):
         pipe.submit(batches[0][0].cuda(), batches[0][1], sizes, sizes, batches[0][2])
 
 
+def test_eval_sweep_shards_reproduce_the_unsharded_run(tiny):
+    """BASELINE configs[4] (C5) at test size: contiguous shards (anyref_b200.dp.shard_range) give the same masks and
+    the same integer IoU counts as one pass over all images; the thresholded masks and counts agree with a torch
+    evaluation of the returned logits (utils/utils.py:79-91 semantics, ignore label 255)."""
+    from anyref_b200 import dp
+    from anyref_b200.eval_sweep import _image_inputs, run_shard
+
+    sam = tiny["sam"]
+    sam.image_encoder.set_operand_dtype(torch.float16)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    kw = dict(n_seg=2, batch=2, device=dev, op_dtype=torch.float16, original_size=(480, 640), input_size=(768, 1024))
+    full, masks = run_shard(sam, 0, 5, **kw)
+    parts = [run_shard(sam, *dp.shard_range(5, r, 2), **kw) for r in range(2)]
+    assert torch.equal(torch.cat([p[1] for p in parts]), masks)
+    summed = parts[0][0] + parts[1][0]
+    assert torch.equal(summed[:4], full[:4]) and full[6].item() == 10.0
+    assert (summed[4:6] - full[4:6]).abs().max().item() < 1e-12
+    # image 3 recomputed through the public module calls
+    img, seg, gt = _image_inputs(3, 2, dev, torch.float16, 480, 640, 0)
+    emb = sam.image_encoder(img[None])
+    sparse, dense = sam.prompt_encoder(points=None, boxes=None, masks=None, text_embeds=seg)
+    low, _ = sam.mask_decoder(image_embeddings=emb, image_pe=sam.prompt_encoder.get_dense_pe(),
+                              sparse_prompt_embeddings=sparse.to(seg.dtype), dense_prompt_embeddings=dense,
+                              multimask_output=False)
+    pred = (sam.postprocess_masks(low, (768, 1024), (480, 640)) > 0).to(torch.uint8)
+    bits = dp.unpack_bits(masks, 10 * 480 * 640).view(5, 2, 1, 480, 640)
+    assert torch.equal(bits[3], pred)
+
+
 def test_whole_path_vs_oracle(tiny):
     from anyref_b200.grounding import GroundingPath
 

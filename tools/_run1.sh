@@ -1,6 +1,3 @@
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gpu_kernels.py -x -q -m gpu -k "window" 2>&1 | tail -3
-for i in 1 2; do
-echo "--- new"; timeout 200 python tools/gpu_check_attn.py bench 2>&1 | grep attn_
-echo "--- prev"; ANYREF_SAM_LIB=$PWD/anyref_b200/libanyref_sam_prev.so timeout 200 python tools/gpu_check_attn.py bench 2>&1 | grep attn_
-done
+timeout 600 python -m pytest tests/test_gpu_path.py -x -q -m gpu -k "eval_sweep or host_pipeline" 2>&1 | tail -5
+timeout 600 python -m anyref_b200.eval_sweep --images 128 --n-seg 2 --batch 16 > gpurun_out/sweep_n1_128.json 2> gpurun_out/sweep_n1_128.err; echo "sweep rc=$?"; cat gpurun_out/sweep_n1_128.json; tail -3 gpurun_out/sweep_n1_128.err
