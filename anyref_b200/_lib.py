@@ -74,6 +74,8 @@ _PROTOS = {
     "sam_dense_pe": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     "sam_postprocess_masks_iou": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                   c_float, c_void_p, c_void_p, c_void_p],
+    "sam_postprocess_masks_packed": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_float,
+                                     c_void_p, c_void_p, c_void_p],
     "sam_iou_finalize": [c_void_p, c_int, c_void_p, c_void_p],
     "sam_prompt_sparse": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                           c_int, c_int, c_void_p],

@@ -125,8 +125,15 @@ int sam_postprocess_masks(const void* low, int low_fmt, int num_masks, int L, in
 int sam_postprocess_masks_iou(const void* low, int low_fmt, int num_masks, int L, int Sz, int h_in, int w_in, int H, int W,
                               float* logits, unsigned char* binary, float threshold, const unsigned char* target,
                               int* counts, void* stream) {
-  return samk_postprocess_iou(low, low_fmt, num_masks, L, Sz, h_in, w_in, H, W, logits, binary, threshold, target, counts,
-                              S(stream));
+  return samk_postprocess_iou(low, low_fmt, num_masks, L, Sz, h_in, w_in, H, W, logits, binary, nullptr, threshold, target,
+                              counts, S(stream));
+}
+int sam_postprocess_masks_packed(const void* low, int low_fmt, int num_masks, int L, int Sz, int h_in, int w_in, int H, int W,
+                                 unsigned char* packed, float threshold, const unsigned char* target, int* counts,
+                                 void* stream) {
+  if (!low || !packed) return samhost::set_error(1, "sam_postprocess_masks_packed: NULL argument");
+  return samk_postprocess_iou(low, low_fmt, num_masks, L, Sz, h_in, w_in, H, W, nullptr, nullptr, packed, threshold, target,
+                              counts, S(stream));
 }
 int sam_iou_finalize(const int* counts, int n, double* stats, void* stream) {
   return samk_iou_finalize(counts, n, stats, S(stream));

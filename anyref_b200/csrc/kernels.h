@@ -102,8 +102,8 @@ int samk_decoder_forward(const SamDecoderShape& s, const float* blob, const void
 int samk_postprocess(const void* low, int low_fmt, int num_masks, int L, int S, int h_in, int w_in, int H, int W,
                      float* logits, uint8_t* binary, float threshold, cudaStream_t stream);
 int samk_postprocess_iou(const void* low, int low_fmt, int num_masks, int L, int S, int h_in, int w_in, int H, int W,
-                         float* logits, uint8_t* binary, float threshold, const uint8_t* target, int* counts,
-                         cudaStream_t stream);
+                         float* logits, uint8_t* binary, uint8_t* packed, float threshold, const uint8_t* target,
+                         int* counts, cudaStream_t stream);
 int samk_iou_finalize(const int* counts, int n, double* stats, cudaStream_t stream);
 int samk_dense_pe(const float* gauss, void* out, int out_fmt, int C, int g, cudaStream_t stream);
 

@@ -58,14 +58,15 @@ __device__ __forceinline__ float stage1(const void* low, int fmt, size_t base, i
 // resolution logits nor the mask in HBM.
 __global__ void __launch_bounds__(256)
 postprocess_kernel(const void* __restrict__ low, int low_fmt, int L, int S, int h_in, int w_in, int H, int W,
-                   float* __restrict__ logits, uint8_t* __restrict__ binary, float threshold,
+                   float* __restrict__ logits, uint8_t* __restrict__ binary, uint8_t* __restrict__ packed, float threshold,
                    const uint8_t* __restrict__ target, int* __restrict__ counts) {
   const int m = blockIdx.z;
   const int Y = blockIdx.y * blockDim.y + threadIdx.y;
   const int X4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   const bool active = (Y < H && X4 < W);
-  if (!active && counts == nullptr) return;
+  if (!active && counts == nullptr && packed == nullptr) return;
   int cnt[6] = {0, 0, 0, 0, 0, 0};
+  uint32_t nib = 0;      // this thread's 4 thresholded pixels, first pixel in bit 3 (numpy.packbits order)
   if (active) {
   const float scale1 = static_cast<float>(L) / static_cast<float>(S);
   const float sy = static_cast<float>(h_in) / static_cast<float>(H);
@@ -107,6 +108,8 @@ postprocess_kernel(const void* __restrict__ low, int low_fmt, int L, int S, int 
         if (X4 + i < W) binary[o + i] = v[i] > threshold;
     }
   }
+  if (packed)
+    nib = (v[0] > threshold ? 8u : 0u) | (v[1] > threshold ? 4u : 0u) | (v[2] > threshold ? 2u : 0u) | (v[3] > threshold ? 1u : 0u);
   if (counts) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -124,6 +127,13 @@ postprocess_kernel(const void* __restrict__ low, int low_fmt, int L, int S, int 
     }
   }
   }  // active
+  if (packed) {
+    // W % 8 == 0 (checked by the launcher): lanes 2k / 2k+1 hold the high / low nibble of one byte of the flattened
+    // [num_masks, H, W] bit stream, both inside the row or both outside it
+    const uint32_t lo = __shfl_down_sync(0xffffffffu, nib, 1);
+    if (active && (threadIdx.x & 1) == 0)
+      packed[((static_cast<size_t>(m) * H + Y) * W + X4) >> 3] = static_cast<uint8_t>((nib << 4) | lo);
+  }
   if (counts) {
     __shared__ int s_cnt[6];
     const int tid = threadIdx.y * blockDim.x + threadIdx.x;
@@ -164,8 +174,8 @@ __global__ void iou_finalize_kernel(const int* __restrict__ counts, int n, doubl
 
 int samk_postprocess(const void* low, int low_fmt, int num_masks, int L, int S, int h_in, int w_in, int H, int W,
                      float* logits, uint8_t* binary, float threshold, cudaStream_t stream) {
-  return samk_postprocess_iou(low, low_fmt, num_masks, L, S, h_in, w_in, H, W, logits, binary, threshold, nullptr, nullptr,
-                              stream);
+  return samk_postprocess_iou(low, low_fmt, num_masks, L, S, h_in, w_in, H, W, logits, binary, nullptr, threshold, nullptr,
+                              nullptr, stream);
 }
 
 int samk_iou_finalize(const int* counts, int n, double* stats, cudaStream_t stream) {
@@ -178,12 +188,13 @@ int samk_iou_finalize(const int* counts, int n, double* stats, cudaStream_t stre
 }
 
 int samk_postprocess_iou(const void* low, int low_fmt, int num_masks, int L, int S, int h_in, int w_in, int H, int W,
-                         float* logits, uint8_t* binary, float threshold, const uint8_t* target, int* counts,
-                         cudaStream_t stream) {
+                         float* logits, uint8_t* binary, uint8_t* packed, float threshold, const uint8_t* target,
+                         int* counts, cudaStream_t stream) {
   SAM_REQUIRE(num_masks > 0 && L > 0 && S > 0 && H > 0 && W > 0, "postprocess: empty problem");
   SAM_REQUIRE(h_in > 0 && w_in > 0 && h_in <= S && w_in <= S, "postprocess: input_size (%d,%d) outside the %d canvas",
               h_in, w_in, S);
-  SAM_REQUIRE(logits || binary || counts, "postprocess: no output requested");
+  SAM_REQUIRE(logits || binary || counts || packed, "postprocess: no output requested");
+  SAM_REQUIRE(!packed || W % 8 == 0, "postprocess: the bit-packed output needs W %% 8 == 0 (got %d)", W);
   SAM_REQUIRE((target == nullptr) == (counts == nullptr), "postprocess: target and counts go together");
   SAM_REQUIRE(low_fmt >= 0 && low_fmt <= 2, "postprocess: bad input format");
   SAM_REQUIRE(num_masks <= 65535, "postprocess: at most 65535 masks per call");
@@ -192,9 +203,9 @@ int samk_postprocess_iou(const void* low, int low_fmt, int num_masks, int L, int
   samhost::LaunchScope scope(samhost::KC_POSTPROCESS, stream, 0.0,
                              static_cast<double>(num_masks) *
                                  (static_cast<double>(L) * L * (low_fmt == 2 ? 4.0 : 2.0) +
-                                  static_cast<double>(H) * W * ((logits ? 4.0 : 0.0) + (binary ? 1.0 : 0.0) + (target ? 1.0 : 0.0))));
-  postprocess_kernel<<<grid, blk, 0, stream>>>(low, low_fmt, L, S, h_in, w_in, H, W, logits, binary, threshold, target,
-                                               counts);
+                                  static_cast<double>(H) * W * ((logits ? 4.0 : 0.0) + (binary ? 1.0 : 0.0) + (packed ? 0.125 : 0.0) + (target ? 1.0 : 0.0))));
+  postprocess_kernel<<<grid, blk, 0, stream>>>(low, low_fmt, L, S, h_in, w_in, H, W, logits, binary, packed, threshold,
+                                               target, counts);
   SAM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -61,7 +61,11 @@ def run_shard(sam, lo: int, hi: int, n_seg: int, batch: int, device, op_dtype=to
         low, _ = sam.mask_decoder.forward_batched(emb, pe, sparse, dense, index, multimask_output)
         if multimask_output:
             gt = gt.expand(-1, low.shape[1], -1, -1).contiguous()
-        if keep_masks:
+        if keep_masks and W % 8 == 0:
+            # thresholded masks leave the kernel bit-packed (H*W/8 bytes per mask), nothing else of full resolution
+            stats, bits = sam.postprocess_and_score(low, input_size, original_size, gt, stats, return_packed=True)
+            packed.append(bits)
+        elif keep_masks:
             stats, binary = sam.postprocess_and_score(low, input_size, original_size, gt, stats, return_binary=True)
             packed.append(dp.pack_bits(binary))
         else:

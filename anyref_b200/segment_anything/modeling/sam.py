@@ -66,12 +66,14 @@ class Sam(nn.Module):
     @torch.no_grad()
     def postprocess_and_score(self, masks: torch.Tensor, input_size: Tuple[int, ...], original_size: Tuple[int, ...],
                               gt_masks: torch.Tensor, stats: Optional[torch.Tensor] = None,
-                              return_binary: bool = False):
+                              return_binary: bool = False, return_packed: bool = False):
         """postprocess_masks + thresholding + the evaluation statistics of eval_referseg.py:186-211 in ONE pass:
         `gt_masks` uint8 [n,C,H,W] (0 / 1, 255 = ignore).  Adds this call's masks to `stats` (fp64 [7] =
         intersection bg/fg, union bg/fg, accumulated IoU bg/fg, count; created when None) and returns it -- that
         vector is what `anyref_b200.dp.all_reduce_stats` sums across ranks.  Nothing of full resolution is written
-        unless return_binary=True (then the uint8 masks are returned as well)."""
+        unless return_binary=True (then the uint8 masks are returned as well) or return_packed=True (then the
+        bit-packed masks, numpy.packbits order over the flattened [n,C,H,W] array, W % 8 == 0 -- the payload of
+        `anyref_b200.dp.all_gather_packed`: H*W/8 bytes per mask)."""
         _runtime.require_cuda(masks, "Sam.postprocess_and_score")
         m = masks.contiguous()
         n, ch, L, _ = m.shape
@@ -81,8 +83,24 @@ class Sam(nn.Module):
         gt = gt_masks.to(m.device).contiguous()
         if stats is None:
             stats = torch.zeros(7, dtype=torch.float64, device=m.device)
+        if return_binary and return_packed:
+            raise ValueError("return_binary and return_packed are mutually exclusive")
+        if return_packed and W % 8 != 0:
+            raise ValueError(f"return_packed needs W % 8 == 0, got W={W} (use return_binary + dp.pack_bits)")
         binary = torch.empty((n, ch, H, W), device=m.device, dtype=torch.uint8) if return_binary else None
-        if n * ch > 0:
+        if return_packed:
+            binary = torch.empty((n * ch * H * W // 8,), device=m.device, dtype=torch.uint8)
+        if n * ch > 0 and return_packed:
+            counts = torch.zeros((n * ch, 6), dtype=torch.int32, device=m.device)
+            L_ = _lib.load()
+            st = _lib.stream_ptr(m.device)
+            rc = L_.sam_postprocess_masks_packed(m.data_ptr(), _lib.fmt_of(m.dtype), n * ch, L, self.image_encoder.img_size,
+                                                 int(input_size[0]), int(input_size[1]), H, W, binary.data_ptr(),
+                                                 float(self.mask_threshold), gt.data_ptr(), counts.data_ptr(), st)
+            _lib.check(rc, "sam_postprocess_masks_packed")
+            rc = L_.sam_iou_finalize(counts.data_ptr(), n * ch, stats.data_ptr(), st)
+            _lib.check(rc, "sam_iou_finalize")
+        elif n * ch > 0:
             counts = torch.zeros((n * ch, 6), dtype=torch.int32, device=m.device)
             L_ = _lib.load()
             st = _lib.stream_ptr(m.device)
@@ -93,7 +111,7 @@ class Sam(nn.Module):
             _lib.check(rc, "sam_postprocess_masks_iou")
             rc = L_.sam_iou_finalize(counts.data_ptr(), n * ch, stats.data_ptr(), st)
             _lib.check(rc, "sam_iou_finalize")
-        return (stats, binary) if return_binary else stats
+        return (stats, binary) if (return_binary or return_packed) else stats
 
     @torch.no_grad()
     def preprocess(self, x: torch.Tensor, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:

@@ -177,6 +177,44 @@ def gemm_traffic():
         return None
 
 
+def golden_parity(sam, path, dev, dtypes):
+    """Parity of the loaded model (synthetic seed-1234 ViT-H) against the committed outputs of the UNMODIFIED reference
+    modules (tests/golden/vit_h_seed1234_in0.pt, generated by oracle/make_goldens.py): relative Frobenius error of the
+    image embeddings and low-res mask logits (on the stored sub-grids) and IoU of the binarised 1024x1024 masks."""
+    import numpy as np
+
+    from anyref_b200.synthetic import synthetic_images, synthetic_seg_embeddings
+
+    gpath = os.path.join(ROOT, "tests", "golden", "vit_h_seed1234_in0.pt")
+    if not os.path.exists(gpath):
+        return None
+    g = torch.load(gpath, weights_only=False)
+    if g["meta"]["seed_ckpt"] != 1234:
+        return None
+    x = synthetic_images(1, seed=g["meta"]["seed_in"]).to(dev)
+    seg = synthetic_seg_embeddings(1, g["meta"]["n_seg"], seed=g["meta"]["seed_in"])[0].to(dev)
+    rel = lambda a, b: ((a.float().cpu() - b).norm() / b.norm()).item()
+    out = {"golden": "tests/golden/vit_h_seed1234_in0.pt (reference modules, fp32 CPU)"}
+    enc = sam.image_encoder
+    keep = enc._operand_dtype
+    for dt in dtypes:
+        enc.set_operand_dtype(dt)
+        emb = enc(x)
+        sparse, dense = sam.prompt_encoder(points=None, boxes=None, masks=None, text_embeds=seg)
+        low, _ = sam.mask_decoder(image_embeddings=emb, image_pe=sam.prompt_encoder.get_dense_pe(),
+                                  sparse_prompt_embeddings=sparse, dense_prompt_embeddings=dense, multimask_output=False)
+        post = sam.postprocess_masks(low, (1024, 1024), (1024, 1024))
+        want = np.unpackbits(g["post_single_1024x1024_1024x1024_bits"].numpy())[:post.numel()].reshape(post.shape).astype(bool)
+        got = (post > 0).cpu().numpy()
+        ious = [float((want[i] & got[i]).sum() / max((want[i] | got[i]).sum(), 1)) for i in range(post.shape[0])]
+        out["bf16" if dt == torch.bfloat16 else "fp16"] = {
+            "embeddings_rel_fro": rel(emb[:, ::4, ::4, ::4], g["emb_sub"]),
+            "low_res_logits_rel_fro": rel(low[:, :, ::4, ::4], g["low_single_sub"]),
+            "mask_iou_min": min(ious)}
+    enc.set_operand_dtype(keep)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -187,6 +225,7 @@ def main():
     ap.add_argument("--n-seg", type=int, default=1, help="[SEG] prompts per image")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the golden-vector parity check after the timing")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -299,6 +338,10 @@ def main():
     path_flops = B * (ENC_FLOP_PER_IMAGE_USEFUL + n_seg * DEC_FLOP_PER_PROMPT)
     path_tflops = path_flops / (ms_step * 1e-3) / 1e12
 
+    parity = None
+    if rank == 0 and not args.no_parity:
+        parity = golden_parity(sam, path, dev, [op_dtype] + ([torch.float16] if op_dtype != torch.float16 else []))
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         oracle = CpuOracle(1, n_seg)
@@ -338,6 +381,7 @@ def main():
                             "frac_of_measured_burst": path_tflops / peaks["bf16_burst"],
                             "frac_of_nominal_2250": path_tflops / 2250.0},
             "kernel_classes": classes,
+            "parity": parity,
             "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(line), flush=True)

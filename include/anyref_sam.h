@@ -207,6 +207,17 @@ int sam_postprocess_masks(const void* low, int low_fmt, int num_masks, int L, in
 int sam_postprocess_masks_iou(const void* low, int low_fmt, int num_masks, int L, int S, int h_in, int w_in, int H, int W,
                               float* logits, unsigned char* binary, float threshold, const unsigned char* target,
                               int* counts, void* stream);
+
+/*
+ * postprocess_masks + thresholding with the BIT-PACKED mask as the only full-resolution output: packed uint8
+ * [num_masks * H * W / 8], bit 7 of byte 0 = pixel 0 of the flattened [num_masks, H, W] array (numpy.packbits order;
+ * needs W % 8 == 0).  This is what the optional ncclAllGather of the masks moves (131,072 B per 1024^2 mask
+ * instead of 4 MB of logits); HBM bytes per mask = L*L*4 read + H*W/8 written.  target / counts as in
+ * sam_postprocess_masks_iou, or both NULL.
+ */
+int sam_postprocess_masks_packed(const void* low, int low_fmt, int num_masks, int L, int S, int h_in, int w_in, int H, int W,
+                                 unsigned char* packed, float threshold, const unsigned char* target, int* counts,
+                                 void* stream);
 int sam_iou_finalize(const int* counts, int n, double* stats, void* stream);
 
 /*

@@ -166,6 +166,25 @@ def test_host_pipeline_equals_direct_calls(tiny):
         pipe.submit(batches[0][0].cuda(), batches[0][1], sizes, sizes, batches[0][2])
 
 
+@pytest.mark.parametrize("inp,orig", [((1024, 1024), (1024, 1024)), ((768, 1024), (480, 640)), ((1024, 683), (33, 8))])
+def test_bit_packed_postprocess_equals_packbits_of_the_binary_mask(tiny, inp, orig):
+    """sam_postprocess_masks_packed == numpy.packbits(postprocess_masks(...) > 0) and the same IoU counts."""
+    from anyref_b200 import dp
+
+    sam = tiny["sam"]
+    g = torch.Generator().manual_seed(5)
+    low = torch.randn(3, 2, 256, 256, generator=g).cuda()
+    gt = (torch.rand(3, 2, *orig, generator=g) > 0.5).to(torch.uint8)
+    gt[:, :, 0, :] = 255
+    gt = gt.cuda()
+    s_bin, binary = sam.postprocess_and_score(low, inp, orig, gt, return_binary=True)
+    s_pk, packed = sam.postprocess_and_score(low, inp, orig, gt, return_packed=True)
+    assert torch.equal(packed, dp.pack_bits(binary)) and torch.equal(s_bin, s_pk)
+    assert np.array_equal(packed.cpu().numpy(), np.packbits(binary.cpu().numpy().reshape(-1)))
+    with pytest.raises(ValueError):
+        sam.postprocess_and_score(low, inp, (33, 12), gt[..., :33, :12].contiguous(), return_packed=True)
+
+
 def test_eval_sweep_shards_reproduce_the_unsharded_run(tiny):
     """BASELINE configs[4] (C5) at test size: contiguous shards (anyref_b200.dp.shard_range) give the same masks and
     the same integer IoU counts as one pass over all images; the thresholded masks and counts agree with a torch
