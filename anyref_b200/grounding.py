@@ -20,6 +20,18 @@ from .segment_anything.modeling import Sam
 class GroundingPath:
     def __init__(self, sam: Sam):
         self.sam = sam
+        self._index_cache: dict = {}      # (device, prompt counts) -> int32 image index of every prompt, on the device
+
+    def _image_index(self, counts, device) -> torch.Tensor:
+        key = (str(device), tuple(counts))
+        idx = self._index_cache.get(key)
+        if idx is None:
+            if len(self._index_cache) > 64:
+                self._index_cache.clear()
+            idx = torch.repeat_interleave(torch.arange(len(counts), dtype=torch.int32),
+                                          torch.tensor(counts, dtype=torch.int64)).to(device)
+            self._index_cache[key] = idx
+        return idx
 
     @torch.no_grad()
     def __call__(self, sam_images: torch.Tensor, seg_embeds: Sequence[torch.Tensor],
@@ -45,8 +57,7 @@ class GroundingPath:
         text = torch.cat([s.to(emb.device) for s in seg_embeds if s.shape[0] > 0], dim=0)
         sparse, dense = sam.prompt_encoder(points=None, boxes=None, masks=None, text_embeds=text)
         sparse = sparse.to(text.dtype)  # model/anyref.py:806
-        index = torch.repeat_interleave(torch.arange(B, dtype=torch.int32),
-                                        torch.tensor(counts, dtype=torch.int64)).to(emb.device, non_blocking=True)
+        index = self._image_index(counts, emb.device)
         low, _ = sam.mask_decoder.forward_batched(emb, sam.prompt_encoder.get_dense_pe(), sparse, dense, index,
                                                   multimask_output)
         # post-process: one launch per run of images that share (input_size, original_size)
