@@ -514,22 +514,13 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       ptx::mbar_wait(&acc_full[as], aph);
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * BN2 + half * 128);
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      // one 32-column chunk of the accumulator, already in registers
+      auto chunk = [&](const int c, const uint32_t (&v)[32]) {
         const int col0 = n_blk * BN2 + half * 128 + c * 32;
-        uint32_t v[32];
-        ptx::tmem_ld_32x32b_x32(t_row + c * 32, v);
-        ptx::tmem_ld_wait();
-        if (c == 3) {
-          // accumulator stage fully read by this warp -> hand it back to the MMA issuer early
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_remote(&acc_empty[as], 0);
-        }
         // tile overhang (all conditions are warp-uniform); TMA clips partially out-of-range boxes itself
         const bool valid = row0 < p.M && col0 < p.N;
         const bool pair_valid = row0 < p.M && (col0 - (c & 1) * 32) < p.N;   // 16-bit mode: chunks c-1 | c share a box
-        if (OUT_FMT != 2 ? !pair_valid : !valid) continue;
+        if (OUT_FMT != 2 ? !pair_valid : !valid) return;
         float f[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
@@ -610,6 +601,28 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
           buf ^= 1;
         }
+      };
+      // the tensor-memory load of chunk c + 1 is in flight behind the arithmetic of chunk c (the GELU epilogue keeps
+      // the epilogue warps busy ~75 % of a tile period: an exposed tcgen05.ld latency per chunk stalls the MMA issuer
+      // on acc_empty)
+      uint32_t va[32], vb[32];
+      ptx::tmem_ld_32x32b_x32(t_row, va);
+      ptx::tmem_ld_wait_dep(va);
+#pragma unroll 1
+      for (int cp = 0; cp < 2; ++cp) {
+        ptx::tmem_ld_32x32b_x32(t_row + (2 * cp + 1) * 32, vb);
+        chunk(2 * cp, va);
+        ptx::tmem_ld_wait_dep(vb);
+        if (cp == 0) {
+          ptx::tmem_ld_32x32b_x32(t_row + 64, va);
+        } else {
+          // accumulator stage fully read by this warp -> hand it back to the MMA issuer early
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(&acc_empty[as], 0);
+        }
+        chunk(2 * cp + 1, vb);
+        if (cp == 0) ptx::tmem_ld_wait_dep(va);
       }
       if (++as == 2) { as = 0; aph ^= 1; }
     }
