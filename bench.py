@@ -162,8 +162,12 @@ def run_reference(args):
 
 
 def workload_name(args):
-    return (f"C2: SAM ViT-H image encoder + [SEG] prompt encoder/mask decoder + postprocess_masks, {args.dtype}, batch "
-            f"{args.batch} images x {args.n_seg} [SEG] per GPU, 1024x1024 synthetic -> 1024x1024 masks")
+    default = (args.batch == 16 and args.n_seg == 1 and not args.multimask and tuple(args.orig_size) == (1024, 1024)
+               and tuple(args.input_size) == (1024, 1024))
+    tag = "C2" if default else ("C3" if (args.batch == 8 and args.n_seg == 4 and args.multimask) else "custom")
+    return (f"{tag}: SAM ViT-H image encoder + [SEG] prompt encoder/mask decoder + postprocess_masks, {args.dtype}, batch "
+            f"{args.batch} images x {args.n_seg} [SEG] per GPU" + (" x 3 masks (multimask_output)" if args.multimask else "") +
+            f", 1024x1024 synthetic (content {args.input_size[0]}x{args.input_size[1]}) -> {args.orig_size[0]}x{args.orig_size[1]} masks")
 
 
 def gemm_traffic():
@@ -224,6 +228,11 @@ def main():
     ap.add_argument("--batch", type=int, default=16, help="images per GPU per step")
     ap.add_argument("--n-seg", type=int, default=1, help="[SEG] prompts per image")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"])
+    ap.add_argument("--multimask", action="store_true", help="multimask_output=True (3 masks per prompt; configs[2])")
+    ap.add_argument("--input-size", type=int, nargs=2, default=[1024, 1024], metavar=("h", "w"),
+                    help="size of the resized image inside the 1024 canvas (postprocess crop)")
+    ap.add_argument("--orig-size", type=int, nargs=2, default=[1024, 1024], metavar=("H", "W"),
+                    help="original image size the masks are post-processed to")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the golden-vector parity check after the timing")
     args = ap.parse_args()
@@ -262,14 +271,16 @@ def main():
     # every rank gets its own shard of the synthetic stream (seed offset by rank)
     host_images = synthetic_images(B, seed=rank).to(op_dtype).pin_memory()
     host_seg = synthetic_seg_embeddings(B, n_seg, seed=rank).to(op_dtype).pin_memory()
-    sizes = [(1024, 1024)] * B
+    sizes_in = [tuple(args.input_size)] * B
+    sizes = [tuple(args.orig_size)] * B
+    n_ch = 3 if args.multimask else 1
     dev_images = host_images.to(dev)
     dev_seg = host_seg.to(dev)
     seg_list = [dev_seg[b] for b in range(B)]
-    host_out = torch.empty((B * n_seg, 1, 1024, 1024), dtype=torch.float32).pin_memory()
+    host_out = torch.empty((B * n_seg, n_ch, sizes[0][0], sizes[0][1]), dtype=torch.float32).pin_memory()
 
     def step_resident():
-        return path(dev_images, seg_list, sizes, sizes, multimask_output=False)
+        return path(dev_images, seg_list, sizes_in, sizes, multimask_output=args.multimask)
 
     # end to end through the public host-to-host API (GroundingPath.host_pipeline): every step uploads its own images
     # and [SEG] embeddings from pinned host memory and downloads its own fp32 mask logits; the copies of neighbouring
@@ -279,7 +290,7 @@ def main():
     e2e_i = [0]
 
     def step_e2e():
-        pipe.submit(host_images, host_seg, sizes, sizes, host_outs[e2e_i[0] & 1], multimask_output=False)
+        pipe.submit(host_images, host_seg, sizes_in, sizes, host_outs[e2e_i[0] & 1], multimask_output=args.multimask)
         e2e_i[0] += 1
 
     def barrier():
@@ -366,7 +377,7 @@ def main():
             "metric": "images/s", "value": images_per_s, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "masks_per_s": images_per_s * n_seg,
+            "masks_per_s": images_per_s * n_seg * n_ch,
             "config": {"workload": workload_name(args), "batch_per_gpu": B, "n_seg": n_seg, "parallelism": f"dp{world}",
                        "weights": "synthetic seed 1234 (no checkpoints offline)",
                        "l2": "no flush needed: per step 100 MB of images and >1 GB of activations stream through the "
