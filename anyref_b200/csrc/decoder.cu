@@ -195,6 +195,97 @@ dec_linear_kernel(const LinArgs a) {
   }
 }
 
+// Same contract, 128 x 16 x 16 tiles (2 x 4 outputs per thread) for launches with only a few hundred rows.
+// The accumulation order over k is the same as in dec_linear_kernel (k ascending, one fmaf per term), so both kernels
+// give bit-identical results.
+__global__ void __launch_bounds__(256)
+dec_linear_skinny_kernel(const LinArgs a) {
+  constexpr int SBN = 16;
+  __shared__ __align__(16) float As[2][LBK][LBM + 4];
+  __shared__ __align__(16) float Ws[2][LBK][SBN + 4];
+  const int tid = threadIdx.x;
+  const int ty = tid >> 2, tx = tid & 3;          // rows 2 ty, 2 ty + 1; columns 4 tx .. 4 tx + 3
+  const int m0 = blockIdx.x * LBM, n0 = blockIdx.y * SBN;
+  const int ar0 = tid >> 2, akq = tid & 3;        // A rows ar0 and ar0 + 64, k-quad akq
+  const int wr = tid >> 2, wkq = tid & 3;         // W row wr (threads 0..63), k-quad wkq
+  float4 ra[2], rw = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto gload = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int row = m0 + ar0 + i * 64;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row < a.M) {
+        v = *reinterpret_cast<const float4*>(a.X + static_cast<size_t>(row) * a.ldx + k0 + akq * 4);
+        if (a.X2) {
+          const float4 u = *reinterpret_cast<const float4*>(a.X2 + static_cast<size_t>(row % a.x2_mod) * a.ldx2 + k0 + akq * 4);
+          v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+        }
+      }
+      ra[i] = v;
+    }
+    if (tid < 4 * SBN) rw = __ldg(reinterpret_cast<const float4*>(a.W + static_cast<size_t>(n0 + wr) * a.K + k0 + wkq * 4));
+  };
+  auto sstore = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int r = ar0 + i * 64;
+      As[buf][akq * 4 + 0][r] = ra[i].x;
+      As[buf][akq * 4 + 1][r] = ra[i].y;
+      As[buf][akq * 4 + 2][r] = ra[i].z;
+      As[buf][akq * 4 + 3][r] = ra[i].w;
+    }
+    if (tid < 4 * SBN) {
+      Ws[buf][wkq * 4 + 0][wr] = rw.x;
+      Ws[buf][wkq * 4 + 1][wr] = rw.y;
+      Ws[buf][wkq * 4 + 2][wr] = rw.z;
+      Ws[buf][wkq * 4 + 3][wr] = rw.w;
+    }
+  };
+  float acc[2][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const int nk = a.K / LBK;
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  for (int kb = 0; kb < nk; ++kb) {
+    const int buf = kb & 1;
+    if (kb + 1 < nk) gload((kb + 1) * LBK);
+#pragma unroll
+    for (int k = 0; k < LBK; ++k) {
+      const float2 av = *reinterpret_cast<const float2*>(&As[buf][k][ty * 2]);
+      const float4 w = *reinterpret_cast<const float4*>(&Ws[buf][k][tx * 4]);
+      acc[0][0] = fmaf(av.x, w.x, acc[0][0]); acc[0][1] = fmaf(av.x, w.y, acc[0][1]);
+      acc[0][2] = fmaf(av.x, w.z, acc[0][2]); acc[0][3] = fmaf(av.x, w.w, acc[0][3]);
+      acc[1][0] = fmaf(av.y, w.x, acc[1][0]); acc[1][1] = fmaf(av.y, w.y, acc[1][1]);
+      acc[1][2] = fmaf(av.y, w.z, acc[1][2]); acc[1][3] = fmaf(av.y, w.w, acc[1][3]);
+    }
+    if (kb + 1 < nk) {
+      sstore(buf ^ 1);
+      __syncthreads();
+    }
+  }
+  const int col = n0 + tx * 4;
+  float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (a.b) bb = __ldg(reinterpret_cast<const float4*>(a.b + col));
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int row = m0 + ty * 2 + i;
+    if (row >= a.M) continue;
+    float4 y = make_float4(acc[i][0] + bb.x, acc[i][1] + bb.y, acc[i][2] + bb.z, acc[i][3] + bb.w);
+    if (a.act == 1) {
+      y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f);
+    }
+    if (a.R) {
+      const float4 r = *reinterpret_cast<const float4*>(a.R + static_cast<size_t>(row) * a.ldr + col);
+      y.x += r.x; y.y += r.y; y.z += r.z; y.w += r.w;
+    }
+    *reinterpret_cast<float4*>(a.Y + static_cast<size_t>(row) * a.ldy + col) = y;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Tensor-core path for the image-token-side linears (M = n*4096 rows): fp32 accuracy from bf16 tcgen05 MMAs by
 // operand splitting.  x = hi + lo with hi = bf16(x), lo = bf16(x - hi)  (16 mantissa bits together);
@@ -476,14 +567,24 @@ struct HyperArgs {
 
 __device__ void mlp_layer(const float* __restrict__ W, const float* __restrict__ b, const float* x, float* y, int nout,
                           int nin, bool relu) {
+  // one warp per output row, four rows in flight per warp (independent load -> fma chains: the layer is latency-bound);
+  // the summation order of every output (k = lane, lane + 32, ..., then the warp tree) does not depend on the grouping
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int o = warp; o < nout; o += 8) {
-    float a = 0.f;
-    for (int k = lane; k < nin; k += 32) a = fmaf(__ldg(W + static_cast<size_t>(o) * nin + k), x[k], a);
-    a = warp_sum(a);
-    if (lane == 0) {
-      a += b[o];
-      y[o] = relu ? fmaxf(a, 0.f) : a;
+  for (int o = warp * 4; o < nout; o += 32) {
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k = lane; k < nin; k += 32) {
+      const float xv = x[k];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (o + j < nout) a[j] = fmaf(__ldg(W + static_cast<size_t>(o + j) * nin + k), xv, a[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float t = warp_sum(a[j]);
+      if (lane == 0 && o + j < nout) {
+        const float v = t + b[o + j];
+        y[o + j] = relu ? fmaxf(v, 0.f) : v;
+      }
     }
   }
   __syncthreads();
@@ -594,9 +695,16 @@ int launch_linear(const float* X, int ldx, const float* X2, int ldx2, int x2_mod
   SAM_REQUIRE(N % LBN == 0 && K % LBK == 0, "dec_linear: N=%d must be a multiple of %d and K=%d of %d", N, LBN, K, LBK);
   SAM_REQUIRE(ldx % 4 == 0 && ldy % 4 == 0 && (!X2 || ldx2 % 4 == 0) && (!R || ldr % 4 == 0), "dec_linear: ld %% 4");
   LinArgs a{X, ldx, X2, ldx2, x2_mod > 0 ? x2_mod : M, W, b, R, ldr, Y, ldy, M, N, K, act};
-  dim3 grid((M + LBM - 1) / LBM, N / LBN);
   samhost::LaunchScope scope(samhost::KC_DECODER, st, 2.0 * M * N * K);
-  dec_linear_kernel<<<grid, 256, 0, st>>>(a);
+  if (M <= 4 * LBM) {
+    // token-side linears (a few hundred rows): 16-column tiles put N / 16 CTAs per row tile on the machine instead of
+    // N / 64 -- these launches are latency-bound (a K = 2048 reduction walked by 4 CTAs took 133 us)
+    dim3 grid((M + LBM - 1) / LBM, N / 16);
+    dec_linear_skinny_kernel<<<grid, 256, 0, st>>>(a);
+  } else {
+    dim3 grid((M + LBM - 1) / LBM, N / LBN);
+    dec_linear_kernel<<<grid, 256, 0, st>>>(a);
+  }
   SAM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
