@@ -115,6 +115,55 @@ def test_gemm_ln_consumer_matches_layernorm_then_linear(ops, dt, tol, M, N, K, a
     assert rel_fro(got, want.float()) < 1.5 * rel_fro(plain, want.float()) + 1e-4
 
 
+def _guarded(shape, dtype, pad=4096):
+    """Output view in the middle of a sentinel-filled allocation (compute-sanitizer is closed on the GPU pool)."""
+    n = 1
+    for d in shape:
+        n *= d
+    raw = torch.full((n + 2 * pad,), 77, device=DEV, dtype=torch.float32).to(dtype)
+    return raw, raw[pad:pad + n].view(shape), pad
+
+
+def _guards_intact(raw, pad):
+    return bool((raw[:pad].float() == 77).all()) and bool((raw[-pad:].float() == 77).all())
+
+
+@pytest.mark.parametrize("M,N,K", [(2048 + 32, 256, 256), (4096, 1280, 1280), (288, 768, 2304)])
+def test_ln_fold_kernels_stay_inside_their_outputs(ops, M, N, K):
+    """Guard bands around every output of the folded-LayerNorm kernels (M not a multiple of the 256-row tile, K long
+    enough for the vector-load x path): nothing outside the [M, *] views is written."""
+    dt = torch.bfloat16
+    torch.manual_seed(7)
+    a = (torch.randn(M, K, device=DEV) * 0.5).to(dt)
+    w = (torch.randn(N, K, device=DEV) * 0.05).to(dt)
+    bias = torch.randn(N, device=DEV)
+    raw_x, x, pad = _guarded((M, N), torch.float32)
+    x.copy_(torch.randn(M, N, device=DEV))
+    x0 = x.clone()
+    raw_xb, xb, _ = _guarded((M, N), dt)
+    raw_st, st, _ = _guarded((M, N // 128, 2), torch.float32)
+    ops.gemm_residual_ln(a, w, x, bias, xb=xb, stats=st)
+    torch.cuda.synchronize()
+    assert _guards_intact(raw_x, pad) and _guards_intact(raw_xb, pad) and _guards_intact(raw_st, pad)
+    assert rel_fro(x, a.float() @ w.float().t() + bias + x0) < 1e-5 and torch.equal(xb, x.to(dt))
+    # cast_stats and the consumer GEMM on the same buffers
+    raw_xb2, xb2, _ = _guarded((M, N), dt)
+    raw_st2, st2, _ = _guarded((M, N // 128, 2), torch.float32)
+    lib_xb, lib_st = ops.cast_stats(x, dt)
+    from anyref_b200 import _lib
+    rc = _lib.load().sam_cast_stats(x.data_ptr(), N, xb2.data_ptr(), N, _lib.fmt_of(dt), st2.data_ptr(), M, N,
+                                    _lib.stream_ptr(x.device))
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert _guards_intact(raw_xb2, pad) and _guards_intact(raw_st2, pad)
+    assert torch.equal(xb2, lib_xb) and torch.equal(st2, lib_st)
+    w2 = (torch.randn(512, N, device=DEV) * 0.05).to(dt)
+    raw_o, out, _ = _guarded((M, 512), dt)
+    ops.gemm_ln(xb2, w2, torch.randn(512, device=DEV), torch.randn(512, device=DEV), st2, 1e-6, act="gelu", out=out)
+    torch.cuda.synchronize()
+    assert _guards_intact(raw_o, pad) and bool(torch.isfinite(out.float()).all())
+
+
 def test_gemm_rejects_bad_arguments(ops):
     a = torch.zeros(64, 60, device=DEV, dtype=torch.bfloat16)
     w = torch.zeros(64, 60, device=DEV, dtype=torch.bfloat16)
