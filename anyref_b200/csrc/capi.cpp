@@ -36,7 +36,7 @@ int sam_gemm_residual_ln(const void* A, int lda, const void* W, int ldw, int M, 
 }
 int sam_cast_stats(const float* x, int ldx, void* xb, int ldxb, int fmt, void* stats, int M, int C, void* stream) {
   if (!x || !xb || !stats) return samhost::set_error(1, "sam_cast_stats: NULL argument");
-  return samk_cast_stats(x, ldx, xb, ldxb, fmt, stats, M, C, S(stream));
+  return samk_cast_stats(const_cast<float*>(x), ldx, xb, ldxb, fmt, stats, M, C, nullptr, 0, S(stream));
 }
 int sam_gemm_ln(const void* xb, int lda, const void* Wg, int ldw, int M, int N, int K, int fmt, void* out, int ldo,
                 int out_fmt, const float* bias_fold, const float* colsum, const void* stats, int parts, float eps,

@@ -154,8 +154,13 @@ int samk_encoder_forward(const SamEncoderShape& s, const void* w16v, const float
   // ---- patch embedding + pos_embed (image_encoder.py:112-113, :418-426)
   const int pk = 3 * s.patch * s.patch;
   RUN(samk_patch_im2col(images, in_fmt, big16, fmt, B, s.img, s.patch, st));
-  RUN(gemm(big16, pk, patch_w, pk, E, x, E, SAM_F32, patch_b, 0, pos, E, g * g));
-  if (s.ln_fold) RUN(samk_cast_stats(x, E, xb, E, fmt, stats, static_cast<int>(M), E, st));
+  if (s.ln_fold) {
+    // plain fp32 store epilogue (2-CTA kernel); pos_embed is added by the pass that makes xb / stats anyway
+    RUN(gemm(big16, pk, patch_w, pk, E, x, E, SAM_F32, patch_b, 0, nullptr, 0, 0));
+    RUN(samk_cast_stats(x, E, xb, E, fmt, stats, static_cast<int>(M), E, pos, g * g, st));
+  } else {
+    RUN(gemm(big16, pk, patch_w, pk, E, x, E, SAM_F32, patch_b, 0, pos, E, g * g));
+  }
 
   // ---- transformer blocks
   for (int i = 0; i < s.depth; ++i) {

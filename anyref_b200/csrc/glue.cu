@@ -300,16 +300,24 @@ ln_nhwc_to_nchw_kernel(const float* __restrict__ x, const float* __restrict__ ga
 // First producer of the LayerNorm-folding chain (gemm2.cu): xb = round(x) in the operand format plus the per-row
 // partial (sum, sum of squares) of every 128-column slice -- what the residual GEMM epilogues emit for all later
 // blocks.  One warp per row; lane l holds columns 128 j + 4 l .. + 3 of slice j.
+// With `pos` the broadcast rows pos[row % pos_mod] (pos_embed, image_encoder.py:112-113) are added first and the sum is
+// written back to x, so the patch-embed GEMM can use the plain fp32 store epilogue of the 2-CTA kernel.
 __global__ void __launch_bounds__(256)
-cast_stats_kernel(const float* __restrict__ x, int ldx, void* __restrict__ xb, int ldxb, int fmt,
-                  float2* __restrict__ stats, int M, int C) {
+cast_stats_kernel(float* __restrict__ x, int ldx, void* __restrict__ xb, int ldxb, int fmt,
+                  float2* __restrict__ stats, int M, int C, const float* __restrict__ pos, int pos_mod) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int parts = C >> 7;
   for (int row = blockIdx.x * 8 + warp; row < M; row += gridDim.x * 8) {
-    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * ldx);
+    float4* xr = reinterpret_cast<float4*>(x + static_cast<size_t>(row) * ldx);
+    const float4* pr = pos ? reinterpret_cast<const float4*>(pos + static_cast<size_t>(row % pos_mod) * C) : nullptr;
     uint2* orow = reinterpret_cast<uint2*>(static_cast<uint16_t*>(xb) + static_cast<size_t>(row) * ldxb);
     for (int j = 0; j < parts; ++j) {
-      const float4 v = xr[j * 32 + lane];
+      float4 v = xr[j * 32 + lane];
+      if (pr) {
+        const float4 q = __ldg(pr + j * 32 + lane);
+        v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+        xr[j * 32 + lane] = v;
+      }
       uint2 u;
       u.x = ptx::pack2(v.x, v.y, fmt);
       u.y = ptx::pack2(v.z, v.w, fmt);
@@ -323,14 +331,16 @@ cast_stats_kernel(const float* __restrict__ x, int ldx, void* __restrict__ xb, i
 
 }  // namespace
 
-int samk_cast_stats(const float* x, int ldx, void* xb, int ldxb, int fmt, void* stats, int M, int C, cudaStream_t stream) {
+int samk_cast_stats(float* x, int ldx, void* xb, int ldxb, int fmt, void* stats, int M, int C, const float* pos,
+                    int pos_mod, cudaStream_t stream) {
   SAM_REQUIRE(C % 128 == 0 && ldx % 4 == 0 && ldxb % 4 == 0 && M > 0, "cast_stats: C=%d must be a multiple of 128", C);
   SAM_REQUIRE(fmt == 0 || fmt == 1, "cast_stats: output must be fp16/bf16");
   samhost::LaunchScope scope(samhost::KC_LAYERNORM, stream, 0.0, static_cast<double>(M) * C * 6.0);
   int grid = (M + 7) / 8;
   const int cap = samhost::sm_count() * 16;
   if (grid > cap) grid = cap;
-  cast_stats_kernel<<<grid, 256, 0, stream>>>(x, ldx, xb, ldxb, fmt, static_cast<float2*>(stats), M, C);
+  SAM_REQUIRE(!pos || pos_mod > 0, "cast_stats: pos_mod must be positive");
+  cast_stats_kernel<<<grid, 256, 0, stream>>>(x, ldx, xb, ldxb, fmt, static_cast<float2*>(stats), M, C, pos, pos_mod);
   SAM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -79,7 +79,9 @@ int samk_attn_global3(const void* qkv, const void* rh_rev, const void* rw_rev, v
 int samk_layernorm_rows(const float* x, int ldx, const float* res, int ldr, const float* gamma, const float* beta,
                         float eps, void* out, int ldo, int out_fmt, int M, int C, int normalize, cudaStream_t stream);
 //   cast_stats : xb = round(x) (operand format) + per-row partial (sum, sumsq) of every 128-column slice [M, C/128]
-int samk_cast_stats(const float* x, int ldx, void* xb, int ldxb, int fmt, void* stats, int M, int C, cudaStream_t stream);
+//                (pos != null: x[row] += pos[row % pos_mod] first, written back to x)
+int samk_cast_stats(float* x, int ldx, void* xb, int ldxb, int fmt, void* stats, int M, int C, const float* pos,
+                    int pos_mod, cudaStream_t stream);
 int samk_patch_im2col(const void* img, int in_fmt, void* out, int out_fmt, int B, int S, int p, cudaStream_t stream);
 int samk_im2col3x3(const void* in, void* out, int B, int g, int C, cudaStream_t stream);
 int samk_ln_nhwc_to_nchw(const float* x, const float* gamma, const float* beta, float eps, void* out, int out_fmt,
