@@ -94,6 +94,35 @@ __device__ __forceinline__ void tmem_alloc_cg2(uint32_t* dst_smem, uint32_t ncol
 __device__ __forceinline__ void tmem_dealloc_cg2(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void tma_load_2d_cg2_hint(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(ptx::smem_u32(dst)), "l"(m), "r"(ptx::smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "l"(pol)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* m, const void* src, int c0, int c1, uint64_t pol) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;" ::"l"(m),
+               "r"(ptx::smem_u32(src)), "r"(c0), "r"(c1), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ void st_global_v4_hint(void* p, uint4 v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
+}
+__device__ __forceinline__ float4 ld_global_v4f_hint(const void* p, uint64_t pol) {
+  float4 v;
+  asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+  return v;
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(m),
                "r"(ptx::smem_u32(src)), "r"(c0), "r"(c1)
@@ -178,6 +207,8 @@ struct Gemm2Params {
   const float* xres;   // == the fp32 output (in-place residual), row stride ldx
   int ldx;
   int x_tma;           // producer: fetch the x chunks with TMA (short main loops) instead of vector loads
+  int l2hint;          // L2 eviction-priority hints: W evict_last; the producer's x / xb streams evict_first, so that
+                       // they do not push the A row block out of L2 before all CTA pairs of a tile row have read it
 };
 
 // OUT_FMT: SamFmt of the output (0 fp16, 1 bf16, 2 fp32);  ACT: 0 none, 1 GELU  (compile-time so the epilogue carries
@@ -234,6 +265,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
+      const uint64_t pol_w = l2_policy_evict_last();
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
         const int row_a = m_blk * (2 * BM2) + static_cast<int>(rank) * BM2;
@@ -246,7 +278,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           // phase because the peer waited for the commit that followed the MMAs of that phase
           if (leader) ptx::mbar_expect_tx(&full_bar[s], 2 * kStage2);
           tma_load_2d_cg2(sa, &tmA, &full_bar[s], kb * BK2, row_a);
-          tma_load_2d_cg2(sb, &tmB, &full_bar[s], kb * BK2, row_b);
+          if (p.l2hint) tma_load_2d_cg2_hint(sb, &tmB, &full_bar[s], kb * BK2, row_b, pol_w);
+          else tma_load_2d_cg2(sb, &tmB, &full_bar[s], kb * BK2, row_b);
           if (++s == kStages2) { s = 0; ph ^= 1; }
         }
       }
@@ -390,6 +423,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           __syncwarp();
         }
       } else {
+      const uint64_t pol_stream = l2_policy_evict_first();
       // coalesced: instruction i of lane l fetches 16 B piece (l & 7) of row 4 i + (l >> 3)  (4 full lines each)
       auto load_x = [&](int q, float4 (&dst)[8]) {
         int c0, r0;
@@ -397,7 +431,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (r0 < p.M && c0 < p.N) {
           const float* src = p.xres + static_cast<size_t>(r0 + (lane >> 3)) * p.ldx + c0 + (lane & 7) * 4;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) dst[i] = *reinterpret_cast<const float4*>(src + static_cast<size_t>(4 * i) * p.ldx);
+          for (int i = 0; i < 8; ++i) {
+            const float4* ptr = reinterpret_cast<const float4*>(src + static_cast<size_t>(4 * i) * p.ldx);
+            dst[i] = p.l2hint ? ld_global_v4f_hint(ptr, pol_stream) : *ptr;
+          }
         }
       };
       // two chunks of x in flight per warp (register sets xa / xb, alternating): the prefetch distance covers the
@@ -464,7 +501,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           ptx::fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tma_store_2d(&tmC, stg + buf * 4096, col0, row0);
+            if (p.l2hint) tma_store_2d_hint(&tmC, stg + buf * 4096, col0, row0, pol_stream);
+            else tma_store_2d(&tmC, stg + buf * 4096, col0, row0);
             bulk_commit();
           }
           buf ^= 1;
@@ -475,7 +513,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             u.y = ptx::pack2(xr[2 * i].z, xr[2 * i].w, p.xb_fmt);
             u.z = ptx::pack2(xr[2 * i + 1].x, xr[2 * i + 1].y, p.xb_fmt);
             u.w = ptx::pack2(xr[2 * i + 1].z, xr[2 * i + 1].w, p.xb_fmt);
-            reinterpret_cast<uint4*>(xb_row)[i] = u;
+            if (p.l2hint) st_global_v4_hint(reinterpret_cast<uint4*>(xb_row) + i, u, pol_stream);
+            else reinterpret_cast<uint4*>(xb_row)[i] = u;
           }
           if (c == 3) {
             const int tile = cluster_id + (q >> 2) * num_clusters;
@@ -715,6 +754,8 @@ int samk_gemm2(const void* A, int lda, const void* W, int ldw, int M, int N, int
   {
     static const char* xl = getenv("SAM_GEMM_XLOAD");   // experiment switch: "tma" | "lsu"
     p.x_tma = xl ? (xl[0] == 't') : (K <= 2048);
+    static const char* lh = getenv("SAM_GEMM_L2HINT");   // "0" switches the L2 eviction hints off (A/B measurements)
+    p.l2hint = lh ? (lh[0] == '1') : 1;
   }
   const int m_tiles = (M + 2 * BM2 - 1) / (2 * BM2), n_tiles = (N + BN2 - 1) / BN2;
   int clusters = m_tiles * n_tiles;
