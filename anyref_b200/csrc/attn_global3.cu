@@ -400,6 +400,7 @@ glob_attn3_kernel(const __grid_constant__ GlobAttnMaps3 maps, const uint16_t* __
       }
     }
     ptx::tc_fence_before();
+    ptx::fence_proxy_async_smem();   // generic-proxy staging stores vs. the TMA writes of K / V into the same bytes
     ptx::mbar_arrive(pro_done);
 
     float m_ref = 0.f;   // reference maximum (log2 domain) all stored probabilities are relative to

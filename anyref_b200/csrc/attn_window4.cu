@@ -459,6 +459,10 @@ win_attn4_kernel(const __grid_constant__ WinAttnMaps4 maps, const uint16_t* __re
         for (int kw = 0; kw < WS; ++kw)
           asm volatile("ld.shared.f32 %0, [%1];" : "=f"(relw[kw]) : "r"(aw - kw * 512) : "memory");
       }
+      // the scratch stores above went through the generic proxy; the producer's next TMA into this stage writes the
+      // same bytes through the async proxy.  Without this fence a late scratch store can land on top of the freshly
+      // loaded Q rows (seen as a few wrong rows of one item in ~4 % of stress runs).
+      ptx::fence_proxy_async_smem();
       ptx::mbar_arrive(&qk_free[s]);   // Q / K of this stage may be overwritten (count 2 MMA commits + 256 threads)
 
       f32x2 s0 = 0ull, s1 = 0ull;
