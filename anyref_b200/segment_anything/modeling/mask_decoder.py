@@ -91,11 +91,21 @@ class MaskDecoder(nn.Module):
         sl = slice(1, None) if multimask_output else slice(0, 1)
         return masks[:, sl, :, :], iou[:, sl]
 
-    @torch.no_grad()
     def predict_masks(self, image_embeddings: torch.Tensor, image_pe: torch.Tensor,
                       sparse_prompt_embeddings: torch.Tensor, dense_prompt_embeddings: torch.Tensor,
                       image_index: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
         """All `num_mask_tokens` masks [n,4,4g,4g] and IoU predictions [n,4] (mask_decoder.py:116-179)."""
+        if torch.is_grad_enabled() and (sparse_prompt_embeddings.requires_grad or
+                                        (self.training and any(p.requires_grad for p in self.parameters()))):
+            # model/anyref.py:108-113 puts the decoder in train() with requires_grad=True for fine-tuning; returning
+            # tensors without a graph there would silently train nothing
+            raise NotImplementedError("MaskDecoder runs the inference path only: call it in eval() mode or under "
+                                      "torch.no_grad(); the decoder backward is SURVEY 8(f)-4, not built yet")
+        with torch.no_grad():
+            return self._predict_masks(image_embeddings, image_pe, sparse_prompt_embeddings, dense_prompt_embeddings,
+                                       image_index)
+
+    def _predict_masks(self, image_embeddings, image_pe, sparse_prompt_embeddings, dense_prompt_embeddings, image_index):
         _runtime.require_cuda(image_embeddings, "MaskDecoder")
         lib = _lib.load()
         emb = image_embeddings.contiguous()

@@ -2,12 +2,13 @@
 normalisation buffers, and `postprocess_masks` -- here one fused CUDA kernel (`sam_postprocess_masks`) instead of two
 F.interpolate calls with a [n,C,1024,1024] intermediate (sam.py:159-172).
 
-The reference's `Sam.forward` (:56-135) is dead code on AnyRef's path (it calls the prompt encoder without the
-required `text_embeds`) and is not provided.
+`Sam.forward` (:54-135) is dead code on AnyRef's path and broken in the reference (it calls the prompt encoder without
+the `text_embeds` argument AnyRef added, prompt_encoder.py:139-145 -> TypeError).  It is provided here
+in working form -- same records in, same records out, plus an optional 'text_embeds' key -- for users of upstream SAM.
 """
 from __future__ import annotations
 
-from typing import Any, List, Optional, Tuple
+from typing import Any, Dict, List, Optional, Tuple
 
 import torch
 import torch.nn as nn
@@ -37,9 +38,32 @@ class Sam(nn.Module):
     def device(self) -> Any:
         return self.pixel_mean.device
 
-    def forward(self, *args, **kwargs):  # pragma: no cover
-        raise NotImplementedError("Sam.forward is unused (and broken) in AnyRef; call image_encoder / prompt_encoder / "
-                                  "mask_decoder / postprocess_masks as model/anyref.py:793-819 does")
+    @torch.no_grad()
+    def forward(self, batched_input: List[Dict[str, Any]], multimask_output: bool) -> List[Dict[str, torch.Tensor]]:
+        """End-to-end prediction for a list of image records (sam.py:54-135).  Each record: 'image' [3,h,w] already
+        resized to the model frame (longest side == img_size), 'original_size' (H, W), and any of 'point_coords' [n,N,2]
+        + 'point_labels' [n,N], 'boxes' [n,4], 'mask_inputs' [n,1,256,256], 'text_embeds' [n,k,256] ([SEG] embeddings;
+        not a key of upstream SAM).  Returns per image 'masks' bool [n,C,H,W], 'iou_predictions' [n,C],
+        'low_res_logits' [n,C,256,256].  The images go through ONE batched encoder call as in the reference
+        (:98-101); thresholding happens inside the postprocess kernel (no fp32 [n,C,H,W] compare pass)."""
+        if len(batched_input) == 0:
+            return []
+        images = torch.stack([self.preprocess(rec["image"]) for rec in batched_input], dim=0)
+        image_embeddings = self.image_encoder(images)
+        image_pe = self.prompt_encoder.get_dense_pe()
+        outputs = []
+        for i, rec in enumerate(batched_input):
+            points = (rec["point_coords"], rec["point_labels"]) if "point_coords" in rec else None
+            sparse, dense = self.prompt_encoder(points=points, boxes=rec.get("boxes", None),
+                                                masks=rec.get("mask_inputs", None),
+                                                text_embeds=rec.get("text_embeds", None))
+            low_res, iou = self.mask_decoder(image_embeddings=image_embeddings[i:i + 1], image_pe=image_pe,
+                                             sparse_prompt_embeddings=sparse.to(image_embeddings.dtype),
+                                             dense_prompt_embeddings=dense, multimask_output=multimask_output)
+            _, binary = self.postprocess_masks(low_res, input_size=tuple(rec["image"].shape[-2:]),
+                                               original_size=tuple(rec["original_size"]), return_binary=True)
+            outputs.append({"masks": binary.view(torch.bool), "iou_predictions": iou, "low_res_logits": low_res})
+        return outputs
 
     @torch.no_grad()
     def postprocess_masks(self, masks: torch.Tensor, input_size: Tuple[int, ...], original_size: Tuple[int, ...],

@@ -437,6 +437,50 @@ def test_sam_predictor_box_prompt_vs_oracle(tiny):
         SamPredictor(sam).predict(box=box)
 
 
+def test_sam_forward_records_vs_oracle(tiny):
+    """Sam.forward (sam.py:54-135) over a list of records with different prompt types and frame sizes: a box record
+    (landscape frame), a point + mask-input record (portrait frame) and a [SEG] text_embeds record; every output is
+    compared with the same steps of the CPU restatement."""
+    sam, cfg, sd = tiny["sam"], tiny["cfg"], tiny["sd"]
+    sam.image_encoder.set_operand_dtype(torch.float16)
+    g = torch.Generator().manual_seed(33)
+    recs = [
+        {"image": torch.randint(0, 256, (3, 768, 1024), generator=g).float(), "original_size": (480, 640),
+         "boxes": torch.tensor([[80.0, 96.0, 640.0, 480.0], [10.0, 20.0, 1000.0, 700.0]])},
+        {"image": torch.randint(0, 256, (3, 1024, 683), generator=g).float(), "original_size": (640, 427),
+         "point_coords": torch.rand(1, 2, 2, generator=g) * 600, "point_labels": torch.tensor([[1.0, 0.0]]),
+         "mask_inputs": torch.randn(1, 1, 256, 256, generator=g)},
+        {"image": torch.randint(0, 256, (3, 1024, 1024), generator=g).float(), "original_size": (1024, 1024),
+         "text_embeds": torch.randn(3, 1, 256, generator=g)},
+    ]
+    mean = torch.tensor([123.675, 116.28, 103.53]).view(-1, 1, 1)
+    std = torch.tensor([58.395, 57.12, 57.375]).view(-1, 1, 1)
+    with torch.no_grad():
+        x = torch.stack([torch.nn.functional.pad((r["image"] - mean) / std,
+                                                 (0, 1024 - r["image"].shape[-1], 0, 1024 - r["image"].shape[-2]))
+                         for r in recs])
+        emb = O.image_encoder(sd, x, cfg)
+        pe = O.dense_pe(sd, cfg)
+    cuda_recs = [{k: (v.cuda() if torch.is_tensor(v) else v) for k, v in r.items()} for r in recs]
+    for multimask in (False, True):
+        outs = sam(cuda_recs, multimask_output=multimask)
+        assert len(outs) == 3
+        for i, (r, o) in enumerate(zip(recs, outs)):
+            pts = (r["point_coords"], r["point_labels"]) if "point_coords" in r else None
+            with torch.no_grad():
+                so, do = O.prompt_encoder(sd, cfg, points=pts, boxes=r.get("boxes"), masks=r.get("mask_inputs"),
+                                          text_embeds=r.get("text_embeds"))
+                mo, io = O.mask_decoder(sd, cfg, emb[i:i + 1], pe, so, do, multimask)
+                full = O.postprocess_masks(mo, tuple(r["image"].shape[-2:]), r["original_size"])
+            n, ch = so.shape[0], 3 if multimask else 1
+            assert o["masks"].dtype == torch.bool and o["masks"].shape == (n, ch, *r["original_size"])
+            assert o["low_res_logits"].shape == (n, ch, 256, 256) and o["iou_predictions"].shape == (n, ch)
+            assert rel_fro(o["low_res_logits"], mo) < 5e-3, (i, multimask)
+            assert (o["iou_predictions"].float().cpu() - io).abs().max() < 5e-3
+            assert mask_iou(o["masks"].float() - 0.5, full) > 0.99, (i, multimask)
+    assert sam([], multimask_output=False) == []
+
+
 @pytest.mark.parametrize("inp,orig", [((1024, 1024), (1024, 1024)), ((1024, 683), (640, 427)), ((768, 1024), (481, 643))])
 def test_fused_iou_statistics_are_exact(tiny, inp, orig):
     """postprocess + threshold + intersectionAndUnionGPU (utils/utils.py:79-91, eval_referseg.py:197-211) in one pass:
