@@ -40,6 +40,16 @@ constexpr int kSmem2 = kStages2 * kStage2 + kEpiWarps * kStagingPerWarp + 1024 /
 static_assert((2 * kStages2 + 4 + 2 * kEpiWarps) * 8 + 4 <= 256, "barrier block overflows its 256 bytes");
 constexpr uint32_t kTmemCols2 = 512;
 
+// which roles use the parked mbarrier wait (ptx::mbar_wait_parked): bit 0 TMA producer, bit 1 MMA issuer, bit 2 epilogue
+// warps waiting for an accumulator, bit 3 epilogue warps waiting for their x-tile loads
+#ifndef GEMM2_PARK_MASK
+#define GEMM2_PARK_MASK 15
+#endif
+template <int BIT>
+__device__ __forceinline__ void wait_role(uint64_t* bar, uint32_t parity) {
+  if ((GEMM2_PARK_MASK >> BIT) & 1) ptx::mbar_wait_parked(bar, parity); else ptx::mbar_wait(bar, parity);
+}
+
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -271,7 +281,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int row_a = m_blk * (2 * BM2) + static_cast<int>(rank) * BM2;
         const int row_b = n_blk * BN2 + static_cast<int>(rank) * (BN2 / 2);
         for (int kb = 0; kb < num_kb; ++kb) {
-          ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+          wait_role<0>(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + s * kStage2;
           uint8_t* sb = sa + kStageA2;
           // the peer's bytes may land before this expect_tx (tx-count is signed); they cannot land in an earlier
@@ -292,11 +302,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       int as = 0;
       uint32_t aph = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        ptx::mbar_wait(&acc_empty[as], aph ^ 1);
+        wait_role<1>(&acc_empty[as], aph ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN2);
         for (int kb = 0; kb < num_kb; ++kb) {
-          ptx::mbar_wait(&full_bar[s], ph);
+          wait_role<1>(&full_bar[s], ph);
           ptx::tc_fence_after();
           const uint32_t sa = ptx::smem_u32(smem + s * kStage2);
           const uint32_t sb = sa + kStageA2;
@@ -354,7 +364,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           int col0, row0;
           chunk_xy(q, col0, row0);
           if (c == 0) {
-            ptx::mbar_wait(&acc_full[as], aph);
+            wait_role<2>(&acc_full[as], aph);
             ptx::tc_fence_after();
             s1 = 0.f;
             s2 = 0.f;
@@ -368,7 +378,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             __syncwarp();
             if (lane == 0) mbar_arrive_remote(&acc_empty[as], 0);
           }
-          ptx::mbar_wait(&ldb[b], (lph >> b) & 1u);
+          wait_role<3>(&ldb[b], (lph >> b) & 1u);
           lph ^= 1u << b;
           const bool valid = row0 < p.M && col0 < p.N;     // warp-uniform (M % 32 == 0, N % 32 == 0)
           const uint32_t sb = ptx::smem_u32(stg) + b * 4096 + lane * 128;
@@ -462,7 +472,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
         if (q + 2 < total_q) load_x(q + 2, xn);
         if (c == 0) {
-          ptx::mbar_wait(&acc_full[as], aph);
+          wait_role<2>(&acc_full[as], aph);
           ptx::tc_fence_after();
           s1 = 0.f;
           s2 = 0.f;
@@ -550,7 +560,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           ln_r = rsqrtf(fmaxf(fmaf(-ln_mu, ln_mu, s2 * p.ln_inv_c), 0.f) + p.ln_eps);
         }
       }
-      ptx::mbar_wait(&acc_full[as], aph);
+      wait_role<2>(&acc_full[as], aph);
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * BN2 + half * 128);
       // one 32-column chunk of the accumulator, already in registers
