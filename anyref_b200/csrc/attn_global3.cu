@@ -52,7 +52,21 @@ constexpr int OFF_STAGE1 = OFF_P;   // tile 1: same, over the P buffers
 constexpr int kStageStride = 127;
 
 constexpr uint32_t TM_O = 128;      // column offset of O inside a tile's 256-column slot
+constexpr uint32_t TM_P = 208;      // GLOB_PTMEM: ring of six 8-column P quarters
 constexpr float kSumLimit = 1024.0f;
+// rel_w term of the logits preloaded into the S accumulator (tcgen05.st of rel_w / scale, the S MMAs accumulate on top)
+// instead of one FADD2 per logit pair in the softmax warps (32 of the ~300 warp instructions per 64-key block)
+#ifndef GLOB_PRELOAD
+#define GLOB_PRELOAD 1
+#endif
+// Probabilities in tensor memory: P(j) goes to a ring of six 8-column quarter slots at columns [208, 256) of the tile's
+// slot (tcgen05.st, quarter q of block j -> ring slot (4 j + q) mod 6) and P.V is the `ts` form of tcgen05.mma (A from
+// TMEM) -- no STS, no swizzle arithmetic, no generic->async proxy fence in the softmax warps.  Quarters 0, 1 of block j
+// reuse the slots of quarters 2, 3 of block j - 2; quarters 2, 3 reuse quarters 0, 1 of block j - 1, whose P.V is
+// waited for halfway through the block (issued at the end of block j - 1, long finished by then).
+#ifndef GLOB_PTMEM
+#define GLOB_PTMEM 0
+#endif
 #ifndef SAM_GLOB3_POLY_EVERY
 #define SAM_GLOB3_POLY_EVERY 0
 #endif
@@ -87,18 +101,34 @@ __device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_
       "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
       : "memory");
 }
+__device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]),
+               "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// 64 fp32 words of this thread's TMEM lane starting at column address taddr
+__device__ __forceinline__ void store_relw(uint32_t taddr, const float (&relw)[64]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint32_t v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(relw[c * 16 + i]);
+    tmem_st_32x32b_x16(taddr + c * 16, v);
+  }
+}
 
 // 16 keys (kw = Q*16 .. Q*16+15) of a key row: logits in the log2 domain relative to the reference maximum (folded
 // into rh), exp2, row-sum (two partial sums), P -> shared memory in operand format (two 16-byte units of the row).
 template <int Q, int FMT, int FAKE = 0>
 __device__ __forceinline__ void softmax_q16(const uint32_t (&v)[16], const float (&relw)[64], f32x2 rh2, f32x2 sc2,
-                                            uint32_t prow /* row base ^ (swizzle << 4) */, f32x2& bsum2) {
+                                            uint32_t prow /* row base ^ (swizzle << 4) */, int qs, f32x2& bsum2) {
   uint32_t pk[8];
 #pragma unroll
   for (int i = 0; i < 16; i += 2) {
     f32x2 x = fma2(pk2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), sc2, rh2);
-    x = add2(x, pk2(relw[Q * 16 + i], relw[Q * 16 + i + 1]));
+    if (!GLOB_PRELOAD) x = add2(x, pk2(relw[Q * 16 + i], relw[Q * 16 + i + 1]));
     float x0, x1, p0, p1;
     upk2(x, x0, x1);
     if (kPolyEvery > 0 && ((Q * 8 + (i >> 1)) % kPolyEvery) == kPolyEvery - 1) {
@@ -130,8 +160,15 @@ __device__ __forceinline__ void softmax_q16(const uint32_t (&v)[16], const float
     bsum2 = add2(bsum2, pk2(p0, p1));
     pk[i >> 1] = ptx::pack2t<FMT>(p0, p1);
   }
-  ptx::st_shared_v4(prow ^ ((Q * 2) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
-  ptx::st_shared_v4(prow ^ ((Q * 2 + 1) << 4), make_uint4(pk[4], pk[5], pk[6], pk[7]));
+  if (GLOB_PTMEM) {
+    // prow = TMEM address of this lane's P ring; quarter Q of the block goes to ring slot (qs + Q) mod 6, qs = 4 j mod 6
+    int slot = qs + Q;
+    slot -= (slot >= 6) ? 6 : 0;
+    tmem_st_32x32b_x8(prow + static_cast<uint32_t>(slot * 8), pk);
+  } else {
+    ptx::st_shared_v4(prow ^ ((Q * 2) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
+    ptx::st_shared_v4(prow ^ ((Q * 2 + 1) << 4), make_uint4(pk[4], pk[5], pk[6], pk[7]));
+  }
 }
 
 template <int Q>
@@ -139,8 +176,8 @@ __device__ __forceinline__ void max_q16(const uint32_t (&v)[16], const float (&r
                                         float& m0, float& m1) {
 #pragma unroll
   for (int i = 0; i < 16; i += 2) {
-    m0 = fmaxf(m0, fmaf(__uint_as_float(v[i]), scale_log2e, rh) + relw[Q * 16 + i]);
-    m1 = fmaxf(m1, fmaf(__uint_as_float(v[i + 1]), scale_log2e, rh) + relw[Q * 16 + i + 1]);
+    m0 = fmaxf(m0, fmaf(__uint_as_float(v[i]), scale_log2e, rh) + (GLOB_PRELOAD ? 0.f : relw[Q * 16 + i]));
+    m1 = fmaxf(m1, fmaf(__uint_as_float(v[i + 1]), scale_log2e, rh) + (GLOB_PRELOAD ? 0.f : relw[Q * 16 + i + 1]));
   }
 }
 
@@ -148,22 +185,27 @@ __device__ __forceinline__ void max_q16(const uint32_t (&v)[16], const float (&r
 // the current quarter (only 32 S registers live).  MODE 0: probabilities (P -> smem, row sum);  MODE 1: maximum only.
 template <int MODE, int FMT, int FAKE = 0>
 __device__ __forceinline__ void block_pass(uint32_t ts, const float (&relw)[64], float rh, float scale_log2e,
-                                           uint32_t prow, f32x2& bsum2, float& bmax) {
+                                           uint32_t prow, int qs, uint64_t* pv_prev, uint32_t pv_prev_parity,
+                                           f32x2& bsum2, float& bmax) {
   const f32x2 sc2 = pk2(scale_log2e, scale_log2e), rh2 = pk2(rh, rh);
   float m0 = -INFINITY, m1 = -INFINITY;
   uint32_t a[16], b[16];
   ptx::tmem_ld_32x32b_x16(ts, a);
   ptx::tmem_ld_wait_dep16(a);
   ptx::tmem_ld_32x32b_x16(ts + 16, b);
-  if (MODE == 0) softmax_q16<0, FMT, FAKE>(a, relw, rh2, sc2, prow, bsum2); else max_q16<0>(a, relw, rh, scale_log2e, m0, m1);
+  if (MODE == 0) softmax_q16<0, FMT, FAKE>(a, relw, rh2, sc2, prow, qs, bsum2); else max_q16<0>(a, relw, rh, scale_log2e, m0, m1);
   ptx::tmem_ld_wait_dep16(b);
   ptx::tmem_ld_32x32b_x16(ts + 32, a);
-  if (MODE == 0) softmax_q16<1, FMT, FAKE>(b, relw, rh2, sc2, prow, bsum2); else max_q16<1>(b, relw, rh, scale_log2e, m0, m1);
+  if (MODE == 0) softmax_q16<1, FMT, FAKE>(b, relw, rh2, sc2, prow, qs, bsum2); else max_q16<1>(b, relw, rh, scale_log2e, m0, m1);
   ptx::tmem_ld_wait_dep16(a);
   ptx::tmem_ld_32x32b_x16(ts + 48, b);
-  if (MODE == 0) softmax_q16<2, FMT, FAKE>(a, relw, rh2, sc2, prow, bsum2); else max_q16<2>(a, relw, rh, scale_log2e, m0, m1);
+  if (GLOB_PTMEM && MODE == 0 && pv_prev != nullptr) {
+    ptx::mbar_wait(pv_prev, pv_prev_parity);   // P.V of the previous block has consumed the ring slots quarters 2, 3 reuse
+    ptx::tc_fence_after();
+  }
+  if (MODE == 0) softmax_q16<2, FMT, FAKE>(a, relw, rh2, sc2, prow, qs, bsum2); else max_q16<2>(a, relw, rh, scale_log2e, m0, m1);
   ptx::tmem_ld_wait_dep16(b);
-  if (MODE == 0) softmax_q16<3, FMT, FAKE>(b, relw, rh2, sc2, prow, bsum2); else max_q16<3>(b, relw, rh, scale_log2e, m0, m1);
+  if (MODE == 0) softmax_q16<3, FMT, FAKE>(b, relw, rh2, sc2, prow, qs, bsum2); else max_q16<3>(b, relw, rh, scale_log2e, m0, m1);
   if (MODE == 1) bmax = fmaxf(m0, m1);
 }
 
@@ -324,7 +366,8 @@ glob_attn3_kernel(const __grid_constant__ GlobAttnMaps3 maps, const uint16_t* __
         const uint64_t dk16 = dk16_0 + static_cast<uint64_t>(s * (2048 >> 4));
         const uint32_t d = slot + (j & 1) * 64;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) ptx::mma_f16_ss(d, dq64 + 2 * k, dk64 + 2 * k, id_S, k != 0);
+        // GLOB_PRELOAD: the S buffer already holds rel_w / scale (written by the softmax warps), accumulate on top
+        for (int k = 0; k < 4; ++k) ptx::mma_f16_ss(d, dq64 + 2 * k, dk64 + 2 * k, id_S, GLOB_PRELOAD ? 1 : (k != 0));
         if (kTail) ptx::mma_f16_ss(d, dq16, dk16, id_S, 1);
         ptx::mma_commit(&s_full[g * 2 + (j & 1)]);
         ptx::mma_commit(&k_free[s]);   // K(j) consumed by this tile (count 2: both issuers)
@@ -332,8 +375,9 @@ glob_attn3_kernel(const __grid_constant__ GlobAttnMaps3 maps, const uint16_t* __
       ptx::mbar_wait(&k_full[0], 0);
       ptx::tc_fence_after();
       issue_s(0);
+      int qs = 0;   // GLOB_PTMEM: 4 j mod 6
 #pragma unroll 1
-      for (int j = 0; j < kNBlk; ++j) {
+      for (int j = 0; j < kNBlk; ++j, qs = (qs >= 2) ? qs - 2 : qs + 4) {
         const int s = j & (kStagesKV - 1);
         const int bf = j & 1;
         if (j + 1 < kNBlk) {
@@ -352,8 +396,16 @@ glob_attn3_kernel(const __grid_constant__ GlobAttnMaps3 maps, const uint16_t* __
         ptx::tc_fence_after();
 #pragma unroll
         for (int ks = 0; ks < BKV / 16; ++ks) {
-          ptx::mma_f16_ss(slot + TM_O, dp + 2 * ks, dv64 + ((ks * 2048) >> 4), id_O64, (j | ks) != 0);
-          if (kTail) ptx::mma_f16_ss(slot + TM_O + 64, dp + 2 * ks, dv16 + ((ks * 512) >> 4), id_O16, (j | ks) != 0);
+          if (GLOB_PTMEM) {
+            int ps = qs + ks;   // ring slot of quarter ks of block j
+            ps -= (ps >= 6) ? 6 : 0;
+            const uint32_t pa = slot + TM_P + static_cast<uint32_t>(ps * 8);
+            ptx::mma_f16_ts(slot + TM_O, pa, dv64 + ((ks * 2048) >> 4), id_O64, (j | ks) != 0);
+            if (kTail) ptx::mma_f16_ts(slot + TM_O + 64, pa, dv16 + ((ks * 512) >> 4), id_O16, (j | ks) != 0);
+          } else {
+            ptx::mma_f16_ss(slot + TM_O, dp + 2 * ks, dv64 + ((ks * 2048) >> 4), id_O64, (j | ks) != 0);
+            if (kTail) ptx::mma_f16_ss(slot + TM_O + 64, dp + 2 * ks, dv16 + ((ks * 512) >> 4), id_O16, (j | ks) != 0);
+          }
         }
         ptx::mma_commit(&pv_done[g * 2 + bf]);
         ptx::mma_commit(&v_free[s]);   // V(j) consumed by this tile (count 2)
@@ -370,7 +422,7 @@ glob_attn3_kernel(const __grid_constant__ GlobAttnMaps3 maps, const uint16_t* __
     const int qh = qh0 + g * 2 + (row >> 6);
     const int qw = row & 63;
     const float kLog2e = 1.4426950408889634f;
-    float relw[64];   // rel_w[kw] * log2e
+    float relw[64];   // rel_w[kw] * log2e  (GLOB_PRELOAD: rel_w[kw] / scale, the value preloaded into S)
     ptx::mbar_wait(&t_full[g], 0);
     ptx::tc_fence_after();
     {
@@ -386,7 +438,7 @@ glob_attn3_kernel(const __grid_constant__ GlobAttnMaps3 maps, const uint16_t* __
       }
       const float* src = st + (63 - qw);
 #pragma unroll
-      for (int i = 0; i < 64; ++i) relw[i] = src[i] * kLog2e;
+      for (int i = 0; i < 64; ++i) relw[i] = GLOB_PRELOAD ? src[i] * (kLog2e / scale_log2e) : src[i] * kLog2e;
       // rel_h: 64 consecutive T_h columns starting at a warp-uniform offset
       const uint32_t th_col = TM_O + static_cast<uint32_t>(63 - qh - th_start);
       uint32_t* relh_w = reinterpret_cast<uint32_t*>(smem + OFF_RELH) + g * 128 + row;
@@ -402,18 +454,28 @@ glob_attn3_kernel(const __grid_constant__ GlobAttnMaps3 maps, const uint16_t* __
         }
       }
     }
+    if (GLOB_PRELOAD) {
+      // both S buffers <- rel_w / scale (T_w has been read out of these columns above)
+      store_relw(trow, relw);
+      store_relw(trow + 64, relw);
+      tmem_st_wait();
+    }
     ptx::tc_fence_before();
     ptx::fence_proxy_async_smem();   // generic-proxy staging stores vs. the TMA writes of K / V into the same bytes
     ptx::mbar_arrive(pro_done);
 
     float m_ref = 0.f;   // reference maximum (log2 domain) all stored probabilities are relative to
     float l = 0.f;       // running row sum relative to m_ref
+    int qs = 0;          // GLOB_PTMEM: ring slot of quarter 0 of block j = 4 j mod 6
 #pragma unroll 1
-    for (int j = 0; j < kNBlk; ++j) {
+    for (int j = 0; j < kNBlk; ++j, qs = (qs >= 2) ? qs - 2 : qs + 4) {
       const int bf = j & 1;
       const uint32_t ph = (j >> 1) & 1;
       const uint32_t ts = trow + bf * 64;
-      const uint32_t prow = (sbase + OFF_P + (g * 2 + bf) * 16384 + row * 128) ^ (sw << 4);   // 128-byte aligned row
+      const uint32_t prow = GLOB_PTMEM ? trow + TM_P
+                                       : ((sbase + OFF_P + (g * 2 + bf) * 16384 + row * 128) ^ (sw << 4));   // 128-byte aligned row
+      uint64_t* const pv_prev = (GLOB_PTMEM && j >= 1) ? &pv_done[g * 2 + (bf ^ 1)] : nullptr;
+      const uint32_t pv_prev_parity = ((j - 1) >> 1) & 1;
       // explicit ld.shared: through the generic pointer this was S2UR SR_SWINHI + 64-bit address arithmetic + LD.E at
       // the head of every block (ncu: 7 % of the loop's stall samples)
       uint32_t rh_bits;
@@ -425,7 +487,7 @@ glob_attn3_kernel(const __grid_constant__ GlobAttnMaps3 maps, const uint16_t* __
       f32x2 bsum2 = 0ull;
       float bm = 0.f;
       if (j == 0) {
-        block_pass<1, FMT>(ts, relw, rh, scale_log2e, prow, bsum2, bm);
+        block_pass<1, FMT>(ts, relw, rh, scale_log2e, prow, qs, pv_prev, pv_prev_parity, bsum2, bm);
         m_ref = bm;
       }
       if (j >= 2) {
@@ -433,9 +495,9 @@ glob_attn3_kernel(const __grid_constant__ GlobAttnMaps3 maps, const uint16_t* __
       }
       rh -= m_ref;
 #ifdef GLOB_DIAG
-      if (g == 1 || GLOB_DIAG == 2) block_pass<0, FMT, 1>(ts, relw, rh, scale_log2e, prow, bsum2, bm); else
+      if (g == 1 || GLOB_DIAG == 2) block_pass<0, FMT, 1>(ts, relw, rh, scale_log2e, prow, qs, pv_prev, pv_prev_parity, bsum2, bm); else
 #endif
-      block_pass<0, FMT>(ts, relw, rh, scale_log2e, prow, bsum2, bm);
+      block_pass<0, FMT>(ts, relw, rh, scale_log2e, prow, qs, pv_prev, pv_prev_parity, bsum2, bm);
       float s0, s1;
       upk2(bsum2, s0, s1);
       float bsum = s0 + s1;
@@ -443,7 +505,7 @@ glob_attn3_kernel(const __grid_constant__ GlobAttnMaps3 maps, const uint16_t* __
         // rare: some row of this warp has logits far above its reference.  Move the reference to the block maximum,
         // rescale the accumulated O row and row sum, and redo the block (S is still in its TMEM buffer).  (j == 0 never
         // gets here: its reference is its own maximum, so bsum <= 64.)
-        block_pass<1, FMT>(ts, relw, rh, scale_log2e, prow, bsum2, bm);
+        block_pass<1, FMT>(ts, relw, rh, scale_log2e, prow, qs, pv_prev, pv_prev_parity, bsum2, bm);
         const float delta = fmaxf(bm, 0.f);
         const float alpha = ex2(-delta);
         m_ref += delta;
@@ -462,14 +524,16 @@ glob_attn3_kernel(const __grid_constant__ GlobAttnMaps3 maps, const uint16_t* __
         }
         tmem_st_wait();
         bsum2 = 0ull;
-        block_pass<0, FMT>(ts, relw, rh, scale_log2e, prow, bsum2, bm);
+        block_pass<0, FMT>(ts, relw, rh, scale_log2e, prow, qs, pv_prev, pv_prev_parity, bsum2, bm);
         upk2(bsum2, s0, s1);
         bsum = s0 + s1;
       }
       l += bsum;
+      if (GLOB_PRELOAD) store_relw(ts, relw);   // this S buffer is read out: re-arm it for Q.K^T of block j + 2
+      if (GLOB_PRELOAD || GLOB_PTMEM) tmem_st_wait();   // ... and the P quarters of this block
       ptx::tc_fence_before();
       ptx::mbar_arrive(&s_free[g * 2 + bf]);
-      ptx::fence_proxy_async_smem();
+      if (!GLOB_PTMEM) ptx::fence_proxy_async_smem();
       ptx::mbar_arrive(&p_ready[g * 2 + bf]);
     }
     // epilogue: O / l -> out
