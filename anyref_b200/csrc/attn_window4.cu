@@ -55,7 +55,30 @@ struct WinAttnMaps4 {
   CUtensorMap qa64, qa16;    // box {64|16, 14, 9, 1}   query tile 0
   CUtensorMap qb64, qb16;    // box {64|16, 14, 5, 1}   query tile 1
   CUtensorMap r64, r16;      // rel-pos operand table [64, 80]: box {64|16, 64}
+  CUtensorMap oa64, oa16;    // WIN4_TMA_OUT: the query-tile boxes over `out` [B, 64, 64, E] (stores clip the padded rows)
+  CUtensorMap ob64, ob16;
 };
+
+// Output through shared memory + TMA stores: every softmax thread parks its normalised O row in the tile's (dead) Q
+// buffer of the stage, in the layout the Q load used, and one thread per tile issues 4-D bulk tensor stores with the
+// load's box -- rows of padded window tokens fall outside the tensor and are clipped.  Replaces ten STG.128 per thread
+// whose warp-level instructions touched 32 different half sectors each (ncu: the item loop stalled ~1200 cycles per
+// item until those stores had drained).  The stage's Q / K buffers are handed back to the producer when the store has
+// READ the staging rows (checked at the top of the next item), not right after the rel-pos gather.
+#ifndef WIN4_TMA_OUT
+#define WIN4_TMA_OUT 1
+#endif
+__device__ __forceinline__ void named_bar_sync4(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(m),
+               "r"(ptx::smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit4() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all4() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all4() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 using ptx::add2;
 using ptx::f32x2;
@@ -233,7 +256,7 @@ win_attn4_kernel(const __grid_constant__ WinAttnMaps4 maps, const uint16_t* __re
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&qk_full[s], 1);
       ptx::mbar_init(&qk_ready[s], 1);
-      ptx::mbar_init(&qk_free[s], 2 + 256);
+      ptx::mbar_init(&qk_free[s], WIN4_TMA_OUT ? 2 + 2 : 2 + 256);
       ptx::mbar_init(&v_full[s], 1);
       ptx::mbar_init(&v_ready[s], 1);
       ptx::mbar_init(&v_free[s], 2);
@@ -430,6 +453,11 @@ win_attn4_kernel(const __grid_constant__ WinAttnMaps4 maps, const uint16_t* __re
       const Item w = decode_item(it, heads);
       const int s = n & 1;
       const uint32_t ph = n & 1;
+      if (WIN4_TMA_OUT && n > 0 && (warp & 3) == 2 && lane == 0) {
+        // the previous item's output store has read its staging rows: that stage's Q / K may be overwritten
+        bulk_wait_read_all4();
+        ptx::mbar_arrive(&qk_free[s ^ 1]);
+      }
       ptx::mbar_wait(&s_full[g], ph);
       ptx::tc_fence_after();
       float relh[WS], relw[WS];
@@ -462,8 +490,10 @@ win_attn4_kernel(const __grid_constant__ WinAttnMaps4 maps, const uint16_t* __re
       // the scratch stores above went through the generic proxy; the producer's next TMA into this stage writes the
       // same bytes through the async proxy.  Without this fence a late scratch store can land on top of the freshly
       // loaded Q rows (seen as a few wrong rows of one item in ~4 % of stress runs).
-      ptx::fence_proxy_async_smem();
-      ptx::mbar_arrive(&qk_free[s]);   // Q / K of this stage may be overwritten (count 2 MMA commits + 256 threads)
+      if (!WIN4_TMA_OUT) {
+        ptx::fence_proxy_async_smem();
+        ptx::mbar_arrive(&qk_free[s]);   // Q / K of this stage may be overwritten (count 2 MMA commits + 256 threads)
+      }
 
       f32x2 s0 = 0ull, s1 = 0ull;
       {
@@ -517,7 +547,32 @@ win_attn4_kernel(const __grid_constant__ WinAttnMaps4 maps, const uint16_t* __re
         const float inv = 1.0f / sum;
         const int y = w.wy * WS + qiy, x = w.wx * WS + qix;
         const bool ok = (row < nq) && (y < 64) && (x < 64);
-        if (ok) {
+        if (WIN4_TMA_OUT) {
+          uint8_t* st = smem + s * kStageBytes;
+          if (row < nq) {
+#pragma unroll
+            for (int c = 0; c < kU4; ++c) {
+              const uint32_t* v = (c < 4) ? &o0[c * 8] : (c < 8) ? &o1[(c - 4) * 8] : &o2[(c - 8) * 8];
+              uint4 u;
+              u.x = ptx::pack2t<FMT>(__uint_as_float(v[0]) * inv, __uint_as_float(v[1]) * inv);
+              u.y = ptx::pack2t<FMT>(__uint_as_float(v[2]) * inv, __uint_as_float(v[3]) * inv);
+              u.z = ptx::pack2t<FMT>(__uint_as_float(v[4]) * inv, __uint_as_float(v[5]) * inv);
+              u.w = ptx::pack2t<FMT>(__uint_as_float(v[6]) * inv, __uint_as_float(v[7]) * inv);
+              if (c < 8)
+                *reinterpret_cast<uint4*>(st + OFF_Q64 + g * 16384 + row_off64(row, c)) = u;
+              else
+                *reinterpret_cast<uint4*>(st + OFF_Q16 + g * 4096 + row_off16(row, c - 8)) = u;
+            }
+          }
+          ptx::fence_proxy_async_smem();   // staging rows (and the gather scratch before them) -> async proxy
+          named_bar_sync4(1 + g, 128);
+          if ((warp & 3) == 2 && lane == 0) {
+            const int co = w.head * HD, x0 = w.wx * WS, y0 = w.wy * WS + (g ? 9 : 0);
+            tma_store_4d(g ? &maps.ob64 : &maps.oa64, st + OFF_Q64 + g * 16384, co, x0, y0, w.b);
+            if (kTail) tma_store_4d(g ? &maps.ob16 : &maps.oa16, st + OFF_Q16 + g * 4096, co + 64, x0, y0, w.b);
+            bulk_commit4();
+          }
+        } else if (ok) {
           uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<size_t>(w.b) * 4096 + (y * 64 + x)) * E + w.head * HD);
 #pragma unroll
           for (int c = 0; c < kU4; ++c) {
@@ -534,6 +589,7 @@ win_attn4_kernel(const __grid_constant__ WinAttnMaps4 maps, const uint16_t* __re
     }
   }
 
+  if (WIN4_TMA_OUT && warp >= 2 && warp <= 9 && (warp & 3) == 2 && lane == 0) bulk_wait_all4();   // output stores landed
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -563,6 +619,18 @@ int samk_attn_window4(const void* qkv, const void* bias_op, const void* rel_tab,
     const uint32_t box[4] = {s.c, 14, s.rows, 1};
     int rc = samhost::encode_tmap_nd(s.m, 2, is_bf16, qkv, 4, dims, strides, box, s.swz);
     if (rc) return rc;
+  }
+  {
+    const uint64_t ldo = static_cast<uint64_t>(E) * 2;   // bytes per output token row
+    const uint64_t odims[4] = {static_cast<uint64_t>(E), 64, 64, static_cast<uint64_t>(B)};
+    const uint64_t ostrides[4] = {2, ldo, 64 * ldo, 4096 * ldo};
+    struct { CUtensorMap* m; uint32_t c, rows; int swz; } ospecs[4] = {
+        {&maps.oa64, 64, 9, 3}, {&maps.oa16, 16, 9, 1}, {&maps.ob64, 64, 5, 3}, {&maps.ob16, 16, 5, 1}};
+    for (auto& s : ospecs) {
+      const uint32_t box[4] = {s.c, 14, s.rows, 1};
+      int rc = samhost::encode_tmap_nd(s.m, 2, is_bf16, out, 4, odims, ostrides, box, s.swz);
+      if (rc) return rc;
+    }
   }
   int rc = samhost::encode_tmap_2d(&maps.r64, 2, is_bf16, rel_tab, HD, 64, HD * 2, 64, 64, 3);
   if (rc) return rc;
