@@ -36,6 +36,25 @@ ENC_FLOP_PER_IMAGE = 5_961_082_830_848          # reference-executed
 ENC_FLOP_PER_IMAGE_USEFUL = 5_641_808_642_048   # padded window rows skipped (what this implementation executes)
 DEC_FLOP_PER_PROMPT = 3_608_291_328
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout() -> None:
+    """Keep stdout to the ONE JSON line: native libraries write there too (NCCL prints its version banner on fd 1 when
+    NCCL_DEBUG >= VERSION, which a box may set in a config file rather than the environment).  fd 1 is pointed at
+    stderr for the rest of the process and the JSON line goes to a duplicate of the original stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def _emit(line: dict) -> None:
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
 
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -157,7 +176,7 @@ def run_reference(args):
         "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
     return 0
 
 
@@ -236,6 +255,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the golden-vector parity check after the timing")
     args = ap.parse_args()
+    _claim_stdout()
     if args.impl == "reference":
         return run_reference(args)
     if args.warmup < 3:
@@ -406,7 +426,7 @@ def main():
             "other_operand_format": alt,
             "cpu_baseline": cpu_baseline,
         }
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
