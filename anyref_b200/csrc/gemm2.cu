@@ -154,6 +154,35 @@ __device__ __forceinline__ void bulk_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 
+// xb rows of a 32 x 32 chunk (64 bytes per row, one row per lane) as FULL 32-byte sectors: lanes 2k / 2k+1 swap halves so
+// that instruction i of the pair covers one whole sector of one row (lane 2k: bytes [32 j, +16), lane 2k+1: the next 16)
+// instead of a half sector of each of its own row -- half as many L1/L2 write requests for the same bytes.
+#ifndef GEMM2_XB_PAIR
+#define GEMM2_XB_PAIR 1
+#endif
+template <typename StoreFn>
+__device__ __forceinline__ void store_xb_paired(uint16_t* xb_base /* row of lane 0 of the warp */, int ldxb, int lane,
+                                                const uint4 (&u)[4], StoreFn&& store) {
+  const bool odd = lane & 1;
+  // the even lane sends its units 1, 3 and receives the odd lane's units 0, 2; the odd lane the other way round
+  uint4 r0, r1;
+  {
+    const uint4 s0 = odd ? u[0] : u[1], s1 = odd ? u[2] : u[3];
+    r0.x = __shfl_xor_sync(0xffffffffu, s0.x, 1); r0.y = __shfl_xor_sync(0xffffffffu, s0.y, 1);
+    r0.z = __shfl_xor_sync(0xffffffffu, s0.z, 1); r0.w = __shfl_xor_sync(0xffffffffu, s0.w, 1);
+    r1.x = __shfl_xor_sync(0xffffffffu, s1.x, 1); r1.y = __shfl_xor_sync(0xffffffffu, s1.y, 1);
+    r1.z = __shfl_xor_sync(0xffffffffu, s1.z, 1); r1.w = __shfl_xor_sync(0xffffffffu, s1.w, 1);
+  }
+  // ra = the even lane's row, rb = the odd lane's row; this lane writes 16-byte unit (odd ? 1 : 0) of both sectors of both
+  uint16_t* ra = xb_base + static_cast<size_t>(lane & ~1) * ldxb;
+  uint16_t* rb = ra + ldxb;
+  const int h = odd ? 1 : 0;
+  store(reinterpret_cast<uint4*>(ra) + 0 + h, odd ? r0 : u[0]);   // ra sector 0: even u0 | even u1 (received by odd)
+  store(reinterpret_cast<uint4*>(ra) + 2 + h, odd ? r1 : u[2]);   // ra sector 1: even u2 | even u3
+  store(reinterpret_cast<uint4*>(rb) + 0 + h, odd ? u[1] : r0);   // rb sector 0: odd u0 (received by even) | odd u1
+  store(reinterpret_cast<uint4*>(rb) + 2 + h, odd ? u[3] : r1);   // rb sector 1: odd u2 | odd u3
+}
+
 // exact-erf GELU (common.py:18) with erfc from Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7, far below the 16-bit
 // rounding of the stored activation).  Uses  x*Phi(x) = max(x,0) - 0.5*|x|*erfc(|x|/sqrt2)  so no sign handling is
 // needed; raw MUFU ex2 / rcp (ftz) -- their arguments are always in range -- 15 instructions per element.
@@ -407,14 +436,20 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             bulk_commit();
           }
           if (valid) {
+            uint4 ub[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              uint4 u;
-              u.x = ptx::pack2(__uint_as_float(v[8 * i + 0]), __uint_as_float(v[8 * i + 1]), p.xb_fmt);
-              u.y = ptx::pack2(__uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3]), p.xb_fmt);
-              u.z = ptx::pack2(__uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5]), p.xb_fmt);
-              u.w = ptx::pack2(__uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7]), p.xb_fmt);
-              reinterpret_cast<uint4*>(xb_row)[i] = u;
+              ub[i].x = ptx::pack2(__uint_as_float(v[8 * i + 0]), __uint_as_float(v[8 * i + 1]), p.xb_fmt);
+              ub[i].y = ptx::pack2(__uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3]), p.xb_fmt);
+              ub[i].z = ptx::pack2(__uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5]), p.xb_fmt);
+              ub[i].w = ptx::pack2(__uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7]), p.xb_fmt);
+            }
+            if (GEMM2_XB_PAIR) {
+              store_xb_paired(xb_row - static_cast<size_t>(lane) * p.ldxb, p.ldxb, lane, ub,
+                              [](uint4* dst, const uint4& val) { *dst = val; });
+            } else {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(xb_row)[i] = ub[i];
             }
             if (c == 3) {
               const int tile = cluster_id + (q >> 2) * num_clusters;
@@ -516,15 +551,23 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             bulk_commit();
           }
           buf ^= 1;
+          uint4 ub[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            uint4 u;
-            u.x = ptx::pack2(xr[2 * i].x, xr[2 * i].y, p.xb_fmt);
-            u.y = ptx::pack2(xr[2 * i].z, xr[2 * i].w, p.xb_fmt);
-            u.z = ptx::pack2(xr[2 * i + 1].x, xr[2 * i + 1].y, p.xb_fmt);
-            u.w = ptx::pack2(xr[2 * i + 1].z, xr[2 * i + 1].w, p.xb_fmt);
-            if (p.l2hint) st_global_v4_hint(reinterpret_cast<uint4*>(xb_row) + i, u, pol_stream);
-            else reinterpret_cast<uint4*>(xb_row)[i] = u;
+            ub[i].x = ptx::pack2(xr[2 * i].x, xr[2 * i].y, p.xb_fmt);
+            ub[i].y = ptx::pack2(xr[2 * i].z, xr[2 * i].w, p.xb_fmt);
+            ub[i].z = ptx::pack2(xr[2 * i + 1].x, xr[2 * i + 1].y, p.xb_fmt);
+            ub[i].w = ptx::pack2(xr[2 * i + 1].z, xr[2 * i + 1].w, p.xb_fmt);
+          }
+          const bool hint = p.l2hint != 0;
+          auto store = [&](uint4* dst, const uint4& val) {
+            if (hint) st_global_v4_hint(dst, val, pol_stream); else *dst = val;
+          };
+          if (GEMM2_XB_PAIR) {
+            store_xb_paired(xb_row - static_cast<size_t>(lane) * p.ldxb, p.ldxb, lane, ub, store);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) store(reinterpret_cast<uint4*>(xb_row) + i, ub[i]);
           }
           if (c == 3) {
             const int tile = cluster_id + (q >> 2) * num_clusters;
