@@ -128,7 +128,8 @@ class CpuOracle:
         from oracle import sam_oracle as O
 
         self.O = O
-        self.cfg = CONFIGS["vit_h"]
+        # ANYREF_BENCH_TEST_CONFIG: contract tests of the JSON line run the CPU arm on a small encoder (never set by the driver)
+        self.cfg = CONFIGS[os.environ.get("ANYREF_BENCH_TEST_CONFIG", "vit_h")]
         torch.set_num_threads(os.cpu_count() or 1)
         self.threads = torch.get_num_threads()
         self.sd = synthetic_state_dict(self.cfg, seed=1234)
