@@ -5,6 +5,7 @@ There is deliberately no fallback: if the library is missing or a call fails, a 
 from __future__ import annotations
 
 import ctypes as C
+import functools
 import os
 from pathlib import Path
 
@@ -128,6 +129,44 @@ def stream_ptr(device=None) -> int:
     import torch
 
     return torch.cuda.current_stream(device).cuda_stream
+
+
+def _first_cuda_device(objs, depth: int = 0):
+    import torch
+
+    for o in objs:
+        if isinstance(o, torch.Tensor):
+            if o.is_cuda:
+                return o.device
+        elif isinstance(o, torch.nn.Module):
+            for t in o.parameters():
+                return t.device if t.is_cuda else None
+            for t in o.buffers():
+                return t.device if t.is_cuda else None
+        elif isinstance(o, (list, tuple)) and depth < 2:
+            d = _first_cuda_device(o, depth + 1)
+            if d is not None:
+                return d
+    return None
+
+
+def device_scoped(fn):
+    """Decorator for every Python entry point that ends in a C-ABI call: the library launches on the CURRENT device
+    (kernel attributes, tensor maps and streams are per device), so the device of the first CUDA tensor argument (or
+    of the module's parameters) is made current for the duration of the call -- a model on cuda:1 works while cuda:0 is
+    current, as with the reference's PyTorch modules."""
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        import torch
+
+        dev = _first_cuda_device(list(args[1:]) + list(kwargs.values()) + list(args[:1]))
+        if dev is None or dev.index is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+
+    return wrapper
 
 
 FMT_F16, FMT_BF16, FMT_F32 = 0, 1, 2

@@ -927,13 +927,13 @@ int samk_decoder_forward(const SamDecoderShape& s, const float* blob, const void
                                                                 n, nm, k, C);
     SAM_CHECK_CUDA(cudaGetLastError());
   }
-  static bool attr_done = false;
+  static samhost::PerDeviceOnce attr_once;
   const int t2i_smem = (TQ * HW + 16 * TQ * 16 + TQ * 16 + 64 + TQ) * sizeof(float);
   const int self_smem = (3 * TMAX * C + s.heads * TMAX * TMAX) * sizeof(float);
-  if (!attr_done) {
+  if (attr_once.need()) {
     SAM_CHECK_CUDA(cudaFuncSetAttribute(dec_attn_t2i_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     SAM_CHECK_CUDA(cudaFuncSetAttribute(dec_self_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, self_smem));
-    attr_done = true;
+    attr_once.done();
   }
   SAM_REQUIRE(t2i_smem <= 200 * 1024, "mask decoder: embedding grid %d too large for the token->image kernel", g);
 

@@ -216,10 +216,10 @@ int launch_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, in
   if (rc) return rc;
   rc = samhost::encode_tmap_2d(&tmB, 2, is_bf16, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw * 2, BK, BN, 3);
   if (rc) return rc;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static samhost::PerDeviceOnce attr_once;
+  if (attr_once.need()) {
     SAM_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
-    attr_done = true;
+    attr_once.done();
   }
   const int m_tiles = (M + BM - 1) / BM, n_tiles = (N + BN - 1) / BN;
   int grid = m_tiles * n_tiles;

@@ -774,13 +774,13 @@ int samk_gemm2(const void* A, int lda, const void* W, int ldw, int M, int N, int
   static const KernelFn kernels[3][2][2] = {{{gemm2_kernel<0, 0, 0>, gemm2_kernel<0, 0, 1>}, {gemm2_kernel<0, 1, 0>, gemm2_kernel<0, 1, 1>}},
                                             {{gemm2_kernel<1, 0, 0>, gemm2_kernel<1, 0, 1>}, {gemm2_kernel<1, 1, 0>, gemm2_kernel<1, 1, 1>}},
                                             {{gemm2_kernel<2, 0, 0>, gemm2_kernel<2, 0, 1>}, {gemm2_kernel<2, 1, 0>, gemm2_kernel<2, 0, 1>}}};
-  static bool attr_done = false;
-  if (!attr_done) {
+  static samhost::PerDeviceOnce attr_once;
+  if (attr_once.need()) {
     for (int a = 0; a < 3; ++a)
       for (int b = 0; b < 2; ++b)
         for (int c = 0; c < 2; ++c)
           SAM_CHECK_CUDA(cudaFuncSetAttribute(kernels[a][b][c], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2));
-    attr_done = true;
+    attr_once.done();
   }
   if (ep.act != 0 && ep.act != 1) return -1;
   const KernelFn kernel = kernels[ep.out_fmt][ep.act][(ln_consumer || ln_producer) ? 1 : 0];
@@ -814,7 +814,8 @@ int samk_gemm2(const void* A, int lda, const void* W, int ldw, int M, int N, int
   int clusters = m_tiles * n_tiles;
   // persistent kernel: never launch more CTA pairs than can be co-resident (GPCs with an odd number of free SMs make
   // this smaller than sm_count / 2), otherwise the late pairs serialise behind the early ones
-  static int max_clusters = 0;
+  static int max_clusters_dev[64] = {0};   // per device
+  int& max_clusters = max_clusters_dev[samhost::device_slot()];
   if (max_clusters == 0) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(samhost::sm_count());

@@ -358,10 +358,11 @@ int samk_layernorm_rows(const float* x, int ldx, const float* res, int ldr, cons
   if (!no_stream && normalize && !res && M >= 8192 && M % kLnGroup == 0 && (C * 4) % 16 == 0 && ldx == C &&
       (reinterpret_cast<uintptr_t>(x) & 15) == 0 && x != out) {
     const int smem = kLnStages * kLnGroup * C * 4 + 2 * kLnStages * 8;
-    static int smem_set = 0;
-    if (smem > smem_set) {
+    static int smem_set[64] = {0};   // per device (function attributes are per device)
+    const int slot = samhost::device_slot();
+    if (smem > smem_set[slot]) {
       SAM_CHECK_CUDA(cudaFuncSetAttribute(layernorm_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      smem_set = smem;
+      smem_set[slot] = smem;
     }
     int grid = 2 * samhost::sm_count();
     layernorm_stream_kernel<<<grid, 32 * (kLnConsumerWarps + 1), smem, stream>>>(x, gamma, beta, eps, out, ldo, out_fmt, M, C);

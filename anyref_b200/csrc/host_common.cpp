@@ -75,13 +75,37 @@ int encode_tmap_2d(CUtensorMap* out, int elem_bytes, int is_bf16, const void* ba
   return encode_tmap_nd(out, elem_bytes, is_bf16, base, 2, dims, strides, box, swizzle);
 }
 
+int device_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  return dev < 0 ? 0 : (dev > 63 ? 63 : dev);
+}
+
 int sm_count() {
-  static int n = 0;
+  static std::atomic<int> cache[64];
+  const int slot = device_slot();
+  int n = cache[slot].load(std::memory_order_relaxed);
   if (n) return n;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 148;
   if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  cache[slot].store(n, std::memory_order_relaxed);
   return n;
+}
+
+namespace {
+std::mutex g_once_mu;
+}
+bool PerDeviceOnce::need() const {
+  std::lock_guard<std::mutex> lk(g_once_mu);
+  return ((mask_ >> device_slot()) & 1ull) == 0;
+}
+void PerDeviceOnce::done() {
+  std::lock_guard<std::mutex> lk(g_once_mu);
+  mask_ |= 1ull << device_slot();
 }
 
 // ------------------------------------------------------------------------------------------------- launch accounting

@@ -32,7 +32,19 @@ int encode_tmap_2d(CUtensorMap* out, int elem_bytes, int is_bf16, const void* ba
 int encode_tmap_nd(CUtensorMap* out, int elem_bytes, int is_bf16, const void* base, int rank, const uint64_t* dims,
                    const uint64_t* strides_bytes, const uint32_t* box, int swizzle);
 
+// SM count of the CURRENT device (cached per device).
 int sm_count();
+// Ordinal of the current device clamped to [0, 63] (per-device caches are small fixed arrays).
+int device_slot();
+
+// Per-device one-time initialisation (cudaFuncSetAttribute opt-ins, occupancy queries): function attributes belong to
+// the device that is current when they are set, so a process-wide `static bool` would leave every other GPU of the
+// process without the opt-in.   if (once.need()) { ...; once.done(); }
+struct PerDeviceOnce {
+  bool need() const;
+  void done();
+  unsigned long long mask_ = 0;
+};
 
 // ---------------------------------------------------------------------------------------------------------------
 // Launch accounting + optional per-kernel-class timing (bench.py: `gpu_launches` and the roofline leg).

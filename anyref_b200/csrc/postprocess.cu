@@ -1,13 +1,22 @@
 // Sam.postprocess_masks (sam.py:159-172) as ONE kernel: bilinear L x L -> S x S (align_corners=False), crop to
 // input_size, bilinear -> original_size, optional thresholding (Sam.mask_threshold, sam.py:19;
-// eval_referseg.py:191 sigmoid(x) > 0.5 == x > 0).  The [n,C,S,S] intermediate of the reference never exists: every
-// output pixel evaluates its 4 stage-2 taps on the fly, each from 4 low-resolution taps (the 256 KB low-res mask
-// stays in L1/L2).  HBM traffic = read L*L*4 + write H*W*4 bytes per mask (the algorithmic minimum).
+// eval_referseg.py:191 sigmoid(x) > 0.5 == x > 0).  The [n,C,S,S] intermediate of the reference never exists.
+// HBM traffic = read L*L*4 + write H*W*4 bytes per mask (the algorithmic minimum).
+//
+// "Column walker": a thread owns ONE output column X and walks a strip of output rows.  Both resizes are separable
+// in exactly the order ATen evaluates them (horizontal lerp of the two source rows, then the vertical lerp), so the
+// thread keeps, in registers,
+//   * the horizontal lerps h(i) of the two most recent LOW-RES rows at its two stage-1 columns (4 loads per new
+//     low-res row -- one every four stage-1 rows),
+//   * the stage-2 horizontal lerps g(y) of the two most recent STAGE-1 rows y,
+// and an output pixel costs one vertical lerp + one coalesced store.  All cache decisions depend on the row only, so
+// they are warp-uniform; arbitrary scales (up- and down-sampling, crop) take the same code and simply reuse less.
+// Round 1 re-derived 4 stage-1 values (16 taps, 16 loads) per output pixel: LSU-bound at 5 % of the HBM rate.
 //
 // Tap arithmetic follows ATen's area_pixel_compute_source_index (scale = in/out in fp32,
 // src = max(0, scale*(dst+0.5)-0.5) evaluated as ONE fused multiply-add, which is what both ATen's vectorised CPU
 // kernel and its CUDA kernel compile to; i1 = i0 + (i0 < in-1)), so tap INDICES are exact with the reference and
-// values agree to fp32 rounding.
+// values agree to fp32 rounding (products and sums are kept un-fused in ATen's order).
 #include "host_common.h"
 #include "kernels.h"
 #include "ptx.cuh"
@@ -29,10 +38,9 @@ __device__ __forceinline__ Tap make_tap(int dst, float scale, int in_size) {
   return t;
 }
 
-__device__ __forceinline__ float lerp2(float a00, float a01, float a10, float a11, const Tap& ty, const Tap& tx) {
-  const float top = __fadd_rn(__fmul_rn(tx.l0, a00), __fmul_rn(tx.l1, a01));
-  const float bot = __fadd_rn(__fmul_rn(tx.l0, a10), __fmul_rn(tx.l1, a11));
-  return __fadd_rn(__fmul_rn(ty.l0, top), __fmul_rn(ty.l1, bot));
+// l0 * a + l1 * b with separately rounded products (ATen's order; no FMA contraction)
+__device__ __forceinline__ float lerp1(float l0, float a, float l1, float b) {
+  return __fadd_rn(__fmul_rn(l0, a), __fmul_rn(l1, b));
 }
 
 __device__ __forceinline__ float ld(const void* p, int fmt, size_t i) {
@@ -40,103 +48,115 @@ __device__ __forceinline__ float ld(const void* p, int fmt, size_t i) {
   return ptx::unpack1(__ldg(static_cast<const uint16_t*>(p) + i), fmt);
 }
 
-// value of the S x S stage-1 image at (yy, xx)
-__device__ __forceinline__ float stage1(const void* low, int fmt, size_t base, int L, float scale1, int yy, int xx) {
-  const Tap ty = make_tap(yy, scale1, L), tx = make_tap(xx, scale1, L);
-  const float a00 = ld(low, fmt, base + static_cast<size_t>(ty.i0) * L + tx.i0);
-  const float a01 = ld(low, fmt, base + static_cast<size_t>(ty.i0) * L + tx.i1);
-  const float a10 = ld(low, fmt, base + static_cast<size_t>(ty.i1) * L + tx.i0);
-  const float a11 = ld(low, fmt, base + static_cast<size_t>(ty.i1) * L + tx.i1);
-  return lerp2(a00, a01, a10, a11, ty, tx);
-}
+constexpr int kPostRows = 32;    // output rows per CTA strip
+constexpr int kPostCols = 128;   // output columns per CTA (= threads)
 
-// grid (ceil(W/128), ceil(H/8), n*C), block (128, 1): each thread produces 8 rows? -> keep it simple: 1 pixel/thread
-// with 4-wide vector stores when W % 4 == 0.
+// grid (ceil(W/128), ceil(H/32), num_masks), block 128.
 // With `target` / `counts` the intersectionAndUnionGPU statistics of the thresholded mask (utils/utils.py:79-91, K = 2,
 // ignore_index = 255) are accumulated in the same pass: counts[m] = {inter_0, inter_1, pred_0, pred_1, target_0,
 // target_1} (int32, atomically added), so the evaluation loop (eval_referseg.py:186-211) needs neither the full
 // resolution logits nor the mask in HBM.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kPostCols)
 postprocess_kernel(const void* __restrict__ low, int low_fmt, int L, int S, int h_in, int w_in, int H, int W,
                    float* __restrict__ logits, uint8_t* __restrict__ binary, uint8_t* __restrict__ packed, float threshold,
                    const uint8_t* __restrict__ target, int* __restrict__ counts) {
   const int m = blockIdx.z;
-  const int Y = blockIdx.y * blockDim.y + threadIdx.y;
-  const int X4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  const bool active = (Y < H && X4 < W);
-  if (!active && counts == nullptr && packed == nullptr) return;
-  int cnt[6] = {0, 0, 0, 0, 0, 0};
-  uint32_t nib = 0;      // this thread's 4 thresholded pixels, first pixel in bit 3 (numpy.packbits order)
-  if (active) {
+  const int Xr = blockIdx.x * kPostCols + threadIdx.x;
+  const bool col_ok = Xr < W;
+  const int X = col_ok ? Xr : W - 1;          // out-of-range threads shadow the last column (no stores)
+  const int Y0 = blockIdx.y * kPostRows;
+  const int Y1 = min(Y0 + kPostRows, H);
   const float scale1 = static_cast<float>(L) / static_cast<float>(S);
   const float sy = static_cast<float>(h_in) / static_cast<float>(H);
   const float sx = static_cast<float>(w_in) / static_cast<float>(W);
   const size_t base = static_cast<size_t>(m) * L * L;
-  const Tap ty = make_tap(Y, sy, h_in);
-  float v[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int X = X4 + i;
-    v[i] = 0.f;
-    if (X < W) {
-      const Tap tx = make_tap(X, sx, w_in);
-      const float a00 = stage1(low, low_fmt, base, L, scale1, ty.i0, tx.i0);
-      const float a01 = stage1(low, low_fmt, base, L, scale1, ty.i0, tx.i1);
-      const float a10 = stage1(low, low_fmt, base, L, scale1, ty.i1, tx.i0);
-      const float a11 = stage1(low, low_fmt, base, L, scale1, ty.i1, tx.i1);
-      v[i] = lerp2(a00, a01, a10, a11, ty, tx);
+  // this thread's column taps: stage 2 (X -> stage-1 columns x0, x1), stage 1 (x0, x1 -> low-res columns)
+  const Tap tx = make_tap(X, sx, w_in);
+  const Tap ca = make_tap(tx.i0, scale1, L), cb = make_tap(tx.i1, scale1, L);
+
+  // low-res row cache: horizontal lerps at stage-1 columns x0 (a) and x1 (b)
+  int hr0 = -1, hr1 = -1;
+  float ha0 = 0.f, hb0 = 0.f, ha1 = 0.f, hb1 = 0.f;
+  auto load_h = [&](int i, float& ha, float& hb) {
+    const size_t r = base + static_cast<size_t>(i) * L;
+    ha = lerp1(ca.l0, ld(low, low_fmt, r + ca.i0), ca.l1, ld(low, low_fmt, r + ca.i1));
+    hb = lerp1(cb.l0, ld(low, low_fmt, r + cb.i0), cb.l1, ld(low, low_fmt, r + cb.i1));
+  };
+  // stage-2 horizontal lerp g(y) of stage-1 row y (all branches depend on y only: warp-uniform)
+  auto stage1_row = [&](int y) -> float {
+    const Tap t = make_tap(y, scale1, L);
+    if (t.i0 == hr1) {
+      hr0 = hr1; ha0 = ha1; hb0 = hb1;
+      hr1 = -1;
     }
-  }
-  const size_t o = (static_cast<size_t>(m) * H + Y) * W + X4;
-  if (logits) {
-    if ((W & 3) == 0) {
-      *reinterpret_cast<float4*>(logits + o) = make_float4(v[0], v[1], v[2], v[3]);
-    } else {
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        if (X4 + i < W) logits[o + i] = v[i];
+    if (t.i0 != hr0) {
+      load_h(t.i0, ha0, hb0);
+      hr0 = t.i0;
     }
-  }
-  if (binary) {
-    if ((W & 3) == 0) {
-      uchar4 b;
-      b.x = v[0] > threshold; b.y = v[1] > threshold; b.z = v[2] > threshold; b.w = v[3] > threshold;
-      *reinterpret_cast<uchar4*>(binary + o) = b;
-    } else {
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        if (X4 + i < W) binary[o + i] = v[i] > threshold;
+    float a1 = ha0, b1 = hb0;
+    if (t.i1 != t.i0) {
+      if (t.i1 != hr1) {
+        load_h(t.i1, ha1, hb1);
+        hr1 = t.i1;
+      }
+      a1 = ha1; b1 = hb1;
     }
-  }
-  if (packed)
-    nib = (v[0] > threshold ? 8u : 0u) | (v[1] > threshold ? 4u : 0u) | (v[2] > threshold ? 2u : 0u) | (v[3] > threshold ? 1u : 0u);
-  if (counts) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      if (X4 + i < W) {
-        const int t = target[o + i];
+    const float sa = lerp1(t.l0, ha0, t.l1, a1);     // stage-1 value at (y, x0)
+    const float sb = lerp1(t.l0, hb0, t.l1, b1);     // stage-1 value at (y, x1)
+    return lerp1(tx.l0, sa, tx.l1, sb);
+  };
+  int gr0 = -1, gr1 = -1;
+  float g0 = 0.f, g1 = 0.f;
+  int cnt[6] = {0, 0, 0, 0, 0, 0};
+  const int lane = threadIdx.x & 31;
+#pragma unroll 1
+  for (int Y = Y0; Y < Y1; ++Y) {
+    const Tap ty = make_tap(Y, sy, h_in);
+    if (ty.i0 == gr1) {
+      gr0 = gr1; g0 = g1;
+      gr1 = -1;
+    }
+    if (ty.i0 != gr0) {
+      g0 = stage1_row(ty.i0);
+      gr0 = ty.i0;
+    }
+    float gb = g0;
+    if (ty.i1 != ty.i0) {
+      if (ty.i1 != gr1) {
+        g1 = stage1_row(ty.i1);
+        gr1 = ty.i1;
+      }
+      gb = g1;
+    }
+    const float v = lerp1(ty.l0, g0, ty.l1, gb);
+    const bool on = v > threshold;
+    const size_t o = (static_cast<size_t>(m) * H + Y) * W + X;
+    if (col_ok) {
+      if (logits) logits[o] = v;
+      if (binary) binary[o] = on ? 1 : 0;
+      if (counts) {
+        const int t = target[o];
         if (t != 255) {
-          const int p = v[i] > threshold ? 1 : 0;
-          cnt[2 + p] += 1;
-          if (t < 2) {
-            cnt[4 + t] += 1;
-            if (t == p) cnt[p] += 1;
-          }
+          const int p = on ? 1 : 0;          // static indices only: the counters stay in registers
+          cnt[2] += (p == 0); cnt[3] += (p == 1);
+          cnt[4] += (t == 0); cnt[5] += (t == 1);
+          cnt[0] += (t == 0 && p == 0); cnt[1] += (t == 1 && p == 1);
         }
       }
     }
-  }
-  }  // active
-  if (packed) {
-    // W % 8 == 0 (checked by the launcher): lanes 2k / 2k+1 hold the high / low nibble of one byte of the flattened
-    // [num_masks, H, W] bit stream, both inside the row or both outside it
-    const uint32_t lo = __shfl_down_sync(0xffffffffu, nib, 1);
-    if (active && (threadIdx.x & 1) == 0)
-      packed[((static_cast<size_t>(m) * H + Y) * W + X4) >> 3] = static_cast<uint8_t>((nib << 4) | lo);
+    if (packed) {
+      // numpy.packbits order: pixel 8k of the flattened [num_masks, H, W] stream is the MSB of byte k.  A warp covers 32
+      // consecutive columns = 4 bytes; W % 8 == 0 (checked by the launcher), so a byte is inside the row or outside it.
+      const uint32_t bits = __ballot_sync(0xffffffffu, on && col_ok);
+      const uint32_t bytes = __byte_perm(__brev(bits), 0, 0x0123);
+      const int xb = Xr - lane + 8 * lane;     // first column of byte `lane` (lanes 0..3)
+      if (lane < 4 && xb < W)
+        packed[((static_cast<size_t>(m) * H + Y) * W + xb) >> 3] = static_cast<uint8_t>(bytes >> (8 * lane));
+    }
   }
   if (counts) {
     __shared__ int s_cnt[6];
-    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    const int tid = threadIdx.x;
     if (tid < 6) s_cnt[tid] = 0;
     __syncthreads();
 #pragma unroll
@@ -198,8 +218,8 @@ int samk_postprocess_iou(const void* low, int low_fmt, int num_masks, int L, int
   SAM_REQUIRE((target == nullptr) == (counts == nullptr), "postprocess: target and counts go together");
   SAM_REQUIRE(low_fmt >= 0 && low_fmt <= 2, "postprocess: bad input format");
   SAM_REQUIRE(num_masks <= 65535, "postprocess: at most 65535 masks per call");
-  dim3 blk(64, 4);
-  dim3 grid(((W + 3) / 4 + blk.x - 1) / blk.x, (H + blk.y - 1) / blk.y, num_masks);
+  dim3 blk(kPostCols);
+  dim3 grid((W + kPostCols - 1) / kPostCols, (H + kPostRows - 1) / kPostRows, num_masks);
   samhost::LaunchScope scope(samhost::KC_POSTPROCESS, stream, 0.0,
                              static_cast<double>(num_masks) *
                                  (static_cast<double>(L) * L * (low_fmt == 2 ? 4.0 : 2.0) +

@@ -170,10 +170,10 @@ int samk_umma_probe(const void* A, const void* B, float* D, const UmmaProbe& p, 
   SAM_REQUIRE(p.K % 16 == 0 && p.K >= 16 && p.K <= 256, "probe: bad K %d", p.K);
   SAM_REQUIRE(((p.a_mode >= 0 && p.a_mode <= 2) || p.a_mode == 7) && p.b_mode >= 0 && p.b_mode <= 6, "probe: bad mode");
   const int smem = 65536 + 131072 + 1024;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static samhost::PerDeviceOnce attr_once;
+  if (attr_once.need()) {
     SAM_CHECK_CUDA(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_done = true;
+    attr_once.done();
   }
   umma_probe_kernel<<<1, 128, smem, stream>>>(static_cast<const uint16_t*>(A), static_cast<const uint16_t*>(B), D, p);
   SAM_CHECK_CUDA(cudaGetLastError());

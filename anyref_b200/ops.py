@@ -17,6 +17,7 @@ def _req_cuda(*ts):
             raise RuntimeError("anyref_b200 kernels need CUDA tensors (no CPU fallback)")
 
 
+@_lib.device_scoped
 def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, act: str = "none", residual=None, res_mod: int | None = None,
          out: torch.Tensor | None = None, out_dtype=None) -> torch.Tensor:
     """out[M,N] = epilogue(a[M,K] @ w[N,K]^T); a, w fp16/bf16; bias/residual fp32; see sam_gemm."""
@@ -43,6 +44,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, act: str = "none", resi
     return out
 
 
+@_lib.device_scoped
 def cast_stats(x: torch.Tensor, out_dtype):
     """-> (xb = x.to(out_dtype), stats [M, C/128, 2] fp32 partial (sum, sumsq) per 128-column slice); see sam_cast_stats."""
     _req_cuda(x)
@@ -56,6 +58,7 @@ def cast_stats(x: torch.Tensor, out_dtype):
     return xb, stats
 
 
+@_lib.device_scoped
 def gemm_residual_ln(a: torch.Tensor, w: torch.Tensor, x: torch.Tensor, bias=None, *, xb=None, stats=None):
     """x += a @ w^T + bias in place (fp32); -> (xb = round(x) in a.dtype, stats [M, N/128, 2]); see sam_gemm_residual_ln."""
     _req_cuda(a, w, x, bias)
@@ -72,6 +75,7 @@ def gemm_residual_ln(a: torch.Tensor, w: torch.Tensor, x: torch.Tensor, bias=Non
     return xb, stats
 
 
+@_lib.device_scoped
 def gemm_ln(xb: torch.Tensor, wg: torch.Tensor, bias_fold: torch.Tensor, colsum: torch.Tensor, stats: torch.Tensor,
             eps: float, act: str = "none", out: torch.Tensor | None = None) -> torch.Tensor:
     """act(LN(x) @ W^T + b) from the folded operands (see sam_gemm_ln / segment_anything/_pack.py::_fold_layernorm)."""
@@ -88,6 +92,7 @@ def gemm_ln(xb: torch.Tensor, wg: torch.Tensor, bias_fold: torch.Tensor, colsum:
     return out
 
 
+@_lib.device_scoped
 def umma_probe(a: torch.Tensor, b: torch.Tensor, N: int, K: int, a_mode: int, b_mode: int, a_lbo=-1, a_sbo=-1,
                b_lbo=-1, b_sbo=-1) -> torch.Tensor:
     _req_cuda(a, b)
@@ -99,6 +104,7 @@ def umma_probe(a: torch.Tensor, b: torch.Tensor, N: int, K: int, a_mode: int, b_
     return d
 
 
+@_lib.device_scoped
 def layernorm(x: torch.Tensor, gamma, beta, eps: float, out_dtype, *, residual=None, normalize: bool = True,
               out: torch.Tensor | None = None) -> torch.Tensor:
     """Row LayerNorm of fp32 [M, C] (optionally of x + residual) -> out_dtype; see sam_layernorm."""
@@ -114,6 +120,7 @@ def layernorm(x: torch.Tensor, gamma, beta, eps: float, out_dtype, *, residual=N
     return out
 
 
+@_lib.device_scoped
 def patch_im2col(img: torch.Tensor, patch: int, out_dtype) -> torch.Tensor:
     _req_cuda(img)
     B, ch, S, S2 = img.shape
@@ -126,6 +133,7 @@ def patch_im2col(img: torch.Tensor, patch: int, out_dtype) -> torch.Tensor:
     return out
 
 
+@_lib.device_scoped
 def im2col3x3(x: torch.Tensor, B: int, g: int) -> torch.Tensor:
     _req_cuda(x)
     Cc = x.shape[-1]
@@ -136,6 +144,7 @@ def im2col3x3(x: torch.Tensor, B: int, g: int) -> torch.Tensor:
     return out
 
 
+@_lib.device_scoped
 def ln_nhwc_to_nchw(x: torch.Tensor, gamma, beta, eps: float, B: int, g: int, out_dtype) -> torch.Tensor:
     _req_cuda(x, gamma, beta)
     Cc = x.shape[-1]
@@ -164,6 +173,7 @@ def global_rel_table(rel_pos: torch.Tensor, dtype) -> torch.Tensor:
     return t
 
 
+@_lib.device_scoped
 def attn_window(qkv: torch.Tensor, bias_op: torch.Tensor, rel_tab: torch.Tensor, B: int, heads: int) -> torch.Tensor:
     _req_cuda(qkv, bias_op, rel_tab)
     E = qkv.shape[1] // 3
@@ -175,6 +185,7 @@ def attn_window(qkv: torch.Tensor, bias_op: torch.Tensor, rel_tab: torch.Tensor,
     return out
 
 
+@_lib.device_scoped
 def attn_global(qkv: torch.Tensor, rh_rev: torch.Tensor, rw_rev: torch.Tensor, B: int, heads: int) -> torch.Tensor:
     _req_cuda(qkv, rh_rev, rw_rev)
     E = qkv.shape[1] // 3

@@ -35,6 +35,10 @@ class SegProjection(nn.Sequential):
         super().__init__(nn.Linear(in_dim, in_dim), nn.ReLU(inplace=True), nn.Linear(in_dim, out_dim), nn.Dropout(0.0))
         self._packed = None
 
+    def invalidate_packed(self) -> None:
+        """Drop the cached operand-format weights (see ImageEncoderViT.invalidate_packed)."""
+        self._packed = None
+
     def _weights(self, dt: torch.dtype):
         ps = (self[0].weight, self[0].bias, self[2].weight, self[2].bias)
         key = tuple((p.data_ptr(), p._version, p.dtype) for p in ps) + (dt,)

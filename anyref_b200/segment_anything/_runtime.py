@@ -29,8 +29,11 @@ def release_workspaces() -> None:
 
 
 def params_signature(module: torch.nn.Module):
-    """Cheap fingerprint that changes whenever a parameter/buffer is replaced, moved, cast or written in place
-    (load_state_dict, .to(), .half(), optimizer steps, peft merge)."""
+    """Cheap fingerprint that changes whenever a parameter/buffer is replaced, moved, cast or written in place through
+    autograd-tracked ops (load_state_dict, .to(), .half(), optimizer steps, `p.add_()` / `p.copy_()`).
+    NOT detected: writes through `.data` (`p.data.copy_(w)`, `p.data += d` -- old-style checkpoint loaders and some
+    peft merge code), which keep data_ptr and do not bump `_version`; after such a write call
+    `module.invalidate_packed()` (ImageEncoderViT, MaskDecoder, SegProjection) so the packed weight blobs are rebuilt."""
     sig = []
     for t in list(module.parameters()) + list(module.buffers()):
         sig.append((t.data_ptr(), t._version, t.dtype))

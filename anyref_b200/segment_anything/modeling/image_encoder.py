@@ -148,6 +148,11 @@ class ImageEncoderViT(nn.Module):
         env = os.environ.get("ANYREF_SAM_OPERAND", "bf16").lower()
         return torch.float16 if env in ("fp16", "float16", "half") else torch.bfloat16
 
+    def invalidate_packed(self) -> None:
+        """Drop the packed weight blobs; the next forward re-packs from the current parameters.  Needed only after
+        writes the parameter fingerprint cannot see (`p.data.copy_()`, `p.data += ...`; _runtime.params_signature)."""
+        self._packed = None
+
     def _weights(self, op_dtype):
         fold = self._resolve_ln_fold()
         sig = (_runtime.params_signature(self), op_dtype, fold)
@@ -157,6 +162,7 @@ class ImageEncoderViT(nn.Module):
         return self._packed[1:]
 
     # ------------------------------------------------------------------------------------------------------ forward
+    @_lib.device_scoped
     @torch.no_grad()
     def forward(self, x: torch.Tensor, _tap: Optional[Tuple[int, torch.Tensor]] = None) -> torch.Tensor:
         _runtime.require_cuda(x, "ImageEncoderViT")

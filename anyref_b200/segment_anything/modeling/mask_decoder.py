@@ -61,6 +61,11 @@ class MaskDecoder(nn.Module):
         self.iou_prediction_head = MLP(transformer_dim, iou_head_hidden_dim, self.num_mask_tokens, iou_head_depth)
         self._packed = None
 
+    def invalidate_packed(self) -> None:
+        """Drop the packed / derived weight blobs (see ImageEncoderViT.invalidate_packed)."""
+        self._packed = None
+
+    @_lib.device_scoped
     def _weights(self, grid: int):
         sig = (_runtime.params_signature(self), grid)
         if self._packed is None or self._packed[0] != sig:
@@ -105,6 +110,7 @@ class MaskDecoder(nn.Module):
             return self._predict_masks(image_embeddings, image_pe, sparse_prompt_embeddings, dense_prompt_embeddings,
                                        image_index)
 
+    @_lib.device_scoped
     def _predict_masks(self, image_embeddings, image_pe, sparse_prompt_embeddings, dense_prompt_embeddings, image_index):
         _runtime.require_cuda(image_embeddings, "MaskDecoder")
         lib = _lib.load()

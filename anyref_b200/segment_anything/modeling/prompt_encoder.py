@@ -30,6 +30,7 @@ class PositionEmbeddingRandom(nn.Module):
         self.register_buffer("positional_encoding_gaussian_matrix", scale * torch.randn((2, num_pos_feats)))
         self._cache = None
 
+    @_lib.device_scoped
     @torch.no_grad()
     def forward(self, size: Tuple[int, int]) -> torch.Tensor:
         """[C, h, w] grid encoding (prompt_encoder.py:216-229)."""
@@ -110,6 +111,7 @@ class PromptEncoder(nn.Module):
             self._mask_cache = (key, blob)
         return self._mask_cache[1]
 
+    @_lib.device_scoped
     @torch.no_grad()
     def _embed_masks(self, masks: torch.Tensor) -> torch.Tensor:
         """mask_downscaling (prompt_encoder.py:111-114) as one kernel: [n,1,4g,4g] -> [n,C,g,g] in the weights' dtype."""
@@ -133,10 +135,23 @@ class PromptEncoder(nn.Module):
         _lib.check(rc, "sam_prompt_mask_embed")
         return out
 
-    @torch.no_grad()
+    @_lib.device_scoped
     def forward(self, points: Optional[Tuple[torch.Tensor, torch.Tensor]], boxes: Optional[torch.Tensor],
                 masks: Optional[torch.Tensor], text_embeds: Optional[torch.Tensor]
                 ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """prompt_encoder.py:140-186.  The [SEG] branch (text_embeds only) is pure tensor plumbing and stays inside
+        autograd, as in the reference: gradients of the mask loss reach text_hidden_fcs through `sparse`
+        (model/anyref.py:770-806).  The point / box / mask branches run CUDA kernels without a backward; with
+        gradients enabled on their inputs they raise instead of silently detaching."""
+        if points is not None or boxes is not None or masks is not None:
+            if torch.is_grad_enabled() and text_embeds is not None and text_embeds.requires_grad:
+                raise NotImplementedError("PromptEncoder: point / box / mask prompts combined with a text embedding "
+                                          "that requires grad have no backward here; call under torch.no_grad()")
+            with torch.no_grad():
+                return self._forward(points, boxes, masks, text_embeds)
+        return self._forward(points, boxes, masks, text_embeds)
+
+    def _forward(self, points, boxes, masks, text_embeds):
         bs = self._get_batch_size(points, boxes, masks, text_embeds)
         dev = self._get_device()
         g = self.image_embedding_size

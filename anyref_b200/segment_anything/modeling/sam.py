@@ -65,6 +65,7 @@ class Sam(nn.Module):
             outputs.append({"masks": binary.view(torch.bool), "iou_predictions": iou, "low_res_logits": low_res})
         return outputs
 
+    @_lib.device_scoped
     @torch.no_grad()
     def postprocess_masks(self, masks: torch.Tensor, input_size: Tuple[int, ...], original_size: Tuple[int, ...],
                           return_binary: bool = False):
@@ -87,6 +88,7 @@ class Sam(nn.Module):
             _lib.check(rc, "sam_postprocess_masks")
         return (out, binary) if return_binary else out
 
+    @_lib.device_scoped
     @torch.no_grad()
     def postprocess_and_score(self, masks: torch.Tensor, input_size: Tuple[int, ...], original_size: Tuple[int, ...],
                               gt_masks: torch.Tensor, stats: Optional[torch.Tensor] = None,
@@ -137,6 +139,7 @@ class Sam(nn.Module):
             _lib.check(rc, "sam_iou_finalize")
         return (stats, binary) if (return_binary or return_packed) else stats
 
+    @_lib.device_scoped
     @torch.no_grad()
     def preprocess(self, x: torch.Tensor, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
         """Normalise pixel values and pad to a square (sam.py:174-184; AnyRef's sam_preprocess,

@@ -270,9 +270,8 @@ def main():
     from anyref_b200.synthetic import synthetic_images, synthetic_seg_embeddings, synthetic_state_dict
     import torch.distributed as dist
 
-    # keep stdout to the one JSON line: NCCL prints its version banner there when NCCL_DEBUG is VERSION / INFO
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO") and not os.environ.get("ANYREF_KEEP_NCCL_DEBUG"):
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # NCCL_DEBUG is left as the launcher set it: _claim_stdout() already keeps fd 1 to the one JSON line, and the
+    # driver reads NCCL's communicator lines (rank counts) from stderr
     rank, world, local = dp.init_from_env("nccl")
     if world == 1:
         torch.cuda.set_device(0)
