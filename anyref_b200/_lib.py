@@ -59,10 +59,10 @@ _PROTOS = {
     "sam_encoder_forward": [_ENC_P, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_size_t,
                             c_void_p],
     "sam_decoder_weight_elems": [_DEC_P],
-    "sam_decoder_workspace_bytes": [_DEC_P, c_int, c_int],
+    "sam_decoder_workspace_bytes": [_DEC_P, c_int, c_int, c_int],
     "sam_decoder_derived_bytes": [_DEC_P],
-    "sam_decoder_prepare": [_DEC_P, c_void_p, c_void_p, c_void_p],
-    "sam_decoder_forward": [_DEC_P, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
+    "sam_decoder_prepare": [_DEC_P, c_void_p, c_void_p, c_int, c_void_p, c_void_p],
+    "sam_decoder_forward": [_DEC_P, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
                             c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p],
     "sam_postprocess_masks": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                               c_float, c_void_p],

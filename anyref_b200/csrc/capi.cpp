@@ -9,7 +9,7 @@ static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
 extern "C" {
 
 const char* sam_last_error(void) { return samhost::last_error(); }
-int sam_abi_version(void) { return 2; }
+int sam_abi_version(void) { return 3; }
 
 int sam_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, int K, int fmt, void* out, int ldo,
              int out_fmt, const float* bias, int act, const float* res, int ldr, int res_mod, void* stream) {
@@ -100,22 +100,24 @@ int sam_encoder_forward(const SamEncoderShape* s, const void* w16, const float* 
   return samk_encoder_forward(*s, w16, w32, images, in_fmt, B, out, out_fmt, workspace, workspace_bytes, S(stream));
 }
 size_t sam_decoder_weight_elems(const SamDecoderShape* s) { return samk_decoder_weight_elems(*s); }
-size_t sam_decoder_workspace_bytes(const SamDecoderShape* s, int n, int k) { return samk_decoder_workspace_bytes(*s, n, k); }
-size_t sam_decoder_derived_bytes(const SamDecoderShape* s) { return samk_decoder_derived_bytes(*s); }
-int sam_decoder_prepare(const SamDecoderShape* s, const float* weights, void* derived, void* stream) {
-  if (!s || !weights || !derived) return samhost::set_error(1, "sam_decoder_prepare: NULL argument");
-  return samk_decoder_prepare(*s, weights, derived, S(stream));
+size_t sam_decoder_workspace_bytes(const SamDecoderShape* s, int n_images, int n, int k) {
+  return samk_decoder_workspace_bytes(*s, n_images, n, k);
 }
-int sam_decoder_forward(const SamDecoderShape* s, const float* weights, const void* derived, const void* image_embeddings, int emb_fmt,
-                        const int* img_index, const void* image_pe, int pe_fmt, const void* sparse, int sparse_fmt,
-                        int n, int k, const void* dense_vec, const void* dense_full, int dense_fmt, void* masks,
-                        void* iou, int out_fmt, void* workspace, size_t workspace_bytes, void* stream) {
-  if (!s || !weights || !derived || !image_embeddings || !image_pe || !masks || !iou || !workspace)
+size_t sam_decoder_derived_bytes(const SamDecoderShape* s) { return samk_decoder_derived_bytes(*s); }
+int sam_decoder_prepare(const SamDecoderShape* s, const float* weights, const void* image_pe, int pe_fmt, void* derived,
+                        void* stream) {
+  if (!s || !weights || !image_pe || !derived) return samhost::set_error(1, "sam_decoder_prepare: NULL argument");
+  return samk_decoder_prepare(*s, weights, image_pe, pe_fmt, derived, S(stream));
+}
+int sam_decoder_forward(const SamDecoderShape* s, const float* weights, const void* derived, const void* image_embeddings,
+                        int emb_fmt, int n_images, const int* img_index, const void* sparse, int sparse_fmt, int n, int k,
+                        const void* dense_vec, const void* dense_full, int dense_fmt, void* masks, void* iou, int out_fmt,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+  if (!s || !weights || !derived || !image_embeddings || !masks || !iou || !workspace)
     return samhost::set_error(1, "sam_decoder_forward: NULL argument");
   if (k > 0 && !sparse) return samhost::set_error(1, "sam_decoder_forward: sparse embeddings missing");
-  return samk_decoder_forward(*s, weights, derived, image_embeddings, emb_fmt, img_index, image_pe, pe_fmt, sparse, sparse_fmt,
-                              n, k, dense_vec, dense_full, dense_fmt, masks, iou, out_fmt, workspace, workspace_bytes,
-                              S(stream));
+  return samk_decoder_forward(*s, weights, derived, image_embeddings, emb_fmt, n_images, img_index, sparse, sparse_fmt, n, k,
+                              dense_vec, dense_full, dense_fmt, masks, iou, out_fmt, workspace, workspace_bytes, S(stream));
 }
 int sam_postprocess_masks(const void* low, int low_fmt, int num_masks, int L, int Sz, int h_in, int w_in, int H, int W,
                           float* logits, unsigned char* binary, float threshold, void* stream) {

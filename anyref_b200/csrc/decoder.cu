@@ -10,6 +10,17 @@
 //
 // Data layout: tokens ("queries") [n, T, C] and image tokens ("keys") [n, HW, C] are fp32, token-major.  Weights come
 // as one fp32 blob in state_dict order (see DecoderWeights below and anyref_b200/segment_anything/_pack.py).
+//
+// Launch plan (20 launches for depth 2; round 1: 45+).  Token side = one CTA per prompt holding its tokens in shared
+// memory; image side = merged tcgen05 GEMMs over split-bf16 operands:
+//   keys0 (+split)                       | token_first: assemble, self-attn, norm1, t2i q-proj
+//   per layer l:  GEMM  keys.[Wk_t2i | Wv_t2i | Wq_i2t]^T   (one A operand for three projections: (keys + pe).W^T =
+//                       keys.W^T + pe.W^T, and pe.W^T is a constant of the model kept in `derived`)
+//                 attn_t2i (split over 16 key chunks) -> token_mlp (out-proj, norm2, MLP slice; 8 CTAs per prompt)
+//                 -> token_tail (norm3, i2t k/v proj, NEXT layer's self-attn block or the final q-proj)
+//                 attn_i2t (warp per pixel, writes the split A operand) -> GEMM out_proj -> ln_split (norm4 + split)
+//   final:        GEMM  keys.[Wk_final | Wv_final | W_upscale0]^T -> attn_t2i -> hyper (out-proj, norm_final,
+//                 hypernetwork MLPs, IoU head) -> upscale tail (LN2d, GELU, ConvT, GELU, mask product)
 #include <math.h>
 
 #include "host_common.h"
@@ -64,28 +75,6 @@ nchw_to_tokens_kernel(const void* __restrict__ src, int src_fmt, const int* __re
   for (int i = threadIdx.y; i < 32; i += 8) {
     const int t = t0 + i, c = c0 + threadIdx.x;
     dst[(static_cast<size_t>(p) * HW + t) * C + c] = tile[threadIdx.x][i];
-  }
-}
-
-// tokens[p, :, :] = cat(iou_token[1,C], mask_tokens[nm,C], sparse[p, k, C])          (mask_decoder.py:126-141)
-__global__ void assemble_tokens_kernel(const float* __restrict__ iou_token, const float* __restrict__ mask_tokens,
-                                       const void* __restrict__ sparse, int sparse_fmt, float* __restrict__ tokens,
-                                       int n, int nm, int k, int C) {
-  const int T = 1 + nm + k;
-  const size_t total = static_cast<size_t>(n) * T * C;
-  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int c = i % C;
-    const int t = (i / C) % T;
-    const int p = i / (static_cast<size_t>(C) * T);
-    float v;
-    if (t == 0)
-      v = iou_token[c];
-    else if (t <= nm)
-      v = mask_tokens[(t - 1) * C + c];
-    else
-      v = load_any(sparse, sparse_fmt, (static_cast<size_t>(p) * k + (t - 1 - nm)) * C + c);
-    tokens[i] = v;
   }
 }
 
@@ -195,97 +184,6 @@ dec_linear_kernel(const LinArgs a) {
   }
 }
 
-// Same contract, 128 x 16 x 16 tiles (2 x 4 outputs per thread) for launches with only a few hundred rows.
-// The accumulation order over k is the same as in dec_linear_kernel (k ascending, one fmaf per term), so both kernels
-// give bit-identical results.
-__global__ void __launch_bounds__(256)
-dec_linear_skinny_kernel(const LinArgs a) {
-  constexpr int SBN = 16;
-  __shared__ __align__(16) float As[2][LBK][LBM + 4];
-  __shared__ __align__(16) float Ws[2][LBK][SBN + 4];
-  const int tid = threadIdx.x;
-  const int ty = tid >> 2, tx = tid & 3;          // rows 2 ty, 2 ty + 1; columns 4 tx .. 4 tx + 3
-  const int m0 = blockIdx.x * LBM, n0 = blockIdx.y * SBN;
-  const int ar0 = tid >> 2, akq = tid & 3;        // A rows ar0 and ar0 + 64, k-quad akq
-  const int wr = tid >> 2, wkq = tid & 3;         // W row wr (threads 0..63), k-quad wkq
-  float4 ra[2], rw = make_float4(0.f, 0.f, 0.f, 0.f);
-  auto gload = [&](int k0) {
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int row = m0 + ar0 + i * 64;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (row < a.M) {
-        v = *reinterpret_cast<const float4*>(a.X + static_cast<size_t>(row) * a.ldx + k0 + akq * 4);
-        if (a.X2) {
-          const float4 u = *reinterpret_cast<const float4*>(a.X2 + static_cast<size_t>(row % a.x2_mod) * a.ldx2 + k0 + akq * 4);
-          v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
-        }
-      }
-      ra[i] = v;
-    }
-    if (tid < 4 * SBN) rw = __ldg(reinterpret_cast<const float4*>(a.W + static_cast<size_t>(n0 + wr) * a.K + k0 + wkq * 4));
-  };
-  auto sstore = [&](int buf) {
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int r = ar0 + i * 64;
-      As[buf][akq * 4 + 0][r] = ra[i].x;
-      As[buf][akq * 4 + 1][r] = ra[i].y;
-      As[buf][akq * 4 + 2][r] = ra[i].z;
-      As[buf][akq * 4 + 3][r] = ra[i].w;
-    }
-    if (tid < 4 * SBN) {
-      Ws[buf][wkq * 4 + 0][wr] = rw.x;
-      Ws[buf][wkq * 4 + 1][wr] = rw.y;
-      Ws[buf][wkq * 4 + 2][wr] = rw.z;
-      Ws[buf][wkq * 4 + 3][wr] = rw.w;
-    }
-  };
-  float acc[2][4];
-#pragma unroll
-  for (int i = 0; i < 2; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  const int nk = a.K / LBK;
-  gload(0);
-  sstore(0);
-  __syncthreads();
-  for (int kb = 0; kb < nk; ++kb) {
-    const int buf = kb & 1;
-    if (kb + 1 < nk) gload((kb + 1) * LBK);
-#pragma unroll
-    for (int k = 0; k < LBK; ++k) {
-      const float2 av = *reinterpret_cast<const float2*>(&As[buf][k][ty * 2]);
-      const float4 w = *reinterpret_cast<const float4*>(&Ws[buf][k][tx * 4]);
-      acc[0][0] = fmaf(av.x, w.x, acc[0][0]); acc[0][1] = fmaf(av.x, w.y, acc[0][1]);
-      acc[0][2] = fmaf(av.x, w.z, acc[0][2]); acc[0][3] = fmaf(av.x, w.w, acc[0][3]);
-      acc[1][0] = fmaf(av.y, w.x, acc[1][0]); acc[1][1] = fmaf(av.y, w.y, acc[1][1]);
-      acc[1][2] = fmaf(av.y, w.z, acc[1][2]); acc[1][3] = fmaf(av.y, w.w, acc[1][3]);
-    }
-    if (kb + 1 < nk) {
-      sstore(buf ^ 1);
-      __syncthreads();
-    }
-  }
-  const int col = n0 + tx * 4;
-  float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (a.b) bb = __ldg(reinterpret_cast<const float4*>(a.b + col));
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const int row = m0 + ty * 2 + i;
-    if (row >= a.M) continue;
-    float4 y = make_float4(acc[i][0] + bb.x, acc[i][1] + bb.y, acc[i][2] + bb.z, acc[i][3] + bb.w);
-    if (a.act == 1) {
-      y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f);
-    }
-    if (a.R) {
-      const float4 r = *reinterpret_cast<const float4*>(a.R + static_cast<size_t>(row) * a.ldr + col);
-      y.x += r.x; y.y += r.y; y.z += r.z; y.w += r.w;
-    }
-    *reinterpret_cast<float4*>(a.Y + static_cast<size_t>(row) * a.ldy + col) = y;
-  }
-}
-
 // ---------------------------------------------------------------------------------------------------------------
 // Tensor-core path for the image-token-side linears (M = n*4096 rows): fp32 accuracy from bf16 tcgen05 MMAs by
 // operand splitting.  x = hi + lo with hi = bf16(x), lo = bf16(x - hi)  (16 mantissa bits together);
@@ -294,37 +192,6 @@ dec_linear_skinny_kernel(const LinArgs a) {
 // TMEM (gemm2.cu).  The activation split (with the positional-encoding add fused in) is one elementwise pass; the
 // weight split is done once per weight change (samk_decoder_prepare).
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-dec_split3_rows_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ X2, int ldx2, int x2_mod,
-                       uint16_t* __restrict__ out, int M, int K) {
-  const int kq = K >> 2;
-  const size_t total = static_cast<size_t>(M) * kq;
-  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int row = static_cast<int>(i / kq), k = static_cast<int>(i % kq) * 4;
-    float4 v = *reinterpret_cast<const float4*>(X + static_cast<size_t>(row) * ldx + k);
-    if (X2) {
-      const float4 u = *reinterpret_cast<const float4*>(X2 + static_cast<size_t>(row % x2_mod) * ldx2 + k);
-      v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
-    }
-    const float f[4] = {v.x, v.y, v.z, v.w};
-    uint16_t hi[4], lo[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const __nv_bfloat16 h = __float2bfloat16_rn(f[j]);
-      const __nv_bfloat16 l = __float2bfloat16_rn(f[j] - __bfloat162float(h));
-      hi[j] = *reinterpret_cast<const uint16_t*>(&h);
-      lo[j] = *reinterpret_cast<const uint16_t*>(&l);
-    }
-    const uint2 H = make_uint2(hi[0] | (uint32_t(hi[1]) << 16), hi[2] | (uint32_t(hi[3]) << 16));
-    const uint2 L = make_uint2(lo[0] | (uint32_t(lo[1]) << 16), lo[2] | (uint32_t(lo[3]) << 16));
-    uint16_t* o = out + static_cast<size_t>(row) * (3 * K) + k;
-    *reinterpret_cast<uint2*>(o) = H;
-    *reinterpret_cast<uint2*>(o + K) = H;
-    *reinterpret_cast<uint2*>(o + 2 * K) = L;
-  }
-}
-
 // W fp32 [N, K] -> [N, 3K] bf16 = [hi | lo | hi]
 __global__ void dec_wsplit3_kernel(const float* __restrict__ W, uint16_t* __restrict__ out, int N, int K) {
   const int total = N * K;
@@ -340,191 +207,179 @@ __global__ void dec_wsplit3_kernel(const float* __restrict__ W, uint16_t* __rest
   }
 }
 
+
+// [N, K] fp32 -> [K, ldo] fp32 transposed copy at column col0 (token-side weights: a thread owns an output column and
+// walks k, so consecutive threads must read consecutive addresses)
+__global__ void dec_transpose_kernel(const float* __restrict__ W, float* __restrict__ out, int N, int K, int ldo, int col0) {
+  __shared__ float tile[32][33];
+  const int n0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int n = n0 + i, k = k0 + threadIdx.x;
+    tile[i][threadIdx.x] = (n < N && k < K) ? W[static_cast<size_t>(n) * K + k] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int k = k0 + i, n = n0 + threadIdx.x;
+    if (n < N && k < K) out[static_cast<size_t>(k) * ldo + col0 + n] = tile[threadIdx.x][i];
+  }
+}
+// out[i] = src ? src[i] : 0   (bias vectors of the merged GEMMs)
+__global__ void dec_fill_kernel(float* __restrict__ out, const float* __restrict__ src, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = src ? src[i] : 0.f;
+}
+
+__device__ __forceinline__ void split_bf16(float x, uint16_t& hi, uint16_t& lo) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(x);
+  const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+  hi = *reinterpret_cast<const uint16_t*>(&h);
+  lo = *reinterpret_cast<const uint16_t*>(&l);
+}
+// four consecutive fp32 -> 8 bytes of hi and 8 bytes of lo
+__device__ __forceinline__ void split4(const float4 v, uint2& H, uint2& L) {
+  uint16_t h[4], l[4];
+  split_bf16(v.x, h[0], l[0]); split_bf16(v.y, h[1], l[1]); split_bf16(v.z, h[2], l[2]); split_bf16(v.w, h[3], l[3]);
+  H = make_uint2(h[0] | (uint32_t(h[1]) << 16), h[2] | (uint32_t(h[3]) << 16));
+  L = make_uint2(l[0] | (uint32_t(l[1]) << 16), l[2] | (uint32_t(l[3]) << 16));
+}
+
 // ---------------------------------------------------------------------------------------------------------------
-// Attention kernels (transformer.py:220-242).  Inputs are the already-projected q / k / v.
+// Prologue: keys0[s, t, c] = emb[img(s), c, t] + dense  (mask_decoder.py:146-147; token-major, transformer.py:82-84)
+// written as fp32 AND as the split-bf16 A operand [hi | hi | lo] of the first merged GEMM.  s runs over SOURCES: the
+// images when the dense embedding is the no_mask_embed broadcast (all prompts of an image share keys0 -- the repeat of
+// mask_decoder.py:146 is never materialised), the prompts when each has its own dense mask embedding.
+// grid (HW/32, C/32, n_src), block (32, 8)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+dec_keys0_kernel(const void* __restrict__ src, int src_fmt, const int* __restrict__ img_index, const void* __restrict__ dense_vec,
+                 const void* __restrict__ dense_full, int dense_fmt, float* __restrict__ keys, uint16_t* __restrict__ a3,
+                 int C, int HW) {
+  __shared__ float tile[32][33];
+  const int s = blockIdx.z;
+  const int img = dense_full ? (img_index ? img_index[s] : 0) : s;
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i, t = t0 + threadIdx.x;
+    float v = load_any(src, src_fmt, (static_cast<size_t>(img) * C + c) * HW + t);
+    if (dense_vec) v += load_any(dense_vec, dense_fmt, c);
+    if (dense_full) v += load_any(dense_full, dense_fmt, (static_cast<size_t>(s) * C + c) * HW + t);
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int t = t0 + i, c = c0 + threadIdx.x;
+    const float v = tile[threadIdx.x][i];
+    const size_t row = static_cast<size_t>(s) * HW + t;
+    keys[row * C + c] = v;
+    uint16_t hi, lo;
+    split_bf16(v, hi, lo);
+    uint16_t* o = a3 + row * (3 * C) + c;
+    o[0] = hi;
+    o[C] = hi;
+    o[2 * C] = lo;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Token side.  One CTA owns ALL tokens of one prompt (T <= 16 rows of C = 256) in shared memory and runs whole
+// sub-blocks of TwoWayAttentionBlock (transformer.py:151-182) without leaving the SM; the weights are read as
+// [K, N]-transposed copies so that thread c walks column c with coalesced loads.  Round 1 ran every linear, norm and
+// attention of the token side as its own launch (22 skinny-GEMM launches of ~25 us each per call).
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int TMAX = 16;    // max tokens per prompt (1 IoU + 4 mask + up to 11 prompt embeddings)
-constexpr int TQ = 8;       // query chunk of the token->image kernel
+constexpr int DC = 256;     // transformer_dim
+constexpr int DCI = 128;    // cross-attention internal dim
+constexpr int NCH = 16;     // key chunks of the split token->image attention
+constexpr int PART = 16 + DCI;   // floats per (chunk, token): m[8 heads], l[8 heads], o[128]
 
-// token -> image: q [n,T,C], K/V [n,HW,C] -> out [n,T,C]; head dim 16.  grid (heads, n, ceil(T/TQ)), block 256.
-// dynamic smem: TQ*HW scores + 16*TQ*16 reduction scratch + TQ*16 q
-__global__ void __launch_bounds__(256)
-dec_attn_t2i_kernel(const float* __restrict__ q, const float* __restrict__ Kp, const float* __restrict__ Vp,
-                    float* __restrict__ out, int T, int HW, int C, float scale) {
-  constexpr int DH = 16;
-  extern __shared__ float sm[];
-  float* sc = sm;                        // [TQ][HW]
-  float* red = sc + TQ * HW;             // [16][TQ][DH]
-  float* qs = red + 16 * TQ * DH;        // [TQ][DH]
-  float* stat = qs + TQ * DH;            // [8 warps][TQ] scratch, then [TQ] results at stat + 64
-  const int h = blockIdx.x, p = blockIdx.y, t0 = blockIdx.z * TQ;
-  const int tq = min(TQ, T - t0);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (tid < TQ * DH) {
-    const int t = tid / DH, d = tid % DH;
-    qs[tid] = (t < tq) ? q[(static_cast<size_t>(p) * T + t0 + t) * C + h * DH + d] * scale : 0.f;
-  }
-  __syncthreads();
-  float mx[TQ];
+// ys[t][c] = act(sum_k xs[t][k] * Wt[k][c] + b[c]) for t < TT, c = threadIdx.x < ncols (256 threads).
+// xs / ys in shared memory (row strides ldx / ldy floats, 16-byte aligned rows); Wt [K, ldw] fp32 in global memory.
+template <int TT>
+__device__ __forceinline__ void tok_linear(const float* __restrict__ Wt, int ldw, const float* __restrict__ b, int ncols,
+                                           const float* xs, int ldx, int K, float* ys, int ldy, bool relu) {
+  const int c = threadIdx.x;
+  if (c < ncols) {
+    float acc[TT];
+    const float bias = b ? __ldg(b + c) : 0.f;
 #pragma unroll
-  for (int t = 0; t < TQ; ++t) mx[t] = -INFINITY;
-  for (int j = tid; j < HW; j += 256) {
-    const float4* kr = reinterpret_cast<const float4*>(Kp + (static_cast<size_t>(p) * HW + j) * C + h * DH);
-    const float4 k0 = kr[0], k1 = kr[1], k2 = kr[2], k3 = kr[3];
+    for (int t = 0; t < TT; ++t) acc[t] = bias;
+    const float* w = Wt + c;
+#pragma unroll 2
+    for (int k = 0; k < K; k += 4) {
+      const float w0 = __ldg(w + static_cast<size_t>(k) * ldw), w1 = __ldg(w + static_cast<size_t>(k + 1) * ldw);
+      const float w2 = __ldg(w + static_cast<size_t>(k + 2) * ldw), w3 = __ldg(w + static_cast<size_t>(k + 3) * ldw);
 #pragma unroll
-    for (int t = 0; t < TQ; ++t) {
-      const float4* qq = reinterpret_cast<const float4*>(qs + t * DH);
-      const float4 q0 = qq[0], q1 = qq[1], q2 = qq[2], q3 = qq[3];
-      float s = q0.x * k0.x;
-      s = fmaf(q0.y, k0.y, s); s = fmaf(q0.z, k0.z, s); s = fmaf(q0.w, k0.w, s);
-      s = fmaf(q1.x, k1.x, s); s = fmaf(q1.y, k1.y, s); s = fmaf(q1.z, k1.z, s); s = fmaf(q1.w, k1.w, s);
-      s = fmaf(q2.x, k2.x, s); s = fmaf(q2.y, k2.y, s); s = fmaf(q2.z, k2.z, s); s = fmaf(q2.w, k2.w, s);
-      s = fmaf(q3.x, k3.x, s); s = fmaf(q3.y, k3.y, s); s = fmaf(q3.z, k3.z, s); s = fmaf(q3.w, k3.w, s);
-      sc[t * HW + j] = s;
-      mx[t] = fmaxf(mx[t], s);
+      for (int t = 0; t < TT; ++t) {
+        const float4 x = *reinterpret_cast<const float4*>(xs + t * ldx + k);
+        acc[t] = fmaf(x.x, w0, acc[t]);
+        acc[t] = fmaf(x.y, w1, acc[t]);
+        acc[t] = fmaf(x.z, w2, acc[t]);
+        acc[t] = fmaf(x.w, w3, acc[t]);
+      }
     }
-  }
 #pragma unroll
-  for (int t = 0; t < TQ; ++t) {
-    const float m = warp_max(mx[t]);
-    if (lane == 0) stat[warp * TQ + t] = m;
+    for (int t = 0; t < TT; ++t) ys[t * ldy + c] = relu ? fmaxf(acc[t], 0.f) : acc[t];
   }
-  __syncthreads();
-  if (tid < TQ) {
-    float m = stat[tid];
-    for (int w = 1; w < 8; ++w) m = fmaxf(m, stat[w * TQ + tid]);
-    stat[64 + tid] = m;
-  }
-  __syncthreads();
-  float sum[TQ];
+}
+
+// rows t < T of xs [.., DC] (optionally + res rows) -> LayerNorm(eps 1e-5) -> out (shared) and out_g (global, optional)
+__device__ __forceinline__ void tok_layernorm(const float* xs, const float* res, const float* __restrict__ gw,
+                                              const float* __restrict__ gb, float* out, float* out_g, int T) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int t = warp; t < T; t += 8) {
+    float v[8];
+    float s = 0.f;
 #pragma unroll
-  for (int t = 0; t < TQ; ++t) {
-    sum[t] = 0.f;
-    mx[t] = stat[64 + t];
-  }
-  for (int j = tid; j < HW; j += 256) {
-#pragma unroll
-    for (int t = 0; t < TQ; ++t) {
-      const float e = expf(sc[t * HW + j] - mx[t]);
-      sc[t * HW + j] = e;
-      sum[t] += e;
+    for (int i = 0; i < 8; ++i) {
+      const int c = lane + 32 * i;
+      v[i] = xs[t * DC + c] + (res ? res[t * DC + c] : 0.f);
+      s += v[i];
     }
-  }
-  __syncthreads();  // all of stat[0..64) consumed, scores final
+    const float mean = warp_sum(s) * (1.0f / DC);
+    float q = 0.f;
 #pragma unroll
-  for (int t = 0; t < TQ; ++t) {
-    const float s = warp_sum(sum[t]);
-    if (lane == 0) stat[warp * TQ + t] = s;
-  }
-  // P.V : thread (kg, d) covers keys [kg*HW/16, (kg+1)*HW/16)
-  const int kg = tid >> 4, d = tid & 15;
-  float acc[TQ];
+    for (int i = 0; i < 8; ++i) {
+      v[i] -= mean;
+      q = fmaf(v[i], v[i], q);
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / DC) + 1e-5f);
 #pragma unroll
-  for (int t = 0; t < TQ; ++t) acc[t] = 0.f;
-  const int per = HW / 16;
-  for (int j = kg * per; j < (kg + 1) * per; ++j) {
-    const float v = Vp[(static_cast<size_t>(p) * HW + j) * C + h * DH + d];
-#pragma unroll
-    for (int t = 0; t < TQ; ++t) acc[t] = fmaf(sc[t * HW + j], v, acc[t]);
-  }
-#pragma unroll
-  for (int t = 0; t < TQ; ++t) red[(kg * TQ + t) * DH + d] = acc[t];
-  __syncthreads();
-  if (tid < TQ * DH) {
-    const int t = tid / DH, dd = tid % DH;
-    if (t < tq) {
-      float l = 0.f;
-      for (int w = 0; w < 8; ++w) l += stat[w * TQ + t];
-      float o = 0.f;
-      for (int g = 0; g < 16; ++g) o += red[(g * TQ + t) * DH + dd];
-      out[(static_cast<size_t>(p) * T + t0 + t) * C + h * DH + dd] = o / l;
+    for (int i = 0; i < 8; ++i) {
+      const int c = lane + 32 * i;
+      const float y = v[i] * rstd * __ldg(gw + c) + __ldg(gb + c);
+      out[t * DC + c] = y;
+      if (out_g) out_g[t * DC + c] = y;
     }
   }
 }
 
-// image -> token: q [n,HW,C], k/v [n,T,C] -> out [n,HW,C]; head dim 16, C = 128.
-// block 256 = 32 image tokens x 8 heads; grid (HW/32, n).  out may alias q.
-__global__ void __launch_bounds__(256)
-dec_attn_i2t_kernel(const float* q, const float* __restrict__ kp, const float* __restrict__ vp, float* out, int T,
-                    int HW, int C, int heads, float scale) {
-  constexpr int DH = 16;
-  __shared__ __align__(16) float ks[TMAX * 128];
-  __shared__ __align__(16) float vs[TMAX * 128];
-  const int p = blockIdx.y;
+struct SelfW {   // transposed [K, N] weights + biases of one self-attention + norm1 + the t2i q projection that follows
+  const float *qw, *qb, *kw, *kb, *vw, *vb, *ow, *ob;   // [DC, DC]
+  const float *n1w, *n1b;
+  const float *cqw, *cqb;                               // [DC, DCI] cross_attn_token_to_image.q_proj
+};
+
+// self-attention sub-block on the tokens in shared memory (transformer.py:153-161): xs <- LN1(xs + attn) (layer 0:
+// LN1(attn), skip_first_layer_pe), then tq_g <- ((xs + pe) . Wq^T + bq) / sqrt(16) for the token->image attention.
+// smem: xs, pe [TT][DC]; b0, b1, b2 [TT][DC] scratch; sc [8][TT][TT]
+template <int TT>
+__device__ __forceinline__ void tok_self_block(const SelfW& w, bool first, float* xs, const float* pe, float* b0, float* b1,
+                                               float* b2, float* sc, int T, int heads, float* q_g, float* tq_g) {
   const int tid = threadIdx.x;
-  for (int i = tid; i < T * C; i += 256) {
-    ks[i] = kp[static_cast<size_t>(p) * T * C + i];
-    vs[i] = vp[static_cast<size_t>(p) * T * C + i];
-  }
+  // b2 = xs + pe (layer 0: xs), the q / k input
+  for (int i = tid; i < T * DC; i += 256) b2[i] = first ? xs[i] : xs[i] + pe[i];
   __syncthreads();
-  const int row = blockIdx.x * 32 + tid / heads, h = tid % heads;
-  if (row >= HW) return;
-  const size_t off = (static_cast<size_t>(p) * HW + row) * C + h * DH;
-  float qv[DH];
-  {
-    const float4* q4 = reinterpret_cast<const float4*>(q + off);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float4 t = q4[i];
-      qv[4 * i] = t.x * scale; qv[4 * i + 1] = t.y * scale; qv[4 * i + 2] = t.z * scale; qv[4 * i + 3] = t.w * scale;
-    }
-  }
-  float s[TMAX];
-  float m = -INFINITY;
-#pragma unroll
-  for (int t = 0; t < TMAX; ++t) {
-    s[t] = -INFINITY;
-    if (t < T) {
-      float a = 0.f;
-#pragma unroll
-      for (int d = 0; d < DH; ++d) a = fmaf(qv[d], ks[t * C + h * DH + d], a);
-      s[t] = a;
-      m = fmaxf(m, a);
-    }
-  }
-  float l = 0.f;
-#pragma unroll
-  for (int t = 0; t < TMAX; ++t) {
-    s[t] = (t < T) ? expf(s[t] - m) : 0.f;
-    l += s[t];
-  }
-  const float inv = 1.0f / l;
-  float o[DH];
-#pragma unroll
-  for (int d = 0; d < DH; ++d) o[d] = 0.f;
-#pragma unroll
-  for (int t = 0; t < TMAX; ++t) {
-    if (t < T) {
-#pragma unroll
-      for (int d = 0; d < DH; ++d) o[d] = fmaf(s[t], vs[t * C + h * DH + d], o[d]);
-    }
-  }
-  float4* o4 = reinterpret_cast<float4*>(out + off);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) o4[i] = make_float4(o[4 * i] * inv, o[4 * i + 1] * inv, o[4 * i + 2] * inv, o[4 * i + 3] * inv);
-}
-
-// token self-attention: q/k/v [n,T,C] (C = heads*32) -> out [n,T,C].  One CTA per prompt.
-__global__ void __launch_bounds__(256)
-dec_self_attn_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
-                     float* __restrict__ out, int T, int C, int heads, float scale) {
-  extern __shared__ float sm[];
-  float* qs = sm;               // [T][C]
-  float* ks = qs + T * C;
-  float* vs = ks + T * C;
-  float* sc = vs + T * C;       // [heads][T][T]
-  const int p = blockIdx.x, tid = threadIdx.x;
-  const int dh = C / heads;
-  for (int i = tid; i < T * C; i += 256) {
-    qs[i] = q[static_cast<size_t>(p) * T * C + i];
-    ks[i] = k[static_cast<size_t>(p) * T * C + i];
-    vs[i] = v[static_cast<size_t>(p) * T * C + i];
-  }
+  tok_linear<TT>(w.qw, DC, w.qb, DC, b2, DC, DC, b0, DC, false);    // q
+  tok_linear<TT>(w.kw, DC, w.kb, DC, b2, DC, DC, b1, DC, false);    // k
   __syncthreads();
+  tok_linear<TT>(w.vw, DC, w.vb, DC, xs, DC, DC, b2, DC, false);    // v (b2's old content is dead)
+  __syncthreads();
+  const int dh = DC / heads;
+  const float scale = 1.0f / sqrtf(static_cast<float>(dh));
   for (int i = tid; i < heads * T * T; i += 256) {
     const int t2 = i % T, t1 = (i / T) % T, h = i / (T * T);
     float a = 0.f;
-    for (int d = 0; d < dh; ++d) a = fmaf(qs[t1 * C + h * dh + d], ks[t2 * C + h * dh + d], a);
+    for (int d = 0; d < dh; ++d) a = fmaf(b0[t1 * DC + h * dh + d], b1[t2 * DC + h * dh + d], a);
     sc[i] = a * scale;
   }
   __syncthreads();
@@ -541,17 +396,370 @@ dec_self_attn_kernel(const float* __restrict__ q, const float* __restrict__ k, c
     for (int t = 0; t < T; ++t) r[t] *= inv;
   }
   __syncthreads();
-  for (int i = tid; i < T * C; i += 256) {
-    const int c = i % C, t1 = i / C, h = c / dh;
+  for (int i = tid; i < T * DC; i += 256) {      // b1 <- attn (k is dead after the scores)
+    const int c = i % DC, t1 = i / DC, h = c / dh;
     float a = 0.f;
-    for (int t2 = 0; t2 < T; ++t2) a = fmaf(sc[(h * T + t1) * T + t2], vs[t2 * C + c], a);
-    out[static_cast<size_t>(p) * T * C + i] = a;
+    for (int t2 = 0; t2 < T; ++t2) a = fmaf(sc[(h * T + t1) * T + t2], b2[t2 * DC + c], a);
+    b1[i] = a;
   }
+  __syncthreads();
+  tok_linear<TT>(w.ow, DC, w.ob, DC, b1, DC, DC, b0, DC, false);   // out_proj -> b0
+  __syncthreads();
+  tok_layernorm(b0, first ? nullptr : xs, w.n1w, w.n1b, xs, q_g, T);
+  __syncthreads();
+  for (int i = tid; i < T * DC; i += 256) b2[i] = xs[i] + pe[i];
+  __syncthreads();
+  tok_linear<TT>(w.cqw, DCI, w.cqb, DCI, b2, DC, DC, b0, DCI, false);
+  __syncthreads();
+  const float sc_cross = 1.0f / sqrtf(static_cast<float>(DCI / heads));
+  for (int i = tid; i < T * DCI; i += 256) tq_g[i] = b0[i] * sc_cross;
+}
+
+constexpr int tok_smem_floats(int TT) { return 5 * TT * DC + 8 * TT * TT; }
+
+// T1 of layer 0: token assembly (mask_decoder.py:126-141) + the first self-attention sub-block.   grid n, block 256
+template <int TT>
+__global__ void __launch_bounds__(256)
+dec_token_first_kernel(const float* __restrict__ iou_token, const float* __restrict__ mask_tokens, const void* __restrict__ sparse,
+                       int sparse_fmt, int nm, int k, const SelfW w, int heads, float* __restrict__ tok0_g,
+                       float* __restrict__ q_g, float* __restrict__ tq_g) {
+  extern __shared__ __align__(16) float tsm[];
+  const int T = 1 + nm + k, p = blockIdx.x, tid = threadIdx.x;
+  float* xs = tsm;
+  float* pe = xs + TT * DC;
+  float* b0 = pe + TT * DC;
+  float* b1 = b0 + TT * DC;
+  float* b2 = b1 + TT * DC;
+  float* sc = b2 + TT * DC;
+  for (int i = tid; i < T * DC; i += 256) {
+    const int c = i % DC, t = i / DC;
+    float v;
+    if (t == 0)
+      v = iou_token[c];
+    else if (t <= nm)
+      v = mask_tokens[(t - 1) * DC + c];
+    else
+      v = load_any(sparse, sparse_fmt, (static_cast<size_t>(p) * k + (t - 1 - nm)) * DC + c);
+    xs[i] = v;
+    pe[i] = v;
+    tok0_g[static_cast<size_t>(p) * T * DC + i] = v;    // query_pe of every later layer (transformer.py:95)
+  }
+  __syncthreads();
+  tok_self_block<TT>(w, true, xs, pe, b0, b1, b2, sc, T, heads, q_g + static_cast<size_t>(p) * T * DC,
+                     tq_g + static_cast<size_t>(p) * T * DCI);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// token -> image attention, split over key chunks (transformer.py:162-166, :220-242 with the q projection done by the
+// token kernel and the k / v projections by the merged GEMM).  K = kv[.., 0:128] + rk[pixel] (rk = pe.Wk^T + bk, the
+// positional half of (keys + pe).Wk^T, constant per model), V = kv[.., 128:256] (bias added by the GEMM).
+// A warp reads one key row (512 B, coalesced); lane l holds dims 4l..4l+3 = a quarter of head l/4, so a score is four
+// FMAs and two shuffles.  Online softmax per (token, head); the chunk's (max, sum, unnormalised out) go to `part` and
+// are combined by the consumer (dec_token_mlp_kernel / dec_hyper_kernel).  grid (NCH, n), block 256.
+// Source rows of prompt p: one_src ? block 0 : src_index ? block src_index[p] : block p (same in the kernels below).
+// ---------------------------------------------------------------------------------------------------------------
+template <int TT>
+__global__ void __launch_bounds__(256)
+dec_attn_t2i_kernel(const float* __restrict__ tq, const float* __restrict__ kv, int ldkv, const float* __restrict__ rk,
+                    const int* __restrict__ src_index, float* __restrict__ part, int T, int HW, int one_src) {
+  extern __shared__ __align__(16) float red_raw[];     // [8 warps][TT][PART]
+  float (*red)[TT][PART] = reinterpret_cast<float (*)[TT][PART]>(red_raw);
+  const int ch = blockIdx.x, p = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int src = one_src ? 0 : (src_index ? src_index[p] : p);
+  float4 q[TT];
+#pragma unroll
+  for (int t = 0; t < TT; ++t)
+    q[t] = (t < T) ? *reinterpret_cast<const float4*>(tq + (static_cast<size_t>(p) * T + t) * DCI + 4 * lane)
+                   : make_float4(0.f, 0.f, 0.f, 0.f);
+  float m[TT], l[TT];
+  float4 o[TT];
+#pragma unroll
+  for (int t = 0; t < TT; ++t) {
+    m[t] = -INFINITY;
+    l[t] = 0.f;
+    o[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const int per = HW / NCH;
+  const int j0 = ch * per;
+#pragma unroll 1
+  for (int j = j0 + warp; j < j0 + per; j += 8) {
+    const float* row = kv + (static_cast<size_t>(src) * HW + j) * ldkv;
+    float4 k4 = *reinterpret_cast<const float4*>(row + 4 * lane);
+    const float4 r4 = __ldg(reinterpret_cast<const float4*>(rk + static_cast<size_t>(j) * DCI) + lane);
+    const float4 v4 = *reinterpret_cast<const float4*>(row + DCI + 4 * lane);
+    k4.x += r4.x; k4.y += r4.y; k4.z += r4.z; k4.w += r4.w;
+#pragma unroll
+    for (int t = 0; t < TT; ++t) {
+      if (t < T) {
+        float s = q[t].x * k4.x;
+        s = fmaf(q[t].y, k4.y, s); s = fmaf(q[t].z, k4.z, s); s = fmaf(q[t].w, k4.w, s);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        const float e = expf(-fabsf(s - m[t]));      // m = -inf on the first key: e = 0
+        const bool up = s > m[t];
+        const float alpha = up ? e : 1.0f, pr = up ? 1.0f : e;
+        m[t] = up ? s : m[t];
+        l[t] = fmaf(l[t], alpha, pr);
+        o[t].x = fmaf(o[t].x, alpha, pr * v4.x); o[t].y = fmaf(o[t].y, alpha, pr * v4.y);
+        o[t].z = fmaf(o[t].z, alpha, pr * v4.z); o[t].w = fmaf(o[t].w, alpha, pr * v4.w);
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < TT; ++t) {
+    if (t < T) {
+      if ((lane & 3) == 0) {
+        red[warp][t][lane >> 2] = m[t];
+        red[warp][t][8 + (lane >> 2)] = l[t];
+      }
+      *reinterpret_cast<float4*>(&red[warp][t][16 + 4 * lane]) = o[t];
+    }
+  }
+  __syncthreads();
+  // combine the 8 warps: thread (t, c) for c < 128 (+ the m / l entries by c < 8)
+  for (int i = threadIdx.x; i < T * DCI; i += 256) {
+    const int t = i / DCI, c = i % DCI, h = c >> 4;
+    float M = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) M = fmaxf(M, red[w][t][h]);
+    float L = 0.f, O = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      const float e = expf(red[w][t][h] - M);
+      L = fmaf(red[w][t][8 + h], e, L);
+      O = fmaf(red[w][t][16 + c], e, O);
+    }
+    float* dst = part + ((static_cast<size_t>(p) * NCH + ch) * T + t) * PART;
+    dst[16 + c] = O;
+    if ((c & 15) == 0) {
+      dst[h] = M;
+      dst[8 + h] = L;
+    }
+  }
+}
+
+// combine the NCH chunk partials of prompt p into the attention output rows ta[t][0:128] (shared memory), t in [t0, t1)
+__device__ __forceinline__ void t2i_combine(const float* __restrict__ part, int p, int T, int t0, int t1, float* ta) {
+  for (int i = threadIdx.x; i < (t1 - t0) * DCI; i += 256) {
+    const int t = t0 + i / DCI, c = i % DCI, h = c >> 4;
+    const float* base = part + (static_cast<size_t>(p) * NCH * T + t) * PART;
+    float M = -INFINITY;
+    for (int ch = 0; ch < NCH; ++ch) M = fmaxf(M, base[static_cast<size_t>(ch) * T * PART + h]);
+    float L = 0.f, O = 0.f;
+    for (int ch = 0; ch < NCH; ++ch) {
+      const float* b = base + static_cast<size_t>(ch) * T * PART;
+      const float e = expf(b[h] - M);
+      L = fmaf(b[8 + h], e, L);
+      O = fmaf(b[16 + c], e, O);
+    }
+    ta[(t - t0) * DCI + c] = O / L;
+  }
+}
+
+struct CrossMlpW {   // after the token->image attention: out_proj + norm2, MLP; all weights transposed [K, N]
+  const float *ow, *ob;         // [DCI, DC]
+  const float *n2w, *n2b;
+  const float *l1w, *l1b;       // [DC, H]
+  const float *l2w;             // [H, DC]
+};
+
+// T2: queries <- LN2(queries + out_proj(attn)) (computed redundantly by the 8 CTAs of a prompt), then this CTA's
+// 256-wide slice j of the MLP hidden layer: part_mlp[p][j] = relu(x.W1_j^T + b1_j) . W2[:, j]^T  (transformer.py:166-172).
+// CTA j == 0 also publishes the post-norm2 queries.   grid (H / 256, n), block 256
+template <int TT>
+__global__ void __launch_bounds__(256)
+dec_token_mlp_kernel(const float* __restrict__ part, float* __restrict__ q_g, const CrossMlpW w, int T, int H,
+                     float* __restrict__ x2_g, float* __restrict__ part_mlp) {
+  __shared__ __align__(16) float ta[TT * DCI];
+  __shared__ __align__(16) float xs[TT * DC];
+  __shared__ __align__(16) float ys[TT * DC];
+  const int j = blockIdx.x, p = blockIdx.y, tid = threadIdx.x;
+  t2i_combine(part, p, T, 0, T, ta);
+  for (int i = tid; i < T * DC; i += 256) xs[i] = q_g[static_cast<size_t>(p) * T * DC + i];
+  __syncthreads();
+  tok_linear<TT>(w.ow, DC, w.ob, DC, ta, DCI, DCI, ys, DC, false);
+  __syncthreads();
+  tok_layernorm(ys, xs, w.n2w, w.n2b, xs, (j == 0) ? x2_g + static_cast<size_t>(p) * T * DC : nullptr, T);
+  __syncthreads();
+  tok_linear<TT>(w.l1w + j * 256, H, w.l1b + j * 256, 256, xs, DC, DC, ys, DC, true);
+  __syncthreads();
+  tok_linear<TT>(w.l2w + static_cast<size_t>(j) * 256 * DC, DC, nullptr, DC, ys, DC, 256, xs, DC, false);
+  __syncthreads();
+  float* dst = part_mlp + (static_cast<size_t>(p) * gridDim.x + j) * T * DC;
+  for (int i = tid; i < T * DC; i += 256) dst[i] = xs[i];
+}
+
+struct TailW {   // end of a layer: lin2 bias + norm3, then the image->token k / v projections (concatenated columns)
+  const float* l2b;
+  const float *n3w, *n3b;
+  const float *kvw, *kvb;       // [DC, 2 * DCI]: k_proj | v_proj of cross_attn_image_to_token
+};
+
+// T3: queries <- LN3(x2 + sum_j part_mlp[j] + b2); tk | tv <- image->token k / v projections (k from queries + pe);
+// then either the NEXT layer's self-attention sub-block (has_next) or only the q projection of the final
+// token->image attention (transformer.py:172-176, :99-101).   grid n, block 256
+template <int TT>
+__global__ void __launch_bounds__(256)
+dec_token_tail_kernel(const float* __restrict__ x2_g, const float* __restrict__ part_mlp, int nj, const TailW w,
+                      const float* __restrict__ tok0_g, int T, int heads, float* __restrict__ tk_g, float* __restrict__ tv_g,
+                      int has_next, const SelfW nw, float* __restrict__ q_g, float* __restrict__ tq_g) {
+  extern __shared__ __align__(16) float tsm[];
+  const int p = blockIdx.x, tid = threadIdx.x;
+  float* xs = tsm;
+  float* pe = xs + TT * DC;
+  float* b0 = pe + TT * DC;
+  float* b1 = b0 + TT * DC;
+  float* b2 = b1 + TT * DC;
+  float* sc = b2 + TT * DC;
+  for (int i = tid; i < T * DC; i += 256) {
+    float a = __ldg(w.l2b + (i % DC));
+    for (int j = 0; j < nj; ++j) a += part_mlp[(static_cast<size_t>(p) * nj + j) * T * DC + i];
+    b0[i] = a;
+    xs[i] = x2_g[static_cast<size_t>(p) * T * DC + i];
+    pe[i] = tok0_g[static_cast<size_t>(p) * T * DC + i];
+  }
+  __syncthreads();
+  tok_layernorm(b0, xs, w.n3w, w.n3b, xs, q_g + static_cast<size_t>(p) * T * DC, T);
+  __syncthreads();
+  for (int i = tid; i < T * DC; i += 256) b2[i] = xs[i] + pe[i];
+  __syncthreads();
+  // k from (queries + pe), v from queries: two half-width passes over the concatenated weight
+  tok_linear<TT>(w.kvw, 2 * DCI, w.kvb, DCI, b2, DC, DC, b0, DCI, false);
+  tok_linear<TT>(w.kvw + DCI, 2 * DCI, w.kvb + DCI, DCI, xs, DC, DC, b1, DCI, false);
+  __syncthreads();
+  for (int i = tid; i < T * DCI; i += 256) {
+    tk_g[static_cast<size_t>(p) * T * DCI + i] = b0[i];
+    tv_g[static_cast<size_t>(p) * T * DCI + i] = b1[i];
+  }
+  __syncthreads();
+  if (has_next) {
+    tok_self_block<TT>(nw, false, xs, pe, b0, b1, b2, sc, T, heads, q_g + static_cast<size_t>(p) * T * DC,
+                       tq_g + static_cast<size_t>(p) * T * DCI);
+  } else {
+    tok_linear<TT>(nw.cqw, DCI, nw.cqb, DCI, b2, DC, DC, b0, DCI, false);   // b2 still holds queries + pe
+    __syncthreads();
+    const float sc_cross = 1.0f / sqrtf(static_cast<float>(DCI / heads));
+    for (int i = tid; i < T * DCI; i += 256) tq_g[static_cast<size_t>(p) * T * DCI + i] = b0[i] * sc_cross;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// image -> token attention (transformer.py:174-180): one WARP per image token.  q = kvq[.., 256:384] + rq[pixel]
+// (rq = pe.Wq^T + bq), softmax over the T tokens of the prompt, output written directly as the split-bf16 A operand
+// [hi | hi | lo] of the out_proj GEMM.   grid (HW / 64, n), block 256 (8 pixels per warp)
+// ---------------------------------------------------------------------------------------------------------------
+template <int TT>
+__global__ void __launch_bounds__(256)
+dec_attn_i2t_kernel(const float* __restrict__ kvq, int ldq, int qcol, const float* __restrict__ rq, const int* __restrict__ src_index,
+                    const float* __restrict__ tk, const float* __restrict__ tv, uint16_t* __restrict__ a3o, int T, int HW,
+                    float scale, int one_src) {
+  __shared__ __align__(16) float ks[TT * DCI];
+  __shared__ __align__(16) float vs[TT * DCI];
+  const int p = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < T * DCI; i += 256) {
+    ks[i] = tk[static_cast<size_t>(p) * T * DCI + i];
+    vs[i] = tv[static_cast<size_t>(p) * T * DCI + i];
+  }
+  __syncthreads();
+  const int src = one_src ? 0 : (src_index ? src_index[p] : p);
+  float4 k4[TT];
+#pragma unroll
+  for (int t = 0; t < TT; ++t)
+    k4[t] = (t < T) ? *reinterpret_cast<const float4*>(ks + t * DCI + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+  for (int i = 0; i < 8; ++i) {
+    const int pix = blockIdx.x * 64 + warp * 8 + i;
+    float4 q4 = *reinterpret_cast<const float4*>(kvq + (static_cast<size_t>(src) * HW + pix) * ldq + qcol + 4 * lane);
+    const float4 r4 = __ldg(reinterpret_cast<const float4*>(rq + static_cast<size_t>(pix) * DCI) + lane);
+    q4.x = (q4.x + r4.x) * scale; q4.y = (q4.y + r4.y) * scale; q4.z = (q4.z + r4.z) * scale; q4.w = (q4.w + r4.w) * scale;
+    float s[TT];
+    float m = -INFINITY;
+#pragma unroll
+    for (int t = 0; t < TT; ++t) {
+      float a = q4.x * k4[t].x;
+      a = fmaf(q4.y, k4[t].y, a); a = fmaf(q4.z, k4[t].z, a); a = fmaf(q4.w, k4[t].w, a);
+      a += __shfl_xor_sync(0xffffffffu, a, 1);
+      a += __shfl_xor_sync(0xffffffffu, a, 2);
+      s[t] = (t < T) ? a : -INFINITY;
+      m = fmaxf(m, s[t]);
+    }
+    float l = 0.f;
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int t = 0; t < TT; ++t) {
+      if (t < T) {
+        const float e = expf(s[t] - m);
+        l += e;
+        const float4 v4 = *reinterpret_cast<const float4*>(vs + t * DCI + 4 * lane);
+        o.x = fmaf(e, v4.x, o.x); o.y = fmaf(e, v4.y, o.y); o.z = fmaf(e, v4.z, o.z); o.w = fmaf(e, v4.w, o.w);
+      }
+    }
+    const float inv = 1.0f / l;
+    o.x *= inv; o.y *= inv; o.z *= inv; o.w *= inv;
+    uint2 H, L;
+    split4(o, H, L);
+    uint16_t* dst = a3o + (static_cast<size_t>(p) * HW + pix) * (3 * DCI) + 4 * lane;
+    *reinterpret_cast<uint2*>(dst) = H;
+    *reinterpret_cast<uint2*>(dst + DCI) = H;
+    *reinterpret_cast<uint2*>(dst + 2 * DCI) = L;
+  }
+}
+
+// keys <- LN4(prev[src row] + delta) (transformer.py:180-181; delta = out_proj output incl. bias), written as fp32 and
+// as the split-bf16 A operand of the next merged GEMM.  One warp per row of C = 256.   grid rows / 8, block 256
+__global__ void __launch_bounds__(256)
+dec_ln_split_kernel(const float* __restrict__ delta, const float* __restrict__ prev, const int* __restrict__ src_index, int HW,
+                    const float* __restrict__ gw, const float* __restrict__ gb, float* __restrict__ keys,
+                    uint16_t* __restrict__ a3, size_t rows, int one_src) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t row = static_cast<size_t>(blockIdx.x) * 8 + warp;
+  if (row >= rows) return;
+  const int p = static_cast<int>(row / HW), pix = static_cast<int>(row % HW);
+  const size_t prow = one_src ? static_cast<size_t>(pix) : (src_index ? static_cast<size_t>(src_index[p]) * HW + pix : row);
+  float v[8];
+  {
+    const float4* d4 = reinterpret_cast<const float4*>(delta + row * DC);
+    const float4* p4 = reinterpret_cast<const float4*>(prev + prow * DC);
+    const float4 a = d4[lane], b = d4[32 + lane], c = p4[lane], d = p4[32 + lane];
+    v[0] = a.x + c.x; v[1] = a.y + c.y; v[2] = a.z + c.z; v[3] = a.w + c.w;
+    v[4] = b.x + d.x; v[5] = b.y + d.y; v[6] = b.z + d.z; v[7] = b.w + d.w;
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += v[i];
+  const float mean = warp_sum(s) * (1.0f / DC);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    v[i] -= mean;
+    q = fmaf(v[i], v[i], q);
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / DC) + 1e-5f);
+  const float4 g0 = __ldg(reinterpret_cast<const float4*>(gw) + lane), g1 = __ldg(reinterpret_cast<const float4*>(gw) + 32 + lane);
+  const float4 b0 = __ldg(reinterpret_cast<const float4*>(gb) + lane), b1 = __ldg(reinterpret_cast<const float4*>(gb) + 32 + lane);
+  const float4 y0 = make_float4(v[0] * rstd * g0.x + b0.x, v[1] * rstd * g0.y + b0.y, v[2] * rstd * g0.z + b0.z, v[3] * rstd * g0.w + b0.w);
+  const float4 y1 = make_float4(v[4] * rstd * g1.x + b1.x, v[5] * rstd * g1.y + b1.y, v[6] * rstd * g1.z + b1.z, v[7] * rstd * g1.w + b1.w);
+  float4* k4 = reinterpret_cast<float4*>(keys + row * DC);
+  k4[lane] = y0;
+  k4[32 + lane] = y1;
+  uint2 H0, L0, H1, L1;
+  split4(y0, H0, L0);
+  split4(y1, H1, L1);
+  uint16_t* o = a3 + row * (3 * DC);
+  reinterpret_cast<uint2*>(o)[lane] = H0;
+  reinterpret_cast<uint2*>(o)[32 + lane] = H1;
+  reinterpret_cast<uint2*>(o + DC)[lane] = H0;
+  reinterpret_cast<uint2*>(o + DC)[32 + lane] = H1;
+  reinterpret_cast<uint2*>(o + 2 * DC)[lane] = L0;
+  reinterpret_cast<uint2*>(o + 2 * DC)[32 + lane] = L1;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // Hypernetwork MLPs + IoU head (mask_decoder.py:159-177, :184-206): grid (nm + 1, n), block 256.
 // which < nm: hyper_in[p, which, :] = MLP_which(hs[p, 1 + which]);   which == nm: iou[p, :] = head(hs[p, 0])
+// hs[p, tok] = norm_final_attn(queries + out_proj(final attention))[tok] (transformer.py:99-104) is computed here for
+// the ONE token the CTA needs: combine of the attention partials, a 128 -> 256 projection and a LayerNorm.
 // ---------------------------------------------------------------------------------------------------------------
 struct Mlp3 {
   const float *w0, *b0, *w1, *b1, *w2, *b2;
@@ -559,7 +767,10 @@ struct Mlp3 {
 struct HyperArgs {
   Mlp3 mlp[5];
   int nm, C, hidden_iou, out_hyper, T;
-  const float* hs;
+  const float* q;       // [n, T, C] queries after the last layer (before the final attention)
+  const float* part;    // chunk partials of the FINAL token->image attention
+  const float *ow, *ob; // final_attn_token_to_image.out_proj, weight transposed [DCI, C]
+  const float *nfw, *nfb;
   float* hyper;    // [n, nm, out_hyper] fp32
   void* iou;       // [n, nm] in iou_fmt
   int iou_fmt;
@@ -597,7 +808,29 @@ dec_hyper_kernel(const HyperArgs a) {
   const int tok = (which < a.nm) ? 1 + which : 0;
   const int hidden = (which < a.nm) ? a.C : a.hidden_iou;
   const int nout = (which < a.nm) ? a.out_hyper : a.nm;
-  for (int i = threadIdx.x; i < a.C; i += 256) x0[i] = a.hs[(static_cast<size_t>(p) * a.T + tok) * a.C + i];
+  {
+    __shared__ __align__(16) float ta[DCI];
+    __shared__ float redm[8], redq[8];
+    t2i_combine(a.part, p, a.T, tok, tok + 1, ta);
+    __syncthreads();
+    const int c = threadIdx.x;      // C == 256 == blockDim.x
+    float v = __ldg(a.ob + c);
+    for (int k = 0; k < DCI; ++k) v = fmaf(ta[k], __ldg(a.ow + static_cast<size_t>(k) * a.C + c), v);
+    v += a.q[(static_cast<size_t>(p) * a.T + tok) * a.C + c];
+    const float s = warp_sum(v);
+    if ((c & 31) == 0) redm[c >> 5] = s;
+    __syncthreads();
+    float mean = 0.f;
+    for (int w = 0; w < 8; ++w) mean += redm[w];
+    mean *= 1.0f / 256.0f;
+    const float d = v - mean;
+    const float qq = warp_sum(d * d);
+    if ((c & 31) == 0) redq[c >> 5] = qq;
+    __syncthreads();
+    float var = 0.f;
+    for (int w = 0; w < 8; ++w) var += redq[w];
+    x0[c] = d * (1.0f / sqrtf(var * (1.0f / 256.0f) + 1e-5f)) * __ldg(a.nfw + c) + __ldg(a.nfb + c);
+  }
   __syncthreads();
   const Mlp3& m = a.mlp[which];
   mlp_layer(m.w0, m.b0, x0, x1, hidden, a.C, true);
@@ -616,10 +849,10 @@ dec_hyper_kernel(const HyperArgs a) {
 // linear (dec_linear with the weight rearranged to [(dy,dx,oc), ic]); this kernel does, per (pixel, dy, dx):
 // LayerNorm2d(64) -> GELU -> second ConvTranspose2d(64->32, k=2,s=2) -> GELU -> dot with the 4 hypernetwork vectors,
 // writing the four 256x256 mask logits directly (the [n,32,256,256] tensor is never materialised).
-// U [n*HW, 4*C1] fp32;  w1r [4 (ey,ex)][C2][C1];  masks [n, nm, 4g, 4g] in out_fmt.   C1 = 64, C2 = 32, nm <= 4.
+// U [n*HW, ldu >= 4*C1] fp32 (a column block of the final merged GEMM's output);  w1r [4 (ey,ex)][C2][C1];  masks [n, nm, 4g, 4g] in out_fmt.   C1 = 64, C2 = 32, nm <= 4.
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-dec_upscale_tail_kernel(const float* __restrict__ U, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+dec_upscale_tail_kernel(const float* __restrict__ U, int ldu, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
                         const float* __restrict__ w1r, const float* __restrict__ b1, const float* __restrict__ hyper,
                         void* __restrict__ masks, int out_fmt, int g, int nm) {
   constexpr int C1 = 64, C2 = 32;
@@ -641,7 +874,7 @@ dec_upscale_tail_kernel(const float* __restrict__ U, const float* __restrict__ l
   const int y = pix / g, x = pix % g;
   float a[C1];
   {
-    const float4* u4 = reinterpret_cast<const float4*>(U + (gt >> 2) * (4 * C1) + sub * C1);
+    const float4* u4 = reinterpret_cast<const float4*>(U + (gt >> 2) * ldu + sub * C1);
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < C1 / 4; ++i) {
@@ -696,15 +929,8 @@ int launch_linear(const float* X, int ldx, const float* X2, int ldx2, int x2_mod
   SAM_REQUIRE(ldx % 4 == 0 && ldy % 4 == 0 && (!X2 || ldx2 % 4 == 0) && (!R || ldr % 4 == 0), "dec_linear: ld %% 4");
   LinArgs a{X, ldx, X2, ldx2, x2_mod > 0 ? x2_mod : M, W, b, R, ldr, Y, ldy, M, N, K, act};
   samhost::LaunchScope scope(samhost::KC_DECODER, st, 2.0 * M * N * K);
-  if (M <= 4 * LBM) {
-    // token-side linears (a few hundred rows): 16-column tiles put N / 16 CTAs per row tile on the machine instead of
-    // N / 64 -- these launches are latency-bound (a K = 2048 reduction walked by 4 CTAs took 133 us)
-    dim3 grid((M + LBM - 1) / LBM, N / 16);
-    dec_linear_skinny_kernel<<<grid, 256, 0, st>>>(a);
-  } else {
-    dim3 grid((M + LBM - 1) / LBM, N / LBN);
-    dec_linear_kernel<<<grid, 256, 0, st>>>(a);
-  }
+  dim3 grid((M + LBM - 1) / LBM, N / LBN);
+  dec_linear_kernel<<<grid, 256, 0, st>>>(a);
   SAM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -781,39 +1007,75 @@ int carve_weights(const SamDecoderShape& s, const float* blob, DecoderWeights* w
   return 0;
 }
 
-// bf16x3-split copies of the weights that multiply image-token-sized operands (layout of the `derived` buffer)
+
+// Everything the forward needs besides the state_dict blob, rebuilt by samk_decoder_prepare whenever the weights or the
+// dense positional encoding change (layout of the `derived` buffer):
+//   * split-bf16 ([hi | lo | hi] along K) weights of the merged image-side GEMMs and the per-layer out_proj,
+//   * their bias vectors (zero for the k / q column blocks: those biases travel inside rk / rq),
+//   * rk / rq = pe . W^T + b  [HW, 128] fp32: the positional half of (keys + pe).W^T,
+//   * [K, N]-transposed fp32 copies of the token-side weights (thread c of a CTA walks column c),
+//   * pe_t: the token-major dense PE (scratch of the preparation).
 struct DerivedW {
-  const uint16_t *t2i_k[9], *t2i_v[9];   // per layer; index depth = final_attn_token_to_image
-  const uint16_t *i2t_q[8], *i2t_o[8];
-  const uint16_t* up0;
-  size_t total;   // elements
+  const uint16_t* kvq[8];     // [3 Ci, 3 C]   rows: k_t2i | v_t2i | q_i2t of layer l
+  const uint16_t* fin;        // [2 Ci + C, 3 C] rows: k_final | v_final | upscale conv 0
+  const uint16_t* i2t_o[8];   // [C, 3 Ci]
+  const float* b_kvq[8];      // [3 Ci] = 0 | v bias | 0
+  const float* b_fin;         // [2 Ci + C] = 0 | v bias | upscale bias
+  const float* rk[9];         // [HW, Ci]  (index depth = final attention)
+  const float* rq[8];         // [HW, Ci]
+  const float* pe_t;          // [HW, C]
+  struct Tok {
+    const float *sq, *sk, *sv, *so;    // self-attention [C, C]
+    const float *cq, *co;              // t2i q [C, Ci], out [Ci, C]
+    const float *l1, *l2;              // [C, H], [H, C]
+    const float *ikv, *ikvb;           // i2t k | v [C, 2 Ci] and their biases [2 Ci]
+  } tok[8];
+  const float *fq, *fo;                // final attention q [C, Ci], out [Ci, C]
+  size_t total;                        // bytes
 };
-void carve_derived(const SamDecoderShape& s, const uint16_t* base, DerivedW* d) {
-  const size_t C = s.C, Ci = C / 2;
+void carve_derived(const SamDecoderShape& s, const void* base, DerivedW* d) {
+  const size_t C = s.C, Ci = C / 2, H = s.mlp_dim, HW = static_cast<size_t>(s.grid) * s.grid;
   size_t off = 0;
-  auto take = [&](size_t n) {
-    const uint16_t* p = base ? base + off : nullptr;
-    off += (n + 7) & ~size_t(7);
+  auto take = [&](size_t bytes) {
+    const uint8_t* p = base ? static_cast<const uint8_t*>(base) + off : nullptr;
+    off += (bytes + 255) & ~size_t(255);
     return p;
   };
-  for (int l = 0; l <= s.depth; ++l) {
-    d->t2i_k[l] = take(Ci * 3 * C);
-    d->t2i_v[l] = take(Ci * 3 * C);
-  }
+  auto t16 = [&](size_t n) { return reinterpret_cast<const uint16_t*>(take(n * 2)); };
+  auto t32 = [&](size_t n) { return reinterpret_cast<const float*>(take(n * 4)); };
   for (int l = 0; l < s.depth; ++l) {
-    d->i2t_q[l] = take(Ci * 3 * C);
-    d->i2t_o[l] = take(C * 3 * Ci);
+    d->kvq[l] = t16(3 * Ci * 3 * C);
+    d->i2t_o[l] = t16(C * 3 * Ci);
+    d->b_kvq[l] = t32(3 * Ci);
+    d->rk[l] = t32(HW * Ci);
+    d->rq[l] = t32(HW * Ci);
+    DerivedW::Tok& t = d->tok[l];
+    t.sq = t32(C * C); t.sk = t32(C * C); t.sv = t32(C * C); t.so = t32(C * C);
+    t.cq = t32(C * Ci); t.co = t32(Ci * C);
+    t.l1 = t32(C * H); t.l2 = t32(H * C);
+    t.ikv = t32(C * 2 * Ci); t.ikvb = t32(2 * Ci);
   }
-  d->up0 = take(C * 3 * C);
+  d->fin = t16((2 * Ci + C) * 3 * C);
+  d->b_fin = t32(2 * Ci + C);
+  d->rk[s.depth] = t32(HW * Ci);
+  d->fq = t32(C * Ci);
+  d->fo = t32(Ci * C);
+  d->pe_t = t32(HW * C);
   d->total = off;
 }
 
 int check_shape(const SamDecoderShape& s) {
-  SAM_REQUIRE(s.C == 256 && s.heads == 8, "mask decoder: transformer_dim must be 256 with 8 heads (got %d, %d)", s.C, s.heads);
+  SAM_REQUIRE(s.C == DC && s.heads == 8, "mask decoder: transformer_dim must be 256 with 8 heads (got %d, %d)", s.C, s.heads);
   SAM_REQUIRE(s.depth >= 1 && s.depth <= 8, "mask decoder: depth %d unsupported", s.depth);
   SAM_REQUIRE(s.num_mask_tokens >= 1 && s.num_mask_tokens <= 4, "mask decoder: num_mask_tokens %d unsupported", s.num_mask_tokens);
-  SAM_REQUIRE(s.mlp_dim % 64 == 0 && s.iou_hidden <= 256 && s.iou_hidden % 32 == 0, "mask decoder: mlp_dim/iou_hidden unsupported");
-  SAM_REQUIRE(s.grid % 32 == 0, "mask decoder: embedding grid %d must be a multiple of 32", s.grid);
+  SAM_REQUIRE(s.mlp_dim % 256 == 0 && s.iou_hidden <= 256 && s.iou_hidden % 32 == 0, "mask decoder: mlp_dim/iou_hidden unsupported");
+  SAM_REQUIRE(s.grid % 32 == 0 && (s.grid * s.grid) % (8 * NCH) == 0, "mask decoder: embedding grid %d must be a multiple of 32", s.grid);
+  return 0;
+}
+
+template <typename K>
+int opt_in_smem(K kernel, int bytes) {
+  SAM_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   return 0;
 }
 
@@ -828,213 +1090,294 @@ size_t samk_decoder_weight_elems(const SamDecoderShape& s) {
 size_t samk_decoder_derived_bytes(const SamDecoderShape& s) {
   DerivedW d;
   carve_derived(s, nullptr, &d);
-  return d.total * sizeof(uint16_t);
+  return d.total;
 }
 
-int samk_decoder_prepare(const SamDecoderShape& s, const float* blob, void* derived, cudaStream_t st) {
+int samk_decoder_prepare(const SamDecoderShape& s, const float* blob, const void* image_pe, int pe_fmt, void* derived,
+                         cudaStream_t st) {
   if (int rc = check_shape(s)) return rc;
-  SAM_REQUIRE((reinterpret_cast<uintptr_t>(derived) & 15) == 0, "mask decoder: derived-weight buffer must be 16-byte aligned");
+  SAM_REQUIRE((reinterpret_cast<uintptr_t>(derived) & 255) == 0, "mask decoder: derived-weight buffer must be 256-byte aligned");
+  SAM_REQUIRE(pe_fmt >= 0 && pe_fmt <= 2, "mask decoder: bad image_pe format");
   DecoderWeights w;
   carve_weights(s, blob, &w);
   DerivedW d;
-  carve_derived(s, static_cast<const uint16_t*>(derived), &d);
-  const int C = s.C, Ci = C / 2;
-  auto split = [&](const float* W, const uint16_t* out, int N, int K) {
+  carve_derived(s, derived, &d);
+  const int C = s.C, Ci = C / 2, H = s.mlp_dim, HW = s.grid * s.grid;
+  auto split = [&](const float* W, const uint16_t* out, int row0, int N, int K) {
     samhost::LaunchScope scope(samhost::KC_DECODER, st);
-    dec_wsplit3_kernel<<<(N * K + 255) / 256, 256, 0, st>>>(W, const_cast<uint16_t*>(out), N, K);
+    dec_wsplit3_kernel<<<(N * K + 255) / 256, 256, 0, st>>>(W, const_cast<uint16_t*>(out) + static_cast<size_t>(row0) * 3 * K, N, K);
   };
-  for (int l = 0; l <= s.depth; ++l) {
-    const AttnW& a = (l < s.depth) ? w.layer[l].t2i : w.final_attn;
-    split(a.kw, d.t2i_k[l], Ci, C);
-    split(a.vw, d.t2i_v[l], Ci, C);
+  auto transpose = [&](const float* W, const float* out, int N, int K, int ldo, int col0) {
+    samhost::LaunchScope scope(samhost::KC_DECODER, st);
+    dim3 grid((N + 31) / 32, (K + 31) / 32), blk(32, 8);
+    dec_transpose_kernel<<<grid, blk, 0, st>>>(W, const_cast<float*>(out), N, K, ldo, col0);
+  };
+  auto fill = [&](const float* out, int off, const float* src, int n) {
+    samhost::LaunchScope scope(samhost::KC_DECODER, st);
+    dec_fill_kernel<<<(n + 255) / 256, 256, 0, st>>>(const_cast<float*>(out) + off, src, n);
+  };
+  {
+    dim3 grid(HW / 32, C / 32, 1), blk(32, 8);
+    samhost::LaunchScope scope(samhost::KC_DECODER, st);
+    nchw_to_tokens_kernel<<<grid, blk, 0, st>>>(image_pe, pe_fmt, nullptr, nullptr, nullptr, 2, const_cast<float*>(d.pe_t), C, HW);
   }
+  // r = pe_t . W^T + b  (fp32 FMA GEMM; once per weight / PE change)
+  auto pe_proj = [&](const float* W, const float* b, const float* out) -> int {
+    return launch_linear(d.pe_t, C, nullptr, 0, 0, W, b, nullptr, 0, const_cast<float*>(out), Ci, HW, Ci, C, 0, st);
+  };
   for (int l = 0; l < s.depth; ++l) {
-    split(w.layer[l].i2t.qw, d.i2t_q[l], Ci, C);
-    split(w.layer[l].i2t.ow, d.i2t_o[l], C, Ci);
+    const LayerW& L = w.layer[l];
+    split(L.t2i.kw, d.kvq[l], 0, Ci, C);
+    split(L.t2i.vw, d.kvq[l], Ci, Ci, C);
+    split(L.i2t.qw, d.kvq[l], 2 * Ci, Ci, C);
+    split(L.i2t.ow, d.i2t_o[l], 0, C, Ci);
+    fill(d.b_kvq[l], 0, nullptr, Ci);
+    fill(d.b_kvq[l], Ci, L.t2i.vb, Ci);
+    fill(d.b_kvq[l], 2 * Ci, nullptr, Ci);
+    if (int rc = pe_proj(L.t2i.kw, L.t2i.kb, d.rk[l])) return rc;
+    if (int rc = pe_proj(L.i2t.qw, L.i2t.qb, d.rq[l])) return rc;
+    const DerivedW::Tok& t = d.tok[l];
+    transpose(L.self_attn.qw, t.sq, C, C, C, 0);
+    transpose(L.self_attn.kw, t.sk, C, C, C, 0);
+    transpose(L.self_attn.vw, t.sv, C, C, C, 0);
+    transpose(L.self_attn.ow, t.so, C, C, C, 0);
+    transpose(L.t2i.qw, t.cq, Ci, C, Ci, 0);
+    transpose(L.t2i.ow, t.co, C, Ci, C, 0);
+    transpose(L.l1w, t.l1, H, C, H, 0);
+    transpose(L.l2w, t.l2, C, H, C, 0);
+    transpose(L.i2t.kw, t.ikv, Ci, C, 2 * Ci, 0);
+    transpose(L.i2t.vw, t.ikv, Ci, C, 2 * Ci, Ci);
+    fill(t.ikvb, 0, L.i2t.kb, Ci);
+    fill(t.ikvb, Ci, L.i2t.vb, Ci);
   }
-  split(w.up0w, d.up0, C, C);
+  split(w.final_attn.kw, d.fin, 0, Ci, C);
+  split(w.final_attn.vw, d.fin, Ci, Ci, C);
+  split(w.up0w, d.fin, 2 * Ci, C, C);
+  fill(d.b_fin, 0, nullptr, Ci);
+  fill(d.b_fin, Ci, w.final_attn.vb, Ci);
+  fill(d.b_fin, 2 * Ci, w.up0b, C);
+  if (int rc = pe_proj(w.final_attn.kw, w.final_attn.kb, d.rk[s.depth])) return rc;
+  transpose(w.final_attn.qw, d.fq, Ci, C, Ci, 0);
+  transpose(w.final_attn.ow, d.fo, C, Ci, C, 0);
   SAM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
-size_t samk_decoder_workspace_bytes(const SamDecoderShape& s, int n, int k) {
-  const size_t HW = static_cast<size_t>(s.grid) * s.grid, C = s.C, T = 1 + s.num_mask_tokens + k;
-  size_t f = 0;
-  f += HW * C;                         // pe_t
-  f += 2 * n * HW * C;                 // keys, tmp
-  f += 3 * n * HW * (C / 2);           // kbuf, vbuf, qbuf
-  f += n * T * C * 8;                  // tokens0, queries, tq, tk, tv, ta, tb + slack
-  f += n * T * s.mlp_dim;              // mlp hidden
-  f += n * s.num_mask_tokens * (C / 8);  // hyper_in
-  f += (3 * n * HW * C) / 2 + 16;         // a3: bf16 [n*HW, 3C] operand of the split-bf16 GEMMs
-  return f * sizeof(float) + 256;
+namespace {
+struct DecWs {   // workspace carve (floats unless noted)
+  float *keys0, *keys, *delta, *kvq;
+  uint16_t *a3, *a3o;
+  float *tok0, *q, *x2, *tq, *tk, *tv, *part, *pmlp, *hyper;
+  size_t total;   // bytes
+};
+void carve_ws(const SamDecoderShape& s, int n, int n_src, int k, void* base, DecWs* w) {
+  const size_t HW = static_cast<size_t>(s.grid) * s.grid, C = s.C, Ci = C / 2, T = 1 + s.num_mask_tokens + k;
+  const size_t nmax = n > n_src ? n : n_src;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    uint8_t* p = base ? static_cast<uint8_t*>(base) + off : nullptr;
+    off += (bytes + 255) & ~size_t(255);
+    return p;
+  };
+  w->keys0 = reinterpret_cast<float*>(take(static_cast<size_t>(n_src) * HW * C * 4));
+  w->keys = reinterpret_cast<float*>(take(static_cast<size_t>(n) * HW * C * 4));
+  w->delta = reinterpret_cast<float*>(take(static_cast<size_t>(n) * HW * C * 4));
+  w->kvq = reinterpret_cast<float*>(take(nmax * HW * (2 * Ci + C) * 4));
+  w->a3 = reinterpret_cast<uint16_t*>(take(nmax * HW * 3 * C * 2));
+  w->a3o = reinterpret_cast<uint16_t*>(take(static_cast<size_t>(n) * HW * 3 * Ci * 2));
+  const size_t tc = static_cast<size_t>(n) * T * C * 4;
+  w->tok0 = reinterpret_cast<float*>(take(tc));
+  w->q = reinterpret_cast<float*>(take(tc));
+  w->x2 = reinterpret_cast<float*>(take(tc));
+  w->tq = reinterpret_cast<float*>(take(tc / 2));
+  w->tk = reinterpret_cast<float*>(take(tc / 2));
+  w->tv = reinterpret_cast<float*>(take(tc / 2));
+  w->part = reinterpret_cast<float*>(take(static_cast<size_t>(n) * NCH * T * PART * 4));
+  w->pmlp = reinterpret_cast<float*>(take(static_cast<size_t>(n) * (s.mlp_dim / 256) * T * C * 4));
+  w->hyper = reinterpret_cast<float*>(take(static_cast<size_t>(n) * s.num_mask_tokens * (C / 8) * 4));
+  w->total = off;
+}
+}  // namespace
+
+size_t samk_decoder_workspace_bytes(const SamDecoderShape& s, int n_images, int n, int k) {
+  DecWs w;
+  carve_ws(s, n, n_images > n ? n_images : n, k, nullptr, &w);   // covers both source modes (images / prompts)
+  return w.total + 256;
 }
 
 int samk_decoder_forward(const SamDecoderShape& s, const float* blob, const void* derived, const void* image_embeddings, int emb_fmt,
-                         const int* img_index, const void* image_pe, int pe_fmt, const void* sparse, int sparse_fmt,
-                         int n, int k, const void* dense_vec, const void* dense_full, int dense_fmt, void* masks,
-                         void* iou, int out_fmt, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+                         int n_images, const int* img_index, const void* sparse, int sparse_fmt, int n, int k,
+                         const void* dense_vec, const void* dense_full, int dense_fmt, void* masks, void* iou, int out_fmt,
+                         void* workspace, size_t workspace_bytes, cudaStream_t st) {
   if (int rc = check_shape(s)) return rc;
   SAM_REQUIRE(n > 0 && k >= 0, "mask decoder: need at least one prompt");
-  const int C = s.C, Ci = C / 2, nm = s.num_mask_tokens, T = 1 + nm + k, g = s.grid, HW = g * g;
-  SAM_REQUIRE(T <= TMAX, "mask decoder: %d tokens per prompt exceed the supported maximum %d", T, TMAX);
-  SAM_REQUIRE(workspace_bytes >= samk_decoder_workspace_bytes(s, n, k), "mask decoder: workspace too small");
-  SAM_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0 && (reinterpret_cast<uintptr_t>(blob) & 15) == 0,
-              "mask decoder: workspace / weight blob must be 16-byte aligned");
+  const int C = s.C, Ci = C / 2, nm = s.num_mask_tokens, T = 1 + nm + k, g = s.grid, HW = g * g, H = s.mlp_dim;
+  SAM_REQUIRE(T <= TMAX, "mask decoder: %d tokens per prompt exceed the supported maximum %d (at most %d sparse prompt "
+              "embeddings per prompt)", T, TMAX, TMAX - 1 - nm);
+  SAM_REQUIRE(n_images >= 1 && (img_index || n_images == 1), "mask decoder: img_index is required with several image embeddings");
+  SAM_REQUIRE(n <= 65535, "mask decoder: at most 65535 prompts per call");
+  // sources of the layer-0 image tokens: the images (shared by their prompts) unless every prompt has its own dense embedding
+  const int n_src = dense_full ? n : n_images;
+  SAM_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0 && (reinterpret_cast<uintptr_t>(blob) & 15) == 0,
+              "mask decoder: workspace must be 256-byte and the weight blob 16-byte aligned");
+  SAM_REQUIRE(derived != nullptr && (reinterpret_cast<uintptr_t>(derived) & 255) == 0,
+              "mask decoder: derived weights missing (call sam_decoder_prepare) or misaligned");
   DecoderWeights w;
   carve_weights(s, blob, &w);
   DerivedW dw;
-  carve_derived(s, static_cast<const uint16_t*>(derived), &dw);
-  SAM_REQUIRE(derived != nullptr && (reinterpret_cast<uintptr_t>(derived) & 15) == 0,
-              "mask decoder: derived weights missing (call sam_decoder_prepare) or misaligned");
-
-  float* f = static_cast<float*>(workspace);
-  auto take = [&](size_t nelem) {
-    float* p = f;
-    f += (nelem + 3) & ~size_t(3);
-    return p;
-  };
-  float* pe_t = take((size_t)HW * C);
-  float* keys = take((size_t)n * HW * C);
-  float* tmp = take((size_t)n * HW * C);
-  float* kbuf = take((size_t)n * HW * Ci);
-  float* vbuf = take((size_t)n * HW * Ci);
-  float* qbuf = take((size_t)n * HW * Ci);
-  const size_t tc = (size_t)n * T * C;
-  float* tok0 = take(tc);     // initial tokens == query_pe (transformer.py:95)
-  float* qry = take(tc);      // running queries
-  float* tq = take(tc);
-  float* tk = take(tc);
-  float* tv = take(tc);
-  float* ta = take(tc);
-  float* tb = take(tc);
-  float* hid = take((size_t)n * T * s.mlp_dim);
-  float* hyper = take((size_t)n * nm * (C / 8));
-  uint16_t* a3 = reinterpret_cast<uint16_t*>(take(((size_t)3 * n * HW * C) / 2 + 8));
-  const int MT = n * T, MK = n * HW;
-  const float sc_self = 1.0f / sqrtf(static_cast<float>(C / s.heads));
-  const float sc_cross = 1.0f / sqrtf(static_cast<float>(Ci / s.heads));
-
-  // ---- prologue (mask_decoder.py:126-149, transformer.py:82-84)
-  {
-    dim3 grid(HW / 32, C / 32, n), blk(32, 8);
-    samhost::LaunchScope scope(samhost::KC_DECODER, st, 0.0, 0.0, 3);
-    nchw_to_tokens_kernel<<<grid, blk, 0, st>>>(image_embeddings, emb_fmt, img_index, dense_vec, dense_full, dense_fmt,
-                                                keys, C, HW);
-    dim3 grid1(HW / 32, C / 32, 1);
-    nchw_to_tokens_kernel<<<grid1, blk, 0, st>>>(image_pe, pe_fmt, nullptr, nullptr, nullptr, 2, pe_t, C, HW);
-    assemble_tokens_kernel<<<(MT * C + 255) / 256, 256, 0, st>>>(w.iou_token, w.mask_tokens, sparse, sparse_fmt, tok0,
-                                                                n, nm, k, C);
-    SAM_CHECK_CUDA(cudaGetLastError());
-  }
+  carve_derived(s, derived, &dw);
+  DecWs ws;
+  carve_ws(s, n, n_src, k, workspace, &ws);
+  SAM_REQUIRE(workspace_bytes >= ws.total, "mask decoder: workspace too small (%zu < %zu)", workspace_bytes, ws.total);
+  const bool big = T > 8;    // kernels are instantiated for up to 8 and up to 16 tokens per prompt
+  const int tok_smem = tok_smem_floats(big ? 16 : 8) * 4;
+  const int t2i_smem = 8 * (big ? 16 : 8) * PART * 4;
   static samhost::PerDeviceOnce attr_once;
-  const int t2i_smem = (TQ * HW + 16 * TQ * 16 + TQ * 16 + 64 + TQ) * sizeof(float);
-  const int self_smem = (3 * TMAX * C + s.heads * TMAX * TMAX) * sizeof(float);
   if (attr_once.need()) {
-    SAM_CHECK_CUDA(cudaFuncSetAttribute(dec_attn_t2i_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    SAM_CHECK_CUDA(cudaFuncSetAttribute(dec_self_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, self_smem));
+    if (int rc = opt_in_smem(dec_token_first_kernel<8>, tok_smem_floats(8) * 4)) return rc;
+    if (int rc = opt_in_smem(dec_token_first_kernel<16>, tok_smem_floats(16) * 4)) return rc;
+    if (int rc = opt_in_smem(dec_token_tail_kernel<8>, tok_smem_floats(8) * 4)) return rc;
+    if (int rc = opt_in_smem(dec_token_tail_kernel<16>, tok_smem_floats(16) * 4)) return rc;
+    if (int rc = opt_in_smem(dec_attn_t2i_kernel<8>, 8 * 8 * PART * 4)) return rc;
+    if (int rc = opt_in_smem(dec_attn_t2i_kernel<16>, 8 * 16 * PART * 4)) return rc;
     attr_once.done();
   }
-  SAM_REQUIRE(t2i_smem <= 200 * 1024, "mask decoder: embedding grid %d too large for the token->image kernel", g);
+  // prompt -> source row block of the layer-0 image tokens: identity with per-prompt dense embeddings, img_index[p]
+  // otherwise; img_index == NULL (one image, the reference's per-image call) makes every prompt read block 0
+  const int* src0 = dense_full ? nullptr : img_index;
+  const bool single_src = (!dense_full && !img_index);
 
-#define LIN(...)                                   \
-  do {                                             \
-    if (int rc_ = launch_linear(__VA_ARGS__, st)) return rc_; \
-  } while (0)
-  // image-token-side linear on the tensor cores: Y = (X [+ X2]) . W^T + b, or Y += ... when `inplace`
-  auto lin_tc = [&](const float* X, int ldx, const float* X2, int ldx2, int x2_mod, const uint16_t* W3, const float* b,
-                    bool inplace, float* Y, int ldy, int M, int N, int K) -> int {
-    {
-      samhost::LaunchScope scope(samhost::KC_DECODER, st);
-      const size_t total = static_cast<size_t>(M) * (K / 4);
-      dec_split3_rows_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(X, ldx, X2, ldx2,
-                                                                                         x2_mod > 0 ? x2_mod : M, a3, M, K);
-      SAM_CHECK_CUDA(cudaGetLastError());
-    }
-    GemmEpilogue ep{Y, ldy, SAM_F32, b, 0, inplace ? Y : nullptr, ldy, M};
-    return samk_gemm(a3, 3 * K, W3, 3 * K, M, N, 3 * K, SAM_BF16, ep, st);
+  auto self_w = [&](int l) {
+    const LayerW& L = w.layer[l];
+    const DerivedW::Tok& t = dw.tok[l];
+    SelfW sw{t.sq, L.self_attn.qb, t.sk, L.self_attn.kb, t.sv, L.self_attn.vb, t.so, L.self_attn.ob,
+             L.n1w, L.n1b, t.cq, L.t2i.qb};
+    return sw;
   };
-#define LINTC(...)                              \
-  do {                                          \
-    if (int rc_ = lin_tc(__VA_ARGS__)) return rc_; \
-  } while (0)
-#define LNORM(x, res, gw, gb, out, M)                                                                       \
-  do {                                                                                                      \
-    if (int rc_ = samk_layernorm_rows(x, C, res, C, gw, gb, 1e-5f, out, C, SAM_F32, M, C, 1, st)) return rc_; \
-  } while (0)
-
-  // token -> image attention: queries(+pe) attend to keys(+pe); result (after out_proj) added to `qry`, then LN.
-  auto token_to_image = [&](const AttnW& a, const uint16_t* k3, const uint16_t* v3, const float* gw,
-                            const float* gb) -> int {
-    LIN(qry, C, tok0, C, MT, a.qw, a.qb, nullptr, 0, tq, Ci, MT, Ci, C, 0);
-    LINTC(keys, C, pe_t, C, HW, k3, a.kb, false, kbuf, Ci, MK, Ci, C);
-    LINTC(keys, C, nullptr, 0, 0, v3, a.vb, false, vbuf, Ci, MK, Ci, C);
-    dim3 grid(s.heads, n, (T + TQ - 1) / TQ);
+  // image-side GEMM on the split operands: out[M, N] = A3[M, 3K] . W3[N, 3K]^T + bias   (fp32 out)
+  auto gemm3 = [&](const uint16_t* A3, const uint16_t* W3, const float* bias, float* out, int M, int N, int K) -> int {
+    samhost::ClassOverride as_decoder(samhost::KC_DECODER);
+    GemmEpilogue ep{out, N, SAM_F32, bias, 0, nullptr, 0, 0};
+    return samk_gemm(A3, 3 * K, W3, 3 * K, M, N, 3 * K, SAM_BF16, ep, st);
+  };
+  auto attn_t2i = [&](const float* kv, int ldkv, const float* rk, const int* idx, bool one_src) -> int {
     samhost::LaunchScope scope(samhost::KC_DECODER, st, 4.0 * n * T * HW * Ci);
-    dec_attn_t2i_kernel<<<grid, 256, t2i_smem, st>>>(tq, kbuf, vbuf, ta, T, HW, Ci, sc_cross);
+    dim3 grid(NCH, n);
+    if (big)
+      dec_attn_t2i_kernel<16><<<grid, 256, t2i_smem, st>>>(ws.tq, kv, ldkv, rk, idx, ws.part, T, HW, one_src ? 1 : 0);
+    else
+      dec_attn_t2i_kernel<8><<<grid, 256, t2i_smem, st>>>(ws.tq, kv, ldkv, rk, idx, ws.part, T, HW, one_src ? 1 : 0);
     SAM_CHECK_CUDA(cudaGetLastError());
-    LIN(ta, Ci, nullptr, 0, 0, a.ow, a.ob, qry, C, tb, C, MT, C, Ci, 0);
-    LNORM(tb, nullptr, gw, gb, qry, MT);
     return 0;
   };
 
-  // layer loop (transformer.py:151-182)
+  // ---- layer-0 image tokens (mask_decoder.py:146-149) and the first token sub-block (independent of each other)
+  {
+    dim3 grid(HW / 32, C / 32, n_src), blk(32, 8);
+    samhost::LaunchScope scope(samhost::KC_DECODER, st, 0.0, static_cast<double>(n_src) * HW * C * (2.0 + 4.0 + 6.0));
+    dec_keys0_kernel<<<grid, blk, 0, st>>>(image_embeddings, emb_fmt, img_index, dense_vec, dense_full, dense_fmt, ws.keys0,
+                                           ws.a3, C, HW);
+    SAM_CHECK_CUDA(cudaGetLastError());
+  }
+  {
+    samhost::LaunchScope scope(samhost::KC_DECODER, st, 2.0 * n * T * (4.0 * C * C + C * Ci));
+    const SelfW sw = self_w(0);
+    if (big)
+      dec_token_first_kernel<16><<<n, 256, tok_smem, st>>>(w.iou_token, w.mask_tokens, sparse, sparse_fmt, nm, k, sw, s.heads,
+                                                          ws.tok0, ws.q, ws.tq);
+    else
+      dec_token_first_kernel<8><<<n, 256, tok_smem, st>>>(w.iou_token, w.mask_tokens, sparse, sparse_fmt, nm, k, sw, s.heads,
+                                                         ws.tok0, ws.q, ws.tq);
+    SAM_CHECK_CUDA(cudaGetLastError());
+  }
+  const float sc_cross = 1.0f / sqrtf(static_cast<float>(Ci / s.heads));
+  const float* prev = ws.keys0;     // image tokens entering the layer
+  int rows_src = n_src;             // row blocks of `prev` / of the merged GEMM's output
+  const int* idx = src0;
+  bool one = single_src;
   for (int l = 0; l < s.depth; ++l) {
     const LayerW& L = w.layer[l];
-    const float* src = (l == 0) ? tok0 : qry;
-    const float* pe = (l == 0) ? nullptr : tok0;   // skip_first_layer_pe
-    // (1) self attention
-    LIN(src, C, pe, C, MT, L.self_attn.qw, L.self_attn.qb, nullptr, 0, tq, C, MT, C, C, 0);
-    LIN(src, C, pe, C, MT, L.self_attn.kw, L.self_attn.kb, nullptr, 0, tk, C, MT, C, C, 0);
-    LIN(src, C, nullptr, 0, 0, L.self_attn.vw, L.self_attn.vb, nullptr, 0, tv, C, MT, C, C, 0);
-    samhost::LaunchScope scope_sa(samhost::KC_DECODER, st, 4.0 * n * T * T * C);
-    dec_self_attn_kernel<<<n, 256, (3 * T * C + s.heads * T * T) * sizeof(float), st>>>(tq, tk, tv, ta, T, C, s.heads,
-                                                                                        sc_self);
-    SAM_CHECK_CUDA(cudaGetLastError());
-    LIN(ta, C, nullptr, 0, 0, L.self_attn.ow, L.self_attn.ob, (l == 0) ? nullptr : qry, C, tb, C, MT, C, C, 0);
-    LNORM(tb, nullptr, L.n1w, L.n1b, qry, MT);
-    // (2) token -> image cross attention
-    if (int rc = token_to_image(L.t2i, dw.t2i_k[l], dw.t2i_v[l], L.n2w, L.n2b)) return rc;
-    // (3) MLP (ReLU)
-    LIN(qry, C, nullptr, 0, 0, L.l1w, L.l1b, nullptr, 0, hid, s.mlp_dim, MT, s.mlp_dim, C, 1);
-    LIN(hid, s.mlp_dim, nullptr, 0, 0, L.l2w, L.l2b, qry, C, tb, C, MT, C, s.mlp_dim, 0);
-    LNORM(tb, nullptr, L.n3w, L.n3b, qry, MT);
-    // (4) image -> token cross attention
-    LINTC(keys, C, pe_t, C, HW, dw.i2t_q[l], L.i2t.qb, false, qbuf, Ci, MK, Ci, C);
-    LIN(qry, C, tok0, C, MT, L.i2t.kw, L.i2t.kb, nullptr, 0, tk, Ci, MT, Ci, C, 0);
-    LIN(qry, C, nullptr, 0, 0, L.i2t.vw, L.i2t.vb, nullptr, 0, tv, Ci, MT, Ci, C, 0);
+    const DerivedW::Tok& t = dw.tok[l];
+    // (a) k_t2i | v_t2i | q_i2t of this layer's image tokens in one GEMM
+    if (int rc = gemm3(ws.a3, dw.kvq[l], dw.b_kvq[l], ws.kvq, rows_src * HW, 3 * Ci, C)) return rc;
+    // (b) token -> image attention, out-proj + norm2 + MLP, norm3 + i2t k/v + next self-attention block
+    if (int rc = attn_t2i(ws.kvq, 3 * Ci, dw.rk[l], idx, one)) return rc;
     {
-      dim3 grid(HW / 32, n);
-      samhost::LaunchScope scope(samhost::KC_DECODER, st, 4.0 * n * T * HW * Ci);
-      dec_attn_i2t_kernel<<<grid, 256, 0, st>>>(qbuf, tk, tv, qbuf, T, HW, Ci, s.heads, sc_cross);
+      samhost::LaunchScope scope(samhost::KC_DECODER, st, 2.0 * n * T * (2.0 * C * H + 8.0 * Ci * C));
+      const CrossMlpW cw{t.co, L.t2i.ob, L.n2w, L.n2b, t.l1, L.l1b, t.l2};
+      dim3 grid(H / 256, n);
+      if (big)
+        dec_token_mlp_kernel<16><<<grid, 256, 0, st>>>(ws.part, ws.q, cw, T, H, ws.x2, ws.pmlp);
+      else
+        dec_token_mlp_kernel<8><<<grid, 256, 0, st>>>(ws.part, ws.q, cw, T, H, ws.x2, ws.pmlp);
       SAM_CHECK_CUDA(cudaGetLastError());
     }
-    LINTC(qbuf, Ci, nullptr, 0, 0, dw.i2t_o[l], L.i2t.ob, true, keys, C, MK, C, Ci);   // keys += out_proj(attn)
-    LNORM(keys, nullptr, L.n4w, L.n4b, keys, MK);
+    {
+      const bool has_next = l + 1 < s.depth;
+      samhost::LaunchScope scope(samhost::KC_DECODER, st, 2.0 * n * T * (2.0 * C * Ci + (has_next ? 4.0 * C * C : 0.0) + C * Ci));
+      const TailW tw{L.l2b, L.n3w, L.n3b, t.ikv, t.ikvb};
+      SelfW nw;
+      if (has_next) {
+        nw = self_w(l + 1);
+      } else {
+        nw = SelfW{};
+        nw.cqw = dw.fq;
+        nw.cqb = w.final_attn.qb;
+      }
+      if (big)
+        dec_token_tail_kernel<16><<<n, 256, tok_smem, st>>>(ws.x2, ws.pmlp, H / 256, tw, ws.tok0, T, s.heads, ws.tk, ws.tv,
+                                                           has_next ? 1 : 0, nw, ws.q, ws.tq);
+      else
+        dec_token_tail_kernel<8><<<n, 256, tok_smem, st>>>(ws.x2, ws.pmlp, H / 256, tw, ws.tok0, T, s.heads, ws.tk, ws.tv,
+                                                          has_next ? 1 : 0, nw, ws.q, ws.tq);
+      SAM_CHECK_CUDA(cudaGetLastError());
+    }
+    // (c) image -> token attention, out-proj GEMM, norm4 (+ the split operand of the next merged GEMM)
+    {
+      samhost::LaunchScope scope(samhost::KC_DECODER, st, 4.0 * n * T * HW * Ci);
+      dim3 grid(HW / 64, n);
+      if (big)
+        dec_attn_i2t_kernel<16><<<grid, 256, 0, st>>>(ws.kvq, 3 * Ci, 2 * Ci, dw.rq[l], idx, ws.tk, ws.tv, ws.a3o, T, HW,
+                                                     sc_cross, one ? 1 : 0);
+      else
+        dec_attn_i2t_kernel<8><<<grid, 256, 0, st>>>(ws.kvq, 3 * Ci, 2 * Ci, dw.rq[l], idx, ws.tk, ws.tv, ws.a3o, T, HW,
+                                                    sc_cross, one ? 1 : 0);
+      SAM_CHECK_CUDA(cudaGetLastError());
+    }
+    if (int rc = gemm3(ws.a3o, dw.i2t_o[l], L.i2t.ob, ws.delta, n * HW, C, Ci)) return rc;
+    {
+      const size_t rows = static_cast<size_t>(n) * HW;
+      samhost::LaunchScope scope(samhost::KC_DECODER, st, 0.0, static_cast<double>(rows) * C * (4.0 + 4.0 + 4.0 + 6.0));
+      dec_ln_split_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, st>>>(ws.delta, prev, idx, HW, L.n4w, L.n4b, ws.keys,
+                                                                                ws.a3, rows, one ? 1 : 0);
+      SAM_CHECK_CUDA(cudaGetLastError());
+    }
+    prev = ws.keys;       // from here on every prompt owns its image tokens
+    rows_src = n;
+    idx = nullptr;
+    one = false;
   }
-  // final token -> image attention + norm (transformer.py:99-104)
-  if (int rc = token_to_image(w.final_attn, dw.t2i_k[s.depth], dw.t2i_v[s.depth], w.nfw, w.nfb)) return rc;
-
-  // hypernetwork MLPs + IoU head
+  // ---- final token -> image attention + upscaling input in one GEMM: k_final | v_final | ConvT0
+  if (int rc = gemm3(ws.a3, dw.fin, dw.b_fin, ws.kvq, n * HW, 2 * Ci + C, C)) return rc;
+  if (int rc = attn_t2i(ws.kvq, 2 * Ci + C, dw.rk[s.depth], nullptr, false)) return rc;
   {
     HyperArgs h;
     for (int i = 0; i < nm; ++i) h.mlp[i] = w.hyper[i];
     h.mlp[nm] = w.iou_head;
     h.nm = nm; h.C = C; h.hidden_iou = s.iou_hidden; h.out_hyper = C / 8; h.T = T;
-    h.hs = qry; h.hyper = hyper; h.iou = iou; h.iou_fmt = out_fmt;
+    h.q = ws.q; h.part = ws.part; h.ow = dw.fo; h.ob = w.final_attn.ob; h.nfw = w.nfw; h.nfb = w.nfb;
+    h.hyper = ws.hyper; h.iou = iou; h.iou_fmt = out_fmt;
     dim3 grid(nm + 1, n);
     samhost::LaunchScope scope(samhost::KC_DECODER, st, 2.0 * n * (nm * (2.0 * C * C + C * C / 8) + 2.0 * C * C));
     dec_hyper_kernel<<<grid, 256, 0, st>>>(h);
     SAM_CHECK_CUDA(cudaGetLastError());
   }
-  // upscaling + mask product
-  LINTC(keys, C, nullptr, 0, 0, dw.up0, w.up0b, false, tmp, C, MK, C, C);
-  samhost::LaunchScope scope_up(samhost::KC_DECODER, st, 2.0 * MK * 4 * (4.0 * (C / 8) * (C / 4) + 4.0 * nm * (C / 8)));
-  dec_upscale_tail_kernel<<<static_cast<unsigned>((size_t)MK * 4 / 256), 256, 0, st>>>(
-      tmp, w.upln_w, w.upln_b, w.up1w, w.up1b, hyper, masks, out_fmt, g, nm);
-  SAM_CHECK_CUDA(cudaGetLastError());
-#undef LIN
-#undef LINTC
-#undef LNORM
+  {
+    const size_t MK = static_cast<size_t>(n) * HW;
+    samhost::LaunchScope scope(samhost::KC_DECODER, st, 2.0 * MK * 4 * (4.0 * (C / 8) * (C / 4) + 4.0 * nm * (C / 8)));
+    dec_upscale_tail_kernel<<<static_cast<unsigned>(MK * 4 / 256), 256, 0, st>>>(
+        ws.kvq + 2 * Ci, 2 * Ci + C, w.upln_w, w.upln_b, w.up1w, w.up1b, ws.hyper, masks, out_fmt, g, nm);
+    SAM_CHECK_CUDA(cudaGetLastError());
+  }
   return 0;
 }

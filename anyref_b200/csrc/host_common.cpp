@@ -127,10 +127,15 @@ struct Tot {
 } g_tot[KC_COUNT];
 }  // namespace
 
+static thread_local int g_class_override = -1;
+ClassOverride::ClassOverride(int cls) : prev_(g_class_override) { g_class_override = cls; }
+ClassOverride::~ClassOverride() { g_class_override = prev_; }
+
 LaunchScope::LaunchScope(int cls, cudaStream_t stream, double flops, double bytes, int launches)
     : slot_(-1), stream_(stream) {
   g_launches.fetch_add(launches, std::memory_order_relaxed);
   if (!g_profile_on.load(std::memory_order_relaxed)) return;
+  if (g_class_override >= 0) cls = g_class_override;
   std::lock_guard<std::mutex> lk(g_mu);
   if (g_used == g_recs.size()) {
     Rec r{};

@@ -61,6 +61,13 @@ struct LaunchScope {
   int slot_;
   cudaStream_t stream_;
 };
+// While alive on this thread, every LaunchScope is accounted to class `cls` (the mask decoder's tensor-core GEMMs are
+// launched through samk_gemm but belong to the decoder's time, not to the encoder GEMM roofline).
+struct ClassOverride {
+  explicit ClassOverride(int cls);
+  ~ClassOverride();
+  int prev_;
+};
 long long launch_count();
 void profile_enable(int on);
 // Folds all recorded event pairs into the totals; returns 0 or a CUDA error code.

@@ -94,13 +94,14 @@ size_t samk_encoder_workspace_bytes(const SamEncoderShape& s, int B);
 int samk_encoder_forward(const SamEncoderShape& s, const void* w16, const float* w32, const void* images, int in_fmt,
                          int B, void* out, int out_fmt, void* workspace, size_t workspace_bytes, cudaStream_t st);
 size_t samk_decoder_weight_elems(const SamDecoderShape& s);
-size_t samk_decoder_workspace_bytes(const SamDecoderShape& s, int n, int k);
+size_t samk_decoder_workspace_bytes(const SamDecoderShape& s, int n_images, int n, int k);
 size_t samk_decoder_derived_bytes(const SamDecoderShape& s);
-int samk_decoder_prepare(const SamDecoderShape& s, const float* blob, void* derived, cudaStream_t st);
+int samk_decoder_prepare(const SamDecoderShape& s, const float* blob, const void* image_pe, int pe_fmt, void* derived,
+                         cudaStream_t st);
 int samk_decoder_forward(const SamDecoderShape& s, const float* blob, const void* derived, const void* image_embeddings, int emb_fmt,
-                         const int* img_index, const void* image_pe, int pe_fmt, const void* sparse, int sparse_fmt,
-                         int n, int k, const void* dense_vec, const void* dense_full, int dense_fmt, void* masks,
-                         void* iou, int out_fmt, void* workspace, size_t workspace_bytes, cudaStream_t st);
+                         int n_images, const int* img_index, const void* sparse, int sparse_fmt, int n, int k,
+                         const void* dense_vec, const void* dense_full, int dense_fmt, void* masks, void* iou, int out_fmt,
+                         void* workspace, size_t workspace_bytes, cudaStream_t st);
 int samk_postprocess(const void* low, int low_fmt, int num_masks, int L, int S, int h_in, int w_in, int H, int W,
                      float* logits, uint8_t* binary, float threshold, cudaStream_t stream);
 int samk_postprocess_iou(const void* low, int low_fmt, int num_masks, int L, int S, int h_in, int w_in, int H, int W,

@@ -43,115 +43,144 @@ __device__ __forceinline__ float lerp1(float l0, float a, float l1, float b) {
   return __fadd_rn(__fmul_rn(l0, a), __fmul_rn(l1, b));
 }
 
-__device__ __forceinline__ float ld(const void* p, int fmt, size_t i) {
-  if (fmt == 2) return __ldg(static_cast<const float*>(p) + i);
-  return ptx::unpack1(__ldg(static_cast<const uint16_t*>(p) + i), fmt);
+// FMT is a template parameter of the kernel: with a run-time format every load sat in its own basic block behind a
+// three-way branch, so the 4 NC loads of a new low-res row were issued one after the other (no memory-level parallelism)
+template <int FMT>
+__device__ __forceinline__ float ld(const void* p, size_t i) {
+  if (FMT == 2) return __ldg(static_cast<const float*>(p) + i);
+  return ptx::unpack1(__ldg(static_cast<const uint16_t*>(p) + i), FMT);
 }
 
-constexpr int kPostRows = 32;    // output rows per CTA strip
-constexpr int kPostCols = 128;   // output columns per CTA (= threads)
+constexpr int kPostRows = 32;      // output rows per CTA strip
+constexpr int kPostThreads = 128;  // a thread owns NC columns, 32 apart (lane-contiguous: coalesced stores)
 
-// grid (ceil(W/128), ceil(H/32), num_masks), block 128.
+// grid (ceil(W / (NC * 128)), ceil(H / 32), num_masks), block 128.  Warp w of a CTA covers columns
+// [x_cta + w * 32 * NC, + 32 * NC): column j of lane l is x_warp + 32 j + l.  The row-dependent work (row taps, cache
+// decisions, loop overhead) is shared by the NC columns of a thread -- with one column per thread the kernel was
+// issue-bound on exactly that work (ncu r02: SM 82 %, DRAM 2 %).
 // With `target` / `counts` the intersectionAndUnionGPU statistics of the thresholded mask (utils/utils.py:79-91, K = 2,
 // ignore_index = 255) are accumulated in the same pass: counts[m] = {inter_0, inter_1, pred_0, pred_1, target_0,
 // target_1} (int32, atomically added), so the evaluation loop (eval_referseg.py:186-211) needs neither the full
 // resolution logits nor the mask in HBM.
-__global__ void __launch_bounds__(kPostCols)
-postprocess_kernel(const void* __restrict__ low, int low_fmt, int L, int S, int h_in, int w_in, int H, int W,
+template <int NC, int FMT>
+__global__ void __launch_bounds__(kPostThreads)
+postprocess_kernel(const void* __restrict__ low, int L, int S, int h_in, int w_in, int H, int W,
                    float* __restrict__ logits, uint8_t* __restrict__ binary, uint8_t* __restrict__ packed, float threshold,
                    const uint8_t* __restrict__ target, int* __restrict__ counts) {
   const int m = blockIdx.z;
-  const int Xr = blockIdx.x * kPostCols + threadIdx.x;
-  const bool col_ok = Xr < W;
-  const int X = col_ok ? Xr : W - 1;          // out-of-range threads shadow the last column (no stores)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int xw = (blockIdx.x * (kPostThreads / 32) + warp) * (32 * NC);     // first column of this warp
   const int Y0 = blockIdx.y * kPostRows;
   const int Y1 = min(Y0 + kPostRows, H);
   const float scale1 = static_cast<float>(L) / static_cast<float>(S);
   const float sy = static_cast<float>(h_in) / static_cast<float>(H);
   const float sx = static_cast<float>(w_in) / static_cast<float>(W);
   const size_t base = static_cast<size_t>(m) * L * L;
-  // this thread's column taps: stage 2 (X -> stage-1 columns x0, x1), stage 1 (x0, x1 -> low-res columns)
-  const Tap tx = make_tap(X, sx, w_in);
-  const Tap ca = make_tap(tx.i0, scale1, L), cb = make_tap(tx.i1, scale1, L);
-
-  // low-res row cache: horizontal lerps at stage-1 columns x0 (a) and x1 (b)
+  // column taps: stage 2 (X -> stage-1 columns x0, x1), stage 1 (x0, x1 -> low-res columns)
+  bool col_ok[NC];
+  Tap tx[NC], ca[NC], cb[NC];
+#pragma unroll
+  for (int j = 0; j < NC; ++j) {
+    const int Xr = xw + 32 * j + lane;
+    col_ok[j] = Xr < W;
+    tx[j] = make_tap(col_ok[j] ? Xr : W - 1, sx, w_in);    // out-of-range columns shadow the last one (no stores)
+    ca[j] = make_tap(tx[j].i0, scale1, L);
+    cb[j] = make_tap(tx[j].i1, scale1, L);
+  }
+  // low-res row cache (rows hr0, hr1): horizontal lerps at stage-1 columns x0 (a) and x1 (b) of every column
   int hr0 = -1, hr1 = -1;
-  float ha0 = 0.f, hb0 = 0.f, ha1 = 0.f, hb1 = 0.f;
-  auto load_h = [&](int i, float& ha, float& hb) {
+  float ha0[NC], hb0[NC], ha1[NC], hb1[NC];
+  auto load_h = [&](int i, float (&ha)[NC], float (&hb)[NC]) {
     const size_t r = base + static_cast<size_t>(i) * L;
-    ha = lerp1(ca.l0, ld(low, low_fmt, r + ca.i0), ca.l1, ld(low, low_fmt, r + ca.i1));
-    hb = lerp1(cb.l0, ld(low, low_fmt, r + cb.i0), cb.l1, ld(low, low_fmt, r + cb.i1));
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      ha[j] = lerp1(ca[j].l0, ld<FMT>(low, r + ca[j].i0), ca[j].l1, ld<FMT>(low, r + ca[j].i1));
+      hb[j] = lerp1(cb[j].l0, ld<FMT>(low, r + cb[j].i0), cb[j].l1, ld<FMT>(low, r + cb[j].i1));
+    }
   };
   // stage-2 horizontal lerp g(y) of stage-1 row y (all branches depend on y only: warp-uniform)
-  auto stage1_row = [&](int y) -> float {
+  auto stage1_row = [&](int y, float (&g)[NC]) {
     const Tap t = make_tap(y, scale1, L);
     if (t.i0 == hr1) {
-      hr0 = hr1; ha0 = ha1; hb0 = hb1;
+      hr0 = hr1;
+#pragma unroll
+      for (int j = 0; j < NC; ++j) { ha0[j] = ha1[j]; hb0[j] = hb1[j]; }
       hr1 = -1;
     }
     if (t.i0 != hr0) {
       load_h(t.i0, ha0, hb0);
       hr0 = t.i0;
     }
-    float a1 = ha0, b1 = hb0;
     if (t.i1 != t.i0) {
       if (t.i1 != hr1) {
         load_h(t.i1, ha1, hb1);
         hr1 = t.i1;
       }
-      a1 = ha1; b1 = hb1;
+#pragma unroll
+      for (int j = 0; j < NC; ++j) {
+        const float sa = lerp1(t.l0, ha0[j], t.l1, ha1[j]);     // stage-1 value at (y, x0)
+        const float sb = lerp1(t.l0, hb0[j], t.l1, hb1[j]);     // stage-1 value at (y, x1)
+        g[j] = lerp1(tx[j].l0, sa, tx[j].l1, sb);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < NC; ++j) {
+        const float sa = lerp1(t.l0, ha0[j], t.l1, ha0[j]);
+        const float sb = lerp1(t.l0, hb0[j], t.l1, hb0[j]);
+        g[j] = lerp1(tx[j].l0, sa, tx[j].l1, sb);
+      }
     }
-    const float sa = lerp1(t.l0, ha0, t.l1, a1);     // stage-1 value at (y, x0)
-    const float sb = lerp1(t.l0, hb0, t.l1, b1);     // stage-1 value at (y, x1)
-    return lerp1(tx.l0, sa, tx.l1, sb);
   };
   int gr0 = -1, gr1 = -1;
-  float g0 = 0.f, g1 = 0.f;
+  float g0[NC], g1[NC];
   int cnt[6] = {0, 0, 0, 0, 0, 0};
-  const int lane = threadIdx.x & 31;
 #pragma unroll 1
   for (int Y = Y0; Y < Y1; ++Y) {
     const Tap ty = make_tap(Y, sy, h_in);
     if (ty.i0 == gr1) {
-      gr0 = gr1; g0 = g1;
+      gr0 = gr1;
+#pragma unroll
+      for (int j = 0; j < NC; ++j) g0[j] = g1[j];
       gr1 = -1;
     }
     if (ty.i0 != gr0) {
-      g0 = stage1_row(ty.i0);
+      stage1_row(ty.i0, g0);
       gr0 = ty.i0;
     }
-    float gb = g0;
-    if (ty.i1 != ty.i0) {
-      if (ty.i1 != gr1) {
-        g1 = stage1_row(ty.i1);
-        gr1 = ty.i1;
-      }
-      gb = g1;
+    const bool two = ty.i1 != ty.i0;
+    if (two && ty.i1 != gr1) {
+      stage1_row(ty.i1, g1);
+      gr1 = ty.i1;
     }
-    const float v = lerp1(ty.l0, g0, ty.l1, gb);
-    const bool on = v > threshold;
-    const size_t o = (static_cast<size_t>(m) * H + Y) * W + X;
-    if (col_ok) {
-      if (logits) logits[o] = v;
-      if (binary) binary[o] = on ? 1 : 0;
-      if (counts) {
-        const int t = target[o];
-        if (t != 255) {
-          const int p = on ? 1 : 0;          // static indices only: the counters stay in registers
-          cnt[2] += (p == 0); cnt[3] += (p == 1);
-          cnt[4] += (t == 0); cnt[5] += (t == 1);
-          cnt[0] += (t == 0 && p == 0); cnt[1] += (t == 1 && p == 1);
+    const size_t orow = (static_cast<size_t>(m) * H + Y) * W;
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      const float v = lerp1(ty.l0, g0[j], ty.l1, two ? g1[j] : g0[j]);
+      const bool on = v > threshold;
+      const int Xr = xw + 32 * j + lane;
+      const size_t o = orow + Xr;
+      if (col_ok[j]) {
+        if (logits) logits[o] = v;
+        if (binary) binary[o] = on ? 1 : 0;
+        if (counts) {
+          const int t = target[o];
+          if (t != 255) {
+            const int p = on ? 1 : 0;          // static indices only: the counters stay in registers
+            cnt[2] += (p == 0); cnt[3] += (p == 1);
+            cnt[4] += (t == 0); cnt[5] += (t == 1);
+            cnt[0] += (t == 0 && p == 0); cnt[1] += (t == 1 && p == 1);
+          }
         }
       }
-    }
-    if (packed) {
-      // numpy.packbits order: pixel 8k of the flattened [num_masks, H, W] stream is the MSB of byte k.  A warp covers 32
-      // consecutive columns = 4 bytes; W % 8 == 0 (checked by the launcher), so a byte is inside the row or outside it.
-      const uint32_t bits = __ballot_sync(0xffffffffu, on && col_ok);
-      const uint32_t bytes = __byte_perm(__brev(bits), 0, 0x0123);
-      const int xb = Xr - lane + 8 * lane;     // first column of byte `lane` (lanes 0..3)
-      if (lane < 4 && xb < W)
-        packed[((static_cast<size_t>(m) * H + Y) * W + xb) >> 3] = static_cast<uint8_t>(bytes >> (8 * lane));
+      if (packed) {
+        // numpy.packbits order: pixel 8k of the flattened [num_masks, H, W] stream is the MSB of byte k.  The 32 lanes
+        // hold 32 consecutive columns = 4 bytes; W % 8 == 0 (checked by the launcher), so a byte is inside the row or
+        // outside it.
+        const uint32_t bits = __ballot_sync(0xffffffffu, on && col_ok[j]);
+        const uint32_t bytes = __byte_perm(__brev(bits), 0, 0x0123);
+        const int xb = xw + 32 * j + 8 * lane;     // first column of byte `lane` (lanes 0..3)
+        if (lane < 4 && xb < W) packed[(orow + xb) >> 3] = static_cast<uint8_t>(bytes >> (8 * lane));
+      }
     }
   }
   if (counts) {
@@ -218,14 +247,18 @@ int samk_postprocess_iou(const void* low, int low_fmt, int num_masks, int L, int
   SAM_REQUIRE((target == nullptr) == (counts == nullptr), "postprocess: target and counts go together");
   SAM_REQUIRE(low_fmt >= 0 && low_fmt <= 2, "postprocess: bad input format");
   SAM_REQUIRE(num_masks <= 65535, "postprocess: at most 65535 masks per call");
-  dim3 blk(kPostCols);
-  dim3 grid((W + kPostCols - 1) / kPostCols, (H + kPostRows - 1) / kPostRows, num_masks);
+  const int nc = (W > 256) ? 4 : 1;    // columns per thread (narrow outputs: one, so that the columns spread over warps)
+  dim3 blk(kPostThreads);
+  dim3 grid((W + nc * kPostThreads - 1) / (nc * kPostThreads), (H + kPostRows - 1) / kPostRows, num_masks);
   samhost::LaunchScope scope(samhost::KC_POSTPROCESS, stream, 0.0,
                              static_cast<double>(num_masks) *
                                  (static_cast<double>(L) * L * (low_fmt == 2 ? 4.0 : 2.0) +
                                   static_cast<double>(H) * W * ((logits ? 4.0 : 0.0) + (binary ? 1.0 : 0.0) + (packed ? 0.125 : 0.0) + (target ? 1.0 : 0.0))));
-  postprocess_kernel<<<grid, blk, 0, stream>>>(low, low_fmt, L, S, h_in, w_in, H, W, logits, binary, packed, threshold,
-                                               target, counts);
+  typedef void (*Fn)(const void*, int, int, int, int, int, int, float*, uint8_t*, uint8_t*, float, const uint8_t*, int*);
+  static const Fn fns[2][3] = {{postprocess_kernel<1, 0>, postprocess_kernel<1, 1>, postprocess_kernel<1, 2>},
+                               {postprocess_kernel<4, 0>, postprocess_kernel<4, 1>, postprocess_kernel<4, 2>}};
+  fns[nc == 4][low_fmt]<<<grid, blk, 0, stream>>>(low, L, S, h_in, w_in, H, W, logits, binary, packed, threshold, target,
+                                                  counts);
   SAM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -66,16 +66,22 @@ class MaskDecoder(nn.Module):
         self._packed = None
 
     @_lib.device_scoped
-    def _weights(self, grid: int):
-        sig = (_runtime.params_signature(self), grid)
+    def _weights(self, grid: int, pe: torch.Tensor):
+        """(shape, fp32 weight blob, derived buffer).  The derived buffer (split / transposed weight copies and the
+        positional halves pe.W^T + b of the image-side projections) is rebuilt when a parameter or the dense positional
+        encoding changes; PromptEncoder.get_dense_pe() returns a cached tensor, so this is once per model in practice."""
+        sig = (_runtime.params_signature(self), grid, pe.data_ptr(), pe._version, pe.dtype)
         if self._packed is None or self._packed[0] != sig:
             shape, blob = _pack.pack_decoder(self, grid)
             lib = _lib.load()
-            derived = torch.empty(lib.sam_decoder_derived_bytes(C.byref(shape)), dtype=torch.uint8, device=blob.device)
-            rc = lib.sam_decoder_prepare(C.byref(shape), blob.data_ptr(), derived.data_ptr(), _lib.stream_ptr(blob.device))
+            nbytes = lib.sam_decoder_derived_bytes(C.byref(shape))
+            derived = torch.empty(nbytes + 256, dtype=torch.uint8, device=blob.device)
+            dptr = (derived.data_ptr() + 255) & ~255
+            rc = lib.sam_decoder_prepare(C.byref(shape), blob.data_ptr(), pe.data_ptr(), _lib.fmt_of(pe.dtype), dptr,
+                                         _lib.stream_ptr(blob.device))
             _lib.check(rc, "sam_decoder_prepare")
-            self._packed = (sig, shape, blob, derived)
-        return self._packed[1:]
+            self._packed = (sig, shape, blob, (derived, dptr), pe)     # pe kept alive: its address is part of the key
+        return self._packed[1:4]
 
     def forward(self, image_embeddings: torch.Tensor, image_pe: torch.Tensor,
                 sparse_prompt_embeddings: torch.Tensor, dense_prompt_embeddings: torch.Tensor,
@@ -136,15 +142,16 @@ class MaskDecoder(nn.Module):
             image_index = image_index.contiguous()
         elif emb.shape[0] != 1:
             raise ValueError("image_index is required when several image embeddings are given")
-        shape, blob, derived = self._weights(g)
+        shape, blob, (_derived_keep, derived_ptr) = self._weights(g, pe)
         out_dtype = emb.dtype
         masks = torch.empty((n, self.num_mask_tokens, 4 * g, 4 * g), device=emb.device, dtype=out_dtype)
         iou = torch.empty((n, self.num_mask_tokens), device=emb.device, dtype=out_dtype)
-        nbytes = lib.sam_decoder_workspace_bytes(C.byref(shape), n, k)
+        n_images = emb.shape[0]
+        nbytes = lib.sam_decoder_workspace_bytes(C.byref(shape), n_images, n, k)
         keep, wsp = _runtime.workspace(emb.device, nbytes, "decoder")
         rc = lib.sam_decoder_forward(
-            C.byref(shape), blob.data_ptr(), derived.data_ptr(), emb.data_ptr(), _lib.fmt_of(emb.dtype),
-            image_index.data_ptr() if image_index is not None else None, pe.data_ptr(), _lib.fmt_of(pe.dtype),
+            C.byref(shape), blob.data_ptr(), derived_ptr, emb.data_ptr(), _lib.fmt_of(emb.dtype), n_images,
+            image_index.data_ptr() if image_index is not None else None,
             sparse.data_ptr() if k > 0 else None, _lib.fmt_of(sparse.dtype), n, k,
             dense_vec.data_ptr() if dense_vec is not None else None,
             dense_full.data_ptr() if dense_full is not None else None, _lib.fmt_of(dense.dtype),

@@ -165,28 +165,33 @@ int sam_encoder_forward(const SamEncoderShape* shape, const void* w16, const flo
 
 /*
  * MaskDecoder.forward / predict_masks (mask_decoder.py:75-179) incl. TwoWayTransformer (transformer.py:62-106) for n
- * prompts in one call.  Prompt p uses image embedding img_index[p] (img_index == NULL: all prompts use image 0, the
- * reference's per-image call, model/anyref.py:807).
+ * prompts in one call.  Prompt p uses image embedding img_index[p] (img_index == NULL: n_images must be 1 and all
+ * prompts use it -- the reference's per-image call, model/anyref.py:807).
  *   weights          fp32 blob, state_dict order of mask_decoder.* with the two ConvTranspose2d weights rearranged
  *                    (see csrc/decoder.cu carve_weights); size from sam_decoder_weight_elems
- *   image_embeddings [Bimg, C, g, g] emb_fmt;  image_pe [1, C, g, g] pe_fmt
- *   sparse           [n, k, C] sparse_fmt (the [SEG] embeddings; tokens = [iou, mask x4, sparse...])
+ *   derived          device buffer of sam_decoder_derived_bytes() bytes (256-byte aligned) filled by
+ *                    sam_decoder_prepare whenever `weights` or the dense positional encoding change: split-bf16 and
+ *                    transposed weight copies and the positional halves pe.W^T + b of the image-side projections
+ *                    ((keys + pe).W^T = keys.W^T + pe.W^T; prompt_encoder.get_dense_pe() is a constant of the model)
+ *   image_pe         [1, C, g, g] pe_fmt, PromptEncoder.get_dense_pe()  (argument of sam_decoder_prepare)
+ *   image_embeddings [n_images, C, g, g] emb_fmt
+ *   sparse           [n, k, C] sparse_fmt (the [SEG] embeddings; tokens = [iou, mask x4, sparse...]); 5 + k <= 16
  *   dense_vec        [C] (no_mask_embed broadcast, prompt_encoder.py:181-184) or NULL;
  *   dense_full       [n, C, g, g] or NULL (mask prompts); both in dense_fmt
  *   masks            [n, num_mask_tokens, 4g, 4g] out_fmt -- ALL mask tokens (caller slices [0:1] or [1:], :106-111)
  *   iou              [n, num_mask_tokens] out_fmt
+ *   workspace        256-byte aligned scratch of sam_decoder_workspace_bytes(shape, n_images, n, k) bytes
  */
 size_t sam_decoder_weight_elems(const SamDecoderShape* shape);
-size_t sam_decoder_workspace_bytes(const SamDecoderShape* shape, int n, int k);
-/* `derived`: device buffer of sam_decoder_derived_bytes() bytes holding split-bf16 copies of the weights that multiply
- * image-token-sized operands; filled by sam_decoder_prepare whenever `weights` change. */
+size_t sam_decoder_workspace_bytes(const SamDecoderShape* shape, int n_images, int n, int k);
 size_t sam_decoder_derived_bytes(const SamDecoderShape* shape);
-int sam_decoder_prepare(const SamDecoderShape* shape, const float* weights, void* derived, void* stream);
+int sam_decoder_prepare(const SamDecoderShape* shape, const float* weights, const void* image_pe, int pe_fmt,
+                        void* derived, void* stream);
 int sam_decoder_forward(const SamDecoderShape* shape, const float* weights, const void* derived,
-                        const void* image_embeddings, int emb_fmt,
-                        const int* img_index, const void* image_pe, int pe_fmt, const void* sparse, int sparse_fmt,
-                        int n, int k, const void* dense_vec, const void* dense_full, int dense_fmt, void* masks,
-                        void* iou, int out_fmt, void* workspace, size_t workspace_bytes, void* stream);
+                        const void* image_embeddings, int emb_fmt, int n_images, const int* img_index,
+                        const void* sparse, int sparse_fmt, int n, int k, const void* dense_vec, const void* dense_full,
+                        int dense_fmt, void* masks, void* iou, int out_fmt, void* workspace, size_t workspace_bytes,
+                        void* stream);
 
 /*
  * Sam.postprocess_masks (sam.py:159-172) fused: bilinear L x L -> S x S, crop [:h_in, :w_in], bilinear -> H x W, both

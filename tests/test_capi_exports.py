@@ -45,7 +45,7 @@ def test_sizes_and_errors_without_gpu(lib):
     from anyref_b200 import _lib
 
     L = _lib.load()
-    assert L.sam_abi_version() == 2
+    assert L.sam_abi_version() == 3
     enc = _lib.SamEncoderShape(embed_dim=1280, depth=32, heads=16, mlp_dim=5120, img=1024, patch=16, window=14,
                                out_chans=256, fmt=1, global_mask=0, tap_block=-1, tap_out=None)
     n16 = L.sam_encoder_w16_elems(ctypes.byref(enc))
