@@ -292,41 +292,63 @@ constexpr int DCI = 128;    // cross-attention internal dim
 constexpr int NCH = 16;     // key chunks of the split token->image attention
 constexpr int PART = 16 + DCI;   // floats per (chunk, token): m[8 heads], l[8 heads], o[128]
 
-// ys[t][c] = act(sum_k xs[t][k] * Wt[k][c] + b[c]) for t < TT, c = threadIdx.x < ncols (256 threads).
-// xs / ys in shared memory (row strides ldx / ldy floats, 16-byte aligned rows); Wt [K, ldw] fp32 in global memory.
+constexpr int kTokThreads = 1024;   // token kernels: 256 columns x a 4-way split of the reduction dimension
+constexpr int kKSplit = kTokThreads / 256;
+
+// ys[t][c] = act(sum_k xs[t][k] * Wt[k][c] + b[c]) for t < TT, c < ncols <= 256 (block of kTokThreads threads, ALL of
+// which must call this: it contains two block barriers and ends with one, so ys may be consumed right after).
+// xs / ys in shared memory (row strides ldx / ldy floats, 16-byte aligned rows); Wt [K, ldw] fp32 in global memory;
+// rs: shared scratch [kKSplit - 1][TT][256].  Thread (ks, c) walks column c over its quarter of K with 16 loads in
+// flight; with 256 threads per prompt and 8 loads in flight the layer was bound by the L2 latency of the weight
+// stream (ncu r02: 30 us per 256 x 256 linear).  The partials are summed in a fixed order: bit-reproducible.
 template <int TT>
 __device__ __forceinline__ void tok_linear(const float* __restrict__ Wt, int ldw, const float* __restrict__ b, int ncols,
-                                           const float* xs, int ldx, int K, float* ys, int ldy, bool relu) {
-  const int c = threadIdx.x;
-  if (c < ncols) {
-    float acc[TT];
-    const float bias = b ? __ldg(b + c) : 0.f;
+                                           const float* xs, int ldx, int K, float* ys, int ldy, bool relu, float* rs) {
+  const int c = threadIdx.x & 255, ks = threadIdx.x >> 8;
+  const int kq = K / kKSplit;
+  float acc[TT];
 #pragma unroll
-    for (int t = 0; t < TT; ++t) acc[t] = bias;
-    const float* w = Wt + c;
-#pragma unroll 2
-    for (int k = 0; k < K; k += 4) {
+  for (int t = 0; t < TT; ++t) acc[t] = 0.f;
+  if (c < ncols) {
+    const float* w = Wt + static_cast<size_t>(ks * kq) * ldw + c;
+    const float* x0 = xs + ks * kq;
+#pragma unroll 4
+    for (int k = 0; k < kq; k += 4) {
       const float w0 = __ldg(w + static_cast<size_t>(k) * ldw), w1 = __ldg(w + static_cast<size_t>(k + 1) * ldw);
       const float w2 = __ldg(w + static_cast<size_t>(k + 2) * ldw), w3 = __ldg(w + static_cast<size_t>(k + 3) * ldw);
 #pragma unroll
       for (int t = 0; t < TT; ++t) {
-        const float4 x = *reinterpret_cast<const float4*>(xs + t * ldx + k);
+        const float4 x = *reinterpret_cast<const float4*>(x0 + t * ldx + k);
         acc[t] = fmaf(x.x, w0, acc[t]);
         acc[t] = fmaf(x.y, w1, acc[t]);
         acc[t] = fmaf(x.z, w2, acc[t]);
         acc[t] = fmaf(x.w, w3, acc[t]);
       }
     }
+    if (ks > 0) {
 #pragma unroll
-    for (int t = 0; t < TT; ++t) ys[t * ldy + c] = relu ? fmaxf(acc[t], 0.f) : acc[t];
+      for (int t = 0; t < TT; ++t) rs[((ks - 1) * TT + t) * 256 + c] = acc[t];
+    }
   }
+  __syncthreads();
+  if (ks == 0 && c < ncols) {
+    const float bias = b ? __ldg(b + c) : 0.f;
+#pragma unroll
+    for (int t = 0; t < TT; ++t) {
+      float v = acc[t] + bias;
+#pragma unroll
+      for (int j = 0; j < kKSplit - 1; ++j) v += rs[(j * TT + t) * 256 + c];
+      ys[t * ldy + c] = relu ? fmaxf(v, 0.f) : v;
+    }
+  }
+  __syncthreads();
 }
 
 // rows t < T of xs [.., DC] (optionally + res rows) -> LayerNorm(eps 1e-5) -> out (shared) and out_g (global, optional)
 __device__ __forceinline__ void tok_layernorm(const float* xs, const float* res, const float* __restrict__ gw,
                                               const float* __restrict__ gb, float* out, float* out_g, int T) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int t = warp; t < T; t += 8) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int t = warp; t < T; t += nwarps) {
     float v[8];
     float s = 0.f;
 #pragma unroll
@@ -364,26 +386,26 @@ struct SelfW {   // transposed [K, N] weights + biases of one self-attention + n
 // smem: xs, pe [TT][DC]; b0, b1, b2 [TT][DC] scratch; sc [8][TT][TT]
 template <int TT>
 __device__ __forceinline__ void tok_self_block(const SelfW& w, bool first, float* xs, const float* pe, float* b0, float* b1,
-                                               float* b2, float* sc, int T, int heads, float* q_g, float* tq_g) {
+                                               float* b2, float* sc, float* rs, int T, int heads, float* q_g, float* tq_g) {
   const int tid = threadIdx.x;
   // b2 = xs + pe (layer 0: xs), the q / k input
-  for (int i = tid; i < T * DC; i += 256) b2[i] = first ? xs[i] : xs[i] + pe[i];
+  for (int i = tid; i < T * DC; i += kTokThreads) b2[i] = first ? xs[i] : xs[i] + pe[i];
   __syncthreads();
-  tok_linear<TT>(w.qw, DC, w.qb, DC, b2, DC, DC, b0, DC, false);    // q
-  tok_linear<TT>(w.kw, DC, w.kb, DC, b2, DC, DC, b1, DC, false);    // k
+  tok_linear<TT>(w.qw, DC, w.qb, DC, b2, DC, DC, b0, DC, false, rs);    // q
+  tok_linear<TT>(w.kw, DC, w.kb, DC, b2, DC, DC, b1, DC, false, rs);    // k
   __syncthreads();
-  tok_linear<TT>(w.vw, DC, w.vb, DC, xs, DC, DC, b2, DC, false);    // v (b2's old content is dead)
+  tok_linear<TT>(w.vw, DC, w.vb, DC, xs, DC, DC, b2, DC, false, rs);    // v (b2's old content is dead)
   __syncthreads();
   const int dh = DC / heads;
   const float scale = 1.0f / sqrtf(static_cast<float>(dh));
-  for (int i = tid; i < heads * T * T; i += 256) {
+  for (int i = tid; i < heads * T * T; i += kTokThreads) {
     const int t2 = i % T, t1 = (i / T) % T, h = i / (T * T);
     float a = 0.f;
     for (int d = 0; d < dh; ++d) a = fmaf(b0[t1 * DC + h * dh + d], b1[t2 * DC + h * dh + d], a);
     sc[i] = a * scale;
   }
   __syncthreads();
-  for (int i = tid; i < heads * T; i += 256) {
+  for (int i = tid; i < heads * T; i += kTokThreads) {
     float* r = sc + i * T;
     float m = -INFINITY;
     for (int t = 0; t < T; ++t) m = fmaxf(m, r[t]);
@@ -396,30 +418,31 @@ __device__ __forceinline__ void tok_self_block(const SelfW& w, bool first, float
     for (int t = 0; t < T; ++t) r[t] *= inv;
   }
   __syncthreads();
-  for (int i = tid; i < T * DC; i += 256) {      // b1 <- attn (k is dead after the scores)
+  for (int i = tid; i < T * DC; i += kTokThreads) {      // b1 <- attn (k is dead after the scores)
     const int c = i % DC, t1 = i / DC, h = c / dh;
     float a = 0.f;
     for (int t2 = 0; t2 < T; ++t2) a = fmaf(sc[(h * T + t1) * T + t2], b2[t2 * DC + c], a);
     b1[i] = a;
   }
   __syncthreads();
-  tok_linear<TT>(w.ow, DC, w.ob, DC, b1, DC, DC, b0, DC, false);   // out_proj -> b0
+  tok_linear<TT>(w.ow, DC, w.ob, DC, b1, DC, DC, b0, DC, false, rs);   // out_proj -> b0
   __syncthreads();
   tok_layernorm(b0, first ? nullptr : xs, w.n1w, w.n1b, xs, q_g, T);
   __syncthreads();
-  for (int i = tid; i < T * DC; i += 256) b2[i] = xs[i] + pe[i];
+  for (int i = tid; i < T * DC; i += kTokThreads) b2[i] = xs[i] + pe[i];
   __syncthreads();
-  tok_linear<TT>(w.cqw, DCI, w.cqb, DCI, b2, DC, DC, b0, DCI, false);
+  tok_linear<TT>(w.cqw, DCI, w.cqb, DCI, b2, DC, DC, b0, DCI, false, rs);
   __syncthreads();
   const float sc_cross = 1.0f / sqrtf(static_cast<float>(DCI / heads));
-  for (int i = tid; i < T * DCI; i += 256) tq_g[i] = b0[i] * sc_cross;
+  for (int i = tid; i < T * DCI; i += kTokThreads) tq_g[i] = b0[i] * sc_cross;
 }
 
-constexpr int tok_smem_floats(int TT) { return 5 * TT * DC + 8 * TT * TT; }
+constexpr int mlp_smem_floats(int TT) { return TT * DCI + 2 * TT * DC + (kKSplit - 1) * TT * 256; }
+constexpr int tok_smem_floats(int TT) { return 5 * TT * DC + 8 * TT * TT + (kKSplit - 1) * TT * 256; }
 
 // T1 of layer 0: token assembly (mask_decoder.py:126-141) + the first self-attention sub-block.   grid n, block 256
 template <int TT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kTokThreads)
 dec_token_first_kernel(const float* __restrict__ iou_token, const float* __restrict__ mask_tokens, const void* __restrict__ sparse,
                        int sparse_fmt, int nm, int k, const SelfW w, int heads, float* __restrict__ tok0_g,
                        float* __restrict__ q_g, float* __restrict__ tq_g) {
@@ -431,7 +454,8 @@ dec_token_first_kernel(const float* __restrict__ iou_token, const float* __restr
   float* b1 = b0 + TT * DC;
   float* b2 = b1 + TT * DC;
   float* sc = b2 + TT * DC;
-  for (int i = tid; i < T * DC; i += 256) {
+  float* rs = sc + 8 * TT * TT;
+  for (int i = tid; i < T * DC; i += kTokThreads) {
     const int c = i % DC, t = i / DC;
     float v;
     if (t == 0)
@@ -445,7 +469,7 @@ dec_token_first_kernel(const float* __restrict__ iou_token, const float* __restr
     tok0_g[static_cast<size_t>(p) * T * DC + i] = v;    // query_pe of every later layer (transformer.py:95)
   }
   __syncthreads();
-  tok_self_block<TT>(w, true, xs, pe, b0, b1, b2, sc, T, heads, q_g + static_cast<size_t>(p) * T * DC,
+  tok_self_block<TT>(w, true, xs, pe, b0, b1, b2, sc, rs, T, heads, q_g + static_cast<size_t>(p) * T * DC,
                      tq_g + static_cast<size_t>(p) * T * DCI);
 }
 
@@ -541,7 +565,7 @@ dec_attn_t2i_kernel(const float* __restrict__ tq, const float* __restrict__ kv, 
 
 // combine the NCH chunk partials of prompt p into the attention output rows ta[t][0:128] (shared memory), t in [t0, t1)
 __device__ __forceinline__ void t2i_combine(const float* __restrict__ part, int p, int T, int t0, int t1, float* ta) {
-  for (int i = threadIdx.x; i < (t1 - t0) * DCI; i += 256) {
+  for (int i = threadIdx.x; i < (t1 - t0) * DCI; i += blockDim.x) {
     const int t = t0 + i / DCI, c = i % DCI, h = c >> 4;
     const float* base = part + (static_cast<size_t>(p) * NCH * T + t) * PART;
     float M = -INFINITY;
@@ -568,26 +592,28 @@ struct CrossMlpW {   // after the token->image attention: out_proj + norm2, MLP;
 // 256-wide slice j of the MLP hidden layer: part_mlp[p][j] = relu(x.W1_j^T + b1_j) . W2[:, j]^T  (transformer.py:166-172).
 // CTA j == 0 also publishes the post-norm2 queries.   grid (H / 256, n), block 256
 template <int TT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kTokThreads)
 dec_token_mlp_kernel(const float* __restrict__ part, float* __restrict__ q_g, const CrossMlpW w, int T, int H,
                      float* __restrict__ x2_g, float* __restrict__ part_mlp) {
-  __shared__ __align__(16) float ta[TT * DCI];
-  __shared__ __align__(16) float xs[TT * DC];
-  __shared__ __align__(16) float ys[TT * DC];
+  extern __shared__ __align__(16) float tsm[];
+  float* ta = tsm;                   // [TT][DCI]
+  float* xs = ta + TT * DCI;         // [TT][DC]
+  float* ys = xs + TT * DC;          // [TT][DC]
+  float* rs = ys + TT * DC;          // [kKSplit - 1][TT][256]
   const int j = blockIdx.x, p = blockIdx.y, tid = threadIdx.x;
   t2i_combine(part, p, T, 0, T, ta);
-  for (int i = tid; i < T * DC; i += 256) xs[i] = q_g[static_cast<size_t>(p) * T * DC + i];
+  for (int i = tid; i < T * DC; i += kTokThreads) xs[i] = q_g[static_cast<size_t>(p) * T * DC + i];
   __syncthreads();
-  tok_linear<TT>(w.ow, DC, w.ob, DC, ta, DCI, DCI, ys, DC, false);
+  tok_linear<TT>(w.ow, DC, w.ob, DC, ta, DCI, DCI, ys, DC, false, rs);
   __syncthreads();
   tok_layernorm(ys, xs, w.n2w, w.n2b, xs, (j == 0) ? x2_g + static_cast<size_t>(p) * T * DC : nullptr, T);
   __syncthreads();
-  tok_linear<TT>(w.l1w + j * 256, H, w.l1b + j * 256, 256, xs, DC, DC, ys, DC, true);
+  tok_linear<TT>(w.l1w + j * 256, H, w.l1b + j * 256, 256, xs, DC, DC, ys, DC, true, rs);
   __syncthreads();
-  tok_linear<TT>(w.l2w + static_cast<size_t>(j) * 256 * DC, DC, nullptr, DC, ys, DC, 256, xs, DC, false);
+  tok_linear<TT>(w.l2w + static_cast<size_t>(j) * 256 * DC, DC, nullptr, DC, ys, DC, 256, xs, DC, false, rs);
   __syncthreads();
   float* dst = part_mlp + (static_cast<size_t>(p) * gridDim.x + j) * T * DC;
-  for (int i = tid; i < T * DC; i += 256) dst[i] = xs[i];
+  for (int i = tid; i < T * DC; i += kTokThreads) dst[i] = xs[i];
 }
 
 struct TailW {   // end of a layer: lin2 bias + norm3, then the image->token k / v projections (concatenated columns)
@@ -600,7 +626,7 @@ struct TailW {   // end of a layer: lin2 bias + norm3, then the image->token k /
 // then either the NEXT layer's self-attention sub-block (has_next) or only the q projection of the final
 // token->image attention (transformer.py:172-176, :99-101).   grid n, block 256
 template <int TT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kTokThreads)
 dec_token_tail_kernel(const float* __restrict__ x2_g, const float* __restrict__ part_mlp, int nj, const TailW w,
                       const float* __restrict__ tok0_g, int T, int heads, float* __restrict__ tk_g, float* __restrict__ tv_g,
                       int has_next, const SelfW nw, float* __restrict__ q_g, float* __restrict__ tq_g) {
@@ -612,7 +638,8 @@ dec_token_tail_kernel(const float* __restrict__ x2_g, const float* __restrict__ 
   float* b1 = b0 + TT * DC;
   float* b2 = b1 + TT * DC;
   float* sc = b2 + TT * DC;
-  for (int i = tid; i < T * DC; i += 256) {
+  float* rs = sc + 8 * TT * TT;
+  for (int i = tid; i < T * DC; i += kTokThreads) {
     float a = __ldg(w.l2b + (i % DC));
     for (int j = 0; j < nj; ++j) a += part_mlp[(static_cast<size_t>(p) * nj + j) * T * DC + i];
     b0[i] = a;
@@ -622,25 +649,25 @@ dec_token_tail_kernel(const float* __restrict__ x2_g, const float* __restrict__ 
   __syncthreads();
   tok_layernorm(b0, xs, w.n3w, w.n3b, xs, q_g + static_cast<size_t>(p) * T * DC, T);
   __syncthreads();
-  for (int i = tid; i < T * DC; i += 256) b2[i] = xs[i] + pe[i];
+  for (int i = tid; i < T * DC; i += kTokThreads) b2[i] = xs[i] + pe[i];
   __syncthreads();
   // k from (queries + pe), v from queries: two half-width passes over the concatenated weight
-  tok_linear<TT>(w.kvw, 2 * DCI, w.kvb, DCI, b2, DC, DC, b0, DCI, false);
-  tok_linear<TT>(w.kvw + DCI, 2 * DCI, w.kvb + DCI, DCI, xs, DC, DC, b1, DCI, false);
+  tok_linear<TT>(w.kvw, 2 * DCI, w.kvb, DCI, b2, DC, DC, b0, DCI, false, rs);
+  tok_linear<TT>(w.kvw + DCI, 2 * DCI, w.kvb + DCI, DCI, xs, DC, DC, b1, DCI, false, rs);
   __syncthreads();
-  for (int i = tid; i < T * DCI; i += 256) {
+  for (int i = tid; i < T * DCI; i += kTokThreads) {
     tk_g[static_cast<size_t>(p) * T * DCI + i] = b0[i];
     tv_g[static_cast<size_t>(p) * T * DCI + i] = b1[i];
   }
   __syncthreads();
   if (has_next) {
-    tok_self_block<TT>(nw, false, xs, pe, b0, b1, b2, sc, T, heads, q_g + static_cast<size_t>(p) * T * DC,
+    tok_self_block<TT>(nw, false, xs, pe, b0, b1, b2, sc, rs, T, heads, q_g + static_cast<size_t>(p) * T * DC,
                        tq_g + static_cast<size_t>(p) * T * DCI);
   } else {
-    tok_linear<TT>(nw.cqw, DCI, nw.cqb, DCI, b2, DC, DC, b0, DCI, false);   // b2 still holds queries + pe
+    tok_linear<TT>(nw.cqw, DCI, nw.cqb, DCI, b2, DC, DC, b0, DCI, false, rs);   // b2 still holds queries + pe
     __syncthreads();
     const float sc_cross = 1.0f / sqrtf(static_cast<float>(DCI / heads));
-    for (int i = tid; i < T * DCI; i += 256) tq_g[static_cast<size_t>(p) * T * DCI + i] = b0[i] * sc_cross;
+    for (int i = tid; i < T * DCI; i += kTokThreads) tq_g[static_cast<size_t>(p) * T * DCI + i] = b0[i] * sc_cross;
   }
 }
 
@@ -1232,12 +1259,15 @@ int samk_decoder_forward(const SamDecoderShape& s, const float* blob, const void
   const bool big = T > 8;    // kernels are instantiated for up to 8 and up to 16 tokens per prompt
   const int tok_smem = tok_smem_floats(big ? 16 : 8) * 4;
   const int t2i_smem = 8 * (big ? 16 : 8) * PART * 4;
+  const int mlp_smem = mlp_smem_floats(big ? 16 : 8) * 4;
   static samhost::PerDeviceOnce attr_once;
   if (attr_once.need()) {
     if (int rc = opt_in_smem(dec_token_first_kernel<8>, tok_smem_floats(8) * 4)) return rc;
     if (int rc = opt_in_smem(dec_token_first_kernel<16>, tok_smem_floats(16) * 4)) return rc;
     if (int rc = opt_in_smem(dec_token_tail_kernel<8>, tok_smem_floats(8) * 4)) return rc;
     if (int rc = opt_in_smem(dec_token_tail_kernel<16>, tok_smem_floats(16) * 4)) return rc;
+    if (int rc = opt_in_smem(dec_token_mlp_kernel<8>, mlp_smem_floats(8) * 4)) return rc;
+    if (int rc = opt_in_smem(dec_token_mlp_kernel<16>, mlp_smem_floats(16) * 4)) return rc;
     if (int rc = opt_in_smem(dec_attn_t2i_kernel<8>, 8 * 8 * PART * 4)) return rc;
     if (int rc = opt_in_smem(dec_attn_t2i_kernel<16>, 8 * 16 * PART * 4)) return rc;
     attr_once.done();
@@ -1283,10 +1313,10 @@ int samk_decoder_forward(const SamDecoderShape& s, const float* blob, const void
     samhost::LaunchScope scope(samhost::KC_DECODER, st, 2.0 * n * T * (4.0 * C * C + C * Ci));
     const SelfW sw = self_w(0);
     if (big)
-      dec_token_first_kernel<16><<<n, 256, tok_smem, st>>>(w.iou_token, w.mask_tokens, sparse, sparse_fmt, nm, k, sw, s.heads,
+      dec_token_first_kernel<16><<<n, kTokThreads, tok_smem, st>>>(w.iou_token, w.mask_tokens, sparse, sparse_fmt, nm, k, sw, s.heads,
                                                           ws.tok0, ws.q, ws.tq);
     else
-      dec_token_first_kernel<8><<<n, 256, tok_smem, st>>>(w.iou_token, w.mask_tokens, sparse, sparse_fmt, nm, k, sw, s.heads,
+      dec_token_first_kernel<8><<<n, kTokThreads, tok_smem, st>>>(w.iou_token, w.mask_tokens, sparse, sparse_fmt, nm, k, sw, s.heads,
                                                          ws.tok0, ws.q, ws.tq);
     SAM_CHECK_CUDA(cudaGetLastError());
   }
@@ -1307,9 +1337,9 @@ int samk_decoder_forward(const SamDecoderShape& s, const float* blob, const void
       const CrossMlpW cw{t.co, L.t2i.ob, L.n2w, L.n2b, t.l1, L.l1b, t.l2};
       dim3 grid(H / 256, n);
       if (big)
-        dec_token_mlp_kernel<16><<<grid, 256, 0, st>>>(ws.part, ws.q, cw, T, H, ws.x2, ws.pmlp);
+        dec_token_mlp_kernel<16><<<grid, kTokThreads, mlp_smem, st>>>(ws.part, ws.q, cw, T, H, ws.x2, ws.pmlp);
       else
-        dec_token_mlp_kernel<8><<<grid, 256, 0, st>>>(ws.part, ws.q, cw, T, H, ws.x2, ws.pmlp);
+        dec_token_mlp_kernel<8><<<grid, kTokThreads, mlp_smem, st>>>(ws.part, ws.q, cw, T, H, ws.x2, ws.pmlp);
       SAM_CHECK_CUDA(cudaGetLastError());
     }
     {
@@ -1325,10 +1355,10 @@ int samk_decoder_forward(const SamDecoderShape& s, const float* blob, const void
         nw.cqb = w.final_attn.qb;
       }
       if (big)
-        dec_token_tail_kernel<16><<<n, 256, tok_smem, st>>>(ws.x2, ws.pmlp, H / 256, tw, ws.tok0, T, s.heads, ws.tk, ws.tv,
+        dec_token_tail_kernel<16><<<n, kTokThreads, tok_smem, st>>>(ws.x2, ws.pmlp, H / 256, tw, ws.tok0, T, s.heads, ws.tk, ws.tv,
                                                            has_next ? 1 : 0, nw, ws.q, ws.tq);
       else
-        dec_token_tail_kernel<8><<<n, 256, tok_smem, st>>>(ws.x2, ws.pmlp, H / 256, tw, ws.tok0, T, s.heads, ws.tk, ws.tv,
+        dec_token_tail_kernel<8><<<n, kTokThreads, tok_smem, st>>>(ws.x2, ws.pmlp, H / 256, tw, ws.tok0, T, s.heads, ws.tk, ws.tv,
                                                           has_next ? 1 : 0, nw, ws.q, ws.tq);
       SAM_CHECK_CUDA(cudaGetLastError());
     }

@@ -4,8 +4,10 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 Workload (BASELINE.json configs[1], "C2"): SAM ViT-H image encoder + [SEG]-prompted mask decoder + postprocess_masks,
-bf16 tensor-core operands, batch 16 synthetic 1024x1024 images x 1 [SEG] embedding per GPU, masks post-processed to
-1024x1024.  One "step" = one pass of the whole path over one batch.  Weak scaling: every rank processes its own batch
+16-bit tensor-core operands (tcgen05 kind::f16, fp32 accumulate), batch 16 synthetic 1024x1024 images x 1 [SEG] embedding
+per GPU, masks post-processed to 1024x1024.  The headline operand format is fp16: same tensor rate as bf16, the
+reference's deployed precision (eval_referseg.py:71,86) and the format that meets north_star's mask-IoU >= 0.999 bar on
+the synthetic checkpoint (bf16 operands: 0.9965 -- reported in `other_operand_format` / `parity`, never as the headline).  One "step" = one pass of the whole path over one batch.  Weak scaling: every rank processes its own batch
 (images are independent units); no collective inside the forward.
 
 Printed JSON line (rank 0): see the driver contract.  `value` = images/s with inputs resident in HBM (CUDA events, max
@@ -185,7 +187,8 @@ def workload_name(args):
     default = (args.batch == 16 and args.n_seg == 1 and not args.multimask and tuple(args.orig_size) == (1024, 1024)
                and tuple(args.input_size) == (1024, 1024))
     tag = "C2" if default else ("C3" if (args.batch == 8 and args.n_seg == 4 and args.multimask) else "custom")
-    return (f"{tag}: SAM ViT-H image encoder + [SEG] prompt encoder/mask decoder + postprocess_masks, {args.dtype}, batch "
+    return (f"{tag}: SAM ViT-H image encoder + [SEG] prompt encoder/mask decoder + postprocess_masks, {args.dtype} "
+            f"tensor-core operands / fp32 accumulate, batch "
             f"{args.batch} images x {args.n_seg} [SEG] per GPU" + (" x 3 masks (multimask_output)" if args.multimask else "") +
             f", 1024x1024 synthetic (content {args.input_size[0]}x{args.input_size[1]}) -> {args.orig_size[0]}x{args.orig_size[1]} masks")
 
@@ -193,12 +196,19 @@ def workload_name(args):
 def gemm_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per GEMM launch (mean over the qkv / proj / lin1 / lin2 launches of an
     encoder block) from the committed ncu capture profiles/r01_kernel_traffic.json; None if the file is absent."""
-    p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_kernel_traffic.json")
+    p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02_kernel_traffic.json")
+    if not os.path.exists(p):
+        p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_kernel_traffic.json")
     try:
         with open(p) as f:
             return json.load(f)["gemm_block_mean"]["traffic_bytes_per_launch"]
     except (OSError, KeyError, ValueError):
         return None
+
+
+# north_star: embeddings / mask logits "within a stated bf16 tolerance" (stated: relative Frobenius error <= 1e-2 on the
+# stored sub-grids, max-abs reported next to it) and binarised masks at IoU >= 0.999 against the reference's fp32 path
+PARITY_BARS = {"embeddings_rel_fro_max": 1e-2, "low_res_logits_rel_fro_max": 1e-2, "mask_iou_min": 0.999}
 
 
 def golden_parity(sam, path, dev, dtypes):
@@ -218,7 +228,7 @@ def golden_parity(sam, path, dev, dtypes):
     x = synthetic_images(1, seed=g["meta"]["seed_in"]).to(dev)
     seg = synthetic_seg_embeddings(1, g["meta"]["n_seg"], seed=g["meta"]["seed_in"])[0].to(dev)
     rel = lambda a, b: ((a.float().cpu() - b).norm() / b.norm()).item()
-    out = {"golden": "tests/golden/vit_h_seed1234_in0.pt (reference modules, fp32 CPU)"}
+    out = {"golden": "tests/golden/vit_h_seed1234_in0.pt (reference modules, fp32 CPU)", "bars": PARITY_BARS}
     enc = sam.image_encoder
     keep = enc._operand_dtype
     for dt in dtypes:
@@ -231,12 +241,88 @@ def golden_parity(sam, path, dev, dtypes):
         want = np.unpackbits(g["post_single_1024x1024_1024x1024_bits"].numpy())[:post.numel()].reshape(post.shape).astype(bool)
         got = (post > 0).cpu().numpy()
         ious = [float((want[i] & got[i]).sum() / max((want[i] | got[i]).sum(), 1)) for i in range(post.shape[0])]
-        out["bf16" if dt == torch.bfloat16 else "fp16"] = {
-            "embeddings_rel_fro": rel(emb[:, ::4, ::4, ::4], g["emb_sub"]),
-            "low_res_logits_rel_fro": rel(low[:, :, ::4, ::4], g["low_single_sub"]),
-            "mask_iou_min": min(ious)}
+        emb_sub, low_sub = emb[:, ::4, ::4, ::4].float().cpu(), low[:, :, ::4, ::4].float().cpu()
+        rec = {"embeddings_rel_fro": rel(emb_sub, g["emb_sub"]),
+               "embeddings_max_abs": (emb_sub - g["emb_sub"]).abs().max().item(),
+               "low_res_logits_rel_fro": rel(low_sub, g["low_single_sub"]),
+               "low_res_logits_max_abs": (low_sub - g["low_single_sub"]).abs().max().item(),
+               "mask_iou_min": min(ious)}
+        rec["pass"] = {"embeddings": rec["embeddings_rel_fro"] <= PARITY_BARS["embeddings_rel_fro_max"],
+                       "low_res_logits": rec["low_res_logits_rel_fro"] <= PARITY_BARS["low_res_logits_rel_fro_max"],
+                       "mask_iou": rec["mask_iou_min"] >= PARITY_BARS["mask_iou_min"]}
+        rec["pass"]["all"] = all(rec["pass"].values())
+        out["bf16" if dt == torch.bfloat16 else "fp16"] = rec
     enc.set_operand_dtype(keep)
     return out
+
+
+def library_baseline(dev, n_seg: int, budget_s: float = 40.0):
+    """SURVEY 8(d) / BASELINE.md section 3: the reference's modules (their bit-identical functional restatement,
+    oracle/sam_oracle.py -- /root/reference does not exist on the GPU box) executed by STOCK PyTorch on this B200, fp32
+    and cast to bf16, 16 images x n_seg [SEG] per step, CUDA-event timed.  This is what a user gets without the new
+    kernels (the reference ships none); no kernel or module of anyref_b200 is on this path."""
+    from anyref_b200.synthetic import CONFIGS, synthetic_images, synthetic_seg_embeddings, synthetic_state_dict
+    from oracle import sam_oracle as O
+
+    cfg = CONFIGS["vit_h"]
+    B, chunk = 16, 4
+    out = {"what": "oracle/sam_oracle.py (restatement of the reference modules) on cuda via stock PyTorch ops, "
+                   f"{B} images x {n_seg} [SEG] per step in chunks of {chunk} images, TF32 off", "unit": "images/s"}
+    sd32 = {k: v.to(dev) for k, v in synthetic_state_dict(cfg, seed=1234).items()}
+    x32 = synthetic_images(B, seed=0).to(dev)
+    seg32 = synthetic_seg_embeddings(B, n_seg, seed=0).to(dev)
+    for name, dt in (("fp32", torch.float32), ("bf16", torch.bfloat16)):
+        sd = sd32 if dt == torch.float32 else {k: (v.to(dt) if v.is_floating_point() else v) for k, v in sd32.items()}
+        x, seg = x32.to(dt), seg32.to(dt)
+
+        def step():
+            # model/anyref.py:793-819 on the restated modules: encoder on a chunk, then per image prompt encoder ->
+            # (cast of the sparse embeddings to the model dtype, :806) -> mask decoder -> postprocess_masks
+            with torch.no_grad():
+                pe = O.dense_pe(sd, cfg)
+                for c0 in range(0, B, chunk):
+                    emb = O.image_encoder(sd, x[c0:c0 + chunk], cfg)
+                    for b in range(chunk):
+                        sparse, dense = O.prompt_encoder(sd, cfg, text_embeds=seg[c0 + b])
+                        low, _ = O.mask_decoder(sd, cfg, emb[b:b + 1], pe, sparse.to(dt), dense, False)
+                        O.postprocess_masks(low, (1024, 1024), (1024, 1024), 1024)
+
+        try:
+            t0 = time.perf_counter()
+            step()                                               # warm-up (cuBLAS / cuDNN heuristics, allocator)
+            torch.cuda.synchronize()
+            per = time.perf_counter() - t0
+            steps = max(1, min(3, int(budget_s / 2 / max(per, 1e-3))))
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[name] = {"value": B / (ms * 1e-3), "ms_per_step": ms, "steps": steps}
+        except Exception as e:  # noqa: BLE001  (a baseline leg must never take the headline down)
+            out[name] = {"error": f"{type(e).__name__}: {e}"[:200]}
+        del sd, x, seg
+        torch.cuda.empty_cache()
+    del sd32, x32, seg32
+    torch.cuda.empty_cache()
+    return out
+
+
+def sub_record_c3(path, dev, op_dtype, rank, timed_fn, world):
+    """BASELINE.json configs[2]: 8 images x 4 [SEG] x 3 masks (multimask_output), content 1024x683 -> 640x427 masks."""
+    from anyref_b200.synthetic import synthetic_images, synthetic_seg_embeddings
+
+    B, n_seg = 8, 4
+    x = synthetic_images(B, seed=100 + rank).to(op_dtype).to(dev)
+    seg = synthetic_seg_embeddings(B, n_seg, seed=100 + rank).to(op_dtype).to(dev)
+    seg_list = [seg[b] for b in range(B)]
+    ins, outs = [(1024, 683)] * B, [(640, 427)] * B
+    ms, launches = timed_fn(lambda: path(x, seg_list, ins, outs, multimask_output=True), 10, 3)
+    return {"workload": "C3: batch 8 images x 4 [SEG] x 3 masks (multimask_output), content 1024x683 -> 640x427, per GPU",
+            "ms_per_step": ms, "images_per_s": world * B / (ms * 1e-3), "masks_per_s": world * B * n_seg * 3 / (ms * 1e-3),
+            "gpu_launches_per_step": launches // 10}
 
 
 def main():
@@ -247,7 +333,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=16, help="images per GPU per step")
     ap.add_argument("--n-seg", type=int, default=1, help="[SEG] prompts per image")
-    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"])
+    ap.add_argument("--dtype", default="fp16", choices=["bf16", "fp16"],
+                    help="tensor-core operand format (accumulation / residual stream / softmax / LayerNorm are fp32)")
     ap.add_argument("--multimask", action="store_true", help="multimask_output=True (3 masks per prompt; configs[2])")
     ap.add_argument("--input-size", type=int, nargs=2, default=[1024, 1024], metavar=("h", "w"),
                     help="size of the resized image inside the 1024 canvas (postprocess crop)")
@@ -255,6 +342,8 @@ def main():
                     help="original image size the masks are post-processed to")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the golden-vector parity check after the timing")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the sub-records (library_baseline, c3, c5, small_batch) -- timing of the headline only")
     args = ap.parse_args()
     _claim_stdout()
     if args.impl == "reference":
@@ -350,7 +439,7 @@ def main():
     # roofline leg: per-kernel-class CUDA-event timing of the same step (events on the launch stream)
     _lib.profile_reset()
     _lib.profile_enable(True)
-    prof_steps = 2
+    prof_steps = max(10, args.steps)
     for _ in range(prof_steps):
         step_resident()
     torch.cuda.synchronize()
@@ -378,6 +467,39 @@ def main():
         sam.image_encoder.set_operand_dtype(op_dtype)
         alt = {"dtype": "fp16" if alt_dtype == torch.float16 else "bf16", "value": world * B / (ms_alt * 1e-3),
                "unit": "images/s", "ms_per_step": ms_alt}
+
+    extras = {}
+    if not args.no_extras:
+        # single-batch latency of the public host-to-host call (no pipelining: upload, kernels, download of ONE batch)
+        lat = []
+        for _ in range(5):
+            t0 = time.perf_counter()
+            pipe.submit(host_images, host_seg, sizes_in, sizes, host_outs[0], multimask_output=args.multimask)
+            pipe.drain()
+            torch.cuda.synchronize()
+            lat.append((time.perf_counter() - t0) * 1e3)
+        extras["e2e_latency_ms_single_batch"] = sorted(lat)[len(lat) // 2]
+        # the reference's real evaluation shape (eval_referseg.py:101-106: batch_size 1): one image x one [SEG]
+        one_img, one_seg = dev_images[:1], [dev_seg[0]]
+        ms1, l1 = timed(lambda: path(one_img, one_seg, sizes_in[:1], sizes[:1], multimask_output=args.multimask), 20, 5)
+        extras["small_batch"] = {"workload": "1 image x %d [SEG] per step (eval_referseg.py batch_size 1)" % n_seg,
+                                 "ms_per_step": ms1, "images_per_s": world * 1e3 / ms1, "gpu_launches_per_step": l1 // 20}
+        extras["c3"] = sub_record_c3(path, dev, op_dtype, rank, timed, world)
+        # BASELINE.json configs[4]: the data-parallel evaluation sweep incl. the all_reduce of the IoU statistics and the
+        # all_gather of the bit-packed masks (the only collectives of the path; both after the forward)
+        from anyref_b200 import eval_sweep
+        n_c5 = int(os.environ.get("ANYREF_BENCH_C5_IMAGES", "1024"))
+        eval_sweep.run_shard(sam, 0, 16, 2, 16, dev, op_dtype=op_dtype)                          # warm-up
+        c5 = eval_sweep.sweep(sam, n_c5, 2, 16, rank, world, dev, gather_masks=True, op_dtype=op_dtype)
+        extras["c5"] = {"workload": f"C5: {n_c5} synthetic images x 2 [SEG] sharded over {world} GPU(s), batch 16, fused "
+                                    "postprocess + IoU counts, all_reduce of 7 statistics + all_gather of bit-packed masks; "
+                                    "includes on-device input generation",
+                        "images_per_s": c5["images_per_s"], "masks_per_s": c5["masks_per_s"], "ms_total": c5["ms_total"],
+                        "ms_forward": c5["ms_forward"], "mask_bytes_gathered": c5.get("mask_bytes"),
+                        "mask_sha256": c5.get("mask_sha256"), "gIoU": c5.get("gIoU"), "cIoU": c5.get("cIoU")}
+        if rank == 0 and world == 1:
+            torch.cuda.empty_cache()
+            extras["library_baseline"] = library_baseline(dev, n_seg)
 
     parity = None
     if rank == 0 and not args.no_parity:
@@ -426,6 +548,7 @@ def main():
             "other_operand_format": alt,
             "cpu_baseline": cpu_baseline,
         }
+        line.update(extras)
         _emit(line)
     if world > 1:
         dist.barrier()

@@ -333,6 +333,49 @@ def test_windowed_attention_token_map_is_exact(ops):
     assert (got.float() - want).abs().max().item() < 2e-2    # fp16 rounding of p = 1/196 only
 
 
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("heads", [2, 16])
+def test_windowed_attention_window_map_is_bit_exact(ops, dt, heads):
+    """INT-exact partition / pad / un-partition map of the CUDA path (image_encoder.py:263-318), independent of any
+    arithmetic: every token carries a random +-8 sign code as its key, and the query of token t is the code of ONE other
+    real token pi(t) of the same window.  The matching logit is 64 * 80 * scale = 572, every other one is <= 572 - 150, so
+    the fp32 softmax is EXACTLY one-hot (exp underflows to 0) and the kernel must return v[pi(t)] bit for bit -- any
+    permutation inside the gather of q / k / v or the scatter of the output changes bits.  Padded window slots carry the
+    qkv bias (own sign code): they must never be selected by these queries, and their own outputs must not be stored."""
+    g = torch.Generator(device="cpu").manual_seed(11 + heads)
+    B, hd = 2, 80
+    E = heads * hd
+    code = (torch.randint(0, 2, (B, 64, 64, heads, hd), generator=g) * 2 - 1).float() * 8.0     # keys
+    bias_code = (torch.randint(0, 2, (3, heads, hd), generator=g) * 2 - 1).float() * 8.0
+    v = torch.randn(B, 64, 64, heads, hd, generator=g).to(dt).float()
+    q = torch.empty_like(code)
+    want = torch.empty_like(v)
+    worst = 0.0
+    for b in range(B):
+        for wy in range(5):
+            for wx in range(5):
+                ys = torch.arange(14 * wy, min(14 * wy + 14, 64))
+                xs = torch.arange(14 * wx, min(14 * wx + 14, 64))
+                yy, xx = torch.meshgrid(ys, xs, indexing="ij")
+                yy, xx = yy.reshape(-1), xx.reshape(-1)
+                perm = torch.randperm(yy.numel(), generator=g)
+                q[b, yy, xx] = code[b, yy[perm], xx[perm]]
+                want[b, yy, xx] = v[b, yy[perm], xx[perm]]
+                # the codes of a window (plus the padding code) must be far from each other, else the test is void
+                kk = code[b, yy, xx]                                        # [t, heads, hd]
+                kk = torch.cat([kk, bias_code[1][None]], dim=0)
+                corr = torch.einsum("thd,uhd->htu", kk, kk) / 64.0
+                corr = corr - torch.eye(kk.shape[0])[None] * 1e9
+                worst = max(worst, corr.max().item())
+    assert worst <= 80 - 24, worst            # margin >= 24 * 64 * 80^-0.5 = 171 > 104 (fp32 exp underflow incl. denormals)
+    qkv = torch.cat([q.reshape(B * 4096, E), code.reshape(B * 4096, E), v.reshape(B * 4096, E)], dim=1).to(dt).to(DEV)
+    bias = bias_code.reshape(3 * E).to(dt).to(DEV)
+    rel_h = (torch.randn(27, hd, generator=g) * 0.01).to(dt).to(DEV)
+    rel_w = (torch.randn(27, hd, generator=g) * 0.01).to(dt).to(DEV)
+    got = ops.attn_window(qkv, bias, ops.window_rel_table(rel_h, rel_w, dt), B, heads)
+    assert torch.equal(got.float().cpu(), want.reshape(B * 4096, E))
+
+
 @pytest.mark.parametrize("dt,tol", [(torch.float16, 1.5e-3), (torch.bfloat16, 5e-3)])
 def test_global_attention(ops, dt, tol):
     torch.manual_seed(4)

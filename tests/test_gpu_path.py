@@ -1,7 +1,11 @@
 """Parity of the whole path through the reference-shaped module API against the CPU oracle (small encoder, full tensors)
 and against the committed reference goldens (ViT-H).  Tolerances (measured precision envelope):
-  fp16 operands : embeddings rel-Frobenius <= 2e-3, low-res logits rel <= 2e-3, mask IoU >= 0.999
-  bf16 operands : embeddings rel-Frobenius <= 1e-2 / max-abs <= 5e-2, low-res logits rel <= 1e-2, mask IoU >= 0.995
+  fp16 operands (the PARITY-GREEN mode, headline of bench.py; the reference's deployed precision, eval_referseg.py:71,86):
+                  embeddings rel-Frobenius <= 2e-3, low-res logits rel <= 2e-3, mask IoU >= 0.999 -- north_star's bar
+  bf16 operands : embeddings rel-Frobenius <= 1e-2 / max-abs <= 5e-2, low-res logits rel <= 1e-2 (the stated bf16
+                  tolerance).  NOT claimed parity-green for masks: on the synthetic checkpoint (logit std 0.066) bf16
+                  operand rounding flips 0.3 % of the pixels (IoU 0.9965; stock all-bf16 PyTorch: 0.978-0.996, SURVEY
+                  Appendix A), so the bf16 IoU assertion below is only a regression floor (0.995), not the 0.999 bar
   decoder / postprocess (fp32 kernels): max-abs <= 2e-5 / 1e-6
 """
 import os
@@ -97,6 +101,73 @@ def test_decoder_with_several_prompt_tokens_and_dense_input(tiny):
                                 multimask_output=True)
     assert (low.cpu() - low_ref).abs().max().item() < 2e-5
     assert (iou.cpu() - iou_ref).abs().max().item() < 2e-5
+
+
+@pytest.mark.parametrize("k", [4, 11])
+def test_decoder_with_up_to_sixteen_tokens_per_prompt(tiny, k):
+    """T = 5 + k tokens per prompt: k = 4 is the first size on the 16-token kernel instances, k = 11 the maximum
+    (T = 16); one more sparse embedding must raise instead of computing something else."""
+    sam, cfg, sd = tiny["sam"], tiny["cfg"], tiny["sd"]
+    g = torch.Generator().manual_seed(50 + k)
+    sparse = torch.randn(3, k, 256, generator=g)
+    _, dense_ref = O.prompt_encoder(sd, cfg, text_embeds=sparse[:, :1])
+    low_ref, iou_ref = O.mask_decoder(sd, cfg, tiny["emb"][1:2], tiny["pe"], sparse, dense_ref, True)
+    _, dense = sam.prompt_encoder(points=None, boxes=None, masks=None, text_embeds=sparse[:, :1].cuda())
+    low, iou = sam.mask_decoder(image_embeddings=tiny["emb"][1:2].cuda(), image_pe=sam.prompt_encoder.get_dense_pe(),
+                                sparse_prompt_embeddings=sparse.cuda(), dense_prompt_embeddings=dense,
+                                multimask_output=True)
+    assert (low.cpu() - low_ref).abs().max().item() < 2e-5
+    assert (iou.cpu() - iou_ref).abs().max().item() < 2e-5
+    if k == 11:
+        too_many = torch.randn(1, 12, 256, generator=g).cuda()
+        with pytest.raises(RuntimeError, match="tokens per prompt"):
+            sam.mask_decoder(image_embeddings=tiny["emb"][1:2].cuda(), image_pe=sam.prompt_encoder.get_dense_pe(),
+                             sparse_prompt_embeddings=too_many, dense_prompt_embeddings=dense[:1], multimask_output=True)
+
+
+def test_batched_decoder_with_promptless_images(tiny):
+    """forward_batched over more image embeddings than prompts (images without a [SEG] in the middle of the batch):
+    prompt p must read image image_index[p], whatever the other embeddings hold."""
+    sam, cfg, sd = tiny["sam"], tiny["cfg"], tiny["sd"]
+    emb = torch.cat([tiny["emb"][:1], torch.full_like(tiny["emb"][:1], float("nan")), tiny["emb"][1:2],
+                     torch.full_like(tiny["emb"][:1], float("nan"))]).cuda()
+    text = torch.cat([tiny["seg"][0][:2], tiny["seg"][1][:1]]).cuda()          # prompts 0, 1 -> image 0; prompt 2 -> image 2
+    index = torch.tensor([0, 0, 2], dtype=torch.int32, device="cuda")
+    sparse, dense = sam.prompt_encoder(points=None, boxes=None, masks=None, text_embeds=text)
+    low, iou = sam.mask_decoder.forward_batched(emb, sam.prompt_encoder.get_dense_pe(), sparse, dense, index, False)
+    for img, sl, seg in ((0, slice(0, 2), tiny["seg"][0][:2]), (1, slice(2, 3), tiny["seg"][1][:1])):
+        s_ref, d_ref = O.prompt_encoder(sd, cfg, text_embeds=seg)
+        low_ref, iou_ref = O.mask_decoder(sd, cfg, tiny["emb"][img:img + 1], tiny["pe"], s_ref, d_ref, False)
+        assert (low[sl].cpu() - low_ref).abs().max().item() < 2e-5
+        assert (iou[sl].cpu() - iou_ref).abs().max().item() < 2e-5
+
+
+def test_model_on_a_non_current_device(tiny):
+    """The library launches on the CURRENT device; every module entry point makes its tensors' device current for the
+    call (per-device kernel attributes, streams, workspaces), so a model on cuda:1 works while cuda:0 is current --
+    as the reference's PyTorch modules do."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from anyref_b200.grounding import GroundingPath
+    from anyref_b200.segment_anything import build_sam_from_config
+
+    cfg, sd = tiny["cfg"], tiny["sd"]
+    segs = [tiny["seg"][0], tiny["seg"][1]]
+    sizes = [(1024, 1024), (1024, 683)]
+    outs = [(1024, 1024), (640, 427)]
+    tiny["sam"].image_encoder.set_operand_dtype(torch.float16)
+    want = GroundingPath(tiny["sam"])(tiny["x"].cuda(), [s.cuda() for s in segs], sizes, outs)
+    torch.cuda.set_device(0)
+    dev1 = torch.device("cuda", 1)
+    sam1 = build_sam_from_config(cfg)
+    sam1.load_state_dict(sd, strict=True)
+    sam1 = sam1.to(dev1)
+    sam1.image_encoder.set_operand_dtype(torch.float16)
+    got = GroundingPath(sam1)(tiny["x"].to(dev1), [s.to(dev1) for s in segs], sizes, outs)
+    torch.cuda.synchronize(dev1)
+    assert torch.cuda.current_device() == 0
+    for g_, w_ in zip(got, want):
+        assert g_.device == dev1 and torch.equal(g_.cpu(), w_.cpu())
 
 
 @pytest.mark.parametrize("inp,orig", SIZES + [((1024, 1024), (333, 517)), ((512, 1024), (1, 7))])
@@ -225,7 +296,7 @@ def test_whole_path_vs_oracle(tiny):
     got = GroundingPath(sam)(tiny["x"].cuda(), [s.cuda() for s in segs], sizes, sizes)
     for g, w in zip(got, want):
         assert rel_fro(g, w) < 3e-3
-        assert mask_iou(g, w) >= 0.995
+        assert mask_iou(g, w) >= 0.999      # north_star's bar, fp16 operands
 
 
 def test_parameter_updates_are_picked_up(tiny):
@@ -245,8 +316,8 @@ def test_parameter_updates_are_picked_up(tiny):
 
 
 @pytest.mark.parametrize("ln_fold", [True, False])
-@pytest.mark.parametrize("dt,emb_tol,low_tol,iou_min", [(torch.float16, 2e-3, 2e-3, 0.999),
-                                                        (torch.bfloat16, 1e-2, 1e-2, 0.995)])
+@pytest.mark.parametrize("dt,emb_tol,low_tol,iou_min", [(torch.float16, 2e-3, 2e-3, 0.999),     # north_star's bar
+                                                        (torch.bfloat16, 1e-2, 1e-2, 0.995)])   # regression floor only
 def test_vit_h_against_reference_goldens(dt, emb_tol, low_tol, iou_min, ln_fold):
     """Full-size ViT-H vs tests/golden/vit_h_seed1234_in0.pt (outputs of the UNMODIFIED reference modules)."""
     if not torch.cuda.is_available():
