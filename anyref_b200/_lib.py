@@ -82,6 +82,8 @@ _PROTOS = {
                           c_int, c_int, c_void_p],
     "sam_prompt_mask_blob_elems": [c_int, c_int],
     "sam_prompt_mask_embed": [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "sam_resize_u8": [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p,
+                      c_void_p, c_int, c_void_p],
     "sam_preprocess": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, C.POINTER(C.c_float),
                        C.POINTER(C.c_float), c_void_p],
 }

@@ -158,6 +158,12 @@ int sam_prompt_mask_embed(const void* masks, int in_fmt, const float* blob, int 
   if (!masks || !blob || !out) return samhost::set_error(1, "sam_prompt_mask_embed: NULL argument");
   return samk_prompt_mask_embed(masks, in_fmt, blob, mask_in_chans, out, out_fmt, n, g, C, S(stream));
 }
+int sam_resize_u8(const unsigned char* in, int H, int W, int C, unsigned char* tmp, unsigned char* out, int new_h, int new_w,
+                  const int* xbounds, const int* xcoeff, int xk, const int* ybounds, const int* ycoeff, int yk,
+                  void* stream) {
+  if (!in || !out) return samhost::set_error(1, "sam_resize_u8: NULL image");
+  return samk_resize_u8(in, H, W, C, tmp, out, new_h, new_w, xbounds, xcoeff, xk, ybounds, ycoeff, yk, S(stream));
+}
 int sam_preprocess(const void* img, int in_fmt, void* out, int out_fmt, int B, int h, int w, int Sz, const float* mean,
                    const float* std, void* stream) {
   if (!img || !out || !mean || !std) return samhost::set_error(1, "sam_preprocess: NULL argument");

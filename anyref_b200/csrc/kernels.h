@@ -119,3 +119,7 @@ int samk_prompt_mask_embed(const void* masks, int in_fmt, const float* blob, int
                            int n, int g, int C, cudaStream_t stream);
 int samk_preprocess(const void* img, int in_fmt, void* out, int out_fmt, int B, int h, int w, int S, const float* mean,
                     const float* std, cudaStream_t stream);
+// ResizeLongestSide.apply_image: PIL-exact separable bilinear resize of an HWC uint8 image (prompt.cu).
+int samk_resize_u8(const uint8_t* in, int H, int W, int C, uint8_t* tmp, uint8_t* out, int new_h, int new_w,
+                   const int* xbounds, const int* xcoeff, int xk, const int* ybounds, const int* ycoeff, int yk,
+                   cudaStream_t stream);

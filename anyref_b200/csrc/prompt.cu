@@ -250,3 +250,78 @@ int samk_preprocess(const void* img, int in_fmt, void* out, int out_fmt, int B, 
   SAM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// ResizeLongestSide.apply_image (utils/transforms.py:27-34) on the device.  The reference resizes with PIL
+// (torchvision resize of a PIL image = Image.resize(BILINEAR)): a separable triangle filter whose support grows with
+// the down-scaling factor, evaluated in 22-bit fixed point on uint8, horizontal pass first with a uint8 intermediate
+// (Pillow src/libImaging/Resample.c).  The integer coefficient tables (bounds [n_out, 2] = first tap, tap count;
+// coeff [n_out, ksize]) are built on the host exactly as Pillow builds them (anyref_b200/segment_anything/utils/
+// transforms.py), so these kernels are pure integer arithmetic: bit-exact with PIL.
+//   image HWC uint8, C interleaved.  pass 0: out[y, x', c] over x;  pass 1: out[y', x, c] over y.
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+__global__ void resize_u8_pass_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int H, int W, int C, int n_out,
+                                      const int* __restrict__ bounds, const int* __restrict__ coeff, int ksize, int vertical) {
+  // horizontal: in [H, W, C] -> out [H, n_out, C];  vertical: in [H, W, C] -> out [n_out, W, C]
+  const size_t total = vertical ? static_cast<size_t>(n_out) * W * C : static_cast<size_t>(H) * n_out * C;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    int o, fixed;      // output index along the resampled axis, index along the other axis
+    if (vertical) {
+      fixed = static_cast<int>((i / C) % W);
+      o = static_cast<int>(i / (static_cast<size_t>(C) * W));
+    } else {
+      o = static_cast<int>((i / C) % n_out);
+      fixed = static_cast<int>(i / (static_cast<size_t>(C) * n_out));
+    }
+    const int first = __ldg(bounds + 2 * o), n = __ldg(bounds + 2 * o + 1);
+    const int* k = coeff + static_cast<size_t>(o) * ksize;
+    int acc = 1 << 21;
+    if (vertical) {
+      const uint8_t* p = in + (static_cast<size_t>(first) * W + fixed) * C + c;
+      for (int t = 0; t < n; ++t) acc += static_cast<int>(p[static_cast<size_t>(t) * W * C]) * __ldg(k + t);
+    } else {
+      const uint8_t* p = in + (static_cast<size_t>(fixed) * W + first) * C + c;
+      for (int t = 0; t < n; ++t) acc += static_cast<int>(p[static_cast<size_t>(t) * C]) * __ldg(k + t);
+    }
+    const int v = acc >> 22;
+    out[i] = static_cast<uint8_t>(v < 0 ? 0 : (v > 255 ? 255 : v));
+  }
+}
+}  // namespace
+
+int samk_resize_u8(const uint8_t* in, int H, int W, int C, uint8_t* tmp, uint8_t* out, int new_h, int new_w,
+                   const int* xbounds, const int* xcoeff, int xk, const int* ybounds, const int* ycoeff, int yk,
+                   cudaStream_t stream) {
+  SAM_REQUIRE(H > 0 && W > 0 && C > 0 && new_h > 0 && new_w > 0, "resize: empty image");
+  SAM_REQUIRE((new_w == W) || (xbounds && xcoeff && xk > 0), "resize: horizontal coefficient table missing");
+  SAM_REQUIRE((new_h == H) || (ybounds && ycoeff && yk > 0), "resize: vertical coefficient table missing");
+  SAM_REQUIRE(new_w == W || new_h == H || tmp, "resize: two passes need the intermediate buffer [H, new_w, C]");
+  const int cap = samhost::sm_count() * 32;
+  auto blocks = [&](size_t total) {
+    const size_t b = (total + 255) / 256;
+    return static_cast<int>(b < static_cast<size_t>(cap) ? b : static_cast<size_t>(cap));
+  };
+  const uint8_t* src = in;
+  if (new_w != W) {
+    uint8_t* dst = (new_h != H) ? tmp : out;
+    const size_t total = static_cast<size_t>(H) * new_w * C;
+    samhost::LaunchScope scope(samhost::KC_LAYOUT, stream, 0.0, static_cast<double>(H) * C * (W + new_w));
+    resize_u8_pass_kernel<<<blocks(total), 256, 0, stream>>>(src, dst, H, W, C, new_w, xbounds, xcoeff, xk, 0);
+    SAM_CHECK_CUDA(cudaGetLastError());
+    src = dst;
+  }
+  if (new_h != H) {
+    const size_t total = static_cast<size_t>(new_h) * new_w * C;
+    samhost::LaunchScope scope(samhost::KC_LAYOUT, stream, 0.0, static_cast<double>(new_w) * C * (H + new_h));
+    resize_u8_pass_kernel<<<blocks(total), 256, 0, stream>>>(src, out, H, new_w, C, new_h, ybounds, ycoeff, yk, 1);
+    SAM_CHECK_CUDA(cudaGetLastError());
+    src = out;
+  }
+  if (src == in) {   // nothing to resample: plain copy (PIL returns a copy as well)
+    SAM_CHECK_CUDA(cudaMemcpyAsync(out, in, static_cast<size_t>(H) * W * C, cudaMemcpyDeviceToDevice, stream));
+  }
+  return 0;
+}

@@ -30,8 +30,10 @@ class SamPredictor:
             raise AssertionError(f"image_format must be in ['RGB', 'BGR'], is {image_format}.")
         if image_format != self.model.image_format:
             image = image[..., ::-1]
-        resized = self.transform.apply_image(np.ascontiguousarray(image))
-        t = torch.as_tensor(resized, device=self.device).permute(2, 0, 1).contiguous()[None]
+        # upload the raw uint8 image once; resize (PIL-exact), normalise, pad and cast all run on the device
+        raw = torch.from_numpy(np.ascontiguousarray(image)).to(self.device)
+        resized = self.transform.apply_image_cuda(raw)
+        t = resized.permute(2, 0, 1).contiguous()[None]
         self.set_torch_image(t, image.shape[:2])
 
     @torch.no_grad()

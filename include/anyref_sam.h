@@ -261,6 +261,18 @@ int sam_preprocess(const void* img, int in_fmt, void* out, int out_fmt, int B, i
                    const float* std, void* stream);
 
 /*
+ * ResizeLongestSide.apply_image (utils/transforms.py:27-34; torchvision resize of a PIL image = PIL BILINEAR with
+ * antialiasing) for an HWC uint8 image on the device: separable 22-bit fixed-point resample, horizontal pass first with
+ * a uint8 intermediate, bit-exact with Pillow's Resample.c given Pillow's coefficient tables
+ *   xbounds [new_w, 2] int32 (first source column, tap count), xcoeff [new_w, xk] int32 (weights * 2^22, rounded);
+ *   ybounds / ycoeff likewise for rows.  A table may be NULL when that axis keeps its size.
+ *   tmp: [H, new_w, C] uint8 scratch (needed when both axes change); out: [new_h, new_w, C] uint8.
+ */
+int sam_resize_u8(const unsigned char* in, int H, int W, int C, unsigned char* tmp, unsigned char* out, int new_h,
+                  int new_w, const int* xbounds, const int* xcoeff, int xk, const int* ybounds, const int* ycoeff,
+                  int yk, void* stream);
+
+/*
  * Launch accounting and per-kernel-class timing (used by bench.py for `gpu_launches` and the roofline leg).
  * sam_launch_count: kernels launched by this library since load.  With profiling enabled every launch is bracketed by
  * a CUDA event pair on its stream; sam_profile_collect synchronises those events and adds them to per-class totals.

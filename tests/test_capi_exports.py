@@ -83,3 +83,16 @@ def test_product_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cpp", ".h", ".cuh")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_integration_md_struct_stub_matches_the_binding():
+    """The ctypes struct shown to a maintainer in INTEGRATION.md must have the fields of the real binding (a missing
+    trailing field yields a short struct and undefined behaviour in sam_encoder_forward)."""
+    import re
+    from anyref_b200 import _lib
+
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = text[text.index("class SamEncoderShape(C.Structure)"):]
+    block = block[:block.index("]") + 1]
+    doc_fields = re.findall(r'\("(\w+)",', block)
+    assert doc_fields == [f[0] for f in _lib.SamEncoderShape._fields_]

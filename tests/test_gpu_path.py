@@ -470,6 +470,24 @@ def test_preprocess_is_bit_exact(tiny, dtype, hw):
     assert torch.equal(sam.preprocess(x[0].cuda(), out_dtype=torch.float32).cpu(), ref[0])
 
 
+@pytest.mark.parametrize("hw", [(480, 640), (1365, 2048), (333, 517), (1024, 1024), (2000, 1500), (50, 37), (1024, 683)])
+def test_gpu_resize_is_bit_exact_with_pil(tiny, hw):
+    """ResizeLongestSide.apply_image on the device (utils/transforms.py:27-34): up- and down-scaling, one axis
+    unchanged, nothing to do -- all bit-exact with the PIL restatement (oracle/resize_oracle.py, itself pinned against
+    PIL in tests/test_resize_oracle.py)."""
+    from anyref_b200.segment_anything.utils.transforms import ResizeLongestSide
+    from oracle import resize_oracle as R
+
+    rng = np.random.default_rng(hw[0] + 3 * hw[1])
+    img = rng.integers(0, 256, (hw[0], hw[1], 3), dtype=np.uint8)
+    want = R.apply_image(img, 1024)
+    tr = ResizeLongestSide(1024)
+    got = tr.apply_image_cuda(torch.from_numpy(img).cuda())
+    assert got.dtype == torch.uint8 and tuple(got.shape) == want.shape
+    assert np.array_equal(got.cpu().numpy(), want)
+    assert np.array_equal(tr.apply_image(img), want)          # the reference's numpy-in / numpy-out signature
+
+
 def test_sam_predictor_box_prompt_vs_oracle(tiny):
     """SamPredictor.set_torch_image + predict (predictor.py:64-176) as convert_avs_masks.py:29-58 drives it: uint8
     image in the resized frame, box in ORIGINAL pixels, multimask_output=True, best mask by predicted IoU."""
