@@ -1,24 +1,28 @@
-// 14x14 windowed attention of the SAM ViT-H encoder: probabilities in TENSOR MEMORY, double-buffered operands.
-// Replaces image_encoder.py:235-257 (Attention.forward), :263-318 (window partition / un-partition) and :354-392
-// (add_decomposed_rel_pos) for the 14x14 windowed blocks.
+// 14x14 windowed attention of the SAM ViT-H encoder (replaces image_encoder.py:235-257, :263-318, :354-392):
+// probabilities in TENSOR MEMORY, double-buffered operands, TWO softmax threads per query row.
 //
-// What v3 (attn_window3.cu) could not do: its P tiles took 104 KB of shared memory, so Q / K / V were single-buffered
-// and the two query tiles of an item ran in lock step (timeline trace: tensor pipe idle under both softmaxes, both
-// softmaxes idle under the MMAs).  Here
-//   * P never touches shared memory: each softmax thread packs its row's probabilities and writes them with tcgen05.st
-//     IN PLACE over the S columns it has already consumed; O = P.V is a tcgen05.mma with the A operand in tensor memory
-//     ("ts" form, layout pinned by tools/gpu_probe_ts.py) and V as five 16-wide MN-major SWIZZLE_32B chunks, so one
-//     N = 80 MMA per 16 keys (13 per tile instead of 26 and no A-operand shared-memory reads);
-//   * the freed shared memory holds a 2-stage ring of Q / K / V: the producers run a whole item ahead and the two
-//     tiles free-run -- one tile's MMAs and epilogue hide under the other tile's softmax;
-//   * the rel-pos gather uses the tile's own (dead) Q buffer as thread-private, bank-conflict-free scratch: no barrier.
-// Softmax is single pass against a reference maximum (max of the first 32 keys); if the running row sum leaves
-// [0, 2^10] the probabilities written so far are rescaled in tensor memory and the reference moved -- exact softmax.
+//   * window partition / padding / un-partition are never materialised: 4-D TMA boxes over the [B, 64, 64, 3E] view
+//     of the un-partitioned qkv gather a window's q / k / v, zero-fill + a bias patch reproduce the padding, the
+//     output goes back through 4-D TMA stores that clip the padded rows;
+//   * S = Q.K^T (N = 208) and the two rel-pos products T = Q.R^T land in tensor memory; each softmax thread packs its
+//     probabilities and writes them with tcgen05.st IN PLACE over S columns it has already consumed; O = P.V is the "ts"
+//     form of tcgen05.mma (A operand in tensor memory), V as five 16-wide MN-major SWIZZLE_32B chunks;
+//   * the shared memory holds a 2-stage ring of Q / K / V: the producers run a whole item ahead, the two query tiles
+//     free-run;
+//   * round 2: a query row is shared by TWO threads (keys 0..95 | keys 96..195), i.e. 16 softmax warps per CTA instead
+//     of 8.  With one thread per row every SM sub-partition ran two softmax warps whose load -> exp -> pack -> store
+//     chains could not fill it (ncu r01e: issue slots 34 %, half of the issued instructions barrier polls, item =
+//     5670 cycles against ~2800 of MUFU / issue work).  The two threads agree on the reference maximum through shared
+//     memory, run the single-pass softmax on their own half (each with its own lazy rescale), reconcile the references
+//     if one of them had to move, add their row sums, and split the O read-out (40 columns each).
+// Softmax is single pass against a reference maximum (max of the first 16 keys of both halves); if a running half-row
+// sum leaves [0, 2^10] the probabilities written so far are rescaled in tensor memory and the reference moved -- exact.
 //
-//   warp 0 / 11  : producers (Q0,Q1,K / V): 4-D TMA boxes straight from the un-partitioned qkv, padded-token patch
-//   warp 1 / 10  : MMA issuers of tile 0 / 1 (one elected thread each)
-//   warps 2..5   : softmax + epilogue of tile 0 (query rows 0..125);  warps 6..9: tile 1 (rows 126..195)
-// TMEM slot g (256 columns): S [0,208) | Tw [196,228) Th [224,256) | P (16-bit pairs) [0,104) | O [112,192).
+//   warp 0 / 3   : producers (Q0,Q1,K / V): 4-D TMA boxes straight from the un-partitioned qkv, padded-token patch
+//   warp 1 / 2   : MMA issuers of tile 0 / 1 (one elected thread each)
+//   warps 4..11  : softmax + epilogue of tile 0 (query rows 0..125);  warps 12..19: tile 1 (rows 126..195);
+//                  within a tile: warps 0..3 = key half 0 of lane quadrants 0..3, warps 4..7 = key half 1
+// TMEM slot g (256 columns): S [0,208) | Tw [196,228) Th [224,256) | P half 0 [0,48), half 1 [96,152) | O [152,232).
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -33,7 +37,8 @@ namespace {
 constexpr int WS = 14;
 constexpr int NTOK = WS * WS;  // 196
 constexpr int NKEY = 208;
-constexpr int kThreads4 = 384;
+constexpr int kThreads4 = 640;
+constexpr int kHalfKeys = 96;       // key half 0 = keys [0, 96), half 1 = keys [96, 196) (+ 12 pad keys)
 
 // shared-memory map (bytes from the 1024-aligned base); stage s at + s * kStageBytes
 constexpr int OFF_Q64 = 0;            // 2 x (128 x 128B) SWIZZLE_128B   (tile g at + g*16384); doubles as gather scratch
@@ -46,9 +51,11 @@ constexpr int kStageBytes = OFF_V + 5 * kVChunk;   // 107520 (multiple of 1024)
 constexpr int OFF_R64 = 2 * kStageBytes;           // 64 x 128B rel-pos operand table
 constexpr int OFF_R16 = OFF_R64 + 8192;            // 64 x 32B
 constexpr int OFF_BAR = OFF_R16 + 2048;
-constexpr int kSmemBytes4 = OFF_BAR + 256 + 1024;
+constexpr int OFF_XCH = OFF_BAR + 256;              // float2 [2 tiles][128 rows][2 halves] exchange of the row pairs
+constexpr int kSmemBytes4 = OFF_XCH + 2 * 128 * 2 * 8 + 1024;
 
-constexpr uint32_t TM_O = 112;
+constexpr uint32_t TM_O = 152;
+constexpr uint32_t TM_P1 = 96;       // P columns of key half 1
 constexpr float kSumLimit = 1024.0f;
 
 struct WinAttnMaps4 {
@@ -69,6 +76,17 @@ struct WinAttnMaps4 {
 #ifndef WIN4_TMA_OUT
 #define WIN4_TMA_OUT 1
 #endif
+// the 16 softmax warps wait for their tile's MMAs with the parked mbarrier wait (suspend-time hint): spinning, they took
+// the issue slots of the MMA issuers and producers that share their SM sub-partitions (ncu r02: 67 % of the executed
+// instructions were barrier polls)
+#ifndef WIN5_PARK
+#define WIN5_PARK 1
+#endif
+#if WIN5_PARK
+#define WIN5_WAIT(bar, ph) ptx::mbar_wait_parked(bar, ph)
+#else
+#define WIN5_WAIT(bar, ph) ptx::mbar_wait(bar, ph)
+#endif
 __device__ __forceinline__ void named_bar_sync4(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -80,6 +98,21 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* s
 __device__ __forceinline__ void bulk_commit4() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read_all4() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all4() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// -DWIN5_TRACE=1: block 0 records clock64 stamps of items 3 and 4 for the Q/K producer, the tile-0 MMA issuer and the two
+// tile-0 softmax threads of row 0, and prints them when the kernel ends (timeline debugging; timing builds only)
+#ifndef WIN5_TRACE
+#define WIN5_TRACE 0
+#endif
+#if WIN5_TRACE
+__device__ long long g_win5_trace[2 * 4 * 12];
+#define WT(role, ev)                                                                                   \
+  do {                                                                                                 \
+    if (blockIdx.x == 0 && n >= 3 && n < 5) g_win5_trace[((n - 3) * 4 + (role)) * 12 + (ev)] = clock64(); \
+  } while (0)
+#else
+#define WT(role, ev) do { } while (0)
+#endif
 
 using ptx::add2;
 using ptx::f32x2;
@@ -103,7 +136,7 @@ __device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&v)[
       "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
       : "memory");
 }
-__device__ __forceinline__ void tmem_st_x8(uint32_t taddr, const uint32_t (&v)[16]) {
+__device__ __forceinline__ void tmem_st_x8(uint32_t taddr, const uint32_t (&v)[8]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]),
                "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                : "memory");
@@ -113,22 +146,22 @@ __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t (&v)[16]) {
   ptx::tmem_ld_32x32b_x16(taddr, v);
 }
 
-#define WIN4_LOGIT(J, VAL) (fmaf(__uint_as_float(VAL), scale_log2e, relh[(J) / WS]) + relw[(J) % WS])
+#define WIN4_LOGIT(J, VAL) (fmaf(__uint_as_float(VAL), scale_log2e, relh[(J) / WS - KH0]) + relw[(J) % WS])
 
-// One 32-key chunk (16 keys for C == 6) already in registers: probabilities against the reference folded into relh,
-// two at a time on the packed fp32 pipe; packed 16-bit pairs go straight back to tensor memory (columns C*16 ..).
-template <int C, int FMT>
-__device__ __forceinline__ void exp_chunk_tm(const uint32_t (&v)[32], const float (&relh)[WS], const float (&relw)[WS],
-                                             f32x2 sc2, uint32_t trow, f32x2& s0, f32x2& s1) {
-  constexpr int kN = (C < 6) ? 32 : 16;
-  uint32_t pk[16];
+// One 16-key chunk (keys J0 .. J0+15) already in registers: probabilities against the reference folded into relh, two
+// at a time on the packed fp32 pipe; the packed 16-bit pairs go straight back to tensor memory (8 columns at pcol).
+// KH0 = first key row of this thread's half (relh holds key rows KH0 ..).
+template <int J0, int KH0, int FMT>
+__device__ __forceinline__ void exp_chunk_tm(const uint32_t (&v)[16], const float (&relh)[8], const float (&relw)[WS],
+                                             f32x2 sc2, uint32_t pcol, f32x2& s0, f32x2& s1) {
+  uint32_t pk[8];
 #pragma unroll
-  for (int i = 0; i < kN; i += 2) {
-    const int j = C * 32 + i;   // even; NTOK and WS are even, so j and j + 1 share their key row and validity
+  for (int i = 0; i < 16; i += 2) {
+    const int j = J0 + i;   // even; NTOK and WS are even, so j and j + 1 share their key row and validity
     if (j < NTOK) {
-      const int jj = j < NTOK ? j : 0;
-      f32x2 x = fma2(pk2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), sc2, pk2(relh[jj / WS], relh[jj / WS]));
-      x = add2(x, pk2(relw[jj % WS], relw[jj % WS + 1]));
+      f32x2 x = fma2(pk2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), sc2,
+                     pk2(relh[j / WS - KH0], relh[j / WS - KH0]));
+      x = add2(x, pk2(relw[j % WS], relw[j % WS + 1]));
       float x0, x1;
       upk2(x, x0, x1);
       const float p0 = ex2(x0), p1 = ex2(x1);
@@ -141,72 +174,99 @@ __device__ __forceinline__ void exp_chunk_tm(const uint32_t (&v)[32], const floa
       pk[i >> 1] = 0u;   // pad keys 196..207: P = 0
     }
   }
-  if (C < 6)
-    tmem_st_x16(trow + C * 16, pk);
-  else
-    tmem_st_x8(trow + C * 16, pk);
+  tmem_st_x8(pcol, pk);
 }
 
-template <int C>
-__device__ __forceinline__ float chunk_max(const uint32_t (&v)[32], const float (&relh)[WS], const float (&relw)[WS],
+template <int J0, int KH0>
+__device__ __forceinline__ float chunk_max(const uint32_t (&v)[16], const float (&relh)[8], const float (&relw)[WS],
                                            float scale_log2e) {
-  constexpr int kN = (C < 6) ? 32 : 16;
   float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
-  for (int i = 0; i < kN; i += 2) {
-    const int j = C * 32 + i;
+  for (int i = 0; i < 16; i += 2) {
+    const int j = J0 + i;
     if (j < NTOK) {
-      const int jj = j < NTOK ? j : 0;
-      m0 = fmaxf(m0, WIN4_LOGIT(jj, v[i]));
-      m1 = fmaxf(m1, WIN4_LOGIT(jj + 1, v[i + 1]));
+      m0 = fmaxf(m0, WIN4_LOGIT(j, v[i]));
+      m1 = fmaxf(m1, WIN4_LOGIT(j + 1, v[i + 1]));
     }
   }
   return fmaxf(m0, m1);
 }
 
-// Rare path: the running row sum left [0, kSumLimit] at chunk C.  Move the reference to this chunk's maximum, rescale
-// the probabilities of chunks 0 .. C-1 in tensor memory (a power of two: exact), and redo chunk C.  Warp-uniform (the
-// tcgen05 instructions are .aligned); lanes that did not overflow use delta = 0.
-template <int C, int FMT>
-__device__ __forceinline__ void rescale_and_redo(const uint32_t (&v)[32], float (&relh)[WS], const float (&relw)[WS],
-                                                 float scale_log2e, uint32_t trow, f32x2& s0, f32x2& s1, f32x2 prev0,
-                                                 f32x2 prev1, bool mine) {
-  tmem_st_wait();   // the probabilities written so far must have landed before they are read back
-  const float cmax = chunk_max<C>(v, relh, relw, scale_log2e);
-  const float delta = mine ? fmaxf(cmax, 0.0f) : 0.0f;
-  const float alpha = ex2(-delta);
+// multiply the NP 8-column probability chunks at pbase by alpha (warp-collective tcgen05.ld / st)
+template <int FMT>
+__device__ __forceinline__ void rescale_p(uint32_t pbase, int np, float alpha) {
 #pragma unroll 1
-  for (int c = 0; c < C; ++c) {
-    uint32_t p[16];
-    tmem_ld_x16(trow + c * 16, p);
+  for (int c = 0; c < np; ++c) {
+    uint32_t p[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(p[0]), "=r"(p[1]), "=r"(p[2]), "=r"(p[3]), "=r"(p[4]), "=r"(p[5]), "=r"(p[6]), "=r"(p[7])
+                 : "r"(pbase + c * 8)
+                 : "memory");
     ptx::tmem_ld_wait();
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
+    for (int i = 0; i < 8; ++i) {
       const float2 f = ptx::unpack2(p[i], FMT);
       p[i] = ptx::pack2t<FMT>(f.x * alpha, f.y * alpha);
     }
-    tmem_st_x16(trow + c * 16, p);
+    tmem_st_x8(pbase + c * 8, p);
   }
+}
+
+// Rare path: the running half-row sum left [0, kSumLimit] at chunk C (C previous chunks already written).  Move this
+// thread's reference to the chunk's maximum, rescale its probabilities of chunks 0 .. C-1 in tensor memory and redo
+// chunk C.  Warp-uniform (the tcgen05 instructions are .aligned); lanes that did not overflow use delta = 0.
+template <int C, int J0, int KH0, int FMT>
+__device__ __forceinline__ void rescale_and_redo(const uint32_t (&v)[16], float (&relh)[8], const float (&relw)[WS],
+                                                 float scale_log2e, uint32_t pbase, f32x2& s0, f32x2& s1, f32x2 prev0,
+                                                 f32x2 prev1, bool mine, float& moved) {
+  tmem_st_wait();   // the probabilities written so far must have landed before they are read back
+  const float cmax = chunk_max<J0, KH0>(v, relh, relw, scale_log2e);
+  const float delta = mine ? fmaxf(cmax, 0.0f) : 0.0f;
+  const float alpha = ex2(-delta);
+  rescale_p<FMT>(pbase, C, alpha);
 #pragma unroll
-  for (int kh = 0; kh < WS; ++kh) relh[kh] -= delta;
+  for (int kh = 0; kh < 8; ++kh) relh[kh] -= delta;
+  moved += delta;
   const f32x2 a2 = pk2(alpha, alpha);
   s0 = ptx::mul2(prev0, a2);
   s1 = ptx::mul2(prev1, a2);
-  exp_chunk_tm<C, FMT>(v, relh, relw, pk2(scale_log2e, scale_log2e), trow, s0, s1);
+  exp_chunk_tm<J0, KH0, FMT>(v, relh, relw, pk2(scale_log2e, scale_log2e), pbase + C * 8, s0, s1);
 }
 
-template <int C, int FMT>
-__device__ __forceinline__ void softmax_chunk(const uint32_t (&v)[32], float (&relh)[WS], const float (&relw)[WS],
-                                              float scale_log2e, uint32_t trow, f32x2& s0, f32x2& s1, bool valid) {
+template <int C, int J0, int KH0, int FMT>
+__device__ __forceinline__ void softmax_chunk(const uint32_t (&v)[16], float (&relh)[8], const float (&relw)[WS],
+                                              float scale_log2e, uint32_t pbase, f32x2& s0, f32x2& s1, bool valid,
+                                              float& moved) {
   const f32x2 prev0 = s0, prev1 = s1;
-  exp_chunk_tm<C, FMT>(v, relh, relw, pk2(scale_log2e, scale_log2e), trow, s0, s1);
+  exp_chunk_tm<J0, KH0, FMT>(v, relh, relw, pk2(scale_log2e, scale_log2e), pbase + C * 8, s0, s1);
   if (C > 0) {
     float a0, a1;
     upk2(add2(s0, s1), a0, a1);
     const bool over = valid && !(a0 + a1 <= kSumLimit);   // rows >= nq hold no query: never trigger
-    if (__any_sync(0xffffffffu, over)) rescale_and_redo<C, FMT>(v, relh, relw, scale_log2e, trow, s0, s1, prev0, prev1, over);
+    if (__any_sync(0xffffffffu, over))
+      rescale_and_redo<C, J0, KH0, FMT>(v, relh, relw, scale_log2e, pbase, s0, s1, prev0, prev1, over, moved);
   }
 }
+
+// The single-pass softmax of one key half: NCHK chunks of 16 keys starting at key JB (S columns from scol, P chunks from
+// pbase), the tensor-memory load of chunk C + 1 in flight behind the arithmetic of chunk C.  `cur` holds chunk C.
+template <int C, int NCHK, int JB, int KH0, int FMT>
+struct HalfLoop {
+  // one chunk buffer: with four softmax warps per SM sub-partition the tensor-memory load latency is hidden by the
+  // other warps, and a second buffer pushed the loop over its 104-register budget (10 % of the loop were local loads)
+  static __device__ __forceinline__ void run(uint32_t scol, uint32_t pbase, uint32_t (&cur)[16], float (&relh)[8],
+                                             const float (&relw)[WS], float scale_log2e, bool valid, f32x2& s0, f32x2& s1,
+                                             float& moved) {
+    if constexpr (C < NCHK) {
+      softmax_chunk<C, JB + 16 * C, KH0, FMT>(cur, relh, relw, scale_log2e, pbase, s0, s1, valid, moved);
+      if constexpr (C + 1 < NCHK) {
+        tmem_ld_x16(scol + (C + 1) * 16, cur);
+        ptx::tmem_ld_wait_dep16(cur);
+        HalfLoop<C + 1, NCHK, JB, KH0, FMT>::run(scol, pbase, cur, relh, relw, scale_log2e, valid, s0, s1, moved);
+      }
+    }
+  }
+};
 
 struct Item {
   int b, wy, wx, head;
@@ -241,9 +301,9 @@ win_attn4_kernel(const __grid_constant__ WinAttnMaps4 maps, const uint16_t* __re
   uint64_t* v_ready = bars + 8;    // [2]
   uint64_t* v_free = bars + 10;    // [2] PV MMAs of both tiles done (count 2)
   uint64_t* s_full = bars + 12;    // [2 tiles] S/T in TMEM                       (MMA -> softmax)
-  uint64_t* p_ready = bars + 14;   // [2 tiles] P in TMEM, count 128              (softmax -> MMA)
+  uint64_t* p_ready = bars + 14;   // [2 tiles] P in TMEM, count 256              (softmax -> MMA)
   uint64_t* o_full = bars + 16;    // [2 tiles] O in TMEM                         (MMA -> softmax)
-  uint64_t* o_done = bars + 18;    // [2 tiles] O read out, slot free, count 128  (softmax -> MMA)
+  uint64_t* o_done = bars + 18;    // [2 tiles] O read out, slot free, count 256  (softmax -> MMA)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -257,14 +317,14 @@ win_attn4_kernel(const __grid_constant__ WinAttnMaps4 maps, const uint16_t* __re
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&qk_full[s], 1);
       ptx::mbar_init(&qk_ready[s], 1);
-      ptx::mbar_init(&qk_free[s], WIN4_TMA_OUT ? 2 + 2 : 2 + 256);
+      ptx::mbar_init(&qk_free[s], 2 + 2);
       ptx::mbar_init(&v_full[s], 1);
       ptx::mbar_init(&v_ready[s], 1);
       ptx::mbar_init(&v_free[s], 2);
       ptx::mbar_init(&s_full[s], 1);
-      ptx::mbar_init(&p_ready[s], 128);
+      ptx::mbar_init(&p_ready[s], 256);
       ptx::mbar_init(&o_full[s], 1);
-      ptx::mbar_init(&o_done[s], 128);
+      ptx::mbar_init(&o_done[s], 256);
     }
     ptx::fence_mbar_init();
   }
@@ -288,6 +348,15 @@ win_attn4_kernel(const __grid_constant__ WinAttnMaps4 maps, const uint16_t* __re
     __trap();
   }
 
+  // register budget: the four service warps (one warpgroup) keep 64 registers, the 16 softmax warps take 104: the pool of
+  // a CTA is what it was launched with, 128 x 64 + 512 x 104 = 640 x 96
+  // (640 threads x 96 at launch; setmaxnreg is warpgroup-collective, so it sits ahead of the role branches)
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;\n");
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;\n");
+  }
+
   if (warp == 0) {
     // ============================================================ Q / K producer: TMA + padded-token patch
     int n = 0;
@@ -300,7 +369,9 @@ win_attn4_kernel(const __grid_constant__ WinAttnMaps4 maps, const uint16_t* __re
       const int x0 = w.wx * WS, y0 = w.wy * WS;
       const bool padded = (w.wy == 4) || (w.wx == 4);
       if (lane == 0) {
+        WT(0, 0);
         if (n >= 2) ptx::mbar_wait(&qk_free[s], sph ^ 1);
+        WT(0, 1);
         uint32_t bytes = static_cast<uint32_t>((2 * NTOK) * HD * 2);   // Q0 (126 rows) + Q1 (70 rows) + K (196 rows)
         if (n == 0) bytes += 64 * HD * 2;
         ptx::mbar_expect_tx(&qk_full[s], bytes);
@@ -322,27 +393,25 @@ win_attn4_kernel(const __grid_constant__ WinAttnMaps4 maps, const uint16_t* __re
         // token r of the window (iy = r / 14, ix = r % 14) lies outside the 64x64 grid -> q / k := qkv bias
         // (image_encoder.py:281 pads x with zeros BEFORE the qkv projection).  The two bias rows are fetched into
         // registers while the TMA is in flight, so the patch itself is shared-memory stores only.
-        uint4 bq[kU4], bk[kU4];
-#pragma unroll
-        for (int c = 0; c < kU4; ++c) {
-          bq[c] = __ldg(reinterpret_cast<const uint4*>(bias_op + w.head * HD) + c);
-          bk[c] = __ldg(reinterpret_cast<const uint4*>(bias_op + E + w.head * HD) + c);
-        }
+        // (unit-major loop: one 16-byte unit of the two bias rows in registers at a time -- this warp runs on a
+        // 64-register budget)
         ptx::mbar_wait(&qk_full[s], sph);
-        for (int r = lane; r < NTOK; r += 32) {
-          const int iy = r / WS, ix = r % WS;
-          if (y0 + iy >= 64 || x0 + ix >= 64) {
-            uint8_t* q64 = st + OFF_Q64 + (r < 126 ? 0 : 16384);
-            uint8_t* q16 = st + OFF_Q16 + (r < 126 ? 0 : 4096);
-            const int rq = r < 126 ? r : r - 126;
-#pragma unroll
-            for (int c = 0; c < kU4; ++c) {
+#pragma unroll 1
+        for (int c = 0; c < kU4; ++c) {
+          const uint4 bq = __ldg(reinterpret_cast<const uint4*>(bias_op + w.head * HD) + c);
+          const uint4 bk = __ldg(reinterpret_cast<const uint4*>(bias_op + E + w.head * HD) + c);
+          for (int r = lane; r < NTOK; r += 32) {
+            const int iy = r / WS, ix = r % WS;
+            if (y0 + iy >= 64 || x0 + ix >= 64) {
+              uint8_t* q64 = st + OFF_Q64 + (r < 126 ? 0 : 16384);
+              uint8_t* q16 = st + OFF_Q16 + (r < 126 ? 0 : 4096);
+              const int rq = r < 126 ? r : r - 126;
               if (c < 8) {
-                *reinterpret_cast<uint4*>(st + OFF_K64 + row_off64(r, c)) = bk[c];
-                *reinterpret_cast<uint4*>(q64 + row_off64(rq, c)) = bq[c];
+                *reinterpret_cast<uint4*>(st + OFF_K64 + row_off64(r, c)) = bk;
+                *reinterpret_cast<uint4*>(q64 + row_off64(rq, c)) = bq;
               } else {
-                *reinterpret_cast<uint4*>(st + OFF_K16 + row_off16(r, c - 8)) = bk[c];
-                *reinterpret_cast<uint4*>(q16 + row_off16(rq, c - 8)) = bq[c];
+                *reinterpret_cast<uint4*>(st + OFF_K16 + row_off16(r, c - 8)) = bk;
+                *reinterpret_cast<uint4*>(q16 + row_off16(rq, c - 8)) = bq;
               }
             }
           }
@@ -352,9 +421,9 @@ win_attn4_kernel(const __grid_constant__ WinAttnMaps4 maps, const uint16_t* __re
         ptx::mbar_wait(&qk_full[s], sph);
       }
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&qk_ready[s]);
+      if (lane == 0) { WT(0, 2); ptx::mbar_arrive(&qk_ready[s]); }
     }
-  } else if (warp == 11) {
+  } else if (warp == 3) {
     // ============================================================ V producer
     int n = 0;
     for (int it = blockIdx.x; it < num_items; it += gridDim.x, ++n) {
@@ -373,16 +442,14 @@ win_attn4_kernel(const __grid_constant__ WinAttnMaps4 maps, const uint16_t* __re
       }
       __syncwarp();
       if (padded) {
-        uint4 bv[kU4];
-#pragma unroll
-        for (int c = 0; c < kU4; ++c) bv[c] = __ldg(reinterpret_cast<const uint4*>(bias_op + cv) + c);
         ptx::mbar_wait(&v_full[s], sph);
-        for (int r = lane; r < NTOK; r += 32) {
-          const int iy = r / WS, ix = r % WS;
-          if (y0 + iy >= 64 || x0 + ix >= 64) {
-#pragma unroll
-            for (int c = 0; c < kU4; ++c)
-              *reinterpret_cast<uint4*>(sv + (c >> 1) * kVChunk + row_off16(r, c & 1)) = bv[c];
+#pragma unroll 1
+        for (int c = 0; c < kU4; ++c) {
+          const uint4 bv = __ldg(reinterpret_cast<const uint4*>(bias_op + cv) + c);
+          for (int r = lane; r < NTOK; r += 32) {
+            const int iy = r / WS, ix = r % WS;
+            if (y0 + iy >= 64 || x0 + ix >= 64)
+              *reinterpret_cast<uint4*>(sv + (c >> 1) * kVChunk + row_off16(r, c & 1)) = bv;
           }
         }
         ptx::fence_proxy_async_smem();
@@ -392,8 +459,8 @@ win_attn4_kernel(const __grid_constant__ WinAttnMaps4 maps, const uint16_t* __re
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&v_ready[s]);
     }
-  } else if (warp == 1 || warp == 10) {
-    // ============================================================ MMA issuers: warp 1 -> tile 0, warp 10 -> tile 1
+  } else if (warp == 1 || warp == 2) {
+    // ============================================================ MMA issuers: warp 1 -> tile 0, warp 2 -> tile 1
     if (ptx::elect_one()) {
       const int g = (warp == 1) ? 0 : 1;
       const uint32_t slot = g * 256;   // TMEM base is 0 (checked above)
@@ -413,8 +480,20 @@ win_attn4_kernel(const __grid_constant__ WinAttnMaps4 maps, const uint16_t* __re
         const uint64_t dq16 = ptx::make_smem_desc(sb + OFF_Q16 + g * 4096, 16, 256, ptx::kSwz32);
         // V: MN-major, five 16-wide SWIZZLE_32B chunks (LBO = chunk stride), 8-key groups of 256 B (SBO)
         const uint64_t dv = ptx::make_smem_desc(sb + OFF_V, kVChunk, 256, ptx::kSwz32);
+        if (g == 0) {
+          WT(1, 0);
+#if WIN5_TRACE
+          if (blockIdx.x == 0 && n >= 3 && n < 5) {
+            unsigned long long gt;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+            g_win5_trace[((n - 3) * 4 + 1) * 12 + 9] = static_cast<long long>(gt);
+          }
+#endif
+        }
         ptx::mbar_wait(&qk_ready[s], sph);
+        if (g == 0) WT(1, 1);
         if (n > 0) ptx::mbar_wait(&o_done[g], ph ^ 1);   // slot g drained by the previous item's epilogue
+        if (g == 0) WT(1, 2);
         ptx::tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 4; ++k) ptx::mma_f16_ss(slot, dq64 + 2 * k, dk64 + 2 * k, id_S, k != 0);
@@ -429,174 +508,212 @@ win_attn4_kernel(const __grid_constant__ WinAttnMaps4 maps, const uint16_t* __re
         if (kTail) ptx::mma_f16_ss(slot + 224, dq16, dr16, id_T, 1);
         ptx::mma_commit(&s_full[g]);
         ptx::mma_commit(&qk_free[s]);
+        if (g == 0) WT(1, 3);
         ptx::mbar_wait(&v_ready[s], sph);
+        if (g == 0) WT(1, 4);
         ptx::mbar_wait(&p_ready[g], ph);
+        if (g == 0) WT(1, 5);
         ptx::tc_fence_after();
+        // P chunk ks (keys 16 ks ..) sits at column 8 ks for key half 0 (ks < 6) and at TM_P1 + 8 (ks - 6) for half 1
 #pragma unroll
         for (int ks = 0; ks < NKEY / 16; ++ks)
-          ptx::mma_f16_ts(slot + TM_O, slot + ks * 8, dv + ((ks * 512) >> 4), id_O, ks != 0);
+          ptx::mma_f16_ts(slot + TM_O, slot + (ks < 6 ? ks * 8 : TM_P1 + (ks - 6) * 8), dv + ((ks * 512) >> 4), id_O,
+                          ks != 0);
         ptx::mma_commit(&o_full[g]);
         ptx::mma_commit(&v_free[s]);
+        if (g == 0) WT(1, 6);
       }
     }
   } else {
-    // ============================================================ softmax warpgroups (g = query tile)
-    const int g = (warp - 2) >> 2;
-    const int row = ((warp & 3) << 5) + lane;          // TMEM lane == query row of the tile (warp & 3 = lane quadrant)
-    const uint32_t trow = tmem + g * 256 + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    // ============================================================ softmax warps (g = query tile, half = key half)
+    const int sw = warp - 4;
+    const int g = sw >> 3;
+    const int half = (sw >> 2) & 1;
+    const int quad = warp & 3;                         // TMEM lane quadrant == warp % 4
+    const int row = (quad << 5) + lane;                // TMEM lane == query row of the tile
+    const uint32_t trow = tmem + g * 256 + (static_cast<uint32_t>(quad * 32) << 16);
+    const int pair_bar = 1 + g * 4 + quad;             // named barrier of the two warps that share these 32 rows
+    const uint32_t xch = sbase + OFF_XCH + ((g * 128 + row) * 2) * 8;                // float2 [half] of this row
     const int nq = g ? 70 : 126;
     const int qiy = (g ? 9 : 0) + row / WS;
     const int qix = row % WS;
     const int qh = (qiy < WS) ? qiy : (WS - 1);
     const float kLog2e = 1.4426950408889634f;
+    const bool store_thread = (half == 0) && (quad == 2) && (lane == 0);
+    constexpr int kOH = HD / 2;                        // O columns read out per thread
     int n = 0;
     for (int it = blockIdx.x; it < num_items; it += gridDim.x, ++n) {
       const Item w = decode_item(it, heads);
       const int s = n & 1;
       const uint32_t ph = n & 1;
-      if (WIN4_TMA_OUT && n > 0 && (warp & 3) == 2 && lane == 0) {
+      if (n > 0 && store_thread) {
         // the previous item's output store has read its staging rows: that stage's Q / K may be overwritten
         bulk_wait_read_all4();
         ptx::mbar_arrive(&qk_free[s ^ 1]);
       }
-      ptx::mbar_wait(&s_full[g], ph);
+      const bool tr = (g == 0) && (quad == 0) && (lane == 0);
+      if (tr) WT(2 + half, 0);
+      WIN5_WAIT(&s_full[g], ph);
+      if (tr) WT(2 + half, 1);
       ptx::tc_fence_after();
-      float relh[WS], relw[WS];
+      float relh[8], relw[WS];
+      uint32_t first[16];
+      const uint32_t scol = trow + (half ? kHalfKeys : 0);
+      tmem_ld_x16(scol, first);            // first key chunk of this half (in flight behind the gather)
       {
-        // rel-pos products of this row: Th[27] (cols 224..250), Tw[27] (cols 196..222).  The 14 + 14 terms the row needs
-        // sit at a row-dependent offset (index = q - k + 13, image_encoder.py:347-351): bounce them through thread-
-        // private scratch in this tile's Q buffer (dead once S / T are in TMEM), word (j, row) at j*128 + row: no
-        // bank conflicts, no other thread involved, no barrier.
-        uint32_t th[32], tw[32];
-        ptx::tmem_ld_32x32b_x32(trow + 224, th);
-        ptx::tmem_ld_32x32b_x32(trow + 196, tw);
-        ptx::tmem_ld_wait_dep(th);
-        ptx::tmem_ld_wait_dep(tw);
+        // rel-pos products of this row: Th[27] (cols 224..250), Tw[27] (cols 196..222).  The terms a row needs sit at a
+        // row-dependent offset (index = q - k + 13, image_encoder.py:347-351): bounce them through scratch in this tile's
+        // Q buffer (dead once S / T are in TMEM), word (j, row) at j*512 + row*4: no bank conflicts.  The two threads of
+        // a row share the scratch: half 0 dumps Th, both read their key rows, half 1 dumps Tw, both read it.
+        uint32_t t[32];
+        ptx::tmem_ld_32x32b_x32(trow + (half ? 196 : 224), t);
+        ptx::tmem_ld_wait();               // also completes `first`
         const uint32_t sc = sbase + s * kStageBytes + OFF_Q64 + g * 16384 + row * 4;
+        if (half == 0) {
 #pragma unroll
-        for (int j = 0; j < 27; ++j)
-          asm volatile("st.shared.f32 [%0], %1;" ::"r"(sc + j * 512), "f"(__uint_as_float(th[j]) * kLog2e) : "memory");
-        const uint32_t ah = sc + (qh + (WS - 1)) * 512;
+          for (int j = 0; j < 27; ++j)
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(sc + j * 512), "f"(__uint_as_float(t[j]) * kLog2e) : "memory");
+        }
+        named_bar_sync4(pair_bar, 64);
+        {
+          // this half's key rows: kh = KH0 .. KH0 + 7 with KH0 = 0 (keys 0..95 -> rows 0..6) or 6 (keys 96..195 -> 6..13)
+          const int kh0 = half ? 6 : 0;
+          const uint32_t ah = sc + (qh + (WS - 1) - kh0) * 512;
 #pragma unroll
-        for (int kh = 0; kh < WS; ++kh)
-          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(relh[kh]) : "r"(ah - kh * 512) : "memory");
+          for (int kh = 0; kh < 8; ++kh)
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(relh[kh]) : "r"(ah - kh * 512) : "memory");
+        }
+        named_bar_sync4(pair_bar, 64);
+        if (half == 1) {
 #pragma unroll
-        for (int j = 0; j < 27; ++j)
-          asm volatile("st.shared.f32 [%0], %1;" ::"r"(sc + j * 512), "f"(__uint_as_float(tw[j]) * kLog2e) : "memory");
+          for (int j = 0; j < 27; ++j)
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(sc + j * 512), "f"(__uint_as_float(t[j]) * kLog2e) : "memory");
+        }
+        named_bar_sync4(pair_bar, 64);
         const uint32_t aw = sc + (qix + (WS - 1)) * 512;
 #pragma unroll
         for (int kw = 0; kw < WS; ++kw)
           asm volatile("ld.shared.f32 %0, [%1];" : "=f"(relw[kw]) : "r"(aw - kw * 512) : "memory");
       }
-      // the scratch stores above went through the generic proxy; the producer's next TMA into this stage writes the
-      // same bytes through the async proxy.  Without this fence a late scratch store can land on top of the freshly
-      // loaded Q rows (seen as a few wrong rows of one item in ~4 % of stress runs).
-      if (!WIN4_TMA_OUT) {
-        ptx::fence_proxy_async_smem();
-        ptx::mbar_arrive(&qk_free[s]);   // Q / K of this stage may be overwritten (count 2 MMA commits + 256 threads)
-      }
-
-      f32x2 s0 = 0ull, s1 = 0ull;
+      if (tr) WT(2 + half, 2);
+      // reference maximum of the row: max over the first 16 keys of both halves
+      float mref = half ? chunk_max<kHalfKeys, 6>(first, relh, relw, scale_log2e)
+                        : chunk_max<0, 0>(first, relh, relw, scale_log2e);
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(xch + half * 8), "f"(mref) : "memory");
+      named_bar_sync4(pair_bar, 64);
       {
-        uint32_t va[32], vb[32];
-        ptx::tmem_ld_32x32b_x32(trow, va);
-        ptx::tmem_ld_wait_dep(va);
-        ptx::tmem_ld_32x32b_x32(trow + 32, vb);
-        const float mref = chunk_max<0>(va, relh, relw, scale_log2e);
-#pragma unroll
-        for (int kh = 0; kh < WS; ++kh) relh[kh] -= mref;
-        softmax_chunk<0, FMT>(va, relh, relw, scale_log2e, trow, s0, s1, row < nq);
-        ptx::tmem_ld_wait_dep(vb);
-        ptx::tmem_ld_32x32b_x32(trow + 64, va);
-        softmax_chunk<1, FMT>(vb, relh, relw, scale_log2e, trow, s0, s1, row < nq);
-        ptx::tmem_ld_wait_dep(va);
-        ptx::tmem_ld_32x32b_x32(trow + 96, vb);
-        softmax_chunk<2, FMT>(va, relh, relw, scale_log2e, trow, s0, s1, row < nq);
-        ptx::tmem_ld_wait_dep(vb);
-        ptx::tmem_ld_32x32b_x32(trow + 128, va);
-        softmax_chunk<3, FMT>(vb, relh, relw, scale_log2e, trow, s0, s1, row < nq);
-        ptx::tmem_ld_wait_dep(va);
-        ptx::tmem_ld_32x32b_x32(trow + 160, vb);
-        softmax_chunk<4, FMT>(va, relh, relw, scale_log2e, trow, s0, s1, row < nq);
-        ptx::tmem_ld_wait_dep(vb);
-        ptx::tmem_ld_32x32b_x16_lo(trow + 192, va);
-        softmax_chunk<5, FMT>(vb, relh, relw, scale_log2e, trow, s0, s1, row < nq);
-        ptx::tmem_ld_wait_dep(va);
-        softmax_chunk<6, FMT>(va, relh, relw, scale_log2e, trow, s0, s1, row < nq);
+        float om;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(om) : "r"(xch + (half ^ 1) * 8) : "memory");
+        mref = fmaxf(mref, om);
       }
+#pragma unroll
+      for (int kh = 0; kh < 8; ++kh) relh[kh] -= mref;
+      named_bar_sync4(pair_bar, 64);       // both have read the maxima before the slots are reused for the sums
+
+      if (tr) WT(2 + half, 3);
+      f32x2 s0 = 0ull, s1 = 0ull;
+      float moved = 0.f;                   // how far this thread's reference has moved up (lazy rescale)
+      const bool valid = row < nq;
+      const uint32_t pbase = trow + (half ? TM_P1 : 0);
+      if (half)
+        HalfLoop<0, 7, kHalfKeys, 6, FMT>::run(scol, pbase, first, relh, relw, scale_log2e, valid, s0, s1, moved);
+      else
+        HalfLoop<0, 6, 0, 0, FMT>::run(scol, pbase, first, relh, relw, scale_log2e, valid, s0, s1, moved);
+      if (tr) WT(2 + half, 4);
       float a0, a1;
       upk2(add2(s0, s1), a0, a1);
-      const float sum = a0 + a1;
+      float sum = a0 + a1;
+      // reconcile the two halves: common reference = the higher of the two; the other half rescales (rare)
+      asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(xch + half * 8), "f"(sum), "f"(moved) : "memory");
+      named_bar_sync4(pair_bar, 64);
+      float2 other;
+      asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(other.x), "=f"(other.y) : "r"(xch + (half ^ 1) * 8) : "memory");
+      {
+        const float top = fmaxf(moved, other.y);
+        const float mine_a = ex2(moved - top), other_a = ex2(other.y - top);     // 1.0 unless a reference moved
+        if (__any_sync(0xffffffffu, moved != top)) {
+          tmem_st_wait();
+          rescale_p<FMT>(pbase, half ? 7 : 6, mine_a);
+        }
+        sum = sum * mine_a + other.x * other_a;
+      }
       tmem_st_wait();
       ptx::tc_fence_before();
       ptx::mbar_arrive(&p_ready[g]);
+      if (tr) WT(2 + half, 5);
 
-      ptx::mbar_wait(&o_full[g], ph);
+      WIN5_WAIT(&o_full[g], ph);
+      if (tr) WT(2 + half, 6);
       ptx::tc_fence_after();
       {
-        // pull the whole O row (80 fp32) into registers with the loads back to back, hand the TMEM slot back to the
-        // MMA issuer at once (its next S overlaps the scaling and the global stores below)
-        uint32_t o0[32], o1[32], o2[32];
-        ptx::tmem_ld_32x32b_x32(trow + TM_O, o0);
-        ptx::tmem_ld_32x32b_x32(trow + TM_O + 32, o1);
-        if (kTail) ptx::tmem_ld_32x32b_x16_lo(trow + TM_O + 64, o2);
+        // this thread's half of the O row (HD / 2 fp32) into registers, then hand the TMEM slot back to the MMA issuer
+        // at once (its next S overlaps the scaling and the stores below)
+        uint32_t o0[32], o1[16];
+        const uint32_t ocol = trow + TM_O + half * kOH;
+        ptx::tmem_ld_32x32b_x32(ocol, o0);
+        if (kTail) {
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                       : "=r"(o1[0]), "=r"(o1[1]), "=r"(o1[2]), "=r"(o1[3]), "=r"(o1[4]), "=r"(o1[5]), "=r"(o1[6]), "=r"(o1[7])
+                       : "r"(ocol + 32)
+                       : "memory");
+        }
         ptx::tmem_ld_wait_dep(o0);
-        ptx::tmem_ld_wait_dep(o1);
-        if (kTail) ptx::tmem_ld_wait_dep(o2);
+        if (kTail) ptx::tmem_ld_wait_dep16(o1);
         ptx::tc_fence_before();
         ptx::mbar_arrive(&o_done[g]);
+        if (tr) WT(2 + half, 7);
         const float inv = 1.0f / sum;
-        const int y = w.wy * WS + qiy, x = w.wx * WS + qix;
-        const bool ok = (row < nq) && (y < 64) && (x < 64);
-        if (WIN4_TMA_OUT) {
-          uint8_t* st = smem + s * kStageBytes;
-          if (row < nq) {
+        uint8_t* st = smem + s * kStageBytes;
+        if (row < nq) {
+          constexpr int kUH = kU4 / 2;     // 16-byte output units per thread (5 for head_dim 80, 4 for 64)
 #pragma unroll
-            for (int c = 0; c < kU4; ++c) {
-              const uint32_t* v = (c < 4) ? &o0[c * 8] : (c < 8) ? &o1[(c - 4) * 8] : &o2[(c - 8) * 8];
-              uint4 u;
-              u.x = ptx::pack2t<FMT>(__uint_as_float(v[0]) * inv, __uint_as_float(v[1]) * inv);
-              u.y = ptx::pack2t<FMT>(__uint_as_float(v[2]) * inv, __uint_as_float(v[3]) * inv);
-              u.z = ptx::pack2t<FMT>(__uint_as_float(v[4]) * inv, __uint_as_float(v[5]) * inv);
-              u.w = ptx::pack2t<FMT>(__uint_as_float(v[6]) * inv, __uint_as_float(v[7]) * inv);
-              if (c < 8)
-                *reinterpret_cast<uint4*>(st + OFF_Q64 + g * 16384 + row_off64(row, c)) = u;
-              else
-                *reinterpret_cast<uint4*>(st + OFF_Q16 + g * 4096 + row_off16(row, c - 8)) = u;
-            }
-          }
-          ptx::fence_proxy_async_smem();   // staging rows (and the gather scratch before them) -> async proxy
-          named_bar_sync4(1 + g, 128);
-          if ((warp & 3) == 2 && lane == 0) {
-            const int co = w.head * HD, x0 = w.wx * WS, y0 = w.wy * WS + (g ? 9 : 0);
-            tma_store_4d(g ? &maps.ob64 : &maps.oa64, st + OFF_Q64 + g * 16384, co, x0, y0, w.b);
-            if (kTail) tma_store_4d(g ? &maps.ob16 : &maps.oa16, st + OFF_Q16 + g * 4096, co + 64, x0, y0, w.b);
-            bulk_commit4();
-          }
-        } else if (ok) {
-          uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<size_t>(w.b) * 4096 + (y * 64 + x)) * E + w.head * HD);
-#pragma unroll
-          for (int c = 0; c < kU4; ++c) {
-            const uint32_t* v = (c < 4) ? &o0[c * 8] : (c < 8) ? &o1[(c - 4) * 8] : &o2[(c - 8) * 8];
+          for (int i = 0; i < kUH; ++i) {
+            const uint32_t* v = (i < 4) ? &o0[i * 8] : &o1[(i - 4) * 8];
             uint4 u;
             u.x = ptx::pack2t<FMT>(__uint_as_float(v[0]) * inv, __uint_as_float(v[1]) * inv);
             u.y = ptx::pack2t<FMT>(__uint_as_float(v[2]) * inv, __uint_as_float(v[3]) * inv);
             u.z = ptx::pack2t<FMT>(__uint_as_float(v[4]) * inv, __uint_as_float(v[5]) * inv);
             u.w = ptx::pack2t<FMT>(__uint_as_float(v[6]) * inv, __uint_as_float(v[7]) * inv);
-            dst[c] = u;
+            const int c = half * kUH + i;  // unit of the output row
+            if (c < 8)
+              *reinterpret_cast<uint4*>(st + OFF_Q64 + g * 16384 + row_off64(row, c)) = u;
+            else
+              *reinterpret_cast<uint4*>(st + OFF_Q16 + g * 4096 + row_off16(row, c - 8)) = u;
           }
+        }
+        ptx::fence_proxy_async_smem();   // staging rows (and the gather scratch before them) -> async proxy
+        named_bar_sync4(9 + g, 256);
+        if (tr) WT(2 + half, 8);
+        if (store_thread) {
+          const int co = w.head * HD, x0 = w.wx * WS, y0 = w.wy * WS + (g ? 9 : 0);
+          tma_store_4d(g ? &maps.ob64 : &maps.oa64, st + OFF_Q64 + g * 16384, co, x0, y0, w.b);
+          if (kTail) tma_store_4d(g ? &maps.ob16 : &maps.oa16, st + OFF_Q16 + g * 4096, co + 64, x0, y0, w.b);
+          bulk_commit4();
         }
       }
     }
+    if (store_thread) bulk_wait_all4();   // output stores landed
   }
 
-  if (WIN4_TMA_OUT && warp >= 2 && warp <= 9 && (warp & 3) == 2 && lane == 0) bulk_wait_all4();   // output stores landed
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem, 512);
   }
+#if WIN5_TRACE
+  if (blockIdx.x == 0 && tid == 0) {
+    const long long t0 = g_win5_trace[0];
+    for (int i = 0; i < 2; ++i)
+      for (int r = 0; r < 4; ++r) {
+        const long long* e = &g_win5_trace[(i * 4 + r) * 12];
+        printf("item %d role %d:", 3 + i, r);
+        for (int k = 0; k < 9; ++k) printf(" %lld", e[k] ? e[k] - t0 : -1ll);
+        if (r == 1) printf("  globaltimer_ns %lld", e[9] - g_win5_trace[1 * 12 + 9]);
+        printf("\n");
+      }
+  }
+#endif
 }
 
 }  // namespace
