@@ -73,7 +73,7 @@ size_t samk_encoder_workspace_bytes(const SamEncoderShape& s, int B) {
   bytes += M * C * 2;        // n16
   if (s.ln_fold) {
     bytes += M * E * 2;            // xb: operand-format copy of the residual stream
-    bytes += M * (E / 128) * 8;    // per-row partial (sum, sumsq) of each 128-column slice
+    bytes += M * (E / 128) * 8;    // per-row (mean, M2) of each 128-column slice
   }
   return bytes + 1024;
 }

@@ -14,7 +14,7 @@
 // LayerNorm folding (LNF).  The encoder's norm1 / norm2 (image_encoder.py:178, :191) never run as kernels of their own:
 //   * producer  (OUT_FMT = fp32, LNF): the residual GEMMs (proj, lin2) load the x tile with TMA, add, store the new
 //     fp32 x with TMA, store a 16-bit copy xb = round(x) for the next GEMM and write per-row partial sums
-//     (sum, sum of squares over each 128-column slice) -- x is read once and never again by a LayerNorm pass;
+//     (mean, sum of squared deviations of each 128-column slice) -- x is read once and never again by a LayerNorm pass;
 //   * consumer  (OUT_FMT = 16-bit, LNF): qkv / lin1 multiply xb by W' = gamma o W and finish the normalisation in
 //     the epilogue:  LN(x).W^T + b = rstd * (xb.W'^T - mean * colsum(W')) + (beta.W^T + b).
 #include <stdio.h>
@@ -227,6 +227,15 @@ __device__ __forceinline__ void gelu_fast2(float& x0, float& x1) {
   ptx::upk2(r, x0, x1);
 }
 
+// LnSlice: statistics of one 128-column slice of a residual row as (mean, M2 = sum of squared deviations from that
+// mean).  The producers accumulate sums of (x - shift) with shift = the slice's first element -- a value within a few
+// standard deviations of the mean, so neither sum cancels -- and the consumer combines the slices with Chan's formula;
+// the textbook E[x^2] - mean^2 loses all precision for rows whose |mean| is far above their standard deviation.
+__device__ __forceinline__ float2 ln_slice(float shift, float s1, float s2) {
+  const float m = s1 * (1.0f / 128.0f);
+  return make_float2(shift + m, fmaxf(fmaf(-s1, m, s2), 0.f));
+}
+
 struct Gemm2Params {
   const float* bias;
   int act;         // 0 none, 1 GELU
@@ -234,7 +243,7 @@ struct Gemm2Params {
   int out_fmt;     // SamFmt of the output
   int M, N, K;
   uint32_t idesc;
-  // LayerNorm folding, consumer side: per-row partial (sum, sumsq) [M, ln_parts], colsum(W') [N]
+  // LayerNorm folding, consumer side: per-row slice statistics (mean, M2) [M, ln_parts], colsum(W') [N]
   const float2* ln_stats;
   int ln_parts;
   const float* ln_colsum;
@@ -386,7 +395,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
         }
         uint32_t lph = 0;
-        float s1 = 0.f, s2 = 0.f;
+        float s1 = 0.f, s2 = 0.f, shift = 0.f;
 #pragma unroll 1
         for (int q = 0; q < total_q; ++q) {
           const int c = q & 3, b = q & 1;
@@ -423,8 +432,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             x4.y += __uint_as_float(v[4 * i + 1]) + b4.y;
             x4.z += __uint_as_float(v[4 * i + 2]) + b4.z;
             x4.w += __uint_as_float(v[4 * i + 3]) + b4.w;
-            s1 += (x4.x + x4.y) + (x4.z + x4.w);
-            s2 = fmaf(x4.x, x4.x, s2); s2 = fmaf(x4.y, x4.y, s2); s2 = fmaf(x4.z, x4.z, s2); s2 = fmaf(x4.w, x4.w, s2);
+            if (c == 0 && i == 0) shift = x4.x;      // per-slice shift: sums of (x - shift) do not cancel (see LnSlice)
+            {
+              const float dx = x4.x - shift, dy = x4.y - shift, dz = x4.z - shift, dw = x4.w - shift;
+              s1 += (dx + dy) + (dz + dw);
+              s2 = fmaf(dx, dx, s2); s2 = fmaf(dy, dy, s2); s2 = fmaf(dz, dz, s2); s2 = fmaf(dw, dw, s2);
+            }
             ptx::st_shared_v4f(sa, x4);
             v[4 * i + 0] = __float_as_uint(x4.x); v[4 * i + 1] = __float_as_uint(x4.y);
             v[4 * i + 2] = __float_as_uint(x4.z); v[4 * i + 3] = __float_as_uint(x4.w);
@@ -454,7 +467,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             if (c == 3) {
               const int tile = cluster_id + (q >> 2) * num_clusters;
               const int part = (tile % n_tiles) * 2 + half;
-              p.stats_out[static_cast<size_t>(row) * (p.N >> 7) + part] = make_float2(s1, s2);
+              p.stats_out[static_cast<size_t>(row) * (p.N >> 7) + part] = ln_slice(shift, s1, s2);
             }
           }
           if (c == 3 && ++as == 2) { as = 0; aph ^= 1; }
@@ -487,7 +500,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       float4 xa[8], xb2[8];
       load_x(0, xa);
       load_x(1, xb2);
-      float s1 = 0.f, s2 = 0.f;
+      float s1 = 0.f, s2 = 0.f, shift = 0.f;
       auto process = [&](const int q, float4 (&xn)[8]) {
         const int c = q & 3;
         int col0, row0;
@@ -538,8 +551,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             x4.y += __uint_as_float(v[4 * i + 1]) + b4.y;
             x4.z += __uint_as_float(v[4 * i + 2]) + b4.z;
             x4.w += __uint_as_float(v[4 * i + 3]) + b4.w;
-            s1 += (x4.x + x4.y) + (x4.z + x4.w);
-            s2 = fmaf(x4.x, x4.x, s2); s2 = fmaf(x4.y, x4.y, s2); s2 = fmaf(x4.z, x4.z, s2); s2 = fmaf(x4.w, x4.w, s2);
+            if (c == 0 && i == 0) shift = x4.x;
+            {
+              const float dx = x4.x - shift, dy = x4.y - shift, dz = x4.z - shift, dw = x4.w - shift;
+              s1 += (dx + dy) + (dz + dw);
+              s2 = fmaf(dx, dx, s2); s2 = fmaf(dy, dy, s2); s2 = fmaf(dz, dz, s2); s2 = fmaf(dw, dw, s2);
+            }
             ptx::st_shared_v4f(sb + ((i ^ (lane & 7)) << 4), x4);
             xr[i] = x4;
           }
@@ -572,7 +589,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (c == 3) {
             const int tile = cluster_id + (q >> 2) * num_clusters;
             const int part = (tile % n_tiles) * 2 + half;
-            p.stats_out[static_cast<size_t>(row) * (p.N >> 7) + part] = make_float2(s1, s2);
+            p.stats_out[static_cast<size_t>(row) * (p.N >> 7) + part] = ln_slice(shift, s1, s2);
           }
         }
         if (c == 3 && ++as == 2) { as = 0; aph ^= 1; }
@@ -592,15 +609,20 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         // LNF consumer: finish the row statistics of this thread's row while the main loop of the tile runs
         const int row = row0 + lane;
         if (row < p.M) {
+          // combine the equal-sized slices (mean_i, M2_i): mean = avg(mean_i), M2 = sum M2_i + n_i * sum (mean_i - mean)^2
           const float2* st = p.ln_stats + static_cast<size_t>(row) * p.ln_parts;
-          float s1 = 0.f, s2 = 0.f;
+          float sm = 0.f;
+          for (int i = 0; i < p.ln_parts; ++i) sm += __ldg(st + i).x;
+          ln_mu = sm / static_cast<float>(p.ln_parts);
+          float m2 = 0.f, dev = 0.f;
           for (int i = 0; i < p.ln_parts; ++i) {
             const float2 t = __ldg(st + i);
-            s1 += t.x;
-            s2 += t.y;
+            const float d = t.x - ln_mu;
+            m2 += t.y;
+            dev = fmaf(d, d, dev);
           }
-          ln_mu = s1 * p.ln_inv_c;
-          ln_r = rsqrtf(fmaxf(fmaf(-ln_mu, ln_mu, s2 * p.ln_inv_c), 0.f) + p.ln_eps);
+          const float n_i = 1.0f / (p.ln_inv_c * static_cast<float>(p.ln_parts));     // columns per slice
+          ln_r = rsqrtf(fmaf(n_i, dev, m2) * p.ln_inv_c + p.ln_eps);
         }
       }
       wait_role<2>(&acc_full[as], aph);

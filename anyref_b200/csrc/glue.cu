@@ -298,7 +298,7 @@ ln_nhwc_to_nchw_kernel(const float* __restrict__ x, const float* __restrict__ ga
 }
 
 // First producer of the LayerNorm-folding chain (gemm2.cu): xb = round(x) in the operand format plus the per-row
-// partial (sum, sum of squares) of every 128-column slice -- what the residual GEMM epilogues emit for all later
+// partial statistics (mean, sum of squared deviations) of every 128-column slice -- what the residual GEMM epilogues emit for all later
 // blocks.  One warp per row; lane l holds columns 128 j + 4 l .. + 3 of slice j.
 // With `pos` the broadcast rows pos[row % pos_mod] (pos_embed, image_encoder.py:112-113) are added first and the sum is
 // written back to x, so the patch-embed GEMM can use the plain fp32 store epilogue of the 2-CTA kernel.
@@ -322,9 +322,12 @@ cast_stats_kernel(float* __restrict__ x, int ldx, void* __restrict__ xb, int ldx
       u.x = ptx::pack2(v.x, v.y, fmt);
       u.y = ptx::pack2(v.z, v.w, fmt);
       orow[j * 32 + lane] = u;
-      const float s1 = warp_sum((v.x + v.y) + (v.z + v.w));
-      const float s2 = warp_sum(fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w))));
-      if (lane == 0) stats[static_cast<size_t>(row) * parts + j] = make_float2(s1, s2);
+      // (mean, M2 = sum of squared deviations from that mean) of the slice: the consumer combines the slices with
+      // Chan's formula, so no E[x^2] - mean^2 cancellation occurs even for rows whose |mean| is far above their std
+      const float mean = warp_sum((v.x + v.y) + (v.z + v.w)) * (1.0f / 128.0f);
+      const float dx = v.x - mean, dy = v.y - mean, dz = v.z - mean, dw = v.w - mean;
+      const float m2 = warp_sum(fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, dw * dw))));
+      if (lane == 0) stats[static_cast<size_t>(row) * parts + j] = make_float2(mean, m2);
     }
   }
 }

@@ -23,7 +23,7 @@ struct GemmEpilogue {
   // LayerNorm folding (gemm2.cu), all optional (zero = off):
   //   consumer: A = 16-bit copy of the un-normalised rows, W = gamma o W; the epilogue computes
   //             rstd * (acc - mean * ln_colsum[n]) + bias[n]  with mean / rstd from the partial sums ln_stats [M, ln_parts]
-  //             ((sum, sum of squares) per slice of the ln_c-wide row); bias must hold beta.W^T + b
+  //             ((mean, sum of squared deviations) per slice of the ln_c-wide row, combined with Chan's formula); bias must hold beta.W^T + b
   const void* ln_stats = nullptr;
   int ln_parts = 0;
   const float* ln_colsum = nullptr;
@@ -78,7 +78,7 @@ int samk_attn_global3(const void* qkv, const void* rh_rev, const void* rw_rev, v
 //   layernorm_rows : out[row] = LN(x[row] (+ res[row])) * gamma + beta  (normalize == 0: plain dtype cast)
 int samk_layernorm_rows(const float* x, int ldx, const float* res, int ldr, const float* gamma, const float* beta,
                         float eps, void* out, int ldo, int out_fmt, int M, int C, int normalize, cudaStream_t stream);
-//   cast_stats : xb = round(x) (operand format) + per-row partial (sum, sumsq) of every 128-column slice [M, C/128]
+//   cast_stats : xb = round(x) (operand format) + per-row (mean, M2) of every 128-column slice [M, C/128]
 //                (pos != null: x[row] += pos[row % pos_mod] first, written back to x)
 int samk_cast_stats(float* x, int ldx, void* xb, int ldxb, int fmt, void* stats, int M, int C, const float* pos,
                     int pos_mod, cudaStream_t stream);

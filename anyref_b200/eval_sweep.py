@@ -80,6 +80,11 @@ def sweep(sam, num_images: int, n_seg: int, batch: int, rank: int, world: int, d
 
     lo, hi = dp.shard_range(num_images, rank, world)
     if world > 1:
+        # the first collective of each kind sets up NCCL's channels (tens of ms, once per process): keep that one-time
+        # cost out of the timed sweep, like the kernels' warm-up batch (round 1 charged it to the 8-GPU sweep: 11 %)
+        dp.all_reduce_stats(torch.zeros(7, dtype=torch.float64, device=device))
+        if gather_masks:
+            dp.all_gather_packed(torch.zeros(1 << 20, dtype=torch.uint8, device=device))
         dist.barrier()
     torch.cuda.synchronize(device)
     e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))

@@ -46,7 +46,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, act: str = "none", resi
 
 @_lib.device_scoped
 def cast_stats(x: torch.Tensor, out_dtype):
-    """-> (xb = x.to(out_dtype), stats [M, C/128, 2] fp32 partial (sum, sumsq) per 128-column slice); see sam_cast_stats."""
+    """-> (xb = x.to(out_dtype), stats [M, C/128, 2] fp32 per-slice (mean, sum of squared deviations) of every 128 columns); see sam_cast_stats."""
     _req_cuda(x)
     assert x.dim() == 2 and x.dtype == torch.float32 and x.stride(1) == 1
     M, Cc = x.shape

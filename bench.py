@@ -310,6 +310,37 @@ def library_baseline(dev, n_seg: int, budget_s: float = 40.0):
     return out
 
 
+def cublas_sustained(dev, seconds: float = 1.5):
+    """cuBLAS (torch.matmul) 8192^3 back to back for `seconds` per operand format ON THIS BOX, the driver's recipe for
+    MEASURED_PEAKS.json's sustained figure: boxes differ by +-5 % under the power cap and fp16 operands draw more power
+    than bf16 ones, so the same-box same-format number is the fair denominator next to the recorded bf16 peak."""
+    out = {"how": "torch.matmul 8192^3 back to back, CUDA events, this process / this GPU", "unit": "TFLOP/s"}
+    n = 8192
+    for name, dt in (("bf16", torch.bfloat16), ("fp16", torch.float16)):
+        a = torch.randn(n, n, device=dev).to(dt)
+        b = torch.randn(n, n, device=dev).to(dt)
+        c = torch.empty(n, n, device=dev, dtype=dt)
+        for _ in range(3):
+            torch.matmul(a, b, out=c)
+        torch.cuda.synchronize()
+        iters = 40
+        t0 = time.perf_counter()
+        done, ms = 0, 0.0
+        while time.perf_counter() - t0 < seconds:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                torch.matmul(a, b, out=c)
+            e1.record()
+            torch.cuda.synchronize()
+            ms += e0.elapsed_time(e1)
+            done += iters
+        out[name] = 2.0 * n ** 3 * done / (ms * 1e-3) / 1e12
+        del a, b, c
+    torch.cuda.empty_cache()
+    return out
+
+
 def sub_record_c3(path, dev, op_dtype, rank, timed_fn, world):
     """BASELINE.json configs[2]: 8 images x 4 [SEG] x 3 masks (multimask_output), content 1024x683 -> 640x427 masks."""
     from anyref_b200.synthetic import synthetic_images, synthetic_seg_embeddings
@@ -500,6 +531,7 @@ def main():
         if rank == 0 and world == 1:
             torch.cuda.empty_cache()
             extras["library_baseline"] = library_baseline(dev, n_seg)
+            extras["cublas_same_box"] = cublas_sustained(dev)
 
     parity = None
     if rank == 0 and not args.no_parity:
@@ -549,6 +581,8 @@ def main():
             "cpu_baseline": cpu_baseline,
         }
         line.update(extras)
+        if "cublas_same_box" in extras:
+            line["roofline"]["frac_vs_cublas_same_box_same_format"] = gemm_tflops / extras["cublas_same_box"][args.dtype]
         _emit(line)
     if world > 1:
         dist.barrier()

@@ -94,7 +94,7 @@ int sam_layernorm(const float* x, int ldx, const float* res, int ldr, const floa
  *
  *   sam_gemm_residual_ln  x[M,N] += A[M,K].W[N,K]^T + bias  in place (fp32; image_encoder.py:190, :192), and in the
  *                         same epilogue  xb[M,ldxb] = round(x) in format `fmt`  and  stats[M, N/128] (float2) = the
- *                         (sum, sum of squares) of every 128-column slice of the new row.  N % 128 == 0, M % 32 == 0.
+ *                         (mean, sum of squared deviations from it) of every 128-column slice of the new row.  N % 128 == 0, M % 32 == 0.
  *   sam_cast_stats        the same xb / stats from an existing fp32 x [M, C] (first block).  C % 128 == 0.
  *   sam_gemm_ln           out[M,N] = act( rstd_r * (xb[M,K].Wg[N,K]^T - mean_r * colsum[n]) + bias_fold[n] )  with
  *                         Wg = gamma o W rounded to `fmt`, colsum[n] = sum_k Wg[n,k], bias_fold = beta.W^T + b,

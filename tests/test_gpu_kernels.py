@@ -58,15 +58,16 @@ def test_cast_stats(ops, dt):
     x = torch.randn(4096 + 24, 1280, device=DEV) * 2 + 0.3
     xb, stats = ops.cast_stats(x, dt)
     assert torch.equal(xb, x.to(dt))                                           # rounding is bit-exact
-    xs = x.double().view(x.shape[0], 10, 128)
-    assert (stats[..., 0].double() - xs.sum(-1)).abs().max().item() < 1e-3
-    assert ((stats[..., 1].double() - (xs * xs).sum(-1)).abs() / (xs * xs).sum(-1)).max().item() < 1e-5
+    xs = x.double().view(x.shape[0], 10, 128)                                  # per 128-column slice: (mean, M2)
+    m2 = ((xs - xs.mean(-1, keepdim=True)) ** 2).sum(-1)
+    assert (stats[..., 0].double() - xs.mean(-1)).abs().max().item() < 1e-5
+    assert ((stats[..., 1].double() - m2).abs() / m2).max().item() < 1e-5
 
 
 @pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("M,N,K", [(4096, 1280, 1280), (8192, 1280, 5120), (2048 + 32, 256, 256), (65536, 1280, 1280)])
 def test_gemm_residual_ln_producer(ops, dt, M, N, K):
-    """x += a.W^T + b in place; xb == round(x) bit-exactly; partial sums of the NEW x (image_encoder.py:190-192)."""
+    """x += a.W^T + b in place; xb == round(x) bit-exactly; slice statistics (mean, M2) of the NEW x (image_encoder.py:190-192)."""
     torch.manual_seed(M + N + K)
     a = (torch.randn(M, K, device=DEV) * 0.5).to(dt)
     w = (torch.randn(N, K, device=DEV) * 0.05).to(dt)
@@ -78,8 +79,9 @@ def test_gemm_residual_ln_producer(ops, dt, M, N, K):
     assert rel_fro(x, ref) < 1e-5
     assert torch.equal(xb, x.to(dt))
     xs = x.double().view(M, N // 128, 128)
-    assert (stats[..., 0].double() - xs.sum(-1)).abs().max().item() < 2e-3
-    assert ((stats[..., 1].double() - (xs * xs).sum(-1)).abs() / (xs * xs).sum(-1)).max().item() < 1e-5
+    m2 = ((xs - xs.mean(-1, keepdim=True)) ** 2).sum(-1)
+    assert (stats[..., 0].double() - xs.mean(-1)).abs().max().item() < 2e-5
+    assert ((stats[..., 1].double() - m2).abs() / m2).max().item() < 2e-5
     # same numbers as the plain in-place residual epilogue (TMA reduce-add) up to the last fp32 bit
     y = x0.clone()
     ops.gemm(a, w, bias=bias, residual=y, out=y)
@@ -113,6 +115,56 @@ def test_gemm_ln_consumer_matches_layernorm_then_linear(ops, dt, tol, M, N, K, a
     a16 = ops.layernorm(x, gamma, beta, 1e-6, dt)
     plain = ops.gemm(a16, W.to(dt), bias=b, act=act, out_dtype=dt)
     assert rel_fro(got, want.float()) < 1.5 * rel_fro(plain, want.float()) + 1e-4
+
+
+def _stats_to_mean_var(stats, C):
+    """Chan combination of the per-slice (mean, M2) statistics [M, C/128, 2] -> (mean [M], biased variance [M])."""
+    mean_i, m2_i = stats[..., 0].double(), stats[..., 1].double()
+    mean = mean_i.mean(dim=1)
+    m2 = m2_i.sum(dim=1) + 128.0 * ((mean_i - mean[:, None]) ** 2).sum(dim=1)
+    return mean, m2 / C
+
+
+@pytest.mark.parametrize("offset", [0.0, 50.0, 1000.0])
+def test_ln_fold_statistics_survive_a_large_row_mean(ops, offset):
+    """Rows whose |mean| is up to 1000x their standard deviation: the folded LayerNorm's statistics -- per 128-column
+    slice (mean, M2) from cast_stats and from the residual-GEMM producer epilogue, combined with Chan's formula in the
+    consumer -- must still give the row variance to 1e-4 (E[x^2] - mean^2 in fp32 is off by several per cent at 1000),
+    and the consumer GEMM must match the same formula evaluated in fp64 on the SAME rounded operand."""
+    torch.manual_seed(17)
+    M, K, N = 2048, 1280, 1280
+    dt = torch.float16
+    x = torch.randn(M, K, device=DEV) + offset * (1.0 + torch.rand(M, 1, device=DEV))
+    mean_ref, var_ref = x.double().mean(1), x.double().var(1, unbiased=False)
+    xb, stats = ops.cast_stats(x.clone(), dt)
+    mean, var = _stats_to_mean_var(stats, K)
+    assert ((mean - mean_ref).abs() / (mean_ref.abs() + 1.0)).max().item() < 1e-6
+    assert ((var - var_ref).abs() / var_ref).max().item() < 1e-4
+    # producer epilogue: x <- x + a.w^T + b, statistics of the NEW rows
+    a = (torch.randn(M, 256, device=DEV) * 0.5).to(dt)
+    w = (torch.randn(N, 256, device=DEV) * 0.05).to(dt)
+    bias = torch.randn(N, device=DEV) * 0.1
+    x2 = x.clone()
+    xb2, stats2 = ops.gemm_residual_ln(a, w, x2, bias)
+    mean2, var2 = _stats_to_mean_var(stats2, N)
+    assert ((mean2 - x2.double().mean(1)).abs() / (x2.double().mean(1).abs() + 1.0)).max().item() < 1e-6
+    assert ((var2 - x2.double().var(1, unbiased=False)).abs() / x2.double().var(1, unbiased=False)).max().item() < 1e-4
+    # consumer: rstd * (xb . W'^T - mean * colsum) + bias'  against fp64 with the exact statistics of x
+    import types
+    from anyref_b200.segment_anything._pack import _fold_layernorm
+
+    gamma = torch.rand(K, device=DEV) * 0.2 + 0.9
+    beta = torch.rand(K, device=DEV) * 0.2 - 0.1
+    W = (torch.rand(256, K, device=DEV) * 2 - 1) / K ** 0.5
+    b = (torch.rand(256, device=DEV) * 2 - 1) / K ** 0.5
+    wg, colsum, bias_fold = _fold_layernorm(types.SimpleNamespace(weight=gamma, bias=beta),
+                                            types.SimpleNamespace(weight=W, bias=b), dt)
+    got = ops.gemm_ln(xb, wg, bias_fold, colsum, stats, 1e-6).float()
+    rstd = 1.0 / torch.sqrt(var_ref + 1e-6)
+    want = rstd[:, None] * (xb.double() @ wg.double().t() - mean_ref[:, None] * colsum.double()[None]) + bias_fold.double()
+    # the products xb.W' and mean.colsum are ~offset times larger than their difference: allow their fp32 rounding
+    tol = 2e-3 * (1.0 + offset / 10.0)
+    assert ((got.double() - want).norm() / want.norm()).item() < tol
 
 
 def _guarded(shape, dtype, pad=4096):
