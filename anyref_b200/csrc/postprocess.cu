@@ -58,11 +58,15 @@ constexpr int kPostThreads = 128;  // a thread owns NC columns, 32 apart (lane-c
 // [x_cta + w * 32 * NC, + 32 * NC): column j of lane l is x_warp + 32 j + l.  The row-dependent work (row taps, cache
 // decisions, loop overhead) is shared by the NC columns of a thread -- with one column per thread the kernel was
 // issue-bound on exactly that work (ncu r02: SM 82 %, DRAM 2 %).
+// IDENT: input_size == original_size, i.e. the second resize is the identity (every stage-2 tap is (i, i, 1, 0)): the
+// output IS the stage-1 image, so the stage-2 lerps, the second column taps and half of the low-res loads drop out --
+// values equal to the general path's (l0 = 1, l1 = 0 exactly), which is the shape the throughput bench and square
+// inputs run.
 // With `target` / `counts` the intersectionAndUnionGPU statistics of the thresholded mask (utils/utils.py:79-91, K = 2,
 // ignore_index = 255) are accumulated in the same pass: counts[m] = {inter_0, inter_1, pred_0, pred_1, target_0,
 // target_1} (int32, atomically added), so the evaluation loop (eval_referseg.py:186-211) needs neither the full
 // resolution logits nor the mask in HBM.
-template <int NC, int FMT>
+template <int NC, int FMT, bool IDENT>
 __global__ void __launch_bounds__(kPostThreads)
 postprocess_kernel(const void* __restrict__ low, int L, int S, int h_in, int w_in, int H, int W,
                    float* __restrict__ logits, uint8_t* __restrict__ binary, uint8_t* __restrict__ packed, float threshold,
@@ -85,7 +89,7 @@ postprocess_kernel(const void* __restrict__ low, int L, int S, int h_in, int w_i
     col_ok[j] = Xr < W;
     tx[j] = make_tap(col_ok[j] ? Xr : W - 1, sx, w_in);    // out-of-range columns shadow the last one (no stores)
     ca[j] = make_tap(tx[j].i0, scale1, L);
-    cb[j] = make_tap(tx[j].i1, scale1, L);
+    cb[j] = IDENT ? ca[j] : make_tap(tx[j].i1, scale1, L);
   }
   // low-res row cache (rows hr0, hr1): horizontal lerps at stage-1 columns x0 (a) and x1 (b) of every column
   int hr0 = -1, hr1 = -1;
@@ -95,7 +99,7 @@ postprocess_kernel(const void* __restrict__ low, int L, int S, int h_in, int w_i
 #pragma unroll
     for (int j = 0; j < NC; ++j) {
       ha[j] = lerp1(ca[j].l0, ld<FMT>(low, r + ca[j].i0), ca[j].l1, ld<FMT>(low, r + ca[j].i1));
-      hb[j] = lerp1(cb[j].l0, ld<FMT>(low, r + cb[j].i0), cb[j].l1, ld<FMT>(low, r + cb[j].i1));
+      if (!IDENT) hb[j] = lerp1(cb[j].l0, ld<FMT>(low, r + cb[j].i0), cb[j].l1, ld<FMT>(low, r + cb[j].i1));
     }
   };
   // stage-2 horizontal lerp g(y) of stage-1 row y (all branches depend on y only: warp-uniform)
@@ -104,7 +108,10 @@ postprocess_kernel(const void* __restrict__ low, int L, int S, int h_in, int w_i
     if (t.i0 == hr1) {
       hr0 = hr1;
 #pragma unroll
-      for (int j = 0; j < NC; ++j) { ha0[j] = ha1[j]; hb0[j] = hb1[j]; }
+      for (int j = 0; j < NC; ++j) {
+        ha0[j] = ha1[j];
+        if (!IDENT) hb0[j] = hb1[j];
+      }
       hr1 = -1;
     }
     if (t.i0 != hr0) {
@@ -119,15 +126,23 @@ postprocess_kernel(const void* __restrict__ low, int L, int S, int h_in, int w_i
 #pragma unroll
       for (int j = 0; j < NC; ++j) {
         const float sa = lerp1(t.l0, ha0[j], t.l1, ha1[j]);     // stage-1 value at (y, x0)
-        const float sb = lerp1(t.l0, hb0[j], t.l1, hb1[j]);     // stage-1 value at (y, x1)
-        g[j] = lerp1(tx[j].l0, sa, tx[j].l1, sb);
+        if (IDENT) {
+          g[j] = sa;
+        } else {
+          const float sb = lerp1(t.l0, hb0[j], t.l1, hb1[j]);   // stage-1 value at (y, x1)
+          g[j] = lerp1(tx[j].l0, sa, tx[j].l1, sb);
+        }
       }
     } else {
 #pragma unroll
       for (int j = 0; j < NC; ++j) {
         const float sa = lerp1(t.l0, ha0[j], t.l1, ha0[j]);
-        const float sb = lerp1(t.l0, hb0[j], t.l1, hb0[j]);
-        g[j] = lerp1(tx[j].l0, sa, tx[j].l1, sb);
+        if (IDENT) {
+          g[j] = sa;
+        } else {
+          const float sb = lerp1(t.l0, hb0[j], t.l1, hb0[j]);
+          g[j] = lerp1(tx[j].l0, sa, tx[j].l1, sb);
+        }
       }
     }
   };
@@ -136,26 +151,34 @@ postprocess_kernel(const void* __restrict__ low, int L, int S, int h_in, int w_i
   int cnt[6] = {0, 0, 0, 0, 0, 0};
 #pragma unroll 1
   for (int Y = Y0; Y < Y1; ++Y) {
-    const Tap ty = make_tap(Y, sy, h_in);
-    if (ty.i0 == gr1) {
-      gr0 = gr1;
+    bool two = false;
+    Tap ty;
+    if (IDENT) {
+      stage1_row(Y, g0);           // the stage-2 taps of row Y are (Y, Y, 1, 0): the output row is stage-1 row Y
+      ty.l0 = 1.0f;
+      ty.l1 = 0.0f;
+    } else {
+      ty = make_tap(Y, sy, h_in);
+      if (ty.i0 == gr1) {
+        gr0 = gr1;
 #pragma unroll
-      for (int j = 0; j < NC; ++j) g0[j] = g1[j];
-      gr1 = -1;
-    }
-    if (ty.i0 != gr0) {
-      stage1_row(ty.i0, g0);
-      gr0 = ty.i0;
-    }
-    const bool two = ty.i1 != ty.i0;
-    if (two && ty.i1 != gr1) {
-      stage1_row(ty.i1, g1);
-      gr1 = ty.i1;
+        for (int j = 0; j < NC; ++j) g0[j] = g1[j];
+        gr1 = -1;
+      }
+      if (ty.i0 != gr0) {
+        stage1_row(ty.i0, g0);
+        gr0 = ty.i0;
+      }
+      two = ty.i1 != ty.i0;
+      if (two && ty.i1 != gr1) {
+        stage1_row(ty.i1, g1);
+        gr1 = ty.i1;
+      }
     }
     const size_t orow = (static_cast<size_t>(m) * H + Y) * W;
 #pragma unroll
     for (int j = 0; j < NC; ++j) {
-      const float v = lerp1(ty.l0, g0[j], ty.l1, two ? g1[j] : g0[j]);
+      const float v = IDENT ? g0[j] : lerp1(ty.l0, g0[j], ty.l1, two ? g1[j] : g0[j]);
       const bool on = v > threshold;
       const int Xr = xw + 32 * j + lane;
       const size_t o = orow + Xr;
@@ -255,10 +278,14 @@ int samk_postprocess_iou(const void* low, int low_fmt, int num_masks, int L, int
                                  (static_cast<double>(L) * L * (low_fmt == 2 ? 4.0 : 2.0) +
                                   static_cast<double>(H) * W * ((logits ? 4.0 : 0.0) + (binary ? 1.0 : 0.0) + (packed ? 0.125 : 0.0) + (target ? 1.0 : 0.0))));
   typedef void (*Fn)(const void*, int, int, int, int, int, int, float*, uint8_t*, uint8_t*, float, const uint8_t*, int*);
-  static const Fn fns[2][3] = {{postprocess_kernel<1, 0>, postprocess_kernel<1, 1>, postprocess_kernel<1, 2>},
-                               {postprocess_kernel<4, 0>, postprocess_kernel<4, 1>, postprocess_kernel<4, 2>}};
-  fns[nc == 4][low_fmt]<<<grid, blk, 0, stream>>>(low, L, S, h_in, w_in, H, W, logits, binary, packed, threshold, target,
-                                                  counts);
+  static const Fn fns[2][2][3] = {
+      {{postprocess_kernel<1, 0, false>, postprocess_kernel<1, 1, false>, postprocess_kernel<1, 2, false>},
+       {postprocess_kernel<4, 0, false>, postprocess_kernel<4, 1, false>, postprocess_kernel<4, 2, false>}},
+      {{postprocess_kernel<1, 0, true>, postprocess_kernel<1, 1, true>, postprocess_kernel<1, 2, true>},
+       {postprocess_kernel<4, 0, true>, postprocess_kernel<4, 1, true>, postprocess_kernel<4, 2, true>}}};
+  const bool ident = (h_in == H && w_in == W);
+  fns[ident][nc == 4][low_fmt]<<<grid, blk, 0, stream>>>(low, L, S, h_in, w_in, H, W, logits, binary, packed, threshold,
+                                                         target, counts);
   SAM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -1,4 +1,5 @@
-"""Tiny single-kernel drivers for `ncu --set full` captures:  python tools/ncu_target.py <lin1|proj|qkv|lin2|attn_window|attn_global|layernorm> [iters]"""
+"""Tiny single-kernel drivers for `ncu --set full` captures:
+    python tools/ncu_target.py <lin1|proj|qkv|lin2|proj_ln|lin2_ln|qkv_fold|lin1_fold|attn_window|attn_global|layernorm> [iters] [fp16|bf16]"""
 import os
 import sys
 
@@ -9,7 +10,7 @@ from anyref_b200 import ops
 
 dev = "cuda"
 M = 65536
-dt = torch.bfloat16
+dt = torch.float16 if (len(sys.argv) > 3 and sys.argv[3] == "fp16") else torch.bfloat16
 which = sys.argv[1]
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 torch.manual_seed(0)
