@@ -106,8 +106,8 @@ def test_rel_pos_matches_reference(ref_sa):
 
 
 def test_resize_longest_side_matches_reference(ref_sa):
-    """The predictor's host-side geometry (utils/transforms.py:17-113): shapes, coordinate and box maps, and the PIL
-    bilinear image resize are identical to the reference's ResizeLongestSide."""
+    """The predictor's host-side geometry (utils/transforms.py:17-113): shapes, coordinate and box maps are identical to
+    the reference's ResizeLongestSide, and the resize oracle reproduces the reference's apply_image bit for bit."""
     import numpy as np
     from segment_anything.utils.transforms import ResizeLongestSide as RefResize
 
@@ -123,8 +123,13 @@ def test_resize_longest_side_matches_reference(ref_sa):
         assert np.array_equal(mine.apply_boxes(box, (h, w)), ref.apply_boxes(box, (h, w)))
         assert torch.equal(mine.apply_boxes_torch(torch.from_numpy(box), (h, w)),
                            ref.apply_boxes_torch(torch.from_numpy(box), (h, w)))
-    img = rng.integers(0, 256, size=(120, 200, 3), dtype=np.uint8)
-    assert np.array_equal(mine.apply_image(img), ref.apply_image(img))
+    # the image resize itself runs on the GPU (sam_resize_u8; bit-exactness vs this oracle is a GPU test): here the
+    # oracle's restatement of Pillow's resampler is pinned against the REFERENCE's own apply_image
+    from oracle import resize_oracle as R
+
+    for (h, w) in ((120, 200), (480, 640), (1365, 2048), (1024, 683), (50, 37)):
+        img = rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)
+        assert np.array_equal(R.apply_image(img, 1024), ref.apply_image(img))
 
 
 @torch.no_grad()
