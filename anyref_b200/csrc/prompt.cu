@@ -157,41 +157,39 @@ __global__ void prompt_mask_kernel(const void* __restrict__ masks, int in_fmt, c
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void preprocess_kernel(const void* __restrict__ img, int in_fmt, void* __restrict__ out, int out_fmt, int B,
                                   int h, int w, int S, float m0, float m1, float m2, float s0, float s1, float s2) {
-  const int per_row = S / 8;
-  const size_t total = static_cast<size_t>(B) * 3 * S * per_row;
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int xg = static_cast<int>(i % per_row);
-    const int y = static_cast<int>((i / per_row) % S);
-    const int c = static_cast<int>((i / (static_cast<size_t>(per_row) * S)) % 3);
-    const int b = static_cast<int>(i / (static_cast<size_t>(per_row) * S * 3));
-    const float mean = c == 0 ? m0 : (c == 1 ? m1 : m2);
-    const float sd = c == 0 ? s0 : (c == 1 ? s1 : s2);
-    float v[8];
+  // grid (ceil(S / 8 / 128), S, B * 3), block 128: row and (batch, channel) plane from the block indices (no 64-bit index
+  // decomposition per thread: that made round 1's version ALU-bound)
+  const int xg = blockIdx.x * blockDim.x + threadIdx.x;
+  if (xg * 8 >= S) return;
+  const int y = blockIdx.y;
+  const int c = blockIdx.z % 3, b = blockIdx.z / 3;
+  const float mean = c == 0 ? m0 : (c == 1 ? m1 : m2);
+  const float sd = c == 0 ? s0 : (c == 1 ? s1 : s2);
+  float v[8];
+  const size_t srow = ((static_cast<size_t>(b) * 3 + c) * h + y) * w;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int x = xg * 8 + k;
-      float t = 0.f;
-      if (y < h && x < w) {
-        const size_t src = ((static_cast<size_t>(b) * 3 + c) * h + y) * w + x;
-        const float p = (in_fmt == 3) ? static_cast<float>(static_cast<const uint8_t*>(img)[src]) : load_any(img, src, in_fmt);
-        t = __fsub_rn(p, mean) / sd;
-      }
-      v[k] = t;
+  for (int k = 0; k < 8; ++k) {
+    const int x = xg * 8 + k;
+    float t = 0.f;
+    if (y < h && x < w) {
+      const size_t src = srow + x;
+      const float p = (in_fmt == 3) ? static_cast<float>(static_cast<const uint8_t*>(img)[src]) : load_any(img, src, in_fmt);
+      t = __fsub_rn(p, mean) / sd;
     }
-    const size_t dst = ((static_cast<size_t>(b) * 3 + c) * S + y) * S + static_cast<size_t>(xg) * 8;
-    if (out_fmt == 2) {
-      float4* o = reinterpret_cast<float4*>(static_cast<float*>(out) + dst);
-      o[0] = make_float4(v[0], v[1], v[2], v[3]);
-      o[1] = make_float4(v[4], v[5], v[6], v[7]);
-    } else {
-      uint4 u;
-      u.x = ptx::pack2(v[0], v[1], out_fmt);
-      u.y = ptx::pack2(v[2], v[3], out_fmt);
-      u.z = ptx::pack2(v[4], v[5], out_fmt);
-      u.w = ptx::pack2(v[6], v[7], out_fmt);
-      *reinterpret_cast<uint4*>(static_cast<uint16_t*>(out) + dst) = u;
-    }
+    v[k] = t;
+  }
+  const size_t dst = ((static_cast<size_t>(b) * 3 + c) * S + y) * S + static_cast<size_t>(xg) * 8;
+  if (out_fmt == 2) {
+    float4* o = reinterpret_cast<float4*>(static_cast<float*>(out) + dst);
+    o[0] = make_float4(v[0], v[1], v[2], v[3]);
+    o[1] = make_float4(v[4], v[5], v[6], v[7]);
+  } else {
+    uint4 u;
+    u.x = ptx::pack2(v[0], v[1], out_fmt);
+    u.y = ptx::pack2(v[2], v[3], out_fmt);
+    u.z = ptx::pack2(v[4], v[5], out_fmt);
+    u.w = ptx::pack2(v[6], v[7], out_fmt);
+    *reinterpret_cast<uint4*>(static_cast<uint16_t*>(out) + dst) = u;
   }
 }
 
@@ -241,12 +239,10 @@ int samk_preprocess(const void* img, int in_fmt, void* out, int out_fmt, int B, 
   samhost::LaunchScope scope(samhost::KC_LAYOUT, stream, 0.0,
                              static_cast<double>(B) * 3 * (static_cast<double>(h) * w * (in_fmt == 3 ? 1 : in_fmt == 2 ? 4 : 2) +
                                                            static_cast<double>(S) * S * (out_fmt == 2 ? 4 : 2)));
-  const size_t total = static_cast<size_t>(B) * 3 * S * (S / 8);
-  int blocks = static_cast<int>((total + 255) / 256);
-  const int cap = samhost::sm_count() * 16;
-  if (blocks > cap) blocks = cap;
-  preprocess_kernel<<<blocks, 256, 0, stream>>>(img, in_fmt, out, out_fmt, B, h, w, S, mean[0], mean[1], mean[2], std[0],
-                                                std[1], std[2]);
+  SAM_REQUIRE(S <= 65535 && B * 3 <= 65535, "preprocess: canvas / batch too large for the launch grid");
+  dim3 grid((S / 8 + 127) / 128, S, B * 3);
+  preprocess_kernel<<<grid, 128, 0, stream>>>(img, in_fmt, out, out_fmt, B, h, w, S, mean[0], mean[1], mean[2], std[0],
+                                              std[1], std[2]);
   SAM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
