@@ -362,6 +362,37 @@ def test_vit_h_against_reference_goldens(dt, emb_tol, low_tol, iou_min, ln_fold)
     torch.cuda.empty_cache()
 
 
+def test_full_size_batch_is_independent_of_batch_position():
+    """BASELINE.json configs[1] at full size (ViT-H, 16 images, M = 65536 token rows): size-independent property --
+    an image's embedding and its mask logits do not depend on what else is in the batch or where it sits in it
+    (persistent tile schedulers, LayerNorm-folding statistics, window / global attention items, the batched decoder):
+    bit-identical to running the image alone."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from anyref_b200.grounding import GroundingPath
+    from anyref_b200.segment_anything import build_sam_vit_h
+
+    sam = build_sam_vit_h(None)
+    sam.load_state_dict(synthetic_state_dict(CONFIGS["vit_h"], seed=1234), strict=True)
+    sam = sam.cuda()
+    sam.image_encoder.set_operand_dtype(torch.float16)
+    path = GroundingPath(sam)
+    B = 16
+    x = synthetic_images(B, seed=3).to(torch.float16).cuda()
+    seg = synthetic_seg_embeddings(B, 2, seed=3).to(torch.float16).cuda()
+    sizes_in, sizes_out = [(1024, 683)] * B, [(640, 427)] * B
+    emb = sam.image_encoder(x)
+    full = path(x, [seg[b] for b in range(B)], sizes_in, sizes_out, multimask_output=True)
+    assert bool(torch.isfinite(emb.float()).all())
+    for b in (0, 7, 15):
+        assert torch.equal(sam.image_encoder(x[b:b + 1]), emb[b:b + 1]), f"embedding of image {b} depends on the batch"
+        alone = path(x[b:b + 1], [seg[b]], sizes_in[:1], sizes_out[:1], multimask_output=True)
+        assert alone[0].shape == (2, 3, 640, 427)
+        assert torch.equal(alone[0], full[b]), f"masks of image {b} depend on the batch"
+    del sam
+    torch.cuda.empty_cache()
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # SURVEY 8(f)-2 / 8(f)-3: point / box / mask prompts and Sam.preprocess (the callers either side of the path)
 # ---------------------------------------------------------------------------------------------------------------------
