@@ -142,6 +142,31 @@ def test_batched_decoder_with_promptless_images(tiny):
         assert (iou[sl].cpu() - iou_ref).abs().max().item() < 2e-5
 
 
+def test_batched_decoder_many_prompts_vs_oracle(tiny):
+    """40 prompts over 5 image embeddings in ONE decoder call (ragged: 13 / 0 / 1 / 20 / 6 prompts per image) against
+    the oracle's per-image calls: exercises the per-image layer-0 projections, the prompt -> image index in every
+    kernel and grids with more prompt CTAs than SMs / 16."""
+    sam, cfg, sd = tiny["sam"], tiny["cfg"], tiny["sd"]
+    g = torch.Generator().manual_seed(77)
+    embs = torch.randn(5, 256, 64, 64, generator=g)
+    counts = [13, 0, 1, 20, 6]
+    texts = [torch.randn(c, 1, 256, generator=g) for c in counts]
+    index = torch.repeat_interleave(torch.arange(5, dtype=torch.int32), torch.tensor(counts)).cuda()
+    text = torch.cat(texts).cuda()
+    sparse, dense = sam.prompt_encoder(points=None, boxes=None, masks=None, text_embeds=text)
+    low, iou = sam.mask_decoder.forward_batched(embs.cuda(), sam.prompt_encoder.get_dense_pe(), sparse, dense, index, True)
+    assert low.shape == (40, 3, 256, 256)
+    o = 0
+    for b, c in enumerate(counts):
+        if c == 0:
+            continue
+        s_ref, d_ref = O.prompt_encoder(sd, cfg, text_embeds=texts[b])
+        low_ref, iou_ref = O.mask_decoder(sd, cfg, embs[b:b + 1], tiny["pe"], s_ref, d_ref, True)
+        assert (low[o:o + c].cpu() - low_ref).abs().max().item() < 2e-5
+        assert (iou[o:o + c].cpu() - iou_ref).abs().max().item() < 2e-5
+        o += c
+
+
 def test_model_on_a_non_current_device(tiny):
     """The library launches on the CURRENT device; every module entry point makes its tensors' device current for the
     call (per-device kernel attributes, streams, workspaces), so a model on cuda:1 works while cuda:0 is current --
