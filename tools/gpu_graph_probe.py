@@ -13,11 +13,11 @@ dev = torch.device("cuda", 0)
 sam = build_sam_vit_h(None)
 sam.load_state_dict(synthetic_state_dict("vit_h", seed=1234), strict=True)
 sam = sam.to(dev)
-sam.image_encoder.set_operand_dtype(torch.bfloat16)
+sam.image_encoder.set_operand_dtype(torch.float16)
 path = GroundingPath(sam)
-B = 16
-x = synthetic_images(B, seed=0).to(torch.bfloat16).to(dev)
-seg = synthetic_seg_embeddings(B, 1, seed=0).to(torch.bfloat16).to(dev)
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+x = synthetic_images(B, seed=0).to(torch.float16).to(dev)
+seg = synthetic_seg_embeddings(B, 1, seed=0).to(torch.float16).to(dev)
 segs = [seg[b] for b in range(B)]
 sizes = [(1024, 1024)] * B
 
@@ -26,7 +26,7 @@ def step():
     return path(x, segs, sizes, sizes)
 
 
-def timeit(fn, n=10):
+def timeit(fn, n=30):
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
