@@ -1,9 +1,5 @@
-// Global (64x64 = 4096 token) attention of the 4 non-windowed SAM ViT-H blocks, decoupled-pipeline version ("v3").
-// Same contract as attn_global.cu (replaces image_encoder.py:235-257 + :354-392 for blocks 7/15/23/31).
-//
-// v2 (attn_global2.cu) ping-pongs two 128-query tiles on one S buffer each, so a tile's softmax warpgroup idles while
-// the tensor core produces its next S (P.V of block j, then Q.K^T of block j+1, plus two mbarrier hand-offs): ncu
-// showed the softmax warps parked on that wait for a third of the kernel.  v3 removes the dependency:
+// Global (64x64 = 4096 token) attention of the 4 non-windowed SAM ViT-H blocks (replaces image_encoder.py:235-257 +
+// :354-392 for blocks 7/15/23/31), decoupled pipeline:
 //   * key blocks are ONE image row (64 keys), S is double-buffered in TMEM (2 x 64 columns per tile) and P is
 //     double-buffered in shared memory, so Q.K^T of block j+1 is issued BEFORE the softmax of block j finishes and the
 //     softmax warps find their next S already waiting;

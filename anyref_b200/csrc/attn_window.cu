@@ -2,9 +2,8 @@
 // Replaces image_encoder.py:235-257 (Attention.forward), :263-318 (window partition / un-partition) and :354-392
 // (add_decomposed_rel_pos) for the 14x14 windowed blocks.
 //
-// What v3 (attn_window3.cu) could not do: its P tiles took 104 KB of shared memory, so Q / K / V were single-buffered
-// and the two query tiles of an item ran in lock step (timeline trace: tensor pipe idle under both softmaxes, both
-// softmaxes idle under the MMAs).  Here
+// An earlier version kept the probabilities in shared memory (104 KB), so Q / K / V were single-buffered and the two
+// query tiles of an item waited for each other at every hand-off.  Here
 //   * P never touches shared memory: each softmax thread packs its row's probabilities and writes them with tcgen05.st
 //     IN PLACE over the S columns it has already consumed; O = P.V is a tcgen05.mma with the A operand in tensor memory
 //     ("ts" form, layout pinned by tools/gpu_probe_ts.py) and V as five 16-wide MN-major SWIZZLE_32B chunks, so one
