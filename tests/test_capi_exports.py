@@ -61,6 +61,25 @@ def test_sizes_and_errors_without_gpu(lib):
     assert rc != 0 and b"fmt" in L.sam_last_error()
     rc = L.sam_postprocess_masks(None, 2, 0, 256, 1024, 1024, 1024, 1024, 1024, None, None, 0.0, None)
     assert rc != 0 and b"postprocess" in L.sam_last_error()
+    # mask decoder: sizes grow with the problem, NULL arguments and unsupported shapes are refused before any launch
+    small = L.sam_decoder_workspace_bytes(ctypes.byref(dec), 1, 1, 1)
+    assert small > 4096 * 256 * 4 * 3
+    assert L.sam_decoder_workspace_bytes(ctypes.byref(dec), 1, 16, 1) > 8 * small // 2
+    assert L.sam_decoder_workspace_bytes(ctypes.byref(dec), 16, 4, 1) >= L.sam_decoder_workspace_bytes(ctypes.byref(dec), 4, 4, 1)
+    derived = L.sam_decoder_derived_bytes(ctypes.byref(dec))
+    assert derived > 2 * (2 * 4096 * 128 * 4) and derived % 256 == 0      # the pe.W^T tables alone are 2 MB each
+    rc = L.sam_decoder_prepare(ctypes.byref(dec), None, None, 2, None, None)
+    assert rc != 0 and b"NULL" in L.sam_last_error()
+    rc = L.sam_decoder_forward(ctypes.byref(dec), None, None, None, 2, 1, None, None, 2, 1, 1, None, None, 2, None, None, 2,
+                               None, 0, None)
+    assert rc != 0 and b"NULL" in L.sam_last_error()
+    rc = L.sam_resize_u8(None, 10, 10, 3, None, None, 20, 20, None, None, 0, None, None, 0, None)
+    assert rc != 0 and b"resize" in L.sam_last_error()
+    bad = _lib.SamDecoderShape(C=192, heads=8, depth=2, mlp_dim=2048, num_mask_tokens=4, iou_hidden=256, grid=64)
+    buf = ctypes.create_string_buffer(1 << 12)                       # any non-NULL host pointer: refused before use
+    ptr = ctypes.cast(buf, ctypes.c_void_p)
+    rc = L.sam_decoder_prepare(ctypes.byref(bad), ptr, ptr, 2, ptr, None)
+    assert rc != 0 and b"transformer_dim" in L.sam_last_error()
 
 
 def test_product_path_has_no_cpu_fallback():
