@@ -375,10 +375,16 @@ __host__ __device__ __forceinline__ uint32_t make_idesc(uint32_t fmt, uint32_t M
 // ----------------------------------------------------------------------------------------------
 // Operand-format helpers: fmt 0 = fp16, 1 = bf16 (matches the idesc encoding)
 // ----------------------------------------------------------------------------------------------
+// fp16 stores saturate (cvt.rn.satfinite: one F2FP either way): an activation beyond +-65504 becomes the largest finite
+// half instead of inf, which the next GEMM would turn into NaN for the whole row.  In-range values are unaffected.
+__device__ __forceinline__ uint32_t pack2_f16_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
 __device__ __forceinline__ uint32_t pack2(float a, float b, int fmt) {
   if (fmt == 0) {
-    __half2 h = __floats2half2_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&h);
+    return pack2_f16_sat(a, b);
   } else {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
@@ -387,8 +393,7 @@ __device__ __forceinline__ uint32_t pack2(float a, float b, int fmt) {
 template <int FMT>
 __device__ __forceinline__ uint32_t pack2t(float a, float b) {
   if (FMT == 0) {
-    __half2 h = __floats2half2_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&h);
+    return pack2_f16_sat(a, b);
   } else {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
@@ -410,8 +415,9 @@ __device__ __forceinline__ float unpack1(uint16_t u, int fmt) {
 }
 __device__ __forceinline__ uint16_t pack1(float a, int fmt) {
   if (fmt == 0) {
-    __half h = __float2half_rn(a);
-    return *reinterpret_cast<uint16_t*>(&h);
+    uint16_t h;
+    asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(a));
+    return h;
   } else {
     __nv_bfloat16 h = __float2bfloat16_rn(a);
     return *reinterpret_cast<uint16_t*>(&h);

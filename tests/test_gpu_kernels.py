@@ -117,6 +117,22 @@ def test_gemm_ln_consumer_matches_layernorm_then_linear(ops, dt, tol, M, N, K, a
     assert rel_fro(got, want.float()) < 1.5 * rel_fro(plain, want.float()) + 1e-4
 
 
+def test_fp16_stores_saturate_instead_of_overflowing(ops):
+    """fp16 operand mode: a result beyond +-65504 is stored as the largest finite half, not inf (the reference's own fp16
+    path would carry the inf into NaNs); in-range values are untouched (every other fp16 test is bit-sensitive to that)."""
+    M, K, N = 256, 64, 256
+    a = torch.full((M, K), 64.0, device=DEV, dtype=torch.float16)
+    w = torch.full((N, K), 32.0, device=DEV, dtype=torch.float16)
+    w[N // 2:] = -32.0
+    out = ops.gemm(a, w, out_dtype=torch.float16)            # +-131072 in fp32
+    assert bool(torch.isfinite(out.float()).all())
+    assert torch.equal(out[:, : N // 2].float(), torch.full((M, N // 2), 65504.0, device=DEV))
+    assert torch.equal(out[:, N // 2:].float(), torch.full((M, N // 2), -65504.0, device=DEV))
+    x = torch.full((128, 1280), 1e6, device=DEV)
+    xb, _ = ops.cast_stats(x, torch.float16)
+    assert torch.equal(xb.float(), torch.full_like(x, 65504.0))
+
+
 def _stats_to_mean_var(stats, C):
     """Chan combination of the per-slice (mean, M2) statistics [M, C/128, 2] -> (mean [M], biased variance [M])."""
     mean_i, m2_i = stats[..., 0].double(), stats[..., 1].double()
