@@ -11,7 +11,7 @@
 // Data layout: tokens ("queries") [n, T, C] and image tokens ("keys") [n, HW, C] are fp32, token-major.  Weights come
 // as one fp32 blob in state_dict order (see DecoderWeights below and anyref_b200/segment_anything/_pack.py).
 //
-// Launch plan (20 launches for depth 2; round 1: 45+).  Token side = one CTA per prompt holding its tokens in shared
+// Launch plan (22 launches for depth 2; round 1: 45+).  Token side = one CTA per prompt holding its tokens in shared
 // memory; image side = merged tcgen05 GEMMs over split-bf16 operands:
 //   keys0 (+split)                       | token_first: assemble, self-attn, norm1, t2i q-proj
 //   per layer l:  GEMM  keys.[Wk_t2i | Wv_t2i | Wq_i2t]^T   (one A operand for three projections: (keys + pe).W^T =
@@ -20,7 +20,7 @@
 //                 -> token_tail (norm3, i2t k/v proj, NEXT layer's self-attn block or the final q-proj)
 //                 attn_i2t (warp per pixel, writes the split A operand) -> GEMM out_proj -> ln_split (norm4 + split)
 //   final:        GEMM  keys.[Wk_final | Wv_final | W_upscale0]^T -> attn_t2i -> hyper (out-proj, norm_final,
-//                 hypernetwork MLPs, IoU head) -> upscale tail (LN2d, GELU, ConvT, GELU, mask product)
+//                 hypernetwork MLPs, IoU head) -> up_prologue (LN2d, GELU, split) -> GEMM ConvT1 (+ GELU) -> up_hyper_dot
 #include <math.h>
 
 #include "host_common.h"
@@ -872,79 +872,89 @@ dec_hyper_kernel(const HyperArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Upscaling tail (mask_decoder.py:53-63, :157-158, :171-174).  The first ConvTranspose2d(k=2,s=2) is a per-pixel
-// linear (dec_linear with the weight rearranged to [(dy,dx,oc), ic]); this kernel does, per (pixel, dy, dx):
-// LayerNorm2d(64) -> GELU -> second ConvTranspose2d(64->32, k=2,s=2) -> GELU -> dot with the 4 hypernetwork vectors,
-// writing the four 256x256 mask logits directly (the [n,32,256,256] tensor is never materialised).
-// U [n*HW, ldu >= 4*C1] fp32 (a column block of the final merged GEMM's output);  w1r [4 (ey,ex)][C2][C1];  masks [n, nm, 4g, 4g] in out_fmt.   C1 = 64, C2 = 32, nm <= 4.
+// Upscaling tail (mask_decoder.py:53-63, :157-158, :171-174).  The first ConvTranspose2d(k=2,s=2) is a per-pixel linear
+// and part of the final merged GEMM (U = its output, one row of 4 x 64 values per pixel).  The rest runs per
+// (pixel, dy, dx) row of 64 channels:
+//   up_prologue : LayerNorm2d(64) -> GELU -> split-bf16 A operand [hi | hi | lo] of the second ConvTranspose2d
+//   tcgen05 GEMM: [rows, 3*64] x W1r3[128 = (ey,ex,oc), 3*64]^T + bias, GELU in the epilogue            (gemm2.cu)
+//   up_hyper_dot: mask logits = sum_oc hyper[p, k, oc] * z[(ey,ex), oc], written straight to the 256x256 masks
+// (the [n,32,256,256] tensor is never materialised).  Round 1 / early round 2 did all of it on fp32 CUDA cores in one
+// kernel: 4.3 GFLOP at 17 TFLOP/s = 251 us for 16 prompts, the largest kernel of the decoder.
+// U [n*HW, ldu >= 4*64] fp32;  a3 [n*HW*4, 192] bf16;  z [n*HW*4, 128] fp32;  masks [n, nm, 4g, 4g] in out_fmt.
 // ---------------------------------------------------------------------------------------------------------------
+constexpr int UC1 = 64, UC2 = 32;
+
+// sixteen threads per (pixel, sub) row, one float4 of channels each: a warp reads 512 contiguous bytes per instruction
+// and writes three 256-byte runs.   grid rows4 * 16 / 256, block 256
 __global__ void __launch_bounds__(256)
-dec_upscale_tail_kernel(const float* __restrict__ U, int ldu, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
-                        const float* __restrict__ w1r, const float* __restrict__ b1, const float* __restrict__ hyper,
-                        void* __restrict__ masks, int out_fmt, int g, int nm) {
-  constexpr int C1 = 64, C2 = 32;
-  __shared__ __align__(16) float ws[4 * C2 * C1];
-  __shared__ float bs[C2], lw[C1], lb[C1], hy[4 * C2];
+dec_up_prologue_kernel(const float* __restrict__ U, int ldu, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                       uint16_t* __restrict__ a3, size_t rows4) {
+  const size_t t = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x;
+  const size_t row = t >> 4;          // (pixel, sub); rows4 * 16 is a multiple of 256: no partial blocks
+  const int q = static_cast<int>(t & 15);
+  float4 v = *reinterpret_cast<const float4*>(U + (row >> 2) * ldu + (row & 3) * UC1 + 4 * q);
+  float s = (v.x + v.y) + (v.z + v.w);
+#pragma unroll
+  for (int o = 1; o < 16; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / UC1;
+  v.x -= mean; v.y -= mean; v.z -= mean; v.w -= mean;
+  float qq = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w)));
+#pragma unroll
+  for (int o = 1; o < 16; o <<= 1) qq += __shfl_xor_sync(0xffffffffu, qq, o);
+  const float rstd = 1.0f / sqrtf(qq / UC1 + 1e-6f);
+  const float4 g4 = __ldg(reinterpret_cast<const float4*>(ln_w) + q), b4 = __ldg(reinterpret_cast<const float4*>(ln_b) + q);
+  v.x = gelu_erf(v.x * rstd * g4.x + b4.x);
+  v.y = gelu_erf(v.y * rstd * g4.y + b4.y);
+  v.z = gelu_erf(v.z * rstd * g4.z + b4.z);
+  v.w = gelu_erf(v.w * rstd * g4.w + b4.w);
+  uint2 H, L;
+  split4(v, H, L);
+  uint16_t* o = a3 + row * (3 * UC1) + 4 * q;
+  *reinterpret_cast<uint2*>(o) = H;
+  *reinterpret_cast<uint2*>(o + UC1) = H;
+  *reinterpret_cast<uint2*>(o + 2 * UC1) = L;
+}
+
+// one thread per (row, (ey,ex)): 32 GELU'd channels of z dotted with the nm hypernetwork vectors of the prompt.  The
+// block's 64 rows of z (32 KB, contiguous) are staged through shared memory so the global reads are coalesced; each
+// 32-channel run is padded to 33 floats, which makes both the staging writes and the per-thread reads conflict-free.
+// grid rows4 / 64, block 256 (all rows of a block belong to one prompt: 4 * HW % 64 == 0)
+__global__ void __launch_bounds__(256)
+dec_up_hyper_dot_kernel(const float* __restrict__ z, const float* __restrict__ hyper, void* __restrict__ masks, int out_fmt,
+                        int g, int nm) {
+  __shared__ float zs[256 * 33];
+  __shared__ float hy[4 * UC2];
+  const int tid = threadIdx.x;
+  const size_t row0 = static_cast<size_t>(blockIdx.x) * 64;
   const int HW = g * g;
-  const size_t gt = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x;  // (p, pixel, sub)
-  const int p = static_cast<int>(gt / (static_cast<size_t>(HW) * 4));
-  for (int i = threadIdx.x; i < 4 * C2 * C1; i += 256) ws[i] = w1r[i];
-  if (threadIdx.x < C2) bs[threadIdx.x] = b1[threadIdx.x];
-  if (threadIdx.x < C1) {
-    lw[threadIdx.x] = ln_w[threadIdx.x];
-    lb[threadIdx.x] = ln_b[threadIdx.x];
+  const int p = static_cast<int>(row0 / (static_cast<size_t>(HW) * 4));
+  if (tid < 4 * UC2) hy[tid] = tid < nm * UC2 ? hyper[static_cast<size_t>(p) * nm * UC2 + tid] : 0.f;
+  const float4* z4 = reinterpret_cast<const float4*>(z + row0 * (4 * UC2));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int f = i * 256 + tid;              // float4 index in the block's tile: run = f / 8, offset 4 * (f % 8)
+    const float4 v = z4[f];
+    float* d = zs + (f >> 3) * 33 + 4 * (f & 7);
+    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
   }
-  if (threadIdx.x < nm * C2) hy[threadIdx.x] = hyper[static_cast<size_t>(p) * nm * C2 + threadIdx.x];
   __syncthreads();
-  const int sub = gt & 3;
-  const int pix = (gt >> 2) % HW;
+  const float* mine = zs + tid * 33;          // run tid = (local row, s2)
+  float m[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < UC2; ++i) {
+    const float v = mine[i];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) m[k] = fmaf(hy[k * UC2 + i], v, m[k]);
+  }
+  const size_t row = row0 + (tid >> 2);
+  const int s2 = tid & 3;
+  const int sub = static_cast<int>(row & 3);
+  const int pix = static_cast<int>((row >> 2) % HW);
   const int y = pix / g, x = pix % g;
-  float a[C1];
-  {
-    const float4* u4 = reinterpret_cast<const float4*>(U + (gt >> 2) * ldu + sub * C1);
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < C1 / 4; ++i) {
-      const float4 t = u4[i];
-      a[4 * i] = t.x; a[4 * i + 1] = t.y; a[4 * i + 2] = t.z; a[4 * i + 3] = t.w;
-      s += (t.x + t.y) + (t.z + t.w);
-    }
-    const float mean = s / C1;
-    float q = 0.f;
-#pragma unroll
-    for (int i = 0; i < C1; ++i) {
-      a[i] -= mean;
-      q = fmaf(a[i], a[i], q);
-    }
-    const float rstd = 1.0f / sqrtf(q / C1 + 1e-6f);
-#pragma unroll
-    for (int i = 0; i < C1; ++i) a[i] = gelu_erf(a[i] * rstd * lw[i] + lb[i]);
-  }
   const int G4 = 4 * g;
-  const int Y0 = 4 * y + 2 * (sub >> 1), X0 = 4 * x + 2 * (sub & 1);
-#pragma unroll 1
-  for (int s2 = 0; s2 < 4; ++s2) {
-    float m[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 2
-    for (int oc = 0; oc < C2; ++oc) {
-      const float4* w4 = reinterpret_cast<const float4*>(ws + (s2 * C2 + oc) * C1);
-      float z0 = bs[oc], z1 = 0.f;
-#pragma unroll
-      for (int i = 0; i < C1 / 4; i += 2) {
-        const float4 w0 = w4[i], w1 = w4[i + 1];
-        z0 = fmaf(a[4 * i], w0.x, z0); z0 = fmaf(a[4 * i + 1], w0.y, z0);
-        z0 = fmaf(a[4 * i + 2], w0.z, z0); z0 = fmaf(a[4 * i + 3], w0.w, z0);
-        z1 = fmaf(a[4 * i + 4], w1.x, z1); z1 = fmaf(a[4 * i + 5], w1.y, z1);
-        z1 = fmaf(a[4 * i + 6], w1.z, z1); z1 = fmaf(a[4 * i + 7], w1.w, z1);
-      }
-      const float gl = gelu_erf(z0 + z1);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) m[k] = fmaf(hy[k * C2 + oc], gl, m[k]);
-    }
-    const int Y = Y0 + (s2 >> 1), X = X0 + (s2 & 1);
-    for (int k = 0; k < nm; ++k)
-      store_any(masks, out_fmt, ((static_cast<size_t>(p) * nm + k) * G4 + Y) * G4 + X, m[k]);
-  }
+  const int Y = 4 * y + 2 * (sub >> 1) + (s2 >> 1), X = 4 * x + 2 * (sub & 1) + (s2 & 1);
+  for (int k = 0; k < nm; ++k)
+    store_any(masks, out_fmt, ((static_cast<size_t>(p) * nm + k) * G4 + Y) * G4 + X, m[k]);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1058,6 +1068,8 @@ struct DerivedW {
     const float *ikv, *ikvb;           // i2t k | v [C, 2 Ci] and their biases [2 Ci]
   } tok[8];
   const float *fq, *fo;                // final attention q [C, Ci], out [Ci, C]
+  const uint16_t* up1;                 // second ConvTranspose2d as a GEMM weight [(ey,ex,oc) = 128, 3 * 64]
+  const float* b_up1;                  // its bias tiled over the 4 (ey,ex) positions [128]
   size_t total;                        // bytes
 };
 void carve_derived(const SamDecoderShape& s, const void* base, DerivedW* d) {
@@ -1088,6 +1100,8 @@ void carve_derived(const SamDecoderShape& s, const void* base, DerivedW* d) {
   d->fq = t32(C * Ci);
   d->fo = t32(Ci * C);
   d->pe_t = t32(HW * C);
+  d->up1 = t16(static_cast<size_t>(4 * (C / 8)) * 3 * (C / 4));
+  d->b_up1 = t32(4 * (C / 8));
   d->total = off;
 }
 
@@ -1186,6 +1200,8 @@ int samk_decoder_prepare(const SamDecoderShape& s, const float* blob, const void
   if (int rc = pe_proj(w.final_attn.kw, w.final_attn.kb, d.rk[s.depth])) return rc;
   transpose(w.final_attn.qw, d.fq, Ci, C, Ci, 0);
   transpose(w.final_attn.ow, d.fo, C, Ci, C, 0);
+  split(w.up1w, d.up1, 0, 4 * (C / 8), C / 4);                       // [(ey,ex), oc, ic] is already [128, 64] row-major
+  for (int e = 0; e < 4; ++e) fill(d.b_up1, e * (C / 8), w.up1b, C / 8);
   SAM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1403,11 +1419,29 @@ int samk_decoder_forward(const SamDecoderShape& s, const float* blob, const void
     SAM_CHECK_CUDA(cudaGetLastError());
   }
   {
-    const size_t MK = static_cast<size_t>(n) * HW;
-    samhost::LaunchScope scope(samhost::KC_DECODER, st, 2.0 * MK * 4 * (4.0 * (C / 8) * (C / 4) + 4.0 * nm * (C / 8)));
-    dec_upscale_tail_kernel<<<static_cast<unsigned>(MK * 4 / 256), 256, 0, st>>>(
-        ws.kvq + 2 * Ci, 2 * Ci + C, w.upln_w, w.upln_b, w.up1w, w.up1b, ws.hyper, masks, out_fmt, g, nm);
-    SAM_CHECK_CUDA(cudaGetLastError());
+    // upscaling tail: prologue -> tensor-core GEMM (+ GELU) -> hypernetwork product.  a3 is free again (the final merged
+    // GEMM has consumed it); z = keys | delta, which are adjacent in the workspace and dead by now
+    const size_t rows4 = static_cast<size_t>(n) * HW * 4;
+    SAM_REQUIRE(C / 4 == UC1 && C / 8 == UC2 && HW % 16 == 0, "mask decoder: upscaling widths / grid");
+    SAM_REQUIRE(reinterpret_cast<uint8_t*>(ws.keys) + static_cast<size_t>(n) * HW * C * 4 == reinterpret_cast<uint8_t*>(ws.delta),
+                "mask decoder: workspace layout (keys | delta must be adjacent)");
+    float* z = ws.keys;
+    {
+      samhost::LaunchScope scope(samhost::KC_DECODER, st, 0.0, static_cast<double>(rows4) * UC1 * (4.0 + 6.0));
+      dec_up_prologue_kernel<<<static_cast<unsigned>(rows4 * 16 / 256), 256, 0, st>>>(ws.kvq + 2 * Ci, 2 * Ci + C, w.upln_w, w.upln_b,
+                                                                                  ws.a3, rows4);
+      SAM_CHECK_CUDA(cudaGetLastError());
+    }
+    {
+      samhost::ClassOverride as_decoder(samhost::KC_DECODER);
+      GemmEpilogue ep{z, 4 * UC2, SAM_F32, dw.b_up1, 1, nullptr, 0, 0};
+      if (int rc = samk_gemm(ws.a3, 3 * UC1, dw.up1, 3 * UC1, static_cast<int>(rows4), 4 * UC2, 3 * UC1, SAM_BF16, ep, st)) return rc;
+    }
+    {
+      samhost::LaunchScope scope(samhost::KC_DECODER, st, 2.0 * rows4 * 4 * UC2 * nm, static_cast<double>(rows4) * 4 * UC2 * 4.0);
+      dec_up_hyper_dot_kernel<<<static_cast<unsigned>(rows4 / 64), 256, 0, st>>>(z, ws.hyper, masks, out_fmt, g, nm);
+      SAM_CHECK_CUDA(cudaGetLastError());
+    }
   }
   return 0;
 }
