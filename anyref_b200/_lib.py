@@ -64,6 +64,16 @@ _PROTOS = {
     "sam_decoder_prepare": [_DEC_P, c_void_p, c_void_p, c_int, c_void_p, c_void_p],
     "sam_decoder_forward": [_DEC_P, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
                             c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p],
+    "sam_decoder_train_workspace_bytes": [_DEC_P, c_int, c_int],
+    "sam_decoder_train_forward": [_DEC_P, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
+                                  c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t, C.POINTER(c_void_p), c_void_p],
+    "sam_decoder_backward": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "sam_decoder_tape_free": [c_void_p],
+    "sam_linear_f32_scratch_bytes": [c_int, c_int, c_int],
+    "sam_linear_f32_forward": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "sam_linear_f32_backward": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                c_void_p, c_size_t, c_void_p],
+    "sam_postprocess_masks_backward": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
     "sam_postprocess_masks": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                               c_float, c_void_p],
     "sam_launch_count": [],
@@ -89,7 +99,8 @@ _PROTOS = {
 }
 _RESTYPES = {"sam_last_error": c_char_p, "sam_encoder_w16_elems": c_size_t, "sam_encoder_w32_elems": c_size_t,
              "sam_encoder_workspace_bytes": c_size_t, "sam_decoder_weight_elems": c_size_t,
-             "sam_decoder_workspace_bytes": c_size_t, "sam_decoder_derived_bytes": c_size_t, "sam_prompt_mask_blob_elems": c_size_t, "sam_launch_count": C.c_longlong, "sam_profile_enable": None,
+             "sam_decoder_workspace_bytes": c_size_t, "sam_decoder_derived_bytes": c_size_t,
+             "sam_decoder_train_workspace_bytes": c_size_t, "sam_linear_f32_scratch_bytes": c_size_t, "sam_decoder_tape_free": None, "sam_prompt_mask_blob_elems": c_size_t, "sam_launch_count": C.c_longlong, "sam_profile_enable": None,
              "sam_profile_reset": None, "sam_profile_get": None}
 
 

@@ -9,7 +9,7 @@ static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
 extern "C" {
 
 const char* sam_last_error(void) { return samhost::last_error(); }
-int sam_abi_version(void) { return 3; }
+int sam_abi_version(void) { return 4; }
 
 int sam_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, int K, int fmt, void* out, int ldo,
              int out_fmt, const float* bias, int act, const float* res, int ldr, int res_mod, void* stream) {
@@ -118,6 +118,33 @@ int sam_decoder_forward(const SamDecoderShape* s, const float* weights, const vo
   if (k > 0 && !sparse) return samhost::set_error(1, "sam_decoder_forward: sparse embeddings missing");
   return samk_decoder_forward(*s, weights, derived, image_embeddings, emb_fmt, n_images, img_index, sparse, sparse_fmt, n, k,
                               dense_vec, dense_full, dense_fmt, masks, iou, out_fmt, workspace, workspace_bytes, S(stream));
+}
+size_t sam_decoder_train_workspace_bytes(const SamDecoderShape* s, int n, int k) {
+  return s ? samk_decoder_train_workspace_bytes(*s, n, k) : 0;
+}
+int sam_decoder_train_forward(const SamDecoderShape* s, const float* weights, const void* image_embeddings, int emb_fmt, int n_images,
+                              const int* img_index, const float* sparse, int n, int k, const void* dense_vec, const void* dense_full,
+                              int dense_fmt, const void* image_pe, int pe_fmt, float* masks, float* iou, void* workspace,
+                              size_t workspace_bytes, void** tape, void* stream) {
+  if (!s || !tape) return samhost::set_error(1, "sam_decoder_train_forward: NULL argument");
+  return samk_decoder_train_forward(*s, weights, image_embeddings, emb_fmt, n_images, img_index, sparse, n, k, dense_vec, dense_full,
+                                    dense_fmt, image_pe, pe_fmt, masks, iou, workspace, workspace_bytes, tape, S(stream));
+}
+int sam_decoder_backward(void* tape, const float* d_masks, const float* d_iou, float* d_weights, float* d_sparse, void* stream) {
+  return samk_decoder_backward(tape, d_masks, d_iou, d_weights, d_sparse, S(stream));
+}
+void sam_decoder_tape_free(void* tape) { samk_decoder_tape_free(tape); }
+size_t sam_linear_f32_scratch_bytes(int M, int N, int K) { return samk_linear_f32_scratch_bytes(M, N, K); }
+int sam_linear_f32_forward(const float* X, const float* W, const float* b, float* Y, int M, int N, int K, int relu, void* stream) {
+  return samk_linear_f32_forward(X, W, b, Y, M, N, K, relu, S(stream));
+}
+int sam_linear_f32_backward(float* dY, const float* relu_y, const float* X, const float* W, float* dX, float* dW, float* db, int M,
+                            int N, int K, void* scratch, size_t scratch_bytes, void* stream) {
+  return samk_linear_f32_backward(dY, relu_y, X, W, dX, dW, db, M, N, K, scratch, scratch_bytes, S(stream));
+}
+int sam_postprocess_masks_backward(const float* d_logits, int num_masks, int L, int Sz, int h_in, int w_in, int H, int W, float* tmp,
+                                   float* d_low, void* stream) {
+  return samk_postprocess_backward(d_logits, num_masks, L, Sz, h_in, w_in, H, W, tmp, d_low, S(stream));
 }
 int sam_postprocess_masks(const void* low, int low_fmt, int num_masks, int L, int Sz, int h_in, int w_in, int H, int W,
                           float* logits, unsigned char* binary, float threshold, void* stream) {

@@ -1,0 +1,1254 @@
+// Training path of the mask decoder: forward that keeps its intermediates + backward.
+//
+// AnyRef fine-tunes SAM's mask decoder with the image encoder and the prompt encoder frozen (model/anyref.py:108-113);
+// the loss reaches it through `mask_decoder(...)` -> `postprocess_masks` (model/anyref.py:406-450).  The gradients this
+// file produces are therefore those of every mask_decoder.* parameter and of `sparse_prompt_embeddings` (which carries
+// them on to text_hidden_fcs and the LLM); image embeddings, the dense prompt embedding and image_pe get none.
+//
+// Design.  The inference decoder (decoder.cu) fuses whole sub-blocks into single kernels and keeps nothing; a backward
+// needs the intermediates.  This path is a separate, deliberately plain fp32 composition: a small set of kernels
+// (one strided / batched / split-K SGEMM, LayerNorm, softmax, GELU / ReLU, column sums, layout gathers), each with its
+// adjoint, composed on the host exactly in the order of the reference modules
+//   MaskDecoder.predict_masks            modeling/mask_decoder.py:116-179
+//   TwoWayTransformer.forward            modeling/transformer.py:62-106
+//   TwoWayAttentionBlock.forward         modeling/transformer.py:151-182
+//   Attention.forward                    modeling/transformer.py:220-242
+// Every forward op pushes the closure of its adjoint on a tape; sam_decoder_backward runs the tape in reverse.  Every
+// adjoint ACCUMULATES into the gradient buffers of its inputs (zeroed once), so fan-out needs no special handling.
+// All arithmetic is fp32 FMA with fixed reduction orders (split-K partials are reduced in index order): the
+// gradients are deterministic.  Throughput is that of a plain SIMT SGEMM; moving the image-side
+// products onto the split-bf16 tcgen05 GEMM of the inference path is the next step.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <algorithm>
+#include <functional>
+#include <vector>
+
+#include "host_common.h"
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace {
+
+typedef long long i64;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float load_any(const void* p, int fmt, size_t i) {
+  if (fmt == 2) return static_cast<const float*>(p)[i];
+  return ptx::unpack1(static_cast<const uint16_t*>(p)[i], fmt);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// SGEMM:  C[b] (+)= alpha * A[b] . B[b] (+ bias),  A(i,k) = A[i*ars + k*acs], B(k,j) = B[k*brs + j*bcs], C(i,j) = C[i*crs + j]
+// (any operand may be a transposed or strided view), two-level batch (z / nb2, z % nb2) with independent strides, and
+// split-K into a partial buffer [split][batch][M][N] that splitk_reduce_kernel folds in index order.
+// 64 x 64 x 16 tiles, 256 threads, 4 x 4 outputs per thread.
+// ---------------------------------------------------------------------------------------------------------------
+struct Gemm {
+  const float* A;
+  const float* B;
+  float* C;
+  const float* bias;   // [bias_mod] or null: added as bias[j % bias_mod]
+  int M, N, K;
+  i64 ars, acs, brs, bcs, crs;
+  int nbatch, nb2;
+  i64 a_b1, a_b2, b_b1, b_b2, c_b1, c_b2;
+  int bias_mod;
+  float alpha;
+  int accumulate;
+  int splits, kchunk;
+  float* partial;
+};
+
+constexpr int GT = 64, GK = 16;
+
+__global__ void __launch_bounds__(256) sgemm_kernel(const Gemm g) {
+  __shared__ __align__(16) float As[GK][GT + 4];
+  __shared__ __align__(16) float Bs[GK][GT + 4];
+  const int z = blockIdx.z;
+  const int batch = z / g.splits, split = z - batch * g.splits;
+  const int b1 = batch / g.nb2, b2 = batch - b1 * g.nb2;
+  const float* __restrict__ A = g.A + b1 * g.a_b1 + b2 * g.a_b2;
+  const float* __restrict__ B = g.B + b1 * g.b_b1 + b2 * g.b_b2;
+  const int k0 = split * g.kchunk;
+  const int k1 = min(g.K, k0 + g.kchunk);
+  const int m0 = blockIdx.x * GT, n0 = blockIdx.y * GT;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  // consecutive threads walk whichever index of the operand is contiguous in memory
+  const bool a_kfast = g.acs == 1 && g.ars != 1;
+  const bool b_kfast = g.brs == 1 && g.bcs != 1;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int kk = k0; kk < k1; kk += GK) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int idx = tid + r * 256;
+      int i, k;
+      if (a_kfast) { k = idx & (GK - 1); i = idx >> 4; } else { i = idx & (GT - 1); k = idx >> 6; }
+      int gi = m0 + i, gk = kk + k;
+      As[k][i] = (gi < g.M && gk < k1) ? A[gi * g.ars + gk * g.acs] : 0.f;
+      int j;
+      if (b_kfast) { k = idx & (GK - 1); j = idx >> 4; } else { j = idx & (GT - 1); k = idx >> 6; }
+      const int gj = n0 + j;
+      gk = kk + k;
+      Bs[k][j] = (gj < g.N && gk < k1) ? B[gk * g.brs + gj * g.bcs] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < GK; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  if (g.splits > 1) {
+    float* P = g.partial + (static_cast<i64>(split) * g.nbatch + batch) * g.M * g.N;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int gi = m0 + ty * 4 + i;
+      if (gi >= g.M) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int gj = n0 + tx * 4 + j;
+        if (gj < g.N) P[static_cast<i64>(gi) * g.N + gj] = acc[i][j];
+      }
+    }
+    return;
+  }
+  float* __restrict__ Cb = g.C + b1 * g.c_b1 + b2 * g.c_b2;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gi = m0 + ty * 4 + i;
+    if (gi >= g.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gj = n0 + tx * 4 + j;
+      if (gj >= g.N) continue;
+      float v = g.alpha * acc[i][j];
+      if (g.bias) v += g.bias[gj % g.bias_mod];
+      float* c = Cb + gi * g.crs + gj;
+      *c = g.accumulate ? *c + v : v;
+    }
+  }
+}
+
+__global__ void splitk_reduce_kernel(const Gemm g) {
+  const i64 per = static_cast<i64>(g.M) * g.N;
+  const i64 total = per * g.nbatch;
+  for (i64 t = static_cast<i64>(blockIdx.x) * blockDim.x + threadIdx.x; t < total; t += static_cast<i64>(gridDim.x) * blockDim.x) {
+    const int batch = static_cast<int>(t / per);
+    const i64 r = t - batch * per;
+    const int i = static_cast<int>(r / g.N), j = static_cast<int>(r - static_cast<i64>(i) * g.N);
+    float s = 0.f;
+    for (int sp = 0; sp < g.splits; ++sp) s += g.partial[(static_cast<i64>(sp) * g.nbatch + batch) * per + r];
+    float v = g.alpha * s;
+    if (g.bias) v += g.bias[j % g.bias_mod];
+    const int b1 = batch / g.nb2, b2 = batch - b1 * g.nb2;
+    float* c = g.C + b1 * g.c_b1 + b2 * g.c_b2 + i * g.crs + j;
+    *c = g.accumulate ? *c + v : v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Column sums:  out[j % mod] (+)= sum_r X[r, j]   (bias gradients, LayerNorm weight gradients from block partials)
+// stage 1: grid (ceil(N/32), chunks), block (32, 8) -> partial[chunk][N];  stage 2: one thread per output column
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kColRows = 1024;   // rows per chunk
+
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ X, i64 ld, i64 R, int N, float* __restrict__ partial) {
+  __shared__ float red[8][33];
+  const int j = blockIdx.x * 32 + threadIdx.x;
+  const i64 r0 = static_cast<i64>(blockIdx.y) * kColRows;
+  const i64 r1 = min(R, r0 + kColRows);
+  float s = 0.f;
+  if (j < N)
+    for (i64 r = r0 + threadIdx.y; r < r1; r += 8) s += X[r * ld + j];
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && j < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) t += red[y][threadIdx.x];
+    partial[static_cast<i64>(blockIdx.y) * N + j] = t;
+  }
+}
+__global__ void colsum_finish_kernel(const float* __restrict__ partial, int chunks, int N, int mod, float* __restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= mod) return;
+  float s = 0.f;
+  for (int c = 0; c < chunks; ++c)
+    for (int jj = j; jj < N; jj += mod) s += partial[static_cast<i64>(c) * N + jj];
+  out[j] += s;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// LayerNorm over the last dimension (C % 32 == 0, C <= 256), one warp per row
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int LNV = 8;   // values per lane
+
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ X, const float* __restrict__ gw, const float* __restrict__ gb,
+                                                     float* __restrict__ Y, float2* __restrict__ stats, i64 R, int C, float eps) {
+  const i64 row = static_cast<i64>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= R) return;
+  const int nv = C >> 5;
+  float v[LNV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < LNV; ++i)
+    if (i < nv) {
+      v[i] = X[row * C + lane + 32 * i];
+      s += v[i];
+    }
+  const float mean = warp_sum(s) / C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < LNV; ++i)
+    if (i < nv) {
+      v[i] -= mean;
+      q = fmaf(v[i], v[i], q);
+    }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) / C + eps);
+#pragma unroll
+  for (int i = 0; i < LNV; ++i)
+    if (i < nv) {
+      const int c = lane + 32 * i;
+      Y[row * C + c] = v[i] * rstd * gw[c] + gb[c];
+    }
+  if (lane == 0) stats[row] = make_float2(mean, rstd);
+}
+
+// dX += rstd * (dy*g - mean(dy*g) - xhat * mean(dy*g*xhat));  block partials of sum dy*xhat | sum dy -> part[block][2C]
+constexpr int kLnRowsPerBlock = 64;
+
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ dY, const float* __restrict__ X, const float2* __restrict__ stats,
+                                                     const float* __restrict__ gw, float* __restrict__ dX, float* __restrict__ part,
+                                                     i64 R, int C) {
+  __shared__ float red[8][2 * 256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nv = C >> 5;
+  float ag[LNV], ab[LNV];
+#pragma unroll
+  for (int i = 0; i < LNV; ++i) ag[i] = ab[i] = 0.f;
+  const i64 r0 = static_cast<i64>(blockIdx.x) * kLnRowsPerBlock;
+  for (int rr = warp; rr < kLnRowsPerBlock; rr += 8) {
+    const i64 row = r0 + rr;
+    if (row >= R) break;
+    const float2 st = stats[row];
+    float xh[LNV], dg[LNV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < LNV; ++i)
+      if (i < nv) {
+        const int c = lane + 32 * i;
+        const float dy = dY[row * C + c];
+        xh[i] = (X[row * C + c] - st.x) * st.y;
+        dg[i] = dy * gw[c];
+        s1 += dg[i];
+        s2 = fmaf(dg[i], xh[i], s2);
+        ag[i] = fmaf(dy, xh[i], ag[i]);
+        ab[i] += dy;
+      }
+    s1 = warp_sum(s1) / C;
+    s2 = warp_sum(s2) / C;
+    if (dX) {
+#pragma unroll
+      for (int i = 0; i < LNV; ++i)
+        if (i < nv) dX[row * C + lane + 32 * i] += st.y * (dg[i] - s1 - xh[i] * s2);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < LNV; ++i)
+    if (i < nv) {
+      red[warp][lane + 32 * i] = ag[i];
+      red[warp][C + lane + 32 * i] = ab[i];
+    }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * C; c += 256) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][c];
+    part[static_cast<i64>(blockIdx.x) * 2 * C + c] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// softmax over rows of length L (in place), and its adjoint dS = P * (dP - sum_j dP_j P_j) (in place on dP)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) softmax_fwd_kernel(float* __restrict__ S, i64 R, int L) {
+  const i64 row = static_cast<i64>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= R) return;
+  float* s = S + row * L;
+  float m = -INFINITY;
+  for (int j = lane; j < L; j += 32) m = fmaxf(m, s[j]);
+  m = warp_max(m);
+  float sum = 0.f;
+  for (int j = lane; j < L; j += 32) {
+    const float e = expf(s[j] - m);
+    s[j] = e;
+    sum += e;
+  }
+  const float inv = 1.0f / warp_sum(sum);
+  for (int j = lane; j < L; j += 32) s[j] *= inv;
+}
+__global__ void __launch_bounds__(256) softmax_bwd_kernel(float* __restrict__ dP, const float* __restrict__ P, i64 R, int L) {
+  const i64 row = static_cast<i64>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= R) return;
+  float* d = dP + row * L;
+  const float* p = P + row * L;
+  float dot = 0.f;
+  for (int j = lane; j < L; j += 32) dot = fmaf(d[j], p[j], dot);
+  dot = warp_sum(dot);
+  for (int j = lane; j < L; j += 32) d[j] = p[j] * (d[j] - dot);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// element-wise
+// ---------------------------------------------------------------------------------------------------------------
+#define GRID_STRIDE(i, n) for (i64 i = static_cast<i64>(blockIdx.x) * blockDim.x + threadIdx.x; i < (n); i += static_cast<i64>(gridDim.x) * blockDim.x)
+
+__global__ void add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ c, i64 n, i64 bmod) {
+  GRID_STRIDE(i, n) c[i] = a[i] + b[i % bmod];
+}
+__global__ void acc_kernel(float* __restrict__ dst, const float* __restrict__ src, i64 n) {
+  GRID_STRIDE(i, n) dst[i] += src[i];
+}
+__global__ void relu_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, i64 n) {
+  GRID_STRIDE(i, n) y[i] = fmaxf(x[i], 0.f);
+}
+__global__ void relu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dx, i64 n) {
+  GRID_STRIDE(i, n) if (y[i] > 0.f) dx[i] += dy[i];
+}
+__global__ void relu_mask_kernel(float* __restrict__ dy, const float* __restrict__ y, i64 n) {
+  GRID_STRIDE(i, n) if (!(y[i] > 0.f)) dy[i] = 0.f;
+}
+// exact-erf GELU (common.py:18 / nn.GELU default) and its derivative Phi(x) + x phi(x)
+__global__ void gelu_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, i64 n) {
+  GRID_STRIDE(i, n) y[i] = 0.5f * x[i] * (1.0f + erff(x[i] * 0.70710678118654752f));
+}
+__global__ void gelu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dx, i64 n) {
+  GRID_STRIDE(i, n) {
+    const float v = x[i];
+    const float cdf = 0.5f * (1.0f + erff(v * 0.70710678118654752f));
+    const float pdf = 0.3989422804014327f * expf(-0.5f * v * v);
+    dx[i] += dy[i] * (cdf + v * pdf);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// layout
+// ---------------------------------------------------------------------------------------------------------------
+// dst[p, t, c] = src[img(p), c, t] (+ dense_vec[c] | + dense_full[p, c, t]);   grid (HW/32, C/32, n), block (32, 8)
+__global__ void __launch_bounds__(256)
+train_nchw_to_tokens_kernel(const void* __restrict__ src, int src_fmt, const int* __restrict__ img_index, const void* __restrict__ dense_vec,
+                            const void* __restrict__ dense_full, int dense_fmt, float* __restrict__ dst, int C, int HW) {
+  __shared__ float tile[32][33];
+  const int p = blockIdx.z;
+  const int img = img_index ? img_index[p] : 0;
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i, t = t0 + threadIdx.x;
+    float v = load_any(src, src_fmt, (static_cast<size_t>(img) * C + c) * HW + t);
+    if (dense_vec) v += load_any(dense_vec, dense_fmt, c);
+    if (dense_full) v += load_any(dense_full, dense_fmt, (static_cast<size_t>(p) * C + c) * HW + t);
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int t = t0 + i, c = c0 + threadIdx.x;
+    dst[(static_cast<size_t>(p) * HW + t) * C + c] = tile[threadIdx.x][i];
+  }
+}
+
+// tokens[p, t, :] = iou_token | mask_tokens[t-1] | sparse[p, t-1-nm]   (mask_decoder.py:137-141)
+__global__ void tok_assemble_kernel(const float* __restrict__ iou_tok, const float* __restrict__ mask_tok, const float* __restrict__ sparse,
+                                    float* __restrict__ out, int n, int nm, int k, int C) {
+  const int T = 1 + nm + k;
+  GRID_STRIDE(i, static_cast<i64>(n) * T * C) {
+    const int c = static_cast<int>(i % C);
+    const int t = static_cast<int>((i / C) % T);
+    const int p = static_cast<int>(i / (static_cast<i64>(C) * T));
+    out[i] = t == 0 ? iou_tok[c] : t <= nm ? mask_tok[(t - 1) * C + c] : sparse[(static_cast<i64>(p) * k + (t - 1 - nm)) * C + c];
+  }
+}
+// adjoint: the learned tokens collect the sum over prompts (index order), the prompt embeddings their own rows
+__global__ void tok_assemble_bwd_kernel(const float* __restrict__ dout, float* __restrict__ d_iou_tok, float* __restrict__ d_mask_tok,
+                                        float* __restrict__ d_sparse, int n, int nm, int k, int C) {
+  const int T = 1 + nm + k;
+  GRID_STRIDE(i, static_cast<i64>(1 + nm) * C + static_cast<i64>(n) * k * C) {
+    if (i < static_cast<i64>(1 + nm) * C) {
+      const int c = static_cast<int>(i % C), t = static_cast<int>(i / C);
+      float s = 0.f;
+      for (int p = 0; p < n; ++p) s += dout[(static_cast<i64>(p) * T + t) * C + c];
+      if (t == 0) d_iou_tok[c] += s; else d_mask_tok[(t - 1) * C + c] += s;
+    } else {
+      const i64 r = i - static_cast<i64>(1 + nm) * C;
+      const int c = static_cast<int>(r % C);
+      const int j = static_cast<int>((r / C) % k);
+      const int p = static_cast<int>(r / (static_cast<i64>(C) * k));
+      d_sparse[r] += dout[(static_cast<i64>(p) * T + 1 + nm + j) * C + c];
+    }
+  }
+}
+
+// mask rows [n, pos = ((pixel*4 + sub)*4 + s2), nm]  <->  masks [n, nm, 4g, 4g]  (two stride-2 ConvTranspose2d:
+// sub = (dy,dx) of the first, s2 = (ey,ex) of the second; Y = 4y + 2dy + ey, X = 4x + 2dx + ex)
+__global__ void mask_rows_kernel(float* __restrict__ rows, float* __restrict__ masks, int n, int nm, int g, int to_rows) {
+  const int G4 = 4 * g;
+  const i64 per = static_cast<i64>(G4) * G4;
+  GRID_STRIDE(i, static_cast<i64>(n) * per * nm) {
+    const int kk = static_cast<int>(i % nm);
+    const i64 pos = (i / nm) % per;
+    const int p = static_cast<int>(i / (per * nm));
+    const int s2 = static_cast<int>(pos & 3), sub = static_cast<int>((pos >> 2) & 3);
+    const int pix = static_cast<int>(pos >> 4);
+    const int y = pix / g, x = pix - y * g;
+    const int Y = 4 * y + 2 * (sub >> 1) + (s2 >> 1), X = 4 * x + 2 * (sub & 1) + (s2 & 1);
+    const i64 m = ((static_cast<i64>(p) * nm + kk) * G4 + Y) * G4 + X;
+    if (to_rows) rows[i] = masks[m]; else masks[m] = rows[i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Adjoint of Sam.postprocess_masks (sam.py:159-172): two bilinear resamplings (align_corners=False) with a crop
+// between them.  Scatter form with float atomics, as PyTorch's own upsample_bilinear2d backward.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tap(int o, float scale, int in_size, int& i0, int& i1, float& l1) {
+  // area_pixel_compute_source_index: max(0, scale * (o + 0.5) - 0.5)
+  const float src = fmaxf(scale * (o + 0.5f) - 0.5f, 0.f);
+  i0 = static_cast<int>(src);
+  i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+  l1 = src - i0;
+}
+// d_in[m, iy, ix] += taps * d_out[m, oy, ox];   d_out [maps, out_h, out_w], d_in [maps, in_h, in_w], source index
+// = max(0, scale * (o + 0.5) - 0.5) as area_pixel_compute_source_index does for align_corners=False
+__global__ void bilinear_bwd_kernel(const float* __restrict__ d_out, float* __restrict__ d_in, int maps, int out_h, int out_w, int in_h,
+                                    int in_w, float sy, float sx) {
+  GRID_STRIDE(i, static_cast<i64>(maps) * out_h * out_w) {
+    const int ox = static_cast<int>(i % out_w);
+    const int oy = static_cast<int>((i / out_w) % out_h);
+    const i64 m = i / (static_cast<i64>(out_w) * out_h);
+    int y0, y1, x0, x1;
+    float ly, lx;
+    tap(oy, sy, in_h, y0, y1, ly);
+    tap(ox, sx, in_w, x0, x1, lx);
+    const float d = d_out[i];
+    float* base = d_in + m * in_h * in_w;
+    atomicAdd(base + static_cast<i64>(y0) * in_w + x0, (1.f - ly) * (1.f - lx) * d);
+    atomicAdd(base + static_cast<i64>(y0) * in_w + x1, (1.f - ly) * lx * d);
+    atomicAdd(base + static_cast<i64>(y1) * in_w + x0, ly * (1.f - lx) * d);
+    atomicAdd(base + static_cast<i64>(y1) * in_w + x1, ly * lx * d);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Host: tensors, tape, ops
+// ---------------------------------------------------------------------------------------------------------------
+struct Ten {
+  float* p = nullptr;   // values
+  float* g = nullptr;   // gradient (null: none wanted)
+  i64 rows = 0;
+  int cols = 0;
+  i64 ld = 0;
+  i64 numel() const { return rows * cols; }
+};
+
+inline unsigned blocks_for(i64 n) { return static_cast<unsigned>(std::min<i64>((n + 255) / 256, 148 * 16)); }
+inline size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
+
+struct Tape {
+  SamDecoderShape s{};
+  int n = 0, k = 0;
+  cudaStream_t st = nullptr;
+  bool dry = true;
+  uint8_t* base = nullptr;
+  size_t act_cap = 0, grad_cap = 0, scratch_cap = 0;   // region sizes (from the dry pass)
+  size_t act_off = 0, grad_off = 0, scratch_off = 0, scratch_peak = 0;
+  std::vector<std::function<int()>> back;
+  Ten masks, iou, sparse;
+  float* gblob = nullptr;   // gradient of the weight blob (inside the gradient region)
+  size_t blob_elems = 0;
+  bool overflow = false;   // an op asked for more scratch than the sizing pass reserved
+
+  Ten alloc(i64 rows, int cols, bool grad = true) {
+    Ten t;
+    t.rows = rows; t.cols = cols; t.ld = cols;
+    const size_t bytes = align256(static_cast<size_t>(rows) * cols * 4);
+    if (!dry) t.p = reinterpret_cast<float*>(base + act_off);
+    act_off += bytes;
+    if (grad) {
+      if (!dry) t.g = reinterpret_cast<float*>(base + act_cap + grad_off);
+      grad_off += bytes;
+    }
+    return t;
+  }
+  // op-local temporary (valid until the next scratch_reset)
+  float* scratch(size_t bytes) {
+    float* p = dry ? nullptr : reinterpret_cast<float*>(base + act_cap + grad_cap + scratch_off);
+    scratch_off += align256(bytes);
+    scratch_peak = std::max(scratch_peak, scratch_off);
+    if (!dry && scratch_cap && scratch_off > scratch_cap) overflow = true;
+    return p;
+  }
+  void scratch_reset() { scratch_off = 0; }
+
+  // ---- launches (no-ops in the dry pass, which only sizes the regions) ----
+  int gemm(Gemm g) {
+    if (g.nbatch <= 0) { g.nbatch = 1; }
+    if (g.nb2 <= 0) g.nb2 = 1;
+    if (g.bias_mod <= 0) g.bias_mod = g.N;
+    if (g.splits <= 1) { g.splits = 1; g.kchunk = g.K; }
+    if (g.splits > 1) g.partial = scratch(static_cast<size_t>(g.splits) * g.nbatch * g.M * g.N * 4);
+    if (dry || g.M == 0 || g.N == 0) return 0;
+    SAM_REQUIRE(!overflow, "decoder training: scratch region too small (internal sizing error)");
+    SAM_REQUIRE(static_cast<i64>(g.nbatch) * g.splits <= 65535 && (g.N + GT - 1) / GT <= 65535, "decoder training: gemm grid too large");
+    {
+      samhost::LaunchScope scope(samhost::KC_DECODER, st, 2.0 * g.M * g.N * g.K * g.nbatch);
+      dim3 grid((g.M + GT - 1) / GT, (g.N + GT - 1) / GT, g.nbatch * g.splits);
+      sgemm_kernel<<<grid, 256, 0, st>>>(g);
+      SAM_CHECK_CUDA(cudaGetLastError());
+    }
+    if (g.splits > 1) {
+      samhost::LaunchScope scope(samhost::KC_DECODER, st);
+      splitk_reduce_kernel<<<blocks_for(static_cast<i64>(g.M) * g.N * g.nbatch), 256, 0, st>>>(g);
+      SAM_CHECK_CUDA(cudaGetLastError());
+    }
+    return 0;
+  }
+  // out[j % mod] += sum_r X[r, j]
+  int colsum(const float* X, i64 ld, i64 R, int N, int mod, float* out) {
+    const int chunks = static_cast<int>((R + kColRows - 1) / kColRows);
+    float* part = scratch(static_cast<size_t>(chunks) * N * 4);
+    if (dry || R == 0) return 0;
+    SAM_REQUIRE(!overflow, "decoder training: scratch region too small (internal sizing error)");
+    SAM_REQUIRE(chunks <= 65535, "decoder training: colsum grid too large");
+    {
+      samhost::LaunchScope scope(samhost::KC_DECODER, st);
+      colsum_partial_kernel<<<dim3((N + 31) / 32, chunks), dim3(32, 8), 0, st>>>(X, ld, R, N, part);
+      SAM_CHECK_CUDA(cudaGetLastError());
+    }
+    {
+      samhost::LaunchScope scope(samhost::KC_DECODER, st);
+      colsum_finish_kernel<<<(mod + 127) / 128, 128, 0, st>>>(part, chunks, N, mod, out);
+      SAM_CHECK_CUDA(cudaGetLastError());
+    }
+    return 0;
+  }
+  template <typename F>
+  int ew(i64 n, F&& launch) {
+    if (dry || n == 0) return 0;
+    samhost::LaunchScope scope(samhost::KC_DECODER, st);
+    launch(blocks_for(n));
+    SAM_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
+  void push(std::function<int()> f) {
+    if (!dry) back.push_back(std::move(f));
+  }
+};
+
+#define TRY(expr)               \
+  do {                          \
+    if (int _rc = (expr)) return _rc; \
+  } while (0)
+
+// ---- ops: forward now, adjoint on the tape ----
+
+// Y = X . W^T + b      W [N, K] (parameter), bias [bias_mod] broadcast as b[j % bias_mod];  `out` may be a strided view
+int linear(Tape& t, const Ten& X, const Ten& W, const Ten& b, Ten* Y, int bias_mod = 0, const Ten* out = nullptr) {
+  const int N = static_cast<int>(W.rows), K = W.cols;
+  if (X.cols != K) return samhost::set_error(1, "decoder training: linear K mismatch (%d vs %d)", X.cols, K);
+  *Y = out ? *out : t.alloc(X.rows, N);
+  const int M = static_cast<int>(X.rows);
+  Gemm g{};
+  g.A = X.p; g.ars = X.ld; g.acs = 1;
+  g.B = W.p; g.brs = 1; g.bcs = K;
+  g.C = Y->p; g.crs = Y->ld;
+  g.bias = b.p; g.bias_mod = bias_mod ? bias_mod : N;
+  g.M = M; g.N = N; g.K = K; g.alpha = 1.f;
+  if (t.dry) g.bias = nullptr;
+  TRY(t.gemm(g));
+  t.scratch_reset();
+  const Ten Yc = *Y;
+  const int bm = g.bias_mod;
+  Tape* tp = &t;
+  t.push([tp, X, W, b, Yc, M, N, K, bm]() -> int {
+    Tape& t = *tp;
+    if (X.g) {   // dX += dY . W
+      Gemm g{};
+      g.A = Yc.g; g.ars = Yc.ld; g.acs = 1;
+      g.B = W.p; g.brs = K; g.bcs = 1;
+      g.C = X.g; g.crs = X.ld; g.accumulate = 1;
+      g.M = M; g.N = K; g.K = N; g.alpha = 1.f;
+      TRY(t.gemm(g));
+    }
+    if (W.g) {   // dW += dY^T . X   (reduction over the rows: split-K)
+      Gemm g{};
+      g.A = Yc.g; g.ars = 1; g.acs = Yc.ld;
+      g.B = X.p; g.brs = X.ld; g.bcs = 1;
+      g.C = W.g; g.crs = K; g.accumulate = 1;
+      g.M = N; g.N = K; g.K = M; g.alpha = 1.f;
+      if (M > 4096) { g.kchunk = 2048; g.splits = (M + g.kchunk - 1) / g.kchunk; }
+      TRY(t.gemm(g));
+    }
+    if (b.g) {
+      if (bm == N) {
+        TRY(t.colsum(Yc.g, Yc.ld, M, N, N, b.g));
+      } else {   // bias shared by N / bm column groups: rows of the [M * N / bm, bm] view (needs a contiguous Y)
+        TRY(t.colsum(Yc.g, bm, static_cast<i64>(M) * (N / bm), bm, bm, b.g));
+      }
+    }
+    t.scratch_reset();
+    return 0;
+  });
+  return 0;
+}
+
+// C = A + B[i % bmod]    (B may be a constant broadcast over the leading dimension)
+int add(Tape& t, const Ten& A, const Ten& B, Ten* C) {
+  *C = t.alloc(A.rows, A.cols);
+  const i64 n = A.numel(), bmod = B.numel();
+  const Ten Cc = *C;
+  TRY(t.ew(n, [&](unsigned nb) { add_kernel<<<nb, 256, 0, t.st>>>(A.p, B.p, Cc.p, n, bmod); }));
+  Tape* tp = &t;
+  t.push([tp, A, B, Cc, n, bmod]() -> int {
+    Tape& t = *tp;
+    if (A.g) TRY(t.ew(n, [&](unsigned nb) { acc_kernel<<<nb, 256, 0, t.st>>>(A.g, Cc.g, n); }));
+    if (B.g) {
+      if (bmod != n) return samhost::set_error(1, "decoder training: gradient of a broadcast addend is not supported");
+      TRY(t.ew(n, [&](unsigned nb) { acc_kernel<<<nb, 256, 0, t.st>>>(B.g, Cc.g, n); }));
+    }
+    return 0;
+  });
+  return 0;
+}
+
+int layernorm(Tape& t, const Ten& X, const Ten& gw, const Ten& gb, float eps, Ten* Y) {
+  const int C = X.cols;
+  const i64 R = X.rows;
+  if (C % 32 != 0 || C > 32 * LNV) return samhost::set_error(1, "decoder training: LayerNorm width %d", C);
+  *Y = t.alloc(R, C);
+  float2* stats = reinterpret_cast<float2*>(t.alloc(R, 2, false).p);
+  const Ten Yc = *Y;
+  if (!t.dry) {
+    samhost::LaunchScope scope(samhost::KC_DECODER, t.st);
+    ln_fwd_kernel<<<static_cast<unsigned>((R + 7) / 8), 256, 0, t.st>>>(X.p, gw.p, gb.p, Yc.p, stats, R, C, eps);
+    SAM_CHECK_CUDA(cudaGetLastError());
+  }
+  Tape* tp = &t;
+  t.push([tp, X, gw, gb, Yc, stats, R, C]() -> int {
+    Tape& t = *tp;
+    const int nblk = static_cast<int>((R + kLnRowsPerBlock - 1) / kLnRowsPerBlock);
+    float* part = t.scratch(static_cast<size_t>(nblk) * 2 * C * 4);
+    {
+      samhost::LaunchScope scope(samhost::KC_DECODER, t.st);
+      ln_bwd_kernel<<<nblk, 256, 0, t.st>>>(Yc.g, X.p, stats, gw.p, X.g, part, R, C);
+      SAM_CHECK_CUDA(cudaGetLastError());
+    }
+    // weight | bias gradients are adjacent in the blob (weight then bias): one column sum over the block partials
+    if (gw.g) {
+      if (gb.g != gw.g + C) return samhost::set_error(1, "decoder training: LayerNorm weight / bias gradients must be adjacent");
+      TRY(t.colsum(part, 2 * C, nblk, 2 * C, 2 * C, gw.g));
+    }
+    t.scratch_reset();
+    return 0;
+  });
+  return 0;
+}
+
+int relu(Tape& t, const Ten& X, Ten* Y) {
+  *Y = t.alloc(X.rows, X.cols);
+  const i64 n = X.numel();
+  const Ten Yc = *Y;
+  TRY(t.ew(n, [&](unsigned nb) { relu_fwd_kernel<<<nb, 256, 0, t.st>>>(X.p, Yc.p, n); }));
+  Tape* tp = &t;
+  t.push([tp, X, Yc, n]() -> int {
+    Tape& t = *tp;
+    return t.ew(n, [&](unsigned nb) { relu_bwd_kernel<<<nb, 256, 0, t.st>>>(Yc.g, Yc.p, X.g, n); });
+  });
+  return 0;
+}
+int gelu(Tape& t, const Ten& X, Ten* Y) {
+  *Y = t.alloc(X.rows, X.cols);
+  const i64 n = X.numel();
+  const Ten Yc = *Y;
+  TRY(t.ew(n, [&](unsigned nb) { gelu_fwd_kernel<<<nb, 256, 0, t.st>>>(X.p, Yc.p, n); }));
+  Tape* tp = &t;
+  t.push([tp, X, Yc, n]() -> int {
+    Tape& t = *tp;
+    return t.ew(n, [&](unsigned nb) { gelu_bwd_kernel<<<nb, 256, 0, t.st>>>(Yc.g, X.p, X.g, n); });
+  });
+  return 0;
+}
+
+// softmax(q k^T / sqrt(dh)) v per (prompt, head)   (transformer.py:232-239);  q [n*Nq, D], k / v [n*Nk, D] -> o [n*Nq, D]
+int attention_core(Tape& t, const Ten& q, const Ten& k, const Ten& v, int n, int Nq, int Nk, int heads, Ten* o) {
+  const int D = q.cols, dh = D / heads;
+  const float scale = 1.0f / sqrtf(static_cast<float>(dh));
+  *o = t.alloc(static_cast<i64>(n) * Nq, D);
+  Ten P = t.alloc(static_cast<i64>(n) * heads * Nq, Nk, false);
+  const Ten oc = *o;
+  auto batch = [&](Gemm& g) { g.nbatch = n * heads; g.nb2 = heads; };
+  {
+    Gemm g{};   // S = scale * Q K^T
+    batch(g);
+    g.A = q.p; g.ars = q.ld; g.acs = 1; g.a_b1 = static_cast<i64>(Nq) * q.ld; g.a_b2 = dh;
+    g.B = k.p; g.brs = 1; g.bcs = k.ld; g.b_b1 = static_cast<i64>(Nk) * k.ld; g.b_b2 = dh;
+    g.C = P.p; g.crs = Nk; g.c_b1 = static_cast<i64>(heads) * Nq * Nk; g.c_b2 = static_cast<i64>(Nq) * Nk;
+    g.M = Nq; g.N = Nk; g.K = dh; g.alpha = scale;
+    TRY(t.gemm(g));
+  }
+  const i64 R = static_cast<i64>(n) * heads * Nq;
+  if (!t.dry) {
+    samhost::LaunchScope scope(samhost::KC_DECODER, t.st);
+    softmax_fwd_kernel<<<static_cast<unsigned>((R + 7) / 8), 256, 0, t.st>>>(P.p, R, Nk);
+    SAM_CHECK_CUDA(cudaGetLastError());
+  }
+  {
+    Gemm g{};   // O = P V
+    batch(g);
+    g.A = P.p; g.ars = Nk; g.acs = 1; g.a_b1 = static_cast<i64>(heads) * Nq * Nk; g.a_b2 = static_cast<i64>(Nq) * Nk;
+    g.B = v.p; g.brs = v.ld; g.bcs = 1; g.b_b1 = static_cast<i64>(Nk) * v.ld; g.b_b2 = dh;
+    g.C = oc.p; g.crs = oc.ld; g.c_b1 = static_cast<i64>(Nq) * oc.ld; g.c_b2 = dh;
+    g.M = Nq; g.N = dh; g.K = Nk; g.alpha = 1.f;
+    TRY(t.gemm(g));
+  }
+  t.scratch_reset();
+  Tape* tp = &t;
+  t.push([tp, q, k, v, oc, P, n, Nq, Nk, heads, dh, scale, R]() -> int {
+    Tape& t = *tp;
+    auto batch = [&](Gemm& g) { g.nbatch = n * heads; g.nb2 = heads; };
+    const i64 pb1 = static_cast<i64>(heads) * Nq * Nk, pb2 = static_cast<i64>(Nq) * Nk;
+    float* dP = t.scratch(static_cast<size_t>(R) * Nk * 4);
+    {
+      Gemm g{};   // dP = dO V^T
+      batch(g);
+      g.A = oc.g; g.ars = oc.ld; g.acs = 1; g.a_b1 = static_cast<i64>(Nq) * oc.ld; g.a_b2 = dh;
+      g.B = v.p; g.brs = 1; g.bcs = v.ld; g.b_b1 = static_cast<i64>(Nk) * v.ld; g.b_b2 = dh;
+      g.C = dP; g.crs = Nk; g.c_b1 = pb1; g.c_b2 = pb2;
+      g.M = Nq; g.N = Nk; g.K = dh; g.alpha = 1.f;
+      TRY(t.gemm(g));
+    }
+    if (v.g) {
+      Gemm g{};   // dV += P^T dO
+      batch(g);
+      g.A = P.p; g.ars = 1; g.acs = Nk; g.a_b1 = pb1; g.a_b2 = pb2;
+      g.B = oc.g; g.brs = oc.ld; g.bcs = 1; g.b_b1 = static_cast<i64>(Nq) * oc.ld; g.b_b2 = dh;
+      g.C = v.g; g.crs = v.ld; g.c_b1 = static_cast<i64>(Nk) * v.ld; g.c_b2 = dh; g.accumulate = 1;
+      g.M = Nk; g.N = dh; g.K = Nq; g.alpha = 1.f;
+      TRY(t.gemm(g));
+    }
+    {
+      samhost::LaunchScope scope(samhost::KC_DECODER, t.st);
+      softmax_bwd_kernel<<<static_cast<unsigned>((R + 7) / 8), 256, 0, t.st>>>(dP, P.p, R, Nk);
+      SAM_CHECK_CUDA(cudaGetLastError());
+    }
+    if (q.g) {
+      Gemm g{};   // dQ += scale * dS K
+      batch(g);
+      g.A = dP; g.ars = Nk; g.acs = 1; g.a_b1 = pb1; g.a_b2 = pb2;
+      g.B = k.p; g.brs = k.ld; g.bcs = 1; g.b_b1 = static_cast<i64>(Nk) * k.ld; g.b_b2 = dh;
+      g.C = q.g; g.crs = q.ld; g.c_b1 = static_cast<i64>(Nq) * q.ld; g.c_b2 = dh; g.accumulate = 1;
+      g.M = Nq; g.N = dh; g.K = Nk; g.alpha = scale;
+      TRY(t.gemm(g));
+    }
+    if (k.g) {
+      Gemm g{};   // dK += scale * dS^T Q
+      batch(g);
+      g.A = dP; g.ars = 1; g.acs = Nk; g.a_b1 = pb1; g.a_b2 = pb2;
+      g.B = q.p; g.brs = q.ld; g.bcs = 1; g.b_b1 = static_cast<i64>(Nq) * q.ld; g.b_b2 = dh;
+      g.C = k.g; g.crs = k.ld; g.c_b1 = static_cast<i64>(Nk) * k.ld; g.c_b2 = dh; g.accumulate = 1;
+      g.M = Nk; g.N = dh; g.K = Nq; g.alpha = scale;
+      TRY(t.gemm(g));
+    }
+    t.scratch_reset();
+    return 0;
+  });
+  return 0;
+}
+
+// parameters: pointers into the weight blob and, at the same offset, into its gradient
+struct ParamWalk {
+  const float* blob;
+  float* gblob;
+  size_t off = 0;
+  Ten take(i64 rows, int cols) {
+    Ten t;
+    t.p = const_cast<float*>(blob) + off;
+    t.g = gblob ? gblob + off : nullptr;
+    t.rows = rows; t.cols = cols; t.ld = cols;
+    off += static_cast<size_t>(rows) * cols;
+    return t;
+  }
+};
+struct AttnP { Ten qw, qb, kw, kb, vw, vb, ow, ob; };
+struct Mlp3P { Ten w0, b0, w1, b1, w2, b2; };
+struct LayerP {
+  AttnP self_attn, t2i, i2t;
+  Ten n1w, n1b, n2w, n2b, n3w, n3b, n4w, n4b, l1w, l1b, l2w, l2b;
+};
+struct Params {
+  Ten iou_token, mask_tokens;
+  LayerP layer[8];
+  AttnP final_attn;
+  Ten nfw, nfb, up0w, up0b, upln_w, upln_b, up1w, up1b;
+  Mlp3P hyper[4], iou_head;
+  size_t total;
+};
+// same order as csrc/decoder.cu carve_weights / _pack.pack_decoder (== state_dict order of mask_decoder.*)
+void carve_params(const SamDecoderShape& s, const float* blob, float* gblob, Params* P) {
+  const int C = s.C, Ci = C / 2, H = s.mlp_dim, nm = s.num_mask_tokens;
+  ParamWalk w{blob, gblob};
+  auto attn = [&](AttnP& a, int inner) {
+    a.qw = w.take(inner, C); a.qb = w.take(1, inner);
+    a.kw = w.take(inner, C); a.kb = w.take(1, inner);
+    a.vw = w.take(inner, C); a.vb = w.take(1, inner);
+    a.ow = w.take(C, inner); a.ob = w.take(1, C);
+  };
+  P->iou_token = w.take(1, C);
+  P->mask_tokens = w.take(nm, C);
+  for (int l = 0; l < s.depth; ++l) {
+    LayerP& L = P->layer[l];
+    attn(L.self_attn, C);
+    L.n1w = w.take(1, C); L.n1b = w.take(1, C);
+    attn(L.t2i, Ci);
+    L.n2w = w.take(1, C); L.n2b = w.take(1, C);
+    L.l1w = w.take(H, C); L.l1b = w.take(1, H);
+    L.l2w = w.take(C, H); L.l2b = w.take(1, C);
+    L.n3w = w.take(1, C); L.n3b = w.take(1, C);
+    L.n4w = w.take(1, C); L.n4b = w.take(1, C);
+    attn(L.i2t, Ci);
+  }
+  attn(P->final_attn, Ci);
+  P->nfw = w.take(1, C); P->nfb = w.take(1, C);
+  const int C1 = C / 4, C2 = C / 8;
+  P->up0w = w.take(4 * C1, C); P->up0b = w.take(1, 4 * C1);
+  P->upln_w = w.take(1, C1); P->upln_b = w.take(1, C1);
+  P->up1w = w.take(4 * C2, C1); P->up1b = w.take(1, C2);
+  for (int i = 0; i < nm; ++i) {
+    Mlp3P& m = P->hyper[i];
+    m.w0 = w.take(C, C); m.b0 = w.take(1, C);
+    m.w1 = w.take(C, C); m.b1 = w.take(1, C);
+    m.w2 = w.take(C2, C); m.b2 = w.take(1, C2);
+  }
+  const int Hi = s.iou_hidden;
+  Mlp3P& h = P->iou_head;
+  h.w0 = w.take(Hi, C); h.b0 = w.take(1, Hi);
+  h.w1 = w.take(Hi, Hi); h.b1 = w.take(1, Hi);
+  h.w2 = w.take(nm, Hi); h.b2 = w.take(1, nm);
+  P->total = w.off;
+}
+
+// Attention module (transformer.py:185-242): projections + attention_core + out_proj
+int attention(Tape& t, const AttnP& a, const Ten& xq, const Ten& xk, const Ten& xv, int n, int Nq, int Nk, int heads, Ten* out) {
+  Ten q, k, v, o;
+  TRY(linear(t, xq, a.qw, a.qb, &q));
+  TRY(linear(t, xk, a.kw, a.kb, &k));
+  TRY(linear(t, xv, a.vw, a.vb, &v));
+  TRY(attention_core(t, q, k, v, n, Nq, Nk, heads, &o));
+  return linear(t, o, a.ow, a.ob, out);
+}
+int mlp3(Tape& t, const Mlp3P& m, const Ten& x, Ten* y, const Ten* out = nullptr) {
+  Ten h0, r0, h1, r1;
+  TRY(linear(t, x, m.w0, m.b0, &h0));
+  TRY(relu(t, h0, &r0));
+  TRY(linear(t, r0, m.w1, m.b1, &h1));
+  TRY(relu(t, h1, &r1));
+  return linear(t, r1, m.w2, m.b2, y, 0, out);
+}
+
+struct TrainInputs {
+  const float* blob;
+  const void* emb; int emb_fmt; int n_images; const int* img_index;
+  const float* sparse;
+  const void* dense_vec; const void* dense_full; int dense_fmt;
+  const void* image_pe; int pe_fmt;
+};
+
+// The whole forward; in the dry pass (t.dry) it only advances the allocators.
+int build_forward(Tape& t, const TrainInputs& in) {
+  const SamDecoderShape& s = t.s;
+  const int C = s.C, nm = s.num_mask_tokens, g = s.grid, HW = g * g, n = t.n, k = t.k, T = 1 + nm + k, heads = s.heads;
+  const int C1 = C / 4, C2 = C / 8;
+  t.gblob = t.dry ? nullptr : reinterpret_cast<float*>(t.base + t.act_cap + t.grad_off);
+  t.grad_off += align256(t.blob_elems * 4);
+  Params P;
+  carve_params(s, in.blob, t.dry ? nullptr : t.gblob, &P);
+  if (P.total != t.blob_elems) return samhost::set_error(1, "decoder training: weight layout mismatch");
+
+  // inputs
+  t.sparse = t.alloc(static_cast<i64>(n) * k, C);
+  if (!t.dry && k > 0)
+    SAM_CHECK_CUDA(cudaMemcpyAsync(t.sparse.p, in.sparse, static_cast<size_t>(n) * k * C * 4, cudaMemcpyDeviceToDevice, t.st));
+  Ten tokens0 = t.alloc(static_cast<i64>(n) * T, C);
+  {
+    const Ten sp = t.sparse, iou_t = P.iou_token, mask_t = P.mask_tokens;
+    TRY(t.ew(tokens0.numel(), [&](unsigned nb) {
+      tok_assemble_kernel<<<nb, 256, 0, t.st>>>(iou_t.p, mask_t.p, sp.p, tokens0.p, n, nm, k, C);
+    }));
+    Tape* tp = &t;
+    t.push([tp, tokens0, sp, iou_t, mask_t, n, nm, k, C]() -> int {
+      Tape& t = *tp;
+      return t.ew(static_cast<i64>(1 + nm + n * k) * C, [&](unsigned nb) {
+        tok_assemble_bwd_kernel<<<nb, 256, 0, t.st>>>(tokens0.g, iou_t.g, mask_t.g, sp.g, n, nm, k, C);
+      });
+    });
+  }
+  Ten keys = t.alloc(static_cast<i64>(n) * HW, C, false);   // image embedding + dense prompt embedding: constants
+  Ten pe = t.alloc(HW, C, false);
+  if (!t.dry) {
+    samhost::LaunchScope scope(samhost::KC_DECODER, t.st, 0.0, 0.0, 2);
+    train_nchw_to_tokens_kernel<<<dim3(HW / 32, C / 32, n), dim3(32, 8), 0, t.st>>>(in.emb, in.emb_fmt, in.img_index, in.dense_vec,
+                                                                                  in.dense_full, in.dense_fmt, keys.p, C, HW);
+    SAM_CHECK_CUDA(cudaGetLastError());
+    train_nchw_to_tokens_kernel<<<dim3(HW / 32, C / 32, 1), dim3(32, 8), 0, t.st>>>(in.image_pe, in.pe_fmt, nullptr, nullptr, nullptr, 2,
+                                                                                  pe.p, C, HW);
+    SAM_CHECK_CUDA(cudaGetLastError());
+  }
+
+  Ten queries = tokens0;
+  for (int l = 0; l < s.depth; ++l) {
+    const LayerP& L = P.layer[l];
+    Ten a, q, kpe, x;
+    if (l == 0) {   // skip_first_layer_pe: the self-attention output replaces the queries (transformer.py:153-155)
+      TRY(attention(t, L.self_attn, queries, queries, queries, n, T, T, heads, &x));
+    } else {
+      TRY(add(t, queries, tokens0, &q));
+      TRY(attention(t, L.self_attn, q, q, queries, n, T, T, heads, &a));
+      TRY(add(t, queries, a, &x));
+    }
+    TRY(layernorm(t, x, L.n1w, L.n1b, 1e-5f, &queries));
+    TRY(add(t, queries, tokens0, &q));
+    TRY(add(t, keys, pe, &kpe));
+    TRY(attention(t, L.t2i, q, kpe, keys, n, T, HW, heads, &a));
+    TRY(add(t, queries, a, &x));
+    TRY(layernorm(t, x, L.n2w, L.n2b, 1e-5f, &queries));
+    Ten h, r, m;
+    TRY(linear(t, queries, L.l1w, L.l1b, &h));
+    TRY(relu(t, h, &r));
+    TRY(linear(t, r, L.l2w, L.l2b, &m));
+    TRY(add(t, queries, m, &x));
+    TRY(layernorm(t, x, L.n3w, L.n3b, 1e-5f, &queries));
+    TRY(add(t, queries, tokens0, &q));
+    TRY(attention(t, L.i2t, kpe, q, queries, n, HW, T, heads, &a));   // keys + key_pe is unchanged since the t2i attention
+    TRY(add(t, keys, a, &x));
+    TRY(layernorm(t, x, L.n4w, L.n4b, 1e-5f, &keys));
+  }
+  {
+    Ten a, q, kpe, x;
+    TRY(add(t, queries, tokens0, &q));
+    TRY(add(t, keys, pe, &kpe));
+    TRY(attention(t, P.final_attn, q, kpe, keys, n, T, HW, heads, &a));
+    TRY(add(t, queries, a, &x));
+    TRY(layernorm(t, x, P.nfw, P.nfb, 1e-5f, &queries));
+  }
+  const Ten hs = queries;   // [n*T, C]
+  auto token_row = [&](int tok) {   // hs[:, tok, :] as a strided [n, C] view
+    Ten v = hs;
+    v.p = hs.p ? hs.p + static_cast<i64>(tok) * C : nullptr;
+    v.g = hs.g ? hs.g + static_cast<i64>(tok) * C : nullptr;
+    v.rows = n; v.ld = static_cast<i64>(T) * C;
+    return v;
+  };
+  // output_upscaling (mask_decoder.py:53-63): both stride-2 ConvTranspose2d are per-pixel linears
+  Ten U, Un, Ug, Z, Zg;
+  TRY(linear(t, keys, P.up0w, P.up0b, &U));                    // [n*HW, (dy,dx,oc)]
+  U.rows *= 4; U.cols = C1; U.ld = C1;                          // -> [(pixel, sub), oc]
+  TRY(layernorm(t, U, P.upln_w, P.upln_b, 1e-6f, &Un));        // LayerNorm2d: over the channels of each output pixel
+  TRY(gelu(t, Un, &Ug));
+  TRY(linear(t, Ug, P.up1w, P.up1b, &Z, C2));                  // [(pixel, sub), (ey,ex,oc)]
+  TRY(gelu(t, Z, &Zg));
+  Ten up = Zg;
+  up.rows *= 4; up.cols = C2; up.ld = C2;                       // [(pixel, sub, s2), oc]
+  // hypernetwork MLPs (mask_decoder.py:163-169) write their rows of hyper_in [n, nm, C2]
+  Ten hyper = t.alloc(n, nm * C2);
+  for (int i = 0; i < nm; ++i) {
+    Ten view = hyper, y;
+    view.p = hyper.p ? hyper.p + i * C2 : nullptr;
+    view.g = hyper.g ? hyper.g + i * C2 : nullptr;
+    view.cols = C2;
+    TRY(mlp3(t, P.hyper[i], token_row(1 + i), &y, &view));
+  }
+  // masks = hyper_in @ upscaled (mask_decoder.py:171-174), as rows [pos, nm] per prompt, then the layout gather
+  const i64 per = static_cast<i64>(HW) * 16;
+  Ten mrows = t.alloc(static_cast<i64>(n) * per, nm);
+  {
+    Gemm gm{};
+    gm.nbatch = n; gm.nb2 = 1;
+    gm.A = up.p; gm.ars = C2; gm.acs = 1; gm.a_b1 = per * C2;
+    gm.B = hyper.p; gm.brs = 1; gm.bcs = C2; gm.b_b1 = static_cast<i64>(nm) * C2;
+    gm.C = mrows.p; gm.crs = nm; gm.c_b1 = per * nm;
+    gm.M = static_cast<int>(per); gm.N = nm; gm.K = C2; gm.alpha = 1.f;
+    TRY(t.gemm(gm));
+    t.scratch_reset();
+    Tape* tp = &t;
+    t.push([tp, up, hyper, mrows, n, nm, C2, per]() -> int {
+      Tape& t = *tp;
+      {
+        Gemm g{};   // d_up += dM . hyper
+        g.nbatch = n; g.nb2 = 1;
+        g.A = mrows.g; g.ars = nm; g.acs = 1; g.a_b1 = per * nm;
+        g.B = hyper.p; g.brs = C2; g.bcs = 1; g.b_b1 = static_cast<i64>(nm) * C2;
+        g.C = up.g; g.crs = C2; g.c_b1 = per * C2; g.accumulate = 1;
+        g.M = static_cast<int>(per); g.N = C2; g.K = nm; g.alpha = 1.f;
+        TRY(t.gemm(g));
+      }
+      {
+        Gemm g{};   // d_hyper += dM^T . up  (reduction over the 65536 positions: split-K)
+        g.nbatch = n; g.nb2 = 1;
+        g.A = mrows.g; g.ars = 1; g.acs = nm; g.a_b1 = per * nm;
+        g.B = up.p; g.brs = C2; g.bcs = 1; g.b_b1 = per * C2;
+        g.C = hyper.g; g.crs = C2; g.c_b1 = static_cast<i64>(nm) * C2; g.accumulate = 1;
+        g.M = nm; g.N = C2; g.K = static_cast<int>(per); g.alpha = 1.f;
+        g.kchunk = 2048; g.splits = static_cast<int>((per + g.kchunk - 1) / g.kchunk);
+        TRY(t.gemm(g));
+      }
+      t.scratch_reset();
+      return 0;
+    });
+  }
+  t.masks = t.alloc(static_cast<i64>(n) * nm, 16 * HW);
+  {
+    const Ten mk = t.masks;
+    const i64 tot = mrows.numel();
+    TRY(t.ew(tot, [&](unsigned nb) { mask_rows_kernel<<<nb, 256, 0, t.st>>>(mrows.p, mk.p, n, nm, g, 0); }));
+    Tape* tp = &t;
+    t.push([tp, mrows, mk, n, nm, g, tot]() -> int {
+      Tape& t = *tp;   // mrows.g is zero here (this is its only consumer): a plain gather
+      return t.ew(tot, [&](unsigned nb) { mask_rows_kernel<<<nb, 256, 0, t.st>>>(mrows.g, mk.g, n, nm, g, 1); });
+    });
+  }
+  TRY(mlp3(t, P.iou_head, token_row(0), &t.iou));
+  return 0;
+}
+
+size_t region_total(const Tape& t) { return t.act_cap + t.grad_cap + t.scratch_cap + 256; }
+
+// Sizes the three regions (host only).  The backward's scratch needs are a function of the same shapes; they are
+// covered by running the adjoint closures' sizing rules here: the largest are the attention dP (as big as P) and the
+// split-K partials, both bounded by `bound` below.
+int size_regions(Tape& t) {
+  t.dry = true;
+  t.act_off = t.grad_off = t.scratch_off = t.scratch_peak = 0;
+  TrainInputs none{};
+  TRY(build_forward(t, none));
+  const SamDecoderShape& s = t.s;
+  const i64 HW = static_cast<i64>(s.grid) * s.grid, T = 1 + s.num_mask_tokens + t.k;
+  const i64 Tm = std::max<i64>(T, 1);
+  size_t bound = 0;
+  // attention dP: n * heads * Nq * Nk floats, largest with one side = HW
+  bound = std::max(bound, align256(static_cast<size_t>(t.n) * s.heads * std::max(Tm * HW, Tm * Tm) * 4));
+  // split-K partials of a weight gradient: ceil(M / 2048) * N * K floats with N*K <= max(C*C, H*C), M = n*HW*4 at most
+  const i64 rows_max = static_cast<i64>(t.n) * HW * 4;
+  const i64 nk_max = std::max<i64>(static_cast<i64>(s.C) * s.C, static_cast<i64>(s.mlp_dim) * s.C);
+  bound = std::max(bound, align256(static_cast<size_t>((rows_max + 2047) / 2048) * nk_max * 4));
+  // column-sum partials and LayerNorm block partials: rows / 64 * 2C floats at most
+  bound = std::max(bound, align256(static_cast<size_t>((rows_max + 63) / 64 + 1) * 2 * s.C * 4));
+  // hyper gradient partials: n * (16 HW / 2048) * nm * C/8
+  bound = std::max(bound, align256(static_cast<size_t>(t.n) * ((16 * HW + 2047) / 2048) * s.num_mask_tokens * (s.C / 8) * 4));
+  t.act_cap = align256(t.act_off);
+  t.grad_cap = align256(t.grad_off);
+  t.scratch_cap = 2 * std::max(bound, t.scratch_peak) + 4096;
+  return 0;
+}
+
+int check_train_shape(const SamDecoderShape& s, int n, int k) {
+  SAM_REQUIRE(s.C == 256 && s.C % s.heads == 0 && (s.C / 2) % s.heads == 0, "decoder training: transformer_dim must be 256 (got %d)", s.C);
+  SAM_REQUIRE(s.depth >= 1 && s.depth <= 8 && s.num_mask_tokens >= 1 && s.num_mask_tokens <= 4, "decoder training: depth / mask tokens");
+  SAM_REQUIRE(s.grid > 0 && (s.grid * s.grid) % 32 == 0, "decoder training: grid %d", s.grid);
+  SAM_REQUIRE(n >= 1 && k >= 0, "decoder training: n = %d prompts, k = %d embeddings per prompt", n, k);
+  return 0;
+}
+
+}  // namespace
+
+size_t samk_decoder_train_workspace_bytes(const SamDecoderShape& s, int n, int k) {
+  if (check_train_shape(s, n, k)) return 0;
+  Tape t;
+  t.s = s; t.n = n; t.k = k;
+  t.blob_elems = samk_decoder_weight_elems(s);
+  if (size_regions(t)) return 0;
+  return region_total(t);
+}
+
+int samk_decoder_train_forward(const SamDecoderShape& s, const float* blob, const void* image_embeddings, int emb_fmt, int n_images,
+                               const int* img_index, const float* sparse, int n, int k, const void* dense_vec, const void* dense_full,
+                               int dense_fmt, const void* image_pe, int pe_fmt, float* masks, float* iou, void* workspace,
+                               size_t workspace_bytes, void** tape_out, cudaStream_t st) {
+  SAM_REQUIRE(tape_out != nullptr, "decoder training: NULL tape_out");
+  *tape_out = nullptr;
+  if (int rc = check_train_shape(s, n, k)) return rc;
+  SAM_REQUIRE(blob && image_embeddings && image_pe && masks && iou && workspace && (k == 0 || sparse), "decoder training: NULL argument");
+  SAM_REQUIRE(n_images >= 1 && (img_index || n_images == 1), "decoder training: img_index is required with several images");
+  SAM_REQUIRE(!(dense_vec && dense_full), "decoder training: pass the dense embedding as a vector OR in full");
+  Tape* t = new Tape();
+  t->s = s; t->n = n; t->k = k; t->st = st;
+  t->blob_elems = samk_decoder_weight_elems(s);
+  int rc = size_regions(*t);
+  if (!rc && region_total(*t) > workspace_bytes)
+    rc = samhost::set_error(1, "decoder training: workspace of %zu bytes, %zu needed", workspace_bytes, region_total(*t));
+  if (!rc) {
+    t->dry = false;
+    t->base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~static_cast<uintptr_t>(255));
+    t->act_off = t->grad_off = t->scratch_off = 0;
+    TrainInputs in{blob, image_embeddings, emb_fmt, n_images, img_index, sparse, dense_vec, dense_full, dense_fmt, image_pe, pe_fmt};
+    rc = build_forward(*t, in);
+  }
+  if (!rc) {
+    const size_t mb = static_cast<size_t>(n) * s.num_mask_tokens * 16 * s.grid * s.grid * 4;
+    cudaError_t e = cudaMemcpyAsync(masks, t->masks.p, mb, cudaMemcpyDeviceToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(iou, t->iou.p, static_cast<size_t>(n) * s.num_mask_tokens * 4, cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) rc = samhost::set_error(2, "decoder training: output copy failed: %s", cudaGetErrorString(e));
+  }
+  if (rc) {
+    delete t;
+    return rc;
+  }
+  *tape_out = t;
+  return 0;
+}
+
+int samk_decoder_backward(void* tape, const float* d_masks, const float* d_iou, float* d_weights, float* d_sparse, cudaStream_t st) {
+  SAM_REQUIRE(tape != nullptr, "decoder backward: NULL tape");
+  Tape& t = *static_cast<Tape*>(tape);
+  SAM_REQUIRE(!t.back.empty(), "decoder backward: this tape has already been consumed");
+  SAM_REQUIRE(d_weights != nullptr, "decoder backward: NULL d_weights");
+  t.st = st;
+  const SamDecoderShape& s = t.s;
+  SAM_CHECK_CUDA(cudaMemsetAsync(t.base + t.act_cap, 0, t.grad_cap, st));
+  if (d_masks)
+    SAM_CHECK_CUDA(cudaMemcpyAsync(t.masks.g, d_masks, static_cast<size_t>(t.masks.numel()) * 4, cudaMemcpyDeviceToDevice, st));
+  if (d_iou)
+    SAM_CHECK_CUDA(cudaMemcpyAsync(t.iou.g, d_iou, static_cast<size_t>(t.n) * s.num_mask_tokens * 4, cudaMemcpyDeviceToDevice, st));
+  for (size_t i = t.back.size(); i-- > 0;) {
+    t.scratch_reset();
+    if (int rc = t.back[i]()) return rc;
+  }
+  t.back.clear();
+  {
+    samhost::LaunchScope scope(samhost::KC_DECODER, st);
+    acc_kernel<<<blocks_for(static_cast<i64>(t.blob_elems)), 256, 0, st>>>(d_weights, t.gblob, static_cast<i64>(t.blob_elems));
+    SAM_CHECK_CUDA(cudaGetLastError());
+  }
+  if (d_sparse && t.k > 0)
+    SAM_CHECK_CUDA(cudaMemcpyAsync(d_sparse, t.sparse.g, static_cast<size_t>(t.n) * t.k * s.C * 4, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+void samk_decoder_tape_free(void* tape) { delete static_cast<Tape*>(tape); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// fp32 linear forward / backward for text_hidden_fcs (model/anyref.py:116-124) in training
+// ---------------------------------------------------------------------------------------------------------------
+size_t samk_linear_f32_scratch_bytes(int M, int N, int K) {
+  const size_t splitk = M > 4096 ? static_cast<size_t>((M + 2047) / 2048) * N * K * 4 : 0;
+  const size_t cols = static_cast<size_t>((M + kColRows - 1) / kColRows) * N * 4;
+  return align256(splitk) + align256(cols) + 1024;
+}
+
+int samk_linear_f32_forward(const float* X, const float* W, const float* b, float* Y, int M, int N, int K, int relu_act, cudaStream_t st) {
+  SAM_REQUIRE(X && W && Y && M >= 0 && N > 0 && K > 0, "linear_f32_forward: bad arguments");
+  if (M == 0) return 0;
+  Gemm g{};
+  g.A = X; g.ars = K; g.acs = 1;
+  g.B = W; g.brs = 1; g.bcs = K;
+  g.C = Y; g.crs = N;
+  g.bias = b; g.bias_mod = N;
+  g.M = M; g.N = N; g.K = K; g.alpha = 1.f;
+  g.nbatch = 1; g.nb2 = 1; g.splits = 1; g.kchunk = K;
+  {
+    samhost::LaunchScope scope(samhost::KC_GEMM, st, 2.0 * M * N * K);
+    sgemm_kernel<<<dim3((M + GT - 1) / GT, (N + GT - 1) / GT, 1), 256, 0, st>>>(g);
+    SAM_CHECK_CUDA(cudaGetLastError());
+  }
+  if (relu_act) {
+    samhost::LaunchScope scope(samhost::KC_GEMM, st);
+    const i64 n = static_cast<i64>(M) * N;
+    relu_fwd_kernel<<<blocks_for(n), 256, 0, st>>>(Y, Y, n);
+    SAM_CHECK_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+// dX = dY . W (overwritten; may be NULL), dW += dY^T . X, db += column sums of dY.  With relu_y (the forward's output of a
+// fused ReLU) dY is first masked IN PLACE with (relu_y > 0)
+int samk_linear_f32_backward(float* dY, const float* relu_y, const float* X, const float* W, float* dX, float* dW, float* db, int M, int N, int K,
+                             void* scratch, size_t scratch_bytes, cudaStream_t st) {
+  SAM_REQUIRE(dY && X && W && M >= 0 && N > 0 && K > 0, "linear_f32_backward: bad arguments");
+  SAM_REQUIRE(scratch && scratch_bytes >= samk_linear_f32_scratch_bytes(M, N, K), "linear_f32_backward: scratch too small");
+  if (M == 0) return 0;
+  Tape t;
+  t.dry = false; t.st = st;
+  t.base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(scratch) + 255) & ~static_cast<uintptr_t>(255));
+  if (relu_y) {
+    samhost::LaunchScope scope(samhost::KC_GEMM, st);
+    const i64 n = static_cast<i64>(M) * N;
+    relu_mask_kernel<<<blocks_for(n), 256, 0, st>>>(dY, relu_y, n);
+    SAM_CHECK_CUDA(cudaGetLastError());
+  }
+  if (dX) {
+    Gemm g{};
+    g.A = dY; g.ars = N; g.acs = 1;
+    g.B = W; g.brs = K; g.bcs = 1;
+    g.C = dX; g.crs = K;
+    g.M = M; g.N = K; g.K = N; g.alpha = 1.f;
+    TRY(t.gemm(g));
+  }
+  if (dW) {
+    Gemm g{};
+    g.A = dY; g.ars = 1; g.acs = N;
+    g.B = X; g.brs = K; g.bcs = 1;
+    g.C = dW; g.crs = K; g.accumulate = 1;
+    g.M = N; g.N = K; g.K = M; g.alpha = 1.f;
+    if (M > 4096) { g.kchunk = 2048; g.splits = (M + g.kchunk - 1) / g.kchunk; }
+    TRY(t.gemm(g));
+  }
+  if (db) TRY(t.colsum(dY, N, M, N, N, db));
+  return 0;
+}
+
+// d_low [maps, low, low] (+)= adjoint of postprocess_masks applied to d_out [maps, out_h, out_w];  tmp [maps, in_h, in_w] fp32
+int samk_postprocess_backward(const float* d_out, int maps, int low, int img, int in_h, int in_w, int out_h, int out_w, float* tmp,
+                              float* d_low, cudaStream_t st) {
+  SAM_REQUIRE(d_out && tmp && d_low && maps >= 0, "postprocess_backward: NULL argument");
+  SAM_REQUIRE(low > 0 && img > 0 && in_h > 0 && in_w > 0 && in_h <= img && in_w <= img && out_h > 0 && out_w > 0,
+              "postprocess_backward: bad sizes");
+  if (maps == 0) return 0;
+  SAM_CHECK_CUDA(cudaMemsetAsync(tmp, 0, static_cast<size_t>(maps) * in_h * in_w * 4, st));
+  SAM_CHECK_CUDA(cudaMemsetAsync(d_low, 0, static_cast<size_t>(maps) * low * low * 4, st));
+  {
+    // adjoint of the second resampling: [in_h, in_w] (the crop of the img x img map) -> [out_h, out_w]
+    samhost::LaunchScope scope(samhost::KC_POSTPROCESS, st);
+    bilinear_bwd_kernel<<<blocks_for(static_cast<i64>(maps) * out_h * out_w), 256, 0, st>>>(
+        d_out, tmp, maps, out_h, out_w, in_h, in_w, static_cast<float>(in_h) / out_h, static_cast<float>(in_w) / out_w);
+    SAM_CHECK_CUDA(cudaGetLastError());
+  }
+  {
+    // adjoint of the first resampling [low, low] -> [img, img]; only the [in_h, in_w] crop of its output carries gradient
+    samhost::LaunchScope scope(samhost::KC_POSTPROCESS, st);
+    const float sc = static_cast<float>(low) / img;
+    bilinear_bwd_kernel<<<blocks_for(static_cast<i64>(maps) * in_h * in_w), 256, 0, st>>>(tmp, d_low, maps, in_h, in_w, low, low, sc, sc);
+    SAM_CHECK_CUDA(cudaGetLastError());
+  }
+  return 0;
+}

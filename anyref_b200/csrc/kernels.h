@@ -102,6 +102,21 @@ int samk_decoder_forward(const SamDecoderShape& s, const float* blob, const void
                          int n_images, const int* img_index, const void* sparse, int sparse_fmt, int n, int k,
                          const void* dense_vec, const void* dense_full, int dense_fmt, void* masks, void* iou, int out_fmt,
                          void* workspace, size_t workspace_bytes, cudaStream_t st);
+// Training path of the mask decoder (decoder_train.cu): forward that keeps its intermediates on a tape + backward
+size_t samk_decoder_train_workspace_bytes(const SamDecoderShape& s, int n, int k);
+int samk_decoder_train_forward(const SamDecoderShape& s, const float* blob, const void* image_embeddings, int emb_fmt, int n_images,
+                               const int* img_index, const float* sparse, int n, int k, const void* dense_vec, const void* dense_full,
+                               int dense_fmt, const void* image_pe, int pe_fmt, float* masks, float* iou, void* workspace,
+                               size_t workspace_bytes, void** tape_out, cudaStream_t st);
+int samk_decoder_backward(void* tape, const float* d_masks, const float* d_iou, float* d_weights, float* d_sparse, cudaStream_t st);
+void samk_decoder_tape_free(void* tape);
+size_t samk_linear_f32_scratch_bytes(int M, int N, int K);
+int samk_linear_f32_forward(const float* X, const float* W, const float* b, float* Y, int M, int N, int K, int relu_act, cudaStream_t st);
+int samk_linear_f32_backward(float* dY, const float* relu_y, const float* X, const float* W, float* dX, float* dW, float* db, int M, int N, int K,
+                             void* scratch, size_t scratch_bytes, cudaStream_t st);
+int samk_postprocess_backward(const float* d_out, int maps, int low, int img, int in_h, int in_w, int out_h, int out_w, float* tmp,
+                              float* d_low, cudaStream_t st);
+
 int samk_postprocess(const void* low, int low_fmt, int num_masks, int L, int S, int h_in, int w_in, int H, int W,
                      float* logits, uint8_t* binary, float threshold, cudaStream_t stream);
 int samk_postprocess_iou(const void* low, int low_fmt, int num_masks, int L, int S, int h_in, int w_in, int H, int W,

@@ -48,12 +48,18 @@ class SegProjection(nn.Sequential):
         return self._packed[1]
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError("SegProjection runs the inference path only (call under torch.no_grad()); "
-                                      "training of text_hidden_fcs is outside the ported scope (SURVEY 8f-4)")
         if not x.is_cuda:
             raise RuntimeError("SegProjection: anyref_b200 runs only on CUDA (sm_100a) tensors -- there is no CPU fallback")
         lead = x.shape[:-1]
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            # training (model/anyref.py:116-124, :395-401): fp32 linears with a backward (csrc/decoder_train.cu)
+            from .segment_anything._train import LinearF32Fn
+            a = x.reshape(-1, x.shape[-1])
+            if a.shape[0] == 0:
+                return x.new_zeros((*lead, self[2].out_features))
+            h = LinearF32Fn.apply(a, self[0].weight, self[0].bias, True)
+            y = LinearF32Fn.apply(h, self[2].weight, self[2].bias, False)
+            return y.to(x.dtype).reshape(*lead, self[2].out_features)
         dt = x.dtype if x.dtype in (torch.float16, torch.bfloat16) else torch.bfloat16
         w1, b1, w2, b2 = self._weights(dt)
         a = x.reshape(-1, x.shape[-1]).to(dt).contiguous()

@@ -189,3 +189,55 @@ def pack_decoder(dec, grid: int):
     if b.off != n:
         raise RuntimeError(f"decoder blob layout mismatch: packed {b.off}, library expects {n}")
     return shape, b.t
+
+
+def unpack_decoder_grads(dec, gblob: torch.Tensor) -> dict:
+    """Inverse of pack_decoder for the gradient blob of sam_decoder_backward: {id(parameter): gradient in the parameter's
+    own layout}.  Same walk as pack_decoder; the ConvTranspose2d weights go back to [in, out, dy, dx] and the four
+    per-sub-pixel copies of the first ConvTranspose2d bias are summed."""
+    out = {}
+    off = 0
+
+    def take(p, transform=None, numel=None):
+        nonlocal off
+        n = p.numel() if numel is None else numel
+        g = gblob[off:off + n]
+        off += n
+        out[id(p)] = transform(g) if transform is not None else g.reshape(p.shape)
+
+    def attn(a):
+        for lin in (a.q_proj, a.k_proj, a.v_proj, a.out_proj):
+            take(lin.weight); take(lin.bias)
+
+    def norm(ln):
+        take(ln.weight); take(ln.bias)
+
+    take(dec.iou_token.weight)
+    take(_unwrap(dec.mask_tokens).weight)
+    tr = dec.transformer
+    for layer in tr.layers:
+        attn(layer.self_attn); norm(layer.norm1)
+        attn(layer.cross_attn_token_to_image); norm(layer.norm2)
+        take(layer.mlp.lin1.weight); take(layer.mlp.lin1.bias)
+        take(layer.mlp.lin2.weight); take(layer.mlp.lin2.bias)
+        norm(layer.norm3); norm(layer.norm4)
+        attn(layer.cross_attn_image_to_token)
+    attn(tr.final_attn_token_to_image); norm(tr.norm_final_attn)
+    up = _unwrap(dec.output_upscaling)
+    cin, cout = up[0].weight.shape[0], up[0].weight.shape[1]
+    take(up[0].weight, lambda g: g.reshape(2, 2, cout, cin).permute(3, 2, 0, 1).contiguous())
+    take(up[0].bias, lambda g: g.reshape(4, cout).sum(0), numel=4 * cout)
+    norm(up[1])
+    cin1, cout1 = up[3].weight.shape[0], up[3].weight.shape[1]
+    take(up[3].weight, lambda g: g.reshape(2, 2, cout1, cin1).permute(3, 2, 0, 1).contiguous())
+    take(up[3].bias)
+    hyper = _unwrap(dec.output_hypernetworks_mlps)
+    for i in range(dec.num_mask_tokens):
+        for lin in hyper[i].layers:
+            take(lin.weight); take(lin.bias)
+    for lin in dec.iou_prediction_head.layers:
+        take(lin.weight); take(lin.bias)
+    if off != gblob.numel():
+        raise RuntimeError(f"decoder gradient blob layout mismatch: walked {off}, blob has {gblob.numel()}")
+    return out
+

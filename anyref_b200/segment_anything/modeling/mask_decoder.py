@@ -108,25 +108,25 @@ class MaskDecoder(nn.Module):
         """All `num_mask_tokens` masks [n,4,4g,4g] and IoU predictions [n,4] (mask_decoder.py:116-179)."""
         if torch.is_grad_enabled() and (sparse_prompt_embeddings.requires_grad or
                                         (self.training and any(p.requires_grad for p in self.parameters()))):
-            # model/anyref.py:108-113 puts the decoder in train() with requires_grad=True for fine-tuning; returning
-            # tensors without a graph there would silently train nothing
-            raise NotImplementedError("MaskDecoder runs the inference path only: call it in eval() mode or under "
-                                      "torch.no_grad(); the decoder backward is SURVEY 8(f)-4, not built yet")
+            # model/anyref.py:108-113 fine-tunes the decoder (train(), requires_grad=True) with the encoders frozen:
+            # the fp32 training path keeps its intermediates and has a backward (csrc/decoder_train.cu).  In eval()
+            # with constant prompts the fused inference path runs and returns tensors without a graph
+            return self._predict_masks_train(image_embeddings, image_pe, sparse_prompt_embeddings,
+                                             dense_prompt_embeddings, image_index)
         with torch.no_grad():
             return self._predict_masks(image_embeddings, image_pe, sparse_prompt_embeddings, dense_prompt_embeddings,
                                        image_index)
 
-    @_lib.device_scoped
-    def _predict_masks(self, image_embeddings, image_pe, sparse_prompt_embeddings, dense_prompt_embeddings, image_index):
+    def _check_inputs(self, image_embeddings, image_pe, sparse_prompt_embeddings, dense_prompt_embeddings, image_index):
+        """Shared argument checks -> (emb, pe, sparse, dense_vec, dense_full, image_index), all contiguous."""
         _runtime.require_cuda(image_embeddings, "MaskDecoder")
-        lib = _lib.load()
         emb = image_embeddings.contiguous()
         pe = image_pe.contiguous()
         _, Cc, g, g2 = emb.shape
         if g != g2 or Cc != self.transformer_dim or pe.shape[1:] != emb.shape[1:]:
             raise ValueError(f"bad embedding shapes {tuple(emb.shape)} / {tuple(pe.shape)}")
         sparse = sparse_prompt_embeddings.contiguous()
-        n, k = sparse.shape[0], sparse.shape[1]
+        n = sparse.shape[0]
         dense = dense_prompt_embeddings
         if dense.shape[0] != n:
             raise ValueError("dense_prompt_embeddings batch must equal the number of prompts")
@@ -135,13 +135,41 @@ class MaskDecoder(nn.Module):
             dense_vec = dense      # no_mask_embed broadcast (prompt_encoder.py:181-184): pass the [C] vector
         else:
             dense_full = dense.contiguous()
-            dense = dense_full
         if image_index is not None:
             if image_index.dtype != torch.int32 or not image_index.is_cuda or image_index.numel() != n:
                 raise ValueError("image_index must be an int32 CUDA tensor with one entry per prompt")
             image_index = image_index.contiguous()
         elif emb.shape[0] != 1:
             raise ValueError("image_index is required when several image embeddings are given")
+        return emb, pe, sparse, dense_vec, dense_full, image_index
+
+    def _predict_masks_train(self, image_embeddings, image_pe, sparse_prompt_embeddings, dense_prompt_embeddings,
+                             image_index):
+        """fp32 forward with a graph: gradients for this module's parameters and for sparse_prompt_embeddings.  Image
+        embeddings, dense prompt embeddings and image_pe are constants here, as in the reference's fine-tuning where
+        the image encoder and the prompt encoder are frozen (model/anyref.py:107-113); asking for their gradient
+        raises instead of silently returning none.  Outputs are fp32 whatever the embedding dtype."""
+        for name, t in (("image_embeddings", image_embeddings), ("dense_prompt_embeddings", dense_prompt_embeddings),
+                        ("image_pe", image_pe)):
+            if t.requires_grad:
+                raise NotImplementedError(f"MaskDecoder training path: no gradient is produced for {name} (frozen in "
+                                          "model/anyref.py:107-113); detach it")
+        from .._train import DecoderTrainFn
+        emb, pe, sparse, dense_vec, dense_full, image_index = self._check_inputs(
+            image_embeddings, image_pe, sparse_prompt_embeddings, dense_prompt_embeddings, image_index)
+        params = tuple(self.parameters())
+        return DecoderTrainFn.apply(self, emb.detach(), pe.detach(), sparse,
+                                    dense_vec.detach() if dense_vec is not None else None,
+                                    dense_full.detach() if dense_full is not None else None, image_index, *params)
+
+    @_lib.device_scoped
+    def _predict_masks(self, image_embeddings, image_pe, sparse_prompt_embeddings, dense_prompt_embeddings, image_index):
+        lib = _lib.load()
+        emb, pe, sparse, dense_vec, dense_full, image_index = self._check_inputs(
+            image_embeddings, image_pe, sparse_prompt_embeddings, dense_prompt_embeddings, image_index)
+        g = emb.shape[-1]
+        n, k = sparse.shape[0], sparse.shape[1]
+        dense = dense_vec if dense_vec is not None else dense_full
         shape, blob, (_derived_keep, derived_ptr) = self._weights(g, pe)
         out_dtype = emb.dtype
         masks = torch.empty((n, self.num_mask_tokens, 4 * g, 4 * g), device=emb.device, dtype=out_dtype)

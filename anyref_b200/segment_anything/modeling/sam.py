@@ -65,15 +65,24 @@ class Sam(nn.Module):
             outputs.append({"masks": binary.view(torch.bool), "iou_predictions": iou, "low_res_logits": low_res})
         return outputs
 
-    @_lib.device_scoped
-    @torch.no_grad()
     def postprocess_masks(self, masks: torch.Tensor, input_size: Tuple[int, ...], original_size: Tuple[int, ...],
                           return_binary: bool = False):
         """[n,C,L,L] low-res logits -> fp32 logits [n,C,H,W] (sam.py:137-172).  With return_binary=True also returns
-        the uint8 mask `logits > mask_threshold` produced in the same pass."""
+        the uint8 mask `logits > mask_threshold` produced in the same pass.  When `masks` carries a graph (the mask
+        loss of model/anyref.py:424-450 is taken on the post-processed logits) the result does too."""
         _runtime.require_cuda(masks, "Sam.postprocess_masks")
         if masks.dim() != 4 or masks.shape[2] != masks.shape[3]:
             raise ValueError(f"expected masks [n,C,L,L], got {tuple(masks.shape)}")
+        if torch.is_grad_enabled() and masks.requires_grad:
+            from .._train import PostprocessFn
+            out = PostprocessFn.apply(masks, masks.shape[2], self.image_encoder.img_size, int(input_size[0]),
+                                      int(input_size[1]), int(original_size[0]), int(original_size[1]))
+            return (out, (out.detach() > self.mask_threshold).to(torch.uint8)) if return_binary else out
+        return self._postprocess_masks(masks, input_size, original_size, return_binary)
+
+    @_lib.device_scoped
+    @torch.no_grad()
+    def _postprocess_masks(self, masks, input_size, original_size, return_binary):
         m = masks.contiguous()
         n, ch, L, _ = m.shape
         h_in, w_in = int(input_size[0]), int(input_size[1])

@@ -194,6 +194,47 @@ int sam_decoder_forward(const SamDecoderShape* shape, const float* weights, cons
                         void* stream);
 
 /*
+ * Training path of the mask decoder.  AnyRef fine-tunes mask_decoder.* with the encoders frozen
+ * (model/anyref.py:108-113); the loss reaches it through mask_decoder -> postprocess_masks (model/anyref.py:406-450).
+ * sam_decoder_train_forward is the same function as sam_decoder_forward (all arithmetic fp32; masks / iou fp32 out;
+ * sparse fp32; image_pe is passed directly, no `derived` buffer) but keeps every intermediate in `workspace` and
+ * returns a tape.  sam_decoder_backward consumes the tape once:
+ *   d_masks   [n, num_mask_tokens, 4g, 4g] fp32 or NULL;   d_iou [n, num_mask_tokens] fp32 or NULL
+ *   d_weights fp32, layout of `weights`: the gradient is ADDED (zero it for a fresh gradient)
+ *   d_sparse  [n, k, C] fp32, overwritten (may be NULL)
+ * Image embeddings, dense prompt embeddings and image_pe receive no gradient (frozen in the reference).  The workspace
+ * must stay untouched between the two calls; sam_decoder_tape_free releases the host-side tape (also after backward).
+ */
+size_t sam_decoder_train_workspace_bytes(const SamDecoderShape* shape, int n, int k);
+int sam_decoder_train_forward(const SamDecoderShape* shape, const float* weights, const void* image_embeddings,
+                              int emb_fmt, int n_images, const int* img_index, const float* sparse, int n, int k,
+                              const void* dense_vec, const void* dense_full, int dense_fmt, const void* image_pe,
+                              int pe_fmt, float* masks, float* iou, void* workspace, size_t workspace_bytes,
+                              void** tape, void* stream);
+int sam_decoder_backward(void* tape, const float* d_masks, const float* d_iou, float* d_weights, float* d_sparse,
+                         void* stream);
+void sam_decoder_tape_free(void* tape);
+
+/*
+ * fp32 nn.Linear forward / backward for text_hidden_fcs in training (model/anyref.py:116-124, :395-401):
+ * Y [M, N] = X [M, K] . W[N, K]^T + b (optionally ReLU);  dX = dY . W (overwritten, may be NULL), dW += dY^T . X,
+ * db += column sums of dY.  With relu_y (the output of a forward that fused the ReLU) dY is first masked IN PLACE with
+ * (relu_y > 0).  scratch: sam_linear_f32_scratch_bytes(M, N, K) bytes.
+ */
+size_t sam_linear_f32_scratch_bytes(int M, int N, int K);
+int sam_linear_f32_forward(const float* X, const float* W, const float* b, float* Y, int M, int N, int K, int relu,
+                           void* stream);
+int sam_linear_f32_backward(float* dY, const float* relu_y, const float* X, const float* W, float* dX, float* dW,
+                            float* db, int M, int N, int K, void* scratch, size_t scratch_bytes, void* stream);
+
+/*
+ * Adjoint of sam_postprocess_masks (the loss of model/anyref.py:432-450 is taken on the post-processed logits):
+ * d_low [num_masks, L, L] fp32 (overwritten) from d_logits [num_masks, H, W] fp32; tmp: num_masks * h_in * w_in floats.
+ */
+int sam_postprocess_masks_backward(const float* d_logits, int num_masks, int L, int S, int h_in, int w_in, int H, int W,
+                                   float* tmp, float* d_low, void* stream);
+
+/*
  * Sam.postprocess_masks (sam.py:159-172) fused: bilinear L x L -> S x S, crop [:h_in, :w_in], bilinear -> H x W, both
  * align_corners=False, no antialias.  low [num_masks, L, L] (low_fmt); logits fp32 [num_masks, H, W] and/or binary
  * uint8 [num_masks, H, W] = logits > threshold (Sam.mask_threshold, sam.py:19).  Either output may be NULL.

@@ -45,7 +45,7 @@ def test_sizes_and_errors_without_gpu(lib):
     from anyref_b200 import _lib
 
     L = _lib.load()
-    assert L.sam_abi_version() == 3
+    assert L.sam_abi_version() == 4
     enc = _lib.SamEncoderShape(embed_dim=1280, depth=32, heads=16, mlp_dim=5120, img=1024, patch=16, window=14,
                                out_chans=256, fmt=1, global_mask=0, tap_block=-1, tap_out=None)
     n16 = L.sam_encoder_w16_elems(ctypes.byref(enc))
@@ -75,6 +75,21 @@ def test_sizes_and_errors_without_gpu(lib):
     assert rc != 0 and b"NULL" in L.sam_last_error()
     rc = L.sam_resize_u8(None, 10, 10, 3, None, None, 20, 20, None, None, 0, None, None, 0, None)
     assert rc != 0 and b"resize" in L.sam_last_error()
+    # training path: the workspace covers activations + gradients + scratch and grows with the number of prompts
+    t1 = L.sam_decoder_train_workspace_bytes(ctypes.byref(dec), 1, 1)
+    t4 = L.sam_decoder_train_workspace_bytes(ctypes.byref(dec), 4, 1)
+    assert t1 > 64 << 20 and 3 * t1 < t4 < 5 * t1
+    tape = ctypes.c_void_p()
+    rc = L.sam_decoder_train_forward(ctypes.byref(dec), None, None, 2, 1, None, None, 1, 1, None, None, 2, None, 2, None, None, None,
+                                     0, ctypes.byref(tape), None)
+    assert rc != 0 and b"NULL" in L.sam_last_error() and not tape.value
+    rc = L.sam_decoder_backward(None, None, None, None, None, None)
+    assert rc != 0 and b"tape" in L.sam_last_error()
+    L.sam_decoder_tape_free(None)
+    rc = L.sam_postprocess_masks_backward(None, 1, 256, 1024, 1024, 1024, 1024, 1024, None, None, None)
+    assert rc != 0 and b"postprocess_backward" in L.sam_last_error()
+    rc = L.sam_linear_f32_backward(None, None, None, None, None, None, None, 1, 1, 1, None, 0, None)
+    assert rc != 0 and b"linear_f32_backward" in L.sam_last_error()
     bad = _lib.SamDecoderShape(C=192, heads=8, depth=2, mlp_dim=2048, num_mask_tokens=4, iou_hidden=256, grid=64)
     buf = ctypes.create_string_buffer(1 << 12)                       # any non-NULL host pointer: refused before use
     ptr = ctypes.cast(buf, ctypes.c_void_p)

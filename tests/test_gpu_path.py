@@ -708,8 +708,8 @@ def test_seg_head_from_hidden_states_vs_oracle(tiny):
     # no [SEG] token: one zero mask per image (model/anyref.py:762-764)
     none = head(hidden.cuda(), (torch.empty(0, dtype=torch.long, device="cuda"),) * 2, tiny["x"].cuda(), sizes, origs)
     assert len(none) == 2 and none[0].shape == (1, 1024, 1024) and float(none[0].abs().max()) == 0.0
-    with pytest.raises(NotImplementedError):
-        fcs[0](torch.randn(1, H, device="cuda"))    # grad enabled + trainable parameters: training is out of scope
+    y = fcs[0](torch.randn(1, H, device="cuda"))    # grad enabled + trainable parameters: the fp32 training route
+    assert y.requires_grad and y.shape == (1, 256)
 
 
 @pytest.mark.parametrize("dt,tol", [(torch.float16, 2e-3), (torch.bfloat16, 1e-2)])

@@ -1,0 +1,304 @@
+"""Training path: the mask decoder's fp32 forward-with-tape and its backward, the adjoint of
+postprocess_masks, and text_hidden_fcs in training -- gradients compared with PyTorch autograd run over the ORACLE
+(oracle/sam_oracle.py is the bit-identical restatement of the reference modules, tests/test_oracle_vs_reference.py) on the
+same device in FLOAT64.  fp64 is the referee because fp32 autograd over the reference modules is itself only good to
+~1e-3 on some tensors (tools/gpu_train_diag.py: the [SEG] embedding gradient of one prompt is 1.3e-3 off the fp64 value
+with stock PyTorch, 8e-7 with this path).  Tolerances:
+  forward masks / iou       max-abs <= 2e-5 of the logit scale vs the fp32 oracle (same bar as the inference decoder)
+  every gradient tensor     relative Frobenius error <= 5e-5 vs the fp64 oracle (tensors whose reference gradient is
+                            exactly zero must be exactly zero; the k_proj biases, whose gradient is mathematically
+                            zero, are only bounded)
+  postprocess adjoint       relative Frobenius error <= 1e-5 (float atomics on both sides)
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from anyref_b200.synthetic import CONFIGS, synthetic_seg_embeddings, synthetic_state_dict
+from oracle import sam_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_fro(got, ref):
+    got, ref = got.double(), ref.double()
+    return ((got - ref).norm() / ref.norm().clamp_min(1e-30)).item()
+
+
+@pytest.fixture(scope="module")
+def setup():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from anyref_b200.segment_anything import build_sam_from_config
+
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    cfg = CONFIGS["vit_tiny80"]
+    sd = synthetic_state_dict(cfg)
+    sam = build_sam_from_config(cfg)
+    sam.load_state_dict(sd, strict=True)
+    sam = sam.cuda()
+    for p in sam.parameters():
+        p.requires_grad_(False)
+    for p in sam.mask_decoder.parameters():       # model/anyref.py:108-113
+        p.requires_grad_(True)
+    sam.mask_decoder.train()
+    g = torch.Generator().manual_seed(5)
+    emb = (torch.randn(2, 256, 64, 64, generator=g) * 0.5).cuda()
+    with torch.no_grad():
+        pe = O.dense_pe({k: v.cuda() for k, v in sd.items()}, cfg)
+    return {"cfg": cfg, "sd": sd, "sam": sam, "emb": emb, "pe": pe}
+
+
+def oracle_sd(sd, trainable_prefix="mask_decoder.", dtype=torch.float64):
+    out = {}
+    for k, v in sd.items():
+        t = v.detach().clone().cuda().to(dtype)
+        if k.startswith(trainable_prefix):
+            t.requires_grad_(True)
+        out[k] = t
+    return out
+
+
+def compare_param_grads(sam, osd, tol=5e-5):
+    """Relative Frobenius error per tensor.  The k_proj biases have a mathematically ZERO gradient (a constant added to
+    every key's score cancels in the softmax): both sides hold rounding noise there, which is only bounded (1e-6 of the
+    largest gradient norm of the decoder).  The same quantity is the floor of every denominator."""
+    refs = {name: osd["mask_decoder." + name].grad for name, _ in sam.mask_decoder.named_parameters()}
+    gmax = max(float(r.double().norm()) for r in refs.values() if r is not None)
+    worst = 0.0
+    checked = 0
+    for name, p in sam.mask_decoder.named_parameters():
+        ref, got = refs[name], p.grad
+        if ref is None or float(ref.abs().max()) == 0.0:
+            assert got is None or float(got.abs().max()) == 0.0, f"{name}: reference gradient is zero"
+            continue
+        assert got is not None, f"{name}: no gradient"
+        assert got.shape == ref.shape, name
+        if name.endswith("k_proj.bias"):
+            assert float(ref.double().norm()) < 1e-6 * gmax and float(got.double().norm()) < 1e-6 * gmax, name
+            continue
+        e = float((got.double() - ref.double()).norm()) / (float(ref.double().norm()) + 1e-6 * gmax)
+        worst = max(worst, e)
+        assert e < tol, f"{name}: rel-Fro {e:.3e}"
+        checked += 1
+    return worst, checked
+
+
+def zero_grads(sam):
+    for p in sam.parameters():
+        p.grad = None
+
+
+def test_train_forward_matches_oracle_and_inference(setup):
+    sam, cfg = setup["sam"], setup["cfg"]
+    osd = {k: v.cuda() for k, v in setup["sd"].items()}
+    seg = synthetic_seg_embeddings(1, 3, seed=2)[0].cuda()
+    with torch.no_grad():
+        sp_o, de_o = O.prompt_encoder(osd, cfg, text_embeds=seg)
+        want_m, want_i = O.mask_decoder(osd, cfg, setup["emb"][:1], setup["pe"], sp_o, de_o, True)
+    sparse, dense = sam.prompt_encoder(points=None, boxes=None, masks=None, text_embeds=seg)
+    masks, iou = sam.mask_decoder(image_embeddings=setup["emb"][:1], image_pe=setup["pe"],
+                                  sparse_prompt_embeddings=sparse, dense_prompt_embeddings=dense, multimask_output=True)
+    assert masks.requires_grad and iou.requires_grad and masks.dtype == torch.float32
+    scale = float(want_m.abs().max())
+    assert float((masks.detach() - want_m).abs().max()) <= 2e-5 * max(scale, 1.0)
+    assert float((iou.detach() - want_i).abs().max()) <= 2e-5
+    sam.mask_decoder.eval()
+    with torch.no_grad():
+        inf_m, _ = sam.mask_decoder(image_embeddings=setup["emb"][:1], image_pe=setup["pe"],
+                                    sparse_prompt_embeddings=sparse.detach(), dense_prompt_embeddings=dense,
+                                    multimask_output=True)
+    sam.mask_decoder.train()
+    assert float((inf_m - masks.detach()).abs().max()) <= 4e-5 * max(scale, 1.0)
+
+
+@pytest.mark.parametrize("n,k", [(1, 1), (3, 1), (2, 3)])
+def test_decoder_gradients_match_autograd_on_the_oracle(setup, n, k):
+    """All four mask tokens and the IoU head enter the loss (two calls: multimask False and True, so the gradients of
+    two tapes accumulate into .grad), with random cotangents."""
+    sam, cfg = setup["sam"], setup["cfg"]
+    zero_grads(sam)
+    osd = oracle_sd(setup["sd"])
+    g = torch.Generator().manual_seed(100 + 10 * n + k)
+    sparse0 = torch.randn(n, k, 256, generator=g).cuda()
+    dense = osd["prompt_encoder.no_mask_embed.weight"].detach().reshape(1, -1, 1, 1).expand(n, -1, 64, 64)
+    dense32 = dense.float()
+    emb, pe = setup["emb"][1:2], setup["pe"]
+
+    def loss_of(fn, sparse):
+        total = 0.0
+        gg = torch.Generator().manual_seed(7)
+        for multi in (False, True):
+            m, i = fn(sparse, multi)
+            rm = torch.randn(m.shape, generator=gg).cuda().to(m.dtype)
+            ri = torch.randn(i.shape, generator=gg).cuda().to(m.dtype)
+            total = total + (m * rm).sum() / 256.0 + (i * ri).sum()
+        return total
+
+    s_ref = sparse0.double().requires_grad_(True)
+    loss_ref = loss_of(lambda sp, multi: O.mask_decoder(osd, cfg, emb.double(), pe.double(), sp, dense, multi), s_ref)
+    loss_ref.backward()
+    s_got = sparse0.clone().requires_grad_(True)
+    loss_got = loss_of(lambda sp, multi: sam.mask_decoder(image_embeddings=emb, image_pe=pe, sparse_prompt_embeddings=sp,
+                                                          dense_prompt_embeddings=dense32, multimask_output=multi), s_got)
+    loss_got.backward()
+    assert abs(float(loss_got.detach()) - float(loss_ref.detach())) <= 1e-4 * max(1.0, abs(float(loss_ref.detach())))
+    assert rel_fro(s_got.grad, s_ref.grad) < 5e-5
+    worst, checked = compare_param_grads(sam, osd)
+    assert checked >= 95, checked        # every tensor of the decoder gets a gradient from this loss
+
+
+def test_batched_training_call_matches_per_image_calls(setup):
+    """forward_batched (prompts of several images in one call) in training: same gradients as the
+    reference's per-image loop (model/anyref.py:406-430)."""
+    sam, cfg = setup["sam"], setup["cfg"]
+    osd = oracle_sd(setup["sd"])
+    g = torch.Generator().manual_seed(9)
+    sparse0 = torch.randn(3, 1, 256, generator=g).cuda()
+    idx = torch.tensor([0, 1, 1], dtype=torch.int32, device="cuda")
+    dense = osd["prompt_encoder.no_mask_embed.weight"].detach().reshape(1, -1, 1, 1).expand(3, -1, 64, 64)
+    cot = torch.randn(3, 1, 256, 256, generator=g).cuda()
+    s_ref = sparse0.double().requires_grad_(True)
+    total = 0.0
+    for b, rows in ((0, [0]), (1, [1, 2])):
+        m, _ = O.mask_decoder(osd, cfg, setup["emb"][b:b + 1].double(), setup["pe"].double(), s_ref[rows], dense[rows], False)
+        total = total + (m * cot[rows].double()).sum()
+    total.backward()
+    zero_grads(sam)
+    s_got = sparse0.clone().requires_grad_(True)
+    m, _ = sam.mask_decoder.forward_batched(setup["emb"], setup["pe"], s_got, dense.float(), idx, False)
+    (m * cot).sum().backward()
+    assert rel_fro(s_got.grad, s_ref.grad) < 5e-5
+    compare_param_grads(sam, osd)
+
+
+@pytest.mark.parametrize("inp,orig", [((1024, 1024), (1024, 1024)), ((1024, 683), (640, 427)), ((768, 1024), (480, 640)),
+                                      ((512, 1024), (37, 61))])
+def test_postprocess_adjoint_matches_autograd(setup, inp, orig):
+    sam = setup["sam"]
+    g = torch.Generator().manual_seed(3)
+    low0 = torch.randn(2, 3, 256, 256, generator=g).cuda()
+    cot = torch.randn(2, 3, *orig, generator=g).cuda()
+    a = low0.clone().requires_grad_(True)
+    O.postprocess_masks(a, inp, orig).mul(cot).sum().backward()
+    b = low0.clone().requires_grad_(True)
+    out = sam.postprocess_masks(b, input_size=inp, original_size=orig)
+    assert out.requires_grad
+    out.mul(cot).sum().backward()
+    assert rel_fro(b.grad, a.grad) < 1e-5
+
+
+def test_text_hidden_fcs_training_gradients(setup):
+    from anyref_b200.seg_head import build_text_hidden_fcs
+
+    H = 512
+    fcs = build_text_hidden_fcs(H, 256).cuda()
+    ref = torch.nn.Sequential(torch.nn.Linear(H, H), torch.nn.ReLU(), torch.nn.Linear(H, 256)).cuda()
+    ref[0].load_state_dict(fcs[0][0].state_dict())
+    ref[2].load_state_dict(fcs[0][2].state_dict())
+    g = torch.Generator().manual_seed(1)
+    x0 = torch.randn(5, H, generator=g).cuda()
+    cot = torch.randn(5, 256, generator=g).cuda()
+    xa = x0.clone().requires_grad_(True)
+    (ref(xa) * cot).sum().backward()
+    xb = x0.clone().requires_grad_(True)
+    y = fcs[0](xb)
+    assert float((y.detach() - ref(x0).detach()).abs().max()) < 1e-4
+    (y * cot).sum().backward()
+    assert rel_fro(xb.grad, xa.grad) < 1e-5
+    for mine, theirs in ((fcs[0][0], ref[0]), (fcs[0][2], ref[2])):
+        assert rel_fro(mine.weight.grad, theirs.weight.grad) < 1e-5
+        assert rel_fro(mine.bias.grad, theirs.bias.grad) < 1e-5
+
+
+def dice_loss(inputs, targets, num_masks):
+    """model/anyref.py:19-46"""
+    inputs = inputs.sigmoid().flatten(1, 2)
+    targets = targets.flatten(1, 2)
+    numerator = 2 * (inputs * targets).sum(-1)
+    denominator = inputs.sum(-1) + targets.sum(-1)
+    return (1 - (numerator + 1) / (denominator + 1)).sum() / num_masks
+
+
+def sigmoid_ce_loss(inputs, targets, num_masks):
+    """model/anyref.py:50-67"""
+    loss = F.binary_cross_entropy_with_logits(inputs, targets, reduction="none")
+    return loss.flatten(1, 2).mean(1).sum() / (num_masks + 1e-8)
+
+
+def test_training_step_like_the_reference(setup):
+    """The mask branch of AnyRefForCausalLM.model_forward (model/anyref.py:395-450): text_hidden_fcs -> prompt encoder ->
+    mask decoder -> postprocess_masks -> BCE + dice, back-propagated into the decoder, text_hidden_fcs and the LLM's
+    hidden states.  Reference side: the same loop over the oracle with autograd."""
+    from anyref_b200.seg_head import build_text_hidden_fcs
+
+    sam, cfg = setup["sam"], setup["cfg"]
+    zero_grads(sam)
+    osd = oracle_sd(setup["sd"])
+    H = 384
+    fcs = build_text_hidden_fcs(H, 256).cuda()
+    ref_fcs = torch.nn.Sequential(torch.nn.Linear(H, H), torch.nn.ReLU(), torch.nn.Linear(H, 256)).cuda()
+    ref_fcs[0].load_state_dict(fcs[0][0].state_dict())
+    ref_fcs[2].load_state_dict(fcs[0][2].state_dict())
+    ref_fcs = ref_fcs.double()
+    g = torch.Generator().manual_seed(21)
+    hidden0 = torch.randn(3, H, generator=g).cuda()
+    seg_batch = torch.tensor([0, 1, 1])
+    sizes, origs = [(1024, 1024), (1024, 683)], [(512, 512), (640, 427)]
+    gts = [(torch.rand(int((seg_batch == b).sum()), *origs[b], generator=g) > 0.6).float().cuda() for b in range(2)]
+
+    def step(project, prompt, decode, post, hidden):
+        pred = project(hidden)
+        ce = dice = 0.0
+        num = 0
+        for b in range(2):
+            e = pred[seg_batch == b].unsqueeze(1)
+            sparse, dense = prompt(e)
+            low, _ = decode(b, sparse.to(e.dtype), dense)
+            pm = post(low, sizes[b], origs[b]).squeeze(1)
+            gt = gts[b].to(pm.dtype)
+            ce = ce + sigmoid_ce_loss(pm, gt, gt.shape[0]) * gt.shape[0]
+            dice = dice + dice_loss(pm, gt, gt.shape[0]) * gt.shape[0]
+            num += gt.shape[0]
+        return 2.0 * ce / (num + 1e-8) + 0.5 * dice / (num + 1e-8)
+
+    ha = hidden0.double().requires_grad_(True)
+    loss_ref = step(ref_fcs, lambda e: O.prompt_encoder(osd, cfg, text_embeds=e),
+                    lambda b, sp, de: O.mask_decoder(osd, cfg, setup["emb"][b:b + 1].double(), setup["pe"].double(), sp, de, False),
+                    lambda low, s, o: O.postprocess_masks(low, s, o), ha)
+    loss_ref.backward()
+    hb = hidden0.clone().requires_grad_(True)
+    loss_got = step(fcs[0], lambda e: sam.prompt_encoder(points=None, boxes=None, masks=None, text_embeds=e),
+                    lambda b, sp, de: sam.mask_decoder(image_embeddings=setup["emb"][b:b + 1], image_pe=setup["pe"],
+                                                       sparse_prompt_embeddings=sp, dense_prompt_embeddings=de,
+                                                       multimask_output=False),
+                    lambda low, s, o: sam.postprocess_masks(low, input_size=s, original_size=o), hb)
+    loss_got.backward()
+    assert abs(float(loss_got.detach()) - float(loss_ref.detach())) <= 1e-5 * abs(float(loss_ref.detach()))
+    assert rel_fro(hb.grad, ha.grad) < 5e-5
+    for mine, theirs in ((fcs[0][0], ref_fcs[0]), (fcs[0][2], ref_fcs[2])):
+        assert rel_fro(mine.weight.grad, theirs.weight.grad) < 5e-5
+        assert rel_fro(mine.bias.grad, theirs.bias.grad) < 5e-5
+    # hypernetwork MLPs 1..3 and the IoU head are not reached by this loss: exactly zero / absent on both sides
+    worst, checked = compare_param_grads(sam, osd)
+    assert checked >= 80
+
+
+def test_tape_is_single_use_and_released(setup):
+    sam = setup["sam"]
+    sparse = torch.randn(1, 1, 256, device="cuda", requires_grad=True)
+    dense = sam.prompt_encoder.no_mask_embed.weight.detach().reshape(1, -1, 1, 1).expand(1, -1, 64, 64)
+    m, _ = sam.mask_decoder(image_embeddings=setup["emb"][:1], image_pe=setup["pe"], sparse_prompt_embeddings=sparse,
+                            dense_prompt_embeddings=dense, multimask_output=False)
+    loss = m.sum()
+    loss.backward(retain_graph=True)
+    with pytest.raises(RuntimeError, match="already been consumed"):
+        loss.backward()
+    # a forward whose graph is dropped without backward frees its tape with the graph
+    before = torch.cuda.memory_allocated()
+    m2, _ = sam.mask_decoder(image_embeddings=setup["emb"][:1], image_pe=setup["pe"], sparse_prompt_embeddings=sparse,
+                             dense_prompt_embeddings=dense, multimask_output=False)
+    assert torch.cuda.memory_allocated() > before + (64 << 20)
+    del m2, _
+    assert torch.cuda.memory_allocated() < before + (32 << 20)

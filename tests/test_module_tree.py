@@ -63,26 +63,30 @@ def test_prompt_encoder_text_embeds_plumbing():
         sam.preprocess(torch.zeros(3, 8, 8))
 
 
-def test_decoder_refuses_to_train_silently():
+def test_decoder_training_route_and_frozen_inputs():
     """model/anyref.py:108-113, :413-429 fine-tunes the decoder (train() + requires_grad) and back-propagates into the
-    [SEG] embedding.  The CUDA decoder has no backward yet: it must say so instead of returning tensors
-    without a graph; in eval() mode or under no_grad it goes on (and then fails on CPU tensors: no CPU fallback)."""
+    [SEG] embedding: those calls take the training path (csrc/decoder_train.cu), everything else the fused inference
+    path.  Both are CUDA-only (no CPU fallback), and the training path refuses to pretend it has a gradient for the
+    inputs the reference keeps frozen."""
     sam = build_sam_from_config(CONFIGS["vit_tiny80"])
     emb, pe = torch.zeros(1, 256, 64, 64), torch.zeros(1, 256, 64, 64)
     text = torch.randn(2, 1, 256)
     sparse, dense = sam.prompt_encoder(points=None, boxes=None, masks=None, text_embeds=text)
-    call = dict(image_embeddings=emb, image_pe=pe, dense_prompt_embeddings=dense, multimask_output=False)
+    sparse, dense = sparse.detach(), dense.detach()
+    call = dict(image_pe=pe, dense_prompt_embeddings=dense, multimask_output=False)
     sam.mask_decoder.train()
-    with pytest.raises(NotImplementedError, match="inference path only"):
-        sam.mask_decoder(sparse_prompt_embeddings=sparse, **call)
-    sam.mask_decoder.eval()
-    with pytest.raises(NotImplementedError, match="inference path only"):
-        sam.mask_decoder(sparse_prompt_embeddings=sparse.clone().requires_grad_(True), **call)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
-        sam.mask_decoder(sparse_prompt_embeddings=sparse, **call)
+        sam.mask_decoder(image_embeddings=emb, sparse_prompt_embeddings=sparse, **call)
+    with pytest.raises(NotImplementedError, match="no gradient is produced for image_embeddings"):
+        sam.mask_decoder(image_embeddings=emb.clone().requires_grad_(True), sparse_prompt_embeddings=sparse, **call)
+    sam.mask_decoder.eval()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        sam.mask_decoder(image_embeddings=emb, sparse_prompt_embeddings=sparse.clone().requires_grad_(True), **call)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        sam.mask_decoder(image_embeddings=emb, sparse_prompt_embeddings=sparse, **call)
     sam.mask_decoder.train()
     with torch.no_grad(), pytest.raises(RuntimeError, match="no CPU fallback"):
-        sam.mask_decoder(sparse_prompt_embeddings=sparse, **call)
+        sam.mask_decoder(image_embeddings=emb, sparse_prompt_embeddings=sparse, **call)
 
 
 @pytest.mark.parametrize("name", ["vit_tiny80", "vit_h"])
