@@ -92,21 +92,33 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const Gemm g) {
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  // per-thread slots of the tile loads (4 of A, 4 of B), fixed over the k loop
+  int ai[4], ak[4], bj[4], bk[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int idx = tid + r * 256;
+    if (a_kfast) { ak[r] = idx & (GK - 1); ai[r] = idx >> 4; } else { ai[r] = idx & (GT - 1); ak[r] = idx >> 6; }
+    if (b_kfast) { bk[r] = idx & (GK - 1); bj[r] = idx >> 4; } else { bj[r] = idx & (GT - 1); bk[r] = idx >> 6; }
+  }
+  float ra[4], rb[4];
+  auto fetch = [&](int kk) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int gi = m0 + ai[r], gka = kk + ak[r];
+      ra[r] = (gi < g.M && gka < k1) ? A[gi * g.ars + gka * g.acs] : 0.f;
+      const int gj = n0 + bj[r], gkb = kk + bk[r];
+      rb[r] = (gj < g.N && gkb < k1) ? B[gkb * g.brs + gj * g.bcs] : 0.f;
+    }
+  };
+  fetch(k0);
   for (int kk = k0; kk < k1; kk += GK) {
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-      const int idx = tid + r * 256;
-      int i, k;
-      if (a_kfast) { k = idx & (GK - 1); i = idx >> 4; } else { i = idx & (GT - 1); k = idx >> 6; }
-      int gi = m0 + i, gk = kk + k;
-      As[k][i] = (gi < g.M && gk < k1) ? A[gi * g.ars + gk * g.acs] : 0.f;
-      int j;
-      if (b_kfast) { k = idx & (GK - 1); j = idx >> 4; } else { j = idx & (GT - 1); k = idx >> 6; }
-      const int gj = n0 + j;
-      gk = kk + k;
-      Bs[k][j] = (gj < g.N && gk < k1) ? B[gk * g.brs + gj * g.bcs] : 0.f;
+      As[ak[r]][ai[r]] = ra[r];
+      Bs[bk[r]][bj[r]] = rb[r];
     }
     __syncthreads();
+    if (kk + GK < k1) fetch(kk + GK);   // the next tile's global loads fly behind this tile's arithmetic
 #pragma unroll
     for (int k = 0; k < GK; ++k) {
       const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
@@ -517,7 +529,18 @@ struct Tape {
     if (g.nbatch <= 0) { g.nbatch = 1; }
     if (g.nb2 <= 0) g.nb2 = 1;
     if (g.bias_mod <= 0) g.bias_mod = g.N;
-    if (g.splits <= 1) { g.splits = 1; g.kchunk = g.K; }
+    // few output tiles + a long reduction (weight gradients, attention over 4096 pixels): split K so that ~2 CTAs per SM
+    // exist; the partials are folded in index order (deterministic)
+    const i64 tiles = static_cast<i64>((g.M + GT - 1) / GT) * ((g.N + GT - 1) / GT) * g.nbatch;
+    g.splits = 1;
+    g.kchunk = g.K;
+    if (tiles < 148 && g.K >= 256) {
+      int want = static_cast<int>(std::min<i64>((296 + tiles - 1) / tiles, g.K / 64));
+      if (want > 1) {
+        g.kchunk = (((g.K + want - 1) / want) + GK - 1) / GK * GK;
+        g.splits = (g.K + g.kchunk - 1) / g.kchunk;
+      }
+    }
     if (g.splits > 1) g.partial = scratch(static_cast<size_t>(g.splits) * g.nbatch * g.M * g.N * 4);
     if (dry || g.M == 0 || g.N == 0) return 0;
     SAM_REQUIRE(!overflow, "decoder training: scratch region too small (internal sizing error)");
@@ -608,7 +631,6 @@ int linear(Tape& t, const Ten& X, const Ten& W, const Ten& b, Ten* Y, int bias_m
       g.B = X.p; g.brs = X.ld; g.bcs = 1;
       g.C = W.g; g.crs = K; g.accumulate = 1;
       g.M = N; g.N = K; g.K = M; g.alpha = 1.f;
-      if (M > 4096) { g.kchunk = 2048; g.splits = (M + g.kchunk - 1) / g.kchunk; }
       TRY(t.gemm(g));
     }
     if (b.g) {
@@ -1020,7 +1042,6 @@ int build_forward(Tape& t, const TrainInputs& in) {
         g.B = up.p; g.brs = C2; g.bcs = 1; g.b_b1 = per * C2;
         g.C = hyper.g; g.crs = C2; g.c_b1 = static_cast<i64>(nm) * C2; g.accumulate = 1;
         g.M = nm; g.N = C2; g.K = static_cast<int>(per); g.alpha = 1.f;
-        g.kchunk = 2048; g.splits = static_cast<int>((per + g.kchunk - 1) / g.kchunk);
         TRY(t.gemm(g));
       }
       t.scratch_reset();
@@ -1058,14 +1079,11 @@ int size_regions(Tape& t) {
   size_t bound = 0;
   // attention dP: n * heads * Nq * Nk floats, largest with one side = HW
   bound = std::max(bound, align256(static_cast<size_t>(t.n) * s.heads * std::max(Tm * HW, Tm * Tm) * 4));
-  // split-K partials of a weight gradient: ceil(M / 2048) * N * K floats with N*K <= max(C*C, H*C), M = n*HW*4 at most
+  // split-K partials: at most ~2 x 296 output tiles of 64 x 64 floats (Tape::gemm), or one split per 64 of K
+  bound = std::max(bound, align256(static_cast<size_t>(640) * GT * GT * 4));
   const i64 rows_max = static_cast<i64>(t.n) * HW * 4;
-  const i64 nk_max = std::max<i64>(static_cast<i64>(s.C) * s.C, static_cast<i64>(s.mlp_dim) * s.C);
-  bound = std::max(bound, align256(static_cast<size_t>((rows_max + 2047) / 2048) * nk_max * 4));
   // column-sum partials and LayerNorm block partials: rows / 64 * 2C floats at most
   bound = std::max(bound, align256(static_cast<size_t>((rows_max + 63) / 64 + 1) * 2 * s.C * 4));
-  // hyper gradient partials: n * (16 HW / 2048) * nm * C/8
-  bound = std::max(bound, align256(static_cast<size_t>(t.n) * ((16 * HW + 2047) / 2048) * s.num_mask_tokens * (s.C / 8) * 4));
   t.act_cap = align256(t.act_off);
   t.grad_cap = align256(t.grad_off);
   t.scratch_cap = 2 * std::max(bound, t.scratch_peak) + 4096;
@@ -1161,7 +1179,8 @@ void samk_decoder_tape_free(void* tape) { delete static_cast<Tape*>(tape); }
 // fp32 linear forward / backward for text_hidden_fcs (model/anyref.py:116-124) in training
 // ---------------------------------------------------------------------------------------------------------------
 size_t samk_linear_f32_scratch_bytes(int M, int N, int K) {
-  const size_t splitk = M > 4096 ? static_cast<size_t>((M + 2047) / 2048) * N * K * 4 : 0;
+  (void)K;
+  const size_t splitk = static_cast<size_t>(640) * GT * GT * 4;   // bound of Tape::gemm's split-K partials
   const size_t cols = static_cast<size_t>((M + kColRows - 1) / kColRows) * N * 4;
   return align256(splitk) + align256(cols) + 1024;
 }
@@ -1220,7 +1239,6 @@ int samk_linear_f32_backward(float* dY, const float* relu_y, const float* X, con
     g.B = X; g.brs = K; g.bcs = 1;
     g.C = dW; g.crs = K; g.accumulate = 1;
     g.M = N; g.N = K; g.K = M; g.alpha = 1.f;
-    if (M > 4096) { g.kchunk = 2048; g.splits = (M + g.kchunk - 1) / g.kchunk; }
     TRY(t.gemm(g));
   }
   if (db) TRY(t.colsum(dY, N, M, N, N, db));
