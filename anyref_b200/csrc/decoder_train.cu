@@ -202,6 +202,22 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __rest
     partial[static_cast<i64>(blockIdx.y) * N + j] = t;
   }
 }
+// R <= kColRows and one output per column: a single launch adds straight into out
+__global__ void __launch_bounds__(256) colsum_small_kernel(const float* __restrict__ X, i64 ld, i64 R, int N, float* __restrict__ out) {
+  __shared__ float red[8][33];
+  const int j = blockIdx.x * 32 + threadIdx.x;
+  float s = 0.f;
+  if (j < N)
+    for (i64 r = threadIdx.y; r < R; r += 8) s += X[r * ld + j];
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && j < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) t += red[y][threadIdx.x];
+    out[j] += t;
+  }
+}
 __global__ void colsum_finish_kernel(const float* __restrict__ partial, int chunks, int N, int mod, float* __restrict__ out) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= mod) return;
@@ -564,6 +580,12 @@ struct Tape {
     float* part = scratch(static_cast<size_t>(chunks) * N * 4);
     if (dry || R == 0) return 0;
     SAM_REQUIRE(!overflow, "decoder training: scratch region too small (internal sizing error)");
+    if (chunks == 1 && mod == N) {
+      samhost::LaunchScope scope(samhost::KC_DECODER, st);
+      colsum_small_kernel<<<(N + 31) / 32, dim3(32, 8), 0, st>>>(X, ld, R, N, out);
+      SAM_CHECK_CUDA(cudaGetLastError());
+      return 0;
+    }
     SAM_REQUIRE(chunks <= 65535, "decoder training: colsum grid too large");
     {
       samhost::LaunchScope scope(samhost::KC_DECODER, st);

@@ -157,6 +157,11 @@ class MaskDecoder(nn.Module):
         from .._train import DecoderTrainFn
         emb, pe, sparse, dense_vec, dense_full, image_index = self._check_inputs(
             image_embeddings, image_pe, sparse_prompt_embeddings, dense_prompt_embeddings, image_index)
+        if sparse.shape[0] == 0:      # an image without a [SEG] token: empty outputs that still hang off the graph
+            g = emb.shape[-1]
+            zero = sparse.sum() * 0.0
+            return (torch.zeros((0, self.num_mask_tokens, 4 * g, 4 * g), device=emb.device) + zero,
+                    torch.zeros((0, self.num_mask_tokens), device=emb.device) + zero)
         params = tuple(self.parameters())
         return DecoderTrainFn.apply(self, emb.detach(), pe.detach(), sparse,
                                     dense_vec.detach() if dense_vec is not None else None,

@@ -310,6 +310,96 @@ def library_baseline(dev, n_seg: int, budget_s: float = 40.0):
     return out
 
 
+def sub_record_train(sam, dev, n_prompts: int = 3):
+    """one fine-tuning step of the mask branch (model/anyref.py:395-450 without the LLM): mask decoder in
+    train() with its parameters trainable, postprocess_masks, BCE + dice, backward into the decoder and the [SEG]
+    embeddings -- this path (csrc/decoder_train.cu through autograd Functions) and, as the baseline leg, stock PyTorch
+    autograd over the restated reference modules on the same GPU (fp32, TF32 off).  ViT-H decoder weights, one image,
+    n_prompts [SEG], 1024x768 content -> 640x480 masks."""
+    import torch.nn.functional as F
+
+    from oracle import sam_oracle as O
+
+    dec = sam.mask_decoder
+    flags = [p.requires_grad for p in dec.parameters()]
+    was_training = dec.training
+    from anyref_b200 import _lib
+    from anyref_b200.synthetic import CONFIGS
+
+    cfg = CONFIGS["vit_h"]            # the decoder is the same for every encoder size (build_sam.py:77-103)
+    out = {"workload": f"1 image x {n_prompts} [SEG]: MaskDecoder (train) -> postprocess_masks (768x1024 -> 480x640) -> BCE + dice "
+                       "-> backward; fp32", "unit": "ms per step"}
+    try:
+        tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
+        for p in dec.parameters():
+            p.requires_grad_(True)
+        dec.train()
+        osd = {"mask_decoder." + k: v.detach().clone().float().requires_grad_(True) for k, v in dec.state_dict().items()}
+        osd["prompt_encoder.no_mask_embed.weight"] = sam.prompt_encoder.no_mask_embed.weight.detach().float()
+        g = torch.Generator(device="cpu").manual_seed(0)
+        emb = (torch.randn(1, 256, 64, 64, generator=g) * 0.5).to(dev)
+        pe = sam.prompt_encoder.get_dense_pe().detach().float()
+        sparse0 = torch.randn(n_prompts, 1, 256, generator=g).to(dev)
+        dense = osd["prompt_encoder.no_mask_embed.weight"].reshape(1, -1, 1, 1).expand(n_prompts, -1, 64, 64)
+        gt = (torch.rand(n_prompts, 480, 640, generator=g) > 0.5).float().to(dev)
+
+        def loss_fn(pm):
+            ce = F.binary_cross_entropy_with_logits(pm, gt, reduction="none").flatten(1, 2).mean(1).sum()
+            sg, t = pm.sigmoid().flatten(1, 2), gt.flatten(1, 2)
+            return 2.0 * ce + 0.5 * (1 - (2 * (sg * t).sum(-1) + 1) / (sg.sum(-1) + t.sum(-1) + 1)).sum()
+
+        def mine():
+            sp = sparse0.clone().requires_grad_(True)
+            low, _ = dec(image_embeddings=emb, image_pe=pe, sparse_prompt_embeddings=sp, dense_prompt_embeddings=dense,
+                         multimask_output=False)
+            loss = loss_fn(sam.postprocess_masks(low, input_size=(768, 1024), original_size=(480, 640)).squeeze(1))
+            loss.backward()
+            return loss.detach(), sp.grad
+
+        def stock():
+            sp = sparse0.clone().requires_grad_(True)
+            low, _ = O.mask_decoder(osd, cfg, emb, pe, sp, dense, False)
+            loss = loss_fn(O.postprocess_masks(low, (768, 1024), (480, 640)).squeeze(1))
+            loss.backward()
+            return loss.detach(), sp.grad
+
+        def time_it(fn):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(10):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn()
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            return sorted(ts)[len(ts) // 2]
+
+        la, ga = mine()
+        lb, gb = stock()
+        out["loss"] = float(la)
+        out["loss_stock_pytorch"] = float(lb)
+        out["seg_grad_rel_diff_vs_stock_fp32"] = float((ga - gb).norm() / gb.norm())
+        launches0 = _lib.launch_count()
+        out["value"] = time_it(mine)
+        out["gpu_launches_per_step"] = (_lib.launch_count() - launches0) // 13
+        out["stock_pytorch_autograd_same_gpu"] = time_it(stock)
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+    except Exception as e:  # noqa: BLE001  (an extra must never take the headline down)
+        out["error"] = f"{type(e).__name__}: {e}"[:300]
+    finally:
+        for p, f in zip(dec.parameters(), flags):
+            p.requires_grad_(f)
+            p.grad = None
+        dec.train(was_training)
+        torch.cuda.empty_cache()
+    return out
+
+
 def cublas_sustained(dev, seconds: float = 1.5):
     """cuBLAS (torch.matmul) 8192^3 back to back for `seconds` per operand format ON THIS BOX, the driver's recipe for
     MEASURED_PEAKS.json's sustained figure: boxes differ by +-5 % under the power cap and fp16 operands draw more power
@@ -530,6 +620,7 @@ def main():
                         "mask_sha256": c5.get("mask_sha256"), "gIoU": c5.get("gIoU"), "cIoU": c5.get("cIoU")}
         if rank == 0 and world == 1:
             torch.cuda.empty_cache()
+            extras["train_step"] = sub_record_train(sam, dev)
             extras["library_baseline"] = library_baseline(dev, n_seg)
             extras["cublas_same_box"] = cublas_sustained(dev)
 

@@ -285,6 +285,20 @@ def test_training_step_like_the_reference(setup):
     assert checked >= 80
 
 
+def test_image_without_seg_token_in_training(setup):
+    """model/anyref.py:406-430 also visits images whose sample has no [SEG] token: empty masks, empty loss, zero grads."""
+    sam = setup["sam"]
+    sparse = torch.zeros(0, 1, 256, device="cuda", requires_grad=True)
+    dense = sam.prompt_encoder.no_mask_embed.weight.detach().reshape(1, -1, 1, 1).expand(0, -1, 64, 64)
+    m, i = sam.mask_decoder(image_embeddings=setup["emb"][:1], image_pe=setup["pe"], sparse_prompt_embeddings=sparse,
+                            dense_prompt_embeddings=dense, multimask_output=False)
+    assert m.shape == (0, 1, 256, 256) and i.shape == (0, 1) and m.requires_grad
+    pm = sam.postprocess_masks(m, input_size=(1024, 1024), original_size=(480, 640))
+    assert pm.shape == (0, 1, 480, 640)
+    pm.sum().backward()
+    assert sparse.grad is not None and sparse.grad.shape == (0, 1, 256)
+
+
 def test_tape_is_single_use_and_released(setup):
     sam = setup["sam"]
     sparse = torch.randn(1, 1, 256, device="cuda", requires_grad=True)

@@ -98,3 +98,26 @@ def test_layout_matches_reference_modules(ref_sa, name):
     a, b = ref.state_dict(), mine.state_dict()
     assert list(a) == list(b)
     assert all(a[k].shape == b[k].shape and a[k].dtype == b[k].dtype for k in a)
+
+
+def test_gradient_blob_unpacking_is_the_adjoint_of_weight_packing():
+    """sam_decoder_backward returns d(loss)/d(weight blob); unpack_decoder_grads must map it to parameter gradients by
+    the transpose of pack_decoder (a linear map: ConvTranspose2d permutations, the first ConvTranspose2d bias repeated
+    four times): <pack(P), B> == sum_p <p, unpack(B)[p]> for random P and B."""
+    from anyref_b200.segment_anything import _pack
+
+    sam = build_sam_from_config(CONFIGS["vit_tiny80"])
+    dec = sam.mask_decoder
+    g = torch.Generator().manual_seed(0)
+    with torch.no_grad():
+        for p in dec.parameters():
+            p.copy_(torch.randn(p.shape, generator=g))
+    _, blob = _pack.pack_decoder(dec, 64)
+    B = torch.randn(blob.shape, generator=g)
+    grads = _pack.unpack_decoder_grads(dec, B)
+    lhs = float((blob.double() * B.double()).sum())
+    rhs = sum(float((p.detach().double() * grads[id(p)].double()).sum()) for p in dec.parameters())
+    assert len(grads) == len(list(dec.parameters()))
+    assert all(grads[id(p)].shape == p.shape for p in dec.parameters())
+    assert abs(lhs - rhs) <= 1e-9 * max(1.0, abs(lhs))
+
