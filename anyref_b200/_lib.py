@@ -67,7 +67,7 @@ _PROTOS = {
     "sam_decoder_train_workspace_bytes": [_DEC_P, c_int, c_int],
     "sam_decoder_train_forward": [_DEC_P, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
                                   c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t, C.POINTER(c_void_p), c_void_p],
-    "sam_decoder_backward": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "sam_decoder_backward": [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     "sam_decoder_tape_free": [c_void_p],
     "sam_linear_f32_scratch_bytes": [c_int, c_int, c_int],
     "sam_linear_f32_forward": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],

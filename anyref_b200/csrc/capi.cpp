@@ -130,8 +130,9 @@ int sam_decoder_train_forward(const SamDecoderShape* s, const float* weights, co
   return samk_decoder_train_forward(*s, weights, image_embeddings, emb_fmt, n_images, img_index, sparse, n, k, dense_vec, dense_full,
                                     dense_fmt, image_pe, pe_fmt, masks, iou, workspace, workspace_bytes, tape, S(stream));
 }
-int sam_decoder_backward(void* tape, const float* d_masks, const float* d_iou, float* d_weights, float* d_sparse, void* stream) {
-  return samk_decoder_backward(tape, d_masks, d_iou, d_weights, d_sparse, S(stream));
+int sam_decoder_backward(void* tape, const float* d_masks, int mask_lo, int mask_hi, const float* d_iou, float* d_weights,
+                         float* d_sparse, void* stream) {
+  return samk_decoder_backward(tape, d_masks, mask_lo, mask_hi, d_iou, d_weights, d_sparse, S(stream));
 }
 void sam_decoder_tape_free(void* tape) { samk_decoder_tape_free(tape); }
 size_t sam_linear_f32_scratch_bytes(int M, int N, int K) { return samk_linear_f32_scratch_bytes(M, N, K); }

@@ -513,6 +513,8 @@ struct Tape {
   size_t act_cap = 0, grad_cap = 0, scratch_cap = 0;   // region sizes (from the dry pass)
   size_t act_off = 0, grad_off = 0, scratch_off = 0, scratch_peak = 0;
   std::vector<std::function<int()>> back;
+  std::vector<int> back_group;   // 0: always; 1 + i: hypernetwork MLP of mask token i; 100: IoU head (skipped when no
+  int group = 0;                 // gradient reaches them: multimask_output selects a sub-range of the mask tokens)
   Ten masks, iou, sparse;
   float* gblob = nullptr;   // gradient of the weight blob (inside the gradient region)
   size_t blob_elems = 0;
@@ -608,7 +610,9 @@ struct Tape {
     return 0;
   }
   void push(std::function<int()> f) {
-    if (!dry) back.push_back(std::move(f));
+    if (dry) return;
+    back.push_back(std::move(f));
+    back_group.push_back(group);
   }
 };
 
@@ -1031,7 +1035,9 @@ int build_forward(Tape& t, const TrainInputs& in) {
     view.p = hyper.p ? hyper.p + i * C2 : nullptr;
     view.g = hyper.g ? hyper.g + i * C2 : nullptr;
     view.cols = C2;
+    t.group = 1 + i;
     TRY(mlp3(t, P.hyper[i], token_row(1 + i), &y, &view));
+    t.group = 0;
   }
   // masks = hyper_in @ upscaled (mask_decoder.py:171-174), as rows [pos, nm] per prompt, then the layout gather
   const i64 per = static_cast<i64>(HW) * 16;
@@ -1081,7 +1087,9 @@ int build_forward(Tape& t, const TrainInputs& in) {
       return t.ew(tot, [&](unsigned nb) { mask_rows_kernel<<<nb, 256, 0, t.st>>>(mrows.g, mk.g, n, nm, g, 1); });
     });
   }
+  t.group = 100;
   TRY(mlp3(t, P.iou_head, token_row(0), &t.iou));
+  t.group = 0;
   return 0;
 }
 
@@ -1168,11 +1176,13 @@ int samk_decoder_train_forward(const SamDecoderShape& s, const float* blob, cons
   return 0;
 }
 
-int samk_decoder_backward(void* tape, const float* d_masks, const float* d_iou, float* d_weights, float* d_sparse, cudaStream_t st) {
+int samk_decoder_backward(void* tape, const float* d_masks, int mask_lo, int mask_hi, const float* d_iou, float* d_weights,
+                          float* d_sparse, cudaStream_t st) {
   SAM_REQUIRE(tape != nullptr, "decoder backward: NULL tape");
   Tape& t = *static_cast<Tape*>(tape);
   SAM_REQUIRE(!t.back.empty(), "decoder backward: this tape has already been consumed");
   SAM_REQUIRE(d_weights != nullptr, "decoder backward: NULL d_weights");
+  SAM_REQUIRE(0 <= mask_lo && mask_lo <= mask_hi && mask_hi <= t.s.num_mask_tokens, "decoder backward: mask range [%d, %d)", mask_lo, mask_hi);
   t.st = st;
   const SamDecoderShape& s = t.s;
   SAM_CHECK_CUDA(cudaMemsetAsync(t.base + t.act_cap, 0, t.grad_cap, st));
@@ -1181,6 +1191,11 @@ int samk_decoder_backward(void* tape, const float* d_masks, const float* d_iou, 
   if (d_iou)
     SAM_CHECK_CUDA(cudaMemcpyAsync(t.iou.g, d_iou, static_cast<size_t>(t.n) * s.num_mask_tokens * 4, cudaMemcpyDeviceToDevice, st));
   for (size_t i = t.back.size(); i-- > 0;) {
+    const int grp = t.back_group[i];
+    // mask tokens outside [mask_lo, mask_hi) and an unused IoU prediction have an all-zero cotangent: their MLPs
+    // would add exact zeros everywhere
+    if (grp == 100 && !d_iou) continue;
+    if (grp >= 1 && grp < 100 && (!d_masks || grp - 1 < mask_lo || grp - 1 >= mask_hi)) continue;
     t.scratch_reset();
     if (int rc = t.back[i]()) return rc;
   }

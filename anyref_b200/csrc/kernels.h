@@ -108,7 +108,8 @@ int samk_decoder_train_forward(const SamDecoderShape& s, const float* blob, cons
                                const int* img_index, const float* sparse, int n, int k, const void* dense_vec, const void* dense_full,
                                int dense_fmt, const void* image_pe, int pe_fmt, float* masks, float* iou, void* workspace,
                                size_t workspace_bytes, void** tape_out, cudaStream_t st);
-int samk_decoder_backward(void* tape, const float* d_masks, const float* d_iou, float* d_weights, float* d_sparse, cudaStream_t st);
+int samk_decoder_backward(void* tape, const float* d_masks, int mask_lo, int mask_hi, const float* d_iou, float* d_weights,
+                          float* d_sparse, cudaStream_t st);
 void samk_decoder_tape_free(void* tape);
 size_t samk_linear_f32_scratch_bytes(int M, int N, int K);
 int samk_linear_f32_forward(const float* X, const float* W, const float* b, float* Y, int M, int N, int K, int relu_act, cudaStream_t st);

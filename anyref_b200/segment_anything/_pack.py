@@ -138,57 +138,67 @@ def _unwrap(m):
     return m
 
 
-def pack_decoder(dec, grid: int):
-    """-> (shape, fp32 blob) in the order of csrc/decoder.cu carve_weights."""
-    lib = _lib.load()
-    shape = decoder_shape(dec, grid)
-    n = lib.sam_decoder_weight_elems(C.byref(shape))
-    dev = dec.iou_token.weight.device
-    b = _Blob(n, torch.float32, dev)
-    f = lambda t: t.detach().float()
+def _decoder_sources(dec):
+    """The decoder's tensors in blob order (csrc/decoder.cu carve_weights == state_dict order of mask_decoder.*), the
+    two ConvTranspose2d weights re-arranged into per-pixel linear weights."""
+    out = []
 
     def attn(a):
         for lin in (a.q_proj, a.k_proj, a.v_proj, a.out_proj):
-            b.put_exact(f(lin.weight)); b.put_exact(f(lin.bias))
+            out.append(lin.weight); out.append(lin.bias)
 
     def norm(ln):
-        b.put_exact(f(ln.weight)); b.put_exact(f(ln.bias))
+        out.append(ln.weight); out.append(ln.bias)
 
-    b.put_exact(f(dec.iou_token.weight))
-    b.put_exact(f(_unwrap(dec.mask_tokens).weight))
+    out.append(dec.iou_token.weight)
+    out.append(_unwrap(dec.mask_tokens).weight)
     tr = dec.transformer
     for layer in tr.layers:
         attn(layer.self_attn); norm(layer.norm1)
         attn(layer.cross_attn_token_to_image); norm(layer.norm2)
-        b.put_exact(f(layer.mlp.lin1.weight)); b.put_exact(f(layer.mlp.lin1.bias))
-        b.put_exact(f(layer.mlp.lin2.weight)); b.put_exact(f(layer.mlp.lin2.bias))
+        out.extend((layer.mlp.lin1.weight, layer.mlp.lin1.bias, layer.mlp.lin2.weight, layer.mlp.lin2.bias))
         norm(layer.norm3); norm(layer.norm4)
         attn(layer.cross_attn_image_to_token)
     attn(tr.final_attn_token_to_image); norm(tr.norm_final_attn)
     up = _unwrap(dec.output_upscaling)
     # ConvTranspose2d(k=2,s=2) weight [in, out, dy, dx] -> per-pixel linear weight [(dy,dx,out), in]
-    w0 = f(up[0].weight)
-    b.put_exact(w0.permute(2, 3, 1, 0).reshape(-1, w0.shape[0]).contiguous())
-    b.put_exact(f(up[0].bias).repeat(4))
+    w0 = up[0].weight.detach()
+    out.append(w0.permute(2, 3, 1, 0).reshape(-1, w0.shape[0]))
+    out.append(up[0].bias.detach().repeat(4))
     norm(up[1])
-    w1 = f(up[3].weight)
-    b.put_exact(w1.permute(2, 3, 1, 0).contiguous())     # [(ey,ex), out, in]
-    b.put_exact(f(up[3].bias))
+    out.append(up[3].weight.detach().permute(2, 3, 1, 0))     # [(ey,ex), out, in]
+    out.append(up[3].bias)
     hyper = _unwrap(dec.output_hypernetworks_mlps)
     for i in range(dec.num_mask_tokens):
         m = hyper[i]
         if len(m.layers) != 3:
             raise RuntimeError("hypernetwork MLPs must have 3 layers")
         for lin in m.layers:
-            b.put_exact(f(lin.weight)); b.put_exact(f(lin.bias))
+            out.append(lin.weight); out.append(lin.bias)
     head = dec.iou_prediction_head
     if len(head.layers) != 3:
         raise RuntimeError("iou_head_depth must be 3")
     for lin in head.layers:
-        b.put_exact(f(lin.weight)); b.put_exact(f(lin.bias))
-    if b.off != n:
-        raise RuntimeError(f"decoder blob layout mismatch: packed {b.off}, library expects {n}")
-    return shape, b.t
+        out.append(lin.weight); out.append(lin.bias)
+    return [t.detach() for t in out]
+
+
+def pack_decoder(dec, grid: int):
+    """-> (shape, fp32 blob) in the order of csrc/decoder.cu carve_weights.  One concatenation (the training path packs
+    on every forward: a parameter update must never meet a stale blob)."""
+    lib = _lib.load()
+    shape = decoder_shape(dec, grid)
+    n = lib.sam_decoder_weight_elems(C.byref(shape))
+    srcs = _decoder_sources(dec)
+    dt = srcs[0].dtype
+    if all(t.dtype == dt for t in srcs):
+        blob = torch.cat([t.reshape(-1) for t in srcs])
+        blob = blob.float() if dt != torch.float32 else blob
+    else:
+        blob = torch.cat([t.reshape(-1).float() for t in srcs])
+    if blob.numel() != n:
+        raise RuntimeError(f"decoder blob layout mismatch: packed {blob.numel()}, library expects {n}")
+    return shape, blob
 
 
 def unpack_decoder_grads(dec, gblob: torch.Tensor) -> dict:

@@ -41,8 +41,10 @@ class DecoderTrainFn(torch.autograd.Function):
     parameters and for sparse_prompt_embeddings."""
 
     @staticmethod
-    def forward(ctx, dec, emb, pe, sparse, dense_vec, dense_full, image_index, *params):
+    def forward(ctx, dec, mask_range, emb, pe, sparse, dense_vec, dense_full, image_index, *params):
         lib = _lib.load()
+        ctx.set_materialize_grads(False)      # an unused output (the IoU prediction in AnyRef) arrives as None
+        ctx.mask_range = mask_range
         dev = emb.device
         with torch.cuda.device(dev):
             g = emb.shape[-1]
@@ -88,8 +90,8 @@ class DecoderTrainFn(torch.autograd.Function):
             di = d_iou.float().contiguous() if d_iou is not None else None
             gblob = torch.zeros(ctx.blob_elems, dtype=torch.float32, device=dev)
             d_sparse = torch.empty(shape, dtype=torch.float32, device=dev)
-            rc = lib.sam_decoder_backward(tape.ptr, dm.data_ptr() if dm is not None else None,
-                                          di.data_ptr() if di is not None else None, gblob.data_ptr(),
+            rc = lib.sam_decoder_backward(tape.ptr, dm.data_ptr() if dm is not None else None, ctx.mask_range[0],
+                                          ctx.mask_range[1], di.data_ptr() if di is not None else None, gblob.data_ptr(),
                                           d_sparse.data_ptr() if d_sparse.numel() else None, _lib.stream_ptr(dev))
             _lib.check(rc, "sam_decoder_backward")
             # the workspace may be recycled by the allocator as soon as this stream has passed the kernels above
@@ -100,8 +102,8 @@ class DecoderTrainFn(torch.autograd.Function):
         for p in ctx.params:
             gp = grads.get(id(p)) if p.requires_grad else None
             out.append(gp.to(p.dtype) if gp is not None else None)
-        ds = d_sparse.to(dtype) if ctx.needs_input_grad[3] else None
-        return (None, None, None, ds, None, None, None, *out)
+        ds = d_sparse.to(dtype) if ctx.needs_input_grad[4] else None
+        return (None, None, None, None, ds, None, None, None, *out)
 
 
 class PostprocessFn(torch.autograd.Function):

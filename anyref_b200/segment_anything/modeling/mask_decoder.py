@@ -89,30 +89,35 @@ class MaskDecoder(nn.Module):
         if image_embeddings.shape[0] != 1:
             raise ValueError("MaskDecoder.forward takes the embedding of ONE image (mask_decoder.py:146 repeats it per "
                              "prompt); use forward_batched for prompts of several images")
-        masks, iou = self.predict_masks(image_embeddings, image_pe, sparse_prompt_embeddings, dense_prompt_embeddings)
         sl = slice(1, None) if multimask_output else slice(0, 1)
+        masks, iou = self.predict_masks(image_embeddings, image_pe, sparse_prompt_embeddings, dense_prompt_embeddings,
+                                        _used=sl)
         return masks[:, sl, :, :], iou[:, sl]
 
     def forward_batched(self, image_embeddings: torch.Tensor, image_pe: torch.Tensor,
                         sparse_prompt_embeddings: torch.Tensor, dense_prompt_embeddings: torch.Tensor,
                         image_index: torch.Tensor, multimask_output: bool) -> Tuple[torch.Tensor, torch.Tensor]:
         """Prompt p is decoded against image_embeddings[image_index[p]] (int32 device tensor [n])."""
-        masks, iou = self.predict_masks(image_embeddings, image_pe, sparse_prompt_embeddings, dense_prompt_embeddings,
-                                        image_index)
         sl = slice(1, None) if multimask_output else slice(0, 1)
+        masks, iou = self.predict_masks(image_embeddings, image_pe, sparse_prompt_embeddings, dense_prompt_embeddings,
+                                        image_index, _used=sl)
         return masks[:, sl, :, :], iou[:, sl]
 
     def predict_masks(self, image_embeddings: torch.Tensor, image_pe: torch.Tensor,
                       sparse_prompt_embeddings: torch.Tensor, dense_prompt_embeddings: torch.Tensor,
-                      image_index: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
-        """All `num_mask_tokens` masks [n,4,4g,4g] and IoU predictions [n,4] (mask_decoder.py:116-179)."""
+                      image_index: Optional[torch.Tensor] = None, _used: Optional[slice] = None
+                      ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """All `num_mask_tokens` masks [n,4,4g,4g] and IoU predictions [n,4] (mask_decoder.py:116-179).  `_used`: the
+        slice of mask tokens the caller keeps (forward's multimask selection) -- the training backward skips the
+        hypernetwork MLPs of the others, whose cotangent is exactly zero."""
         if torch.is_grad_enabled() and (sparse_prompt_embeddings.requires_grad or
                                         (self.training and any(p.requires_grad for p in self.parameters()))):
             # model/anyref.py:108-113 fine-tunes the decoder (train(), requires_grad=True) with the encoders frozen:
             # the fp32 training path keeps its intermediates and has a backward (csrc/decoder_train.cu).  In eval()
             # with constant prompts the fused inference path runs and returns tensors without a graph
+            lo, hi, _ = (_used or slice(None)).indices(self.num_mask_tokens)
             return self._predict_masks_train(image_embeddings, image_pe, sparse_prompt_embeddings,
-                                             dense_prompt_embeddings, image_index)
+                                             dense_prompt_embeddings, image_index, (lo, hi))
         with torch.no_grad():
             return self._predict_masks(image_embeddings, image_pe, sparse_prompt_embeddings, dense_prompt_embeddings,
                                        image_index)
@@ -144,7 +149,7 @@ class MaskDecoder(nn.Module):
         return emb, pe, sparse, dense_vec, dense_full, image_index
 
     def _predict_masks_train(self, image_embeddings, image_pe, sparse_prompt_embeddings, dense_prompt_embeddings,
-                             image_index):
+                             image_index, mask_range):
         """fp32 forward with a graph: gradients for this module's parameters and for sparse_prompt_embeddings.  Image
         embeddings, dense prompt embeddings and image_pe are constants here, as in the reference's fine-tuning where
         the image encoder and the prompt encoder are frozen (model/anyref.py:107-113); asking for their gradient
@@ -163,7 +168,7 @@ class MaskDecoder(nn.Module):
             return (torch.zeros((0, self.num_mask_tokens, 4 * g, 4 * g), device=emb.device) + zero,
                     torch.zeros((0, self.num_mask_tokens), device=emb.device) + zero)
         params = tuple(self.parameters())
-        return DecoderTrainFn.apply(self, emb.detach(), pe.detach(), sparse,
+        return DecoderTrainFn.apply(self, mask_range, emb.detach(), pe.detach(), sparse,
                                     dense_vec.detach() if dense_vec is not None else None,
                                     dense_full.detach() if dense_full is not None else None, image_index, *params)
 

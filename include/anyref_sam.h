@@ -200,6 +200,9 @@ int sam_decoder_forward(const SamDecoderShape* shape, const float* weights, cons
  * sparse fp32; image_pe is passed directly, no `derived` buffer) but keeps every intermediate in `workspace` and
  * returns a tape.  sam_decoder_backward consumes the tape once:
  *   d_masks   [n, num_mask_tokens, 4g, 4g] fp32 or NULL;   d_iou [n, num_mask_tokens] fp32 or NULL
+ *   mask_lo, mask_hi   the caller's promise that d_masks is zero outside mask tokens [mask_lo, mask_hi)
+ *             (multimask_output=False uses token 0, True tokens 1.., mask_decoder.py:106-111): the hypernetwork MLPs of
+ *             the other tokens are skipped; pass 0, num_mask_tokens when unknown
  *   d_weights fp32, layout of `weights`: the gradient is ADDED (zero it for a fresh gradient)
  *   d_sparse  [n, k, C] fp32, overwritten (may be NULL)
  * Image embeddings, dense prompt embeddings and image_pe receive no gradient (frozen in the reference).  The workspace
@@ -211,8 +214,8 @@ int sam_decoder_train_forward(const SamDecoderShape* shape, const float* weights
                               const void* dense_vec, const void* dense_full, int dense_fmt, const void* image_pe,
                               int pe_fmt, float* masks, float* iou, void* workspace, size_t workspace_bytes,
                               void** tape, void* stream);
-int sam_decoder_backward(void* tape, const float* d_masks, const float* d_iou, float* d_weights, float* d_sparse,
-                         void* stream);
+int sam_decoder_backward(void* tape, const float* d_masks, int mask_lo, int mask_hi, const float* d_iou,
+                         float* d_weights, float* d_sparse, void* stream);
 void sam_decoder_tape_free(void* tape);
 
 /*

@@ -83,7 +83,7 @@ def test_sizes_and_errors_without_gpu(lib):
     rc = L.sam_decoder_train_forward(ctypes.byref(dec), None, None, 2, 1, None, None, 1, 1, None, None, 2, None, 2, None, None, None,
                                      0, ctypes.byref(tape), None)
     assert rc != 0 and b"NULL" in L.sam_last_error() and not tape.value
-    rc = L.sam_decoder_backward(None, None, None, None, None, None)
+    rc = L.sam_decoder_backward(None, None, 0, 4, None, None, None, None)
     assert rc != 0 and b"tape" in L.sam_last_error()
     L.sam_decoder_tape_free(None)
     rc = L.sam_postprocess_masks_backward(None, 1, 256, 1024, 1024, 1024, 1024, 1024, None, None, None)
