@@ -70,11 +70,16 @@ struct Gemm {
   float* partial;
 };
 
-constexpr int GT = 64, GK = 16;
+constexpr int GT = 64, GK = 16;       // the general tile
+constexpr int HM = 16, HN = 32, HK = 64;   // the thin tile: M <= 16, N <= 32 and a long K (attention against 6 tokens)
 
+// TM x TN x TK tiles, 256 threads as 16 x 16, (TM/16) x (TN/16) outputs per thread
+template <int TM, int TN, int TK>
 __global__ void __launch_bounds__(256) sgemm_kernel(const Gemm g) {
-  __shared__ __align__(16) float As[GK][GT + 4];
-  __shared__ __align__(16) float Bs[GK][GT + 4];
+  constexpr int RM = TM / 16, RN = TN / 16;
+  constexpr int SA = TM * TK / 256, SB = TK * TN / 256;   // tile-load slots per thread
+  __shared__ __align__(16) float As[TK][TM + 4];
+  __shared__ __align__(16) float Bs[TK][TN + 4];
   const int z = blockIdx.z;
   const int batch = z / g.splits, split = z - batch * g.splits;
   const int b1 = batch / g.nb2, b2 = batch - b1 * g.nb2;
@@ -82,64 +87,82 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const Gemm g) {
   const float* __restrict__ B = g.B + b1 * g.b_b1 + b2 * g.b_b2;
   const int k0 = split * g.kchunk;
   const int k1 = min(g.K, k0 + g.kchunk);
-  const int m0 = blockIdx.x * GT, n0 = blockIdx.y * GT;
+  const int m0 = blockIdx.x * TM, n0 = blockIdx.y * TN;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   // consecutive threads walk whichever index of the operand is contiguous in memory
   const bool a_kfast = g.acs == 1 && g.ars != 1;
   const bool b_kfast = g.brs == 1 && g.bcs != 1;
-  float acc[4][4];
+  float acc[RM][RN];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < RM; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  // per-thread slots of the tile loads (4 of A, 4 of B), fixed over the k loop
-  int ai[4], ak[4], bj[4], bk[4];
+    for (int j = 0; j < RN; ++j) acc[i][j] = 0.f;
+  // per-thread slots of the tile loads, fixed over the k loop
+  int ai[SA], ak[SA], bj[SB], bk[SB];
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
+  for (int r = 0; r < SA; ++r) {
     const int idx = tid + r * 256;
-    if (a_kfast) { ak[r] = idx & (GK - 1); ai[r] = idx >> 4; } else { ai[r] = idx & (GT - 1); ak[r] = idx >> 6; }
-    if (b_kfast) { bk[r] = idx & (GK - 1); bj[r] = idx >> 4; } else { bj[r] = idx & (GT - 1); bk[r] = idx >> 6; }
+    if (a_kfast) { ak[r] = idx % TK; ai[r] = idx / TK; } else { ai[r] = idx % TM; ak[r] = idx / TM; }
   }
-  float ra[4], rb[4];
+#pragma unroll
+  for (int r = 0; r < SB; ++r) {
+    const int idx = tid + r * 256;
+    if (b_kfast) { bk[r] = idx % TK; bj[r] = idx / TK; } else { bj[r] = idx % TN; bk[r] = idx / TN; }
+  }
+  float ra[SA], rb[SB];
   auto fetch = [&](int kk) {
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < SA; ++r) {
       const int gi = m0 + ai[r], gka = kk + ak[r];
       ra[r] = (gi < g.M && gka < k1) ? A[gi * g.ars + gka * g.acs] : 0.f;
+    }
+#pragma unroll
+    for (int r = 0; r < SB; ++r) {
       const int gj = n0 + bj[r], gkb = kk + bk[r];
       rb[r] = (gj < g.N && gkb < k1) ? B[gkb * g.brs + gj * g.bcs] : 0.f;
     }
   };
   fetch(k0);
-  for (int kk = k0; kk < k1; kk += GK) {
+  for (int kk = k0; kk < k1; kk += TK) {
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      As[ak[r]][ai[r]] = ra[r];
-      Bs[bk[r]][bj[r]] = rb[r];
-    }
+    for (int r = 0; r < SA; ++r) As[ak[r]][ai[r]] = ra[r];
+#pragma unroll
+    for (int r = 0; r < SB; ++r) Bs[bk[r]][bj[r]] = rb[r];
     __syncthreads();
-    if (kk + GK < k1) fetch(kk + GK);   // the next tile's global loads fly behind this tile's arithmetic
+    if (kk + TK < k1) fetch(kk + TK);   // the next tile's global loads fly behind this tile's arithmetic
 #pragma unroll
-    for (int k = 0; k < GK; ++k) {
-      const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
-      const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+    for (int k = 0; k < TK; ++k) {
+      float av[RM], bv[RN];
+      if constexpr (RM == 4) {
+        const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+        av[0] = a.x; av[1] = a.y; av[2] = a.z; av[3] = a.w;
+      } else {
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < RM; ++i) av[i] = As[k][ty * RM + i];
+      }
+      if constexpr (RN == 4) {
+        const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+        bv[0] = b.x; bv[1] = b.y; bv[2] = b.z; bv[3] = b.w;
+      } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        for (int j = 0; j < RN; ++j) bv[j] = Bs[k][tx * RN + j];
+      }
+#pragma unroll
+      for (int i = 0; i < RM; ++i)
+#pragma unroll
+        for (int j = 0; j < RN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
     __syncthreads();
   }
   if (g.splits > 1) {
     float* P = g.partial + (static_cast<i64>(split) * g.nbatch + batch) * g.M * g.N;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int gi = m0 + ty * 4 + i;
+    for (int i = 0; i < RM; ++i) {
+      const int gi = m0 + ty * RM + i;
       if (gi >= g.M) continue;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int gj = n0 + tx * 4 + j;
+      for (int j = 0; j < RN; ++j) {
+        const int gj = n0 + tx * RN + j;
         if (gj < g.N) P[static_cast<i64>(gi) * g.N + gj] = acc[i][j];
       }
     }
@@ -147,12 +170,12 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const Gemm g) {
   }
   float* __restrict__ Cb = g.C + b1 * g.c_b1 + b2 * g.c_b2;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int gi = m0 + ty * 4 + i;
+  for (int i = 0; i < RM; ++i) {
+    const int gi = m0 + ty * RM + i;
     if (gi >= g.M) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int gj = n0 + tx * 4 + j;
+    for (int j = 0; j < RN; ++j) {
+      const int gj = n0 + tx * RN + j;
       if (gj >= g.N) continue;
       float v = g.alpha * acc[i][j];
       if (g.bias) v += g.bias[gj % g.bias_mod];
@@ -218,13 +241,19 @@ __global__ void __launch_bounds__(256) colsum_small_kernel(const float* __restri
     out[j] += t;
   }
 }
-__global__ void colsum_finish_kernel(const float* __restrict__ partial, int chunks, int N, int mod, float* __restrict__ out) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per output column: lanes stride over the (chunk, column group) partials, fixed-order warp reduction
+__global__ void __launch_bounds__(256) colsum_finish_kernel(const float* __restrict__ partial, int chunks, int N, int mod, float* __restrict__ out) {
+  const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (j >= mod) return;
+  const int groups = N / mod;
   float s = 0.f;
-  for (int c = 0; c < chunks; ++c)
-    for (int jj = j; jj < N; jj += mod) s += partial[static_cast<i64>(c) * N + jj];
-  out[j] += s;
+  for (int i = lane; i < chunks * groups; i += 32) {
+    const int c = i / groups, gq = i - c * groups;
+    s += partial[static_cast<i64>(c) * N + gq * mod + j];
+  }
+  s = warp_sum(s);
+  if (lane == 0) out[j] += s;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -547,26 +576,31 @@ struct Tape {
     if (g.nbatch <= 0) { g.nbatch = 1; }
     if (g.nb2 <= 0) g.nb2 = 1;
     if (g.bias_mod <= 0) g.bias_mod = g.N;
-    // few output tiles + a long reduction (weight gradients, attention over 4096 pixels): split K so that ~2 CTAs per SM
-    // exist; the partials are folded in index order (deterministic)
-    const i64 tiles = static_cast<i64>((g.M + GT - 1) / GT) * ((g.N + GT - 1) / GT) * g.nbatch;
+    // few output tiles + a long reduction (weight gradients, attention over 4096 pixels): split K so that ~4 CTAs per SM
+    // exist (a CTA's k-step is latency-bound: one tile of prefetch); the partials are folded in index order (deterministic)
+    const bool thin = g.M <= HM && g.N <= HN && g.K >= 256;
+    const int tm = thin ? HM : GT, tn = thin ? HN : GT, tk = thin ? HK : GK;
+    const i64 tiles = static_cast<i64>((g.M + tm - 1) / tm) * ((g.N + tn - 1) / tn) * g.nbatch;
     g.splits = 1;
     g.kchunk = g.K;
     if (tiles < 148 && g.K >= 256) {
-      int want = static_cast<int>(std::min<i64>((296 + tiles - 1) / tiles, g.K / 64));
+      int want = static_cast<int>(std::min<i64>((592 + tiles - 1) / tiles, g.K / (4 * tk) > 0 ? g.K / (4 * tk) : 1));
       if (want > 1) {
-        g.kchunk = (((g.K + want - 1) / want) + GK - 1) / GK * GK;
+        g.kchunk = (((g.K + want - 1) / want) + tk - 1) / tk * tk;
         g.splits = (g.K + g.kchunk - 1) / g.kchunk;
       }
     }
     if (g.splits > 1) g.partial = scratch(static_cast<size_t>(g.splits) * g.nbatch * g.M * g.N * 4);
     if (dry || g.M == 0 || g.N == 0) return 0;
     SAM_REQUIRE(!overflow, "decoder training: scratch region too small (internal sizing error)");
-    SAM_REQUIRE(static_cast<i64>(g.nbatch) * g.splits <= 65535 && (g.N + GT - 1) / GT <= 65535, "decoder training: gemm grid too large");
+    SAM_REQUIRE(static_cast<i64>(g.nbatch) * g.splits <= 65535 && (g.N + tn - 1) / tn <= 65535, "decoder training: gemm grid too large");
     {
       samhost::LaunchScope scope(samhost::KC_DECODER, st, 2.0 * g.M * g.N * g.K * g.nbatch);
-      dim3 grid((g.M + GT - 1) / GT, (g.N + GT - 1) / GT, g.nbatch * g.splits);
-      sgemm_kernel<<<grid, 256, 0, st>>>(g);
+      dim3 grid((g.M + tm - 1) / tm, (g.N + tn - 1) / tn, g.nbatch * g.splits);
+      if (thin)
+        sgemm_kernel<HM, HN, HK><<<grid, 256, 0, st>>>(g);
+      else
+        sgemm_kernel<GT, GT, GK><<<grid, 256, 0, st>>>(g);
       SAM_CHECK_CUDA(cudaGetLastError());
     }
     if (g.splits > 1) {
@@ -596,7 +630,7 @@ struct Tape {
     }
     {
       samhost::LaunchScope scope(samhost::KC_DECODER, st);
-      colsum_finish_kernel<<<(mod + 127) / 128, 128, 0, st>>>(part, chunks, N, mod, out);
+      colsum_finish_kernel<<<(mod + 7) / 8, 256, 0, st>>>(part, chunks, N, mod, out);
       SAM_CHECK_CUDA(cudaGetLastError());
     }
     return 0;
@@ -1109,8 +1143,8 @@ int size_regions(Tape& t) {
   size_t bound = 0;
   // attention dP: n * heads * Nq * Nk floats, largest with one side = HW
   bound = std::max(bound, align256(static_cast<size_t>(t.n) * s.heads * std::max(Tm * HW, Tm * Tm) * 4));
-  // split-K partials: at most ~2 x 296 output tiles of 64 x 64 floats (Tape::gemm), or one split per 64 of K
-  bound = std::max(bound, align256(static_cast<size_t>(640) * GT * GT * 4));
+  // split-K partials: at most 592 + 148 output tiles of 64 x 64 floats (Tape::gemm)
+  bound = std::max(bound, align256(static_cast<size_t>(768) * GT * GT * 4));
   const i64 rows_max = static_cast<i64>(t.n) * HW * 4;
   // column-sum partials and LayerNorm block partials: rows / 64 * 2C floats at most
   bound = std::max(bound, align256(static_cast<size_t>((rows_max + 63) / 64 + 1) * 2 * s.C * 4));
@@ -1217,7 +1251,7 @@ void samk_decoder_tape_free(void* tape) { delete static_cast<Tape*>(tape); }
 // ---------------------------------------------------------------------------------------------------------------
 size_t samk_linear_f32_scratch_bytes(int M, int N, int K) {
   (void)K;
-  const size_t splitk = static_cast<size_t>(640) * GT * GT * 4;   // bound of Tape::gemm's split-K partials
+  const size_t splitk = static_cast<size_t>(768) * GT * GT * 4;   // bound of Tape::gemm's split-K partials
   const size_t cols = static_cast<size_t>((M + kColRows - 1) / kColRows) * N * 4;
   return align256(splitk) + align256(cols) + 1024;
 }
@@ -1234,7 +1268,7 @@ int samk_linear_f32_forward(const float* X, const float* W, const float* b, floa
   g.nbatch = 1; g.nb2 = 1; g.splits = 1; g.kchunk = K;
   {
     samhost::LaunchScope scope(samhost::KC_GEMM, st, 2.0 * M * N * K);
-    sgemm_kernel<<<dim3((M + GT - 1) / GT, (N + GT - 1) / GT, 1), 256, 0, st>>>(g);
+    sgemm_kernel<GT, GT, GK><<<dim3((M + GT - 1) / GT, (N + GT - 1) / GT, 1), 256, 0, st>>>(g);
     SAM_CHECK_CUDA(cudaGetLastError());
   }
   if (relu_act) {
