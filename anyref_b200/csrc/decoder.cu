@@ -1243,6 +1243,7 @@ void carve_ws(const SamDecoderShape& s, int n, int n_src, int k, void* base, Dec
 }  // namespace
 
 size_t samk_decoder_workspace_bytes(const SamDecoderShape& s, int n_images, int n, int k) {
+  if (1 + s.num_mask_tokens + k > TMAX) return samk_decoder_generic_workspace_bytes(s, n, k);   // the generic path
   DecWs w;
   carve_ws(s, n, n_images > n ? n_images : n, k, nullptr, &w);   // covers both source modes (images / prompts)
   return w.total + 256;
@@ -1255,8 +1256,16 @@ int samk_decoder_forward(const SamDecoderShape& s, const float* blob, const void
   if (int rc = check_shape(s)) return rc;
   SAM_REQUIRE(n > 0 && k >= 0, "mask decoder: need at least one prompt");
   const int C = s.C, Ci = C / 2, nm = s.num_mask_tokens, T = 1 + nm + k, g = s.grid, HW = g * g, H = s.mlp_dim;
-  SAM_REQUIRE(T <= TMAX, "mask decoder: %d tokens per prompt exceed the supported maximum %d (at most %d sparse prompt "
-              "embeddings per prompt)", T, TMAX, TMAX - 1 - nm);
+  if (T > TMAX) {
+    // more tokens per prompt than the fused token kernels keep in shared memory (more than 11 sparse prompt embeddings,
+    // e.g. many points): the plain fp32 composition of decoder_train.cu without its tape -- slower, no limit
+    SAM_REQUIRE(derived != nullptr && (reinterpret_cast<uintptr_t>(derived) & 255) == 0,
+                "mask decoder: derived weights missing (call sam_decoder_prepare) or misaligned");
+    DerivedW dw;
+    carve_derived(s, derived, &dw);
+    return samk_decoder_forward_generic(s, blob, dw.pe_t, image_embeddings, emb_fmt, n_images, img_index, sparse, sparse_fmt, n, k,
+                                        dense_vec, dense_full, dense_fmt, masks, iou, out_fmt, workspace, workspace_bytes, st);
+  }
   SAM_REQUIRE(n_images >= 1 && (img_index || n_images == 1), "mask decoder: img_index is required with several image embeddings");
   SAM_REQUIRE(n <= 65535, "mask decoder: at most 65535 prompts per call");
   // sources of the layer-0 image tokens: the images (shared by their prompts) unless every prompt has its own dense embedding

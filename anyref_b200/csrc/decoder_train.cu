@@ -412,6 +412,18 @@ __global__ void gelu_bwd_kernel(const float* __restrict__ dy, const float* __res
   }
 }
 
+__global__ void to_f32_kernel(const void* __restrict__ src, int fmt, float* __restrict__ dst, i64 n) {
+  GRID_STRIDE(i, n) dst[i] = load_any(src, fmt, static_cast<size_t>(i));
+}
+__global__ void from_f32_kernel(const float* __restrict__ src, void* __restrict__ dst, int fmt, i64 n) {
+  GRID_STRIDE(i, n) {
+    if (fmt == 2)
+      static_cast<float*>(dst)[i] = src[i];
+    else
+      static_cast<uint16_t*>(dst)[i] = ptx::pack1(src[i], fmt);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // layout
 // ---------------------------------------------------------------------------------------------------------------
@@ -548,6 +560,7 @@ struct Tape {
   float* gblob = nullptr;   // gradient of the weight blob (inside the gradient region)
   size_t blob_elems = 0;
   bool overflow = false;   // an op asked for more scratch than the sizing pass reserved
+  bool tape_on = true;     // false: plain forward (no gradient buffers, no adjoints) -- the inference path for T > 16
 
   Ten alloc(i64 rows, int cols, bool grad = true) {
     Ten t;
@@ -555,7 +568,7 @@ struct Tape {
     const size_t bytes = align256(static_cast<size_t>(rows) * cols * 4);
     if (!dry) t.p = reinterpret_cast<float*>(base + act_off);
     act_off += bytes;
-    if (grad) {
+    if (grad && tape_on) {
       if (!dry) t.g = reinterpret_cast<float*>(base + act_cap + grad_off);
       grad_off += bytes;
     }
@@ -644,7 +657,7 @@ struct Tape {
     return 0;
   }
   void push(std::function<int()> f) {
-    if (dry) return;
+    if (dry || !tape_on) return;
     back.push_back(std::move(f));
     back_group.push_back(group);
   }
@@ -962,9 +975,10 @@ int mlp3(Tape& t, const Mlp3P& m, const Ten& x, Ten* y, const Ten* out = nullptr
 struct TrainInputs {
   const float* blob;
   const void* emb; int emb_fmt; int n_images; const int* img_index;
-  const float* sparse;
+  const void* sparse; int sparse_fmt;
   const void* dense_vec; const void* dense_full; int dense_fmt;
-  const void* image_pe; int pe_fmt;
+  const void* image_pe; int pe_fmt;      // [1, C, g, g], or
+  const float* pe_tokens;                // the token-major fp32 copy [HW, C] (sam_decoder_prepare's pe_t)
 };
 
 // The whole forward; in the dry pass (t.dry) it only advances the allocators.
@@ -972,16 +986,23 @@ int build_forward(Tape& t, const TrainInputs& in) {
   const SamDecoderShape& s = t.s;
   const int C = s.C, nm = s.num_mask_tokens, g = s.grid, HW = g * g, n = t.n, k = t.k, T = 1 + nm + k, heads = s.heads;
   const int C1 = C / 4, C2 = C / 8;
-  t.gblob = t.dry ? nullptr : reinterpret_cast<float*>(t.base + t.act_cap + t.grad_off);
-  t.grad_off += align256(t.blob_elems * 4);
+  t.gblob = nullptr;
+  if (t.tape_on) {
+    t.gblob = t.dry ? nullptr : reinterpret_cast<float*>(t.base + t.act_cap + t.grad_off);
+    t.grad_off += align256(t.blob_elems * 4);
+  }
   Params P;
-  carve_params(s, in.blob, t.dry ? nullptr : t.gblob, &P);
+  carve_params(s, in.blob, t.gblob, &P);
   if (P.total != t.blob_elems) return samhost::set_error(1, "decoder training: weight layout mismatch");
 
   // inputs
   t.sparse = t.alloc(static_cast<i64>(n) * k, C);
-  if (!t.dry && k > 0)
-    SAM_CHECK_CUDA(cudaMemcpyAsync(t.sparse.p, in.sparse, static_cast<size_t>(n) * k * C * 4, cudaMemcpyDeviceToDevice, t.st));
+  {
+    const Ten sp = t.sparse;
+    const void* src = in.sparse;
+    const int fmt = in.sparse_fmt;
+    TRY(t.ew(sp.numel(), [&](unsigned nb) { to_f32_kernel<<<nb, 256, 0, t.st>>>(src, fmt, sp.p, sp.numel()); }));
+  }
   Ten tokens0 = t.alloc(static_cast<i64>(n) * T, C);
   {
     const Ten sp = t.sparse, iou_t = P.iou_token, mask_t = P.mask_tokens;
@@ -1003,9 +1024,13 @@ int build_forward(Tape& t, const TrainInputs& in) {
     train_nchw_to_tokens_kernel<<<dim3(HW / 32, C / 32, n), dim3(32, 8), 0, t.st>>>(in.emb, in.emb_fmt, in.img_index, in.dense_vec,
                                                                                   in.dense_full, in.dense_fmt, keys.p, C, HW);
     SAM_CHECK_CUDA(cudaGetLastError());
-    train_nchw_to_tokens_kernel<<<dim3(HW / 32, C / 32, 1), dim3(32, 8), 0, t.st>>>(in.image_pe, in.pe_fmt, nullptr, nullptr, nullptr, 2,
-                                                                                  pe.p, C, HW);
-    SAM_CHECK_CUDA(cudaGetLastError());
+    if (in.pe_tokens) {
+      SAM_CHECK_CUDA(cudaMemcpyAsync(pe.p, in.pe_tokens, static_cast<size_t>(HW) * C * 4, cudaMemcpyDeviceToDevice, t.st));
+    } else {
+      train_nchw_to_tokens_kernel<<<dim3(HW / 32, C / 32, 1), dim3(32, 8), 0, t.st>>>(in.image_pe, in.pe_fmt, nullptr, nullptr, nullptr,
+                                                                                    2, pe.p, C, HW);
+      SAM_CHECK_CUDA(cudaGetLastError());
+    }
   }
 
   Ten queries = tokens0;
@@ -1193,7 +1218,8 @@ int samk_decoder_train_forward(const SamDecoderShape& s, const float* blob, cons
     t->dry = false;
     t->base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~static_cast<uintptr_t>(255));
     t->act_off = t->grad_off = t->scratch_off = 0;
-    TrainInputs in{blob, image_embeddings, emb_fmt, n_images, img_index, sparse, dense_vec, dense_full, dense_fmt, image_pe, pe_fmt};
+    TrainInputs in{blob, image_embeddings, emb_fmt, n_images, img_index, sparse, SAM_F32, dense_vec, dense_full, dense_fmt, image_pe,
+                   pe_fmt, nullptr};
     rc = build_forward(*t, in);
   }
   if (!rc) {
@@ -1245,6 +1271,42 @@ int samk_decoder_backward(void* tape, const float* d_masks, int mask_lo, int mas
 }
 
 void samk_decoder_tape_free(void* tape) { delete static_cast<Tape*>(tape); }
+
+// The same composition without a tape: the inference path for prompts with more tokens than the fused kernels of
+// decoder.cu hold in shared memory (T > 16, e.g. SamPredictor calls with more than 10 points).  Slower, no limit on k.
+size_t samk_decoder_generic_workspace_bytes(const SamDecoderShape& s, int n, int k) {
+  if (check_train_shape(s, n, k)) return 0;
+  Tape t;
+  t.s = s; t.n = n; t.k = k; t.tape_on = false;
+  t.blob_elems = samk_decoder_weight_elems(s);
+  if (size_regions(t)) return 0;
+  return region_total(t);
+}
+
+int samk_decoder_forward_generic(const SamDecoderShape& s, const float* blob, const float* pe_tokens, const void* image_embeddings,
+                                 int emb_fmt, int n_images, const int* img_index, const void* sparse, int sparse_fmt, int n, int k,
+                                 const void* dense_vec, const void* dense_full, int dense_fmt, void* masks, void* iou, int out_fmt,
+                                 void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  if (int rc = check_train_shape(s, n, k)) return rc;
+  SAM_REQUIRE(blob && pe_tokens && image_embeddings && masks && iou && workspace && (k == 0 || sparse), "mask decoder: NULL argument");
+  Tape t;
+  t.s = s; t.n = n; t.k = k; t.st = st; t.tape_on = false;
+  t.blob_elems = samk_decoder_weight_elems(s);
+  TRY(size_regions(t));
+  SAM_REQUIRE(region_total(t) <= workspace_bytes, "mask decoder: workspace of %zu bytes, %zu needed", workspace_bytes, region_total(t));
+  t.dry = false;
+  t.base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~static_cast<uintptr_t>(255));
+  t.act_off = t.grad_off = t.scratch_off = 0;
+  TrainInputs in{blob, image_embeddings, emb_fmt, n_images, img_index, sparse, sparse_fmt, dense_vec, dense_full, dense_fmt, nullptr, 2,
+                 pe_tokens};
+  TRY(build_forward(t, in));
+  const i64 nmask = t.masks.numel(), niou = static_cast<i64>(n) * s.num_mask_tokens;
+  samhost::LaunchScope scope(samhost::KC_DECODER, st, 0.0, 0.0, 2);
+  from_f32_kernel<<<blocks_for(nmask), 256, 0, st>>>(t.masks.p, masks, out_fmt, nmask);
+  from_f32_kernel<<<blocks_for(niou), 256, 0, st>>>(t.iou.p, iou, out_fmt, niou);
+  SAM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // fp32 linear forward / backward for text_hidden_fcs (model/anyref.py:116-124) in training

@@ -111,6 +111,12 @@ int samk_decoder_train_forward(const SamDecoderShape& s, const float* blob, cons
 int samk_decoder_backward(void* tape, const float* d_masks, int mask_lo, int mask_hi, const float* d_iou, float* d_weights,
                           float* d_sparse, cudaStream_t st);
 void samk_decoder_tape_free(void* tape);
+// the same composition without a tape: inference for more tokens per prompt than decoder.cu's fused kernels hold
+size_t samk_decoder_generic_workspace_bytes(const SamDecoderShape& s, int n, int k);
+int samk_decoder_forward_generic(const SamDecoderShape& s, const float* blob, const float* pe_tokens, const void* image_embeddings,
+                                 int emb_fmt, int n_images, const int* img_index, const void* sparse, int sparse_fmt, int n, int k,
+                                 const void* dense_vec, const void* dense_full, int dense_fmt, void* masks, void* iou, int out_fmt,
+                                 void* workspace, size_t workspace_bytes, cudaStream_t st);
 size_t samk_linear_f32_scratch_bytes(int M, int N, int K);
 int samk_linear_f32_forward(const float* X, const float* W, const float* b, float* Y, int M, int N, int K, int relu_act, cudaStream_t st);
 int samk_linear_f32_backward(float* dY, const float* relu_y, const float* X, const float* W, float* dX, float* dW, float* db, int M, int N, int K,

@@ -175,7 +175,8 @@ int sam_encoder_forward(const SamEncoderShape* shape, const void* w16, const flo
  *                    ((keys + pe).W^T = keys.W^T + pe.W^T; prompt_encoder.get_dense_pe() is a constant of the model)
  *   image_pe         [1, C, g, g] pe_fmt, PromptEncoder.get_dense_pe()  (argument of sam_decoder_prepare)
  *   image_embeddings [n_images, C, g, g] emb_fmt
- *   sparse           [n, k, C] sparse_fmt (the [SEG] embeddings; tokens = [iou, mask x4, sparse...]); 5 + k <= 16
+ *   sparse           [n, k, C] sparse_fmt (the [SEG] embeddings; tokens = [iou, mask x4, sparse...]); up to 5 + k = 16
+ *                    tokens run on the fused token kernels, more on a plain (slower) fp32 composition of the same call
  *   dense_vec        [C] (no_mask_embed broadcast, prompt_encoder.py:181-184) or NULL;
  *   dense_full       [n, C, g, g] or NULL (mask prompts); both in dense_fmt
  *   masks            [n, num_mask_tokens, 4g, 4g] out_fmt -- ALL mask tokens (caller slices [0:1] or [1:], :106-111)

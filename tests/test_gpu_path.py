@@ -105,8 +105,8 @@ def test_decoder_with_several_prompt_tokens_and_dense_input(tiny):
 
 @pytest.mark.parametrize("k", [4, 11])
 def test_decoder_with_up_to_sixteen_tokens_per_prompt(tiny, k):
-    """T = 5 + k tokens per prompt: k = 4 is the first size on the 16-token kernel instances, k = 11 the maximum
-    (T = 16); one more sparse embedding must raise instead of computing something else."""
+    """T = 5 + k tokens per prompt: k = 4 is the first size on the 16-token kernel instances, k = 11 the last one
+    (T = 16) of the fused token kernels."""
     sam, cfg, sd = tiny["sam"], tiny["cfg"], tiny["sd"]
     g = torch.Generator().manual_seed(50 + k)
     sparse = torch.randn(3, k, 256, generator=g)
@@ -118,11 +118,27 @@ def test_decoder_with_up_to_sixteen_tokens_per_prompt(tiny, k):
                                 multimask_output=True)
     assert (low.cpu() - low_ref).abs().max().item() < 2e-5
     assert (iou.cpu() - iou_ref).abs().max().item() < 2e-5
-    if k == 11:
-        too_many = torch.randn(1, 12, 256, generator=g).cuda()
-        with pytest.raises(RuntimeError, match="tokens per prompt"):
-            sam.mask_decoder(image_embeddings=tiny["emb"][1:2].cuda(), image_pe=sam.prompt_encoder.get_dense_pe(),
-                             sparse_prompt_embeddings=too_many, dense_prompt_embeddings=dense[:1], multimask_output=True)
+
+
+@pytest.mark.parametrize("k,dt", [(12, torch.float32), (40, torch.float16)])
+def test_decoder_beyond_sixteen_tokens_uses_the_generic_path(tiny, k, dt):
+    """More than 11 sparse prompt embeddings per prompt (many clicks): the fused token kernels hold at most 16 tokens in
+    shared memory, beyond that the same call runs the plain fp32 composition (csrc/decoder_train.cu without its tape).
+    Same tolerance vs the oracle; 16-bit embeddings / outputs only add their own rounding."""
+    sam, cfg, sd = tiny["sam"], tiny["cfg"], tiny["sd"]
+    g = torch.Generator().manual_seed(70 + k)
+    sparse = torch.randn(2, k, 256, generator=g)
+    emb = tiny["emb"][1:2].to(dt)
+    _, dense_ref = O.prompt_encoder(sd, cfg, text_embeds=sparse[:, :1])
+    low_ref, iou_ref = O.mask_decoder(sd, cfg, emb.float(), tiny["pe"], sparse.to(dt).float(), dense_ref, True)
+    _, dense = sam.prompt_encoder(points=None, boxes=None, masks=None, text_embeds=sparse[:, :1].cuda())
+    low, iou = sam.mask_decoder(image_embeddings=emb.cuda(), image_pe=sam.prompt_encoder.get_dense_pe(),
+                                sparse_prompt_embeddings=sparse.cuda().to(dt), dense_prompt_embeddings=dense,
+                                multimask_output=True)
+    assert low.dtype == dt and low.shape == (2, 3, 256, 256)
+    tol = 2e-5 if dt == torch.float32 else 2e-3 * float(low_ref.abs().max())
+    assert (low.float().cpu() - low_ref).abs().max().item() < tol
+    assert (iou.float().cpu() - iou_ref).abs().max().item() < (2e-5 if dt == torch.float32 else 2e-3)
 
 
 def test_batched_decoder_with_promptless_images(tiny):
