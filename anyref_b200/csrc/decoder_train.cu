@@ -22,6 +22,7 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <functional>
 #include <vector>
 
@@ -412,6 +413,41 @@ __global__ void gelu_bwd_kernel(const float* __restrict__ dy, const float* __res
   }
 }
 
+// split-bf16 operands of the tensor-core GEMM (x = hi + lo, x.w ~ hi.hi + hi.lo + lo.hi as ONE product over 3K):
+// activations [rows, K] -> [rows, 3K] = [hi | hi | lo], weights [N, K] -> [N, 3K] = [hi | lo | hi]
+__device__ __forceinline__ void split_bf16(float x, uint16_t& hi, uint16_t& lo) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(x);
+  const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+  hi = *reinterpret_cast<const uint16_t*>(&h);
+  lo = *reinterpret_cast<const uint16_t*>(&l);
+}
+__global__ void split_act_kernel(const float* __restrict__ X, uint16_t* __restrict__ A3, i64 rows, int K) {
+  GRID_STRIDE(i, rows * K) {
+    const i64 r = i / K;
+    const int c = static_cast<int>(i - r * K);
+    uint16_t h, l;
+    split_bf16(X[i], h, l);
+    uint16_t* o = A3 + r * (3 * K) + c;
+    o[0] = h; o[K] = h; o[2 * K] = l;
+  }
+}
+// W [N, K] (element (n, k) at W[n*K + k]) -> out [R, 3*Cc] with (r, c) = (n, k), or (k, n) when transposed
+__global__ void split_weight_kernel(const float* __restrict__ W, uint16_t* __restrict__ out, int N, int K, int transposed) {
+  const int R = transposed ? K : N, Cc = transposed ? N : K;
+  GRID_STRIDE(i, static_cast<i64>(R) * Cc) {
+    const int r = static_cast<int>(i / Cc), c = static_cast<int>(i - static_cast<i64>(r) * Cc);
+    const float x = transposed ? W[static_cast<i64>(c) * K + r] : W[static_cast<i64>(r) * K + c];
+    uint16_t h, l;
+    split_bf16(x, h, l);
+    uint16_t* o = out + static_cast<i64>(r) * (3 * Cc) + c;
+    o[0] = h; o[Cc] = l; o[2 * Cc] = h;
+  }
+}
+__global__ void tile_bias_kernel(const float* __restrict__ b, float* __restrict__ out, int N, int mod) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < N) out[j] = b[j % mod];
+}
+
 __global__ void to_f32_kernel(const void* __restrict__ src, int fmt, float* __restrict__ dst, i64 n) {
   GRID_STRIDE(i, n) dst[i] = load_any(src, fmt, static_cast<size_t>(i));
 }
@@ -560,6 +596,7 @@ struct Tape {
   float* gblob = nullptr;   // gradient of the weight blob (inside the gradient region)
   size_t blob_elems = 0;
   bool overflow = false;   // an op asked for more scratch than the sizing pass reserved
+  bool use_tc = getenv("SAM_TRAIN_SIMT") == nullptr;   // image-side products (>= 8192 rows) on the split-bf16 tcgen05 GEMM; SAM_TRAIN_SIMT=1 turns it off
   bool tape_on = true;     // false: plain forward (no gradient buffers, no adjoints) -- the inference path for T > 16
 
   Ten alloc(i64 rows, int cols, bool grad = true) {
@@ -623,6 +660,38 @@ struct Tape {
     }
     return 0;
   }
+  // Image-side products on the tensor cores: C[M, N] (+)= A[M, K] . op(W) with both operands split into bf16 pairs
+  // (fp32-accurate: the dropped lo.lo term is 2^-18 relative) and run by the tcgen05 GEMM of the inference path.
+  //   transposed = false: C = A . W^T + bias   (W [N, K]);   transposed = true: C += A . W   (W [K, N] i.e. dX = dY . W)
+  static bool tc_eligible(i64 M, int N, int K, i64 lda, i64 ldc) {
+    return M >= 8192 && M <= 0x7fffffff && K % 64 == 0 && N % 8 == 0 && lda == K && ldc == N;
+  }
+  int gemm_tc(const float* A, i64 M, int K, const float* W, int N, bool transposed, const float* bias, int bias_mod, float* Cout,
+              bool accumulate) {
+    // scratch is claimed in the dry pass too (sizing)
+    uint16_t* A3 = reinterpret_cast<uint16_t*>(scratch(static_cast<size_t>(M) * 3 * K * 2));
+    uint16_t* W3 = reinterpret_cast<uint16_t*>(scratch(static_cast<size_t>(N) * 3 * K * 2));
+    float* btile = (bias && bias_mod != N) ? scratch(static_cast<size_t>(N) * 4) : nullptr;
+    if (dry) return 0;
+    SAM_REQUIRE(!overflow, "decoder training: scratch region too small (internal sizing error)");
+    {
+      samhost::LaunchScope scope(samhost::KC_DECODER, st, 0.0, static_cast<double>(M) * K * 10.0, 2);
+      split_act_kernel<<<blocks_for(M * K), 256, 0, st>>>(A, A3, M, K);
+      // the GEMM wants W as [N, K] rows: for dX = dY . W that is W^T
+      split_weight_kernel<<<blocks_for(static_cast<i64>(N) * K), 256, 0, st>>>(W, W3, transposed ? K : N, transposed ? N : K,
+                                                                             transposed ? 1 : 0);
+      SAM_CHECK_CUDA(cudaGetLastError());
+    }
+    if (btile) {
+      samhost::LaunchScope scope(samhost::KC_DECODER, st);
+      tile_bias_kernel<<<(N + 255) / 256, 256, 0, st>>>(bias, btile, N, bias_mod);
+      SAM_CHECK_CUDA(cudaGetLastError());
+      bias = btile;
+    }
+    samhost::ClassOverride as_decoder(samhost::KC_DECODER);
+    GemmEpilogue ep{Cout, N, SAM_F32, bias, 0, accumulate ? Cout : nullptr, accumulate ? N : 0, accumulate ? static_cast<int>(M) : 0};
+    return samk_gemm(A3, 3 * K, W3, 3 * K, static_cast<int>(M), N, 3 * K, SAM_BF16, ep, st);
+  }
   // out[j % mod] += sum_r X[r, j]
   int colsum(const float* X, i64 ld, i64 R, int N, int mod, float* out) {
     const int chunks = static_cast<int>((R + kColRows - 1) / kColRows);
@@ -676,21 +745,28 @@ int linear(Tape& t, const Ten& X, const Ten& W, const Ten& b, Ten* Y, int bias_m
   if (X.cols != K) return samhost::set_error(1, "decoder training: linear K mismatch (%d vs %d)", X.cols, K);
   *Y = out ? *out : t.alloc(X.rows, N);
   const int M = static_cast<int>(X.rows);
-  Gemm g{};
-  g.A = X.p; g.ars = X.ld; g.acs = 1;
-  g.B = W.p; g.brs = 1; g.bcs = K;
-  g.C = Y->p; g.crs = Y->ld;
-  g.bias = b.p; g.bias_mod = bias_mod ? bias_mod : N;
-  g.M = M; g.N = N; g.K = K; g.alpha = 1.f;
-  if (t.dry) g.bias = nullptr;
-  TRY(t.gemm(g));
+  const int bm = bias_mod ? bias_mod : N;
+  const bool tc_fwd = t.use_tc && Tape::tc_eligible(X.rows, N, K, X.ld, Y->ld);
+  if (tc_fwd) {
+    TRY(t.gemm_tc(X.p, X.rows, K, W.p, N, false, b.p, bm, Y->p, false));
+  } else {
+    Gemm g{};
+    g.A = X.p; g.ars = X.ld; g.acs = 1;
+    g.B = W.p; g.brs = 1; g.bcs = K;
+    g.C = Y->p; g.crs = Y->ld;
+    g.bias = b.p; g.bias_mod = bm;
+    g.M = M; g.N = N; g.K = K; g.alpha = 1.f;
+    if (t.dry) g.bias = nullptr;
+    TRY(t.gemm(g));
+  }
   t.scratch_reset();
   const Ten Yc = *Y;
-  const int bm = g.bias_mod;
   Tape* tp = &t;
   t.push([tp, X, W, b, Yc, M, N, K, bm]() -> int {
     Tape& t = *tp;
-    if (X.g) {   // dX += dY . W
+    if (X.g && t.use_tc && Tape::tc_eligible(M, K, N, Yc.ld, X.ld)) {   // dX += dY . W on the tensor cores
+      TRY(t.gemm_tc(Yc.g, M, N, W.p, K, true, nullptr, 0, X.g, true));
+    } else if (X.g) {   // dX += dY . W
       Gemm g{};
       g.A = Yc.g; g.ars = Yc.ld; g.acs = 1;
       g.B = W.p; g.brs = K; g.bcs = 1;
@@ -1173,6 +1249,9 @@ int size_regions(Tape& t) {
   const i64 rows_max = static_cast<i64>(t.n) * HW * 4;
   // column-sum partials and LayerNorm block partials: rows / 64 * 2C floats at most
   bound = std::max(bound, align256(static_cast<size_t>((rows_max + 63) / 64 + 1) * 2 * s.C * 4));
+  // split-bf16 operands of the tensor-core products: rows x 3 x width x 2 bytes, widest for the gradient of the second
+  // ConvTranspose2d ([n * 4 HW, 128]) and for the [n * HW, 256] tensors; plus the split weight and a tiled bias
+  bound = std::max(bound, align256(static_cast<size_t>(rows_max) * 3 * (s.C / 2) * 2) + align256(static_cast<size_t>(s.C) * 3 * s.C * 2 * 2) + 4096);
   t.act_cap = align256(t.act_off);
   t.grad_cap = align256(t.grad_off);
   t.scratch_cap = 2 * std::max(bound, t.scratch_peak) + 4096;

@@ -85,6 +85,22 @@ def compare_param_grads(sam, osd, tol=5e-5):
     return worst, checked
 
 
+def references_agree(osd64, osd32, extra64=(), extra32=(), tol=2e-5):
+    """The decoder is piecewise linear in places (ReLU in the MLPs): when a pre-activation sits within rounding of zero,
+    fp32 and fp64 evaluations take different branches and their gradients differ by 1e-3 -- both valid.  Such an input
+    says nothing about an implementation, so the gradient tests only use cases on which stock fp32 autograd and fp64
+    autograd over the oracle agree (tools/gpu_train_diag.py shows one that does not)."""
+    names = [k for k in osd64 if k.startswith("mask_decoder.") and osd64[k].grad is not None]
+    gmax = max(float(osd64[k].grad.norm()) for k in names)
+    for k in names:
+        if k.endswith("k_proj.bias"):
+            continue
+        a, b = osd64[k].grad, osd32[k].grad.double()
+        if float((a - b).norm()) > tol * (float(a.norm()) + 1e-6 * gmax) * 5:
+            return False
+    return all(rel_fro(b, a) < tol * 5 for a, b in zip(extra64, extra32))
+
+
 def zero_grads(sam):
     for p in sam.parameters():
         p.grad = None
@@ -118,12 +134,6 @@ def test_decoder_gradients_match_autograd_on_the_oracle(setup, n, k):
     """All four mask tokens and the IoU head enter the loss (two calls: multimask False and True, so the gradients of
     two tapes accumulate into .grad), with random cotangents."""
     sam, cfg = setup["sam"], setup["cfg"]
-    zero_grads(sam)
-    osd = oracle_sd(setup["sd"])
-    g = torch.Generator().manual_seed(100 + 10 * n + k)
-    sparse0 = torch.randn(n, k, 256, generator=g).cuda()
-    dense = osd["prompt_encoder.no_mask_embed.weight"].detach().reshape(1, -1, 1, 1).expand(n, -1, 64, 64)
-    dense32 = dense.float()
     emb, pe = setup["emb"][1:2], setup["pe"]
 
     def loss_of(fn, sparse):
@@ -136,17 +146,32 @@ def test_decoder_gradients_match_autograd_on_the_oracle(setup, n, k):
             total = total + (m * rm).sum() / 256.0 + (i * ri).sum()
         return total
 
-    s_ref = sparse0.double().requires_grad_(True)
-    loss_ref = loss_of(lambda sp, multi: O.mask_decoder(osd, cfg, emb.double(), pe.double(), sp, dense, multi), s_ref)
-    loss_ref.backward()
-    s_got = sparse0.clone().requires_grad_(True)
-    loss_got = loss_of(lambda sp, multi: sam.mask_decoder(image_embeddings=emb, image_pe=pe, sparse_prompt_embeddings=sp,
-                                                          dense_prompt_embeddings=dense32, multimask_output=multi), s_got)
-    loss_got.backward()
-    assert abs(float(loss_got.detach()) - float(loss_ref.detach())) <= 1e-4 * max(1.0, abs(float(loss_ref.detach())))
-    assert rel_fro(s_got.grad, s_ref.grad) < 5e-5
-    worst, checked = compare_param_grads(sam, osd)
-    assert checked >= 95, checked        # every tensor of the decoder gets a gradient from this loss
+    def reference(sparse0, dtype):
+        osd = oracle_sd(setup["sd"], dtype=dtype)
+        dense = osd["prompt_encoder.no_mask_embed.weight"].detach().reshape(1, -1, 1, 1).expand(n, -1, 64, 64)
+        s_ref = sparse0.detach().clone().to(dtype).requires_grad_(True)
+        loss = loss_of(lambda sp, multi: O.mask_decoder(osd, cfg, emb.to(dtype), pe.to(dtype), sp, dense, multi), s_ref)
+        loss.backward()
+        return osd, s_ref, loss.detach(), dense
+
+    for seed in range(100 + 10 * n + k, 100 + 10 * n + k + 600, 100):
+        g = torch.Generator().manual_seed(seed)
+        sparse0 = torch.randn(n, k, 256, generator=g).cuda()
+        osd, s_ref, loss_ref, dense = reference(sparse0, torch.float64)
+        osd32, s_ref32, _, _ = reference(sparse0, torch.float32)
+        if not references_agree(osd, osd32, [s_ref.grad], [s_ref32.grad]):
+            continue
+        zero_grads(sam)
+        s_got = sparse0.clone().requires_grad_(True)
+        loss_got = loss_of(lambda sp, multi: sam.mask_decoder(image_embeddings=emb, image_pe=pe, sparse_prompt_embeddings=sp,
+                                                              dense_prompt_embeddings=dense.float(), multimask_output=multi), s_got)
+        loss_got.backward()
+        assert abs(float(loss_got.detach()) - float(loss_ref)) <= 1e-4 * max(1.0, abs(float(loss_ref)))
+        assert rel_fro(s_got.grad, s_ref.grad) < 5e-5
+        worst, checked = compare_param_grads(sam, osd)
+        assert checked >= 95, checked        # every tensor of the decoder gets a gradient from this loss
+        return
+    pytest.fail("no well-conditioned case among the candidate seeds")
 
 
 def test_batched_training_call_matches_per_image_calls(setup):
