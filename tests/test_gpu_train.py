@@ -310,6 +310,44 @@ def test_training_step_like_the_reference(setup):
     assert checked >= 80
 
 
+def test_training_with_bf16_parameters_and_embeddings(setup):
+    """AnyRef trains in bf16 (DeepSpeed): parameters, image embeddings and the [SEG] embedding arrive as bfloat16.  The
+    training path computes in fp32 on exactly those values, so its gradients must equal -- to bf16 rounding of the
+    returned tensors -- the gradients of an fp32 model holding the same (bf16-representable) values."""
+    import copy
+
+    sam = setup["sam"]
+    dec16 = copy.deepcopy(sam.mask_decoder).to(torch.bfloat16)
+    dec32 = copy.deepcopy(dec16).float()
+    for d in (dec16, dec32):
+        d.train()
+        d.invalidate_packed()
+    g = torch.Generator().manual_seed(31)
+    sparse0 = torch.randn(2, 1, 256, generator=g).cuda().to(torch.bfloat16)
+    emb = setup["emb"][:1].to(torch.bfloat16)
+    dense = sam.prompt_encoder.no_mask_embed.weight.detach().to(torch.bfloat16).reshape(1, -1, 1, 1).expand(2, -1, 64, 64)
+    cot = torch.randn(2, 1, 256, 256, generator=g).cuda()
+    outs = []
+    for d, dt in ((dec16, torch.bfloat16), (dec32, torch.float32)):
+        sp = sparse0.detach().clone().to(dt).requires_grad_(True)
+        m, _ = d(image_embeddings=emb.to(dt), image_pe=setup["pe"], sparse_prompt_embeddings=sp,
+                 dense_prompt_embeddings=dense.to(dt), multimask_output=False)
+        assert m.dtype == torch.float32
+        (m * cot).sum().backward()
+        outs.append((m.detach(), sp.grad))
+    assert torch.equal(outs[0][0], outs[1][0])                       # same fp32 arithmetic on the same values
+    assert outs[0][1].dtype == torch.bfloat16 and rel_fro(outs[0][1], outs[1][1]) < 4e-3
+    checked = 0
+    for (name, p16), (_, p32) in zip(dec16.named_parameters(), dec32.named_parameters()):
+        if p32.grad is None or float(p32.grad.abs().max()) == 0.0:
+            continue
+        assert p16.grad is not None and p16.grad.dtype == torch.bfloat16, name
+        if not name.endswith("k_proj.bias"):
+            assert rel_fro(p16.grad, p32.grad) < 4e-3, name
+        checked += 1
+    assert checked >= 60
+
+
 def test_image_without_seg_token_in_training(setup):
     """model/anyref.py:406-430 also visits images whose sample has no [SEG] token: empty masks, empty loss, zero grads."""
     sam = setup["sam"]
