@@ -348,6 +348,60 @@ def test_training_with_bf16_parameters_and_embeddings(setup):
     assert checked >= 60
 
 
+def test_finetuning_follows_the_reference_trajectory(setup):
+    """Eight AdamW steps on a fixed batch (mask decoder + text_hidden_fcs trainable, BCE + dice on the post-processed
+    logits): the loss must go down and follow, step by step, the trajectory of the same optimisation run with stock
+    PyTorch autograd over the oracle's modules from the same initial weights -- this exercises what the single-step
+    gradient tests cannot: every step's forward has to see the weights the optimizer just wrote."""
+    import copy
+
+    from anyref_b200.seg_head import build_text_hidden_fcs
+
+    sam, cfg = setup["sam"], setup["cfg"]
+    dec = copy.deepcopy(sam.mask_decoder).float().train()
+    dec.invalidate_packed()
+    H = 256
+    fcs = build_text_hidden_fcs(H, 256).cuda()
+    osd = {"mask_decoder." + k: v.detach().clone().requires_grad_(True) for k, v in dec.state_dict().items()}
+    osd["prompt_encoder.no_mask_embed.weight"] = sam.prompt_encoder.no_mask_embed.weight.detach().clone()
+    ref_fcs = torch.nn.Sequential(torch.nn.Linear(H, H), torch.nn.ReLU(), torch.nn.Linear(H, 256)).cuda()
+    ref_fcs[0].load_state_dict(fcs[0][0].state_dict())
+    ref_fcs[2].load_state_dict(fcs[0][2].state_dict())
+    g = torch.Generator().manual_seed(77)
+    hidden = torch.randn(2, H, generator=g).cuda()
+    gt = (torch.rand(2, 320, 480, generator=g) > 0.7).float().cuda()
+    emb, pe = setup["emb"][:1], setup["pe"]
+    dense = osd["prompt_encoder.no_mask_embed.weight"].reshape(1, -1, 1, 1).expand(2, -1, 64, 64)
+
+    def loss_of(pm):
+        return 2.0 * sigmoid_ce_loss(pm, gt, 2) + 0.5 * dice_loss(pm, gt, 2)
+
+    mine_params = list(dec.parameters()) + list(fcs.parameters())
+    ref_params = [osd[k] for k in osd if k.startswith("mask_decoder.")] + list(ref_fcs.parameters())
+    opt_a = torch.optim.AdamW(mine_params, lr=3e-4, weight_decay=0.0)
+    opt_b = torch.optim.AdamW(ref_params, lr=3e-4, weight_decay=0.0)
+    traj_a, traj_b = [], []
+    for step in range(8):
+        opt_a.zero_grad(set_to_none=True)
+        sp = fcs[0](hidden).unsqueeze(1)
+        low, _ = dec(image_embeddings=emb, image_pe=pe, sparse_prompt_embeddings=sp, dense_prompt_embeddings=dense,
+                     multimask_output=False)
+        la = loss_of(sam.postprocess_masks(low, input_size=(683, 1024), original_size=(320, 480)).squeeze(1))
+        la.backward()
+        opt_a.step()
+        traj_a.append(float(la.detach()))
+        opt_b.zero_grad(set_to_none=True)
+        spb = ref_fcs(hidden).unsqueeze(1)
+        lowb, _ = O.mask_decoder(osd, cfg, emb, pe, spb, dense, False)
+        lb = loss_of(O.postprocess_masks(lowb, (683, 1024), (320, 480)).squeeze(1))
+        lb.backward()
+        opt_b.step()
+        traj_b.append(float(lb.detach()))
+    assert traj_a[-1] < traj_a[0] - 0.08, traj_a                     # it learns (random targets: the floor is ~1.5)
+    for a, b in zip(traj_a, traj_b):
+        assert abs(a - b) <= 2e-3 * abs(b), (traj_a, traj_b)        # and follows the reference run (Adam amplifies 1e-6)
+
+
 def test_image_without_seg_token_in_training(setup):
     """model/anyref.py:406-430 also visits images whose sample has no [SEG] token: empty masks, empty loss, zero grads."""
     sam = setup["sam"]
