@@ -62,6 +62,7 @@ struct Gemm {
   const float* bias;   // [bias_mod] or null: added as bias[j % bias_mod]
   int M, N, K;
   i64 ars, acs, brs, bcs, crs;
+  i64 ccs;   // column stride of C (0 = 1)
   int nbatch, nb2;
   i64 a_b1, a_b2, b_b1, b_b2, c_b1, c_b2;
   int bias_mod;
@@ -69,6 +70,7 @@ struct Gemm {
   int accumulate;
   int splits, kchunk;
   float* partial;
+  int part_rows;   // rows per partial block (0: M) -- the tensor-core weight gradient pads its blocks to 256 rows
 };
 
 constexpr int GT = 64, GK = 16;       // the general tile
@@ -180,25 +182,72 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const Gemm g) {
       if (gj >= g.N) continue;
       float v = g.alpha * acc[i][j];
       if (g.bias) v += g.bias[gj % g.bias_mod];
-      float* c = Cb + gi * g.crs + gj;
+      float* c = Cb + gi * g.crs + gj * (g.ccs ? g.ccs : 1);
       *c = g.accumulate ? *c + v : v;
+    }
+  }
+}
+
+// Tall and shallow products (M >= 1024 rows, N <= 32, K <= 32: attention of 4096 pixels against 6 tokens, the mask
+// product, ...): one thread per output row, B (K x N) in shared memory; no tile padding, every byte read is used.
+// grid (ceil(M / 256), batch), block 256
+template <int NT>
+__global__ void __launch_bounds__(256) sgemm_rows_kernel(const Gemm g) {
+  __shared__ float Bs[32][NT + 1];
+  const int batch = blockIdx.y;
+  const int b1 = batch / g.nb2, b2 = batch - b1 * g.nb2;
+  const float* __restrict__ A = g.A + b1 * g.a_b1 + b2 * g.a_b2;
+  const float* __restrict__ B = g.B + b1 * g.b_b1 + b2 * g.b_b2;
+  for (int idx = threadIdx.x; idx < g.K * NT; idx += 256) {
+    const int k = idx / NT, j = idx - k * NT;
+    Bs[k][j] = j < g.N ? B[k * g.brs + j * g.bcs] : 0.f;
+  }
+  __syncthreads();
+  const int row = blockIdx.x * 256 + threadIdx.x;
+  if (row >= g.M) return;
+  float acc[NT];
+#pragma unroll
+  for (int j = 0; j < NT; ++j) acc[j] = 0.f;
+  const float* a = A + row * g.ars;
+  for (int k = 0; k < g.K; ++k) {
+    const float av = a[k * g.acs];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) acc[j] = fmaf(av, Bs[k][j], acc[j]);
+  }
+  float* c = g.C + b1 * g.c_b1 + b2 * g.c_b2 + row * g.crs;
+  const i64 ccs = g.ccs ? g.ccs : 1;
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    if (j < g.N) {
+      float v = g.alpha * acc[j];
+      if (g.bias) v += g.bias[j % g.bias_mod];
+      c[j * ccs] = g.accumulate ? c[j * ccs] + v : v;
     }
   }
 }
 
 __global__ void splitk_reduce_kernel(const Gemm g) {
   const i64 per = static_cast<i64>(g.M) * g.N;
+  const i64 pitch = static_cast<i64>(g.part_rows ? g.part_rows : g.M) * g.N;   // elements per partial block
   const i64 total = per * g.nbatch;
   for (i64 t = static_cast<i64>(blockIdx.x) * blockDim.x + threadIdx.x; t < total; t += static_cast<i64>(gridDim.x) * blockDim.x) {
     const int batch = static_cast<int>(t / per);
     const i64 r = t - batch * per;
     const int i = static_cast<int>(r / g.N), j = static_cast<int>(r - static_cast<i64>(i) * g.N);
-    float s = 0.f;
-    for (int sp = 0; sp < g.splits; ++sp) s += g.partial[(static_cast<i64>(sp) * g.nbatch + batch) * per + r];
-    float v = g.alpha * s;
+    // four independent chains (loads in flight), combined in a fixed order: deterministic
+    float s4[4] = {0.f, 0.f, 0.f, 0.f};
+    const float* pp = g.partial + static_cast<i64>(batch) * pitch + r;
+    const i64 step = static_cast<i64>(g.nbatch) * pitch;
+    int sp = 0;
+    for (; sp + 4 <= g.splits; sp += 4) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) s4[u] += pp[(sp + u) * step];
+    }
+    for (; sp < g.splits; ++sp) s4[0] += pp[sp * step];
+    float v = g.alpha * ((s4[0] + s4[1]) + (s4[2] + s4[3]));
     if (g.bias) v += g.bias[j % g.bias_mod];
     const int b1 = batch / g.nb2, b2 = batch - b1 * g.nb2;
-    float* c = g.C + b1 * g.c_b1 + b2 * g.c_b2 + i * g.crs + j;
+    float* c = g.C + b1 * g.c_b1 + b2 * g.c_b2 + i * g.crs + j * (g.ccs ? g.ccs : 1);
     *c = g.accumulate ? *c + v : v;
   }
 }
@@ -421,14 +470,21 @@ __device__ __forceinline__ void split_bf16(float x, uint16_t& hi, uint16_t& lo) 
   hi = *reinterpret_cast<const uint16_t*>(&h);
   lo = *reinterpret_cast<const uint16_t*>(&l);
 }
+// four consecutive elements per thread (K % 4 == 0): one 16-byte load, three 8-byte stores
 __global__ void split_act_kernel(const float* __restrict__ X, uint16_t* __restrict__ A3, i64 rows, int K) {
-  GRID_STRIDE(i, rows * K) {
-    const i64 r = i / K;
-    const int c = static_cast<int>(i - r * K);
-    uint16_t h, l;
-    split_bf16(X[i], h, l);
+  const int K4 = K >> 2;
+  GRID_STRIDE(i, rows * K4) {
+    const i64 r = i / K4;
+    const int c = static_cast<int>(i - r * K4) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(X + r * K + c);
+    uint16_t h[4], l[4];
+    split_bf16(v.x, h[0], l[0]); split_bf16(v.y, h[1], l[1]); split_bf16(v.z, h[2], l[2]); split_bf16(v.w, h[3], l[3]);
+    const uint2 H = make_uint2(h[0] | (uint32_t(h[1]) << 16), h[2] | (uint32_t(h[3]) << 16));
+    const uint2 Lo = make_uint2(l[0] | (uint32_t(l[1]) << 16), l[2] | (uint32_t(l[3]) << 16));
     uint16_t* o = A3 + r * (3 * K) + c;
-    o[0] = h; o[K] = h; o[2 * K] = l;
+    *reinterpret_cast<uint2*>(o) = H;
+    *reinterpret_cast<uint2*>(o + K) = H;
+    *reinterpret_cast<uint2*>(o + 2 * K) = Lo;
   }
 }
 // W [N, K] (element (n, k) at W[n*K + k]) -> out [R, 3*Cc] with (r, c) = (n, k), or (k, n) when transposed
@@ -441,6 +497,35 @@ __global__ void split_weight_kernel(const float* __restrict__ W, uint16_t* __res
     split_bf16(x, h, l);
     uint16_t* o = out + static_cast<i64>(r) * (3 * Cc) + c;
     o[0] = h; o[Cc] = l; o[2 * Cc] = h;
+  }
+}
+// Operands of a weight gradient dW[N, K] = dY^T . X on the tensor cores.  The reduction runs over the rows, so both
+// operands are needed transposed; they are written chunk-major for the block-diagonal GEMM (GemmEpilogue::diag_*):
+//   out[(s * pitch + i) * 3L + c] = split(Y[s * L + c, i])   for chunk s of L rows (zero beyond the last row),
+// [hi | hi | lo] for the A role (dY), [hi | lo | hi] for the W role (X).   grid (L/64, ceil(N/32), S), block (32, 8)
+__global__ void __launch_bounds__(256)
+split_transposed_kernel(const float* __restrict__ Y, i64 ld, i64 rows, int N, int L, int pitch, int w_role, uint16_t* __restrict__ out) {
+  __shared__ float tile[64][33];   // [c][i]
+  const int s = blockIdx.z;
+  const int c0 = blockIdx.x * 64, i0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 64; r += 8) {
+    const i64 row = static_cast<i64>(s) * L + c0 + r;
+    const int i = i0 + threadIdx.x;
+    tile[r][threadIdx.x] = (row < rows && i < N) ? Y[row * ld + i] : 0.f;
+  }
+  __syncthreads();
+  // a thread writes the pair (c, c + 1) of one output row: 128 bytes per warp and store
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int i = i0 + r, c = c0 + 2 * threadIdx.x;
+    if (i >= N) continue;
+    uint16_t h0, l0, h1, l1;
+    split_bf16(tile[2 * threadIdx.x][r], h0, l0);
+    split_bf16(tile[2 * threadIdx.x + 1][r], h1, l1);
+    const uint32_t H = h0 | (uint32_t(h1) << 16), Lo = l0 | (uint32_t(l1) << 16);
+    uint16_t* o = out + (static_cast<i64>(s) * pitch + i) * (3 * L) + c;
+    *reinterpret_cast<uint32_t*>(o) = H;
+    *reinterpret_cast<uint32_t*>(o + L) = w_role ? Lo : H;
+    *reinterpret_cast<uint32_t*>(o + 2 * L) = w_role ? H : Lo;
   }
 }
 __global__ void tile_bias_kernel(const float* __restrict__ b, float* __restrict__ out, int N, int mod) {
@@ -628,6 +713,34 @@ struct Tape {
     if (g.bias_mod <= 0) g.bias_mod = g.N;
     // few output tiles + a long reduction (weight gradients, attention over 4096 pixels): split K so that ~4 CTAs per SM
     // exist (a CTA's k-step is latency-bound: one tile of prefetch); the partials are folded in index order (deterministic)
+    // tall and shallow (or, transposed, wide and shallow): the one-thread-per-row kernel
+    if (!g.bias && g.K <= 32 && g.K >= 1 && ((g.N <= 32 && g.M >= 1024) || (g.M <= 32 && g.N >= 1024))) {
+      if (g.M <= 32 && g.N >= 1024 && !(g.N <= 32 && g.M >= 1024)) {
+        // C^T = B^T . A^T: swap the operands and the roles of the output's strides
+        Gemm t2 = g;
+        t2.A = g.B; t2.ars = g.bcs; t2.acs = g.brs; t2.a_b1 = g.b_b1; t2.a_b2 = g.b_b2;
+        t2.B = g.A; t2.brs = g.acs; t2.bcs = g.ars; t2.b_b1 = g.a_b1; t2.b_b2 = g.a_b2;
+        t2.M = g.N; t2.N = g.M;
+        t2.crs = g.ccs ? g.ccs : 1; t2.ccs = g.crs;
+        g = t2;
+      }
+      {
+        g.splits = 1;
+        g.kchunk = g.K;
+        if (dry || g.M == 0 || g.N == 0) return 0;
+        SAM_REQUIRE(g.nbatch <= 65535, "decoder training: gemm grid too large");
+        samhost::LaunchScope scope(samhost::KC_DECODER, st, 2.0 * g.M * g.N * g.K * g.nbatch);
+        const dim3 grid((g.M + 255) / 256, g.nbatch);
+        if (g.N <= 8)
+          sgemm_rows_kernel<8><<<grid, 256, 0, st>>>(g);
+        else if (g.N <= 16)
+          sgemm_rows_kernel<16><<<grid, 256, 0, st>>>(g);
+        else
+          sgemm_rows_kernel<32><<<grid, 256, 0, st>>>(g);
+        SAM_CHECK_CUDA(cudaGetLastError());
+        return 0;
+      }
+    }
     const bool thin = g.M <= HM && g.N <= HN && g.K >= 256;
     const int tm = thin ? HM : GT, tn = thin ? HN : GT, tk = thin ? HK : GK;
     const i64 tiles = static_cast<i64>((g.M + tm - 1) / tm) * ((g.N + tn - 1) / tn) * g.nbatch;
@@ -676,7 +789,7 @@ struct Tape {
     SAM_REQUIRE(!overflow, "decoder training: scratch region too small (internal sizing error)");
     {
       samhost::LaunchScope scope(samhost::KC_DECODER, st, 0.0, static_cast<double>(M) * K * 10.0, 2);
-      split_act_kernel<<<blocks_for(M * K), 256, 0, st>>>(A, A3, M, K);
+      split_act_kernel<<<blocks_for(M * K / 4), 256, 0, st>>>(A, A3, M, K);
       // the GEMM wants W as [N, K] rows: for dX = dY . W that is W^T
       split_weight_kernel<<<blocks_for(static_cast<i64>(N) * K), 256, 0, st>>>(W, W3, transposed ? K : N, transposed ? N : K,
                                                                              transposed ? 1 : 0);
@@ -692,6 +805,61 @@ struct Tape {
     GemmEpilogue ep{Cout, N, SAM_F32, bias, 0, accumulate ? Cout : nullptr, accumulate ? N : 0, accumulate ? static_cast<int>(M) : 0};
     return samk_gemm(A3, 3 * K, W3, 3 * K, static_cast<int>(M), N, 3 * K, SAM_BF16, ep, st);
   }
+  // Weight gradient dW[N, K] += dY[rows, N]^T . X[rows, K] on the tensor cores: the rows are cut into S chunks of L, both
+  // operands are written transposed / split / chunk-major, ONE block-diagonal tcgen05 GEMM produces the S partial
+  // products [S, 256, K] and splitk_reduce_kernel folds them in chunk order (deterministic).
+  static void dw_plan(i64 rows, int* L, int* S) {
+    i64 l = (rows + 255) / 256;             // at most 256 chunks
+    l = std::max<i64>(rows >= 16384 ? 512 : 256, (l + 63) / 64 * 64);
+    *L = static_cast<int>(l);
+    *S = static_cast<int>((rows + l - 1) / l);
+  }
+  static bool dw_eligible(i64 rows, int N, int K, i64 ldy, i64 ldx) {
+    return rows >= 8192 && N <= 256 && K <= 256 && N % 8 == 0 && K % 8 == 0 && ldy == N && ldx == K;
+  }
+  static size_t dw_scratch_bytes(i64 rows, int K) {
+    int L, S;
+    dw_plan(rows, &L, &S);
+    return align256(static_cast<size_t>(S) * 256 * 3 * L * 2) + align256(static_cast<size_t>(S) * K * 3 * L * 2 + 256 * 3 * L * 2) +
+           align256(static_cast<size_t>(S) * 256 * K * 4);
+  }
+  int gemm_tc_dw(const float* dY, const float* X, i64 rows, int N, int K, float* dW) {
+    int L, S;
+    dw_plan(rows, &L, &S);
+    uint16_t* A3 = reinterpret_cast<uint16_t*>(scratch(static_cast<size_t>(S) * 256 * 3 * L * 2));
+    // the second CTA of a pair reads W rows [128, 256) of a chunk: with K < 256 those are the next chunk's rows or, for
+    // the last chunk, the 256 rows of slack behind the buffer (their products land in output columns >= K: clipped)
+    uint16_t* W3 = reinterpret_cast<uint16_t*>(scratch(static_cast<size_t>(S) * K * 3 * L * 2 + 256 * 3 * L * 2));
+    float* part = scratch(static_cast<size_t>(S) * 256 * K * 4);
+    if (dry) return 0;
+    SAM_REQUIRE(!overflow, "decoder training: scratch region too small (internal sizing error)");
+    {
+      samhost::LaunchScope scope(samhost::KC_DECODER, st, 0.0, static_cast<double>(rows) * (N + K) * 10.0, 2);
+      split_transposed_kernel<<<dim3(L / 64, (N + 31) / 32, S), dim3(32, 8), 0, st>>>(dY, N, rows, N, L, 256, 0, A3);
+      split_transposed_kernel<<<dim3(L / 64, (K + 31) / 32, S), dim3(32, 8), 0, st>>>(X, K, rows, K, L, K, 1, W3);
+      SAM_CHECK_CUDA(cudaGetLastError());
+    }
+    {
+      samhost::ClassOverride as_decoder(samhost::KC_DECODER);
+      GemmEpilogue ep{part, K, SAM_F32, nullptr, 0, nullptr, 0, 0};
+      ep.diag_mt = 1;
+      ep.diag_wrows = K;
+      ep.diag_wtotal = S * K;
+      if (int rc = samk_gemm(A3, 3 * L, W3, 3 * L, S * 256, K, 3 * L, SAM_BF16, ep, st)) return rc;
+    }
+    // partial[s][i < 256][k]: rows i >= N of a chunk are the products of the unwritten operand rows -- never read
+    Gemm g{};
+    g.C = dW; g.crs = K; g.accumulate = 1; g.alpha = 1.f;
+    g.M = N; g.N = K; g.nbatch = 1; g.nb2 = 1; g.splits = S; g.bias_mod = K;
+    g.partial = part;
+    g.part_rows = 256;
+    samhost::LaunchScope scope(samhost::KC_DECODER, st);
+    splitk_reduce_kernel<<<blocks_for(static_cast<i64>(N) * K), 256, 0, st>>>(g);
+    SAM_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
+  // an op's adjoint will need this much scratch: registered at forward time so that the sizing pass sees it
+  void need_bwd(size_t bytes) { scratch_peak = std::max(scratch_peak, align256(bytes) + 4096); }
   // out[j % mod] += sum_r X[r, j]
   int colsum(const float* X, i64 ld, i64 R, int N, int mod, float* out) {
     const int chunks = static_cast<int>((R + kColRows - 1) / kColRows);
@@ -761,6 +929,14 @@ int linear(Tape& t, const Ten& X, const Ten& W, const Ten& b, Ten* Y, int bias_m
   }
   t.scratch_reset();
   const Ten Yc = *Y;
+  if (t.use_tc && t.tape_on) {   // scratch of the adjoint's tensor-core products (the sizing pass only runs the forward)
+    size_t need = 0;
+    if (Tape::tc_eligible(M, K, N, Yc.ld, X.ld))
+      need = align256(static_cast<size_t>(M) * 3 * N * 2) + align256(static_cast<size_t>(K) * 3 * N * 2);
+    if (Tape::dw_eligible(M, N, K, Yc.ld, X.ld)) need = std::max(need, Tape::dw_scratch_bytes(M, K));
+    // + the column-sum partials of the bias gradient, claimed after them in the same adjoint
+    t.need_bwd(need + align256(static_cast<size_t>((static_cast<i64>(M) * (N / bm) + kColRows - 1) / kColRows) * N * 4));
+  }
   Tape* tp = &t;
   t.push([tp, X, W, b, Yc, M, N, K, bm]() -> int {
     Tape& t = *tp;
@@ -774,7 +950,10 @@ int linear(Tape& t, const Ten& X, const Ten& W, const Ten& b, Ten* Y, int bias_m
       g.M = M; g.N = K; g.K = N; g.alpha = 1.f;
       TRY(t.gemm(g));
     }
-    if (W.g) {   // dW += dY^T . X   (reduction over the rows: split-K)
+    t.scratch_reset();
+    if (W.g && t.use_tc && Tape::dw_eligible(M, N, K, Yc.ld, X.ld)) {   // dW += dY^T . X on the tensor cores
+      TRY(t.gemm_tc_dw(Yc.g, X.p, M, N, K, W.g));
+    } else if (W.g) {   // dW += dY^T . X   (reduction over the rows: split-K)
       Gemm g{};
       g.A = Yc.g; g.ars = 1; g.acs = Yc.ld;
       g.B = X.p; g.brs = X.ld; g.bcs = 1;

@@ -255,7 +255,8 @@ int samk_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, int 
     const int rc2 = samk_gemm2(A, lda, W, ldw, M, N, K, fmt, ep, stream);
     if (rc2 >= 0) return rc2;
   }
-  SAM_REQUIRE(!ep.ln_stats && !ep.xb, "gemm: the LayerNorm-folding epilogues exist only in the 2-CTA kernel (shape %dx%dx%d declined)", M, N, K);
+  SAM_REQUIRE(!ep.ln_stats && !ep.xb && !ep.diag_mt,
+              "gemm: the LayerNorm-folding / block-diagonal modes exist only in the 2-CTA kernel (shape %dx%dx%d declined)", M, N, K);
   if (N % 256 == 0 || N > 256) return launch_gemm<256>(A, lda, W, ldw, M, N, K, fmt, ep, 0, stream);
   return launch_gemm<128>(A, lda, W, ldw, M, N, K, fmt, ep, 0, stream);
 }

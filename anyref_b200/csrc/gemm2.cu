@@ -255,6 +255,7 @@ struct Gemm2Params {
   const float* xres;   // == the fp32 output (in-place residual), row stride ldx
   int ldx;
   int x_tma;           // producer: fetch the x chunks with TMA (short main loops) instead of vector loads
+  int diag_mt, diag_wrows;   // block-diagonal mode (GemmEpilogue::diag_*): W rows of a tile start at chunk * diag_wrows
   int l2hint;          // L2 eviction-priority hints: W evict_last; the producer's x / xb streams evict_first, so that
                        // they do not push the A row block out of L2 before all CTA pairs of a tile row have read it
 };
@@ -317,7 +318,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
         const int row_a = m_blk * (2 * BM2) + static_cast<int>(rank) * BM2;
-        const int row_b = n_blk * BN2 + static_cast<int>(rank) * (BN2 / 2);
+        const int row_b = n_blk * BN2 + static_cast<int>(rank) * (BN2 / 2) + (p.diag_mt ? (m_blk / p.diag_mt) * p.diag_wrows : 0);
         for (int kb = 0; kb < num_kb; ++kb) {
           wait_role<0>(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + s * kStage2;
@@ -780,11 +781,17 @@ int samk_gemm2(const void* A, int lda, const void* W, int ldw, int M, int N, int
                 "gemm (LN-fold producer): needs stats_out, N %% 128 == 0, M %% 32 == 0, 16-byte aligned xb rows, no activation");
   }
   if (N % 8 != 0 || M < 1) return -1;
+  if (ep.diag_mt) {
+    SAM_REQUIRE(out_mode == 1 && !ln_consumer && ep.act == 0 && !ep.bias && ep.diag_wrows > 0 && ep.diag_wtotal >= ep.diag_wrows &&
+                    M % (2 * BM2 * ep.diag_mt) == 0 && N <= BN2,
+                "gemm (block-diagonal mode): fp32 store without epilogue extras, whole row blocks per chunk, N <= 256");
+  }
   CUtensorMap tmA, tmB, tmC;
   const int is_bf16 = (fmt == 1);
   int rc = samhost::encode_tmap_2d(&tmA, 2, is_bf16, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, BK2, BM2, 3);
   if (rc) return rc;
-  rc = samhost::encode_tmap_2d(&tmB, 2, is_bf16, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw * 2, BK2, BN2 / 2, 3);
+  rc = samhost::encode_tmap_2d(&tmB, 2, is_bf16, W, (uint64_t)K, (uint64_t)(ep.diag_mt ? ep.diag_wtotal : N), (uint64_t)ldw * 2, BK2,
+                               BN2 / 2, 3);
   if (rc) return rc;
   if (out_mode == 0)
     rc = samhost::encode_tmap_2d(&tmC, 2, ep.out_fmt == SAM_BF16, ep.out, (uint64_t)N, (uint64_t)M, (uint64_t)ep.ldo * 2, 64, 32, 3);
@@ -824,6 +831,8 @@ int samk_gemm2(const void* A, int lda, const void* W, int ldw, int M, int N, int
   p.ldxb = ep.ldxb;
   p.xb_fmt = fmt;
   p.stats_out = static_cast<float2*>(ep.stats_out);
+  p.diag_mt = ep.diag_mt;
+  p.diag_wrows = ep.diag_wrows;
   p.xres = static_cast<const float*>(ep.out);
   p.ldx = ep.ldo;
   {

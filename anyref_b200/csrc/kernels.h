@@ -34,6 +34,12 @@ struct GemmEpilogue {
   void* xb = nullptr;
   int ldxb = 0;
   void* stats_out = nullptr;
+  // Block-diagonal mode (gemm2.cu only; fp32 store): A is [S * diag_mt * 256, K] and W [S * diag_wrows, K]; the output
+  // tile of A's row block m_blk multiplies the W rows of chunk s = m_blk / diag_mt, i.e. S independent products
+  // C_s = A_s . W_s^T stacked along the rows of C -- the split-K partials of a weight gradient dY^T . X
+  int diag_mt = 0;
+  int diag_wrows = 0;
+  int diag_wtotal = 0;   // S * diag_wrows
 };
 
 int samk_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, int K, int fmt, const GemmEpilogue& ep,

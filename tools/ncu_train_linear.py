@@ -27,3 +27,29 @@ for _ in range(2):
 torch.cuda.synchronize()
 ref = torch.nn.functional.linear(x, w, b)
 print("forward max-abs vs torch:", float((y - ref).abs().max()), " dW rel:", float((dw / 2 - dy.t() @ x).norm() / (dy.t() @ x).norm()))
+
+
+def timed(fn, iters=20):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e3
+
+
+if not os.environ.get("NCU"):
+    gf = 2.0 * M * N * K / 1e9
+    t = timed(lambda: lib.sam_linear_f32_forward(x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), M, N, K, 0, None))
+    print(f"forward  {t:7.1f} us  {gf / t * 1e3:6.1f} TFLOP/s")
+    t = timed(lambda: lib.sam_linear_f32_backward(dy.data_ptr(), None, x.data_ptr(), w.data_ptr(), dx.data_ptr(), None, None, M, N, K,
+                                                  scratch.data_ptr(), scratch.numel(), None))
+    print(f"dX       {t:7.1f} us  {gf / t * 1e3:6.1f} TFLOP/s")
+    t = timed(lambda: lib.sam_linear_f32_backward(dy.data_ptr(), None, x.data_ptr(), w.data_ptr(), None, dw.data_ptr(), None, M, N, K,
+                                                  scratch.data_ptr(), scratch.numel(), None))
+    print(f"dW       {t:7.1f} us  {gf / t * 1e3:6.1f} TFLOP/s  (split-K + reduce)")
+
