@@ -16,10 +16,11 @@ over its last-layer hidden states.
 """
 from __future__ import annotations
 
-from typing import List, Sequence, Tuple
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from . import ops
 from .grounding import GroundingPath
@@ -70,6 +71,21 @@ class SegProjection(nn.Sequential):
         return y.to(x.dtype).reshape(*lead, w2.shape[0])
 
 
+def dice_loss(inputs: torch.Tensor, targets: torch.Tensor, num_masks: float) -> torch.Tensor:
+    """model/anyref.py:19-46 (the live branch: +1 smoothing, no scale): inputs are logits [n, H, W]."""
+    inputs = inputs.sigmoid().flatten(1, 2)
+    targets = targets.flatten(1, 2)
+    numerator = 2 * (inputs * targets).sum(-1)
+    denominator = inputs.sum(-1) + targets.sum(-1)
+    return (1 - (numerator + 1) / (denominator + 1)).sum() / num_masks
+
+
+def sigmoid_ce_loss(inputs: torch.Tensor, targets: torch.Tensor, num_masks: float) -> torch.Tensor:
+    """model/anyref.py:50-67."""
+    loss = F.binary_cross_entropy_with_logits(inputs, targets, reduction="none")
+    return loss.flatten(1, 2).mean(1).sum() / (num_masks + 1e-8)
+
+
 def build_text_hidden_fcs(in_dim: int = 4096, out_dim: int = 256) -> nn.ModuleList:
     """`self.text_hidden_fcs` of model/anyref.py:124 -- a one-element ModuleList, indexed `[0]` by the callers."""
     return nn.ModuleList([SegProjection(in_dim, out_dim)])
@@ -105,3 +121,55 @@ class SegHead:
         seg_list = [pred[[j for j, b_ in enumerate(bi_host) if b_ == b]].unsqueeze(1) for b in range(bs)]
         outs = self.path(sam_images, seg_list, sam_resized_sizes, original_sizes, multimask_output=multimask_output)
         return [o.squeeze(1) if not multimask_output else o for o in outs]
+
+    def mask_loss(self, last_hidden_state: torch.Tensor, seg_token_index: Tuple[torch.Tensor, torch.Tensor],
+                  sam_images: torch.Tensor, sam_resized_sizes: Sequence[Tuple[int, int]],
+                  original_sizes: Sequence[Tuple[int, int]], gt_masks: Sequence[torch.Tensor],
+                  bce_loss_weight: float = 2.0, dice_loss_weight: float = 0.5,
+                  loc_embeddings: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        """The mask branch of `AnyRefForCausalLM.model_forward` (model/anyref.py:366-451) in training: frozen image
+        encoder under no_grad (:366-367), `text_hidden_fcs` on the hidden states at the [SEG] tokens (:392-401, index
+        already offset by the caller as `seg_token_idx_offset_one`), optional location embeddings (:403-404), prompt
+        encoder, mask decoder, postprocess_masks (:406-430) and the BCE / dice losses with the reference's weights and
+        normalisation (:432-450).  The per-image decoder calls of the reference are ONE batched call here (identical
+        results, tests/test_gpu_train.py).  Everything that is trainable in AnyRef's recipe -- `text_hidden_fcs`, the
+        mask decoder when `train_mask_decoder` -- and `last_hidden_state` itself receive gradients from the returned
+        `mask_loss`; the caller adds the LM loss (:453-459)."""
+        sam = self.sam
+        bs = sam_images.shape[0]
+        bi, pos = seg_token_index
+        with torch.no_grad():
+            image_embeddings = sam.image_encoder(sam_images)
+        hidden = last_hidden_state[bi, pos, :]
+        pred = self.text_hidden_fcs[0](hidden)                               # [#seg, 256]
+        if loc_embeddings is not None:
+            pred = pred + loc_embeddings
+        order = torch.argsort(bi, stable=True)                               # prompts grouped by image, original order kept
+        counts = torch.bincount(bi, minlength=bs).tolist()
+        sparse, dense = sam.prompt_encoder(points=None, boxes=None, masks=None, text_embeds=pred[order].unsqueeze(1))
+        index = bi[order].to(torch.int32)
+        low, _ = sam.mask_decoder.forward_batched(image_embeddings, sam.prompt_encoder.get_dense_pe(),
+                                                  sparse.to(pred.dtype), dense, index, False)
+        ce = dice = 0.0
+        num = 0
+        pred_masks = []
+        start = 0
+        for b in range(bs):
+            n_b = counts[b]
+            if n_b == 0:                                                     # (the reference would divide 0 by 0 here)
+                pred_masks.append(low.new_zeros((0, *original_sizes[b])))
+                continue
+            pm = sam.postprocess_masks(low[start:start + n_b], input_size=sam_resized_sizes[b],
+                                       original_size=original_sizes[b]).squeeze(1)
+            start += n_b
+            pred_masks.append(pm)
+            gt = gt_masks[b].to(pm)
+            if pm.shape[-2:] != gt.shape[-2:]:                               # AVS targets (model/anyref.py:437-441)
+                pm = F.interpolate(pm.unsqueeze(0), size=gt.shape[-2:], mode="bilinear", align_corners=False).squeeze(0)
+            ce = ce + sigmoid_ce_loss(pm, gt, num_masks=gt.shape[0]) * gt.shape[0]
+            dice = dice + dice_loss(pm, gt, num_masks=gt.shape[0]) * gt.shape[0]
+            num += gt.shape[0]
+        ce = bce_loss_weight * ce / (num + 1e-8)
+        dice = dice_loss_weight * dice / (num + 1e-8)
+        return {"ce_loss": ce, "dice_loss": dice, "mask_loss": ce + dice, "pred_masks": pred_masks}
+

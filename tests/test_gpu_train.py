@@ -402,6 +402,59 @@ def test_finetuning_follows_the_reference_trajectory(setup):
         assert abs(a - b) <= 2e-3 * abs(b), (traj_a, traj_b)        # and follows the reference run (Adam amplifies 1e-6)
 
 
+def test_seg_head_mask_loss_matches_the_reference_loop(setup):
+    """SegHead.mask_loss = the mask branch of model_forward (model/anyref.py:366-451) with ONE batched decoder call;
+    reference side: the per-image loop over the oracle in fp64, [SEG] tokens of the two images interleaved in the batch
+    order `torch.where` would never produce but the method must still get right, plus an image without any."""
+    from anyref_b200.seg_head import SegHead, build_text_hidden_fcs
+    from anyref_b200.synthetic import synthetic_images
+
+    sam, cfg = setup["sam"], setup["cfg"]
+    zero_grads(sam)
+    H, Lseq = 320, 12
+    fcs = build_text_hidden_fcs(H, 256).cuda()
+    ref_fcs = torch.nn.Sequential(torch.nn.Linear(H, H), torch.nn.ReLU(), torch.nn.Linear(H, 256)).cuda()
+    ref_fcs[0].load_state_dict(fcs[0][0].state_dict())
+    ref_fcs[2].load_state_dict(fcs[0][2].state_dict())
+    ref_fcs = ref_fcs.double()
+    images = synthetic_images(3, seed=4).cuda()
+    sizes, origs = [(1024, 1024), (1024, 683), (768, 1024)], [(256, 256), (320, 214), (240, 320)]
+    bi = torch.tensor([2, 0, 2], device="cuda")
+    pos = torch.tensor([5, 7, 9], device="cuda")
+    g = torch.Generator().manual_seed(13)
+    hidden0 = torch.randn(3, Lseq, H, generator=g).cuda()
+    gts = [(torch.rand(int((bi == b).sum()), *origs[b], generator=g) > 0.5).float().cuda() for b in range(3)]
+    head = SegHead(sam, fcs)
+    h_got = hidden0.clone().requires_grad_(True)
+    out = head.mask_loss(h_got, (bi, pos), images, sizes, origs, gts)
+    out["mask_loss"].backward()
+    assert [tuple(m.shape) for m in out["pred_masks"]] == [(1, 256, 256), (0, 320, 214), (2, 240, 320)]
+    # reference: the same embeddings (this path's encoder output), per-image loop, fp64
+    osd = oracle_sd(setup["sd"])
+    with torch.no_grad():
+        emb = sam.image_encoder(images).double()
+    h_ref = hidden0.double().requires_grad_(True)
+    pred = ref_fcs(h_ref[bi, pos, :])
+    ce = dice = 0.0
+    num = 0
+    for b in (0, 2):
+        e = pred[bi == b].unsqueeze(1)
+        sp, de = O.prompt_encoder(osd, cfg, text_embeds=e)
+        low, _ = O.mask_decoder(osd, cfg, emb[b:b + 1], setup["pe"].double(), sp, de, False)
+        pm = O.postprocess_masks(low, sizes[b], origs[b]).squeeze(1)
+        gt = gts[b].double()
+        ce = ce + sigmoid_ce_loss(pm, gt, gt.shape[0]) * gt.shape[0]
+        dice = dice + dice_loss(pm, gt, gt.shape[0]) * gt.shape[0]
+        num += gt.shape[0]
+    loss_ref = 2.0 * ce / (num + 1e-8) + 0.5 * dice / (num + 1e-8)
+    loss_ref.backward()
+    assert abs(float(out["mask_loss"].detach()) - float(loss_ref.detach())) <= 1e-5 * abs(float(loss_ref.detach()))
+    assert rel_fro(h_got.grad, h_ref.grad) < 5e-5
+    for mine, theirs in ((fcs[0][0], ref_fcs[0]), (fcs[0][2], ref_fcs[2])):
+        assert rel_fro(mine.weight.grad, theirs.weight.grad) < 5e-5
+    compare_param_grads(sam, osd)
+
+
 def test_image_without_seg_token_in_training(setup):
     """model/anyref.py:406-430 also visits images whose sample has no [SEG] token: empty masks, empty loss, zero grads."""
     sam = setup["sam"]
