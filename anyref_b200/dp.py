@@ -91,17 +91,43 @@ def unpack_bits(packed: torch.Tensor, numel: int) -> torch.Tensor:
     return ((packed.view(-1, 1) & w) != 0).to(torch.uint8).reshape(-1)[:numel]
 
 
-def all_gather_packed(packed: torch.Tensor) -> List[torch.Tensor]:
-    """all_gather of per-rank bit-packed masks of possibly different lengths (padded to the max length)."""
+def _checksum(t: torch.Tensor) -> torch.Tensor:
+    """Order-sensitive 64-bit checksum of a uint8 tensor, computed where the tensor lives: the bytes are read as int64
+    words (zero-padded to a multiple of 8) and summed with weights 1 + (index mod 65521), wrap-around arithmetic."""
+    n = t.numel()
+    if n == 0:
+        return torch.zeros(1, dtype=torch.int64, device=t.device)
+    flat = t.reshape(-1)
+    if n % 8 or flat.data_ptr() % 8 or not flat.is_contiguous():
+        padded = flat.new_zeros((n + 7) // 8 * 8)
+        padded[:n] = flat
+        flat = padded
+    words = flat.view(torch.int64)
+    w = (torch.arange(words.numel(), device=t.device, dtype=torch.int64) % 65521) + 1
+    return (words * w).sum().reshape(1)
+
+
+def all_gather_packed(packed: torch.Tensor, verify: bool = True) -> List[torch.Tensor]:
+    """all_gather of per-rank bit-packed masks of possibly different lengths (padded to the max length).  With
+    `verify`, every rank also contributes a checksum of what it sent and every rank checks the pieces it received
+    against them: a transfer that does not reproduce the sender's bytes raises instead of returning silently different
+    masks (the gathered masks are an evaluation artefact that is compared bit for bit between 1-rank and N-rank runs)."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return [packed]
     world = dist.get_world_size()
-    n = torch.tensor([packed.numel()], dtype=torch.int64, device=packed.device)
-    sizes = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(sizes, n)
-    m = int(max(s.item() for s in sizes))
+    meta = torch.cat([torch.tensor([packed.numel()], dtype=torch.int64, device=packed.device),
+                      _checksum(packed) if verify else torch.zeros(1, dtype=torch.int64, device=packed.device)])
+    metas = [torch.zeros_like(meta) for _ in range(world)]
+    dist.all_gather(metas, meta)
+    sizes = [int(m[0].item()) for m in metas]
+    m = max(sizes)
     buf = packed.new_zeros(m)
     buf[:packed.numel()] = packed
     outs = [torch.empty_like(buf) for _ in range(world)]
     dist.all_gather(outs, buf)
-    return [o[:int(s.item())] for o, s in zip(outs, sizes)]
+    pieces = [o[:n] for o, n in zip(outs, sizes)]
+    if verify:
+        for r, (piece, mt) in enumerate(zip(pieces, metas)):
+            if int(_checksum(piece).item()) != int(mt[1].item()):
+                raise RuntimeError(f"all_gather_packed: the bytes received from rank {r} do not match what it sent")
+    return pieces

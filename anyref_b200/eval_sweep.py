@@ -106,12 +106,15 @@ def sweep(sam, num_images: int, n_seg: int, batch: int, rank: int, world: int, d
     if gather_masks and rank == 0:
         h = hashlib.sha256()
         nbytes = 0
+        per_rank = []
         for p in gathered:
             b = p.cpu().numpy().tobytes()
             h.update(b)
+            per_rank.append(hashlib.sha256(b).hexdigest()[:16])
             nbytes += len(b)
         out["mask_bytes"] = nbytes
         out["mask_sha256"] = h.hexdigest()
+        out["mask_sha256_per_rank"] = per_rank      # localises a mismatch between an N-rank and a 1-rank run
     return out
 
 
