@@ -141,6 +141,38 @@ def test_decoder_beyond_sixteen_tokens_uses_the_generic_path(tiny, k, dt):
     assert (iou.float().cpu() - iou_ref).abs().max().item() < (2e-5 if dt == torch.float32 else 2e-3)
 
 
+@pytest.mark.parametrize("n,k", [(3, 1), (2, 14)])
+def test_decoder_stays_inside_its_buffers(tiny, n, k):
+    """Guard bands around the workspace and the outputs of sam_decoder_forward (fused path: k = 1, incl. the tensor-core
+    upscaling tail that aliases dead workspace regions; generic path: k = 14)."""
+    import ctypes as C
+
+    from anyref_b200 import _lib
+
+    sam = tiny["sam"]
+    dec = sam.mask_decoder
+    lib = _lib.load()
+    pe = sam.prompt_encoder.get_dense_pe()
+    shape, blob, (_keep, derived_ptr) = dec._weights(64, pe)
+    G = 1 << 20
+    nm = 4
+    sizes = {"ws": lib.sam_decoder_workspace_bytes(C.byref(shape), 1, n, k), "masks": n * nm * 256 * 256 * 4, "iou": n * nm * 4}
+    bufs = {name: torch.full((sz + 2 * G,), 0xA5, dtype=torch.uint8, device="cuda") for name, sz in sizes.items()}
+    ptr = {name: t.data_ptr() + G for name, t in bufs.items()}
+    g = torch.Generator().manual_seed(5)
+    sparse = torch.randn(n, k, 256, generator=g).cuda()
+    emb = tiny["emb"][:1].cuda().contiguous()
+    dense_vec = sam.prompt_encoder.no_mask_embed.weight.detach().reshape(-1).contiguous()
+    rc = lib.sam_decoder_forward(C.byref(shape), blob.data_ptr(), derived_ptr, emb.data_ptr(), 2, 1, None, sparse.data_ptr(), 2, n, k,
+                                 dense_vec.data_ptr(), None, 2, ptr["masks"], ptr["iou"], 2, ptr["ws"], sizes["ws"], None)
+    assert rc == 0, lib.sam_last_error()
+    torch.cuda.synchronize()
+    for name, t in bufs.items():
+        assert bool((t[:G] == 0xA5).all()) and bool((t[G + sizes[name]:] == 0xA5).all()), f"{name}: guard band overwritten"
+    masks = bufs["masks"][G:G + sizes["masks"]].view(torch.float32)
+    assert bool(torch.isfinite(masks).all())
+
+
 def test_batched_decoder_with_promptless_images(tiny):
     """forward_batched over more image embeddings than prompts (images without a [SEG] in the middle of the batch):
     prompt p must read image image_index[p], whatever the other embeddings hold."""

@@ -455,6 +455,56 @@ def test_seg_head_mask_loss_matches_the_reference_loop(setup):
     compare_param_grads(sam, osd)
 
 
+@pytest.mark.parametrize("n,k", [(1, 1), (3, 2)])
+def test_training_path_stays_inside_its_buffers(setup, n, k):
+    """Guard bands around every buffer handed to the C ABI (workspace, outputs, gradient blob, [SEG] gradient): the
+    training forward / backward -- incl. the tensor-core products with their split operands and the block-diagonal
+    weight-gradient GEMM -- must leave them untouched."""
+    import ctypes as C
+
+    from anyref_b200 import _lib
+    from anyref_b200.segment_anything import _pack
+
+    sam = setup["sam"]
+    lib = _lib.load()
+    shape, blob = _pack.pack_decoder(sam.mask_decoder, 64)
+    G = 1 << 20                                    # guard bytes on either side
+
+    def guarded(nbytes):
+        t = torch.full((nbytes + 2 * G,), 0xA5, dtype=torch.uint8, device="cuda")
+        return t, t.data_ptr() + G
+
+    def intact(t, nbytes):
+        return bool((t[:G] == 0xA5).all()) and bool((t[G + nbytes:] == 0xA5).all())
+
+    nm = 4
+    ws_bytes = lib.sam_decoder_train_workspace_bytes(C.byref(shape), n, k)
+    sizes = {"ws": ws_bytes, "masks": n * nm * 256 * 256 * 4, "iou": n * nm * 4, "gblob": blob.numel() * 4, "ds": n * k * 256 * 4}
+    bufs = {name: guarded(sz) for name, sz in sizes.items()}
+    # the gradient blob is accumulated into: zero its payload
+    bufs["gblob"][0][G:G + sizes["gblob"]] = 0
+    g = torch.Generator().manual_seed(3)
+    sparse = torch.randn(n, k, 256, generator=g).cuda()
+    emb = setup["emb"][:1].contiguous()
+    pe = setup["pe"].contiguous()
+    dense_vec = sam.prompt_encoder.no_mask_embed.weight.detach().reshape(-1).contiguous()
+    tape = C.c_void_p()
+    rc = lib.sam_decoder_train_forward(C.byref(shape), blob.data_ptr(), emb.data_ptr(), 2, 1, None, sparse.data_ptr(), n, k,
+                                       dense_vec.data_ptr(), None, 2, pe.data_ptr(), 2, bufs["masks"][1], bufs["iou"][1],
+                                       bufs["ws"][1], sizes["ws"], C.byref(tape), None)
+    assert rc == 0, lib.sam_last_error()
+    d_masks = torch.randn(n, nm, 256, 256, generator=g).cuda()
+    d_iou = torch.randn(n, nm, generator=g).cuda()
+    rc = lib.sam_decoder_backward(tape, d_masks.data_ptr(), 0, nm, d_iou.data_ptr(), bufs["gblob"][1], bufs["ds"][1], None)
+    assert rc == 0, lib.sam_last_error()
+    lib.sam_decoder_tape_free(tape)
+    torch.cuda.synchronize()
+    for name, (t, _) in bufs.items():
+        assert intact(t, sizes[name]), f"{name}: guard band overwritten"
+    gb = bufs["gblob"][0][G:G + sizes["gblob"]].view(torch.float32)
+    assert bool(torch.isfinite(gb).all()) and float(gb.abs().max()) > 0
+
+
 def test_image_without_seg_token_in_training(setup):
     """model/anyref.py:406-430 also visits images whose sample has no [SEG] token: empty masks, empty loss, zero grads."""
     sam = setup["sam"]
