@@ -173,6 +173,49 @@ def test_decoder_stays_inside_its_buffers(tiny, n, k):
     assert bool(torch.isfinite(masks).all())
 
 
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+def test_encoder_and_packed_postprocess_stay_inside_their_buffers(tiny, dt):
+    """Guard bands around the encoder's workspace and output (all its kernels carve the one workspace) and around the
+    bit-packed masks / counts of the fused postprocess: nothing may be written outside."""
+    import ctypes as C
+
+    from anyref_b200 import _lib
+
+    sam = tiny["sam"]
+    enc = sam.image_encoder
+    enc.set_operand_dtype(dt)
+    lib = _lib.load()
+    shape, w16, w32 = enc._weights(dt)
+    B, G = 2, 1 << 20
+    x = tiny["x"].cuda().contiguous()
+    sizes = {"ws": lib.sam_encoder_workspace_bytes(C.byref(shape), B), "out": B * 256 * 64 * 64 * 4}
+    bufs = {name: torch.full((sz + 2 * G,), 0xA5, dtype=torch.uint8, device="cuda") for name, sz in sizes.items()}
+    rc = lib.sam_encoder_forward(C.byref(shape), w16.data_ptr(), w32.data_ptr(), x.data_ptr(), 2, B, bufs["out"].data_ptr() + G, 2,
+                                 bufs["ws"].data_ptr() + G, sizes["ws"], None)
+    assert rc == 0, lib.sam_last_error()
+    torch.cuda.synchronize()
+    for name, t in bufs.items():
+        assert bool((t[:G] == 0xA5).all()) and bool((t[G + sizes[name]:] == 0xA5).all()), f"encoder {name}: guard band overwritten"
+    emb = bufs["out"][G:G + sizes["out"]].view(torch.float32).reshape(B, 256, 64, 64)
+    assert rel_fro(emb, tiny["emb"]) < (2e-3 if dt == torch.float16 else 1e-2)
+    # fused postprocess with bit-packed output + counts
+    n, H, W = 3, 1024, 1024
+    low = torch.randn(n, 256, 256, device="cuda")
+    gt = (torch.rand(n, H, W, device="cuda") > 0.5).to(torch.uint8)
+    psz = {"packed": n * H * W // 8, "counts": n * 6 * 4}
+    pb = {name: torch.full((sz + 2 * G,), 0xA5, dtype=torch.uint8, device="cuda") for name, sz in psz.items()}
+    pb["counts"][G:G + psz["counts"]] = 0
+    rc = lib.sam_postprocess_masks_packed(low.data_ptr(), 2, n, 256, 1024, 1024, 1024, H, W, pb["packed"].data_ptr() + G, 0.0,
+                                          gt.data_ptr(), pb["counts"].data_ptr() + G, None)
+    assert rc == 0, lib.sam_last_error()
+    torch.cuda.synchronize()
+    for name, t in pb.items():
+        assert bool((t[:G] == 0xA5).all()) and bool((t[G + psz[name]:] == 0xA5).all()), f"postprocess {name}: guard band overwritten"
+    want = O.postprocess_masks(low.cpu()[:, None], (1024, 1024), (H, W))[:, 0] > 0
+    got = pb["packed"][G:G + psz["packed"]].cpu().numpy()
+    assert np.array_equal(got, np.packbits(want.numpy().reshape(-1)))
+
+
 def test_batched_decoder_with_promptless_images(tiny):
     """forward_batched over more image embeddings than prompts (images without a [SEG] in the middle of the batch):
     prompt p must read image image_index[p], whatever the other embeddings hold."""
