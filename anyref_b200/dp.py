@@ -11,7 +11,7 @@ Works with backend "nccl" (GPU) and "gloo" (CPU tests).
 from __future__ import annotations
 
 import os
-from typing import List, Tuple
+from typing import List, Optional, Tuple
 
 import torch
 import torch.distributed as dist
@@ -107,11 +107,13 @@ def _checksum(t: torch.Tensor) -> torch.Tensor:
     return (words * w).sum().reshape(1)
 
 
-def all_gather_packed(packed: torch.Tensor, verify: bool = True) -> List[torch.Tensor]:
+def all_gather_packed(packed: torch.Tensor, verify: bool = True, mismatches: Optional[List[int]] = None) -> List[torch.Tensor]:
     """all_gather of per-rank bit-packed masks of possibly different lengths (padded to the max length).  With
     `verify`, every rank also contributes a checksum of what it sent and every rank checks the pieces it received
     against them: a transfer that does not reproduce the sender's bytes raises instead of returning silently different
-    masks (the gathered masks are an evaluation artefact that is compared bit for bit between 1-rank and N-rank runs)."""
+    masks (the gathered masks are an evaluation artefact that is compared bit for bit between 1-rank and N-rank runs).
+    When a list is passed as `mismatches`, the offending source ranks are appended to it instead of raising (a sweep
+    that must reach its next collective on every rank)."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return [packed]
     world = dist.get_world_size()
@@ -129,5 +131,7 @@ def all_gather_packed(packed: torch.Tensor, verify: bool = True) -> List[torch.T
     if verify:
         for r, (piece, mt) in enumerate(zip(pieces, metas)):
             if int(_checksum(piece).item()) != int(mt[1].item()):
-                raise RuntimeError(f"all_gather_packed: the bytes received from rank {r} do not match what it sent")
+                if mismatches is None:
+                    raise RuntimeError(f"all_gather_packed: the bytes received from rank {r} do not match what it sent")
+                mismatches.append(r)
     return pieces

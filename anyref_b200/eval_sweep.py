@@ -92,7 +92,8 @@ def sweep(sam, num_images: int, n_seg: int, batch: int, rank: int, world: int, d
     stats, packed = run_shard(sam, lo, hi, n_seg, batch, device, keep_masks=gather_masks, **kw)
     e1.record()
     stats = dp.all_reduce_stats(stats)
-    gathered = dp.all_gather_packed(packed) if gather_masks else None
+    bad_ranks: List[int] = []
+    gathered = dp.all_gather_packed(packed, mismatches=bad_ranks) if gather_masks else None
     e2.record()
     torch.cuda.synchronize(device)
     t = torch.tensor([e0.elapsed_time(e1), e0.elapsed_time(e2)], dtype=torch.float64, device=device)
@@ -115,6 +116,9 @@ def sweep(sam, num_images: int, n_seg: int, batch: int, rank: int, world: int, d
         out["mask_bytes"] = nbytes
         out["mask_sha256"] = h.hexdigest()
         out["mask_sha256_per_rank"] = per_rank      # localises a mismatch between an N-rank and a 1-rank run
+        out["gather_verified"] = not bad_ranks     # every received piece reproduces its sender's checksum
+        if bad_ranks:
+            out["gather_mismatch_ranks"] = bad_ranks
     return out
 
 

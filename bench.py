@@ -617,7 +617,7 @@ def main():
                                     "includes on-device input generation",
                         "images_per_s": c5["images_per_s"], "masks_per_s": c5["masks_per_s"], "ms_total": c5["ms_total"],
                         "ms_forward": c5["ms_forward"], "mask_bytes_gathered": c5.get("mask_bytes"),
-                        "mask_sha256": c5.get("mask_sha256"), "mask_sha256_per_rank": c5.get("mask_sha256_per_rank"), "gIoU": c5.get("gIoU"), "cIoU": c5.get("cIoU")}
+                        "mask_sha256": c5.get("mask_sha256"), "mask_sha256_per_rank": c5.get("mask_sha256_per_rank"), "gather_verified": c5.get("gather_verified"), "gIoU": c5.get("gIoU"), "cIoU": c5.get("cIoU")}
         if rank == 0 and world == 1:
             torch.cuda.empty_cache()
             extras["train_step"] = sub_record_train(sam, dev)
