@@ -70,7 +70,7 @@ _PROTOS = {
     "sam_decoder_backward": [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     "sam_decoder_tape_free": [c_void_p],
     "sam_linear_f32_scratch_bytes": [c_int, c_int, c_int],
-    "sam_linear_f32_forward": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "sam_linear_f32_forward": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p],
     "sam_linear_f32_backward": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                 c_void_p, c_size_t, c_void_p],
     "sam_postprocess_masks_backward": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],

@@ -136,8 +136,9 @@ int sam_decoder_backward(void* tape, const float* d_masks, int mask_lo, int mask
 }
 void sam_decoder_tape_free(void* tape) { samk_decoder_tape_free(tape); }
 size_t sam_linear_f32_scratch_bytes(int M, int N, int K) { return samk_linear_f32_scratch_bytes(M, N, K); }
-int sam_linear_f32_forward(const float* X, const float* W, const float* b, float* Y, int M, int N, int K, int relu, void* stream) {
-  return samk_linear_f32_forward(X, W, b, Y, M, N, K, relu, S(stream));
+int sam_linear_f32_forward(const float* X, const float* W, const float* b, float* Y, int M, int N, int K, int relu, void* scratch,
+                           size_t scratch_bytes, void* stream) {
+  return samk_linear_f32_forward(X, W, b, Y, M, N, K, relu, scratch, scratch_bytes, S(stream));
 }
 int sam_linear_f32_backward(float* dY, const float* relu_y, const float* X, const float* W, float* dX, float* dW, float* db, int M,
                             int N, int K, void* scratch, size_t scratch_bytes, void* stream) {

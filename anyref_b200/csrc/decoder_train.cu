@@ -1576,20 +1576,24 @@ size_t samk_linear_f32_scratch_bytes(int M, int N, int K) {
   return align256(splitk) + align256(cols) + 1024;
 }
 
-int samk_linear_f32_forward(const float* X, const float* W, const float* b, float* Y, int M, int N, int K, int relu_act, cudaStream_t st) {
+int samk_linear_f32_forward(const float* X, const float* W, const float* b, float* Y, int M, int N, int K, int relu_act, void* scratch,
+                            size_t scratch_bytes, cudaStream_t st) {
   SAM_REQUIRE(X && W && Y && M >= 0 && N > 0 && K > 0, "linear_f32_forward: bad arguments");
+  SAM_REQUIRE(scratch && scratch_bytes >= samk_linear_f32_scratch_bytes(M, N, K), "linear_f32_forward: scratch too small");
   if (M == 0) return 0;
+  // a few [SEG] rows against a 4096 x 4096 weight is a memory-bound product with 64 output tiles: Tape::gemm splits K
+  Tape t;
+  t.dry = false; t.st = st;
+  t.base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(scratch) + 255) & ~static_cast<uintptr_t>(255));
   Gemm g{};
   g.A = X; g.ars = K; g.acs = 1;
   g.B = W; g.brs = 1; g.bcs = K;
   g.C = Y; g.crs = N;
   g.bias = b; g.bias_mod = N;
   g.M = M; g.N = N; g.K = K; g.alpha = 1.f;
-  g.nbatch = 1; g.nb2 = 1; g.splits = 1; g.kchunk = K;
   {
-    samhost::LaunchScope scope(samhost::KC_GEMM, st, 2.0 * M * N * K);
-    sgemm_kernel<GT, GT, GK><<<dim3((M + GT - 1) / GT, (N + GT - 1) / GT, 1), 256, 0, st>>>(g);
-    SAM_CHECK_CUDA(cudaGetLastError());
+    samhost::ClassOverride as_gemm(samhost::KC_GEMM);
+    TRY(t.gemm(g));
   }
   if (relu_act) {
     samhost::LaunchScope scope(samhost::KC_GEMM, st);

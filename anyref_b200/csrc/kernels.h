@@ -124,7 +124,8 @@ int samk_decoder_forward_generic(const SamDecoderShape& s, const float* blob, co
                                  const void* dense_vec, const void* dense_full, int dense_fmt, void* masks, void* iou, int out_fmt,
                                  void* workspace, size_t workspace_bytes, cudaStream_t st);
 size_t samk_linear_f32_scratch_bytes(int M, int N, int K);
-int samk_linear_f32_forward(const float* X, const float* W, const float* b, float* Y, int M, int N, int K, int relu_act, cudaStream_t st);
+int samk_linear_f32_forward(const float* X, const float* W, const float* b, float* Y, int M, int N, int K, int relu_act, void* scratch,
+                            size_t scratch_bytes, cudaStream_t st);
 int samk_linear_f32_backward(float* dY, const float* relu_y, const float* X, const float* W, float* dX, float* dW, float* db, int M, int N, int K,
                              void* scratch, size_t scratch_bytes, cudaStream_t st);
 int samk_postprocess_backward(const float* d_out, int maps, int low, int img, int in_h, int in_w, int out_h, int out_w, float* tmp,

@@ -151,8 +151,11 @@ class LinearF32Fn(torch.autograd.Function):
         N = wf.shape[0]
         y = torch.empty((M, N), device=xf.device, dtype=torch.float32)
         with torch.cuda.device(xf.device):
+            nbytes = lib.sam_linear_f32_scratch_bytes(M, N, K)
+            scratch = torch.empty(nbytes + 256, dtype=torch.uint8, device=xf.device)
             rc = lib.sam_linear_f32_forward(xf.data_ptr(), wf.data_ptr(), bf.data_ptr() if bf is not None else None,
-                                            y.data_ptr(), M, N, K, 1 if relu else 0, _lib.stream_ptr(xf.device))
+                                            y.data_ptr(), M, N, K, 1 if relu else 0, scratch.data_ptr(), scratch.numel(),
+                                            _lib.stream_ptr(xf.device))
             _lib.check(rc, "sam_linear_f32_forward")
         ctx.save_for_backward(xf, wf, y if relu else None)
         ctx.meta = (x.dtype, weight.dtype, bias.dtype if bias is not None else None, relu)

@@ -223,11 +223,11 @@ void sam_decoder_tape_free(void* tape);
  * fp32 nn.Linear forward / backward for text_hidden_fcs in training (model/anyref.py:116-124, :395-401):
  * Y [M, N] = X [M, K] . W[N, K]^T + b (optionally ReLU);  dX = dY . W (overwritten, may be NULL), dW += dY^T . X,
  * db += column sums of dY.  With relu_y (the output of a forward that fused the ReLU) dY is first masked IN PLACE with
- * (relu_y > 0).  scratch: sam_linear_f32_scratch_bytes(M, N, K) bytes.
+ * (relu_y > 0).  scratch (both calls): sam_linear_f32_scratch_bytes(M, N, K) bytes.
  */
 size_t sam_linear_f32_scratch_bytes(int M, int N, int K);
 int sam_linear_f32_forward(const float* X, const float* W, const float* b, float* Y, int M, int N, int K, int relu,
-                           void* stream);
+                           void* scratch, size_t scratch_bytes, void* stream);
 int sam_linear_f32_backward(float* dY, const float* relu_y, const float* X, const float* W, float* dX, float* dW,
                             float* db, int M, int N, int K, void* scratch, size_t scratch_bytes, void* stream);
 

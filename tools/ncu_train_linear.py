@@ -21,7 +21,7 @@ db = torch.zeros(N, device="cuda")
 nb = lib.sam_linear_f32_scratch_bytes(M, N, K)
 scratch = torch.empty(nb + 256, dtype=torch.uint8, device="cuda")
 for _ in range(2):
-    assert lib.sam_linear_f32_forward(x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), M, N, K, 0, None) == 0
+    assert lib.sam_linear_f32_forward(x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), M, N, K, 0, scratch.data_ptr(), scratch.numel(), None) == 0
     assert lib.sam_linear_f32_backward(dy.data_ptr(), None, x.data_ptr(), w.data_ptr(), dx.data_ptr(), dw.data_ptr(), db.data_ptr(),
                                        M, N, K, scratch.data_ptr(), scratch.numel(), None) == 0
 torch.cuda.synchronize()
@@ -44,7 +44,7 @@ def timed(fn, iters=20):
 
 if not os.environ.get("NCU"):
     gf = 2.0 * M * N * K / 1e9
-    t = timed(lambda: lib.sam_linear_f32_forward(x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), M, N, K, 0, None))
+    t = timed(lambda: lib.sam_linear_f32_forward(x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), M, N, K, 0, scratch.data_ptr(), scratch.numel(), None))
     print(f"forward  {t:7.1f} us  {gf / t * 1e3:6.1f} TFLOP/s")
     t = timed(lambda: lib.sam_linear_f32_backward(dy.data_ptr(), None, x.data_ptr(), w.data_ptr(), dx.data_ptr(), None, None, M, N, K,
                                                   scratch.data_ptr(), scratch.numel(), None))
