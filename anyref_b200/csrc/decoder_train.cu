@@ -15,9 +15,12 @@
 //   Attention.forward                    modeling/transformer.py:220-242
 // Every forward op pushes the closure of its adjoint on a tape; sam_decoder_backward runs the tape in reverse.  Every
 // adjoint ACCUMULATES into the gradient buffers of its inputs (zeroed once), so fan-out needs no special handling.
-// All arithmetic is fp32 FMA with fixed reduction orders (split-K partials are reduced in index order): the
-// gradients are deterministic.  Throughput is that of a plain SIMT SGEMM; moving the image-side
-// products onto the split-bf16 tcgen05 GEMM of the inference path is the next step.
+// Reduction orders are fixed (split-K and per-chunk partials are folded in index order): the gradients are deterministic.
+// Products with >= 8192 rows (the image side) run on the tensor cores: operands split into bf16 pairs (x = hi + lo,
+// x.w ~ hi.hi + hi.lo + lo.hi as ONE tcgen05 GEMM over 3K, fp32-accurate) through the 2-CTA GEMM of the inference path
+// -- forward, input gradient (in-place reduce-add epilogue) and weight gradient (block-diagonal mode: one GEMM for all
+// row chunks, Tape::gemm_tc_dw).  Everything else is fp32 FMA on the SGEMM below.  The same composition without its tape
+// is the inference path for prompts with more than 16 tokens (samk_decoder_forward_generic).  DESIGN.md 4b.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
