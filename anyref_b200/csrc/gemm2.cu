@@ -17,6 +17,11 @@
 //     (mean, sum of squared deviations of each 128-column slice) -- x is read once and never again by a LayerNorm pass;
 //   * consumer  (OUT_FMT = 16-bit, LNF): qkv / lin1 multiply xb by W' = gamma o W and finish the normalisation in
 //     the epilogue:  LN(x).W^T + b = rstd * (xb.W'^T - mean * colsum(W')) + (beta.W^T + b).
+//
+// Block-diagonal mode (GemmEpilogue::diag_*, fp32 store): A [S * 256, K] and W [S * wrows, K] hold S independent chunks
+// and the tile of A's row block s multiplies the W rows of chunk s -- one launch computes the S partial products of a
+// weight gradient dY^T . X whose reduction dimension was cut into S chunks (decoder_train.cu, Tape::gemm_tc_dw).  The only
+// difference to the plain GEMM is one term in the producer's W row coordinate.
 #include <stdio.h>
 #include <stdlib.h>
 
