@@ -1607,7 +1607,7 @@ int samk_linear_f32_forward(const float* X, const float* W, const float* b, floa
   return 0;
 }
 
-// dX = dY . W (overwritten; may be NULL), dW += dY^T . X, db += column sums of dY.  With relu_y (the forward's output of a
+// dX = dY . W and dW = dY^T . X (both overwritten; either may be NULL), db += column sums of dY.  With relu_y (the forward's output of a
 // fused ReLU) dY is first masked IN PLACE with (relu_y > 0)
 int samk_linear_f32_backward(float* dY, const float* relu_y, const float* X, const float* W, float* dX, float* dW, float* db, int M, int N, int K,
                              void* scratch, size_t scratch_bytes, cudaStream_t st) {
@@ -1635,7 +1635,7 @@ int samk_linear_f32_backward(float* dY, const float* relu_y, const float* X, con
     Gemm g{};
     g.A = dY; g.ars = 1; g.acs = N;
     g.B = X; g.brs = K; g.bcs = 1;
-    g.C = dW; g.crs = K; g.accumulate = 1;
+    g.C = dW; g.crs = K; g.accumulate = 0;
     g.M = N; g.N = K; g.K = M; g.alpha = 1.f;
     TRY(t.gemm(g));
   }

@@ -173,7 +173,7 @@ class LinearF32Fn(torch.autograd.Function):
         dev = xf.device
         need_x, need_w, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
         dx = torch.empty((M, K), device=dev, dtype=torch.float32) if need_x else None
-        dw = torch.zeros((N, K), device=dev, dtype=torch.float32) if need_w else None
+        dw = torch.empty((N, K), device=dev, dtype=torch.float32) if need_w else None
         db = torch.zeros((N,), device=dev, dtype=torch.float32) if need_b and bdt is not None else None
         with torch.cuda.device(dev):
             nbytes = lib.sam_linear_f32_scratch_bytes(M, N, K)

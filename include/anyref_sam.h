@@ -221,8 +221,8 @@ void sam_decoder_tape_free(void* tape);
 
 /*
  * fp32 nn.Linear forward / backward for text_hidden_fcs in training (model/anyref.py:116-124, :395-401):
- * Y [M, N] = X [M, K] . W[N, K]^T + b (optionally ReLU);  dX = dY . W (overwritten, may be NULL), dW += dY^T . X,
- * db += column sums of dY.  With relu_y (the output of a forward that fused the ReLU) dY is first masked IN PLACE with
+ * Y [M, N] = X [M, K] . W[N, K]^T + b (optionally ReLU);  dX = dY . W and dW = dY^T . X (both overwritten, either may be
+ * NULL), db += column sums of dY (zero it first).  With relu_y (the output of a forward that fused the ReLU) dY is first masked IN PLACE with
  * (relu_y > 0).  scratch (both calls): sam_linear_f32_scratch_bytes(M, N, K) bytes.
  */
 size_t sam_linear_f32_scratch_bytes(int M, int N, int K);

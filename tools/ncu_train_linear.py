@@ -26,7 +26,7 @@ for _ in range(2):
                                        M, N, K, scratch.data_ptr(), scratch.numel(), None) == 0
 torch.cuda.synchronize()
 ref = torch.nn.functional.linear(x, w, b)
-print("forward max-abs vs torch:", float((y - ref).abs().max()), " dW rel:", float((dw / 2 - dy.t() @ x).norm() / (dy.t() @ x).norm()))
+print("forward max-abs vs torch:", float((y - ref).abs().max()), " dW rel:", float((dw - dy.t() @ x).norm() / (dy.t() @ x).norm()))
 
 
 def timed(fn, iters=20):
