@@ -76,3 +76,28 @@ def test_intersection_and_union_matches_reference_semantics():
     gt = torch.tensor([[0, 1, 0], [1, 1, 0]])
     i, u, t = dp.intersection_and_union(pred, gt, 2)
     assert i.tolist() == [2.0, 2.0] and u.tolist() == [4.0, 4.0] and t.tolist() == [3.0, 3.0]
+
+
+def test_gather_checksum_is_order_and_length_sensitive():
+    """The checksum all_gather_packed verifies transfers with must notice what a corrupted or shifted piece looks like:
+    a swapped pair of bytes, a dropped byte, a shift by one; and must not depend on alignment or length padding."""
+    import torch
+
+    from anyref_b200.dp import _checksum
+
+    g = torch.Generator().manual_seed(0)
+    a = torch.randint(0, 256, (100003,), dtype=torch.uint8, generator=g)
+    base = int(_checksum(a))
+    b = a.clone()
+    b[[10, 11]] = b[[11, 10]]
+    assert int(_checksum(b)) != base or int(a[10]) == int(a[11])
+    assert int(_checksum(a[:-1])) != base and int(_checksum(a[1:])) != base
+    c = a.clone()
+    c[77777] ^= 1
+    assert int(_checksum(c)) != base
+    # a non-contiguous / unaligned view of the same bytes gives the same value
+    padded = torch.zeros(a.numel() + 3, dtype=torch.uint8)
+    padded[3:] = a
+    assert int(_checksum(padded[3:])) == base
+    assert int(_checksum(torch.zeros(0, dtype=torch.uint8))) == 0
+
