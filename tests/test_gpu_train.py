@@ -505,6 +505,28 @@ def test_training_path_stays_inside_its_buffers(setup, n, k):
     assert bool(torch.isfinite(gb).all()) and float(gb.abs().max()) > 0
 
 
+def test_training_gradients_are_bitwise_deterministic(setup):
+    """No atomics and fixed reduction orders in the decoder's forward-with-tape and backward: two runs on
+    the same inputs give bit-identical outputs and gradients (3 prompts: the tensor-core products incl. the block-diagonal
+    weight gradient are on the path)."""
+    sam = setup["sam"]
+    g = torch.Generator().manual_seed(41)
+    sparse0 = torch.randn(3, 1, 256, generator=g).cuda()
+    dense = sam.prompt_encoder.no_mask_embed.weight.detach().reshape(1, -1, 1, 1).expand(3, -1, 64, 64)
+    cot = torch.randn(3, 1, 256, 256, generator=g).cuda()
+    runs = []
+    for _ in range(3):
+        zero_grads(sam)
+        sp = sparse0.clone().requires_grad_(True)
+        m, i = sam.mask_decoder(image_embeddings=setup["emb"][:1], image_pe=setup["pe"], sparse_prompt_embeddings=sp,
+                                dense_prompt_embeddings=dense, multimask_output=False)
+        ((m * cot).sum() + i.sum()).backward()
+        runs.append((m.detach().clone(), sp.grad.clone(), [p.grad.clone() for p in sam.mask_decoder.parameters() if p.grad is not None]))
+    for other in runs[1:]:
+        assert torch.equal(runs[0][0], other[0]) and torch.equal(runs[0][1], other[1])
+        assert len(runs[0][2]) == len(other[2]) and all(torch.equal(a, b) for a, b in zip(runs[0][2], other[2]))
+
+
 def test_image_without_seg_token_in_training(setup):
     """model/anyref.py:406-430 also visits images whose sample has no [SEG] token: empty masks, empty loss, zero grads."""
     sam = setup["sam"]
