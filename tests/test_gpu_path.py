@@ -580,6 +580,27 @@ def test_box_prompt_through_decoder_vs_oracle(tiny):
     assert int(iou.argmax()) == int(io.argmax())
 
 
+def test_many_points_and_a_box_through_decoder_vs_oracle(tiny):
+    """20 clicks + a box per prompt = 22 sparse embeddings (27 tokens): beyond the 16 tokens of the fused token kernels, so
+    the decoder call takes its generic composition; prompt encoder kernels and decoder against the oracle."""
+    sam, cfg, sd = tiny["sam"], tiny["cfg"], tiny["sd"]
+    g = torch.Generator().manual_seed(17)
+    coords = torch.rand(2, 20, 2, generator=g) * 1024
+    labels = (torch.rand(2, 20, generator=g) > 0.4).float()
+    boxes = torch.tensor([[100.0, 200.0, 700.0, 900.0], [10.0, 20.0, 500.0, 400.0]])
+    with torch.no_grad():
+        so, do = O.prompt_encoder(sd, cfg, points=(coords, labels), boxes=boxes)
+        mo, io = O.mask_decoder(sd, cfg, tiny["emb"][:1], tiny["pe"], so, do, True)
+    assert so.shape == (2, 22, 256)
+    sp, de = sam.prompt_encoder(points=(coords.cuda(), labels.cuda()), boxes=boxes.cuda(), masks=None, text_embeds=None)
+    assert (sp.cpu() - so).abs().max().item() < 1e-5
+    m, iou = sam.mask_decoder(image_embeddings=tiny["emb"][:1].cuda(), image_pe=sam.prompt_encoder.get_dense_pe(),
+                              sparse_prompt_embeddings=sp, dense_prompt_embeddings=de, multimask_output=True)
+    assert m.shape == (2, 3, 256, 256)
+    assert (m.cpu() - mo).abs().max().item() < 1e-4
+    assert (iou.cpu() - io).abs().max().item() < 1e-4
+
+
 def test_mask_prompt_through_decoder_vs_oracle(tiny):
     """SamPredictor.predict_torch with mask_input (predictor.py:233-252): the dense embedding is a full tensor."""
     sam, cfg, sd = tiny["sam"], tiny["cfg"], tiny["sd"]
