@@ -76,6 +76,7 @@ _PROTOS = {
     "sam_postprocess_masks_backward": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
     "sam_postprocess_masks": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                               c_float, c_void_p],
+    "sam_gemm_set_tile_split": [c_int],
     "sam_launch_count": [],
     "sam_profile_enable": [c_int],
     "sam_profile_reset": [],
@@ -100,7 +101,7 @@ _PROTOS = {
 _RESTYPES = {"sam_last_error": c_char_p, "sam_encoder_w16_elems": c_size_t, "sam_encoder_w32_elems": c_size_t,
              "sam_encoder_workspace_bytes": c_size_t, "sam_decoder_weight_elems": c_size_t,
              "sam_decoder_workspace_bytes": c_size_t, "sam_decoder_derived_bytes": c_size_t,
-             "sam_decoder_train_workspace_bytes": c_size_t, "sam_linear_f32_scratch_bytes": c_size_t, "sam_decoder_tape_free": None, "sam_prompt_mask_blob_elems": c_size_t, "sam_launch_count": C.c_longlong, "sam_profile_enable": None,
+             "sam_decoder_train_workspace_bytes": c_size_t, "sam_linear_f32_scratch_bytes": c_size_t, "sam_decoder_tape_free": None, "sam_prompt_mask_blob_elems": c_size_t, "sam_gemm_set_tile_split": None, "sam_launch_count": C.c_longlong, "sam_profile_enable": None,
              "sam_profile_reset": None, "sam_profile_get": None}
 
 
@@ -198,6 +199,11 @@ def fmt_of(dtype) -> int:
 
 
 KERNEL_CLASSES = ("gemm", "attn_window", "attn_global", "layernorm", "layout", "decoder", "postprocess")
+
+
+def gemm_set_tile_split(mode: int) -> None:
+    """Half-tile items in the last round of the 2-CTA GEMM (include/anyref_sam.h): -1 policy, 0 never, 1 whenever possible."""
+    load().sam_gemm_set_tile_split(int(mode))
 
 
 def launch_count() -> int:

@@ -199,6 +199,7 @@ int sam_preprocess(const void* img, int in_fmt, void* out, int out_fmt, int B, i
   return samk_preprocess(img, in_fmt, out, out_fmt, B, h, w, Sz, mean, std, S(stream));
 }
 
+void sam_gemm_set_tile_split(int mode) { samk_gemm2_set_tile_split(mode); }
 long long sam_launch_count(void) { return samhost::launch_count(); }
 void sam_profile_enable(int on) { samhost::profile_enable(on); }
 void sam_profile_reset(void) { samhost::profile_reset(); }

@@ -41,7 +41,9 @@ constexpr int kStage2 = kStageA2 + kStageB2;
 constexpr int kEpiWarps = 8;
 constexpr int kStagingPerWarp = 2 * 4096;       // double-buffered 32 x 128 B boxes
 constexpr int kThreads2 = 64 + kEpiWarps * 32;
-constexpr int kSmem2 = kStages2 * kStage2 + kEpiWarps * kStagingPerWarp + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int kSmem2 = kStages2 * kStage2 + kEpiWarps * kStagingPerWarp + 1024 /*align*/ + 256 /*barriers*/ +
+                       1024 /*half_stats*/;
+static_assert(kSmem2 <= 232448, "more than the 227 KB of shared memory a CTA may opt in to");
 static_assert((2 * kStages2 + 4 + 2 * kEpiWarps) * 8 + 4 <= 256, "barrier block overflows its 256 bytes");
 constexpr uint32_t kTmemCols2 = 512;
 
@@ -261,16 +263,47 @@ struct Gemm2Params {
   int ldx;
   int x_tma;           // producer: fetch the x chunks with TMA (short main loops) instead of vector loads
   int diag_mt, diag_wrows;   // block-diagonal mode (GemmEpilogue::diag_*): W rows of a tile start at chunk * diag_wrows
+  int nsplit;          // split the tiles of a final, at most half-full round into two 256 x 128 halves (see Sched)
+  uint32_t idesc_half; // instruction descriptor of those half tiles (M = 256, N = 128)
   int l2hint;          // L2 eviction-priority hints: W evict_last; the producer's x / xb streams evict_first, so that
                        // they do not push the A row block out of L2 before all CTA pairs of a tile row have read it
 };
+
+// Work items of one CTA pair.  Tiles [0, lim) go round-robin over the pairs as whole 256 x 256 tiles.  When the last
+// round would leave at least half of the pairs idle (0 < rem <= pairs / 2), its rem tiles are cut into 2 * rem half
+// items of 256 x 128 (column slice h of the tile) and pair j takes half (tile lim + j / 2, h = j & 1) as its last item:
+// the round costs about half a tile period instead of a whole one.  A half item loads 64 W rows per CTA (tmBh) and
+// runs the N = 128 form of the same MMA; its 128 accumulator columns are one 128-column slice of the output, so every
+// column is still accumulated in the same order (bit-identical results) and a LayerNorm slice still has one owner.
+struct Sched {
+  int full_items;   // whole tiles of this pair: tile = cluster_id + i * num_clusters
+  int n_items;      // full_items + (0 | 1 half item)
+  int half_tile, half_h;
+  __device__ __forceinline__ bool is_half(int it) const { return it >= full_items; }
+};
+__device__ __forceinline__ Sched make_sched(int num_tiles, int num_clusters, int cluster_id, int nsplit) {
+  int lim = num_tiles, n_half = 0;
+  if (nsplit) {
+    const int full = (num_tiles / num_clusters) * num_clusters, rem = num_tiles - full;
+    if (rem > 0 && 2 * rem <= num_clusters) {
+      lim = full;
+      n_half = 2 * rem;
+    }
+  }
+  Sched sc;
+  sc.full_items = lim > cluster_id ? (lim - cluster_id + num_clusters - 1) / num_clusters : 0;
+  sc.n_items = sc.full_items + (cluster_id < n_half ? 1 : 0);
+  sc.half_tile = lim + (cluster_id >> 1);
+  sc.half_h = cluster_id & 1;
+  return sc;
+}
 
 // OUT_FMT: SamFmt of the output (0 fp16, 1 bf16, 2 fp32);  ACT: 0 none, 1 GELU  (compile-time so the epilogue carries
 // exactly one conversion / activation path)
 template <int OUT_FMT, int ACT, int LNF>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-             const __grid_constant__ CUtensorMap tmC, const Gemm2Params p) {
+             const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmBh, const Gemm2Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* staging = smem + kStages2 * kStage2;
@@ -280,6 +313,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint64_t* acc_empty = acc_full + 2;
   uint64_t* ld_bar = acc_empty + 2;                       // LNF producer: x-tile loads, 2 per epilogue warp
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ld_bar + 2 * kEpiWarps);
+  float2* half_stats = reinterpret_cast<float2*>(staging + kEpiWarps * kStagingPerWarp + 256);   // [128] LNF producer, half items
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -291,11 +325,13 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const int num_kb = (p.K + BK2 - 1) / BK2;
   const int cluster_id = blockIdx.x >> 1;
   const int num_clusters = gridDim.x >> 1;
+  const Sched sc = make_sched(num_tiles, num_clusters, cluster_id, p.nsplit);
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB);
     ptx::prefetch_tmap(&tmC);
+    if (p.nsplit) ptx::prefetch_tmap(&tmBh);
     for (int s = 0; s < kStages2; ++s) {
       ptx::mbar_init(&full_bar[s], 1);    // leader's arrive.expect_tx (bytes of BOTH CTAs' loads)
       ptx::mbar_init(&empty_bar[s], 1);   // multicast tcgen05.commit
@@ -320,20 +356,26 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       int s = 0;
       uint32_t ph = 0;
       const uint64_t pol_w = l2_policy_evict_last();
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      for (int it = 0; it < sc.n_items; ++it) {
+        const bool hf = sc.is_half(it);
+        const int tile = hf ? sc.half_tile : cluster_id + it * num_clusters;
         const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
         const int row_a = m_blk * (2 * BM2) + static_cast<int>(rank) * BM2;
-        const int row_b = n_blk * BN2 + static_cast<int>(rank) * (BN2 / 2) + (p.diag_mt ? (m_blk / p.diag_mt) * p.diag_wrows : 0);
+        // whole tile: this CTA's 128 W rows; half item: its 64 rows of column slice h (MMA N = 128 takes 64 from each CTA)
+        const int row_b = hf ? n_blk * BN2 + sc.half_h * (BN2 / 2) + static_cast<int>(rank) * (BN2 / 4)
+                             : n_blk * BN2 + static_cast<int>(rank) * (BN2 / 2) + (p.diag_mt ? (m_blk / p.diag_mt) * p.diag_wrows : 0);
+        const CUtensorMap* mapB = hf ? &tmBh : &tmB;
+        const uint32_t tx = hf ? 2 * (kStageA2 + kStageB2 / 2) : 2 * kStage2;
         for (int kb = 0; kb < num_kb; ++kb) {
           wait_role<0>(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + s * kStage2;
           uint8_t* sb = sa + kStageA2;
           // the peer's bytes may land before this expect_tx (tx-count is signed); they cannot land in an earlier
           // phase because the peer waited for the commit that followed the MMAs of that phase
-          if (leader) ptx::mbar_expect_tx(&full_bar[s], 2 * kStage2);
+          if (leader) ptx::mbar_expect_tx(&full_bar[s], tx);
           tma_load_2d_cg2(sa, &tmA, &full_bar[s], kb * BK2, row_a);
-          if (p.l2hint) tma_load_2d_cg2_hint(sb, &tmB, &full_bar[s], kb * BK2, row_b, pol_w);
-          else tma_load_2d_cg2(sb, &tmB, &full_bar[s], kb * BK2, row_b);
+          if (p.l2hint) tma_load_2d_cg2_hint(sb, mapB, &full_bar[s], kb * BK2, row_b, pol_w);
+          else tma_load_2d_cg2(sb, mapB, &full_bar[s], kb * BK2, row_b);
           if (++s == kStages2) { s = 0; ph ^= 1; }
         }
       }
@@ -345,7 +387,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       uint32_t ph = 0;
       int as = 0;
       uint32_t aph = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      for (int it = 0; it < sc.n_items; ++it) {
+        const uint32_t idesc = sc.is_half(it) ? p.idesc_half : p.idesc;
         wait_role<1>(&acc_empty[as], aph ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN2);
@@ -357,7 +400,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           const uint64_t da = ptx::make_smem_desc(sa, 16, 1024, ptx::kSwz128);
           const uint64_t db = ptx::make_smem_desc(sb, 16, 1024, ptx::kSwz128);
 #pragma unroll
-          for (int k = 0; k < BK2 / 16; ++k) mma_f16_ss_cg2(d_tmem, da + 2 * k, db + 2 * k, p.idesc, (kb | k) != 0);
+          for (int k = 0; k < BK2 / 16; ++k) mma_f16_ss_cg2(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
           mma_commit_cg2(&empty_bar[s]);
           if (++s == kStages2) { s = 0; ph ^= 1; }
         }
@@ -379,13 +422,35 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       // The x chunk of the NEXT step is loaded with plain vector loads one chunk ahead (it does not depend on the
       // accumulator; x loads through the TMA queue would sit in front of the main loop's operand loads and stall
       // them on their HBM misses); the new x leaves through the staging buffers as TMA stores.
-      const int my_tiles = (num_tiles - cluster_id + num_clusters - 1) / num_clusters;
-      const int total_q = 4 * my_tiles;
+      // chunk q of this warp: 4 chunks of 32 columns per whole tile; a half item (always the last one) has 2 -- this
+      // warp's 64 columns of the item's 128-column slice
+      const int total_q = 4 * sc.full_items + (sc.n_items > sc.full_items ? 2 : 0);
       auto chunk_xy = [&](int q, int& col0, int& row0) {
-        const int tile = cluster_id + (q >> 2) * num_clusters;
+        const bool hf = sc.is_half(q >> 2);
+        const int tile = hf ? sc.half_tile : cluster_id + (q >> 2) * num_clusters;
         const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
         row0 = m_blk * (2 * BM2) + static_cast<int>(rank) * BM2 + quad * 32;
-        col0 = n_blk * BN2 + half * 128 + (q & 3) * 32;
+        col0 = n_blk * BN2 + (hf ? sc.half_h * 128 + half * 64 : half * 128) + (q & 3) * 32;
+      };
+      // slice statistics of the finished chunks.  Whole tile: this warp owns the 128-column slice.  Half item: the two
+      // warps of a lane quadrant hold 64 columns each of the same rows; they meet at a named barrier and the
+      // half == 0 warp writes the combination (Chan's formula for two equal halves).
+      auto write_stats = [&](int q, int row, float shift, float s1, float s2) {
+        if (!sc.is_half(q >> 2)) {
+          const int tile = cluster_id + (q >> 2) * num_clusters;
+          p.stats_out[static_cast<size_t>(row) * (p.N >> 7) + (tile % n_tiles) * 2 + half] = ln_slice(shift, s1, s2);
+        } else {
+          const float m = s1 * (1.0f / 64.0f);
+          const float2 mine = make_float2(shift + m, fmaxf(fmaf(-s1, m, s2), 0.f));
+          if (half == 1) half_stats[quad * 32 + lane] = mine;
+          asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+          if (half == 0) {
+            const float2 o = half_stats[quad * 32 + lane];
+            const float d = mine.x - o.x;
+            p.stats_out[static_cast<size_t>(row) * (p.N >> 7) + (sc.half_tile % n_tiles) * 2 + sc.half_h] =
+                make_float2(0.5f * (mine.x + o.x), fmaf(32.0f * d, d, mine.y + o.y));
+          }
+        }
       };
       if (p.x_tma) {
         // Short main loops (proj, K = E): the x chunks stream through the two staging buffers with TMA loads issued
@@ -405,6 +470,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll 1
         for (int q = 0; q < total_q; ++q) {
           const int c = q & 3, b = q & 1;
+          const bool hf = sc.is_half(q >> 2);
+          const int last_c = hf ? 1 : 3;
           int col0, row0;
           chunk_xy(q, col0, row0);
           if (c == 0) {
@@ -413,11 +480,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             s1 = 0.f;
             s2 = 0.f;
           }
-          const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * BN2 + half * 128);
+          const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
+                                 static_cast<uint32_t>(as * BN2 + (hf ? half * 64 : half * 128));
           uint32_t v[32];
           ptx::tmem_ld_32x32b_x32(t_row + c * 32, v);
           ptx::tmem_ld_wait();
-          if (c == 3) {
+          if (c == last_c) {
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_remote(&acc_empty[as], 0);
@@ -470,13 +538,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
               for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(xb_row)[i] = ub[i];
             }
-            if (c == 3) {
-              const int tile = cluster_id + (q >> 2) * num_clusters;
-              const int part = (tile % n_tiles) * 2 + half;
-              p.stats_out[static_cast<size_t>(row) * (p.N >> 7) + part] = ln_slice(shift, s1, s2);
-            }
+            if (c == last_c) write_stats(q, row, shift, s1, s2);
           }
-          if (c == 3 && ++as == 2) { as = 0; aph ^= 1; }
+          if (c == last_c && ++as == 2) { as = 0; aph ^= 1; }
           if (lane == 0 && q + 2 < total_q) {
             bulk_wait_read<0>();              // the store of this chunk has read buffer b
             int c2, r2;
@@ -509,6 +573,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       float s1 = 0.f, s2 = 0.f, shift = 0.f;
       auto process = [&](const int q, float4 (&xn)[8]) {
         const int c = q & 3;
+        const bool hf = sc.is_half(q >> 2);
+        const int last_c = hf ? 1 : 3;
         int col0, row0;
         chunk_xy(q, col0, row0);
         const bool valid = row0 < p.M && col0 < p.N;     // warp-uniform (M % 32 == 0, N % 32 == 0)
@@ -531,11 +597,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           s1 = 0.f;
           s2 = 0.f;
         }
-        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * BN2 + half * 128);
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
+                               static_cast<uint32_t>(as * BN2 + (hf ? half * 64 : half * 128));
         uint32_t v[32];
         ptx::tmem_ld_32x32b_x32(t_row + c * 32, v);
         ptx::tmem_ld_wait();
-        if (c == 3) {
+        if (c == last_c) {
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_remote(&acc_empty[as], 0);
@@ -592,24 +659,26 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
             for (int i = 0; i < 4; ++i) store(reinterpret_cast<uint4*>(xb_row) + i, ub[i]);
           }
-          if (c == 3) {
-            const int tile = cluster_id + (q >> 2) * num_clusters;
-            const int part = (tile % n_tiles) * 2 + half;
-            p.stats_out[static_cast<size_t>(row) * (p.N >> 7) + part] = ln_slice(shift, s1, s2);
-          }
+          if (c == last_c) write_stats(q, row, shift, s1, s2);
         }
-        if (c == 3 && ++as == 2) { as = 0; aph ^= 1; }
+        if (c == last_c && ++as == 2) { as = 0; aph ^= 1; }
       };
 #pragma unroll 1
-      for (int q = 0; q < total_q; q += 2) {      // total_q is a multiple of 4
+      for (int q = 0; q < total_q; q += 2) {      // total_q is even
         process(q, xa);
         process(q + 1, xb2);
       }
       }
     } else
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+    for (int it = 0; it < sc.n_items; ++it) {
+      const bool hf = sc.is_half(it);
+      const int tile = hf ? sc.half_tile : cluster_id + it * num_clusters;
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       const int row0 = m_blk * (2 * BM2) + static_cast<int>(rank) * BM2 + quad * 32;
+      // first output / accumulator column of this warp: its 128-column half of a whole tile (4 chunks of 32), or its
+      // 64 columns of the half item's 128-column slice (2 chunks)
+      const int col_base = n_blk * BN2 + (hf ? sc.half_h * 128 + half * 64 : half * 128);
+      const int ncp = hf ? 1 : 2;
       float ln_mu = 0.f, ln_r = 0.f;
       if constexpr (LNF == 1) {
         // LNF consumer: finish the row statistics of this thread's row while the main loop of the tile runs
@@ -633,10 +702,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
       wait_role<2>(&acc_full[as], aph);
       ptx::tc_fence_after();
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * BN2 + half * 128);
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
+                             static_cast<uint32_t>(as * BN2 + (hf ? half * 64 : half * 128));
       // one 32-column chunk of the accumulator, already in registers
       auto chunk = [&](const int c, const uint32_t (&v)[32]) {
-        const int col0 = n_blk * BN2 + half * 128 + c * 32;
+        const int col0 = col_base + c * 32;
         // tile overhang (all conditions are warp-uniform); TMA clips partially out-of-range boxes itself
         const bool valid = row0 < p.M && col0 < p.N;
         const bool pair_valid = row0 < p.M && (col0 - (c & 1) * 32) < p.N;   // 16-bit mode: chunks c-1 | c share a box
@@ -729,11 +799,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       ptx::tmem_ld_32x32b_x32(t_row, va);
       ptx::tmem_ld_wait_dep(va);
 #pragma unroll 1
-      for (int cp = 0; cp < 2; ++cp) {
+      for (int cp = 0; cp < ncp; ++cp) {
+        const bool more = cp + 1 < ncp;
         ptx::tmem_ld_32x32b_x32(t_row + (2 * cp + 1) * 32, vb);
         chunk(2 * cp, va);
         ptx::tmem_ld_wait_dep(vb);
-        if (cp == 0) {
+        if (more) {
           ptx::tmem_ld_32x32b_x32(t_row + 64, va);
         } else {
           // accumulator stage fully read by this warp -> hand it back to the MMA issuer early
@@ -742,7 +813,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (lane == 0) mbar_arrive_remote(&acc_empty[as], 0);
         }
         chunk(2 * cp + 1, vb);
-        if (cp == 0) ptx::tmem_ld_wait_dep(va);
+        if (more) ptx::tmem_ld_wait_dep(va);
       }
       if (++as == 2) { as = 0; aph ^= 1; }
     }
@@ -758,6 +829,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 }
 
 }  // namespace
+
+// -1: policy (launches of fewer than 8 whole rounds), 0: whole tiles only, 1: whenever the last round allows
+static int g_tile_split_mode = -1;
+void samk_gemm2_set_tile_split(int mode) { g_tile_split_mode = mode < 0 ? -1 : (mode ? 1 : 0); }
 
 // Returns -1 if this kernel does not cover the request (caller falls back to the 1-CTA kernel), else 0 / error code.
 int samk_gemm2(const void* A, int lda, const void* W, int ldw, int M, int N, int K, int fmt, const GemmEpilogue& ep,
@@ -791,19 +866,23 @@ int samk_gemm2(const void* A, int lda, const void* W, int ldw, int M, int N, int
                     M % (2 * BM2 * ep.diag_mt) == 0 && N <= BN2,
                 "gemm (block-diagonal mode): fp32 store without epilogue extras, whole row blocks per chunk, N <= 256");
   }
-  CUtensorMap tmA, tmB, tmC;
+  CUtensorMap tmA, tmB, tmC, tmBh;
   const int is_bf16 = (fmt == 1);
   int rc = samhost::encode_tmap_2d(&tmA, 2, is_bf16, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, BK2, BM2, 3);
   if (rc) return rc;
   rc = samhost::encode_tmap_2d(&tmB, 2, is_bf16, W, (uint64_t)K, (uint64_t)(ep.diag_mt ? ep.diag_wtotal : N), (uint64_t)ldw * 2, BK2,
                                BN2 / 2, 3);
   if (rc) return rc;
+  // W rows of a half item (Sched): 64 per CTA
+  rc = samhost::encode_tmap_2d(&tmBh, 2, is_bf16, W, (uint64_t)K, (uint64_t)(ep.diag_mt ? ep.diag_wtotal : N), (uint64_t)ldw * 2, BK2,
+                               BN2 / 4, 3);
+  if (rc) return rc;
   if (out_mode == 0)
     rc = samhost::encode_tmap_2d(&tmC, 2, ep.out_fmt == SAM_BF16, ep.out, (uint64_t)N, (uint64_t)M, (uint64_t)ep.ldo * 2, 64, 32, 3);
   else
     rc = samhost::encode_tmap_2d(&tmC, 4, 0, ep.out, (uint64_t)N, (uint64_t)M, (uint64_t)ep.ldo * 4, 32, 32, 3);
   if (rc) return rc;
-  typedef void (*KernelFn)(CUtensorMap, CUtensorMap, CUtensorMap, Gemm2Params);
+  typedef void (*KernelFn)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, Gemm2Params);
   // [out_fmt][act][LNF]; the fp32 kernels have no activation, their LNF variant is the residual producer
   static const KernelFn kernels[3][2][2] = {{{gemm2_kernel<0, 0, 0>, gemm2_kernel<0, 0, 1>}, {gemm2_kernel<0, 1, 0>, gemm2_kernel<0, 1, 1>}},
                                             {{gemm2_kernel<1, 0, 0>, gemm2_kernel<1, 0, 1>}, {gemm2_kernel<1, 1, 0>, gemm2_kernel<1, 1, 1>}},
@@ -827,6 +906,7 @@ int samk_gemm2(const void* A, int lda, const void* W, int ldw, int M, int N, int
   p.N = N;
   p.K = K;
   p.idesc = ptx::make_idesc((uint32_t)fmt, 2 * BM2, BN2, 0, 0);
+  p.idesc_half = ptx::make_idesc((uint32_t)fmt, 2 * BM2, BN2 / 2, 0, 0);
   p.ln_stats = static_cast<const float2*>(ep.ln_stats);
   p.ln_parts = ep.ln_parts;
   p.ln_colsum = ep.ln_colsum;
@@ -872,12 +952,23 @@ int samk_gemm2(const void* A, int lda, const void* W, int ldw, int M, int N, int
     max_clusters = n;
     if (getenv("SAM_GEMM_DEBUG")) fprintf(stderr, "[anyref_sam] gemm2: max co-resident CTA pairs = %d\n", n);
   }
+  {
+    // Half items in the last round (Sched) pay off while the launch is short: measured on the whole path at B = 1
+    // (1 - 4 rounds per linear) 7.96 -> 7.67 ms per image; at B = 16 (17 - 69 rounds) the step is energy-bound under the
+    // power cap, the idle pairs of the last round give their power to the busy ones, and halves -- more operand bytes
+    // per FLOP -- measure equal or slower (92.9 vs 92.6 ms).  Hence: only launches of fewer than 8 whole rounds.
+    static const char* ns = getenv("SAM_GEMM_NSPLIT");   // "0": never, "1": whenever the last round allows (A/B measurements)
+    const int mode = g_tile_split_mode >= 0 ? g_tile_split_mode : (ns ? (ns[0] == '1') : -1);
+    const bool few_rounds = clusters < 8 * max_clusters;
+    p.nsplit = (mode >= 0 ? mode != 0 : few_rounds) && !ep.diag_mt;
+  }
   if (clusters > max_clusters) clusters = max_clusters;
+  else if (p.nsplit && 2 * clusters <= max_clusters) clusters *= 2;   // fewer tiles than half the pairs: all of them as half items
   const double out_b = (ep.out_fmt == 2) ? 4.0 : 2.0;
   samhost::LaunchScope scope(samhost::KC_GEMM, stream, 2.0 * M * N * K,
                              2.0 * (static_cast<double>(M) * K + static_cast<double>(N) * K) + out_b * M * N +
                                  (ep.res ? 4.0 * M * N : 0.0) + (ln_producer ? 2.0 * M * N : 0.0));
-  kernel<<<2 * clusters, kThreads2, kSmem2, stream>>>(tmA, tmB, tmC, p);
+  kernel<<<2 * clusters, kThreads2, kSmem2, stream>>>(tmA, tmB, tmC, tmBh, p);
   SAM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

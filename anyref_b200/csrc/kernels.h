@@ -49,6 +49,9 @@ int samk_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, int 
 int samk_gemm2(const void* A, int lda, const void* W, int ldw, int M, int N, int K, int fmt, const GemmEpilogue& ep,
                cudaStream_t stream);
 
+// Half-tile items in the last round of samk_gemm2 (gemm2.cu, Sched): -1 policy, 0 off, 1 whenever possible.
+void samk_gemm2_set_tile_split(int mode);
+
 // UMMA layout probe (test-only kernel, see probe.cu).
 struct UmmaProbe {
   int N;          // MMA N (multiple of 16, <= 256); M is fixed at 128

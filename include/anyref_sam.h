@@ -318,6 +318,16 @@ int sam_resize_u8(const unsigned char* in, int H, int W, int C, unsigned char* t
                   int yk, void* stream);
 
 /*
+ * Scheduling switch of the 2-CTA GEMM behind every sam_gemm* entry point and the encoder (no reference counterpart:
+ * the reference's nn.Linear calls, modeling/image_encoder.py:238, :257, modeling/common.py:26, leave tiling to cuBLAS).
+ * When the last round of 256 x 256 output tiles would leave at least half of the CTA pairs idle, its tiles are cut into
+ * 256 x 128 halves, one per pair.  Results are bit-identical either way except the LayerNorm slice statistics of the
+ * residual producers, which combine two 64-column halves (same value to fp32 rounding).
+ * mode: -1 = policy (only launches of fewer than 8 whole rounds, i.e. small batches), 0 = never, 1 = whenever possible.
+ */
+void sam_gemm_set_tile_split(int mode);
+
+/*
  * Launch accounting and per-kernel-class timing (used by bench.py for `gpu_launches` and the roofline leg).
  * sam_launch_count: kernels launched by this library since load.  With profiling enabled every launch is bracketed by
  * a CUDA event pair on its stream; sam_profile_collect synchronises those events and adds them to per-class totals.

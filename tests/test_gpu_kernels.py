@@ -196,6 +196,66 @@ def _guards_intact(raw, pad):
     return bool((raw[:pad].float() == 77).all()) and bool((raw[-pad:].float() == 77).all())
 
 
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (513, 480, 160), (4096, 1280, 5120), (4900, 3840, 1280), (16384 + 256, 1280, 320)])
+def test_gemm_half_tiles_of_the_last_round_are_bit_identical(ops, dt, M, N, K):
+    """An underfull last round of 256 x 256 tiles is cut into 256 x 128 halves (gemm2.cu, Sched): every output column is
+    still accumulated in the same order, so each epilogue must return the same bits with the split forced on and off."""
+    from anyref_b200 import _lib
+    torch.manual_seed(M + N + K)
+    a = (torch.randn(M, K, device=DEV) * 0.5).to(dt)
+    w = (torch.randn(N, K, device=DEV) * 0.05).to(dt)
+    bias = torch.randn(N, device=DEV)
+    res = torch.randn(M, N, device=DEV)
+    got = {}
+    try:
+        for mode in (0, 1):
+            _lib.gemm_set_tile_split(mode)
+            x = res.clone()
+            ops.gemm(a, w, bias=bias, residual=x, out=x)
+            got[mode] = (ops.gemm(a, w, out_dtype=torch.float32), ops.gemm(a, w, bias=bias, act="gelu", out_dtype=dt), x)
+    finally:
+        _lib.gemm_set_tile_split(-1)
+    for u, v in zip(got[0], got[1]):
+        assert torch.equal(u, v)
+    assert rel_fro(got[1][0], a.float() @ w.float().t()) < 1e-5
+
+
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("M,N,K", [(4096, 1280, 1280), (4096, 1280, 5120), (2048 + 32, 256, 256), (16384 + 256, 1280, 320)])
+def test_ln_fold_with_half_tiles(ops, dt, M, N, K):
+    """LayerNorm folding through half tiles: the residual producer's x / xb are bit-identical to the whole-tile schedule,
+    its slice statistics (two 64-column halves combined by the two warps of a lane quadrant) agree with fp64, and the
+    consumer returns the same bits."""
+    from anyref_b200 import _lib
+    torch.manual_seed(M + N + K)
+    a = (torch.randn(M, K, device=DEV) * 0.5).to(dt)
+    w = (torch.randn(N, K, device=DEV) * 0.05).to(dt)
+    bias = torch.randn(N, device=DEV)
+    x0 = torch.randn(M, N, device=DEV) * 2 + 3.0
+    colsum = torch.randn(N, device=DEV)
+    st_in = torch.rand(M, K // 128, 2, device=DEV) if K % 128 == 0 else None     # (mean, M2) per 128-column slice
+    got = {}
+    try:
+        for mode in (0, 1):
+            _lib.gemm_set_tile_split(mode)
+            x = x0.clone()
+            xb, stats = ops.gemm_residual_ln(a, w, x, bias)
+            y = ops.gemm_ln(a, w, bias, colsum, st_in, 1e-6, act="gelu") if st_in is not None else None
+            got[mode] = (x, xb, stats, y)
+    finally:
+        _lib.gemm_set_tile_split(-1)
+    assert torch.equal(got[0][0], got[1][0]) and torch.equal(got[0][1], got[1][1])
+    if got[0][3] is not None:
+        assert torch.equal(got[0][3], got[1][3])
+    x, _, stats, _ = got[1]
+    xs = x.double().view(M, N // 128, 128)
+    m2 = ((xs - xs.mean(-1, keepdim=True)) ** 2).sum(-1)
+    assert (stats[..., 0].double() - xs.mean(-1)).abs().max().item() < 2e-5
+    assert ((stats[..., 1].double() - m2).abs() / m2).max().item() < 2e-5
+    assert (got[0][2] - stats).abs().max().item() < 1e-3 * stats.abs().max().item()
+
+
 @pytest.mark.parametrize("M,N,K", [(2048 + 32, 256, 256), (4096, 1280, 1280), (288, 768, 2304)])
 def test_ln_fold_kernels_stay_inside_their_outputs(ops, M, N, K):
     """Guard bands around every output of the folded-LayerNorm kernels (M not a multiple of the 256-row tile, K long
