@@ -431,6 +431,41 @@ def cublas_sustained(dev, seconds: float = 1.5):
     return out
 
 
+def cublas_encoder_shapes(dev, op_dtype, B: int, seconds: float = 1.5):
+    """cuBLAS (torch.matmul, no bias / LayerNorm / GELU / residual) on the four linears of one encoder block at this
+    step's shapes (M = B * 4096 tokens; image_encoder.py:238, :257, common.py:26) and operand format, run back to back in
+    block order for `seconds` on this GPU: the library's sustained rate on the SHAPES this path has to run (short K = 1280
+    for three of the four) -- the 8192^3 figure of `cublas_sustained` is the library's best case."""
+    M, E = B * 4096, 1280
+    shapes = (("qkv", 3 * E, E), ("proj", E, E), ("lin1", 4 * E, E), ("lin2", E, 4 * E))
+    ops_ = []
+    for _, N, K in shapes:
+        a = (torch.randn(M, K, device=dev) * 0.5).to(op_dtype)
+        w = (torch.randn(N, K, device=dev) * 0.05).to(op_dtype)
+        ops_.append((a, w.t(), torch.empty(M, N, device=dev, dtype=op_dtype)))
+    for a, wt, c in ops_:
+        torch.matmul(a, wt, out=c)
+    torch.cuda.synchronize()
+    t0, blocks, ms = time.perf_counter(), 0, 0.0
+    while time.perf_counter() - t0 < seconds:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(32):
+            for a, wt, c in ops_:
+                torch.matmul(a, wt, out=c)
+        e1.record()
+        torch.cuda.synchronize()
+        ms += e0.elapsed_time(e1)
+        blocks += 32
+    flop = sum(2.0 * M * N * K for _, N, K in shapes)
+    del ops_
+    torch.cuda.empty_cache()
+    return {"how": f"torch.matmul on the qkv / proj / lin1 / lin2 shapes of one block (M = {M}), plain products without "
+                   "any epilogue, back to back in block order, CUDA events, this process / this GPU",
+            "dtype": str(op_dtype).replace("torch.", ""), "ms_per_block": ms / blocks, "unit": "TFLOP/s",
+            "value": flop * blocks / (ms * 1e-3) / 1e12}
+
+
 def sub_record_c3(path, dev, op_dtype, rank, timed_fn, world):
     """BASELINE.json configs[2]: 8 images x 4 [SEG] x 3 masks (multimask_output), content 1024x683 -> 640x427 masks."""
     from anyref_b200.synthetic import synthetic_images, synthetic_seg_embeddings
@@ -623,6 +658,7 @@ def main():
             extras["train_step"] = sub_record_train(sam, dev)
             extras["library_baseline"] = library_baseline(dev, n_seg)
             extras["cublas_same_box"] = cublas_sustained(dev)
+            extras["cublas_encoder_shapes"] = cublas_encoder_shapes(dev, op_dtype, B)
 
     parity = None
     if rank == 0 and not args.no_parity:
@@ -674,6 +710,10 @@ def main():
         line.update(extras)
         if "cublas_same_box" in extras:
             line["roofline"]["frac_vs_cublas_same_box_same_format"] = gemm_tflops / extras["cublas_same_box"][args.dtype]
+        if "cublas_encoder_shapes" in extras:
+            # this path's GEMM class WITH its fused LayerNorm / bias / GELU / residual epilogues (and the patch-embed and
+            # neck products, 1 % of its FLOPs) against the library's plain products on the same shapes
+            line["roofline"]["frac_vs_cublas_same_shapes_plain"] = gemm_tflops / extras["cublas_encoder_shapes"]["value"]
         _emit(line)
     if world > 1:
         dist.barrier()
