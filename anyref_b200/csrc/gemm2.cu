@@ -235,12 +235,20 @@ __device__ __forceinline__ void gelu_fast2(float& x0, float& x1) {
 }
 
 // LnSlice: statistics of one 128-column slice of a residual row as (mean, M2 = sum of squared deviations from that
-// mean).  The producers accumulate sums of (x - shift) with shift = the slice's first element -- a value within a few
-// standard deviations of the mean, so neither sum cancels -- and the consumer combines the slices with Chan's formula;
-// the textbook E[x^2] - mean^2 loses all precision for rows whose |mean| is far above their standard deviation.
-__device__ __forceinline__ float2 ln_slice(float shift, float s1, float s2) {
-  const float m = s1 * (1.0f / 128.0f);
+// mean).  The producers accumulate sums of (x - shift) with shift = the first element of the columns they sum -- a value
+// within a few standard deviations of the mean, so neither sum cancels -- and the consumer combines the slices with
+// Chan's formula; the textbook E[x^2] - mean^2 loses all precision for rows whose |mean| is far above their standard deviation.
+// The residual producers build a slice from its two 64-column halves (each with its own shift) and combine them with
+// Chan's formula for equal halves -- in exactly this form whether one warp walks both halves (whole tile) or the two
+// warps of a lane quadrant hold one half each (half item, Sched), so the statistics, and with them every downstream
+// bit, do not depend on the tile schedule (test_full_size_batch_is_independent_of_batch_position).
+__device__ __forceinline__ float2 ln_half(float shift, float s1, float s2) {
+  const float m = s1 * (1.0f / 64.0f);
   return make_float2(shift + m, fmaxf(fmaf(-s1, m, s2), 0.f));
+}
+__device__ __forceinline__ float2 ln_combine(float2 a, float2 b) {
+  const float d = a.x - b.x;
+  return make_float2(0.5f * (a.x + b.x), fmaf(32.0f * d, d, a.y + b.y));
 }
 
 struct Gemm2Params {
@@ -435,21 +443,22 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       // slice statistics of the finished chunks.  Whole tile: this warp owns the 128-column slice.  Half item: the two
       // warps of a lane quadrant hold 64 columns each of the same rows; they meet at a named barrier and the
       // half == 0 warp writes the combination (Chan's formula for two equal halves).
-      auto write_stats = [&](int q, int row, float shift, float s1, float s2) {
+      // called after every odd chunk with the statistics of the 64 columns just finished (chunks c - 1, c)
+      float2 first_half = make_float2(0.f, 0.f);
+      auto write_stats = [&](int q, int row, float2 h64) {
         if (!sc.is_half(q >> 2)) {
-          const int tile = cluster_id + (q >> 2) * num_clusters;
-          p.stats_out[static_cast<size_t>(row) * (p.N >> 7) + (tile % n_tiles) * 2 + half] = ln_slice(shift, s1, s2);
-        } else {
-          const float m = s1 * (1.0f / 64.0f);
-          const float2 mine = make_float2(shift + m, fmaxf(fmaf(-s1, m, s2), 0.f));
-          if (half == 1) half_stats[quad * 32 + lane] = mine;
-          asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
-          if (half == 0) {
-            const float2 o = half_stats[quad * 32 + lane];
-            const float d = mine.x - o.x;
-            p.stats_out[static_cast<size_t>(row) * (p.N >> 7) + (sc.half_tile % n_tiles) * 2 + sc.half_h] =
-                make_float2(0.5f * (mine.x + o.x), fmaf(32.0f * d, d, mine.y + o.y));
+          if ((q & 3) == 1) {
+            first_half = h64;
+          } else {
+            const int tile = cluster_id + (q >> 2) * num_clusters;
+            p.stats_out[static_cast<size_t>(row) * (p.N >> 7) + (tile % n_tiles) * 2 + half] = ln_combine(first_half, h64);
           }
+        } else {
+          if (half == 1) half_stats[quad * 32 + lane] = h64;
+          asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+          if (half == 0)
+            p.stats_out[static_cast<size_t>(row) * (p.N >> 7) + (sc.half_tile % n_tiles) * 2 + sc.half_h] =
+                ln_combine(h64, half_stats[quad * 32 + lane]);
         }
       };
       if (p.x_tma) {
@@ -477,6 +486,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (c == 0) {
             wait_role<2>(&acc_full[as], aph);
             ptx::tc_fence_after();
+          }
+          if ((c & 1) == 0) {
             s1 = 0.f;
             s2 = 0.f;
           }
@@ -506,7 +517,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             x4.y += __uint_as_float(v[4 * i + 1]) + b4.y;
             x4.z += __uint_as_float(v[4 * i + 2]) + b4.z;
             x4.w += __uint_as_float(v[4 * i + 3]) + b4.w;
-            if (c == 0 && i == 0) shift = x4.x;      // per-slice shift: sums of (x - shift) do not cancel (see LnSlice)
+            if ((c & 1) == 0 && i == 0) shift = x4.x;      // per-half shift: sums of (x - shift) do not cancel (see LnSlice)
             {
               const float dx = x4.x - shift, dy = x4.y - shift, dz = x4.z - shift, dw = x4.w - shift;
               s1 += (dx + dy) + (dz + dw);
@@ -538,7 +549,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
               for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(xb_row)[i] = ub[i];
             }
-            if (c == last_c) write_stats(q, row, shift, s1, s2);
+            if (c & 1) write_stats(q, row, ln_half(shift, s1, s2));
           }
           if (c == last_c && ++as == 2) { as = 0; aph ^= 1; }
           if (lane == 0 && q + 2 < total_q) {
@@ -594,6 +605,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (c == 0) {
           wait_role<2>(&acc_full[as], aph);
           ptx::tc_fence_after();
+        }
+        if ((c & 1) == 0) {
           s1 = 0.f;
           s2 = 0.f;
         }
@@ -624,7 +637,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             x4.y += __uint_as_float(v[4 * i + 1]) + b4.y;
             x4.z += __uint_as_float(v[4 * i + 2]) + b4.z;
             x4.w += __uint_as_float(v[4 * i + 3]) + b4.w;
-            if (c == 0 && i == 0) shift = x4.x;
+            if ((c & 1) == 0 && i == 0) shift = x4.x;
             {
               const float dx = x4.x - shift, dy = x4.y - shift, dz = x4.z - shift, dw = x4.w - shift;
               s1 += (dx + dy) + (dz + dw);
@@ -659,7 +672,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
             for (int i = 0; i < 4; ++i) store(reinterpret_cast<uint4*>(xb_row) + i, ub[i]);
           }
-          if (c == last_c) write_stats(q, row, shift, s1, s2);
+          if (c & 1) write_stats(q, row, ln_half(shift, s1, s2));
         }
         if (c == last_c && ++as == 2) { as = 0; aph ^= 1; }
       };

@@ -224,9 +224,9 @@ def test_gemm_half_tiles_of_the_last_round_are_bit_identical(ops, dt, M, N, K):
 @pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("M,N,K", [(4096, 1280, 1280), (4096, 1280, 5120), (2048 + 32, 256, 256), (16384 + 256, 1280, 320)])
 def test_ln_fold_with_half_tiles(ops, dt, M, N, K):
-    """LayerNorm folding through half tiles: the residual producer's x / xb are bit-identical to the whole-tile schedule,
-    its slice statistics (two 64-column halves combined by the two warps of a lane quadrant) agree with fp64, and the
-    consumer returns the same bits."""
+    """LayerNorm folding through half tiles: the residual producer's x / xb / slice statistics (two 64-column halves, held
+    by the two warps of a lane quadrant instead of one warp) are bit-identical to the whole-tile schedule and agree with
+    fp64, and the consumer returns the same bits."""
     from anyref_b200 import _lib
     torch.manual_seed(M + N + K)
     a = (torch.randn(M, K, device=DEV) * 0.5).to(dt)
@@ -253,7 +253,8 @@ def test_ln_fold_with_half_tiles(ops, dt, M, N, K):
     m2 = ((xs - xs.mean(-1, keepdim=True)) ** 2).sum(-1)
     assert (stats[..., 0].double() - xs.mean(-1)).abs().max().item() < 2e-5
     assert ((stats[..., 1].double() - m2).abs() / m2).max().item() < 2e-5
-    assert (got[0][2] - stats).abs().max().item() < 1e-3 * stats.abs().max().item()
+    # a slice is always the Chan combination of its two 64-column halves, whoever computed them: same bits either way
+    assert torch.equal(got[0][2], stats)
 
 
 @pytest.mark.parametrize("M,N,K", [(2048 + 32, 256, 256), (4096, 1280, 1280), (288, 768, 2304)])
