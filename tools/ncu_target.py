@@ -1,5 +1,6 @@
 """Tiny single-kernel drivers for `ncu --set full` captures:
-    python tools/ncu_target.py <lin1|proj|qkv|lin2|proj_ln|lin2_ln|qkv_fold|lin1_fold|attn_window|attn_global|layernorm> [iters] [fp16|bf16]"""
+    [NCU_M=rows] [NCU_SPLIT=-1|0|1] python tools/ncu_target.py <lin1|proj|qkv|lin2|proj_ln|lin2_ln|qkv_fold|lin1_fold|attn_window|attn_global|layernorm> [iters] [fp16|bf16]
+NCU_M: token rows of the GEMM targets (default 65536 = 16 images; 4096 = one image); NCU_SPLIT: sam_gemm_set_tile_split mode."""
 import os
 import sys
 
@@ -9,7 +10,10 @@ import torch
 from anyref_b200 import ops
 
 dev = "cuda"
-M = 65536
+M = int(os.environ.get("NCU_M", "65536"))
+if "NCU_SPLIT" in os.environ:
+    from anyref_b200 import _lib
+    _lib.gemm_set_tile_split(int(os.environ["NCU_SPLIT"]))
 dt = torch.float16 if (len(sys.argv) > 3 and sys.argv[3] == "fp16") else torch.bfloat16
 which = sys.argv[1]
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 3
@@ -28,7 +32,7 @@ if which in ("lin1", "proj", "qkv", "lin2", "proj_ln", "lin2_ln", "qkv_fold", "l
         fn = lambda: ops.gemm(a, w, bias=bias, out=out)
     elif which.endswith("_fold"):
         out = torch.empty(M, N, device=dev, dtype=dt)
-        stats = torch.zeros(M, 10, 2, device=dev)
+        stats = torch.zeros(M, K // 128, 2, device=dev)
         stats[..., 1] = 128.0
         colsum = torch.randn(N, device=dev)
         fn = lambda: ops.gemm_ln(a, w, bias, colsum, stats, 1e-6, act="gelu" if which == "lin1_fold" else "none", out=out)
