@@ -77,6 +77,7 @@ _PROTOS = {
     "sam_postprocess_masks": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                               c_float, c_void_p],
     "sam_gemm_set_tile_split": [c_int],
+    "sam_gemm_schedule": [c_int, c_int, c_int, c_int, c_void_p, c_int],
     "sam_launch_count": [],
     "sam_profile_enable": [c_int],
     "sam_profile_reset": [],

@@ -200,6 +200,9 @@ int sam_preprocess(const void* img, int in_fmt, void* out, int out_fmt, int B, i
 }
 
 void sam_gemm_set_tile_split(int mode) { samk_gemm2_set_tile_split(mode); }
+int sam_gemm_schedule(int num_tiles, int num_pairs, int pair, int split, int* out, int cap) {
+  return samk_gemm2_schedule(num_tiles, num_pairs, pair, split, out, cap);
+}
 long long sam_launch_count(void) { return samhost::launch_count(); }
 void sam_profile_enable(int on) { samhost::profile_enable(on); }
 void sam_profile_reset(void) { samhost::profile_reset(); }

@@ -287,9 +287,9 @@ struct Sched {
   int full_items;   // whole tiles of this pair: tile = cluster_id + i * num_clusters
   int n_items;      // full_items + (0 | 1 half item)
   int half_tile, half_h;
-  __device__ __forceinline__ bool is_half(int it) const { return it >= full_items; }
+  __host__ __device__ __forceinline__ bool is_half(int it) const { return it >= full_items; }
 };
-__device__ __forceinline__ Sched make_sched(int num_tiles, int num_clusters, int cluster_id, int nsplit) {
+__host__ __device__ __forceinline__ Sched make_sched(int num_tiles, int num_clusters, int cluster_id, int nsplit) {
   int lim = num_tiles, n_half = 0;
   if (nsplit) {
     const int full = (num_tiles / num_clusters) * num_clusters, rem = num_tiles - full;
@@ -842,6 +842,21 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 }
 
 }  // namespace
+
+// Work items of one CTA pair as the kernel enumerates them (host copy of the same function, for the CPU tests):
+// out[4 * i + {0, 1, 2, 3}] = tile, is_half, column slice h, 0.  Returns the number of items, or -1 if they exceed `cap`.
+int samk_gemm2_schedule(int num_tiles, int num_clusters, int cluster_id, int nsplit, int* out, int cap) {
+  const Sched sc = make_sched(num_tiles, num_clusters, cluster_id, nsplit);
+  if (sc.n_items > cap) return -1;
+  for (int it = 0; it < sc.n_items; ++it) {
+    const bool hf = sc.is_half(it);
+    out[4 * it + 0] = hf ? sc.half_tile : cluster_id + it * num_clusters;
+    out[4 * it + 1] = hf ? 1 : 0;
+    out[4 * it + 2] = hf ? sc.half_h : 0;
+    out[4 * it + 3] = 0;
+  }
+  return sc.n_items;
+}
 
 // -1: policy (launches of fewer than 8 whole rounds), 0: whole tiles only, 1: whenever the last round allows
 static int g_tile_split_mode = -1;

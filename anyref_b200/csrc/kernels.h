@@ -51,6 +51,7 @@ int samk_gemm2(const void* A, int lda, const void* W, int ldw, int M, int N, int
 
 // Half-tile items in the last round of samk_gemm2 (gemm2.cu, Sched): -1 policy, 0 off, 1 whenever possible.
 void samk_gemm2_set_tile_split(int mode);
+int samk_gemm2_schedule(int num_tiles, int num_clusters, int cluster_id, int nsplit, int* out, int cap);
 
 // UMMA layout probe (test-only kernel, see probe.cu).
 struct UmmaProbe {

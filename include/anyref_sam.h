@@ -326,6 +326,12 @@ int sam_resize_u8(const unsigned char* in, int H, int W, int C, unsigned char* t
  * mode: -1 = policy (only launches of fewer than 8 whole rounds, i.e. small batches), 0 = never, 1 = whenever possible.
  */
 void sam_gemm_set_tile_split(int mode);
+/*
+ * Test-only, host code (no GPU needed): the work items CTA pair `pair` of `num_pairs` walks for a launch of `num_tiles`
+ * output tiles, from the same function the kernel calls.  out[4 i + 0] = tile, [4 i + 1] = 1 for a 256 x 128 half item,
+ * [4 i + 2] = its column slice (0 | 1).  Returns the number of items, -1 if more than `cap`.
+ */
+int sam_gemm_schedule(int num_tiles, int num_pairs, int pair, int split, int* out, int cap);
 
 /*
  * Launch accounting and per-kernel-class timing (used by bench.py for `gpu_launches` and the roofline leg).

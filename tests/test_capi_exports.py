@@ -130,3 +130,50 @@ def test_integration_md_struct_stub_matches_the_binding():
     block = block[:block.index("]") + 1]
     doc_fields = re.findall(r'\("(\w+)",', block)
     assert doc_fields == [f[0] for f in _lib.SamEncoderShape._fields_]
+
+
+def test_gemm_schedule_covers_every_tile_exactly_once(lib):
+    """The persistent 2-CTA GEMM's work list (csrc/gemm2.cu, Sched; host copy of the function the kernel calls): whole
+    256 x 256 tiles round-robin over the CTA pairs and, when the last round would leave at least half of the pairs idle,
+    that round as 256 x 128 half items -- one per pair, always a pair's LAST item (the residual producers' cross-warp
+    statistics hand-off relies on that).  Every tile must be covered exactly once: as a whole, or as both of its halves."""
+    from anyref_b200 import _lib
+
+    L = _lib.load()
+    cap = 1024
+    buf = (ctypes.c_int * (4 * cap))()
+
+    def items(tiles, pairs, pair, split):
+        n = L.sam_gemm_schedule(tiles, pairs, pair, split, ctypes.cast(buf, ctypes.c_void_p), cap)
+        assert n >= 0
+        return [(buf[4 * i], buf[4 * i + 1], buf[4 * i + 2]) for i in range(n)]
+
+    # ViT-H linears at 1 / 2 / 16 images on 74 pairs, a smaller device, tiny launches, and a sweep
+    cases = [(t, p) for p in (74, 72, 37, 8) for t in (1, 2, 5, 6, 16, 37, 38, 80, 160, 240, 320, 325, 1280, 3840, 5120)]
+    cases += [(t, 74) for t in range(1, 400)]
+    for tiles, pairs in cases:
+        for split in (0, 1):
+            # the host launches min(tiles, pairs) pairs, or 2 * tiles when all of them fit as half items
+            grid = min(tiles, pairs)
+            if split and 2 * tiles <= pairs:
+                grid = 2 * tiles
+            whole, halves, loads = {}, {}, []
+            for pair in range(grid):
+                its = items(tiles, grid, pair, split)
+                loads.append(sum(0.5 if hf else 1.0 for _, hf, _ in its))
+                for i, (t, hf, h) in enumerate(its):
+                    assert 0 <= t < tiles
+                    if hf:
+                        assert split and i == len(its) - 1 and h in (0, 1)
+                        halves.setdefault(t, []).append(h)
+                    else:
+                        assert t == pair + i * grid
+                        whole[t] = whole.get(t, 0) + 1
+            assert all(v == 1 for v in whole.values()) and all(sorted(v) == [0, 1] for v in halves.values())
+            assert not (set(whole) & set(halves)) and len(whole) + len(halves) == tiles
+            rem = tiles % grid
+            if split and 0 < rem <= grid // 2 or (split and grid == 2 * tiles):
+                assert len(halves) == (tiles if grid == 2 * tiles else rem)
+                assert max(loads) == tiles // grid + 0.5        # the last round costs half a tile period
+            else:
+                assert not halves and max(loads) == -(-tiles // grid)
