@@ -858,7 +858,7 @@ int samk_gemm2_schedule(int num_tiles, int num_clusters, int cluster_id, int nsp
   return sc.n_items;
 }
 
-// -1: policy (launches of fewer than 8 whole rounds), 0: whole tiles only, 1: whenever the last round allows
+// -1: policy (launches of fewer than 8 whole rounds or at most 16384 rows), 0: whole tiles only, 1: whenever the last round allows
 static int g_tile_split_mode = -1;
 void samk_gemm2_set_tile_split(int mode) { g_tile_split_mode = mode < 0 ? -1 : (mode ? 1 : 0); }
 
@@ -981,13 +981,14 @@ int samk_gemm2(const void* A, int lda, const void* W, int ldw, int M, int N, int
     if (getenv("SAM_GEMM_DEBUG")) fprintf(stderr, "[anyref_sam] gemm2: max co-resident CTA pairs = %d\n", n);
   }
   {
-    // Half items in the last round (Sched) pay off while the launch is short: measured on the whole path at B = 1
-    // (1 - 4 rounds per linear) 7.96 -> 7.67 ms per image; at B = 16 (17 - 69 rounds) the step is energy-bound under the
+    // Half items in the last round (Sched) pay off for small batches: measured on the whole path (forced on / off) at
+    // 1 / 2 / 4 images 7.96 -> 7.67, 13.43 -> 13.09 and 24.31 -> 24.07 ms; at 16 images the step is energy-bound under the
     // power cap, the idle pairs of the last round give their power to the busy ones, and halves -- more operand bytes
-    // per FLOP -- measure equal or slower (92.9 vs 92.6 ms).  Hence: only launches of fewer than 8 whole rounds.
+    // per FLOP -- measure equal or slower (92.9 vs 92.6 ms).  Hence: launches of fewer than 8 whole rounds, or of at
+    // most 16384 rows (4 images).
     static const char* ns = getenv("SAM_GEMM_NSPLIT");   // "0": never, "1": whenever the last round allows (A/B measurements)
     const int mode = g_tile_split_mode >= 0 ? g_tile_split_mode : (ns ? (ns[0] == '1') : -1);
-    const bool few_rounds = clusters < 8 * max_clusters;
+    const bool few_rounds = clusters < 8 * max_clusters || M <= 16384;
     p.nsplit = (mode >= 0 ? mode != 0 : few_rounds) && !ep.diag_mt;
   }
   if (clusters > max_clusters) clusters = max_clusters;

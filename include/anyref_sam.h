@@ -323,7 +323,8 @@ int sam_resize_u8(const unsigned char* in, int H, int W, int C, unsigned char* t
  * When the last round of 256 x 256 output tiles would leave at least half of the CTA pairs idle, its tiles are cut into
  * 256 x 128 halves, one per pair.  Results are bit-identical either way except the LayerNorm slice statistics of the
  * residual producers, which combine two 64-column halves (same value to fp32 rounding).
- * mode: -1 = policy (only launches of fewer than 8 whole rounds, i.e. small batches), 0 = never, 1 = whenever possible.
+ * mode: -1 = policy (launches of fewer than 8 whole rounds or of at most 16384 rows, i.e. batches of up to 4 images),
+ *       0 = never, 1 = whenever possible.
  */
 void sam_gemm_set_tile_split(int mode);
 /*
